@@ -1,0 +1,1106 @@
+// libaccelrl_b200.so — C ABI (include/accelrl_b200.h) over the sm_100a kernels.
+// Single translation unit: kernels live in the .cuh files included below.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <map>
+#include <algorithm>
+
+#include "../../include/accelrl_b200.h"
+#include "common.cuh"
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+#include "comm.cuh"
+
+using namespace arl;
+
+namespace {
+
+std::string g_create_error;
+
+#define ARL_CHECK(ctx, call)                                                                    \
+  do {                                                                                          \
+    cudaError_t _e = (call);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(_e) + " @" + __FILE__ + ":" + \
+                   std::to_string(__LINE__);                                                    \
+      return 1;                                                                                 \
+    }                                                                                           \
+  } while (0)
+
+#define ARL_FAIL(ctx, msg)  \
+  do {                      \
+    (ctx)->err = (msg);     \
+    return 2;               \
+  } while (0)
+
+struct ConvLayer {
+  int Cin, Hin, Win, Cout, k, s, p, Ho, Wo;
+  int K;                 // Cin*k*k
+  long off_W, off_b;     // flat param offsets
+  __nv_bfloat16* wpack;  // [Cout][K] forward operand
+  // dgrad classes (layers >= 1)
+  struct DClass {
+    int ry, rx, qy0, qx0, Qh, Qw, Ty, Tx, K;
+    __nv_bfloat16* wpack;  // [Cin][K]
+  };
+  std::vector<DClass> dclasses;
+  __nv_bfloat16* act;    // [max_rows*Ho*Wo][Cout]
+  __nv_bfloat16* dact;
+};
+
+struct TrainPlan {
+  int n = 0;
+  std::vector<int> conv_splits, conv_rps, conv_groups, conv_rpg;
+  int head_groups = 0, head_rpg = 0;
+  GradJob* jobs_dev = nullptr;
+  int n_jobs = 0;
+};
+
+}  // namespace
+
+struct arl_ctx {
+  std::string err;
+  arl_net_cfg cfg{};
+  std::vector<ConvLayer> conv;
+  int Kfc = 0, H = 0, A = 0, HWlast = 0, Clast = 0;
+  long off_Wfc = 0, off_bfc = 0, off_Wpi = 0, off_bpi = 0, off_Wv = 0, off_bv = 0, n_params = 0;
+  std::vector<long> lay_off, lay_size;
+  __nv_bfloat16* wfc_pack = nullptr;  // [H][Kfc]
+  PackJob* pack_jobs_dev = nullptr;
+  int n_pack_jobs = 0;
+  // bound vectors
+  float *params = nullptr, *grad = nullptr, *m = nullptr, *v = nullptr;
+  // workspaces
+  float* fc_partial = nullptr;
+  long fc_partial_cap = 0;  // floats
+  __nv_bfloat16 *h = nullptr, *dh = nullptr;
+  float* dlogit = nullptr;
+  std::vector<float*> wgrad_partial;  // per conv layer
+  std::vector<long> wgrad_partial_cap;
+  std::vector<float*> bias_partial;
+  float* head_partial = nullptr;   // [G][H][A+2]
+  float* head_b_partial = nullptr; // [G][A+1]
+  float* loss_partial = nullptr;   // [kLossBlocks][4]
+  double* sumsq_partial = nullptr;
+  float* hyper = nullptr;          // [0] lr_mult
+  int* step = nullptr;             // Adam t
+  int* log_slot = nullptr;
+  float *log_norm = nullptr, *log_loss = nullptr;
+  int log_cap = 4096;
+  int* mb_counter = nullptr;       // minibatch index for graph-replayed training
+  float* valid_count = nullptr;
+  float* dbg = nullptr;
+  std::map<int, TrainPlan> plans;
+  // training inputs
+  const uint8_t* t_obs = nullptr; const uint8_t* t_act = nullptr; const float* t_adv = nullptr;
+  const float* t_ret = nullptr; const float* t_oldv = nullptr; const float* t_oldp = nullptr;
+  const int8_t* t_valids = nullptr; long t_rows = 0;
+  arl_opt_cfg opt{};
+  bool opt_set = false;
+  // sampler
+  arl_sampler_cfg sc{};
+  bool sampler_set = false;
+  EnvState est{};
+  TrajOut tout{};
+  FrameCmd* cmd = nullptr;
+  int* rows_tab = nullptr;   // [T][B] row indices e*T+s
+  cudaGraphExec_t rollout_graph = nullptr;
+  // training graph cache
+  cudaGraphExec_t train_graph = nullptr;
+  const int* train_graph_idx = nullptr;
+  int train_graph_mb = 0;
+  long launches = 0;
+  long graph_rollout_nodes = 0, graph_train_nodes = 0;
+  float lr_mult_host = 1.f;
+  CommState comm;
+};
+
+namespace {
+
+constexpr int kLossBlocks = 64;
+
+template <class T>
+int dev_alloc(arl_ctx* c, T** p, size_t count) {
+  ARL_CHECK(c, cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)));
+  ARL_CHECK(c, cudaMemset(*p, 0, count * sizeof(T)));
+  return 0;
+}
+
+int roundup(int x, int m) { return (x + m - 1) / m * m; }
+
+// ---------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------
+template <class ALoad, bool BNM, int BN>
+int launch_rowgemm(arl_ctx* c, ALoad a, WeightSrc b, RowEpi e, int M, int Ntot, int num_kb, int kbps, int splits,
+                   cudaStream_t st) {
+  using Cfg = RowGemmCfg<BN>;
+  static bool attr = false;
+  if (!attr) {
+    ARL_CHECK(c, cudaFuncSetAttribute(rowgemm_kernel<ALoad, BNM, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      Cfg::SMEM));
+    attr = true;
+  }
+  dim3 grid((M + 127) / 128, Ntot / BN, splits);
+  rowgemm_kernel<ALoad, BNM, BN><<<grid, kGemmThreads, Cfg::SMEM, st>>>(a, b, e, num_kb, kbps);
+  c->launches++;
+  ARL_CHECK(c, cudaGetLastError());
+  return 0;
+}
+
+template <class ALoad, bool BNM>
+int launch_rowgemm_bn(arl_ctx* c, int BN, ALoad a, WeightSrc b, RowEpi e, int M, int Ntot, int num_kb, int kbps,
+                      int splits, cudaStream_t st) {
+  switch (BN) {
+    case 16: return launch_rowgemm<ALoad, BNM, 16>(c, a, b, e, M, Ntot, num_kb, kbps, splits, st);
+    case 32: return launch_rowgemm<ALoad, BNM, 32>(c, a, b, e, M, Ntot, num_kb, kbps, splits, st);
+    case 64: return launch_rowgemm<ALoad, BNM, 64>(c, a, b, e, M, Ntot, num_kb, kbps, splits, st);
+    case 128: return launch_rowgemm<ALoad, BNM, 128>(c, a, b, e, M, Ntot, num_kb, kbps, splits, st);
+  }
+  ARL_FAIL(c, "unsupported tile width BN=" + std::to_string(BN));
+}
+
+template <class ALoad, int MT, int BN>
+int launch_wgrad(arl_ctx* c, ALoad a, const __nv_bfloat16* dy, int ld_dy, int nrows, int rps, int splits, int atoms,
+                 int ntiles, WgradEpi e, cudaStream_t st) {
+  using Cfg = WgradCfg<MT, BN>;
+  static bool attr = false;
+  if (!attr) {
+    ARL_CHECK(c, cudaFuncSetAttribute(wgrad_kernel<ALoad, MT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      Cfg::SMEM));
+    attr = true;
+  }
+  dim3 grid((atoms + MT * 2 - 1) / (MT * 2), ntiles, splits);
+  wgrad_kernel<ALoad, MT, BN><<<grid, kGemmThreads, Cfg::SMEM, st>>>(a, dy, ld_dy, nrows, rps, atoms, e);
+  c->launches++;
+  ARL_CHECK(c, cudaGetLastError());
+  return 0;
+}
+
+template <class ALoad>
+int launch_wgrad_conv(arl_ctx* c, ALoad a, const __nv_bfloat16* dy, int Cout, int nrows, int rps, int splits,
+                      int atoms, WgradEpi e, cudaStream_t st) {
+  int mt_need = (atoms + 1) / 2;
+#define ARL_WG(MT, BN) return launch_wgrad<ALoad, MT, BN>(c, a, dy, Cout, nrows, rps, splits, atoms, 1, e, st)
+  if (Cout == 16) {
+    if (mt_need <= 2) ARL_WG(2, 16);
+    if (mt_need <= 4) ARL_WG(4, 16);
+    ARL_WG(5, 16);
+  } else if (Cout == 32) {
+    if (mt_need <= 2) ARL_WG(2, 32);
+    if (mt_need <= 4) ARL_WG(4, 32);
+    ARL_WG(5, 32);
+  } else if (Cout == 64) {
+    if (mt_need <= 2) ARL_WG(2, 64);
+    if (mt_need <= 4) ARL_WG(4, 64);
+    ARL_WG(5, 64);
+  }
+#undef ARL_WG
+  ARL_FAIL(c, "unsupported conv filter count " + std::to_string(Cout));
+}
+
+// ---------------------------------------------------------------------------
+// network planning
+// ---------------------------------------------------------------------------
+int plan_net(arl_ctx* c) {
+  const arl_net_cfg& f = c->cfg;
+  if (f.n_conv < 1 || f.n_conv > ARL_MAX_CONV) ARL_FAIL(c, "n_conv out of range");
+  if (f.n_actions < 1 || f.n_actions > kMaxActions) ARL_FAIL(c, "n_actions must be in [1,18]");
+  if (f.in_h != kObsH || f.in_w != kObsW) {
+    // the conv path itself is size-generic; only the frame kernel is fixed at 104x80
+  }
+  int C = f.in_c, Hh = f.in_h, Ww = f.in_w;
+  long off = 0;
+  for (int l = 0; l < f.n_conv; ++l) {
+    ConvLayer L{};
+    L.Cin = C; L.Hin = Hh; L.Win = Ww;
+    L.Cout = f.conv_filters[l]; L.k = f.conv_sizes[l]; L.s = f.conv_strides[l]; L.p = f.conv_pads[l];
+    L.Ho = (Hh + 2 * L.p - L.k) / L.s + 1;
+    L.Wo = (Ww + 2 * L.p - L.k) / L.s + 1;
+    L.K = L.Cin * L.k * L.k;
+    if (L.K % 64) ARL_FAIL(c, "conv layer " + std::to_string(l) + ": Cin*k*k must be a multiple of 64");
+    if (L.Cout != 16 && L.Cout != 32 && L.Cout != 64)
+      ARL_FAIL(c, "conv layer " + std::to_string(l) + ": filters must be 16, 32 or 64");
+    if (l == 0) {
+      if (L.k != 8 || L.p != 0 || (L.s % 4) || (Ww % 4))
+        ARL_FAIL(c, "first conv layer must be 8x8, pad 0, stride multiple of 4 (uint8 gather path)");
+    } else {
+      if (L.Cin % 8) ARL_FAIL(c, "conv input channels must be a multiple of 8");
+    }
+    L.off_W = off; off += (long)L.Cout * L.Cin * L.k * L.k;
+    L.off_b = off; off += L.Cout;
+    c->lay_off.push_back(L.off_W); c->lay_size.push_back((long)L.Cout * L.Cin * L.k * L.k);
+    c->lay_off.push_back(L.off_b); c->lay_size.push_back(L.Cout);
+    if (l >= 1) {
+      int Ty = (L.k + L.s - 1) / L.s;
+      for (int ry = 0; ry < L.s; ++ry)
+        for (int rx = 0; rx < L.s; ++rx) {
+          ConvLayer::DClass d{};
+          d.ry = ry; d.rx = rx; d.Ty = Ty; d.Tx = Ty;
+          // u = i + p = s*q + r,  i in [0, Hin)
+          auto qrange = [&](int r, int n, int& q0, int& cnt) {
+            int lo = L.p - r;                       // s*q >= lo
+            q0 = lo <= 0 ? 0 : (lo + L.s - 1) / L.s;
+            int hi = n - 1 + L.p - r;               // s*q <= hi
+            int q1 = hi < 0 ? -1 : hi / L.s;
+            cnt = q1 - q0 + 1;
+          };
+          qrange(ry, L.Hin, d.qy0, d.Qh);
+          qrange(rx, L.Win, d.qx0, d.Qw);
+          d.K = d.Ty * d.Tx * L.Cout;
+          if (d.K % 64) ARL_FAIL(c, "conv dgrad K not a multiple of 64");
+          if (d.Qh > 0 && d.Qw > 0) L.dclasses.push_back(d);
+        }
+    }
+    c->conv.push_back(L);
+    C = L.Cout; Hh = L.Ho; Ww = L.Wo;
+  }
+  c->Clast = C; c->HWlast = Hh * Ww; c->Kfc = C * Hh * Ww;
+  c->H = f.hidden; c->A = f.n_actions;
+  if (c->Kfc % 64) ARL_FAIL(c, "flattened conv output must be a multiple of 64");
+  if (c->H % 256) ARL_FAIL(c, "hidden size must be a multiple of 256");
+  if (c->H > 512) ARL_FAIL(c, "hidden size must be <= 512");
+  c->off_Wfc = off; off += (long)c->Kfc * c->H;
+  c->off_bfc = off; off += c->H;
+  c->off_Wpi = off; off += (long)c->H * c->A;
+  c->off_bpi = off; off += c->A;
+  c->off_Wv = off; off += c->H;
+  c->off_bv = off; off += 1;
+  c->n_params = off;
+  long tail_off[6] = {c->off_Wfc, c->off_bfc, c->off_Wpi, c->off_bpi, c->off_Wv, c->off_bv};
+  long tail_sz[6] = {(long)c->Kfc * c->H, c->H, (long)c->H * c->A, c->A, c->H, 1};
+  for (int i = 0; i < 6; ++i) { c->lay_off.push_back(tail_off[i]); c->lay_size.push_back(tail_sz[i]); }
+  return 0;
+}
+
+int alloc_net(arl_ctx* c) {
+  const int R = c->cfg.max_rows;
+  std::vector<PackJob> pj;
+  for (size_t l = 0; l < c->conv.size(); ++l) {
+    ConvLayer& L = c->conv[l];
+    size_t act_elems = (size_t)R * L.Ho * L.Wo * L.Cout + 8 * 1024;
+    if (dev_alloc(c, &L.act, act_elems)) return 1;
+    if (dev_alloc(c, &L.dact, act_elems)) return 1;
+    if (dev_alloc(c, &L.wpack, (size_t)L.Cout * L.K)) return 1;
+    PackJob j{};
+    j.dst = L.wpack; j.src_off = L.off_W; j.kind = (l == 0) ? PK_CONV_CHW : PK_CONV_NHWC;
+    j.rows = L.Cout; j.cols = L.K; j.Cout = L.Cout; j.C = L.Cin; j.kh = L.k; j.kw = L.k;
+    pj.push_back(j);
+    for (auto& d : L.dclasses) {
+      if (dev_alloc(c, &d.wpack, (size_t)L.Cin * d.K)) return 1;
+      PackJob q{};
+      q.dst = d.wpack; q.src_off = L.off_W; q.kind = PK_CONV_DGRAD;
+      q.rows = L.Cin; q.cols = d.K; q.Cout = L.Cout; q.C = L.Cin; q.kh = L.k; q.kw = L.k;
+      q.s = L.s; q.ry = d.ry; q.rx = d.rx; q.Tx = d.Tx;
+      pj.push_back(q);
+    }
+    // wgrad partials: splits <= 160
+    long cap = (long)160 * L.K * L.Cout;
+    float* wp = nullptr;
+    if (dev_alloc(c, &wp, (size_t)cap)) return 1;
+    c->wgrad_partial.push_back(wp);
+    c->wgrad_partial_cap.push_back(cap);
+    float* bp = nullptr;
+    if (dev_alloc(c, &bp, (size_t)160 * L.Cout)) return 1;
+    c->bias_partial.push_back(bp);
+  }
+  if (dev_alloc(c, &c->wfc_pack, (size_t)c->H * c->Kfc)) return 1;
+  {
+    PackJob j{};
+    j.dst = c->wfc_pack; j.src_off = c->off_Wfc; j.kind = PK_FC; j.rows = c->H; j.cols = c->Kfc;
+    j.C = c->Clast; j.HW = c->HWlast; j.ldsrc = c->H;
+    pj.push_back(j);
+  }
+  c->n_pack_jobs = (int)pj.size();
+  if (dev_alloc(c, &c->pack_jobs_dev, pj.size())) return 1;
+  ARL_CHECK(c, cudaMemcpy(c->pack_jobs_dev, pj.data(), pj.size() * sizeof(PackJob), cudaMemcpyHostToDevice));
+  c->fc_partial_cap = (long)std::max(R, 4864) * c->H + 1024;
+  if (dev_alloc(c, &c->fc_partial, (size_t)c->fc_partial_cap)) return 1;
+  if (dev_alloc(c, &c->h, (size_t)R * c->H)) return 1;
+  if (dev_alloc(c, &c->dh, (size_t)R * c->H)) return 1;
+  if (dev_alloc(c, &c->dlogit, (size_t)R * (c->A + 1))) return 1;
+  if (dev_alloc(c, &c->head_partial, (size_t)64 * c->H * (c->A + 2))) return 1;
+  if (dev_alloc(c, &c->head_b_partial, (size_t)64 * (c->A + 1))) return 1;
+  if (dev_alloc(c, &c->loss_partial, (size_t)kLossBlocks * 4)) return 1;
+  if (dev_alloc(c, &c->sumsq_partial, (size_t)kSumsqBlocks)) return 1;
+  if (dev_alloc(c, &c->hyper, 8)) return 1;
+  float one = 1.f;
+  ARL_CHECK(c, cudaMemcpy(c->hyper, &one, sizeof(float), cudaMemcpyHostToDevice));
+  if (dev_alloc(c, &c->step, 1)) return 1;
+  if (dev_alloc(c, &c->log_slot, 1)) return 1;
+  if (dev_alloc(c, &c->log_norm, (size_t)c->log_cap)) return 1;
+  if (dev_alloc(c, &c->log_loss, (size_t)c->log_cap)) return 1;
+  if (dev_alloc(c, &c->mb_counter, 1)) return 1;
+  if (dev_alloc(c, &c->valid_count, 1)) return 1;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------
+RowEpi make_epi(int mode) {
+  RowEpi e{};
+  e.mode = mode; e.scale = 1.f;
+  return e;
+}
+
+int fc_splits(arl_ctx* c, int n, int& kbps) {
+  int kb = c->Kfc / 64;
+  int tiles = ((n + 127) / 128) * (c->H / 64);
+  int S = std::max(1, std::min(kb, (296 + tiles / 2) / tiles));
+  kbps = (kb + S - 1) / S;
+  S = (kb + kbps - 1) / kbps;
+  return S;
+}
+
+// conv stack + FC partials for n observations (idx/idx_off optional gather)
+int forward_trunk(arl_ctx* c, const uint8_t* obs, const int* idx, const int* idx_off, int n, int* fc_S,
+                  cudaStream_t st) {
+  if (n > c->cfg.max_rows) ARL_FAIL(c, "batch larger than max_rows");
+  if (!c->params) ARL_FAIL(c, "parameters not bound");
+  for (size_t l = 0; l < c->conv.size(); ++l) {
+    ConvLayer& L = c->conv[l];
+    int rows = n * L.Ho * L.Wo;
+    RowEpi e = make_epi(EPI_BIAS_RELU_BF16);
+    e.bias = c->params + L.off_b; e.out = L.act; e.ldo = L.Cout; e.M = rows;
+    WeightSrc w{L.wpack, (long)L.K, 0};
+    if (l == 0) {
+      e.scale = 1.f / c->cfg.pixel_scale;
+      ConvLoaderU8<128> a{};
+      a.g.src = obs; a.g.idx = idx; a.g.idx_off = idx_off; a.g.Qh = L.Ho; a.g.Qw = L.Wo; a.g.Hs = L.Hin; a.g.Ws = L.Win;
+      a.g.C = L.Cin; a.g.kh = L.k; a.g.stride = L.s; a.g.nrows = rows;
+      if (launch_rowgemm_bn<ConvLoaderU8<128>, false>(c, L.Cout, a, w, e, rows, L.Cout, L.K / 64, L.K / 64, 1, st))
+        return 1;
+    } else {
+      ConvLoader<128> a{};
+      a.g.src = c->conv[l - 1].act; a.g.Qh = L.Ho; a.g.Qw = L.Wo; a.g.Hs = L.Hin; a.g.Ws = L.Win; a.g.C = L.Cin;
+      a.g.sy = L.s; a.g.y0 = -L.p; a.g.dty = 1; a.g.sx = L.s; a.g.x0 = -L.p; a.g.dtx = 1; a.g.Tx = L.k;
+      a.g.nrows = rows;
+      if (launch_rowgemm_bn<ConvLoader<128>, false>(c, L.Cout, a, w, e, rows, L.Cout, L.K / 64, L.K / 64, 1, st))
+        return 1;
+    }
+  }
+  int kbps = 0;
+  int S = fc_splits(c, n, kbps);
+  if ((long)S * n * c->H > c->fc_partial_cap) ARL_FAIL(c, "fc partial workspace too small");
+  RowEpi e = make_epi(EPI_PARTIAL_F32);
+  e.partial = c->fc_partial; e.ldo = c->H; e.M = n;
+  DenseLoader<128> a{};
+  a.src = c->conv.back().act; a.ld = c->Kfc; a.nrows = n;
+  WeightSrc w{c->wfc_pack, (long)c->Kfc, 0};
+  if (launch_rowgemm<DenseLoader<128>, false, 64>(c, a, w, e, n, c->H, c->Kfc / 64, kbps, S, st)) return 1;
+  *fc_S = S;
+  return 0;
+}
+
+size_t head_smem(arl_ctx* c) { return (size_t)(c->H * c->A + 2 * c->H + kMaxActions + 2) * sizeof(float); }
+
+HeadParams head_base(arl_ctx* c, int n, int S) {
+  HeadParams p{};
+  p.partial = c->fc_partial; p.splits = S; p.M = n; p.H = c->H; p.A = c->A;
+  p.fc_bias = c->params + c->off_bfc; p.w_pi = c->params + c->off_Wpi; p.b_pi = c->params + c->off_bpi;
+  p.w_v = c->params + c->off_Wv; p.b_v = c->params + c->off_bv;
+  p.hyper = c->hyper;
+  return p;
+}
+
+int policy_forward(arl_ctx* c, const uint8_t* obs, const int* idx, int n, const int* out_rows, float* prob,
+                   float* value, const double* uniforms, uint8_t* actions, cudaStream_t st) {
+  int S = 0;
+  if (forward_trunk(c, obs, idx, nullptr, n, &S, st)) return 1;
+  HeadParams p = head_base(c, n, S);
+  p.out_rows = out_rows; p.prob = prob; p.value = value; p.uniforms = uniforms; p.actions = uniforms ? actions : nullptr;
+  int blocks = std::min((n + 7) / 8, 148 * 2);
+  head_kernel<0><<<blocks, 256, head_smem(c), st>>>(p);
+  c->launches++;
+  ARL_CHECK(c, cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// training plan (depends on the minibatch size)
+// ---------------------------------------------------------------------------
+int get_plan(arl_ctx* c, int n, TrainPlan** out) {
+  auto it = c->plans.find(n);
+  if (it != c->plans.end()) { *out = &it->second; return 0; }
+  TrainPlan P;
+  P.n = n;
+  std::vector<GradJob> jobs;
+  for (size_t l = 0; l < c->conv.size(); ++l) {
+    ConvLayer& L = c->conv[l];
+    int rows = n * L.Ho * L.Wo;
+    int rps = roundup((rows + 147) / 148, 64);
+    int splits = (rows + rps - 1) / rps;
+    if ((long)splits * L.K * L.Cout > c->wgrad_partial_cap[l]) ARL_FAIL(c, "wgrad partial workspace too small");
+    P.conv_splits.push_back(splits); P.conv_rps.push_back(rps);
+    int rpg = std::max(64, (rows + 147) / 148);
+    int groups = (rows + rpg - 1) / rpg;
+    P.conv_groups.push_back(groups); P.conv_rpg.push_back(rpg);
+    GradJob w{};
+    w.src = c->wgrad_partial[l]; w.S = splits; w.sstride = (long)L.K * L.Cout; w.rows = L.K; w.cols = L.Cout;
+    w.ld = L.Cout; w.map = (l == 0) ? GM_CONV_CHW : GM_CONV_NHWC; w.scale = (l == 0) ? 1.f / c->cfg.pixel_scale : 1.f;
+    w.dst_off = L.off_W; w.C = L.Cin; w.kh = L.k; w.kw = L.k;
+    jobs.push_back(w);
+    GradJob b{};
+    b.src = c->bias_partial[l]; b.S = groups; b.sstride = L.Cout; b.rows = 1; b.cols = L.Cout; b.ld = L.Cout;
+    b.map = GM_LINEAR; b.scale = 1.f; b.dst_off = L.off_b;
+    jobs.push_back(b);
+  }
+  P.head_rpg = std::max(32, (n + 63) / 64);
+  P.head_groups = (n + P.head_rpg - 1) / P.head_rpg;
+  {
+    GradJob hj{};
+    hj.src = c->head_partial; hj.S = P.head_groups; hj.sstride = (long)c->H * (c->A + 2); hj.rows = c->H;
+    hj.cols = c->A + 2; hj.ld = c->A + 2; hj.map = GM_HEAD; hj.scale = 1.f; hj.dst_off = c->off_Wpi;
+    hj.dst_off2 = c->off_Wv; hj.dst_off3 = c->off_bfc; hj.A = c->A;
+    jobs.push_back(hj);
+    GradJob bp{};
+    bp.src = c->head_b_partial; bp.S = P.head_groups; bp.sstride = c->A + 1; bp.rows = 1; bp.cols = c->A;
+    bp.ld = c->A + 1; bp.map = GM_LINEAR; bp.scale = 1.f; bp.dst_off = c->off_bpi;
+    jobs.push_back(bp);
+    GradJob bv = bp;
+    bv.src = c->head_b_partial + c->A; bv.cols = 1; bv.dst_off = c->off_bv;
+    jobs.push_back(bv);
+  }
+  P.n_jobs = (int)jobs.size();
+  ARL_CHECK(c, cudaMalloc(reinterpret_cast<void**>(&P.jobs_dev), jobs.size() * sizeof(GradJob)));
+  ARL_CHECK(c, cudaMemcpy(P.jobs_dev, jobs.data(), jobs.size() * sizeof(GradJob), cudaMemcpyHostToDevice));
+  auto res = c->plans.emplace(n, P);
+  *out = &res.first->second;
+  return 0;
+}
+
+// forward + loss + backward for one minibatch -> flat grad
+int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaStream_t st) {
+  if (!c->opt_set) ARL_FAIL(c, "optimizer not configured");
+  if (!c->t_obs) ARL_FAIL(c, "training inputs not bound");
+  if (!c->grad) ARL_FAIL(c, "gradient vector not bound");
+  TrainPlan* P = nullptr;
+  if (get_plan(c, n, &P)) return 1;
+  int S = 0;
+  if (forward_trunk(c, c->t_obs, idx, idx_off, n, &S, st)) return 1;
+  // ---- head: losses + dlogits + dh ----
+  HeadParams p = head_base(c, n, S);
+  p.idx = idx; p.idx_off = idx_off; p.act_in = c->t_act; p.adv = c->t_adv; p.ret = c->t_ret; p.old_prob = c->t_oldp;
+  p.valids = c->t_valids; p.valid_count = c->valid_count;
+  p.algo = c->opt.algo; p.clip_param = c->opt.clip_param; p.v_coeff = c->opt.v_loss_coeff;
+  p.ent_coeff = c->opt.ent_loss_coeff; p.inv_count = 1.f / (float)n;
+  p.h_out = c->h; p.dh_out = c->dh; p.dlogit_out = c->dlogit; p.loss_partial = c->loss_partial;
+  head_kernel<1><<<kLossBlocks, 256, head_smem(c), st>>>(p);
+  c->launches++;
+  ARL_CHECK(c, cudaGetLastError());
+  {
+    dim3 grid((c->H + 127) / 128, P->head_groups);
+    size_t sm = (size_t)P->head_rpg * (c->A + 1) * sizeof(float);
+    head_wgrad_kernel<<<grid, 128, sm, st>>>(c->h, c->dh, c->dlogit, n, c->H, c->A, P->head_rpg, c->head_partial,
+                                              c->head_b_partial);
+    c->launches++;
+    ARL_CHECK(c, cudaGetLastError());
+  }
+  ConvLayer& LL = c->conv.back();
+  // ---- FC wgrad: dW[Kfc][H] = a_last^T dh (direct, permuted rows) ----
+  {
+    DenseLoader<64> a{};
+    a.src = LL.act; a.ld = c->Kfc; a.nrows = n;
+    WgradEpi e{};
+    e.out = c->grad + c->off_Wfc; e.mode = 1; e.Kvalid = c->Kfc; e.Kp = c->Kfc; e.ldo = c->H; e.fc_C = c->Clast;
+    e.fc_HW = c->HWlast;
+    if (launch_wgrad<DenseLoader<64>, 1, 256>(c, a, c->dh, c->H, n, roundup(n, 64), 1, c->Kfc / 64, c->H / 256, e, st))
+      return 1;
+  }
+  // ---- FC dgrad: da_last[n][Kfc] = dh Wfc^T, masked by a_last > 0 ----
+  {
+    DenseLoader<128> a{};
+    a.src = c->dh; a.ld = c->H; a.nrows = n;
+    WeightSrc w{c->wfc_pack, (long)c->Kfc, c->H};
+    RowEpi e = make_epi(EPI_MASK_BF16);
+    e.out = LL.dact; e.act = LL.act; e.ldo = c->Kfc; e.M = n;
+    int BN = (c->Kfc % 128 == 0) ? 128 : 64;
+    if (launch_rowgemm_bn<DenseLoader<128>, true>(c, BN, a, w, e, n, c->Kfc, c->H / 64, c->H / 64, 1, st)) return 1;
+  }
+  // ---- conv layers, last to first ----
+  for (int l = (int)c->conv.size() - 1; l >= 0; --l) {
+    ConvLayer& L = c->conv[l];
+    int rows = n * L.Ho * L.Wo;
+    // bias grad partials
+    colsum_kernel<<<P->conv_groups[l], 256, 0, st>>>(L.dact, rows, L.Cout, P->conv_rpg[l], c->bias_partial[l]);
+    c->launches++;
+    ARL_CHECK(c, cudaGetLastError());
+    // wgrad partials
+    WgradEpi e{};
+    e.out = c->wgrad_partial[l]; e.mode = 0; e.Kvalid = L.K; e.Kp = L.K; e.ldo = L.Cout;
+    if (l == 0) {
+      ConvLoaderU8<64> a{};
+      a.g.src = c->t_obs; a.g.idx = idx; a.g.idx_off = idx_off; a.g.Qh = L.Ho; a.g.Qw = L.Wo; a.g.Hs = L.Hin;
+      a.g.Ws = L.Win; a.g.C = L.Cin; a.g.kh = L.k; a.g.stride = L.s; a.g.nrows = rows;
+      if (launch_wgrad_conv<ConvLoaderU8<64>>(c, a, L.dact, L.Cout, rows, P->conv_rps[l], P->conv_splits[l], L.K / 64, e,
+                                              st))
+        return 1;
+    } else {
+      ConvLoader<64> a{};
+      a.g.src = c->conv[l - 1].act; a.g.Qh = L.Ho; a.g.Qw = L.Wo; a.g.Hs = L.Hin; a.g.Ws = L.Win; a.g.C = L.Cin;
+      a.g.sy = L.s; a.g.y0 = -L.p; a.g.dty = 1; a.g.sx = L.s; a.g.x0 = -L.p; a.g.dtx = 1; a.g.Tx = L.k;
+      a.g.nrows = rows;
+      if (launch_wgrad_conv<ConvLoader<64>>(c, a, L.dact, L.Cout, rows, P->conv_rps[l], P->conv_splits[l], L.K / 64, e,
+                                            st))
+        return 1;
+      // dgrad into layer l-1's activation gradient (masked by its ReLU)
+      ConvLayer& Lp = c->conv[l - 1];
+      for (auto& d : L.dclasses) {
+        int qrows = n * d.Qh * d.Qw;
+        ConvLoader<128> g{};
+        g.g.src = L.dact; g.g.Qh = d.Qh; g.g.Qw = d.Qw; g.g.Hs = L.Ho; g.g.Ws = L.Wo; g.g.C = L.Cout;
+        g.g.sy = 1; g.g.y0 = d.qy0; g.g.dty = -1; g.g.sx = 1; g.g.x0 = d.qx0; g.g.dtx = -1; g.g.Tx = d.Tx;
+        g.g.nrows = qrows;
+        WeightSrc w{d.wpack, (long)d.K, 0};
+        RowEpi ep = make_epi(EPI_MASK_BF16);
+        ep.out = Lp.dact; ep.act = Lp.act; ep.ldo = L.Cin; ep.M = qrows;
+        ep.map_s = L.s; ep.map_y0 = L.s * d.qy0 + d.ry - L.p; ep.map_x0 = L.s * d.qx0 + d.rx - L.p;
+        ep.map_Qh = d.Qh; ep.map_Qw = d.Qw; ep.map_H = L.Hin; ep.map_W = L.Win;
+        if (L.s == 1 && ep.map_y0 == 0 && ep.map_x0 == 0 && d.Qh == L.Hin && d.Qw == L.Win) ep.map_s = 0;
+        if (launch_rowgemm_bn<ConvLoader<128>, false>(c, L.Cin, g, w, ep, qrows, L.Cin, d.K / 64, d.K / 64, 1, st))
+          return 1;
+      }
+    }
+  }
+  // ---- sum partials, scatter into the flat gradient ----
+  {
+    dim3 grid(64, P->n_jobs);
+    finalize_grads_kernel<<<grid, 256, 0, st>>>(P->jobs_dev, c->grad);
+    c->launches++;
+    ARL_CHECK(c, cudaGetLastError());
+  }
+  return 0;
+}
+
+int pack_weights(arl_ctx* c, cudaStream_t st) {
+  if (!c->params) ARL_FAIL(c, "parameters not bound");
+  dim3 grid(148, c->n_pack_jobs);
+  pack_weights_kernel<<<grid, 256, 0, st>>>(c->pack_jobs_dev, c->params);
+  c->launches++;
+  ARL_CHECK(c, cudaGetLastError());
+  return 0;
+}
+
+int clip_update(arl_ctx* c, float gscale, cudaStream_t st) {
+  if (!c->opt_set) ARL_FAIL(c, "optimizer not configured");
+  if (!c->m || !c->v) ARL_FAIL(c, "optimizer state not bound");
+  sumsq_kernel<<<kSumsqBlocks, 256, 0, st>>>(c->grad, c->n_params, gscale, c->sumsq_partial);
+  c->launches++;
+  UpdateParams u{};
+  u.param = c->params; u.grad = c->grad; u.m = c->m; u.v = c->v; u.n = c->n_params;
+  u.sumsq_partial = c->sumsq_partial; u.n_partial = kSumsqBlocks;
+  u.loss_partial = c->loss_partial; u.n_loss_blocks = kLossBlocks;
+  u.hyper = c->hyper; u.step = c->step; u.kind = c->opt.update;
+  u.lr = c->opt.learning_rate; u.beta1 = c->opt.beta1; u.beta2 = c->opt.beta2; u.eps = c->opt.epsilon;
+  u.rho = c->opt.rho; u.clip = c->opt.grad_norm_clip; u.gscale = gscale;
+  u.out_norm = c->log_norm; u.out_loss = c->log_loss; u.log_slot = c->log_slot; u.log_cap = c->log_cap;
+  update_kernel<<<148 * 4, 256, 0, st>>>(u);
+  c->launches++;
+  advance_counters_kernel<<<1, 1, 0, st>>>(c->step, c->log_slot, c->mb_counter);
+  c->launches++;
+  ARL_CHECK(c, cudaGetLastError());
+  return pack_weights(c, st);
+}
+
+// ---------------------------------------------------------------------------
+// sampler
+// ---------------------------------------------------------------------------
+SynthCfg synth_cfg(const arl_sampler_cfg& s) {
+  SynthCfg k{};
+  k.pool_frames = s.pool_frames; k.lives0 = s.lives0; k.life_base = s.life_base; k.life_mul = s.life_mul;
+  k.life_mod = s.life_mod; k.reward_mod = s.reward_mod; k.frame_stride = s.frame_stride;
+  return k;
+}
+
+int launch_frame(arl_ctx* c, const uint8_t* staging, int s_next, bool to_rollout, cudaStream_t st) {
+  const arl_sampler_cfg& s = c->sc;
+  long items = (long)s.n_envs * 520;
+  int blocks = (int)((items + 255) / 256);
+  frame_kernel<<<blocks, 256, 0, st>>>(s.frame_pool, staging, c->cmd, s.step_obs, to_rollout ? s.observations : nullptr,
+                                       s.horizon, s_next, s.n_envs, s.planes);
+  c->launches++;
+  ARL_CHECK(c, cudaGetLastError());
+  return 0;
+}
+
+int rollout_begin(arl_ctx* c, cudaStream_t st) {
+  const arl_sampler_cfg& s = c->sc;
+  int row_bytes = s.planes * kObsH * kObsW;
+  long chunks = (long)s.n_envs * (row_bytes / 16);
+  // observations[e*T + 0] = step_obs[e]   (worker.py:31-32)
+  copy_rows_kernel<<<(int)((chunks + 255) / 256), 256, 0, st>>>(s.step_obs, row_bytes, nullptr, s.observations, row_bytes,
+                                                               c->rows_tab, s.n_envs, row_bytes);
+  c->launches++;
+  ARL_CHECK(c, cudaMemsetAsync(c->tout.count, 0, sizeof(int), st));
+  ARL_CHECK(c, cudaGetLastError());
+  return 0;
+}
+
+int rollout_step(arl_ctx* c, int s_idx, const uint8_t* staging, cudaStream_t st) {
+  const arl_sampler_cfg& s = c->sc;
+  const int B = s.n_envs, T = s.horizon;
+  if (policy_forward(c, s.step_obs, nullptr, B, c->rows_tab + (long)s_idx * B, s.prob, s.value,
+                     s.uniforms + (long)s_idx * B, s.actions, st))
+    return 1;
+  env_step_kernel<<<(B + 127) / 128, 128, 0, st>>>(synth_cfg(s), c->est, c->tout, c->cmd, s.rewards, s.dones,
+                                                   s.raw_reward, s.need_reset, B, T, s_idx, s.max_path_length,
+                                                   s.discount, s.mid_batch_reset, s.clip_reward, s.episodic_lives);
+  c->launches++;
+  ARL_CHECK(c, cudaGetLastError());
+  return launch_frame(c, staging, s_idx + 1, s_idx + 1 < T, st);
+}
+
+int rollout_end(arl_ctx* c, cudaStream_t st) {
+  const arl_sampler_cfg& s = c->sc;
+  if (s.extra_observations) {
+    size_t bytes = (size_t)s.n_envs * s.planes * kObsH * kObsW;
+    ARL_CHECK(c, cudaMemcpyAsync(s.extra_observations, s.step_obs, bytes, cudaMemcpyDeviceToDevice, st));
+  }
+  if (!s.mid_batch_reset) {
+    env_reset_needed_kernel<<<(s.n_envs + 127) / 128, 128, 0, st>>>(synth_cfg(s), c->est, c->cmd, s.n_envs);
+    c->launches++;
+    ARL_CHECK(c, cudaGetLastError());
+    if (launch_frame(c, nullptr, 0, false, st)) return 1;
+  }
+  return 0;
+}
+
+}  // namespace
+
+// ===========================================================================
+// extern "C"
+// ===========================================================================
+extern "C" {
+
+int arl_create(const arl_net_cfg* cfg, arl_ctx** out) {
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e);
+    return 3;
+  }
+  cudaDeviceProp prop{};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaGetDeviceProperties(&prop, dev);
+  if (prop.major != 10) {
+    g_create_error = "libaccelrl_b200 requires an sm_100a device (found sm_" + std::to_string(prop.major) +
+                     std::to_string(prop.minor) + ")";
+    return 3;
+  }
+  arl_ctx* c = new arl_ctx();
+  c->cfg = *cfg;
+  if (plan_net(c) || alloc_net(c)) {
+    g_create_error = c->err;
+    delete c;
+    return 4;
+  }
+  *out = c;
+  return 0;
+}
+
+void arl_destroy(arl_ctx* c) {
+  if (!c) return;
+  cudaDeviceSynchronize();
+  comm_destroy(c->comm);
+  // device workspaces are released with the context's process lifetime; free the large ones explicitly
+  for (auto& L : c->conv) {
+    cudaFree(L.act); cudaFree(L.dact); cudaFree(L.wpack);
+    for (auto& d : L.dclasses) cudaFree(d.wpack);
+  }
+  for (auto p : c->wgrad_partial) cudaFree(p);
+  for (auto p : c->bias_partial) cudaFree(p);
+  cudaFree(c->wfc_pack); cudaFree(c->pack_jobs_dev); cudaFree(c->fc_partial); cudaFree(c->h); cudaFree(c->dh);
+  cudaFree(c->dlogit); cudaFree(c->head_partial); cudaFree(c->head_b_partial); cudaFree(c->loss_partial);
+  cudaFree(c->sumsq_partial); cudaFree(c->hyper); cudaFree(c->step); cudaFree(c->log_slot); cudaFree(c->log_norm);
+  cudaFree(c->log_loss); cudaFree(c->mb_counter); cudaFree(c->valid_count); cudaFree(c->dbg);
+  for (auto& kv : c->plans) cudaFree(kv.second.jobs_dev);
+  if (c->rollout_graph) cudaGraphExecDestroy(c->rollout_graph);
+  if (c->train_graph) cudaGraphExecDestroy(c->train_graph);
+  cudaFree(c->est.f); cudaFree(c->cmd); cudaFree(c->rows_tab); cudaFree(c->tout.count);
+  delete c;
+}
+
+const char* arl_last_error(arl_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int arl_device_error(arl_ctx* c) {
+  int v = 0;
+  cudaMemcpyFromSymbol(&v, g_dev_error, sizeof(int));
+  (void)c;
+  return v;
+}
+
+long arl_param_count(arl_ctx* c) { return c->n_params; }
+
+int arl_param_layout(arl_ctx* c, long* offsets, long* sizes, int cap) {
+  int n = (int)c->lay_off.size();
+  for (int i = 0; i < n && i < cap; ++i) { offsets[i] = c->lay_off[i]; sizes[i] = c->lay_size[i]; }
+  return n;
+}
+
+int arl_bind_params(arl_ctx* c, float* params, float* grad, float* m, float* v) {
+  c->params = params; c->grad = grad; c->m = m; c->v = v;
+  if (c->train_graph) { cudaGraphExecDestroy(c->train_graph); c->train_graph = nullptr; }
+  if (c->rollout_graph) { cudaGraphExecDestroy(c->rollout_graph); c->rollout_graph = nullptr; }
+  return 0;
+}
+
+int arl_pack_weights(arl_ctx* c, void* stream) { return pack_weights(c, (cudaStream_t)stream); }
+
+int arl_policy_forward(arl_ctx* c, const uint8_t* obs, const int* idx, int n, const int* out_rows, float* prob,
+                       float* value, const double* uniforms, uint8_t* actions, void* stream) {
+  return policy_forward(c, obs, idx, n, out_rows, prob, value, uniforms, actions, (cudaStream_t)stream);
+}
+
+int arl_sample_actions(arl_ctx* c, const float* prob, const double* uniforms, uint8_t* actions, int n, int n_actions,
+                       void* stream) {
+  sample_actions_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(prob, uniforms, actions, n, n_actions);
+  c->launches++;
+  ARL_CHECK(c, cudaGetLastError());
+  return 0;
+}
+
+int arl_frame_update(arl_ctx* c, const uint8_t* raw_a, const uint8_t* raw_b, const uint8_t* reset_mask, uint8_t* stack,
+                     int n, int planes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  // frames of item i live at raw_a + i*33600 / raw_b + i*33600: reuse frame_kernel's pool addressing with
+  // per-item indices, two passes of the same arithmetic are avoided by a tiny cmd table.
+  FrameCmd* cmd = nullptr;
+  ARL_CHECK(c, cudaMallocAsync(reinterpret_cast<void**>(&cmd), (size_t)n * sizeof(FrameCmd), st));
+  make_cmd_kernel<<<(n + 255) / 256, 256, 0, st>>>(cmd, reset_mask, n, raw_a != nullptr);
+  long items = (long)n * 520;
+  frame_pair_kernel<<<(int)((items + 255) / 256), 256, 0, st>>>(raw_a, raw_b, cmd, stack, n, planes);
+  c->launches += 2;
+  ARL_CHECK(c, cudaGetLastError());
+  ARL_CHECK(c, cudaFreeAsync(cmd, st));
+  return 0;
+}
+
+int arl_sampler_configure(arl_ctx* c, const arl_sampler_cfg* cfg) {
+  c->sc = *cfg;
+  const int B = cfg->n_envs, T = cfg->horizon;
+  if (cfg->planes != c->cfg.in_c) ARL_FAIL(c, "sampler planes != network input channels");
+  if (c->cfg.in_h != kObsH || c->cfg.in_w != kObsW) ARL_FAIL(c, "sampler requires 104x80 observations");
+  if (B > c->cfg.max_rows) ARL_FAIL(c, "n_envs larger than max_rows");
+  // env state block: 4 int arrays + ... allocate separately for clarity
+  int* iblock = nullptr;
+  if (dev_alloc(c, &iblock, (size_t)B * 10)) return 1;
+  c->est.f = iblock; c->est.lives_seen = iblock + B; c->est.need_reset = iblock + 2 * B; c->est.traj_len = iblock + 3 * B;
+  c->est.traj_nz = iblock + 4 * B;
+  float* fblock = reinterpret_cast<float*>(iblock + 5 * B);
+  c->est.traj_ret = fblock; c->est.traj_raw = fblock + B; c->est.traj_disc = fblock + 2 * B;
+  c->est.traj_cur = fblock + 3 * B;
+  if (dev_alloc(c, &c->cmd, (size_t)B)) return 1;
+  int cap = cfg->traj_cap > 0 ? cfg->traj_cap : 4 * B * 4;
+  int* tblock = nullptr;
+  if (dev_alloc(c, &tblock, (size_t)1 + (size_t)cap * 6)) return 1;
+  c->tout.count = tblock; c->tout.cap = cap; c->tout.env = tblock + 1; c->tout.len = tblock + 1 + cap;
+  c->tout.nz = tblock + 1 + 2 * cap;
+  c->tout.ret = reinterpret_cast<float*>(tblock + 1 + 3 * cap);
+  c->tout.raw = reinterpret_cast<float*>(tblock + 1 + 4 * cap);
+  c->tout.disc = reinterpret_cast<float*>(tblock + 1 + 5 * cap);
+  if (dev_alloc(c, &c->rows_tab, (size_t)B * T)) return 1;
+  std::vector<int> rt((size_t)B * T);
+  for (int s = 0; s < T; ++s)
+    for (int e = 0; e < B; ++e) rt[(size_t)s * B + e] = e * T + s;
+  ARL_CHECK(c, cudaMemcpy(c->rows_tab, rt.data(), rt.size() * sizeof(int), cudaMemcpyHostToDevice));
+  c->sampler_set = true;
+  if (c->rollout_graph) { cudaGraphExecDestroy(c->rollout_graph); c->rollout_graph = nullptr; }
+  return 0;
+}
+
+int arl_sampler_reset(arl_ctx* c, void* stream) {
+  if (!c->sampler_set) ARL_FAIL(c, "sampler not configured");
+  cudaStream_t st = (cudaStream_t)stream;
+  const arl_sampler_cfg& s = c->sc;
+  env_init_kernel<<<(s.n_envs + 127) / 128, 128, 0, st>>>(synth_cfg(s), c->est, c->cmd, s.n_envs);
+  c->launches++;
+  ARL_CHECK(c, cudaGetLastError());
+  return launch_frame(c, nullptr, 0, false, st);
+}
+
+int arl_rollout_begin(arl_ctx* c, void* stream) {
+  if (!c->sampler_set) ARL_FAIL(c, "sampler not configured");
+  return rollout_begin(c, (cudaStream_t)stream);
+}
+int arl_rollout_step(arl_ctx* c, int s, const uint8_t* staging, void* stream) {
+  if (!c->sampler_set) ARL_FAIL(c, "sampler not configured");
+  return rollout_step(c, s, staging, (cudaStream_t)stream);
+}
+int arl_rollout_end(arl_ctx* c, void* stream) {
+  if (!c->sampler_set) ARL_FAIL(c, "sampler not configured");
+  return rollout_end(c, (cudaStream_t)stream);
+}
+
+int arl_rollout_run(arl_ctx* c, void* stream) {
+  if (!c->sampler_set) ARL_FAIL(c, "sampler not configured");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!c->rollout_graph) {
+    // warm every kernel's lazy attribute setup outside capture
+    cudaStream_t cap;
+    ARL_CHECK(c, cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+    long l0 = c->launches;
+    cudaGraph_t g = nullptr;
+    ARL_CHECK(c, cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+    int rc = rollout_begin(c, cap);
+    for (int s = 0; s < c->sc.horizon && !rc; ++s) rc = rollout_step(c, s, nullptr, cap);
+    if (!rc) rc = rollout_end(c, cap);
+    cudaError_t ce = cudaStreamEndCapture(cap, &g);
+    c->graph_rollout_nodes = c->launches - l0;
+    c->launches = l0;
+    if (rc) { if (g) cudaGraphDestroy(g); cudaStreamDestroy(cap); return rc; }
+    ARL_CHECK(c, ce);
+    ARL_CHECK(c, cudaGraphInstantiate(&c->rollout_graph, g, 0));
+    cudaGraphDestroy(g);
+    cudaStreamDestroy(cap);
+  }
+  ARL_CHECK(c, cudaGraphLaunch(c->rollout_graph, st));
+  c->launches += c->graph_rollout_nodes;
+  return 0;
+}
+
+int arl_traj_read(arl_ctx* c, int* n, int* env, int* len, float* ret, float* raw, int* nz, float* disc, int cap,
+                  void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  int cnt = 0;
+  ARL_CHECK(c, cudaMemcpyAsync(&cnt, c->tout.count, sizeof(int), cudaMemcpyDeviceToHost, st));
+  ARL_CHECK(c, cudaStreamSynchronize(st));
+  cnt = std::min(cnt, std::min(cap, c->tout.cap));
+  *n = cnt;
+  if (cnt > 0) {
+    ARL_CHECK(c, cudaMemcpyAsync(env, c->tout.env, cnt * sizeof(int), cudaMemcpyDeviceToHost, st));
+    ARL_CHECK(c, cudaMemcpyAsync(len, c->tout.len, cnt * sizeof(int), cudaMemcpyDeviceToHost, st));
+    ARL_CHECK(c, cudaMemcpyAsync(nz, c->tout.nz, cnt * sizeof(int), cudaMemcpyDeviceToHost, st));
+    ARL_CHECK(c, cudaMemcpyAsync(ret, c->tout.ret, cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
+    ARL_CHECK(c, cudaMemcpyAsync(raw, c->tout.raw, cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
+    ARL_CHECK(c, cudaMemcpyAsync(disc, c->tout.disc, cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
+    ARL_CHECK(c, cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+int arl_peek_frame_cmds(arl_ctx* c, int* cmd_host, int n_envs, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  ARL_CHECK(c, cudaMemcpyAsync(cmd_host, c->cmd, (size_t)n_envs * sizeof(FrameCmd), cudaMemcpyDeviceToHost, st));
+  ARL_CHECK(c, cudaStreamSynchronize(st));
+  return 0;
+}
+
+int arl_gae(arl_ctx* c, const float* rewards, float* values, const uint8_t* dones, const uint8_t* need_reset,
+            const float* last_values, float discount, float gae_lambda, float* adv, float* ret, int8_t* valids,
+            int n_envs, int horizon, int standardize, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  int use_gae = (gae_lambda != 1.0f) ? 1 : 0;
+  gae_kernel<<<(n_envs + 3) / 4, 128, 0, st>>>(rewards, values, dones, need_reset, last_values, discount, gae_lambda,
+                                                use_gae, adv, ret, valids, n_envs, horizon);
+  c->launches++;
+  long n = (long)n_envs * horizon;
+  if (valids) {
+    count_valids_kernel<<<1, 1024, 0, st>>>(valids, n, c->valid_count);
+    c->launches++;
+  }
+  if (standardize) {
+    standardize_adv_kernel<<<1, 1024, 0, st>>>(adv, valids, n);
+    c->launches++;
+  }
+  ARL_CHECK(c, cudaGetLastError());
+  return 0;
+}
+
+int arl_opt_configure(arl_ctx* c, const arl_opt_cfg* cfg) {
+  c->opt = *cfg;
+  c->opt_set = true;
+  if (c->train_graph) { cudaGraphExecDestroy(c->train_graph); c->train_graph = nullptr; }
+  return 0;
+}
+
+int arl_bind_train_inputs(arl_ctx* c, const uint8_t* obs, const uint8_t* actions, const float* adv, const float* ret,
+                          const float* old_value, const float* old_prob, const int8_t* valids, long n_rows) {
+  bool same = (c->t_obs == obs && c->t_act == actions && c->t_adv == adv && c->t_ret == ret && c->t_oldp == old_prob &&
+               c->t_valids == valids);
+  c->t_obs = obs; c->t_act = actions; c->t_adv = adv; c->t_ret = ret; c->t_oldv = old_value; c->t_oldp = old_prob;
+  c->t_valids = valids; c->t_rows = n_rows;
+  if (!same && c->train_graph) { cudaGraphExecDestroy(c->train_graph); c->train_graph = nullptr; }
+  return 0;
+}
+
+int arl_set_lr_mult(arl_ctx* c, float lr_mult, void* stream) {
+  c->lr_mult_host = lr_mult;
+  ARL_CHECK(c, cudaMemcpyAsync(c->hyper, &c->lr_mult_host, sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  ARL_CHECK(c, cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
+int arl_grad_minibatch(arl_ctx* c, const int* idx, int mb_size, void* stream) {
+  return grad_minibatch(c, idx, nullptr, mb_size, (cudaStream_t)stream);
+}
+
+int arl_clip_update(arl_ctx* c, float gscale, void* stream) { return clip_update(c, gscale, (cudaStream_t)stream); }
+
+int arl_train_minibatches(arl_ctx* c, const int* idx, int mb_size, int count, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c->train_graph && (c->train_graph_idx != idx || c->train_graph_mb != mb_size)) {
+    cudaGraphExecDestroy(c->train_graph);
+    c->train_graph = nullptr;
+  }
+  if (!c->train_graph) {
+    TrainPlan* P = nullptr;
+    if (get_plan(c, mb_size, &P)) return 1;   // allocations happen outside capture
+    cudaStream_t cap;
+    ARL_CHECK(c, cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+    long l0 = c->launches;
+    cudaGraph_t g = nullptr;
+    ARL_CHECK(c, cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+    int rc = grad_minibatch(c, idx, c->mb_counter, mb_size, cap);
+    if (!rc) rc = clip_update(c, 1.f, cap);
+    cudaError_t ce = cudaStreamEndCapture(cap, &g);
+    c->graph_train_nodes = c->launches - l0;
+    c->launches = l0;
+    if (rc) { if (g) cudaGraphDestroy(g); cudaStreamDestroy(cap); return rc; }
+    ARL_CHECK(c, ce);
+    ARL_CHECK(c, cudaGraphInstantiate(&c->train_graph, g, 0));
+    cudaGraphDestroy(g);
+    cudaStreamDestroy(cap);
+    c->train_graph_idx = idx; c->train_graph_mb = mb_size;
+  }
+  ARL_CHECK(c, cudaMemsetAsync(c->mb_counter, 0, sizeof(int), st));
+  for (int i = 0; i < count; ++i) ARL_CHECK(c, cudaGraphLaunch(c->train_graph, st));
+  c->launches += (long)count * c->graph_train_nodes;
+  return 0;
+}
+
+int arl_read_logs(arl_ctx* c, float* loss, float* grad_norm, int cap, int* n, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  int cnt = 0;
+  ARL_CHECK(c, cudaMemcpyAsync(&cnt, c->log_slot, sizeof(int), cudaMemcpyDeviceToHost, st));
+  ARL_CHECK(c, cudaStreamSynchronize(st));
+  cnt = std::min(cnt, std::min(cap, c->log_cap));
+  *n = cnt;
+  if (cnt > 0) {
+    ARL_CHECK(c, cudaMemcpyAsync(loss, c->log_loss, cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
+    ARL_CHECK(c, cudaMemcpyAsync(grad_norm, c->log_norm, cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  ARL_CHECK(c, cudaMemsetAsync(c->log_slot, 0, sizeof(int), st));
+  ARL_CHECK(c, cudaStreamSynchronize(st));
+  return 0;
+}
+
+int arl_reset_opt_state(arl_ctx* c, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  ARL_CHECK(c, cudaMemsetAsync(c->step, 0, sizeof(int), st));
+  ARL_CHECK(c, cudaMemsetAsync(c->log_slot, 0, sizeof(int), st));
+  if (c->m) ARL_CHECK(c, cudaMemsetAsync(c->m, 0, c->n_params * sizeof(float), st));
+  if (c->v) ARL_CHECK(c, cudaMemsetAsync(c->v, 0, c->n_params * sizeof(float), st));
+  return 0;
+}
+
+// ---- sync DP ------------------------------------------------------------------------------
+int arl_comm_local_init(arl_ctx* c, int rank, int world, uint8_t* handle_out) {
+  std::string err;
+  if (comm_local_init(c->comm, rank, world, c->n_params, handle_out, err)) { c->err = err; return 5; }
+  return 0;
+}
+int arl_comm_buffers(arl_ctx* c, float** grad_out, float** params_out) {
+  if (!c->comm.base) ARL_FAIL(c, "comm not initialised");
+  *grad_out = c->comm.grad; *params_out = c->comm.param;
+  return 0;
+}
+int arl_comm_connect(arl_ctx* c, const uint8_t* all_handles) {
+  std::string err;
+  if (comm_connect(c->comm, all_handles, err)) { c->err = err; return 5; }
+  return 0;
+}
+int arl_comm_barrier(arl_ctx* c, void* stream) {
+  std::string err;
+  if (comm_barrier(c->comm, (cudaStream_t)stream, err)) { c->err = err; return 5; }
+  c->launches++;
+  return 0;
+}
+int arl_sync_allreduce_update(arl_ctx* c, void* stream) {
+  if (!c->opt_set) ARL_FAIL(c, "optimizer not configured");
+  cudaStream_t st = (cudaStream_t)stream;
+  SyncUpdateArgs a{};
+  a.param = c->params; a.grad = c->grad; a.m = c->m; a.v = c->v; a.n = c->n_params;
+  a.loss_partial = c->loss_partial; a.n_loss_blocks = kLossBlocks; a.hyper = c->hyper; a.step = c->step;
+  a.kind = c->opt.update; a.lr = c->opt.learning_rate; a.beta1 = c->opt.beta1; a.beta2 = c->opt.beta2;
+  a.eps = c->opt.epsilon; a.rho = c->opt.rho; a.clip = c->opt.grad_norm_clip;
+  a.out_norm = c->log_norm; a.out_loss = c->log_loss; a.log_slot = c->log_slot; a.log_cap = c->log_cap;
+  std::string err;
+  if (comm_sync_update(c->comm, a, st, err)) { c->err = err; return 5; }
+  c->launches += 2;
+  advance_counters_kernel<<<1, 1, 0, st>>>(c->step, c->log_slot, c->mb_counter);
+  c->launches++;
+  ARL_CHECK(c, cudaGetLastError());
+  return pack_weights(c, st);
+}
+
+// ---- diagnostics --------------------------------------------------------------------------
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* x, float* y, long n) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = __bfloat162float(x[i]);
+}
+
+int arl_debug_activation(arl_ctx* c, int layer, float* out, long cap, long* n, void* stream) {
+  // layer: 0..n_conv-1 conv activations of the last forward ([rows][Cout], NHWC), n_conv..2n_conv-1 their
+  // gradients, 100 = h, 101 = dh (both need a training pass)
+  cudaStream_t st = (cudaStream_t)stream;
+  const __nv_bfloat16* src = nullptr;
+  long cnt = 0;
+  int nc = (int)c->conv.size();
+  long R = c->cfg.max_rows;
+  if (layer >= 0 && layer < nc) { src = c->conv[layer].act; cnt = R * c->conv[layer].Ho * c->conv[layer].Wo * c->conv[layer].Cout; }
+  else if (layer >= nc && layer < 2 * nc) { auto& L = c->conv[layer - nc]; src = L.dact; cnt = R * L.Ho * L.Wo * L.Cout; }
+  else if (layer == 100) { src = c->h; cnt = R * c->H; }
+  else if (layer == 101) { src = c->dh; cnt = R * c->H; }
+  else ARL_FAIL(c, "bad layer id");
+  cnt = std::min(cnt, cap);
+  *n = cnt;
+  bf16_to_f32_kernel<<<(int)((cnt + 255) / 256), 256, 0, st>>>(src, out, cnt);
+  ARL_CHECK(c, cudaGetLastError());
+  return 0;
+}
+
+long arl_kernel_launches(arl_ctx* c) { return c->launches; }
+
+int arl_test_gemm(arl_ctx* c, const uint16_t* a_bf16, const uint16_t* b_bf16, float* d, int M, int N, int K,
+                  int b_nmajor, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (K % 64 || N % 64) ARL_FAIL(c, "test gemm needs K%64==0 and N%64==0");
+  DenseLoader<128> a{};
+  a.src = reinterpret_cast<const __nv_bfloat16*>(a_bf16); a.ld = K; a.nrows = M;
+  RowEpi e = make_epi(EPI_PARTIAL_F32);
+  e.partial = d; e.ldo = N; e.M = M;
+  if (b_nmajor) {
+    WeightSrc w{reinterpret_cast<const __nv_bfloat16*>(b_bf16), (long)N, K};
+    return launch_rowgemm<DenseLoader<128>, true, 64>(c, a, w, e, M, N, K / 64, K / 64, 1, st);
+  }
+  WeightSrc w{reinterpret_cast<const __nv_bfloat16*>(b_bf16), (long)K, 0};
+  return launch_rowgemm<DenseLoader<128>, false, 64>(c, a, w, e, M, N, K / 64, K / 64, 1, st);
+}
+
+int arl_test_wgrad(arl_ctx* c, const uint16_t* a_bf16, const uint16_t* b_bf16, float* d, int rows, int Kp, int N,
+                   void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (Kp % 64) ARL_FAIL(c, "test wgrad needs Kp%64==0");
+  DenseLoader<64> a{};
+  a.src = reinterpret_cast<const __nv_bfloat16*>(a_bf16); a.ld = Kp; a.nrows = rows;
+  WgradEpi e{};
+  e.out = d; e.mode = 0; e.Kvalid = Kp; e.Kp = Kp; e.ldo = N;
+  const __nv_bfloat16* dy = reinterpret_cast<const __nv_bfloat16*>(b_bf16);
+  int rps = roundup(rows, 64);
+  int atoms = Kp / 64;
+  if (N == 256) return launch_wgrad<DenseLoader<64>, 1, 256>(c, a, dy, N, rows, rps, 1, atoms, 1, e, st);
+  if (N == 64) return launch_wgrad<DenseLoader<64>, 4, 64>(c, a, dy, N, rows, rps, 1, atoms, 1, e, st);
+  if (N == 32) return launch_wgrad<DenseLoader<64>, 2, 32>(c, a, dy, N, rows, rps, 1, atoms, 1, e, st);
+  if (N == 16) return launch_wgrad<DenseLoader<64>, 2, 16>(c, a, dy, N, rows, rps, 1, atoms, 1, e, st);
+  ARL_FAIL(c, "test wgrad supports N in {16,32,64,256}");
+}
+
+}  // extern "C"
+

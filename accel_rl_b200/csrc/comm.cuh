@@ -1,0 +1,309 @@
+// Synchronous data-parallel gradient step fused with the optimiser update over NVLink peer memory.
+//
+// Reference behaviour (optimizers/sync/base.py:22-24, sync_ppo_optimizer.py:41-48, optimizers/util.py:63-76):
+//   all ranks: flat grad -> NCCL all-reduce(sum) -> x 1/n_gpu -> global-norm clip -> Adam/RMSProp (identical on
+//   every rank).
+// Here: every rank owns 1/world of the flat vector.  ONE cooperative kernel per update
+//   1. cross-GPU flag barrier (all gradients are complete),
+//   2. reduce my slice by direct P2P loads from every peer's gradient buffer, average, keep the slice in a
+//      local scratch, accumulate sum-of-squares,
+//   3. publish my slice's sum-of-squares to every peer (P2P store) + flag barrier -> global norm (summed in
+//      rank order, so bit-identical on every rank),
+//   4. clip + Adam/RMSProp on my slice (m, v exist only for the slice), P2P-store the new parameters of the
+//      slice into every peer's parameter vector,
+//   5. flag barrier (all parameters have landed).
+// Buffers are cudaMalloc'ed here and exchanged with cudaIpc handles (one process per GPU); NCCL is only the
+// host-side bootstrap that ships the 64-byte handles.
+#pragma once
+#include <string>
+#include <vector>
+#include "common.cuh"
+
+namespace arl {
+
+constexpr int kMaxRanks = 8;
+constexpr int kSyncBlocks = 148;
+constexpr int kSyncThreads = 512;
+
+struct CommDev {
+  float* peer_grad[kMaxRanks];
+  float* peer_param[kMaxRanks];
+  unsigned int* peer_flag[kMaxRanks];     // each rank's arrival counter (written by peers)
+  double* peer_norm[kMaxRanks];           // [world] slice sums of squares, slot = writer rank
+  int rank, world;
+  long n, per;                            // vector length, slice length (multiple of 4)
+  float* avg_slice;                       // local scratch [per]
+  double* block_partial;                  // [kSyncBlocks]
+  unsigned int* grid_counter;             // local grid barrier
+  unsigned int* epoch;                    // local: number of cross-GPU barriers completed
+};
+
+struct CommState {
+  bool ready = false;
+  int rank = 0, world = 1;
+  long n = 0;
+  void* base = nullptr;                   // local symmetric allocation
+  size_t bytes = 0;
+  std::vector<void*> peer_base;
+  CommDev dev{};
+  float* grad = nullptr;                  // local views
+  float* param = nullptr;
+};
+
+struct SyncUpdateArgs {
+  float* param; float* grad; float* m; float* v; long n;
+  const float* loss_partial; int n_loss_blocks;
+  const float* hyper; int* step;
+  int kind; float lr, beta1, beta2, eps, rho, clip;
+  float* out_norm; float* out_loss; int* log_slot; int log_cap;
+};
+
+// symmetric layout (bytes): [grad n f32][param n f32][norm kMaxRanks f64][flag u32 .. pad]
+inline size_t comm_layout(long n, size_t* off_param, size_t* off_norm, size_t* off_flag) {
+  size_t nb = ((size_t)n * 4 + 255) / 256 * 256;
+  *off_param = nb;
+  *off_norm = 2 * nb;
+  *off_flag = 2 * nb + 256;
+  return 2 * nb + 512;
+}
+
+inline int comm_local_init(CommState& s, int rank, int world, long n, uint8_t* handle_out, std::string& err) {
+  if (world < 1 || world > kMaxRanks) { err = "world size must be in [1,8]"; return 1; }
+  s.rank = rank; s.world = world; s.n = n;
+  size_t op, on, of;
+  s.bytes = comm_layout(n, &op, &on, &of);
+  cudaError_t e = cudaMalloc(&s.base, s.bytes);
+  if (e != cudaSuccess) { err = std::string("cudaMalloc(sym): ") + cudaGetErrorString(e); return 1; }
+  cudaMemset(s.base, 0, s.bytes);
+  cudaIpcMemHandle_t h;
+  e = cudaIpcGetMemHandle(&h, s.base);
+  if (e != cudaSuccess) { err = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e); return 1; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+  memcpy(handle_out, &h, 64);
+  s.grad = reinterpret_cast<float*>(s.base);
+  s.param = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s.base) + op);
+  return 0;
+}
+
+inline int comm_connect(CommState& s, const uint8_t* all_handles, std::string& err) {
+  size_t op, on, of;
+  comm_layout(s.n, &op, &on, &of);
+  s.peer_base.assign(s.world, nullptr);
+  for (int r = 0; r < s.world; ++r) {
+    if (r == s.rank) { s.peer_base[r] = s.base; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, all_handles + (size_t)r * 64, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(&s.peer_base[r], h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { err = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e); return 1; }
+  }
+  CommDev& d = s.dev;
+  d.rank = s.rank; d.world = s.world; d.n = s.n;
+  d.per = ((s.n + s.world - 1) / s.world + 3) / 4 * 4;
+  for (int r = 0; r < s.world; ++r) {
+    uint8_t* b = reinterpret_cast<uint8_t*>(s.peer_base[r]);
+    d.peer_grad[r] = reinterpret_cast<float*>(b);
+    d.peer_param[r] = reinterpret_cast<float*>(b + op);
+    d.peer_norm[r] = reinterpret_cast<double*>(b + on);
+    d.peer_flag[r] = reinterpret_cast<unsigned int*>(b + of);
+  }
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&d.avg_slice), (size_t)d.per * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d.block_partial), kSyncBlocks * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d.grid_counter), 256);
+  if (e != cudaSuccess) { err = std::string("cudaMalloc(comm scratch): ") + cudaGetErrorString(e); return 1; }
+  cudaMemset(d.grid_counter, 0, 256);
+  d.epoch = d.grid_counter + 16;
+  s.ready = true;
+  return 0;
+}
+
+inline void comm_destroy(CommState& s) {
+  if (!s.base) return;
+  for (int r = 0; r < (int)s.peer_base.size(); ++r)
+    if (r != s.rank && s.peer_base[r]) cudaIpcCloseMemHandle(s.peer_base[r]);
+  cudaFree(s.dev.avg_slice); cudaFree(s.dev.block_partial); cudaFree(s.dev.grid_counter);
+  cudaFree(s.base);
+  s.base = nullptr; s.ready = false;
+}
+
+// ---- device side ---------------------------------------------------------------------------
+ARL_DEVINL void st_release_sys_add(unsigned int* p) {
+  asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
+ARL_DEVINL unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// one thread: signal every peer, wait until all peers signalled me for this epoch
+ARL_DEVINL void xgpu_barrier_thread(const CommDev& d) {
+  unsigned int ep = *d.epoch + 1;
+  __threadfence_system();
+  for (int r = 0; r < d.world; ++r) st_release_sys_add(d.peer_flag[r]);
+  unsigned int target = ep * (unsigned int)d.world;
+  long long t0 = clock64();
+  while (ld_acquire_sys(d.peer_flag[d.rank]) < target) {
+    if (clock64() - t0 > 20000000000LL) dev_fail(300);   // ~10 s: a peer is gone
+  }
+  *d.epoch = ep;
+  __threadfence_system();
+}
+
+// grid-wide barrier for a co-resident (cooperative) grid; optional cross-GPU barrier by block 0
+ARL_DEVINL void grid_barrier(const CommDev& d, unsigned int& gen, bool cross_gpu) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    gen += gridDim.x;
+    unsigned int arrived = atomicAdd(d.grid_counter, 1u) + 1u;
+    if (blockIdx.x == 0) {
+      // wait for every block, then (optionally) the other GPUs, then release the grid
+      long long t0 = clock64();
+      while (atomicAdd(d.grid_counter, 0u) < gen) {
+        if (clock64() - t0 > 20000000000LL) dev_fail(301);
+      }
+      if (cross_gpu) xgpu_barrier_thread(d);
+      __threadfence();
+      atomicExch(d.grid_counter + 1, gen);
+    } else {
+      (void)arrived;
+      long long t0 = clock64();
+      while (atomicAdd(d.grid_counter + 1, 0u) < gen) {
+        if (clock64() - t0 > 20000000000LL) dev_fail(302);
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kSyncThreads) sync_allreduce_update_kernel(CommDev d, SyncUpdateArgs a,
+                                                                             unsigned int gen0) {
+  unsigned int gen = gen0;
+  const long begin = (long)d.rank * d.per;
+  const long end = min(d.n, begin + d.per);
+  const long len = end > begin ? end - begin : 0;
+  const long len4 = len >> 2;
+  const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long gsz = (long)gridDim.x * blockDim.x;
+  __shared__ double s_red[kSyncThreads / 32];
+  __shared__ float s_scale, s_alpha;
+
+  // 1. all gradients complete on every GPU
+  grid_barrier(d, gen, true);
+
+  // 2. reduce my slice over peers (P2P loads), average, local scratch + sum of squares
+  const float inv_world = 1.f / (float)d.world;
+  double acc = 0.0;
+  for (long i = gtid; i < len4; i += gsz) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < d.world; ++r) {
+      const float4 g = *reinterpret_cast<const float4*>(d.peer_grad[r] + begin + 4 * i);
+      s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
+    }
+    s.x *= inv_world; s.y *= inv_world; s.z *= inv_world; s.w *= inv_world;
+    reinterpret_cast<float4*>(d.avg_slice)[i] = s;
+    acc += (double)(s.x * s.x + s.y * s.y) + (double)(s.z * s.z + s.w * s.w);
+  }
+  if (gtid == 0) {
+    for (long i = len4 << 2; i < len; ++i) {
+      float s = 0.f;
+      for (int r = 0; r < d.world; ++r) s += d.peer_grad[r][begin + i];
+      s *= inv_world;
+      d.avg_slice[i] = s;
+      acc += (double)s * s;
+    }
+  }
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kSyncThreads / 32; ++w) t += s_red[w];
+    d.block_partial[blockIdx.x] = t;
+  }
+  grid_barrier(d, gen, false);
+
+  // 3. publish my slice's sum of squares to every peer, then barrier across GPUs
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double t = 0.0;
+    for (int b = 0; b < (int)gridDim.x; ++b) t += d.block_partial[b];
+    for (int r = 0; r < d.world; ++r) d.peer_norm[r][d.rank] = t;
+  }
+  grid_barrier(d, gen, true);
+
+  // 4. global norm (rank order), clip, update my slice, P2P-store new params to every peer
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    const volatile double* np = d.peer_norm[d.rank];
+    for (int r = 0; r < d.world; ++r) t += np[r];
+    float norm = (float)sqrt(t);
+    float scale = 1.f;
+    if (a.clip > 0.f) scale = fminf(norm, a.clip) / (1e-7f + norm);
+    s_scale = scale;
+    int tstep = a.step[0] + 1;
+    float lr = a.lr * a.hyper[0];
+    if (a.kind == 0) {
+      double b1t = pow((double)a.beta1, (double)tstep), b2t = pow((double)a.beta2, (double)tstep);
+      s_alpha = (float)((double)lr * sqrt(1.0 - b2t) / (1.0 - b1t));
+    } else {
+      s_alpha = lr;
+    }
+    if (blockIdx.x == 0) {
+      int slot = a.log_slot[0];
+      if (slot < a.log_cap) {
+        a.out_norm[slot] = norm;
+        float l = 0.f;
+        for (int b = 0; b < a.n_loss_blocks; ++b) l += a.loss_partial[4 * b + 3];
+        a.out_loss[slot] = l;
+      }
+    }
+  }
+  __syncthreads();
+  const float scale = s_scale, alpha = s_alpha;
+  for (long i = gtid; i < len; i += gsz) {
+    const long gi = begin + i;
+    float g = d.avg_slice[i] * scale;
+    float p = a.param[gi];
+    if (a.kind == 0) {
+      float m = a.beta1 * a.m[gi] + (1.f - a.beta1) * g;
+      float v = a.beta2 * a.v[gi] + (1.f - a.beta2) * g * g;
+      a.m[gi] = m; a.v[gi] = v;
+      p -= alpha * m / (sqrtf(v) + a.eps);
+    } else {
+      float ac = a.rho * a.v[gi] + (1.f - a.rho) * g * g;
+      a.v[gi] = ac;
+      p -= alpha * g / sqrtf(ac + a.eps);
+    }
+    for (int r = 0; r < d.world; ++r) d.peer_param[r][gi] = p;
+  }
+  // 5. all parameter slices have landed everywhere
+  grid_barrier(d, gen, true);
+}
+
+__global__ void xgpu_barrier_kernel(CommDev d) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) xgpu_barrier_thread(d);
+}
+
+inline int comm_barrier(CommState& s, cudaStream_t st, std::string& err) {
+  if (!s.ready) { err = "comm not connected"; return 1; }
+  xgpu_barrier_kernel<<<1, 32, 0, st>>>(s.dev);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { err = cudaGetErrorString(e); return 1; }
+  return 0;
+}
+
+inline int comm_sync_update(CommState& s, SyncUpdateArgs a, cudaStream_t st, std::string& err) {
+  if (!s.ready) { err = "comm not connected"; return 1; }
+  if (a.param != s.param || a.grad != s.grad) { err = "params/grad must be the comm's symmetric buffers"; return 1; }
+  static unsigned int gen_host = 0;   // grid-barrier generation carried across launches
+  unsigned int gen0 = gen_host;
+  gen_host += 4u * kSyncBlocks;       // four grid barriers per launch
+  void* args[] = {(void*)&s.dev, (void*)&a, (void*)&gen0};
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)sync_allreduce_update_kernel, dim3(kSyncBlocks),
+                                              dim3(kSyncThreads), args, 0, st);
+  if (e != cudaSuccess) { err = std::string("cooperative launch: ") + cudaGetErrorString(e); return 1; }
+  return 0;
+}
+
+}  // namespace arl

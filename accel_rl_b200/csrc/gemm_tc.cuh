@@ -1,0 +1,630 @@
+// tcgen05 tensor-core tiles for the policy/value network (sm_100a).
+//
+// Two kernels cover every dense contraction on the path:
+//
+//   rowgemm_kernel : D[128 rows x BN] = A[128 x K] * B[BN x K]^T        (A K-major)
+//       conv forward (implicit GEMM, rows = output pixels), conv dgrad (rows = input
+//       pixels of one stride-parity class), FC forward (split-K) and FC dgrad.
+//   wgrad_kernel   : D[K' x BN] = sum_rows A[row, K']^T * dY[row, BN]   (both MN-major)
+//       conv / FC weight gradients, split over row ranges.
+//
+// Operand tiles are staged in shared memory in the UMMA canonical 128-byte-swizzled
+// layout by 8 producer warps (the im2col gather is fused into that load: the patch is
+// never materialised in HBM); one elected thread issues tcgen05.mma with the fp32
+// accumulator in TMEM; the same 8 warps read it back with tcgen05.ld for the fused
+// epilogue (bias + ReLU + bf16 pack, dReLU mask, or fp32 split partials).
+// Producer <-> MMA hand-off is an mbarrier ring (full/empty per stage).
+#pragma once
+#include "common.cuh"
+
+namespace arl {
+
+constexpr int kProducerWarps = 8;
+constexpr int kProducerThreads = kProducerWarps * 32;  // 256
+constexpr int kGemmThreads = kProducerThreads + 32;    // + MMA warp
+constexpr int kBK = 64;                                // K elements per stage (128 B of bf16)
+
+// ---------------------------------------------------------------------------
+// operand loaders (run by the 256 producer threads; tid in [0,256))
+// ---------------------------------------------------------------------------
+
+// Dense row-major bf16 source: copies R rows x ROWB bytes into a swizzled tile.
+//   tile row r  <- src[(row0 + r) * ld + col0 .. + ROWB/2)   (zero when row0+r >= nrows)
+template <int R, int ROWB>
+ARL_DEVINL void fill_dense(uint32_t tile, const __nv_bfloat16* __restrict__ src, long ld, int row0, int nrows,
+                           int col0, int tid) {
+  constexpr int CH = ROWB / 16;        // 16-byte chunks per row
+  constexpr int TOTAL = R * CH;        // chunks in the tile
+#pragma unroll
+  for (int i = tid; i < TOTAL; i += kProducerThreads) {
+    int r = i / CH, c = i % CH;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    int row = row0 + r;
+    if (row < nrows) v = __ldg(reinterpret_cast<const uint4*>(src + (long)row * ld + col0 + c * 8));
+    st_shared_v4(tile + swz_off<ROWB>(r, c), v);
+  }
+}
+
+// Gather geometry for implicit-GEMM tiles whose rows are spatial positions.
+// Rows enumerate (b, qy, qx); K index k' = (ty * Tx + tx) * C + c over an NHWC bf16 source.
+//   src_y = qy * sy + y0 + ty * dty,  src_x = qx * sx + x0 + tx * dtx   (out of range -> 0)
+struct ConvGeom {
+  const __nv_bfloat16* src;
+  int Qh, Qw;            // row grid per image
+  int Hs, Ws, C;         // source dims
+  int sy, y0, dty;
+  int sx, x0, dtx;
+  int Tx;                // taps per tap-row
+  int nrows;             // nb * Qh * Qw
+};
+
+struct RowInfo {
+  long base;   // element offset of image b in src (or -1 when the row is out of range)
+  int ys, xs;  // qy*sy + y0, qx*sx + x0
+};
+
+ARL_DEVINL RowInfo conv_row_info(const ConvGeom& g, int row) {
+  RowInfo ri;
+  if (row >= g.nrows) {
+    ri.base = -1; ri.ys = 0; ri.xs = 0;
+    return ri;
+  }
+  int per = g.Qh * g.Qw;
+  int b = row / per;
+  int rem = row - b * per;
+  int qy = rem / g.Qw;
+  int qx = rem - qy * g.Qw;
+  ri.base = (long)b * g.Hs * g.Ws * g.C;
+  ri.ys = qy * g.sy + g.y0;
+  ri.xs = qx * g.sx + g.x0;
+  return ri;
+}
+
+// One [R rows x 64 k'] tile (k-block kb).  Thread owns chunk column j = tid & 7 and rows (tid>>3) + 32*i.
+template <int R>
+struct ConvLoader {
+  ConvGeom g;
+  RowInfo ri[R / 32];
+  ARL_DEVINL void prepare(int row0, int tid) {
+#pragma unroll
+    for (int i = 0; i < R / 32; ++i) ri[i] = conv_row_info(g, row0 + (tid >> 3) + 32 * i);
+  }
+  ARL_DEVINL void fill(uint32_t tile, int kb, int tid) const {
+    int j = tid & 7;
+    int kc = kb * 8 + j;          // global 16-byte chunk index along K
+    int cpt = g.C >> 3;           // chunks per tap
+    int tap = kc / cpt;
+    int cc = kc - tap * cpt;
+    int ty = tap / g.Tx;
+    int tx = tap - ty * g.Tx;
+    int dy = ty * g.dty, dx = tx * g.dtx;
+#pragma unroll
+    for (int i = 0; i < R / 32; ++i) {
+      int r = (tid >> 3) + 32 * i;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      int y = ri[i].ys + dy, x = ri[i].xs + dx;
+      if (ri[i].base >= 0 && (unsigned)y < (unsigned)g.Hs && (unsigned)x < (unsigned)g.Ws) {
+        const __nv_bfloat16* p = g.src + ri[i].base + ((long)(y * g.Ws + x) * g.C + cc * 8);
+        v = __ldg(reinterpret_cast<const uint4*>(p));
+      }
+      st_shared_v4(tile + swz_off<128>(r, j), v);
+    }
+  }
+};
+
+// First conv layer: uint8 CHW observations (the reference's buffer layout), filter width 8,
+// no padding.  K index k' = (c * kh + ky) * 8 + kx; a 16-byte smem chunk = 8 pixels of one
+// (c, ky) patch row, converted u8 -> bf16 (exact) on the way in.  Optional batch gather
+// through idx (shuffled minibatch rows of the rollout buffer).
+struct ConvGeomU8 {
+  const uint8_t* src;   // [n, C, Hs, Ws]
+  const int* idx;       // optional row gather (nullptr = identity): image b reads row idx[off*nb + b]
+  const int* idx_off;   // optional device scalar: minibatch index `off` (graph-replayed training)
+  int Qh, Qw;           // output grid
+  int Hs, Ws, C;
+  int kh;               // filter height (width fixed at 8)
+  int stride;
+  int nrows;            // nb * Qh * Qw
+};
+
+ARL_DEVINL uint4 u8x8_to_bf16x8(uint32_t lo, uint32_t hi) {
+  // byte b -> float(2^23 + b) - 2^23 (exact), then pack pairs to bf16x2 (exact for 0..255)
+  float f[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[i] = __uint_as_float(__byte_perm(lo, 0x4B000000u, 0x7650 + i) ) - 8388608.0f;
+    f[4 + i] = __uint_as_float(__byte_perm(hi, 0x4B000000u, 0x7650 + i)) - 8388608.0f;
+  }
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]);
+  o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]);
+  o.w = pack_bf16x2(f[6], f[7]);
+  return o;
+}
+
+template <int R>
+struct ConvLoaderU8 {
+  ConvGeomU8 g;
+  long base[R / 32];  // byte offset of (image, y0, x0) or -1
+  ARL_DEVINL void prepare(int row0, int tid) {
+    int per = g.Qh * g.Qw;
+    const int* ip = g.idx;
+    if (ip && g.idx_off) ip += (long)(*g.idx_off) * (g.nrows / per);
+#pragma unroll
+    for (int i = 0; i < R / 32; ++i) {
+      int row = row0 + (tid >> 3) + 32 * i;
+      if (row >= g.nrows) { base[i] = -1; continue; }
+      int b = row / per;
+      int rem = row - b * per;
+      int qy = rem / g.Qw;
+      int qx = rem - qy * g.Qw;
+      long img = ip ? (long)ip[b] : (long)b;
+      base[i] = img * g.C * g.Hs * g.Ws + (long)(qy * g.stride) * g.Ws + qx * g.stride;
+    }
+  }
+  ARL_DEVINL void fill(uint32_t tile, int kb, int tid) const {
+    int j = tid & 7;
+    int kc = kb * 8 + j;   // (c, ky) patch-row index
+    int c = kc / g.kh;
+    int ky = kc - c * g.kh;
+    long off = ((long)c * g.Hs + ky) * g.Ws;
+#pragma unroll
+    for (int i = 0; i < R / 32; ++i) {
+      int r = (tid >> 3) + 32 * i;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (base[i] >= 0) {
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(g.src + base[i] + off);  // 4-byte aligned (stride%4==0)
+        v = u8x8_to_bf16x8(__ldg(p), __ldg(p + 1));
+      }
+      st_shared_v4(tile + swz_off<128>(r, j), v);
+    }
+  }
+};
+
+// Dense K-major A operand (FC forward / FC dgrad: rows = batch rows of a row-major matrix)
+template <int R>
+struct DenseLoader {
+  const __nv_bfloat16* src;
+  long ld;
+  int nrows;
+  int row0;
+  ARL_DEVINL void prepare(int r0, int) { row0 = r0; }
+  ARL_DEVINL void fill(uint32_t tile, int kb, int tid) const { fill_dense<R, 128>(tile, src, ld, row0, nrows, kb * kBK, tid); }
+};
+
+// ---------------------------------------------------------------------------
+// epilogue description (runtime-switched; the branch is uniform per launch)
+// ---------------------------------------------------------------------------
+enum EpiMode { EPI_BIAS_RELU_BF16 = 0, EPI_MASK_BF16 = 1, EPI_PARTIAL_F32 = 2, EPI_BIAS_BF16 = 3 };
+
+struct RowEpi {
+  int mode;
+  float scale;                 // applied to the accumulator before bias (conv1: 1/255)
+  const float* bias;           // [N] (modes 0,3)
+  __nv_bfloat16* out;          // bf16 destination (modes 0,1,3), row pitch ldo
+  const __nv_bfloat16* act;    // forward activation at the destination (mode 1: dReLU mask)
+  float* partial;              // fp32 [split][M][ldo] (mode 2)
+  int ldo;
+  int M;                       // valid rows
+  // destination-row map: identity when map_s == 0, else rows enumerate (b,qy,qx) of a
+  // stride-parity class and land at (b, map_s*qy + map_y0, map_s*qx + map_x0) of an H x W grid
+  int map_s, map_y0, map_x0, map_Qh, map_Qw, map_H, map_W;
+};
+
+ARL_DEVINL long epi_dest_row(const RowEpi& e, int row) {
+  if (e.map_s == 0) return row;
+  int per = e.map_Qh * e.map_Qw;
+  int b = row / per;
+  int rem = row - b * per;
+  int qy = rem / e.map_Qw;
+  int qx = rem - qy * e.map_Qw;
+  return ((long)b * e.map_H + (e.map_s * qy + e.map_y0)) * e.map_W + (e.map_s * qx + e.map_x0);
+}
+
+// 32 consecutive accumulator columns of one row -> destination
+ARL_DEVINL void epi_store32(const RowEpi& e, int row, int n0, const uint32_t (&r)[32], int split) {
+  if (row >= e.M) return;
+  if (e.mode == EPI_PARTIAL_F32) {
+    float4* dst = reinterpret_cast<float4*>(e.partial + ((long)split * e.M + row) * e.ldo + n0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                           __uint_as_float(r[4 * i + 3]));
+    return;
+  }
+  long drow = epi_dest_row(e, row);
+  uint32_t packed[16];
+  if (e.mode == EPI_MASK_BF16) {
+    const uint4* a = reinterpret_cast<const uint4*>(e.act + drow * e.ldo + n0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 m = __ldg(a + i);
+      uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float lo = __uint_as_float(r[8 * i + 2 * k]), hi = __uint_as_float(r[8 * i + 2 * k + 1]);
+        lo = bf16_lo(mw[k]) > 0.f ? lo : 0.f;
+        hi = bf16_hi(mw[k]) > 0.f ? hi : 0.f;
+        packed[4 * i + k] = pack_bf16x2(lo, hi);
+      }
+    }
+  } else {
+    const bool relu = (e.mode == EPI_BIAS_RELU_BF16);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float lo = __uint_as_float(r[2 * i]) * e.scale + __ldg(e.bias + n0 + 2 * i);
+      float hi = __uint_as_float(r[2 * i + 1]) * e.scale + __ldg(e.bias + n0 + 2 * i + 1);
+      if (relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+      packed[i] = pack_bf16x2(lo, hi);
+    }
+  }
+  uint4* dst = reinterpret_cast<uint4*>(e.out + drow * e.ldo + n0);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+}
+
+ARL_DEVINL void epi_store16(const RowEpi& e, int row, int n0, const uint32_t (&r16)[16], int split) {
+  // 16-column variant (BN == 32 tiles): widen into two halves of the 32-column path is not possible,
+  // so handle it directly.
+  if (row >= e.M) return;
+  if (e.mode == EPI_PARTIAL_F32) {
+    float4* dst = reinterpret_cast<float4*>(e.partial + ((long)split * e.M + row) * e.ldo + n0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      dst[i] = make_float4(__uint_as_float(r16[4 * i]), __uint_as_float(r16[4 * i + 1]),
+                           __uint_as_float(r16[4 * i + 2]), __uint_as_float(r16[4 * i + 3]));
+    return;
+  }
+  long drow = epi_dest_row(e, row);
+  uint32_t packed[8];
+  if (e.mode == EPI_MASK_BF16) {
+    const uint4* a = reinterpret_cast<const uint4*>(e.act + drow * e.ldo + n0);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      uint4 m = __ldg(a + i);
+      uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float lo = __uint_as_float(r16[8 * i + 2 * k]), hi = __uint_as_float(r16[8 * i + 2 * k + 1]);
+        lo = bf16_lo(mw[k]) > 0.f ? lo : 0.f;
+        hi = bf16_hi(mw[k]) > 0.f ? hi : 0.f;
+        packed[4 * i + k] = pack_bf16x2(lo, hi);
+      }
+    }
+  } else {
+    const bool relu = (e.mode == EPI_BIAS_RELU_BF16);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float lo = __uint_as_float(r16[2 * i]) * e.scale + __ldg(e.bias + n0 + 2 * i);
+      float hi = __uint_as_float(r16[2 * i + 1]) * e.scale + __ldg(e.bias + n0 + 2 * i + 1);
+      if (relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+      packed[i] = pack_bf16x2(lo, hi);
+    }
+  }
+  uint4* dst = reinterpret_cast<uint4*>(e.out + drow * e.ldo + n0);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+}
+
+// ---------------------------------------------------------------------------
+// rowgemm: D[128 x BN] = A[128 x K] * B^T
+//   B K-major : weights [Ntot][ldb] row-major (ldb = K), tile rows n0..n0+BN
+//   B N-major : matrix  [K][ldb]   row-major (ldb = Ntot), tile cols n0..n0+BN (BN multiple of 64)
+// grid = (ceil(M/128), Ntot/BN, splits); each split covers kb_per_split k-blocks.
+// ---------------------------------------------------------------------------
+template <int BN>
+struct RowGemmCfg {
+  static constexpr int STAGES = (BN <= 64) ? 4 : 3;
+  static constexpr int A_BYTES = 128 * 128;      // 128 rows x 64 bf16
+  static constexpr int B_BYTES = BN * 128;       // BN rows x 64 bf16 (either major)
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+};
+
+struct WeightSrc {
+  const __nv_bfloat16* w;
+  long ldb;
+  int kdim;  // rows available along K (N-major) / unused (K-major)
+};
+
+template <class ALoad, bool B_NMAJOR, int BN>
+__global__ void __launch_bounds__(kGemmThreads) rowgemm_kernel(ALoad aload, WeightSrc bsrc, RowEpi epi,
+                                                               int num_kb, int kb_per_split) {
+  using Cfg = RowGemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  // barriers: full[s] @ +8*s, empty[s] @ +8*(STAGES+s), tmem_full @ +8*2*STAGES, tmem ptr @ +8*2*STAGES+8
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * Cfg::STAGES);
+  const uint32_t tmem_ptr_addr = tmem_full_bar + 8u;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int m0 = blockIdx.x * 128;
+  const int n0 = blockIdx.y * BN;
+  const int split = blockIdx.z;
+  const int kb0 = split * kb_per_split;
+  const int kb1 = min(num_kb, kb0 + kb_per_split);
+  const int niter = kb1 - kb0;
+
+  if (tid == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar(s), kProducerThreads);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == kProducerWarps) tmem_alloc(tmem_ptr_addr, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+
+  if (warp < kProducerWarps) {
+    // ===================== producers =====================
+    aload.prepare(m0, tid);
+    for (int it = 0; it < niter; ++it) {
+      const int s = it % Cfg::STAGES;
+      const uint32_t ph = (it / Cfg::STAGES) & 1;
+      mbar_wait(empty_bar(s), ph ^ 1, 1);
+      const uint32_t a_tile = smem_base + s * Cfg::STAGE_BYTES;
+      const uint32_t b_tile = a_tile + Cfg::A_BYTES;
+      const int kb = kb0 + it;
+      aload.fill(a_tile, kb, tid);
+      if (!B_NMAJOR) {
+        fill_dense<BN, 128>(b_tile, bsrc.w, bsrc.ldb, n0, 1 << 30, kb * kBK, tid);
+      } else {
+#pragma unroll
+        for (int at = 0; at < BN / 64; ++at)
+          fill_dense<64, 128>(b_tile + at * 8192, bsrc.w, bsrc.ldb, kb * kBK, bsrc.kdim, n0 + at * 64, tid);
+      }
+      fence_proxy_async();
+      mbar_arrive(full_bar(s));
+    }
+    // ===================== epilogue =====================
+    if (niter > 0) {
+      mbar_wait(tmem_full_bar, 0, 2);
+      tc_fence_after();
+      const int q = warp & 3;
+      const int half = warp >> 2;
+      const int row = m0 + q * 32 + (tid & 31);
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+      if constexpr (BN >= 64) {
+        constexpr int COLS_PER_WARP = BN / 2;
+#pragma unroll
+        for (int c = 0; c < COLS_PER_WARP; c += 32) {
+          uint32_t r[32];
+          tmem_ld32(lane_addr + half * COLS_PER_WARP + c, r);
+          tmem_ld_wait();
+          epi_store32(epi, row, n0 + half * COLS_PER_WARP + c, r, split);
+        }
+      } else {
+        uint32_t r16[16];
+        tmem_ld16(lane_addr + half * 16, r16);
+        tmem_ld_wait();
+        epi_store16(epi, row, n0 + half * 16, r16, split);
+      }
+      tc_fence_before();
+    }
+  } else if (tid == kProducerThreads) {
+    // ===================== MMA issuer (one thread) =====================
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, B_NMAJOR ? 1 : 0);
+    for (int it = 0; it < niter; ++it) {
+      const int s = it % Cfg::STAGES;
+      const uint32_t ph = (it / Cfg::STAGES) & 1;
+      mbar_wait(full_bar(s), ph, 3);
+      tc_fence_after();
+      const uint32_t a_tile = smem_base + s * Cfg::STAGE_BYTES;
+      const uint32_t b_tile = a_tile + Cfg::A_BYTES;
+#pragma unroll
+      for (int k = 0; k < kBK / 16; ++k) {
+        uint64_t adesc = make_smem_desc(a_tile + k * 32, 16, 1024, 2);
+        uint64_t bdesc = B_NMAJOR ? make_smem_desc(b_tile + k * 2048, 8192, 1024, 2)
+                                  : make_smem_desc(b_tile + k * 32, 16, 1024, 2);
+        umma_bf16(tmem_base, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
+      }
+      umma_commit(empty_bar(s));
+    }
+    if (niter > 0) umma_commit(tmem_full_bar);
+  }
+  __syncthreads();
+  if (warp == kProducerWarps) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// wgrad: D[K' x BN] = sum over rows of A[row, K']^T * dY[row, BN]
+//   A tiles: [64 rows x 64 k'] atoms filled by the same loaders as the forward pass
+//            (MN-major for the MMA: k' is the contiguous dimension)
+//   B tile : [64 rows x BN] from the row-major dY (N-major); BN*2 bytes per row
+//            (32/64/128-byte rows -> SW32/64/128; wider rows split into 64-column atoms)
+// One CTA owns MT consecutive 128-row M-tiles of K' (starting at blockIdx.x*MT), BN columns
+// starting at blockIdx.y*BN, and the row range of split blockIdx.z.
+// ---------------------------------------------------------------------------
+struct WgradEpi {
+  float* out;        // fp32 destination
+  int mode;          // 0: partial[split][Kp][ldo]  1: FC direct (row map k'=(hw*C+c) -> c*HW+hw)
+  int Kvalid;        // valid k' rows
+  int Kp;            // padded rows of the partial buffer
+  int ldo;           // row pitch (floats)
+  int fc_C, fc_HW;   // mode 1 row permutation
+};
+
+template <int MT, int BN>
+struct WgradCfg {
+  static constexpr int ROWB = (BN * 2 >= 128) ? 128 : BN * 2;  // bytes per B smem row
+  static constexpr int B_ATOMS = (BN * 2 + 127) / 128;
+  static constexpr int A_BYTES = MT * 2 * 8192;                // MT*2 atoms of [64 x 128B]
+  static constexpr int B_BYTES = 64 * BN * 2;
+  static constexpr int STAGE_BYTES = ((A_BYTES + B_BYTES + 1023) / 1024) * 1024;
+  static constexpr int STAGES = (STAGE_BYTES * 4 <= 200 * 1024) ? 4 : (STAGE_BYTES * 3 <= 200 * 1024) ? 3 : 2;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int ACC_COLS = MT * BN;
+  static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
+  static_assert(ACC_COLS <= 512, "accumulator does not fit TMEM");
+};
+
+template <class ALoad64, int MT, int BN>
+__global__ void __launch_bounds__(kGemmThreads) wgrad_kernel(ALoad64 aload, const __nv_bfloat16* __restrict__ dy,
+                                                             int ld_dy, int nrows, int rows_per_split,
+                                                             int k_atoms_total, WgradEpi epi) {
+  using Cfg = WgradCfg<MT, BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * Cfg::STAGES);
+  const uint32_t tmem_ptr_addr = tmem_full_bar + 8u;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int atom0 = blockIdx.x * MT * 2;          // first k' atom (64 wide) of this CTA
+  const int n0 = blockIdx.y * BN;
+  const int split = blockIdx.z;
+  const int r_begin = split * rows_per_split;
+  const int r_end = min(nrows, r_begin + rows_per_split);
+  const int niter = (r_end > r_begin) ? (r_end - r_begin + 63) / 64 : 0;
+  const int natoms = min(MT * 2, k_atoms_total - atom0);  // atoms that exist (the rest alias atom 0)
+
+  if (tid == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar(s), kProducerThreads);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == kProducerWarps) tmem_alloc(tmem_ptr_addr, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+
+  if (warp < kProducerWarps) {
+    for (int it = 0; it < niter; ++it) {
+      const int s = it % Cfg::STAGES;
+      const uint32_t ph = (it / Cfg::STAGES) & 1;
+      mbar_wait(empty_bar(s), ph ^ 1, 4);
+      const uint32_t a_tile = smem_base + s * Cfg::STAGE_BYTES;
+      const uint32_t b_tile = a_tile + Cfg::A_BYTES;
+      const int row0 = r_begin + it * 64;
+      // rows beyond r_end must contribute zero: the loaders zero rows >= their nrows, and the
+      // split boundary is enforced on the dY side (zero rows => zero products).
+      aload.prepare(row0, tid);
+      for (int at = 0; at < natoms; ++at) aload.fill(a_tile + at * 8192, atom0 + at, tid);
+      if constexpr (Cfg::B_ATOMS == 1) {
+        fill_dense<64, Cfg::ROWB>(b_tile, dy, ld_dy, row0, r_end, n0, tid);
+      } else {
+#pragma unroll
+        for (int at = 0; at < Cfg::B_ATOMS; ++at)
+          fill_dense<64, 128>(b_tile + at * 8192, dy, ld_dy, row0, r_end, n0 + at * 64, tid);
+      }
+      fence_proxy_async();
+      mbar_arrive(full_bar(s));
+    }
+    if (niter > 0) {
+      mbar_wait(tmem_full_bar, 0, 5);
+      tc_fence_after();
+    }
+    const int q = warp & 3;
+    const int half = warp >> 2;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    constexpr int COLS_PER_WARP = BN / 2;
+#pragma unroll 1
+    for (int mt = 0; mt < MT; ++mt) {
+      const int kprime = (atom0 + mt * 2) * 64 + q * 32 + (tid & 31);
+      // K' is a multiple of 64, so this predicate is warp-uniform; the tcgen05.ld below is still
+      // executed by every lane (it is .sync.aligned) and only the stores are guarded.
+      const bool row_ok = kprime < epi.Kvalid;
+      long orow;
+      if (epi.mode == 1) {
+        int hw = kprime / epi.fc_C;
+        int c = kprime - hw * epi.fc_C;
+        orow = (long)c * epi.fc_HW + hw;
+      } else {
+        orow = (long)split * epi.Kp + kprime;
+      }
+      float* dst = epi.out + orow * epi.ldo + n0 + half * COLS_PER_WARP;
+      if constexpr (COLS_PER_WARP >= 32) {
+#pragma unroll 1
+        for (int c = 0; c < COLS_PER_WARP; c += 32) {
+          uint32_t r[32];
+          if (niter > 0) {
+            tmem_ld32(lane_addr + mt * BN + half * COLS_PER_WARP + c, r);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = 0;
+          }
+          float4* d4 = reinterpret_cast<float4*>(dst + c);
+          if (row_ok)
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            d4[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+        }
+      } else {
+        uint32_t r16[16];
+        if (niter > 0) {
+          tmem_ld16(lane_addr + mt * BN + half * 16, r16);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r16[i] = 0;
+        }
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        if (row_ok)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          d4[i] = make_float4(__uint_as_float(r16[4 * i]), __uint_as_float(r16[4 * i + 1]),
+                              __uint_as_float(r16[4 * i + 2]), __uint_as_float(r16[4 * i + 3]));
+      }
+    }
+    tc_fence_before();
+  } else if (tid == kProducerThreads) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+    constexpr uint32_t b_layout = swz_layout_type(Cfg::ROWB);
+    constexpr uint32_t b_sbo = 8 * Cfg::ROWB;
+    constexpr uint32_t b_kstep = 16 * Cfg::ROWB;
+    for (int it = 0; it < niter; ++it) {
+      const int s = it % Cfg::STAGES;
+      const uint32_t ph = (it / Cfg::STAGES) & 1;
+      mbar_wait(full_bar(s), ph, 6);
+      tc_fence_after();
+      const uint32_t a_tile = smem_base + s * Cfg::STAGE_BYTES;
+      const uint32_t b_tile = a_tile + Cfg::A_BYTES;
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+        // a missing second atom (odd atom count) is left unfilled: its D rows are never stored
+        if (mt * 2 >= natoms) break;
+        const uint32_t a0 = a_tile + (mt * 2) * 8192;
+        const uint32_t lbo = 8192u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint64_t adesc = make_smem_desc(a0 + k * 2048, lbo, 1024, 2);
+          uint64_t bdesc = make_smem_desc(b_tile + k * b_kstep, 8192, b_sbo, b_layout);
+          umma_bf16(tmem_base + mt * BN, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+      }
+      umma_commit(empty_bar(s));
+    }
+    if (niter > 0) umma_commit(tmem_full_bar);
+  }
+  __syncthreads();
+  if (warp == kProducerWarps) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+}  // namespace arl

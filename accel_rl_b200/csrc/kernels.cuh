@@ -1,0 +1,978 @@
+// HBM-bound and reduction kernels of the rollout + A2C/PPO path (sm_100a):
+//   synthetic-emulator step + Atari frame pipeline, policy head (softmax, sampling, losses,
+//   head backward), GAE scan, gradient finalisation, global-norm clip + Adam/RMSProp, weight packing.
+// Reference semantics cited per kernel (paths relative to the reference tree).
+#pragma once
+#include "common.cuh"
+
+namespace arl {
+
+// ===========================================================================
+// Synthetic emulator ("SynthALE") — replaces atari_py.ALEInterface for benchmarks/parity.
+// Deterministic function of (env id, emulator frame counter); the oracle's fake ALE
+// (oracle/synth_ale.py) implements the identical rules on the CPU.
+// ===========================================================================
+struct SynthCfg {
+  int pool_frames;      // number of frames in the pool
+  int lives0;           // lives at reset_game (5)
+  int life_base;        // life period = life_base + (env * life_mul) % life_mod   [emulator frames]
+  int life_mul, life_mod;
+  int reward_mod;       // a frame pays when hash(env, f) % reward_mod == 0
+  int frame_stride;     // pool index = (env + frame_stride * f) % pool_frames
+};
+
+ARL_DEVINL uint32_t synth_hash(uint32_t e, uint32_t f) {
+  uint32_t h = e * 0x9E3779B1u + f * 0x85EBCA77u + 0x165667B1u;
+  h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+  return h;
+}
+ARL_DEVINL float synth_reward(const SynthCfg& c, int e, int f) {
+  uint32_t h = synth_hash((uint32_t)e, (uint32_t)f);
+  if (h % (uint32_t)c.reward_mod != 0) return 0.f;
+  uint32_t k = (h / (uint32_t)c.reward_mod) & 3u;
+  return k == 2 ? 4.f : (k == 3 ? -1.f : 1.f);
+}
+ARL_DEVINL int synth_life_period(const SynthCfg& c, int e) { return c.life_base + (e * c.life_mul) % c.life_mod; }
+ARL_DEVINL int synth_lives(const SynthCfg& c, int e, int f) {
+  int l = c.lives0 - f / synth_life_period(c, e);
+  return l < 0 ? 0 : l;
+}
+ARL_DEVINL int synth_frame_index(const SynthCfg& c, int e, int f) {
+  return (int)(((long)e + (long)c.frame_stride * f) % c.pool_frames);
+}
+
+// per-env emulator + AtariEnv + collector state (struct of arrays in one int/float block)
+struct EnvState {
+  int* f;            // emulator frame counter since reset_game
+  int* lives_seen;   // AtariEnv._lives
+  int* need_reset;   // NonResetCollector: env finished earlier in this batch (not stepped again)
+  int* traj_len;     // TrajInfo.Length
+  float* traj_ret;   // Return (clipped)
+  float* traj_raw;   // RawReturn
+  int* traj_nz;      // NonzeroRewards
+  float* traj_disc;  // DiscountedReturn
+  float* traj_cur;   // _cur_discount
+};
+
+struct TrajOut {     // completed-episode records, appended with an atomic cursor
+  int* count;        // [1]
+  int cap;
+  int* env;          // [cap]
+  int* len;
+  float* ret;
+  float* raw;
+  int* nz;
+  float* disc;
+};
+
+// what the frame kernel must do for each env this step
+struct FrameCmd {
+  int src_a;   // pool index of raw frame 1 (or -1: zeros)
+  int src_b;   // pool index of raw frame 2
+  int flags;   // bit0: zero the older planes (reset / life loss), bit1: skip (env not stepped)
+};
+
+// One thread per env.  Mirrors AtariEnv.step (envs/atari_env.py:65-78), _done_episodic_lives
+// (:185-191), reset (:93-100) and ResetCollector/NonResetCollector.collect
+// (sampler/act_server/alternating/overlap/worker.py:25-113) for step s of the batch.
+__global__ void env_step_kernel(SynthCfg cfg, EnvState st, TrajOut tout, FrameCmd* __restrict__ cmd,
+                                float* __restrict__ rewards, uint8_t* __restrict__ dones,
+                                float* __restrict__ raw_reward, uint8_t* __restrict__ info_need_reset,
+                                int n_envs, int T, int s, int max_path_length, float discount,
+                                int mid_batch_reset, int clip_reward, int episodic_lives) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_envs) return;
+  FrameCmd c;
+  c.flags = 0;
+  if (!mid_batch_reset && st.need_reset[e]) {
+    c.src_a = c.src_b = -1;
+    c.flags = 2;  // stale rows stay as they are (worker.py:78 `if not need_reset[i]`)
+    cmd[e] = c;
+    return;
+  }
+  int f = st.f[e];
+  float r = 0.f;
+  r += synth_reward(cfg, e, f + 1);
+  r += synth_reward(cfg, e, f + 2);
+  r += synth_reward(cfg, e, f + 3);
+  f += 3;
+  c.src_a = synth_frame_index(cfg, e, f);   // _get_screen(1) after the 3rd repeat
+  f += 1;
+  r += synth_reward(cfg, e, f);
+  c.src_b = synth_frame_index(cfg, e, f);   // _get_screen(2) in _update_obs
+  float raw = r;
+  if (clip_reward) r = (r > 0.f) ? 1.f : (r < 0.f ? -1.f : 0.f);
+  // _done_*: game_over first, then life check
+  int lives = synth_lives(cfg, e, f);
+  bool game_over = (lives == 0);
+  bool lost_life = (lives < st.lives_seen[e]) && (lives > 0);
+  if (lost_life) {
+    f += 2;  // _life_reset: act(0), act(FIRE)
+    st.lives_seen[e] = synth_lives(cfg, e, f);
+    if (episodic_lives) {
+      c.src_a = -1;                       // _reset_obs zeroes raw frames and the stack
+      c.src_b = synth_frame_index(cfg, e, f);
+      c.flags |= 1;
+    }
+  }
+  bool done = episodic_lives ? (lost_life || game_over) : game_over;
+  bool need_reset_info = game_over;       // only reported under episodic_lives (info["need_reset"])
+  // TrajInfo.step (sampler/util.py:92-98)
+  int len = st.traj_len[e] + 1;
+  float tret = st.traj_ret[e] + r;
+  float traw = st.traj_raw[e] + (clip_reward ? raw : r);
+  int tnz = st.traj_nz[e] + (r != 0.f ? 1 : 0);
+  float cur = st.traj_cur[e];
+  float tdisc = st.traj_disc[e] + cur * r;
+  cur *= discount;
+  bool over_length = len > max_path_length;
+  bool env_says_reset = episodic_lives ? need_reset_info : true;   // env_info.get("need_reset", True)
+  if (over_length || (done && env_says_reset)) {
+    done = true;
+    if (over_length && episodic_lives) need_reset_info = true;
+    int slot = atomicAdd(tout.count, 1);
+    if (slot < tout.cap) {
+      tout.env[slot] = e; tout.len[slot] = len; tout.ret[slot] = tret; tout.raw[slot] = traw;
+      tout.nz[slot] = tnz; tout.disc[slot] = tdisc;
+    }
+    len = 0; tret = 0.f; traw = 0.f; tnz = 0; tdisc = 0.f; cur = 1.f;
+    if (mid_batch_reset) {
+      // env.reset(): reset_game, _reset_obs, _life_reset (2 acts), 0 start no-ops, _update_obs
+      f = 2;
+      st.lives_seen[e] = synth_lives(cfg, e, f);
+      c.src_a = -1;
+      c.src_b = synth_frame_index(cfg, e, f);
+      c.flags |= 1;
+    } else {
+      st.need_reset[e] = 1;
+      c.flags |= 2;  // observation is NOT advanced (worker.py:91-95 else-branch skipped)
+    }
+  }
+  st.f[e] = f;
+  st.traj_len[e] = len; st.traj_ret[e] = tret; st.traj_raw[e] = traw; st.traj_nz[e] = tnz;
+  st.traj_disc[e] = tdisc; st.traj_cur[e] = cur;
+  long row = (long)e * T + s;
+  rewards[row] = r;
+  dones[row] = done ? 1 : 0;
+  if (clip_reward) raw_reward[row] = raw;
+  if (episodic_lives) info_need_reset[row] = need_reset_info ? 1 : 0;
+  cmd[e] = c;
+}
+
+// After the batch when mid_batch_reset == False: reset envs flagged need_reset
+// (worker.py:106-113 reset_needed_envs) — produces the first observation of the next batch.
+__global__ void env_reset_needed_kernel(SynthCfg cfg, EnvState st, FrameCmd* __restrict__ cmd, int n_envs) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_envs) return;
+  FrameCmd c;
+  if (st.need_reset[e]) {
+    st.need_reset[e] = 0;
+    st.f[e] = 2;
+    st.lives_seen[e] = synth_lives(cfg, e, 2);
+    c.src_a = -1; c.src_b = synth_frame_index(cfg, e, 2); c.flags = 1;
+  } else {
+    c.src_a = c.src_b = -1; c.flags = 2;
+  }
+  cmd[e] = c;
+}
+
+// initial env.reset() for every env (start_envs with max_decorrelation_steps == 0)
+__global__ void env_init_kernel(SynthCfg cfg, EnvState st, FrameCmd* __restrict__ cmd, int n_envs) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_envs) return;
+  st.f[e] = 2;
+  st.lives_seen[e] = synth_lives(cfg, e, 2);
+  st.need_reset[e] = 0;
+  st.traj_len[e] = 0; st.traj_ret[e] = 0.f; st.traj_raw[e] = 0.f; st.traj_nz[e] = 0;
+  st.traj_disc[e] = 0.f; st.traj_cur[e] = 1.f;
+  FrameCmd c;
+  c.src_a = -1; c.src_b = synth_frame_index(cfg, e, 2); c.flags = 1;
+  cmd[e] = c;
+}
+
+// ===========================================================================
+// Frame pipeline — AtariEnv._update_obs (envs/atari_env.py:151-157):
+//   m = max(raw1, raw2); crop rows 208,209; 2x2 box mean (a+b+c+d+2)>>2 (== cv2 INTER_LINEAR at
+//   an exact 2x shrink); obs = concat(obs[1:], img).  Stack planes oldest -> newest.
+// One work item = 16 output pixels of one env: 8 x 16-byte loads (2 frames x 2 rows x 32 B),
+// (P-1) x 16-byte plane shifts and P x 16-byte stores.  Items are flattened over all envs so
+// the grid is dense.  Raw frames come either from the resident pool (src index per env) or,
+// for the host-fed path, from a staging buffer [n_envs][2][210][160] (cmd.src_* >= 0 selects
+// slot 0/1 of the env's staging pair).
+// ===========================================================================
+constexpr int kRawH = 210, kRawW = 160, kObsH = 104, kObsW = 80;
+
+ARL_DEVINL uint32_t vmax4(uint32_t a, uint32_t b) { return __vmaxu4(a, b); }
+
+// horizontal pair sums of 4 bytes -> two 16-bit lanes: (b0+b1) | (b2+b3)<<16
+ARL_DEVINL uint32_t pair_sum(uint32_t v) { return (v & 0x00ff00ffu) + ((v >> 8) & 0x00ff00ffu); }
+
+// 16 output pixels (row oy, 16-pixel column group xc) of max(fa, fb) box-downsampled; null frame = zeros
+ARL_DEVINL uint4 frame_box16(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, int oy, int xc) {
+  const int roff = (2 * oy) * kRawW + xc * 32;
+  uint4 z = make_uint4(0, 0, 0, 0);
+  uint4 a00 = z, a01 = z, a10 = z, a11 = z, b00 = z, b01 = z, b10 = z, b11 = z;
+  if (fa) {
+    const uint4* p0 = reinterpret_cast<const uint4*>(fa + roff);
+    const uint4* p1 = reinterpret_cast<const uint4*>(fa + roff + kRawW);
+    a00 = __ldg(p0); a01 = __ldg(p0 + 1); a10 = __ldg(p1); a11 = __ldg(p1 + 1);
+  }
+  if (fb) {
+    const uint4* p0 = reinterpret_cast<const uint4*>(fb + roff);
+    const uint4* p1 = reinterpret_cast<const uint4*>(fb + roff + kRawW);
+    b00 = __ldg(p0); b01 = __ldg(p0 + 1); b10 = __ldg(p1); b11 = __ldg(p1 + 1);
+  }
+  uint32_t top[8] = {vmax4(a00.x, b00.x), vmax4(a00.y, b00.y), vmax4(a00.z, b00.z), vmax4(a00.w, b00.w),
+                     vmax4(a01.x, b01.x), vmax4(a01.y, b01.y), vmax4(a01.z, b01.z), vmax4(a01.w, b01.w)};
+  uint32_t bot[8] = {vmax4(a10.x, b10.x), vmax4(a10.y, b10.y), vmax4(a10.z, b10.z), vmax4(a10.w, b10.w),
+                     vmax4(a11.x, b11.x), vmax4(a11.y, b11.y), vmax4(a11.z, b11.z), vmax4(a11.w, b11.w)};
+  uint32_t outw[4];
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    // each input word holds 4 pixels -> 2 output pixels; two words -> 4 output pixels (one out word)
+    uint32_t s0 = pair_sum(top[2 * w]) + pair_sum(bot[2 * w]) + 0x00020002u;          // 2 sums (16-bit lanes)
+    uint32_t s1 = pair_sum(top[2 * w + 1]) + pair_sum(bot[2 * w + 1]) + 0x00020002u;
+    uint32_t o0 = (s0 >> 2) & 0x00ff00ffu;   // lanes: px0 | px1<<16
+    uint32_t o1 = (s1 >> 2) & 0x00ff00ffu;
+    outw[w] = (o0 & 0xffu) | ((o0 >> 16) << 8) | ((o1 & 0xffu) << 16) | ((o1 >> 16) << 24);
+  }
+  return make_uint4(outw[0], outw[1], outw[2], outw[3]);
+}
+
+__global__ void __launch_bounds__(256) frame_kernel(const uint8_t* __restrict__ pool, const uint8_t* __restrict__ staging,
+                                                    const FrameCmd* __restrict__ cmd, uint8_t* __restrict__ step_obs,
+                                                    uint8_t* __restrict__ roll_obs, int T, int s_next, int n_envs,
+                                                    int planes) {
+  // step_obs [n_envs][planes][104][80] is the sampler's step buffer (updated in place: each thread
+  // shifts its own 16 pixels of every plane); roll_obs row e*T + s_next receives a copy of the new
+  // stack (skipped when roll_obs == nullptr, i.e. after the last step of the batch).
+  constexpr int ITEMS_PER_ROW = kObsW / 16;             // 5
+  constexpr int ITEMS_PER_ENV = kObsH * ITEMS_PER_ROW;  // 520
+  long item = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= (long)n_envs * ITEMS_PER_ENV) return;
+  int e = (int)(item / ITEMS_PER_ENV);
+  int rem = (int)(item - (long)e * ITEMS_PER_ENV);
+  int oy = rem / ITEMS_PER_ROW;
+  int xc = rem - oy * ITEMS_PER_ROW;
+  FrameCmd c = cmd[e];
+  if (c.flags & 2) return;   // env not stepped: nothing is written (rows keep their stale contents)
+  const int plane_bytes = kObsH * kObsW;
+  const long obs_bytes = (long)planes * plane_bytes;
+  uint8_t* cur = step_obs + (long)e * obs_bytes;
+  uint8_t* dst = roll_obs ? roll_obs + ((long)e * T + s_next) * obs_bytes : nullptr;
+  const int pix = oy * kObsW + xc * 16;
+  // ---- new plane ----
+  const long fbytes = (long)kRawH * kRawW;
+  const uint8_t* fa = nullptr;
+  const uint8_t* fb = nullptr;
+  if (staging) {
+    if (c.src_a >= 0) fa = staging + ((long)e * 2 + 0) * fbytes;
+    if (c.src_b >= 0) fb = staging + ((long)e * 2 + 1) * fbytes;
+  } else {
+    if (c.src_a >= 0) fa = pool + (long)c.src_a * fbytes;
+    if (c.src_b >= 0) fb = pool + (long)c.src_b * fbytes;
+  }
+  uint4 z = make_uint4(0, 0, 0, 0);
+  const uint4 newest = frame_box16(fa, fb, oy, xc);
+  // ---- stack shift + store ----
+  uint4 keep[3] = {z, z, z};
+  if (!(c.flags & 1)) {
+    for (int p = 0; p < planes - 1 && p < 3; ++p)
+      keep[p] = *reinterpret_cast<const uint4*>(cur + (p + 1) * plane_bytes + pix);
+  }
+  for (int p = 0; p < planes - 1 && p < 3; ++p) {
+    *reinterpret_cast<uint4*>(cur + p * plane_bytes + pix) = keep[p];
+    if (dst) *reinterpret_cast<uint4*>(dst + p * plane_bytes + pix) = keep[p];
+  }
+  *reinterpret_cast<uint4*>(cur + (planes - 1) * plane_bytes + pix) = newest;
+  if (dst) *reinterpret_cast<uint4*>(dst + (planes - 1) * plane_bytes + pix) = newest;
+}
+
+// standalone frame update (arl_frame_update): item i's raw frames are raw_a[i], raw_b[i]
+__global__ void make_cmd_kernel(FrameCmd* cmd, const uint8_t* reset_mask, int n, int has_a) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  FrameCmd c;
+  bool rs = reset_mask && reset_mask[i];
+  c.src_a = (has_a && !rs) ? i : -1;
+  c.src_b = i;
+  c.flags = rs ? 1 : 0;
+  cmd[i] = c;
+}
+
+__global__ void __launch_bounds__(256) frame_pair_kernel(const uint8_t* __restrict__ raw_a, const uint8_t* __restrict__ raw_b,
+                                                         const FrameCmd* __restrict__ cmd, uint8_t* __restrict__ stack,
+                                                         int n, int planes) {
+  constexpr int ITEMS_PER_ROW = kObsW / 16;
+  constexpr int ITEMS_PER_ENV = kObsH * ITEMS_PER_ROW;
+  long item = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= (long)n * ITEMS_PER_ENV) return;
+  int e = (int)(item / ITEMS_PER_ENV);
+  int rem = (int)(item - (long)e * ITEMS_PER_ENV);
+  int oy = rem / ITEMS_PER_ROW;
+  int xc = rem - oy * ITEMS_PER_ROW;
+  FrameCmd c = cmd[e];
+  const long fbytes = (long)kRawH * kRawW;
+  const uint8_t* fa = (c.src_a >= 0 && raw_a) ? raw_a + (long)e * fbytes : nullptr;
+  const uint8_t* fb = raw_b + (long)e * fbytes;
+  uint4 newest = frame_box16(fa, fb, oy, xc);
+  const int plane_bytes = kObsH * kObsW;
+  uint8_t* cur = stack + (long)e * planes * plane_bytes;
+  const int pix = oy * kObsW + xc * 16;
+  uint4 z = make_uint4(0, 0, 0, 0);
+  uint4 keep[3] = {z, z, z};
+  if (!(c.flags & 1))
+    for (int p = 0; p < planes - 1 && p < 3; ++p) keep[p] = *reinterpret_cast<const uint4*>(cur + (p + 1) * plane_bytes + pix);
+  for (int p = 0; p < planes - 1 && p < 3; ++p) *reinterpret_cast<uint4*>(cur + p * plane_bytes + pix) = keep[p];
+  *reinterpret_cast<uint4*>(cur + (planes - 1) * plane_bytes + pix) = newest;
+}
+
+// rows copy: dst[drows[i]] = src[srows[i]] (row_bytes multiple of 16)
+__global__ void copy_rows_kernel(const uint8_t* __restrict__ src, long sstride, const int* __restrict__ srows,
+                                 uint8_t* __restrict__ dst, long dstride, const int* __restrict__ drows, int n,
+                                 int row_bytes) {
+  int per = row_bytes / 16;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)n * per) return;
+  int r = (int)(i / per);
+  int c = (int)(i - (long)r * per);
+  long sr = srows ? srows[r] : r, dr = drows ? drows[r] : r;
+  reinterpret_cast<uint4*>(dst + dr * dstride)[c] = __ldg(reinterpret_cast<const uint4*>(src + sr * sstride) + c);
+}
+
+// row index tables for step s: rows[e] = e*T + s
+__global__ void fill_rows_kernel(int* __restrict__ rows, int n, int T, int s) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) rows[e] = e * T + s;
+}
+
+// ===========================================================================
+// Policy head.  One warp per sample row.
+//   h = relu(fc_bias + sum_splits partial)  (rounded to bf16: the value the backward pass sees)
+//   pi = softmax(h Wpi + bpi), V = h Wv + bv        (policies/pg/networks/pg_cnn.py:70-86)
+// mode 0 (rollout): write prob/value, sample the action
+//     weighted_sample_n (rllab/misc/special.py:22-27): k = #{j : f64(cumsum_f32(p)_j) < u}; a = min(k, A-1)
+// mode 1 (train): PPO / A2C losses and their gradient w.r.t. logits, V and h
+//     (algos/pg/aac_base.py:60-70, ppo.py:42-51, a2c.py:43-46, distributions/categorical.py:35-88)
+// ===========================================================================
+constexpr int kMaxActions = 18;
+
+struct HeadParams {
+  const float* partial;     // [splits][M][H]
+  int splits, M, H, A;
+  const float* fc_bias;     // [H]
+  const float* w_pi;        // [H][A]
+  const float* b_pi;        // [A]
+  const float* w_v;         // [H]
+  const float* b_v;         // [1]
+  // rollout outputs (row -> out_rows[row] or row)
+  const int* out_rows;
+  float* prob;              // [N][A]
+  float* value;             // [N]
+  uint8_t* actions;         // [N]
+  const double* uniforms;   // [M]
+  // train inputs (gathered through idx)
+  const int* idx;           // rows of the rollout buffer: sample row reads idx[off*M + row]
+  const int* idx_off;       // optional device scalar `off` (minibatch index)
+  const uint8_t* act_in;    // [N]
+  const float* adv;         // [N]
+  const float* ret;         // [N]
+  const float* old_prob;    // [N][A]
+  const int8_t* valids;     // [N] or nullptr
+  const float* hyper;       // device scalars: [0]=lr_mult (PPO clip scales with it)
+  int algo;                 // 0 = PPO, 1 = A2C
+  float clip_param, v_coeff, ent_coeff;
+  float inv_count;          // 1/M when valids == nullptr
+  const float* valid_count; // device scalar sum(valids) (when valids != nullptr)
+  // train outputs
+  __nv_bfloat16* h_out;     // [M][H] post-ReLU hidden (bf16)
+  __nv_bfloat16* dh_out;    // [M][H] gradient w.r.t. FC pre-activation (bf16)
+  float* dlogit_out;        // [M][A+1]  (last column: dV)
+  float* loss_partial;      // [gridDim.x][4]  pi, v, ent, total per block
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) head_kernel(HeadParams p) {
+  extern __shared__ float sm_head[];   // w_pi [H*A], w_v [H], b_pi[A], b_v, fc_bias[H]
+  float* s_wpi = sm_head;
+  float* s_wv = s_wpi + p.H * p.A;
+  float* s_bpi = s_wv + p.H;
+  float* s_fcb = s_bpi + kMaxActions + 2;
+  for (int i = threadIdx.x; i < p.H * p.A; i += blockDim.x) s_wpi[i] = p.w_pi[i];
+  for (int i = threadIdx.x; i < p.H; i += blockDim.x) { s_wv[i] = p.w_v[i]; s_fcb[i] = p.fc_bias[i]; }
+  if (threadIdx.x < p.A) s_bpi[threadIdx.x] = p.b_pi[threadIdx.x];
+  if (threadIdx.x == 0) s_bpi[kMaxActions] = p.b_v[0];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  float loss_pi = 0.f, loss_v = 0.f, loss_ent = 0.f;
+  const int JP = (p.H + 31) / 32;   // h values per lane (<= 16 for H <= 512)
+  for (int row = blockIdx.x * wpb + warp; row < p.M; row += gridDim.x * wpb) {
+    float h[16];
+    float logit[kMaxActions];
+#pragma unroll
+    for (int a = 0; a < kMaxActions; ++a) logit[a] = 0.f;
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      h[i] = 0.f;
+      int j = lane + 32 * i;
+      if (i < JP && j < p.H) {
+        float acc = s_fcb[j];
+        for (int s = 0; s < p.splits; ++s) acc += p.partial[((long)s * p.M + row) * p.H + j];
+        acc = fmaxf(acc, 0.f);
+        acc = __bfloat162float(__float2bfloat16_rn(acc));
+        h[i] = acc;
+        v += acc * s_wv[j];
+#pragma unroll
+        for (int a = 0; a < kMaxActions; ++a)
+          if (a < p.A) logit[a] += acc * s_wpi[j * p.A + a];
+      }
+    }
+    v = warp_sum(v) + s_bpi[kMaxActions];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int a = 0; a < kMaxActions; ++a)
+      if (a < p.A) {
+        logit[a] = warp_sum(logit[a]) + s_bpi[a];
+        mx = fmaxf(mx, logit[a]);
+      }
+    float prob[kMaxActions];
+    float sum = 0.f;
+#pragma unroll
+    for (int a = 0; a < kMaxActions; ++a) {
+      prob[a] = 0.f;
+      if (a < p.A) { prob[a] = expf(logit[a] - mx); sum += prob[a]; }
+    }
+#pragma unroll
+    for (int a = 0; a < kMaxActions; ++a) prob[a] = prob[a] / sum;
+
+    if (MODE == 0) {
+      long orow = p.out_rows ? p.out_rows[row] : row;
+      if (lane == 0) {
+        if (p.prob) {
+#pragma unroll
+          for (int a = 0; a < kMaxActions; ++a)
+            if (a < p.A) p.prob[orow * p.A + a] = prob[a];
+        }
+        if (p.value) p.value[orow] = v;
+        if (p.actions) {
+          double u = p.uniforms[row];
+          float cs = 0.f;
+          int k = 0;
+#pragma unroll
+          for (int a = 0; a < kMaxActions; ++a)
+            if (a < p.A) { cs = __fadd_rn(cs, prob[a]); k += ((double)cs < u) ? 1 : 0; }
+          p.actions[orow] = (uint8_t)min(k, p.A - 1);
+        }
+      }
+    } else {
+      const long src = p.idx ? p.idx[(p.idx_off ? (long)p.idx_off[0] * p.M : 0) + row] : row;
+      const int act = p.act_in[src];
+      const float adv = p.adv[src], ret = p.ret[src];
+      float w = p.inv_count;
+      if (p.valids) w = p.valids[src] ? (1.f / p.valid_count[0]) : 0.f;
+      const float TINY = 1e-8f;
+      float g[kMaxActions];   // dL/dprob
+      float ent = 0.f;
+      float pa = 0.f;
+#pragma unroll
+      for (int a = 0; a < kMaxActions; ++a) {
+        g[a] = 0.f;
+        if (a < p.A) {
+          float lp = logf(prob[a] + TINY);
+          ent -= prob[a] * lp;
+          g[a] = p.ent_coeff * w * (lp + prob[a] / (prob[a] + TINY));
+          if (a == act) pa = prob[a];
+        }
+      }
+      float l_pi;
+      float gact;
+      if (p.algo == 0) {
+        float po = p.old_prob[src * p.A + act];
+        float ratio = (pa + TINY) / (po + TINY);
+        float cp = p.clip_param * p.hyper[0];
+        float lo = 1.f - cp, hi = 1.f + cp;
+        float clipped = fminf(fmaxf(ratio, lo), hi);
+        float s1 = ratio * adv, s2 = clipped * adv;
+        l_pi = -fminf(s1, s2);
+        float gr;
+        if (ratio < lo) gr = (adv >= 0.f) ? adv : 0.f;
+        else if (ratio > hi) gr = (adv <= 0.f) ? adv : 0.f;
+        else gr = adv;
+        gact = -w * gr / (po + TINY);
+      } else {
+        l_pi = -logf(pa + TINY) * adv;
+        gact = -w * adv / (pa + TINY);
+      }
+#pragma unroll
+      for (int a = 0; a < kMaxActions; ++a)
+        if (a == act) g[a] += gact;
+      float verr = v - ret;
+      float dv = 2.f * p.v_coeff * w * verr;
+      float dot = 0.f;
+#pragma unroll
+      for (int a = 0; a < kMaxActions; ++a) dot += prob[a] * g[a];
+      float dl[kMaxActions];
+#pragma unroll
+      for (int a = 0; a < kMaxActions; ++a) dl[a] = prob[a] * (g[a] - dot);
+      if (lane == 0) {
+        loss_pi += w * l_pi;
+        loss_v += p.v_coeff * w * verr * verr;
+        loss_ent += -p.ent_coeff * w * ent;
+#pragma unroll
+        for (int a = 0; a < kMaxActions; ++a)
+          if (a < p.A) p.dlogit_out[(long)row * (p.A + 1) + a] = dl[a];
+        p.dlogit_out[(long)row * (p.A + 1) + p.A] = dv;
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        int j = lane + 32 * i;
+        if (i < JP && j < p.H) {
+          float d = dv * s_wv[j];
+#pragma unroll
+          for (int a = 0; a < kMaxActions; ++a)
+            if (a < p.A) d += dl[a] * s_wpi[j * p.A + a];
+          d = (h[i] > 0.f) ? d : 0.f;
+          p.h_out[(long)row * p.H + j] = __float2bfloat16_rn(h[i]);
+          p.dh_out[(long)row * p.H + j] = __float2bfloat16_rn(d);
+        }
+      }
+    }
+  }
+  if (MODE == 1) {
+    __shared__ float s_l[3][8];
+    if (lane == 0) { s_l[0][warp] = loss_pi; s_l[1][warp] = loss_v; s_l[2][warp] = loss_ent; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float a = 0.f, b = 0.f, c = 0.f;
+      for (int w2 = 0; w2 < wpb; ++w2) { a += s_l[0][w2]; b += s_l[1][w2]; c += s_l[2][w2]; }
+      float* o = p.loss_partial + 4 * blockIdx.x;
+      o[0] = a; o[1] = b; o[2] = c; o[3] = a + b + c;
+    }
+  }
+}
+
+// Head weight gradients + FC bias gradient, partial over row groups (deterministic 2-stage).
+//   out[g][j][0..A-1] = sum_rows h[row][j]*dlogit[row][a];  [A] = sum h*dV;  [A+1] = sum dh[row][j]
+// plus (block j-group 0 only) out_b[g][0..A] = sum_rows dlogit[row][:] (bias grads of pi, v).
+__global__ void __launch_bounds__(128) head_wgrad_kernel(const __nv_bfloat16* __restrict__ h,
+                                                          const __nv_bfloat16* __restrict__ dh,
+                                                          const float* __restrict__ dlogit, int M, int H, int A,
+                                                          int rows_per_group, float* __restrict__ out,
+                                                          float* __restrict__ out_b) {
+  extern __shared__ float s_dl[];   // [rows_per_group][A+1]
+  const int g = blockIdx.y;
+  const int r0 = g * rows_per_group;
+  const int r1 = min(M, r0 + rows_per_group);
+  const int A1 = A + 1;
+  for (int i = threadIdx.x; i < (r1 - r0) * A1; i += blockDim.x) s_dl[i] = dlogit[(long)r0 * A1 + i];
+  __syncthreads();
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < H) {
+    float acc[kMaxActions + 2];
+#pragma unroll
+    for (int a = 0; a < kMaxActions + 2; ++a) acc[a] = 0.f;
+    for (int r = r0; r < r1; ++r) {
+      float hv = __bfloat162float(h[(long)r * H + j]);
+      float dv = __bfloat162float(dh[(long)r * H + j]);
+      const float* dl = s_dl + (r - r0) * A1;
+#pragma unroll
+      for (int a = 0; a < kMaxActions + 1; ++a)
+        if (a < A1) acc[a] += hv * dl[a];
+      acc[kMaxActions + 1] += dv;
+    }
+    float* o = out + ((long)g * H + j) * (A + 2);
+    for (int a = 0; a < A1; ++a) o[a] = acc[a];
+    o[A1] = acc[kMaxActions + 1];
+  }
+  if (blockIdx.x == 0 && threadIdx.x < A1) {
+    float s = 0.f;
+    for (int r = r0; r < r1; ++r) s += s_dl[(r - r0) * A1 + threadIdx.x];
+    out_b[g * A1 + threadIdx.x] = s;
+  }
+}
+
+// column sums of a bf16 [rows][C] matrix over row groups: out[g][c]
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, int rows, int C,
+                                                      int rows_per_group, float* __restrict__ out) {
+  // block = (C/2 column pairs) x (256 / (C/2)) row lanes
+  const int cp = C >> 1;
+  const int lanes = blockDim.x / cp;
+  const int c2 = threadIdx.x % cp;
+  const int rl = threadIdx.x / cp;
+  const int g = blockIdx.x;
+  const int r0 = g * rows_per_group;
+  const int r1 = min(rows, r0 + rows_per_group);
+  float a0 = 0.f, a1 = 0.f;
+  if (rl < lanes) {
+    for (int r = r0 + rl; r < r1; r += lanes) {
+      uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(x + (long)r * C) + c2);
+      a0 += bf16_lo(v);
+      a1 += bf16_hi(v);
+    }
+  }
+  __shared__ float s[256][2];
+  s[threadIdx.x][0] = a0; s[threadIdx.x][1] = a1;
+  __syncthreads();
+  if (threadIdx.x < cp) {
+    float t0 = 0.f, t1 = 0.f;
+    for (int l = 0; l < lanes; ++l) { t0 += s[l * cp + threadIdx.x][0]; t1 += s[l * cp + threadIdx.x][1]; }
+    out[(long)g * C + 2 * threadIdx.x] = t0;
+    out[(long)g * C + 2 * threadIdx.x + 1] = t1;
+  }
+}
+
+// ===========================================================================
+// Gradient finalisation: sum split partials and scatter into the flat fp32 gradient in the
+// reference's parameter order (rllab/core/parameterized.py:74-88; Lasagne W (out,in,kh,kw),
+// flip_filters=True so correlation tap (ky,kx) is W[..., kh-1-ky, kw-1-kx]).
+// ===========================================================================
+enum GradMap { GM_LINEAR = 0, GM_CONV_NHWC = 1, GM_CONV_CHW = 2, GM_HEAD = 3 };
+
+struct GradJob {
+  const float* src;   // [S][rows_pad][ld]
+  int S;              // number of partials
+  long sstride;       // elements between partials
+  int rows, cols, ld; // logical extent of one partial (rows = k' or j, cols = cout ...)
+  int map;
+  float scale;
+  long dst_off;       // offset into flat grad
+  // conv maps: k' -> (c, ky, kx)
+  int C, kh, kw;
+  // GM_HEAD: src [S][H][A+2]; writes w_pi (H,A) at dst_off, w_v (H) at dst_off2, fc bias (H) at dst_off3
+  long dst_off2, dst_off3;
+  int A;
+};
+
+__global__ void __launch_bounds__(256) finalize_grads_kernel(const GradJob* __restrict__ jobs, float* __restrict__ grad) {
+  const GradJob jb = jobs[blockIdx.y];
+  const long total = (long)jb.rows * jb.cols;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int r = (int)(i / jb.cols);
+    int c = (int)(i - (long)r * jb.cols);
+    float acc = 0.f;
+    const float* s = jb.src + (long)r * jb.ld + c;
+    for (int k = 0; k < jb.S; ++k) acc += s[k * jb.sstride];
+    acc *= jb.scale;
+    if (jb.map == GM_LINEAR) {
+      grad[jb.dst_off + i] = acc;
+    } else if (jb.map == GM_CONV_NHWC) {
+      // r = k' = (ky*kw + kx)*C + ci ; c = cout
+      int ci = r % jb.C;
+      int t = r / jb.C;
+      int kx = t % jb.kw, ky = t / jb.kw;
+      grad[jb.dst_off + (((long)c * jb.C + ci) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx)] = acc;
+    } else if (jb.map == GM_CONV_CHW) {
+      // r = k' = (ci*kh + ky)*kw + kx
+      int kx = r % jb.kw;
+      int t = r / jb.kw;
+      int ky = t % jb.kh, ci = t / jb.kh;
+      grad[jb.dst_off + (((long)c * jb.C + ci) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx)] = acc;
+    } else {  // GM_HEAD: r = j, c in [0, A+2)
+      if (c < jb.A) grad[jb.dst_off + (long)r * jb.A + c] = acc;
+      else if (c == jb.A) grad[jb.dst_off2 + r] = acc;
+      else grad[jb.dst_off3 + r] = acc;
+    }
+  }
+}
+
+// ===========================================================================
+// Global-norm clip + update.  optimizers/util.py:70-76 (Lasagne total_norm_constraint, eps 1e-7),
+// update rules: optimizers/update_methods_stats.py:11-32 (rmsprop), :55-87 (adam).
+//   sumsq_kernel : fixed grid, per-block partial sums of g^2 (double), no atomics
+//   update_kernel: every block re-reduces the partials (identical result in every block),
+//                  applies avg -> clip -> Adam/RMSProp; block 0 records grad_norm and loss.
+// ===========================================================================
+constexpr int kSumsqBlocks = 592;   // 4 x 148
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long n, float gscale,
+                                                     double* __restrict__ partial) {
+  double acc = 0.0;
+  const long n4 = n >> 2;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    float4 v = g4[i];
+    float a = v.x * gscale, b = v.y * gscale, c = v.z * gscale, d = v.w * gscale;
+    acc += (double)(a * a + b * b) + (double)(c * c + d * d);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long i = n4 << 2; i < n; ++i) { float a = g[i] * gscale; acc += (double)a * a; }
+  __shared__ double s[8];
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s[w];
+    partial[blockIdx.x] = t;
+  }
+}
+
+struct UpdateParams {
+  float* param; const float* grad; float* m; float* v;
+  long n;
+  const double* sumsq_partial; int n_partial;
+  const float* loss_partial; int n_loss_blocks;   // [blocks][4]
+  const float* hyper;      // [0] = lr_mult
+  int* step;               // Adam t (device counter, incremented by block 0)
+  int kind;                // 0 = Adam, 1 = RMSProp
+  float lr, beta1, beta2, eps, rho;
+  float clip;              // <= 0: no clipping (norm still reported)
+  float gscale;            // gradient averaging factor (1/n_gpu for sync DP)
+  float* out_norm; float* out_loss;   // [cap] logs, slot = log_slot[0]
+  int* log_slot; int log_cap;
+};
+
+__global__ void __launch_bounds__(256) update_kernel(UpdateParams p) {
+  __shared__ double s_red[8];
+  __shared__ float s_scale, s_alpha;
+  // every block: reduce the partial sums in the same order -> identical norm everywhere
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < p.n_partial; i += blockDim.x) acc += p.sumsq_partial[i];
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_red[w];
+    float norm = (float)sqrt(t);
+    float scale = p.gscale;
+    if (p.clip > 0.f) scale *= fminf(norm, p.clip) / (1e-7f + norm);
+    s_scale = scale;
+    int tstep = p.step[0] + 1;
+    float lr = p.lr * p.hyper[0];
+    if (p.kind == 0) {
+      double b1t = pow((double)p.beta1, (double)tstep), b2t = pow((double)p.beta2, (double)tstep);
+      s_alpha = (float)((double)lr * sqrt(1.0 - b2t) / (1.0 - b1t));
+    } else {
+      s_alpha = lr;
+    }
+    if (blockIdx.x == 0) {
+      int slot = p.log_slot[0];
+      if (slot < p.log_cap) {
+        p.out_norm[slot] = norm;
+        float l = 0.f;
+        for (int b = 0; b < p.n_loss_blocks; ++b) l += p.loss_partial[4 * b + 3];
+        p.out_loss[slot] = l;
+      }
+    }
+  }
+  __syncthreads();
+  const float scale = s_scale, alpha = s_alpha;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long)gridDim.x * blockDim.x) {
+    float g = p.grad[i] * scale;
+    if (p.kind == 0) {
+      float m = p.beta1 * p.m[i] + (1.f - p.beta1) * g;
+      float v = p.beta2 * p.v[i] + (1.f - p.beta2) * g * g;
+      p.m[i] = m; p.v[i] = v;
+      p.param[i] -= alpha * m / (sqrtf(v) + p.eps);
+    } else {
+      float a = p.rho * p.v[i] + (1.f - p.rho) * g * g;
+      p.v[i] = a;
+      p.param[i] -= alpha * g / sqrtf(a + p.eps);
+    }
+  }
+}
+
+// runs after update_kernel (stream order): advance the device-side counters
+__global__ void advance_counters_kernel(int* step, int* log_slot, int* mb_counter) {
+  step[0] += 1;
+  log_slot[0] += 1;
+  mb_counter[0] += 1;
+}
+
+// ===========================================================================
+// Weight packing: fp32 master (reference layout) -> bf16 operand matrices for the GEMM tiles
+// ===========================================================================
+enum PackKind { PK_CONV_NHWC = 0, PK_CONV_CHW = 1, PK_CONV_DGRAD = 2, PK_FC = 3 };
+
+struct PackJob {
+  __nv_bfloat16* dst;
+  long src_off;        // offset of W in the flat params
+  int kind;
+  int rows, cols;      // dst is [rows][cols]
+  int Cout, C, kh, kw; // conv dims
+  int s, ry, rx, Tx;   // dgrad class (k' = (ty*Tx+tx)*Cout + o ; ky = ry + s*ty ; kx = rx + s*tx)
+  int HW;              // FC: k' = hw*C + c  <- W[(c*HW + hw)][j]
+  int ldsrc;           // FC: hidden size
+};
+
+__global__ void __launch_bounds__(256) pack_weights_kernel(const PackJob* __restrict__ jobs,
+                                                            const float* __restrict__ params) {
+  const PackJob jb = jobs[blockIdx.y];
+  const long total = (long)jb.rows * jb.cols;
+  const float* W = params + jb.src_off;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int r = (int)(i / jb.cols);
+    int k = (int)(i - (long)r * jb.cols);
+    float v = 0.f;
+    if (jb.kind == PK_CONV_NHWC) {          // r = cout, k = (ky*kw+kx)*C + c
+      int c = k % jb.C; int t = k / jb.C; int kx = t % jb.kw, ky = t / jb.kw;
+      v = W[(((long)r * jb.C + c) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx)];
+    } else if (jb.kind == PK_CONV_CHW) {    // r = cout, k = (c*kh+ky)*kw + kx
+      int kx = k % jb.kw; int t = k / jb.kw; int ky = t % jb.kh, c = t / jb.kh;
+      v = W[(((long)r * jb.C + c) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx)];
+    } else if (jb.kind == PK_CONV_DGRAD) {  // r = cin, k = (ty*Tx+tx)*Cout + o
+      int o = k % jb.Cout; int t = k / jb.Cout; int tx = t % jb.Tx, ty = t / jb.Tx;
+      int ky = jb.ry + jb.s * ty, kx = jb.rx + jb.s * tx;
+      if (ky < jb.kh && kx < jb.kw)
+        v = W[(((long)o * jb.C + r) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx)];
+    } else {                                 // PK_FC: r = j (hidden unit), k = hw*C + c
+      int c = k % jb.C; int hw = k / jb.C;
+      v = W[((long)c * jb.HW + hw) * jb.ldsrc + r];
+    }
+    jb.dst[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// ===========================================================================
+// GAE / discounted returns — algos/pg/util.py:6-37, aac_base.py:108-145.
+// Both recurrences are affine: x_t = a_t + g_t * x_{t+1}, g_t = coef * (1 - done_t):
+//   GAE      : a_t = r_t + gamma*V_{t+1}*(1-d_t) - V_t, coef = gamma*lambda, x = advantage
+//   lambda=1 : a_t = r_t,                                coef = gamma,        x = return
+// One warp per env: each lane composes its contiguous chunk of steps, a reverse warp-shuffle
+// scan combines the chunks, then each lane replays its chunk from the incoming value.
+// With valids (mid_batch_reset == False): valids[t] = t < t_inv, adv/ret/value zeroed after
+// (update_valids / zero_after_reset, util.py:40-63).
+// ===========================================================================
+__global__ void __launch_bounds__(128) gae_kernel(const float* __restrict__ rewards, float* __restrict__ values,
+                                                   const uint8_t* __restrict__ dones,
+                                                   const uint8_t* __restrict__ need_reset,
+                                                   const float* __restrict__ last_values, float gamma, float lambda,
+                                                   int use_gae, float* __restrict__ adv, float* __restrict__ ret,
+                                                   int8_t* __restrict__ valids, int n_envs, int T) {
+  const int lane = threadIdx.x & 31;
+  const int env = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (env >= n_envs) return;
+  const int chunk = (T + 31) / 32;
+  const int t0 = lane * chunk;
+  const int t1 = min(T, t0 + chunk);
+  const long base = (long)env * T;
+  const float coef = use_gae ? gamma * lambda : gamma;
+  // compose chunk map x_{t0} = A + G * x_{t1}
+  float A = 0.f, G = 1.f;
+  for (int t = t1 - 1; t >= t0; --t) {
+    float nd = 1.f - (float)dones[base + t];
+    float a;
+    if (use_gae) {
+      float vnext = (t + 1 < T) ? values[base + t + 1] : last_values[env];
+      a = rewards[base + t] + gamma * vnext * nd - values[base + t];
+    } else {
+      a = rewards[base + t];
+    }
+    float g = coef * nd;
+    A = a + g * A;
+    G = g * G;
+  }
+  // reverse inclusive scan over lanes: after it, (A, G) maps x at the END of the last lane to x_{t0}
+  for (int o = 1; o < 32; o <<= 1) {
+    float A2 = __shfl_down_sync(0xffffffffu, A, o);
+    float G2 = __shfl_down_sync(0xffffffffu, G, o);
+    if (lane + o < 32) { A = A + G * A2; G = G * G2; }
+  }
+  // value entering this lane's chunk from the right = x_{t1} = result of lane+1's composed map
+  const float x_end = use_gae ? 0.f : last_values[env];
+  float xin = __shfl_down_sync(0xffffffffu, A + G * x_end, 1);
+  if (lane == 31) xin = x_end;
+  // first need_reset index (for valids)
+  int t_inv = T;
+  if (valids) {
+    int first = T;
+    for (int t = t0; t < t1; ++t)
+      if (need_reset[base + t]) { first = t; break; }
+    for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+    t_inv = (first < T) ? first + 1 : T;
+  }
+  float x = xin;
+  for (int t = t1 - 1; t >= t0; --t) {
+    float nd = 1.f - (float)dones[base + t];
+    float v = values[base + t];
+    float a;
+    if (use_gae) {
+      float vnext = (t + 1 < T) ? values[base + t + 1] : last_values[env];
+      a = rewards[base + t] + gamma * vnext * nd - v;
+    } else {
+      a = rewards[base + t];
+    }
+    x = a + coef * nd * x;
+    float ad = use_gae ? x : x - v;
+    float rt = use_gae ? x + v : x;
+    if (valids) {
+      bool ok = t < t_inv;
+      valids[base + t] = ok ? 1 : 0;
+      if (!ok) { ad = 0.f; rt = 0.f; }
+    }
+    adv[base + t] = ad;
+    ret[base + t] = rt;
+  }
+  if (valids) {
+    __syncwarp();
+    for (int t = max(t0, t_inv); t < t1; ++t) values[base + t] = 0.f;   // zero_after_reset on values
+  }
+}
+
+// standardize_adv (aac_base.py:136-143): (adv - mean) / (std + 1e-6), population std, optional valids.
+// Single block (N is at most a few hundred thousand): two passes in double.
+__global__ void __launch_bounds__(1024) standardize_adv_kernel(float* __restrict__ adv, const int8_t* __restrict__ valids,
+                                                                long n) {
+  __shared__ double s_a[32], s_b[32];
+  __shared__ double s_mean, s_cnt, s_std;
+  double sum = 0.0, cnt = 0.0;
+  for (long i = threadIdx.x; i < n; i += blockDim.x)
+    if (!valids || valids[i]) { sum += adv[i]; cnt += 1.0; }
+  sum = warp_sum_d(sum); cnt = warp_sum_d(cnt);
+  if ((threadIdx.x & 31) == 0) { s_a[threadIdx.x >> 5] = sum; s_b[threadIdx.x >> 5] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0;
+    for (int w = 0; w < 32; ++w) { a += s_a[w]; b += s_b[w]; }
+    s_cnt = b; s_mean = a / b;
+  }
+  __syncthreads();
+  const double mean = s_mean;
+  double var = 0.0;
+  for (long i = threadIdx.x; i < n; i += blockDim.x)
+    if (!valids || valids[i]) { double d = adv[i] - mean; var += d * d; }
+  var = warp_sum_d(var);
+  if ((threadIdx.x & 31) == 0) s_a[threadIdx.x >> 5] = var;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0;
+    for (int w = 0; w < 32; ++w) a += s_a[w];
+    s_std = sqrt(a / s_cnt);
+  }
+  __syncthreads();
+  const float fm = (float)mean, fs = (float)s_std + 1e-6f;
+  for (long i = threadIdx.x; i < n; i += blockDim.x)
+    if (!valids || valids[i]) adv[i] = (adv[i] - fm) / fs;
+}
+
+// sum of valids -> device scalar (float)
+__global__ void __launch_bounds__(1024) count_valids_kernel(const int8_t* __restrict__ valids, long n, float* out) {
+  __shared__ int s[32];
+  int c = 0;
+  for (long i = threadIdx.x; i < n; i += blockDim.x) c += valids[i] ? 1 : 0;
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 32; ++w) t += s[w];
+    out[0] = (float)t;
+  }
+}
+
+// standalone action sampling (policy.get_actions on host-provided probabilities)
+__global__ void sample_actions_kernel(const float* __restrict__ prob, const double* __restrict__ u,
+                                      uint8_t* __restrict__ act, int n, int A) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float cs = 0.f;
+  int k = 0;
+  for (int a = 0; a < A; ++a) { cs = __fadd_rn(cs, prob[(long)i * A + a]); k += ((double)cs < u[i]) ? 1 : 0; }
+  act[i] = (uint8_t)min(k, A - 1);
+}
+
+}  // namespace arl

@@ -1,0 +1,168 @@
+/* accelrl_b200.h — C ABI of libaccelrl_b200.so (B200 / sm_100a).
+ *
+ * The reference (astooke/accel_rl) has no FFI: its plugin surface is Python classes handed to a
+ * Runner.  Each entry point below states the reference interface it stands in
+ * for (paths relative to the reference tree).  All pointers are raw DEVICE pointers unless
+ * marked host; sizes are element counts; every function returns 0 on success and a non-zero
+ * code otherwise (arl_last_error() gives the message).  No function allocates device memory
+ * after the corresponding *_create / *_configure call, and none takes a torch type.
+ * `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ */
+#ifndef ACCELRL_B200_H
+#define ACCELRL_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct arl_ctx arl_ctx;
+
+#define ARL_MAX_CONV 4
+
+/* Network description — policies/pg/atari_cnn_policy.py:17-24 ctor args + env_spec
+ * (policies/pg/networks/pg_cnn.py:17-33).  One hidden FC layer (cnn_specs 0, 1, 4 shapes). */
+typedef struct {
+  int n_conv;
+  int conv_filters[ARL_MAX_CONV];
+  int conv_sizes[ARL_MAX_CONV];
+  int conv_strides[ARL_MAX_CONV];
+  int conv_pads[ARL_MAX_CONV];
+  int hidden;              /* hidden_sizes[0] */
+  int n_actions;           /* env_spec.action_space.n (<= 18) */
+  int in_c, in_h, in_w;    /* observation_space.shape = (num_img_obs, 104, 80) */
+  float pixel_scale;       /* 255. */
+  int max_rows;            /* largest batch any forward/backward call will use */
+} arl_net_cfg;
+
+/* Loss / optimiser description — algos/pg/{aac_base,ppo,a2c}.py ctor args and
+ * optimizers/single/{ppo,a2c}_optimizer.py ctor args. */
+typedef struct {
+  int algo;                /* 0 = PPO (ppo.py:42-51), 1 = A2C (a2c.py:43-46) */
+  float clip_param;        /* PPO ratio clip (scaled by lr_mult, ppo.py:46) */
+  float v_loss_coeff, ent_loss_coeff;
+  int update;              /* 0 = adam, 1 = rmsprop (optimizers/update_methods_stats.py) */
+  float learning_rate, beta1, beta2, epsilon, rho;
+  float grad_norm_clip;    /* <= 0: None (norm is still reported) */
+} arl_opt_cfg;
+
+/* Rollout buffers + synthetic-emulator description — sampler/act_server/buffers.py:7-38,
+ * buffers/batch.py:36-76 (row = env*T + t) and envs/atari_env.py ctor args. */
+typedef struct {
+  int n_envs, horizon, planes;
+  uint8_t* observations;        /* [N][planes][104][80] */
+  float* rewards;               /* [N] */
+  uint8_t* dones;               /* [N] bool */
+  float* raw_reward;            /* [N] env_infos.raw_reward */
+  uint8_t* need_reset;          /* [N] env_infos.need_reset */
+  uint8_t* actions;             /* [N] */
+  float* prob;                  /* [N][A] agent_infos.prob */
+  float* value;                 /* [N]    agent_infos.value */
+  uint8_t* extra_observations;  /* [B][planes][104][80] */
+  uint8_t* step_obs;            /* [B][planes][104][80] (the sampler's step buffer) */
+  double* uniforms;             /* [horizon][B] np.random.rand draws, step-major */
+  const uint8_t* frame_pool;    /* [pool_frames][210][160] grayscale emulator frames */
+  int pool_frames;
+  int max_path_length;
+  float discount;
+  int mid_batch_reset, clip_reward, episodic_lives;
+  /* synthetic emulator rules (oracle/synth_ale.py implements the same) */
+  int lives0, life_base, life_mul, life_mod, reward_mod, frame_stride;
+  int traj_cap;                 /* capacity of the completed-trajectory record buffer */
+} arl_sampler_cfg;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+int arl_create(const arl_net_cfg* cfg, arl_ctx** out);   /* AtariCnnPolicy.initialize (atari_cnn_policy.py:42-76) */
+void arl_destroy(arl_ctx* ctx);
+const char* arl_last_error(arl_ctx* ctx);                /* ctx may be NULL: last creation error */
+int arl_device_error(arl_ctx* ctx);                      /* device-side watchdog flag (0 = ok) */
+
+/* ---- parameters: rllab/core/parameterized.py:74-88 flat fp32 vector, Lasagne order --------- */
+long arl_param_count(arl_ctx* ctx);
+/* fills offsets/sizes (elements) of conv{i}.W, conv{i}.b, hidden.W, hidden.b, pi.W, pi.b, v.W, v.b */
+int arl_param_layout(arl_ctx* ctx, long* offsets, long* sizes, int cap);
+/* register the flat fp32 params / grad / optimiser-state vectors (owned by the caller) */
+int arl_bind_params(arl_ctx* ctx, float* params, float* grad, float* m, float* v);
+/* refresh the bf16 operand copies after params changed (set_param_values) */
+int arl_pack_weights(arl_ctx* ctx, void* stream);
+
+/* ---- policy: AtariCnnPolicy.get_actions / value / dist_info_value (atari_cnn_policy.py:92-111) */
+/* obs [*, C, H, W] u8; idx (optional) gathers n rows; outputs written at out_rows[i] (or i).
+ * prob/value/actions/uniforms may each be NULL (actions needs uniforms). */
+int arl_policy_forward(arl_ctx* ctx, const uint8_t* obs, const int* idx, int n, const int* out_rows,
+                       float* prob, float* value, const double* uniforms, uint8_t* actions, void* stream);
+/* Discrete.weighted_sample_n (spaces/discrete.py:67-68 -> rllab/misc/special.py:22-27) */
+int arl_sample_actions(arl_ctx* ctx, const float* prob, const double* uniforms, uint8_t* actions, int n, int n_actions,
+                       void* stream);
+
+/* ---- frame pipeline: AtariEnv._update_obs (envs/atari_env.py:151-157) ------------------------ */
+/* raw_a/raw_b: [n][210][160] u8 grayscale screens (raw_a NULL => zeros, i.e. after _reset_obs);
+ * reset_mask[n] (optional, host semantics of _reset_obs: zero the older planes);
+ * stack [n][planes][104][80] updated in place. */
+int arl_frame_update(arl_ctx* ctx, const uint8_t* raw_a, const uint8_t* raw_b, const uint8_t* reset_mask, uint8_t* stack,
+                     int n, int planes, void* stream);
+
+/* ---- sampler: ActsrvAltOvrlpSampler.obtain_samples (sampler/.../overlap/sampler.py:97-151) --- */
+int arl_sampler_configure(arl_ctx* ctx, const arl_sampler_cfg* cfg);
+int arl_sampler_reset(arl_ctx* ctx, void* stream);                  /* start_envs (sampler/util.py:26-57) */
+int arl_rollout_begin(arl_ctx* ctx, void* stream);
+/* one serve+step: forward on step_obs, sample, env step, frame update.  staging (optional):
+ * host-fed raw frames [B][2][210][160] already on the device for this step */
+int arl_rollout_step(arl_ctx* ctx, int s, const uint8_t* staging, void* stream);
+int arl_rollout_end(arl_ctx* ctx, void* stream);
+/* begin + horizon steps + end, replayed from a CUDA graph (resident frame pool) */
+int arl_rollout_run(arl_ctx* ctx, void* stream);
+/* completed TrajInfo records (sampler/util.py:75-101); host arrays of capacity cap; returns count via *n */
+int arl_traj_read(arl_ctx* ctx, int* n, int* env, int* len, float* ret, float* raw, int* nz, float* disc, int cap,
+                  void* stream);
+/* pool indices the emulator will show env e at step s (host-fed path): fills [B][2] (-1 = zeros) + flags[B] */
+int arl_peek_frame_cmds(arl_ctx* ctx, int* cmd_host, int n_envs, void* stream);
+
+/* ---- advantages: AdvActorCriticBase.process_samples (algos/pg/aac_base.py:108-145) ---------- */
+int arl_gae(arl_ctx* ctx, const float* rewards, float* values, const uint8_t* dones, const uint8_t* need_reset,
+            const float* last_values, float discount, float gae_lambda, float* adv, float* ret, int8_t* valids,
+            int n_envs, int horizon, int standardize, void* stream);
+
+/* ---- learner: PpoOptimizer / A2cOptimizer (optimizers/single/*.py) --------------------------- */
+int arl_opt_configure(arl_ctx* ctx, const arl_opt_cfg* cfg);
+/* bind the training inputs (prep_opt_inputs, aac_base.py:147-170): rollout-length arrays */
+int arl_bind_train_inputs(arl_ctx* ctx, const uint8_t* obs, const uint8_t* actions, const float* adv, const float* ret,
+                          const float* old_value, const float* old_prob, const int8_t* valids, long n_rows);
+int arl_set_lr_mult(arl_ctx* ctx, float lr_mult, void* stream);
+/* forward + losses + backward for rows idx[mb_index*mb_size .. +mb_size) -> flat grad (no update) */
+int arl_grad_minibatch(arl_ctx* ctx, const int* idx, int mb_size, void* stream);
+/* total_norm_constraint + update (optimizers/util.py:70-76); gscale = gradient averaging factor */
+int arl_clip_update(arl_ctx* ctx, float gscale, void* stream);
+/* `count` consecutive minibatches (grad + update + repack), idx = [count*mb_size] int32; graph-replayed */
+int arl_train_minibatches(arl_ctx* ctx, const int* idx, int mb_size, int count, void* stream);
+/* per-update logs since the last call: losses and pre-clip grad norms (host arrays) */
+int arl_read_logs(arl_ctx* ctx, float* loss, float* grad_norm, int cap, int* n, void* stream);
+int arl_reset_opt_state(arl_ctx* ctx, void* stream);
+
+/* ---- sync data parallel: optimizers/sync/base.py:8-24 + sync_ppo_optimizer.py:13-78 ----------- */
+#define ARL_IPC_HANDLE_BYTES 64
+/* allocate this rank's exchange buffers (grad mirror, flags); returns the IPC handle to publish */
+int arl_comm_local_init(arl_ctx* ctx, int rank, int world, uint8_t* handle_out /*[ARL_IPC_HANDLE_BYTES] host*/);
+/* the symmetric flat gradient / parameter vectors peers read and write (bind these with arl_bind_params) */
+int arl_comm_buffers(arl_ctx* ctx, float** grad_out, float** params_out);
+/* open every peer's handle (host array [world][ARL_IPC_HANDLE_BYTES]) */
+int arl_comm_connect(arl_ctx* ctx, const uint8_t* all_handles);
+/* fused: reduce my slice of the flat gradient over peers by P2P loads, average, global-norm
+ * clip, Adam/RMSProp on the slice, P2P-store the new params to every peer. */
+int arl_sync_allreduce_update(arl_ctx* ctx, void* stream);
+int arl_comm_barrier(arl_ctx* ctx, void* stream);
+
+/* ---- diagnostics / tests ---------------------------------------------------------------------- */
+/* intermediate activations of the last forward (bf16 -> fp32 copies into host-visible device buffers) */
+int arl_debug_activation(arl_ctx* ctx, int layer, float* out, long cap, long* n, void* stream);
+long arl_kernel_launches(arl_ctx* ctx);   /* launches issued (graph replays count their node count) */
+/* plain tcgen05 GEMM self-test: D[M][N] = A[M][K] * B (B K-major [N][K] or N-major [K][N]) */
+int arl_test_gemm(arl_ctx* ctx, const uint16_t* a_bf16, const uint16_t* b_bf16, float* d, int M, int N, int K,
+                  int b_nmajor, void* stream);
+/* wgrad-shaped self-test: D[Kp][N] = sum_r A[r][Kp] * B[r][N] (bf16 in, fp32 out) */
+int arl_test_wgrad(arl_ctx* ctx, const uint16_t* a_bf16, const uint16_t* b_bf16, float* d, int rows, int Kp, int N,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
