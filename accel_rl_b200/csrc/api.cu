@@ -484,6 +484,10 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
   int S = 0;
   if (forward_trunk(c, c->t_obs, idx, idx_off, n, &S, st)) return 1;
   // ---- head: losses + dlogits + dh ----
+  if (c->t_valids) {
+    count_valids_idx_kernel<<<1, 1024, 0, st>>>(c->t_valids, idx, idx_off, n, c->valid_count);
+    c->launches++;
+  }
   HeadParams p = head_base(c, n, S);
   p.idx = idx; p.idx_off = idx_off; p.act_in = c->t_act; p.adv = c->t_adv; p.ret = c->t_ret; p.old_prob = c->t_oldp;
   p.valids = c->t_valids; p.valid_count = c->valid_count;
@@ -901,10 +905,6 @@ int arl_gae(arl_ctx* c, const float* rewards, float* values, const uint8_t* done
                                                 use_gae, adv, ret, valids, n_envs, horizon);
   c->launches++;
   long n = (long)n_envs * horizon;
-  if (valids) {
-    count_valids_kernel<<<1, 1024, 0, st>>>(valids, n, c->valid_count);
-    c->launches++;
-  }
   if (standardize) {
     standardize_adv_kernel<<<1, 1024, 0, st>>>(adv, valids, n);
     c->launches++;

@@ -404,11 +404,13 @@ __global__ void __launch_bounds__(kGemmThreads) rowgemm_kernel(ALoad aload, Weig
           tmem_ld_wait();
           epi_store32(epi, row, n0 + half * COLS_PER_WARP + c, r, split);
         }
-      } else {
+      } else if (BN == 32 || half == 0) {
+        // BN == 32: two column halves of 16; BN == 16: warps 0-3 only (warp-uniform branch)
+        const int coff = (BN == 32) ? half * 16 : 0;
         uint32_t r16[16];
-        tmem_ld16(lane_addr + half * 16, r16);
+        tmem_ld16(lane_addr + coff, r16);
         tmem_ld_wait();
-        epi_store16(epi, row, n0 + half * 16, r16, split);
+        epi_store16(epi, row, n0 + coff, r16, split);
       }
       tc_fence_before();
     }
@@ -554,7 +556,8 @@ __global__ void __launch_bounds__(kGemmThreads) wgrad_kernel(ALoad64 aload, cons
       } else {
         orow = (long)split * epi.Kp + kprime;
       }
-      float* dst = epi.out + orow * epi.ldo + n0 + half * COLS_PER_WARP;
+      constexpr int COFF = (BN >= 32) ? COLS_PER_WARP : 0;   // BN == 16: warps 0-3 own all 16 columns
+      float* dst = epi.out + orow * epi.ldo + n0 + half * COFF;
       if constexpr (COLS_PER_WARP >= 32) {
 #pragma unroll 1
         for (int c = 0; c < COLS_PER_WARP; c += 32) {
@@ -573,10 +576,10 @@ __global__ void __launch_bounds__(kGemmThreads) wgrad_kernel(ALoad64 aload, cons
             d4[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
                                 __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
         }
-      } else {
+      } else if (BN == 32 || half == 0) {
         uint32_t r16[16];
         if (niter > 0) {
-          tmem_ld16(lane_addr + mt * BN + half * 16, r16);
+          tmem_ld16(lane_addr + mt * BN + half * COFF, r16);
           tmem_ld_wait();
         } else {
 #pragma unroll

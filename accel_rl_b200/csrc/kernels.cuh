@@ -964,6 +964,25 @@ __global__ void __launch_bounds__(1024) count_valids_kernel(const int8_t* __rest
   }
 }
 
+// sum of valids over the rows of one minibatch (valids_mean denominators are per minibatch, util.py:49-53)
+__global__ void __launch_bounds__(1024) count_valids_idx_kernel(const int8_t* __restrict__ valids,
+                                                                const int* __restrict__ idx,
+                                                                const int* __restrict__ idx_off, int n, float* out) {
+  __shared__ int s[32];
+  const int* ip = idx;
+  if (ip && idx_off) ip += (long)idx_off[0] * n;
+  int c = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) c += valids[ip ? ip[i] : i] ? 1 : 0;
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 32; ++w) t += s[w];
+    out[0] = (float)t;
+  }
+}
+
 // standalone action sampling (policy.get_actions on host-provided probabilities)
 __global__ void sample_actions_kernel(const float* __restrict__ prob, const double* __restrict__ u,
                                       uint8_t* __restrict__ act, int n, int A) {

@@ -1,0 +1,81 @@
+"""Atari environment description (reference: accel_rl/envs/atari_env.py).
+
+The reference steps one ALE emulator per env on CPU worker processes.  Here the environments are
+device-resident: the frame pipeline (_update_obs, atari_env.py:151-157), frame-skip / reward /
+life / reset logic (:65-100, :165-191) run for ALL envs in env_step_kernel + frame_kernel
+(csrc/kernels.cuh), driven by the synthetic emulator rules (the real emulator is out of scope,
+SURVEY.md §2a).  This class therefore only carries the constructor arguments, spaces and the
+synthetic-emulator rule set; `AtariEnv.device_resident` tells the sampler not to look for step().
+"""
+import numpy as np
+
+from accel_rl_b200.spaces.discrete import Discrete
+from accel_rl_b200.spaces.uintbox import UintBox
+
+W, H = (80, 104)  # atari_env.py:13
+
+# Minimal action sets (ALE getMinimalActionSet) for the games the BASELINE configs name
+MINIMAL_ACTIONS = {"breakout": 4, "pong": 6, "space_invaders": 6, "seaquest": 18, "qbert": 6, "beam_rider": 9}
+
+DEFAULT_SYNTH_RULES = dict(pool_frames=1024, lives0=5, life_base=400, life_mul=31, life_mod=257, reward_mod=389,
+                           frame_stride=263, pool_seed=0)
+
+
+class EnvSpec(object):
+    def __init__(self, observation_space, action_space):
+        self._observation_space = observation_space
+        self._action_space = action_space
+
+    observation_space = property(lambda self: self._observation_space)
+    action_space = property(lambda self: self._action_space)
+
+
+class AtariEnv(object):
+    device_resident = True
+
+    def __init__(self, game="pong", frame_skip=4, num_img_obs=4, clip_reward=True, episodic_lives=True,
+                 max_start_noops=30, repeat_action_probability=0., synth_rules=None, n_actions=None):
+        if frame_skip != 4:
+            raise NotImplementedError("device env implements frame_skip=4 (atari_env.py:19 default)")
+        if num_img_obs not in (1, 4):
+            raise NotImplementedError("num_img_obs must be 1 or 4")
+        self._game = game
+        self._frame_skip = frame_skip
+        self._num_img_obs = num_img_obs
+        self._clip_reward = clip_reward
+        self._episodic_lives = episodic_lives
+        self._max_start_noops = max_start_noops
+        self._repeat_action_probability = repeat_action_probability
+        self.synth_rules = dict(DEFAULT_SYNTH_RULES)
+        if synth_rules:
+            self.synth_rules.update(synth_rules)
+        n = n_actions if n_actions is not None else MINIMAL_ACTIONS.get(game, 4)
+        self._action_space = Discrete(n)
+        self._observation_space = UintBox(shape=(num_img_obs, H, W), bits=8)
+        # the reference ctor ends with self.reset(), whose start no-ops draw from the global stream
+        # (atari_env.py:63,97); keep the draw so master-process RNG consumption stays identical
+        self._draw_start_noops()
+
+    def _draw_start_noops(self):
+        return int(np.random.randint(0, self._max_start_noops + 1))
+
+    def reset(self):
+        """Host-visible reset only consumes the start-noop draw; observations live on the device."""
+        self._draw_start_noops()
+        return np.zeros(self._observation_space.shape, np.uint8)
+
+    action_space = property(lambda self: self._action_space)
+    observation_space = property(lambda self: self._observation_space)
+    spec = property(lambda self: EnvSpec(self._observation_space, self._action_space))
+    game = property(lambda self: self._game)
+    frame_skip = property(lambda self: self._frame_skip)
+    num_img_obs = property(lambda self: self._num_img_obs)
+    clip_reward = property(lambda self: self._clip_reward)
+    episodic_lives = property(lambda self: self._episodic_lives)
+    max_start_noops = property(lambda self: self._max_start_noops)
+    repeat_action_probability = property(lambda self: self._repeat_action_probability)
+
+
+def make_frame_pool(pool_frames, seed=0):
+    """Synthetic grayscale emulator frames (pool_frames, 210, 160) uint8 — same generator as the oracle."""
+    return np.random.RandomState(seed).randint(0, 256, (pool_frames, 210, 160), dtype=np.uint8)

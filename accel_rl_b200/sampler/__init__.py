@@ -1,0 +1,2 @@
+from accel_rl_b200.sampler.base import Sampler, BaseMbSampler
+from accel_rl_b200.sampler.device_sampler import ActsrvAltOvrlpSampler, DeviceSampler, TrajInfo

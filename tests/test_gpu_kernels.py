@@ -1,0 +1,206 @@
+"""Per-kernel parity: CUDA (through the C ABI) vs the oracle.  Needs a B200."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import frame as oframe, gae as ogae, net as onet, sampler as osampler
+from tests.util_gpu import make_policy, relerr, t2n
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pol1():
+    pol, flat, spec = make_policy(1, max_rows=160)
+    yield pol, flat, spec
+    pol.engine.close()
+
+
+def test_frame_kernel_bit_exact(pol1, golden_dir):
+    eng = pol1[0].engine
+    g = np.load(golden_dir + "/frames.npz")
+    stack = torch.tensor(g["stacks"]).cuda()
+    eng.frame_update(torch.tensor(g["raw1"]).cuda(), torch.tensor(g["raw2"]).cuda(),
+                     torch.tensor(g["reset"].astype(np.uint8)).cuda(), stack)
+    assert np.array_equal(t2n(stack), g["out"])            # vs the reference's own cv2 path
+    # larger random batch incl. single-plane stacks (num_img_obs=1) vs the oracle
+    rng = np.random.RandomState(1)
+    for planes, n in ((4, 300), (1, 65)):
+        a = rng.randint(0, 256, (n, 210, 160), dtype=np.uint8)
+        b = rng.randint(0, 256, (n, 210, 160), dtype=np.uint8)
+        st = rng.randint(0, 256, (n, planes, 104, 80), dtype=np.uint8)
+        rs = (rng.rand(n) < 0.25).astype(np.uint8)
+        d = torch.tensor(st).cuda()
+        eng.frame_update(torch.tensor(a).cuda(), torch.tensor(b).cuda(), torch.tensor(rs).cuda(), d)
+        assert np.array_equal(t2n(d), oframe.update_obs_batch(st, a, b, rs))
+    # raw_a == NULL (after _reset_obs)
+    d = torch.tensor(st).cuda()
+    eng.frame_update(None, torch.tensor(b).cuda(), None, d)
+    assert np.array_equal(t2n(d), oframe.update_obs_batch(st, None, b, None))
+
+
+@pytest.mark.parametrize("A", [4, 6, 18])
+def test_action_sampling_bit_exact(pol1, golden_dir, A):
+    eng = pol1[0].engine
+    g = np.load(golden_dir + "/sampling.npz")
+    act = torch.zeros(257, dtype=torch.uint8, device="cuda")
+    eng.sample_actions(torch.tensor(g["p%d" % A]).cuda(), torch.tensor(g["u%d" % A]).cuda(), act)
+    assert np.array_equal(t2n(act), g["a%d" % A])          # vs rllab weighted_sample_n
+    rng = np.random.RandomState(A)
+    p = rng.dirichlet(np.ones(A) * 0.3, 20000).astype(np.float32)
+    u = rng.rand(20000)
+    u[:50] = 1.0 - 1e-17                                   # beyond the last cumsum -> clamp to A-1
+    act = torch.zeros(20000, dtype=torch.uint8, device="cuda")
+    eng.sample_actions(torch.tensor(p).cuda(), torch.tensor(u).cuda(), act)
+    assert np.array_equal(t2n(act), osampler.weighted_sample_n(p, u, A))
+
+
+@pytest.mark.parametrize("lam,use_valids,std", [(0.95, False, False), (1.0, False, False), (0.95, True, False),
+                                                (1.0, True, True), (0.95, False, True)])
+@pytest.mark.parametrize("B,T", [(7, 33), (256, 128), (3, 5), (64, 1)])
+def test_gae_kernel(pol1, lam, use_valids, std, B, T):
+    eng = pol1[0].engine
+    rng = np.random.RandomState(B * 1000 + T)
+    N = B * T
+    r = rng.choice([0., 0., 1., -1.], N).astype(np.float32)
+    v = rng.randn(N).astype(np.float32)
+    d = rng.rand(N) < 0.08
+    nr = d & (rng.rand(N) < 0.5)
+    lv = rng.randn(B).astype(np.float32)
+    want = ogae.process_samples(r, v, d, nr, lv, 0.99, lam, T, use_valids=use_valids, standardize_adv=std)
+    dv = torch.tensor(v).cuda()
+    adv = torch.zeros(N, device="cuda"); ret = torch.zeros(N, device="cuda")
+    valids = torch.zeros(N, dtype=torch.int8, device="cuda") if use_valids else None
+    eng.gae(torch.tensor(r).cuda(), dv, torch.tensor(d).cuda(), torch.tensor(nr).cuda() if use_valids else None,
+            torch.tensor(lv).cuda(), 0.99, lam, adv, ret, valids, B, T, std)
+    tol = dict(rtol=1e-4, atol=1e-4)                       # north-star: advantages within 1e-4
+    np.testing.assert_allclose(t2n(adv), want[0], **tol)
+    np.testing.assert_allclose(t2n(ret), want[1], **tol)
+    if use_valids:
+        assert np.array_equal(t2n(valids), want[2])
+        np.testing.assert_allclose(t2n(dv), want[3], rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("nmajor", [0, 1])
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (300, 128, 512), (1000, 192, 576), (1, 64, 128)])
+def test_tcgen05_gemm_tile(pol1, M, N, K, nmajor):
+    from accel_rl_b200 import _lib as L
+    eng = pol1[0].engine
+    torch.manual_seed(M + N + K)
+    A = torch.randn(M, K).to(torch.bfloat16).cuda()
+    B = torch.randn(N, K).to(torch.bfloat16).cuda()
+    Bm = B.t().contiguous() if nmajor else B
+    D = torch.zeros(M, N, device="cuda")
+    eng.check(eng.lib.arl_test_gemm(eng.ctx, L.ptr(A), L.ptr(Bm), L.ptr(D), M, N, K, nmajor, eng._s()))
+    ref = A.float() @ B.float().t()
+    assert (D - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item()) * 1e-1 + 1e-3
+
+
+@pytest.mark.parametrize("N", [16, 32, 64, 256])
+@pytest.mark.parametrize("rows,Kp", [(64, 128), (1000, 256), (777, 192)])
+def test_tcgen05_wgrad_tile(pol1, rows, Kp, N):
+    from accel_rl_b200 import _lib as L
+    eng = pol1[0].engine
+    torch.manual_seed(rows + Kp + N)
+    A = torch.randn(rows, Kp).to(torch.bfloat16).cuda()
+    B = torch.randn(rows, N).to(torch.bfloat16).cuda()
+    D = torch.zeros(Kp, N, device="cuda")
+    eng.check(eng.lib.arl_test_wgrad(eng.ctx, L.ptr(A), L.ptr(B), L.ptr(D), rows, Kp, N, eng._s()))
+    ref = A.float().t() @ B.float()
+    assert (D - ref).abs().max().item() <= 1e-3 + 1e-4 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("spec_id,n,A", [(1, 37, 4), (0, 37, 4), (1, 128, 6), (1, 1, 18), (0, 130, 9)])
+def test_policy_forward_vs_oracle(spec_id, n, A):
+    pol, flat, spec = make_policy(spec_id, max_rows=n, n_actions=A)
+    try:
+        obs = np.random.RandomState(n).randint(0, 256, (n, 4, 104, 80), dtype=np.uint8)
+        info = pol.dist_info_value(obs)
+        p_ref, v_ref = onet.forward(torch.tensor(flat), torch.tensor(obs), spec, A, emulate_bf16=True)
+        # bf16-operand mirror: differences are fp32 summation order + rare 1-ulp bf16 rounding flips
+        np.testing.assert_allclose(info["prob"], p_ref.numpy(), rtol=2e-3, atol=2e-5)
+        np.testing.assert_allclose(info["value"], v_ref.numpy(), rtol=2e-3, atol=2e-3)
+        assert abs(info["prob"].sum(axis=1) - 1).max() < 1e-5
+        # against the un-rounded fp32 graph: documented looser bound for bf16 operands
+        p32, v32 = onet.forward(torch.tensor(flat), torch.tensor(obs), spec, A, emulate_bf16=False)
+        np.testing.assert_allclose(info["prob"], p32.numpy(), rtol=3e-2, atol=1e-3)
+        np.testing.assert_allclose(info["value"], v32.numpy(), rtol=3e-2, atol=2e-2)
+    finally:
+        pol.engine.close()
+
+
+@pytest.mark.parametrize("spec_id,algo,n,valids", [(1, "ppo", 64, False), (0, "a2c", 48, False), (1, "a2c", 33, False),
+                                                   (1, "ppo", 160, False)])
+def test_loss_and_gradient_vs_oracle(spec_id, algo, n, valids):
+    pol, flat, spec = make_policy(spec_id, max_rows=n)
+    eng = pol.engine
+    try:
+        rng = np.random.RandomState(5 + n)
+        N = n + 40
+        obs = rng.randint(0, 256, (N, 4, 104, 80), dtype=np.uint8)
+        act = rng.randint(0, 4, N).astype(np.uint8)
+        adv = rng.randn(N).astype(np.float32)
+        ret = rng.randn(N).astype(np.float32)
+        oldp = rng.dirichlet(np.ones(4), N).astype(np.float32)
+        oldv = rng.randn(N).astype(np.float32)
+        val = (rng.rand(N) < 0.7).astype(np.int8) if valids else None
+        idx = rng.permutation(N)[:n].astype(np.int32)
+        vc = 1.0 if algo == "ppo" else 0.25
+        eng.opt_configure(algo=0 if algo == "ppo" else 1, clip_param=0.2, v_loss_coeff=vc, ent_loss_coeff=0.01, update=0,
+                          learning_rate=1e-3, beta1=0.9, beta2=0.999, epsilon=1e-5, rho=0.9, grad_norm_clip=-1.0)
+        d = [torch.tensor(x).cuda() for x in (obs, act, adv, ret, oldv, oldp)]
+        dval = torch.tensor(val).cuda() if valids else None
+        eng.bind_train_inputs(*d, valids=dval)
+        didx = torch.tensor(idx).cuda()
+        eng.grad_minibatch(didx, n)
+        torch.cuda.synchronize()
+        g = t2n(eng.grad)
+        vsub = None
+        loss_ref, g_ref, _ = onet.loss_and_grad(flat, obs[idx], act[idx], adv[idx], ret[idx], oldp[idx], spec, 4, algo,
+                                                emulate_bf16=True, v_coeff=vc, valids=vsub)
+        shapes = onet.param_shapes(spec, (4, 104, 80), 4)
+        i = 0
+        for k, s in enumerate(shapes):
+            m = int(np.prod(s))
+            # activation gradients are stored in bf16 between layers: per-tensor relative error bound 1e-2
+            assert relerr(g[i:i + m], g_ref[i:i + m]) < 1e-2, "tensor %d %s" % (k, s)
+            i += m
+        assert relerr(g, g_ref) < 5e-3
+        # loss value (north-star: within 1e-4 relative of the bf16-mirrored graph ... 1e-3 abs floor)
+        eng.clip_update(1.0)
+        losses, norms = eng.read_logs()
+        assert abs(losses[0] - loss_ref) <= 1e-4 * abs(loss_ref) + 2e-4
+        assert abs(norms[0] - np.linalg.norm(g_ref)) <= 5e-3 * np.linalg.norm(g_ref)
+    finally:
+        eng.close()
+
+
+@pytest.mark.parametrize("kind,clip", [("adam", None), ("adam", 0.5), ("rmsprop", 0.5), ("rmsprop", None)])
+def test_clip_and_update_rules(kind, clip):
+    pol, flat, spec = make_policy(0, max_rows=8)
+    eng = pol.engine
+    try:
+        rng = np.random.RandomState(3)
+        n = flat.size
+        eng.opt_configure(algo=0, clip_param=0.2, v_loss_coeff=1.0, ent_loss_coeff=0.01, update=0 if kind == "adam" else 1,
+                          learning_rate=1e-3 if kind == "adam" else 7e-4, beta1=0.9, beta2=0.999,
+                          epsilon=1e-5 if kind == "adam" else 1e-6, rho=0.9, grad_norm_clip=clip if clip else -1.0)
+        eng.reset_opt_state()
+        opt = onet.Adam(n, 1e-3, epsilon=1e-5) if kind == "adam" else onet.RMSProp(n, 7e-4)
+        p = flat.copy()
+        for step in range(3):
+            g = (rng.randn(n) * 0.01).astype(np.float32)
+            eng.grad.copy_(torch.tensor(g))
+            eng.set_lr_mult(1.0 - 0.25 * step)
+            eng.clip_update(1.0)
+            gc, norm = onet.total_norm_clip(g, clip)
+            p = opt.step(p, gc, 1.0 - 0.25 * step)
+            losses, norms = eng.read_logs()
+            assert abs(norms[0] - norm) <= 1e-5 * norm
+        got = eng.get_params()
+        assert relerr(got - flat, p - flat) < 1e-4          # the applied update
+        np.testing.assert_allclose(got, p, rtol=1e-6, atol=1e-7)
+    finally:
+        eng.close()

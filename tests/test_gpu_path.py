@@ -1,0 +1,260 @@
+"""Path-level parity on the GPU: the device sampler vs the REAL reference sampler's golden buffers,
+one full optimize_policy vs the oracle learner, and the runner end to end.  Needs a B200."""
+import os
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import net as onet, sampler as osampler, learner as olearner, synth_ale
+from tests.golden.make_golden import RULES, POOL_FRAMES
+from tests.util_gpu import make_policy, relerr, t2n
+
+pytestmark = pytest.mark.gpu
+
+
+def _make_sampler(n_parallel, envs_per, T, mid_batch_reset=True, max_path_length=27000, rules=None, env_kw=None, **kw):
+    from accel_rl_b200.sampler import ActsrvAltOvrlpSampler
+    from accel_rl_b200.envs import AtariEnv
+    r = dict(RULES if rules is None else rules)
+    r.setdefault("pool_seed", 0)
+    env_args = dict(game="breakout", max_start_noops=0, synth_rules=r)
+    if env_kw:
+        env_args.update(env_kw)
+    return ActsrvAltOvrlpSampler(EnvCls=AtariEnv, env_args=env_args, horizon=T, n_parallel=n_parallel, envs_per=envs_per,
+                                 max_path_length=max_path_length, mid_batch_reset=mid_batch_reset,
+                                 max_decorrelation_steps=0, **kw)
+
+
+def _buf_np(buf):
+    return dict(observations=t2n(buf.observations), rewards=t2n(buf.rewards), dones=t2n(buf.dones),
+                raw_reward=t2n(buf.env_infos.raw_reward), need_reset=t2n(buf.env_infos.need_reset),
+                actions=t2n(buf.actions), prob=t2n(buf.agent_infos.prob), value=t2n(buf.agent_infos.value),
+                extra_observations=t2n(buf.extra_observations))
+
+
+@pytest.mark.parametrize("tag,mbr", [("reset", True), ("nonreset", False), ("overlength", True)])
+def test_device_sampler_reproduces_reference_sampler_buffers(golden_dir, tag, mbr):
+    """Everything the policy does not influence must be bit-identical to what the reference's real
+    multi-process sampler produced (tests/golden/sampler_*.npz); actions must equal weighted_sample_n of
+    the device probabilities with the master's uniforms; the consumed uniforms must be the reference
+    master's stream."""
+    from accel_rl_b200.util.seeding import set_seed
+    g = np.load(os.path.join(golden_dir, "sampler_%s.npz" % tag))
+    B, T, itrs = int(g["n_envs"]), int(g["horizon"]), int(g["itrs"])
+    set_seed(3)                                                        # the fixture's master seed
+    sampler = _make_sampler(2, 2, T, mid_batch_reset=mbr, max_path_length=int(g["max_path_length"]))
+    env_spec, sample_size, horizon, _ = sampler.initialize(seed=4, affinities=dict(), discount=0.99, need_extra_obs=True)
+    assert (sample_size, horizon) == (B * T, T)
+    state = np.random.get_state()
+    pol, flat, spec = make_policy(1, max_rows=B)                        # fixed params: no RNG consumed
+    np.random.set_state(state)
+    sampler.policy_init(pol)
+    try:
+        for itr in range(itrs):
+            buf, infos = sampler.obtain_samples(itr)
+            b = _buf_np(buf)
+            assert np.array_equal(sampler._uniforms_host.numpy(), g["uniforms"][itr]), "master RNG consumption differs"
+            if itr == 0:
+                assert np.array_equal(b["observations"], g["obs_0"])
+            crc = np.array([zlib.crc32(r.tobytes()) for r in b["observations"]], dtype=np.uint32)
+            assert np.array_equal(crc, g["obscrc_%d" % itr]), "observation rows differ at itr %d" % itr
+            assert np.array_equal(b["extra_observations"], g["extra_%d" % itr])
+            assert np.array_equal(b["rewards"], g["rew_%d" % itr])
+            assert np.array_equal(b["dones"], g["done_%d" % itr])
+            assert np.array_equal(b["raw_reward"], g["raw_%d" % itr])
+            assert np.array_equal(b["need_reset"], g["nr_%d" % itr])
+            assert b["actions"].dtype == np.uint8 and b["dones"].dtype == np.bool_
+            # actions: bit-exact given the device probabilities and the master's uniforms
+            u = g["uniforms"][itr]                                     # (T, B)
+            prob = b["prob"].reshape(B, T, -1)
+            want = np.stack([osampler.weighted_sample_n(prob[:, s], u[s], 4) for s in range(T)], axis=1).reshape(-1)
+            stepped = np.ones(B * T, bool)
+            assert np.array_equal(b["actions"][stepped], want[stepped])
+            # prob / value of every row: the oracle net on that row's observation
+            p_ref, v_ref = onet.forward(torch.tensor(flat), torch.tensor(b["observations"]), spec, 4, emulate_bf16=True)
+            if mbr:   # (non-reset mode leaves stale observation rows after an env finished)
+                np.testing.assert_allclose(b["prob"], p_ref.numpy(), rtol=2e-3, atol=2e-5)
+                np.testing.assert_allclose(b["value"], v_ref.numpy(), rtol=2e-3, atol=2e-3)
+            ti = sorted([(i.Length, float(i.Return), float(i.RawReturn), int(i.NonzeroRewards), float(i.DiscountedReturn))
+                         for i in infos])
+            want_ti = g["traj_%d" % itr]
+            assert len(ti) == len(want_ti)
+            if len(ti):
+                np.testing.assert_allclose(np.array(ti, dtype=np.float64), want_ti, rtol=1e-5)
+        # samples_buf contract: struct with attribute + key access, per-env segment views (row = env*T + t)
+        assert buf.segs_view[1]["rewards"].data_ptr() == buf.rewards[T:2 * T].data_ptr()
+        assert buf["agent_infos"]["prob"].shape == (B * T, 4) and buf.segs_view[0].agent_infos["value"].shape == (T,)
+    finally:
+        pol.engine.close()
+
+
+def test_device_sampler_vs_oracle_larger_batch():
+    """B=64, T=16, default emulator rules, several iterations: device buffers == oracle restatement."""
+    from accel_rl_b200.util.seeding import set_seed
+    rules = dict(synth_ale.DEFAULT_RULES, pool_frames=256, life_base=40, life_mod=17, reward_mod=23, pool_seed=0)
+    set_seed(1)
+    B, T = 64, 16
+    sampler = _make_sampler(8, 4, T, rules=rules)
+    sampler.initialize(seed=2, affinities=dict(), discount=0.99, need_extra_obs=True)
+    pol, flat, spec = make_policy(1, max_rows=B)
+    sampler.policy_init(pol)
+    pool = synth_ale.make_pool(256, seed=0)
+    orc = osampler.OracleSampler(B, T, pool, {k: v for k, v in rules.items() if k != "pool_seed"}, 4, 0.99)
+    try:
+        n_traj = 0
+        for itr in range(5):
+            buf, infos = sampler.obtain_samples(itr)
+            b = _buf_np(buf)
+            u = sampler._uniforms_host.numpy().copy()
+            gp = b["prob"].reshape(B, T, 4); gv = b["value"].reshape(B, T)
+            calls = {"k": 0}
+
+            def policy_fn(obs):   # feed the oracle sampler the device's probabilities (same numerics)
+                k = calls["k"]; calls["k"] += 1
+                s, j = divmod(k, 2)
+                lo, hi = j * B // 2, (j + 1) * B // 2
+                return gp[lo:hi, s], gv[lo:hi, s]
+            ob, oinf = orc.obtain_samples(policy_fn, u)
+            for k in ("observations", "extra_observations", "rewards", "dones", "raw_reward", "need_reset", "actions"):
+                assert np.array_equal(b[k], ob[k]), (k, itr)
+            assert len(infos) == len(oinf)
+            n_traj += len(infos)
+        assert n_traj > 0
+    finally:
+        pol.engine.close()
+
+
+def _run_iteration(algo_name, B, T, spec_id, mbr, mb, epochs, standardize=False, itrs=2):
+    from accel_rl_b200.algos import PPO, A2C
+    from accel_rl_b200.util.seeding import set_seed
+    rules = dict(synth_ale.DEFAULT_RULES, pool_frames=128, life_base=24, life_mod=11, reward_mod=7, pool_seed=0)
+    set_seed(7)
+    sampler = _make_sampler(B // 4, 2, T, mid_batch_reset=mbr, rules=rules)
+    env_spec, sample_size, horizon, _ = sampler.initialize(seed=8, affinities=dict(), discount=0.99, need_extra_obs=True)
+    pol, flat, spec = make_policy(spec_id)
+    if algo_name == "ppo":
+        algo = PPO(optimizer_args=dict(minibatch_size=mb, epochs=epochs), standardize_adv=standardize)
+        opt = onet.Adam(flat.size, 1e-3, epsilon=1e-5)
+    else:
+        algo = A2C(standardize_adv=standardize)
+        opt = onet.RMSProp(flat.size, 7e-4)
+    algo.initialize(pol, env_spec, sample_size, horizon, mbr)
+    sampler.policy_init(pol)
+    algo.set_n_itr(10)
+    out = []
+    try:
+        for itr in range(itrs):
+            buf, _ = sampler.obtain_samples(itr)
+            b = _buf_np(buf)
+            rng_state = np.random.get_state()
+            opt_data, opt_infos = algo.optimize_policy(itr, buf)
+            torch.cuda.synchronize()
+            new = pol.get_param_values()
+            # oracle on the same buffers, same shuffles (replay the global stream)
+            rng = np.random.RandomState()
+            rng.set_state(rng_state)
+            last_values = t2n(algo._last_values)
+            flat_ref, losses, norms, od = olearner.optimize_policy(
+                flat, opt, b, spec, 4, T, algo_name, rng, epochs=epochs, minibatch_size=mb, use_valids=not mbr,
+                standardize_adv=standardize, last_values=last_values)
+            out.append(dict(flat_old=flat, flat_new=new, flat_ref=flat_ref, losses=losses, norms=norms, od=od,
+                            opt_data={k: t2n(v) for k, v in opt_data.items() if torch.is_tensor(v)},
+                            grad_norm=opt_infos["GradNorm"], value_after=t2n(buf.agent_infos.value)))
+            flat = new            # continue from the device's parameters (no drift accumulation in the check)
+            opt_sync = opt
+            if algo_name == "ppo":
+                opt_sync.m = t2n(pol.engine.m).copy(); opt_sync.v = t2n(pol.engine.v).copy()
+            else:
+                opt_sync.v = t2n(pol.engine.v).copy()
+    finally:
+        pol.engine.close()
+    return out
+
+
+@pytest.mark.parametrize("standardize", [False, True])
+def test_ppo_iteration_vs_oracle(standardize):
+    res = _run_iteration("ppo", B=16, T=16, spec_id=1, mbr=True, mb=64, epochs=2, standardize=standardize)
+    for r in res:
+        # advantages / returns: north-star 1e-4
+        np.testing.assert_allclose(r["opt_data"]["advantages"], r["od"]["advantages"], rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(r["opt_data"]["returns"], r["od"]["returns"], rtol=1e-4, atol=1e-4)
+        assert len(r["grad_norm"]) == len(r["norms"]) == 8
+        # first minibatch starts from identical parameters: tight
+        assert abs(r["grad_norm"][0] - r["norms"][0]) <= 5e-3 * r["norms"][0]
+        # Adam amplifies bf16-level gradient differences on near-zero-gradient coordinates; compare the
+        # accumulated update direction and size
+        du, dr = r["flat_new"] - r["flat_old"], r["flat_ref"] - r["flat_old"]
+        assert relerr(du, dr) < 0.15
+        cos = float(np.dot(du, dr) / (np.linalg.norm(du) * np.linalg.norm(dr)))
+        assert cos > 0.99
+
+
+def test_a2c_nonreset_iteration_vs_oracle():
+    """A2C as shipped by the reference example: mid_batch_reset=False -> valids mask, zero_after_reset,
+    valids-weighted loss means (SURVEY.md §8 a6')."""
+    res = _run_iteration("a2c", B=16, T=12, spec_id=0, mbr=False, mb=None, epochs=1, itrs=3)
+    saw_invalid = False
+    for r in res:
+        assert np.array_equal(r["opt_data"]["valids"], r["od"]["valids"])
+        saw_invalid |= bool((r["od"]["valids"] == 0).any())
+        np.testing.assert_allclose(r["opt_data"]["advantages"], r["od"]["advantages"], rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(r["opt_data"]["returns"], r["od"]["returns"], rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(r["value_after"], r["od"]["values"], rtol=0, atol=0)
+        assert abs(r["grad_norm"] - r["norms"][0]) <= 5e-3 * r["norms"][0]
+        du, dr = r["flat_new"] - r["flat_old"], r["flat_ref"] - r["flat_old"]
+        assert relerr(du, dr) < 0.05
+    assert saw_invalid, "test must exercise the validity mask"
+
+
+def test_runner_trains_and_logs(tmp_path):
+    from accel_rl_b200.algos import PPO
+    from accel_rl_b200.policies import AtariCnnPolicy, cnn_specs
+    from accel_rl_b200.runners import AccelRL
+    from accel_rl_b200.util import logger
+    rules = dict(synth_ale.DEFAULT_RULES, pool_frames=128, life_base=24, life_mod=11, reward_mod=7, pool_seed=0)
+    sampler = _make_sampler(4, 4, 16, rules=rules)
+    algo = PPO(optimizer_args=dict(minibatch_size=128, epochs=2), lr_schedule="linear")
+    policy = AtariCnnPolicy(**cnn_specs[0])
+    logger.configure(str(tmp_path), quiet=True)
+    runner = AccelRL(algo=algo, policy=policy, sampler=sampler, n_steps=32 * 16 * 6, seed=0, log_interval_steps=32 * 16 * 2)
+    runner.train()
+    row = dict(logger.last_row)
+    for k in ("Iteration", "CumTotalSteps", "Entropy", "GradNormAverage", "ParamsNorm", "NormFromInit", "SamplesPerSecond",
+              "LengthAverage", "ReturnAverage"):
+        assert k in row, k
+    assert row["NormFromInit"] > 0 and np.isfinite(row["GradNormAverage"])
+    assert os.path.exists(os.path.join(str(tmp_path), "progress.csv"))
+    policy.engine.close()
+    logger.configure(None)
+
+
+def test_runner_rejects_mismatched_parallelism():
+    from accel_rl_b200.algos import mPPO
+    from accel_rl_b200.policies import AtariCnnPolicy, cnn_specs
+    from accel_rl_b200.runners import AccelRL
+    with pytest.raises(TypeError):
+        AccelRL(algo=mPPO(), policy=AtariCnnPolicy(**cnn_specs[0]), sampler=_make_sampler(1, 1, 4), n_steps=100)
+
+
+def test_host_fed_rollout_runs():
+    """frame_feed='host': raw frames arrive from pinned host memory every step (H2D inside the step)."""
+    from accel_rl_b200.util.seeding import set_seed
+    set_seed(0)
+    sampler = _make_sampler(4, 2, 8, frame_feed="host", host_ring_steps=4)
+    sampler.initialize(seed=1, affinities=dict(), discount=0.99, need_extra_obs=True)
+    pol, flat, spec = make_policy(0, max_rows=16)
+    sampler.policy_init(pol)
+    try:
+        buf, _ = sampler.obtain_samples(0)
+        torch.cuda.synchronize()
+        obs = t2n(buf.observations)
+        assert obs[1].any() and sampler.h2d_bytes >= 8 * 16 * 2 * 33600
+        # newest plane of row (e, 1) is the box-downsample of max(ring frames) for step 0
+        from oracle import frame as oframe
+        ring = sampler._ring_host.numpy()
+        want = oframe.downsample(np.maximum(ring[0, 3, 0], ring[0, 3, 1]))
+        assert np.array_equal(obs[3 * 8 + 1, 3], want)
+    finally:
+        pol.engine.close()

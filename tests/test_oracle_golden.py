@@ -1,0 +1,113 @@
+"""Oracle restatement vs the golden fixtures generated from the reference's own code
+(tests/golden/make_golden.py).  CPU only."""
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from oracle import frame as oframe, gae as ogae, sampler as osampler, synth_ale, net as onet
+
+from tests.golden.make_golden import RULES, POOL_FRAMES, fake_policy_fn
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def test_frame_pipeline_matches_reference(golden_dir):
+    g = _load(golden_dir, "frames.npz")
+    got = oframe.update_obs_batch(g["stacks"], g["raw1"], g["raw2"], g["reset"])
+    assert got.dtype == np.uint8 and got.shape == g["out"].shape
+    assert np.array_equal(got, g["out"])
+
+
+@pytest.mark.parametrize("A", [4, 6, 18])
+def test_weighted_sample_n_matches_reference(golden_dir, A):
+    g = _load(golden_dir, "sampling.npz")
+    got = osampler.weighted_sample_n(g["p%d" % A], g["u%d" % A], A)
+    assert got.dtype == np.uint8
+    assert np.array_equal(got, g["a%d" % A])
+
+
+def test_uniform_stream_is_legacy_mt19937(golden_dir):
+    g = _load(golden_dir, "sampling.npz")
+    np.random.seed(77 + 4)
+    assert np.array_equal(np.random.rand(257), g["u4"])
+
+
+@pytest.mark.parametrize("name,lam", [("gae", 0.95), ("ret", 1.0)])
+def test_gae_matches_reference(golden_dir, name, lam):
+    g = _load(golden_dir, "gae.npz")
+    B, T = g["r"].shape
+    adv, ret, _, _ = ogae.process_samples(g["r"].ravel(), g["v"].ravel(), g["d"].ravel(), g["nr"].ravel(), g["lv"],
+                                          0.99, lam, T)
+    np.testing.assert_allclose(adv.reshape(B, T), g["adv_" + name], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(ret.reshape(B, T), g["ret_" + name], rtol=1e-5, atol=1e-6)
+    adv, ret, valids, v2 = ogae.process_samples(g["r"].ravel(), g["v"].ravel(), g["d"].ravel(), g["nr"].ravel(),
+                                                g["lv"], 0.99, lam, T, use_valids=True)
+    assert np.array_equal(valids.reshape(B, T), g["valids"])
+    np.testing.assert_allclose(adv.reshape(B, T), g["adv_%s_valid" % name], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(ret.reshape(B, T), g["ret_%s_valid" % name], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(v2.reshape(B, T), g["v_valid"], rtol=0, atol=0)
+
+
+def test_minibatch_indices_match_reference(golden_dir):
+    g = _load(golden_dir, "mb_idxs.npz")
+    rng = np.random.RandomState(int(g["seed"]))
+    for row in g["idx"]:
+        got = np.concatenate(list(onet.iterate_mb_idxs(int(g["batch"]), int(g["length"]), rng)))
+        assert np.array_equal(got, row)
+    # host-side product helper consumes the GLOBAL stream the same way
+    from accel_rl_b200.optimizers.util import iterate_mb_idxs, epoch_index_block
+    np.random.seed(int(g["seed"]))
+    for row in g["idx"]:
+        got = np.concatenate([b[0] for b in iterate_mb_idxs(int(g["batch"]), int(g["length"]), shuffle=True)])
+        assert np.array_equal(got, row)
+    np.random.seed(int(g["seed"]))
+    block, n_mb = epoch_index_block(int(g["batch"]), int(g["length"]), 3, True)
+    assert n_mb == 6 and np.array_equal(block.reshape(3, -1), g["idx"])
+
+
+@pytest.mark.parametrize("tag,mbr", [("reset", True), ("nonreset", False), ("overlength", True)])
+def test_sampler_restatement_matches_real_reference_sampler(golden_dir, tag, mbr):
+    g = _load(golden_dir, "sampler_%s.npz" % tag)
+    B, T, itrs = int(g["n_envs"]), int(g["horizon"]), int(g["itrs"])
+    pool = synth_ale.make_pool(POOL_FRAMES, seed=0)
+    s = osampler.OracleSampler(B, T, pool, RULES, n_actions=4, discount=0.99, mid_batch_reset=mbr,
+                               max_path_length=int(g["max_path_length"]))
+    for itr in range(itrs):
+        buf, infos = s.obtain_samples(lambda o: fake_policy_fn(o, 4), g["uniforms"][itr])
+        if itr == 0:
+            assert np.array_equal(buf["observations"], g["obs_0"])
+        crc = np.array([zlib.crc32(r.tobytes()) for r in buf["observations"]], dtype=np.uint32)
+        assert np.array_equal(crc, g["obscrc_%d" % itr]), "observation rows differ at itr %d" % itr
+        assert np.array_equal(buf["extra_observations"], g["extra_%d" % itr])
+        assert np.array_equal(buf["rewards"], g["rew_%d" % itr])
+        assert np.array_equal(buf["dones"], g["done_%d" % itr])
+        assert np.array_equal(buf["raw_reward"], g["raw_%d" % itr])
+        assert np.array_equal(buf["need_reset"], g["nr_%d" % itr])
+        assert np.array_equal(buf["actions"], g["act_%d" % itr])
+        np.testing.assert_array_equal(buf["prob"], g["prob_%d" % itr])
+        np.testing.assert_array_equal(buf["value"], g["val_%d" % itr])
+        ti = sorted([(i["Length"], float(i["Return"]), float(i["RawReturn"]), int(i["NonzeroRewards"]),
+                      float(i["DiscountedReturn"])) for i in infos])
+        want = g["traj_%d" % itr]
+        assert len(ti) == len(want)
+        if len(ti):
+            np.testing.assert_allclose(np.array(ti, dtype=np.float64), want, rtol=1e-6)
+
+
+def test_fixture_covers_edge_cases(golden_dir):
+    g = _load(golden_dir, "sampler_reset.npz")
+    dones = np.concatenate([g["done_%d" % i] for i in range(int(g["itrs"]))])
+    nr = np.concatenate([g["nr_%d" % i] for i in range(int(g["itrs"]))])
+    assert dones.any() and nr.any() and (dones & ~nr).any(), "fixture must contain life losses and game overs"
+    g2 = _load(golden_dir, "sampler_overlength.npz")
+    assert sum(len(g2["traj_%d" % i]) for i in range(int(g2["itrs"]))) > 0
+
+
+def test_net_param_count_matches_reference_comment():
+    # accel_rl/policies/atari_cnn_specs.py:22 "3.6M params", :10 "900k params"
+    assert onet.n_params(onet.CNN_SPECS[1], (4, 104, 80), 4) == 3620005
+    assert onet.n_params(onet.CNN_SPECS[0], (4, 104, 80), 4) == 898613
