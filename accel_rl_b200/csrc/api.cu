@@ -114,6 +114,11 @@ struct arl_ctx {
   const int* train_graph_idx = nullptr;
   int train_graph_mb = 0;
   long launches = 0;
+  // per-kernel CUDA-event profiling (arl_profile_*): events recorded after each launch when enabled
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<std::string> prof_names;
+  int prof_n = 0;
   long graph_rollout_nodes = 0, graph_train_nodes = 0;
   float lr_mult_host = 1.f;
   CommState comm;
@@ -131,6 +136,20 @@ int dev_alloc(arl_ctx* c, T** p, size_t count) {
 }
 
 int roundup(int x, int m) { return (x + m - 1) / m * m; }
+
+// record an event after the launch that just happened (profiling mode only)
+void prof_mark(arl_ctx* c, const char* name, cudaStream_t st) {
+  if (!c->prof_on) return;
+  if (c->prof_n >= (int)c->prof_ev.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    c->prof_ev.push_back(e);
+    c->prof_names.push_back("");
+  }
+  c->prof_names[c->prof_n] = name;
+  cudaEventRecord(c->prof_ev[c->prof_n], st);
+  c->prof_n++;
+}
 
 // ---------------------------------------------------------------------------
 // launch helpers
@@ -277,6 +296,15 @@ int plan_net(arl_ctx* c) {
   return 0;
 }
 
+int fc_splits(arl_ctx* c, int n, int& kbps) {
+  int kb = c->Kfc / 64;
+  int tiles = ((n + 127) / 128) * (c->H / 64);
+  int S = std::max(1, std::min(kb, (296 + tiles / 2) / tiles));
+  kbps = (kb + S - 1) / S;
+  S = (kb + kbps - 1) / kbps;
+  return S;
+}
+
 int alloc_net(arl_ctx* c) {
   const int R = c->cfg.max_rows;
   std::vector<PackJob> pj;
@@ -318,7 +346,15 @@ int alloc_net(arl_ctx* c) {
   c->n_pack_jobs = (int)pj.size();
   if (dev_alloc(c, &c->pack_jobs_dev, pj.size())) return 1;
   ARL_CHECK(c, cudaMemcpy(c->pack_jobs_dev, pj.data(), pj.size() * sizeof(PackJob), cudaMemcpyHostToDevice));
-  c->fc_partial_cap = (long)std::max(R, 4864) * c->H + 1024;
+  {
+    long worst = R;
+    for (int n = 1; n <= R; ++n) {
+      int kbps = 0;
+      long s = fc_splits(c, n, kbps);
+      worst = std::max(worst, s * n);
+    }
+    c->fc_partial_cap = worst * c->H + 1024;
+  }
   if (dev_alloc(c, &c->fc_partial, (size_t)c->fc_partial_cap)) return 1;
   if (dev_alloc(c, &c->h, (size_t)R * c->H)) return 1;
   if (dev_alloc(c, &c->dh, (size_t)R * c->H)) return 1;
@@ -348,14 +384,6 @@ RowEpi make_epi(int mode) {
   return e;
 }
 
-int fc_splits(arl_ctx* c, int n, int& kbps) {
-  int kb = c->Kfc / 64;
-  int tiles = ((n + 127) / 128) * (c->H / 64);
-  int S = std::max(1, std::min(kb, (296 + tiles / 2) / tiles));
-  kbps = (kb + S - 1) / S;
-  S = (kb + kbps - 1) / kbps;
-  return S;
-}
 
 // conv stack + FC partials for n observations (idx/idx_off optional gather)
 int forward_trunk(arl_ctx* c, const uint8_t* obs, const int* idx, const int* idx_off, int n, int* fc_S,
@@ -375,6 +403,7 @@ int forward_trunk(arl_ctx* c, const uint8_t* obs, const int* idx, const int* idx
       a.g.C = L.Cin; a.g.kh = L.k; a.g.stride = L.s; a.g.nrows = rows;
       if (launch_rowgemm_bn<ConvLoaderU8<128>, false>(c, L.Cout, a, w, e, rows, L.Cout, L.K / 64, L.K / 64, 1, st))
         return 1;
+      prof_mark(c, "conv0_fwd", st);
     } else {
       ConvLoader<128> a{};
       a.g.src = c->conv[l - 1].act; a.g.Qh = L.Ho; a.g.Qw = L.Wo; a.g.Hs = L.Hin; a.g.Ws = L.Win; a.g.C = L.Cin;
@@ -382,6 +411,7 @@ int forward_trunk(arl_ctx* c, const uint8_t* obs, const int* idx, const int* idx
       a.g.nrows = rows;
       if (launch_rowgemm_bn<ConvLoader<128>, false>(c, L.Cout, a, w, e, rows, L.Cout, L.K / 64, L.K / 64, 1, st))
         return 1;
+      prof_mark(c, l == 1 ? "conv1_fwd" : (l == 2 ? "conv2_fwd" : "conv3_fwd"), st);
     }
   }
   int kbps = 0;
@@ -393,6 +423,7 @@ int forward_trunk(arl_ctx* c, const uint8_t* obs, const int* idx, const int* idx
   a.src = c->conv.back().act; a.ld = c->Kfc; a.nrows = n;
   WeightSrc w{c->wfc_pack, (long)c->Kfc, 0};
   if (launch_rowgemm<DenseLoader<128>, false, 64>(c, a, w, e, n, c->H, c->Kfc / 64, kbps, S, st)) return 1;
+  prof_mark(c, "fc_fwd", st);
   *fc_S = S;
   return 0;
 }
@@ -417,6 +448,7 @@ int policy_forward(arl_ctx* c, const uint8_t* obs, const int* idx, int n, const 
   int blocks = std::min((n + 7) / 8, 148 * 2);
   head_kernel<0><<<blocks, 256, head_smem(c), st>>>(p);
   c->launches++;
+  prof_mark(c, "head_sample", st);
   ARL_CHECK(c, cudaGetLastError());
   return 0;
 }
@@ -496,6 +528,7 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
   p.h_out = c->h; p.dh_out = c->dh; p.dlogit_out = c->dlogit; p.loss_partial = c->loss_partial;
   head_kernel<1><<<kLossBlocks, 256, head_smem(c), st>>>(p);
   c->launches++;
+  prof_mark(c, "head_loss", st);
   ARL_CHECK(c, cudaGetLastError());
   {
     dim3 grid((c->H + 127) / 128, P->head_groups);
@@ -503,6 +536,7 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
     head_wgrad_kernel<<<grid, 128, sm, st>>>(c->h, c->dh, c->dlogit, n, c->H, c->A, P->head_rpg, c->head_partial,
                                               c->head_b_partial);
     c->launches++;
+    prof_mark(c, "head_wgrad", st);
     ARL_CHECK(c, cudaGetLastError());
   }
   ConvLayer& LL = c->conv.back();
@@ -515,6 +549,7 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
     e.fc_HW = c->HWlast;
     if (launch_wgrad<DenseLoader<64>, 1, 256>(c, a, c->dh, c->H, n, roundup(n, 64), 1, c->Kfc / 64, c->H / 256, e, st))
       return 1;
+    prof_mark(c, "fc_wgrad", st);
   }
   // ---- FC dgrad: da_last[n][Kfc] = dh Wfc^T, masked by a_last > 0 ----
   {
@@ -525,6 +560,7 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
     e.out = LL.dact; e.act = LL.act; e.ldo = c->Kfc; e.M = n;
     int BN = (c->Kfc % 128 == 0) ? 128 : 64;
     if (launch_rowgemm_bn<DenseLoader<128>, true>(c, BN, a, w, e, n, c->Kfc, c->H / 64, c->H / 64, 1, st)) return 1;
+    prof_mark(c, "fc_dgrad", st);
   }
   // ---- conv layers, last to first ----
   for (int l = (int)c->conv.size() - 1; l >= 0; --l) {
@@ -533,6 +569,10 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
     // bias grad partials
     colsum_kernel<<<P->conv_groups[l], 256, 0, st>>>(L.dact, rows, L.Cout, P->conv_rpg[l], c->bias_partial[l]);
     c->launches++;
+    static const char* kColsum[4] = {"conv0_bgrad", "conv1_bgrad", "conv2_bgrad", "conv3_bgrad"};
+    static const char* kWgrad[4] = {"conv0_wgrad", "conv1_wgrad", "conv2_wgrad", "conv3_wgrad"};
+    static const char* kDgrad[4] = {"conv0_dgrad", "conv1_dgrad", "conv2_dgrad", "conv3_dgrad"};
+    prof_mark(c, kColsum[l], st);
     ARL_CHECK(c, cudaGetLastError());
     // wgrad partials
     WgradEpi e{};
@@ -544,6 +584,7 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
       if (launch_wgrad_conv<ConvLoaderU8<64>>(c, a, L.dact, L.Cout, rows, P->conv_rps[l], P->conv_splits[l], L.K / 64, e,
                                               st))
         return 1;
+      prof_mark(c, kWgrad[l], st);
     } else {
       ConvLoader<64> a{};
       a.g.src = c->conv[l - 1].act; a.g.Qh = L.Ho; a.g.Qw = L.Wo; a.g.Hs = L.Hin; a.g.Ws = L.Win; a.g.C = L.Cin;
@@ -552,6 +593,7 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
       if (launch_wgrad_conv<ConvLoader<64>>(c, a, L.dact, L.Cout, rows, P->conv_rps[l], P->conv_splits[l], L.K / 64, e,
                                             st))
         return 1;
+      prof_mark(c, kWgrad[l], st);
       // dgrad into layer l-1's activation gradient (masked by its ReLU)
       ConvLayer& Lp = c->conv[l - 1];
       for (auto& d : L.dclasses) {
@@ -569,6 +611,7 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
         if (launch_rowgemm_bn<ConvLoader<128>, false>(c, L.Cin, g, w, ep, qrows, L.Cin, d.K / 64, d.K / 64, 1, st))
           return 1;
       }
+      prof_mark(c, kDgrad[l], st);
     }
   }
   // ---- sum partials, scatter into the flat gradient ----
@@ -576,6 +619,7 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
     dim3 grid(64, P->n_jobs);
     finalize_grads_kernel<<<grid, 256, 0, st>>>(P->jobs_dev, c->grad);
     c->launches++;
+    prof_mark(c, "finalize_grads", st);
     ARL_CHECK(c, cudaGetLastError());
   }
   return 0;
@@ -586,6 +630,7 @@ int pack_weights(arl_ctx* c, cudaStream_t st) {
   dim3 grid(148, c->n_pack_jobs);
   pack_weights_kernel<<<grid, 256, 0, st>>>(c->pack_jobs_dev, c->params);
   c->launches++;
+  prof_mark(c, "pack_weights", st);
   ARL_CHECK(c, cudaGetLastError());
   return 0;
 }
@@ -595,6 +640,7 @@ int clip_update(arl_ctx* c, float gscale, cudaStream_t st) {
   if (!c->m || !c->v) ARL_FAIL(c, "optimizer state not bound");
   sumsq_kernel<<<kSumsqBlocks, 256, 0, st>>>(c->grad, c->n_params, gscale, c->sumsq_partial);
   c->launches++;
+  prof_mark(c, "grad_sumsq", st);
   UpdateParams u{};
   u.param = c->params; u.grad = c->grad; u.m = c->m; u.v = c->v; u.n = c->n_params;
   u.sumsq_partial = c->sumsq_partial; u.n_partial = kSumsqBlocks;
@@ -605,8 +651,10 @@ int clip_update(arl_ctx* c, float gscale, cudaStream_t st) {
   u.out_norm = c->log_norm; u.out_loss = c->log_loss; u.log_slot = c->log_slot; u.log_cap = c->log_cap;
   update_kernel<<<148 * 4, 256, 0, st>>>(u);
   c->launches++;
+  prof_mark(c, "clip_update", st);
   advance_counters_kernel<<<1, 1, 0, st>>>(c->step, c->log_slot, c->mb_counter);
   c->launches++;
+  prof_mark(c, "advance_counters", st);
   ARL_CHECK(c, cudaGetLastError());
   return pack_weights(c, st);
 }
@@ -628,6 +676,7 @@ int launch_frame(arl_ctx* c, const uint8_t* staging, int s_next, bool to_rollout
   frame_kernel<<<blocks, 256, 0, st>>>(s.frame_pool, staging, c->cmd, s.step_obs, to_rollout ? s.observations : nullptr,
                                        s.horizon, s_next, s.n_envs, s.planes);
   c->launches++;
+  prof_mark(c, "frame", st);
   ARL_CHECK(c, cudaGetLastError());
   return 0;
 }
@@ -655,6 +704,7 @@ int rollout_step(arl_ctx* c, int s_idx, const uint8_t* staging, cudaStream_t st)
                                                    s.raw_reward, s.need_reset, B, T, s_idx, s.max_path_length,
                                                    s.discount, s.mid_batch_reset, s.clip_reward, s.episodic_lives);
   c->launches++;
+  prof_mark(c, "env_step", st);
   ARL_CHECK(c, cudaGetLastError());
   return launch_frame(c, staging, s_idx + 1, s_idx + 1 < T, st);
 }
@@ -1067,6 +1117,30 @@ int arl_debug_activation(arl_ctx* c, int layer, float* out, long cap, long* n, v
 }
 
 long arl_kernel_launches(arl_ctx* c) { return c->launches; }
+
+int arl_profile_begin(arl_ctx* c, void* stream) {
+  c->prof_on = true;
+  c->prof_n = 0;
+  prof_mark(c, "begin", (cudaStream_t)stream);
+  return 0;
+}
+
+int arl_profile_end(arl_ctx* c, char* names, int names_cap, float* ms, int cap, int* n, void* stream) {
+  ARL_CHECK(c, cudaStreamSynchronize((cudaStream_t)stream));
+  c->prof_on = false;
+  int cnt = std::min(cap, c->prof_n - 1);
+  std::string all;
+  for (int i = 0; i < cnt; ++i) {
+    float t = 0.f;
+    ARL_CHECK(c, cudaEventElapsedTime(&t, c->prof_ev[i], c->prof_ev[i + 1]));
+    ms[i] = t;
+    all += c->prof_names[i + 1];
+    all += ';';
+  }
+  *n = cnt < 0 ? 0 : cnt;
+  snprintf(names, names_cap, "%s", all.c_str());
+  return 0;
+}
 
 int arl_test_gemm(arl_ctx* c, const uint16_t* a_bf16, const uint16_t* b_bf16, float* d, int M, int N, int K,
                   int b_nmajor, void* stream) {

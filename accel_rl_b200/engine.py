@@ -183,6 +183,19 @@ class Engine(object):
     def reset_opt_state(self):
         self.check(self.lib.arl_reset_opt_state(self.ctx, self._s()))
 
+    # ---- profiling ---------------------------------------------------------------------------
+    def profile_begin(self):
+        self.check(self.lib.arl_profile_begin(self.ctx, self._s()))
+
+    def profile_end(self, cap=4096):
+        names = C.create_string_buffer(cap * 24)
+        ms = np.zeros(cap, np.float32)
+        n = C.c_int()
+        self.check(self.lib.arl_profile_end(self.ctx, names, len(names), ms.ctypes.data_as(C.c_void_p), cap,
+                                            C.byref(n), self._s()))
+        labels = names.value.decode().split(";")[:n.value]
+        return labels, ms[:n.value].copy()
+
     # ---- sync data parallel ------------------------------------------------------------------
     def comm_init(self, rank, world, exchange):
         """exchange(handle_bytes) -> list of every rank's handle bytes (e.g. torch.distributed all_gather)."""

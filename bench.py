@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: env-steps/s of full PPO iterations (rollout + GAE + 4-epoch update).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one PPO iteration over one batch of synthetic emulator frames: 256 envs/GPU x 128-step
+rollout (policy forward + action sampling + env step + frame pipeline per step), bootstrap value +
+GAE, then 4 epochs x 64 shuffled minibatches of 512 (forward, losses, backward, clip, Adam) —
+BASELINE.json configs[1] (PPO Breakout-shaped, 256 envs, Nature-CNN preset 1 @ (4,104,80), bf16
+tensor-core operands / fp32 accumulate).  `value` keeps the frame pool resident in HBM; `e2e` feeds
+the raw frames of every step from pinned host memory through the same public API
+(sampler.obtain_samples / algo.optimize_policy) with the H2D/D2H copies inside the timed region.
+`--impl reference` times the CPU port of the reference path (oracle/) on the host cores.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# per-sample MACs of preset 1 @ (4,104,80), A=4
+MACS = {"conv0": 3891200, "conv1": 3538944, "conv2": 3981312, "fc": 3538944}
+FLOP_PER_ENV_STEP_PPO = 357.9e6     # 1 act-fwd + 1/128 bootstrap fwd + 4 x train (81.936 MFLOP)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=256)
+    ap.add_argument("--horizon", type=int, default=128)
+    ap.add_argument("--spec", type=int, default=1)
+    ap.add_argument("--minibatch", type=int, default=512)
+    ap.add_argument("--epochs", type=int, default=4)
+    ap.add_argument("--pool-frames", type=int, default=4096)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-steps", type=int, default=8, help="rollout steps in the bounded CPU sample")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        reasons = []
+        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
+            if any(r[col].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows)}
+
+
+# =============================================================================================
+# our arm
+# =============================================================================================
+def build_runner(args, frame_feed, rank, world):
+    import torch
+    from accel_rl_b200.algos import PPO, mPPO
+    from accel_rl_b200.envs import AtariEnv
+    from accel_rl_b200.policies import AtariCnnPolicy, cnn_specs
+    from accel_rl_b200.runners import AccelRL, AccelRLSync
+    from accel_rl_b200.sampler import ActsrvAltOvrlpSampler
+    from accel_rl_b200.util import logger
+    logger.configure(None, quiet=True)
+    rules = dict(pool_frames=args.pool_frames)
+    sampler = ActsrvAltOvrlpSampler(
+        EnvCls=AtariEnv, env_args=dict(game="breakout", max_start_noops=0, synth_rules=rules),
+        horizon=args.horizon, n_parallel=args.envs // 8, envs_per=4, max_path_length=27000, mid_batch_reset=True,
+        max_decorrelation_steps=0, frame_feed=frame_feed)
+    opt_args = dict(minibatch_size=args.minibatch, epochs=args.epochs)
+    policy = AtariCnnPolicy(**cnn_specs[args.spec])
+    n_steps = args.envs * args.horizon * 10 ** 6
+    if world > 1:
+        runner = AccelRLSync(algo=mPPO(optimizer_args=opt_args), policy=policy, sampler=sampler, n_steps=n_steps, seed=0,
+                             affinities=[dict(gpu=torch.cuda.current_device())] * world, log_interval_steps=10 ** 12)
+    else:
+        runner = AccelRL(algo=PPO(optimizer_args=opt_args), policy=policy, sampler=sampler, n_steps=n_steps, seed=0,
+                         affinities=dict(), log_interval_steps=10 ** 12)
+    runner.startup()
+    return runner
+
+
+def timed_iterations(runner, steps, warmup, world, itr0=0):
+    """-> (ms per step on the device: max over ranks, launches, host wall seconds)"""
+    import torch
+    import torch.distributed as dist
+    eng = runner.policy.engine
+    itr = itr0
+    for _ in range(warmup):
+        s, _ = runner.sampler.obtain_samples(itr)
+        runner.algo.optimize_policy(itr, s)
+        itr += 1
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = eng.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    ev0.record()
+    last = None
+    for _ in range(steps):
+        s, _ = runner.sampler.obtain_samples(itr)
+        _, info = runner.algo.optimize_policy(itr, s)      # reads losses / grad norms back (D2H)
+        last = info
+        itr += 1
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    wall = time.time() - t0
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms / steps, eng.launches - l0, wall, last, itr
+
+
+def kernel_breakdown(runner, args):
+    """CUDA-event duration of every kernel of one minibatch update and one rollout step (launched outside the
+    graphs, same order, same data) -> {label: (avg ms, launches per PPO iteration)}"""
+    import numpy as np
+    import torch
+    eng = runner.policy.engine
+    N = args.envs * args.horizon
+    reps = 6
+    idx = torch.randperm(N, device="cuda")[:reps * args.minibatch].to(torch.int32).contiguous()
+    acc = {}
+    for warm in (True, False):
+        for r in range(reps):
+            eng.profile_begin()
+            eng.grad_minibatch(idx[r * args.minibatch:(r + 1) * args.minibatch], args.minibatch)
+            eng.clip_update(1.0)
+            labels, ms = eng.profile_end()
+            if not warm:
+                for l, t in zip(labels, ms):
+                    acc.setdefault(l, []).append(float(t))
+    n_mb = (N // args.minibatch) * args.epochs
+    out = {l: (float(np.mean(v)) * (len(v) / reps), n_mb) for l, v in acc.items()}   # dgrad classes share a label
+    acc = {}
+    eng.rollout_begin()
+    for s in range(min(12, args.horizon)):
+        eng.profile_begin()
+        eng.rollout_step(s)
+        labels, ms = eng.profile_end()
+        if s >= 4:
+            for l, t in zip(labels, ms):
+                acc.setdefault("rollout/" + l, []).append(float(t))
+    eng.rollout_end()
+    eng.read_logs()
+    for l, v in acc.items():
+        out[l] = (float(np.mean(v)), args.horizon)
+    return out
+
+
+def kernel_flops(label, n, args):
+    """algorithmic FLOPs of one launch processing n samples (None for non-GEMM kernels)"""
+    base = label.split("/")[-1]
+    for k in ("conv0", "conv1", "conv2"):
+        if base.startswith(k + "_") and base.split("_")[1] in ("fwd", "wgrad", "dgrad"):
+            return 2.0 * MACS[k] * n
+    if base in ("fc_fwd", "fc_wgrad", "fc_dgrad"):
+        return 2.0 * MACS["fc"] * n
+    return None
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pk = peaks()
+    runner = build_runner(args, "device", rank, world)
+    N = args.envs * args.horizon
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms_step, launches, wall, last, itr = timed_iterations(runner, args.steps, args.warmup, world)
+    clk = clocks.summary() if rank == 0 else None
+    value = world * N / (ms_step * 1e-3)
+
+    result = None
+    if rank == 0:
+        bd = kernel_breakdown(runner, args) if args.spec == 1 else {}
+        # dominant kernel by time per PPO iteration
+        roof = None
+        kernels = []
+        total_ms = sum(t * c for t, c in bd.values())
+        for label, (t, count) in sorted(bd.items(), key=lambda kv: -kv[1][0] * kv[1][1]):
+            n = args.envs if label.startswith("rollout/") else args.minibatch
+            fl = kernel_flops(label, n, args)
+            kernels.append({"kernel": label, "ms": round(t, 5), "launches_per_step": count,
+                            "share": round(t * count / total_ms, 4) if total_ms else None,
+                            "tflops": round(fl / (t * 1e-3) / 1e12, 2) if fl else None})
+        for k in kernels:
+            if k["tflops"] is not None:
+                roof = {"bound": "tensor", "kernel": k["kernel"], "achieved": k["tflops"], "peak": pk["tf_sustained"],
+                        "unit": "TFLOP/s", "frac": round(k["tflops"] / pk["tf_sustained"], 4), "traffic": None,
+                        "peak_source": pk["src"] + " (sustained bf16, kernel timed inside a long step)",
+                        "share_of_step": k["share"]}
+                break
+        result = {
+            "metric": "env-steps/sec (PPO Atari, 256 envs/GPU)", "value": round(value, 1), "unit": "env-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "PPO Breakout-shaped, %d envs/GPU x %d-step rollout, cnn preset %d @ (4,104,80), "
+                                   "%d epochs x mb %d, Adam; synthetic 210x160 grayscale emulator frames"
+                                   % (args.envs, args.horizon, args.spec, args.epochs, args.minibatch),
+                       "envs_per_gpu": args.envs, "horizon": args.horizon, "parallelism": "dp%d" % world,
+                       "l2_policy": "inputs larger than L2 (1.09 GB rollout buffer, %d MB frame pool)" %
+                                    (args.pool_frames * 33600 // 2 ** 20),
+                       "step": "one full PPO iteration"},
+            "clocks": clk,
+            "gpu_launches": int(launches),
+            "model_flops_per_env_step": FLOP_PER_ENV_STEP_PPO if args.spec == 1 else None,
+            "tensor_roofline_frac_whole_step": round(value / world * FLOP_PER_ENV_STEP_PPO / (pk["tf_sustained"] * 1e12), 4)
+            if args.spec == 1 else None,
+            "roofline": roof,
+            "kernels": kernels[:14],
+            "host_wall_s": round(wall, 3),
+        }
+    # ---- e2e: raw frames from pinned host memory every step, results read back ----
+    if not args.no_e2e:
+        runner.policy.engine.close()
+        del runner
+        torch.cuda.empty_cache()
+        r2 = build_runner(args, "host", rank, world)
+        smp = r2.sampler
+        h0, d0 = smp.h2d_bytes, smp.d2h_bytes
+        steps2 = max(2, args.steps // 2)
+        ms2, _, _, _, _ = timed_iterations(r2, steps2, max(1, args.warmup // 2), world)
+        n_it = steps2 + max(1, args.warmup // 2)
+        idx_bytes = args.epochs * (N // args.minibatch) * args.minibatch * 4
+        log_bytes = 2 * 4 * args.epochs * (N // args.minibatch)
+        if rank == 0:
+            result["e2e"] = {"value": round(world * N / (ms2 * 1e-3), 1), "unit": "env-steps/s",
+                             "h2d_bytes_per_step": int((smp.h2d_bytes - h0) / n_it + idx_bytes),
+                             "d2h_bytes_per_step": int((smp.d2h_bytes - d0) / n_it + log_bytes),
+                             "ms_per_step": round(ms2, 3),
+                             "note": "raw emulator frames (2 x 210x160 u8 per env-step) H2D from pinned memory on a copy "
+                                     "stream, actions D2H every step, losses/grad norms D2H every iteration"}
+        r2.policy.engine.close()
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        result["cpu_baseline"] = cpu_port(args, steps=1)
+    if rank == 0:
+        print(json.dumps(result))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# =============================================================================================
+# CPU port of the reference path (oracle/): --impl reference and the cpu_baseline leg
+# =============================================================================================
+def cpu_port(args, steps=1, warmup=0):
+    """The reference's CPU implementation of the path, restated (oracle/): vectorised-sampler semantics with the
+    synthetic emulator + fp32 policy on the CPU + GAE + PPO epochs, on a BOUNDED sample of the workload:
+    `--cpu-sample-steps` rollout steps of all envs, trained for the same epochs x minibatch ratio."""
+    import numpy as np
+    import torch
+    from oracle import net as onet, sampler as osampler, learner as olearner, synth_ale
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B, Ts = args.envs, args.cpu_sample_steps
+    spec = onet.CNN_SPECS[args.spec]
+    rules = dict(synth_ale.DEFAULT_RULES, pool_frames=256)
+    pool = synth_ale.make_pool(256, seed=0)
+    flat = onet.init_params(spec, (4, 104, 80), 4, np.random.RandomState(0), np.random.RandomState(1))
+    smp = osampler.OracleSampler(B, Ts, pool, rules, 4, 0.99)
+    opt = onet.Adam(flat.size, 1e-3, epsilon=1e-5)
+    rng = np.random.RandomState(0)
+
+    def policy_fn(obs):
+        with torch.no_grad():
+            p, v = onet.forward(torch.from_numpy(flat), torch.from_numpy(obs), spec, 4)
+        return p.numpy(), v.numpy()
+
+    mb = min(args.minibatch, B * Ts)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.time()
+        buf, _ = smp.obtain_samples(policy_fn, rng.rand(Ts, B))
+        t1 = time.time()
+        flat, _, _, _ = olearner.optimize_policy(flat, opt, buf, spec, 4, Ts, "ppo", rng, epochs=args.epochs,
+                                                 minibatch_size=mb, emulate_bf16=False)
+        t2 = time.time()
+        if it >= warmup:
+            times.append((t1 - t0, t2 - t1))
+    samp = float(np.mean([a for a, _ in times]))
+    learn = float(np.mean([b for _, b in times]))
+    n = B * Ts
+    return {"value": round(n / (samp + learn), 1), "unit": "env-steps/s", "cores": cores, "kind": "port",
+            "sample": "%d envs x %d rollout steps (%d env-steps) + GAE + %d epochs x mb %d on them; oracle/ port: Theano "
+                      "replaced by an fp32 torch-CPU restatement (%d threads), ALE by the synthetic emulator"
+                      % (B, Ts, n, args.epochs, mb, cores),
+            "sampler_env_steps_per_s": round(n / samp, 1), "learner_env_steps_per_s": round(n / learn, 1),
+            "seconds_per_sample": round(samp + learn, 2)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.time()
+    r = cpu_port(args, steps=max(1, args.steps), warmup=min(1, args.warmup))
+    N = args.envs * args.horizon
+    out = {"impl": "reference", "metric": "env-steps/sec (PPO Atari, 256 envs/GPU)", "value": r["value"],
+           "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": round(1e3 * N / r["value"], 1), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "PPO Breakout-shaped, %d envs x %d-step rollout, cnn preset %d @ (4,104,80), %d epochs x "
+                                  "mb %d (CPU port of the reference path; ms_per_step extrapolated from the bounded sample)"
+                                  % (args.envs, args.horizon, args.spec, args.epochs, args.minibatch)},
+           "cpu_baseline": r,
+           "e2e": {"value": r["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "wall_s": round(time.time() - t0, 1)}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -154,7 +154,11 @@ int arl_comm_barrier(arl_ctx* ctx, void* stream);
 /* ---- diagnostics / tests ---------------------------------------------------------------------- */
 /* intermediate activations of the last forward (bf16 -> fp32 copies into host-visible device buffers) */
 int arl_debug_activation(arl_ctx* ctx, int layer, float* out, long cap, long* n, void* stream);
-long arl_kernel_launches(arl_ctx* ctx);   /* launches issued (graph replays count their node count) */
+long arl_kernel_launches(arl_ctx* ctx);
+/* CUDA-event timing of every kernel launched (outside graphs) between begin and end, on `stream`:
+ * names = ';'-separated launch labels, ms[i] = device time of launch i */
+int arl_profile_begin(arl_ctx* ctx, void* stream);
+int arl_profile_end(arl_ctx* ctx, char* names, int names_cap, float* ms, int cap, int* n, void* stream);   /* launches issued (graph replays count their node count) */
 /* plain tcgen05 GEMM self-test: D[M][N] = A[M][K] * B (B K-major [N][K] or N-major [K][N]) */
 int arl_test_gemm(arl_ctx* ctx, const uint16_t* a_bf16, const uint16_t* b_bf16, float* d, int M, int N, int K,
                   int b_nmajor, void* stream);
