@@ -37,27 +37,32 @@ std::string g_create_error;
     return 2;               \
   } while (0)
 
+// One conv layer as the GEMM tiles see it.  Layer 0 is evaluated over the bf16 space-to-depth(stride)
+// image of the observation: an 8x8/4 conv over (C,104,80) == a 2x2/1 conv over (26,20,C*16).
 struct ConvLayer {
+  // reference view (parameters, gradients)
   int Cin, Hin, Win, Cout, k, s, p, Ho, Wo;
-  int K;                 // Cin*k*k
-  long off_W, off_b;     // flat param offsets
-  __nv_bfloat16* wpack;  // [Cout][K] forward operand
-  // dgrad classes (layers >= 1)
-  struct DClass {
+  // tile view (NHWC source)
+  int gC, gH, gW, gk, gs, gp;   // source channels / dims, taps per side, stride, pad
+  int K;                        // gC*gk*gk == Cin*k*k
+  long off_W, off_b;            // flat param offsets
+  __nv_bfloat16* wpack;         // [Cout][K] forward operand
+  struct DClass {               // dgrad stride-parity classes (layers >= 1)
     int ry, rx, qy0, qx0, Qh, Qw, Ty, Tx, K;
-    __nv_bfloat16* wpack;  // [Cin][K]
+    __nv_bfloat16* wpack;       // [Cin][K]
   };
   std::vector<DClass> dclasses;
-  __nv_bfloat16* act;    // [max_rows*Ho*Wo][Cout]
+  __nv_bfloat16* act;           // [max_rows*Ho*Wo][Cout]
   __nv_bfloat16* dact;
 };
 
 struct TrainPlan {
   int n = 0;
-  std::vector<int> conv_splits, conv_rps, conv_groups, conv_rpg;
+  std::vector<int> conv_splits, conv_rps;
   int head_groups = 0, head_rpg = 0;
   GradJob* jobs_dev = nullptr;
   int n_jobs = 0;
+  int fin_blocks = 1;
 };
 
 }  // namespace
@@ -69,7 +74,9 @@ struct arl_ctx {
   int Kfc = 0, H = 0, A = 0, HWlast = 0, Clast = 0;
   long off_Wfc = 0, off_bfc = 0, off_Wpi = 0, off_bpi = 0, off_Wv = 0, off_bv = 0, n_params = 0;
   std::vector<long> lay_off, lay_size;
-  __nv_bfloat16* wfc_pack = nullptr;  // [H][Kfc]
+  long obs16_elems = 0;                // bf16 elements of one space-to-depth observation
+  __nv_bfloat16* obs16_stage = nullptr;  // [max_rows] converted inputs (callers that hand in uint8 obs)
+  __nv_bfloat16* wfc_bf16 = nullptr;   // [Kfc][H] bf16 copy of the FC weights in the reference's row order
   PackJob* pack_jobs_dev = nullptr;
   int n_pack_jobs = 0;
   // bound vectors
@@ -81,7 +88,7 @@ struct arl_ctx {
   float* dlogit = nullptr;
   std::vector<float*> wgrad_partial;  // per conv layer
   std::vector<long> wgrad_partial_cap;
-  std::vector<float*> bias_partial;
+  std::vector<float*> bias_partial;   // per conv layer [splits][Cout]
   float* head_partial = nullptr;   // [G][H][A+2]
   float* head_b_partial = nullptr; // [G][A+1]
   float* loss_partial = nullptr;   // [kLossBlocks][4]
@@ -93,7 +100,6 @@ struct arl_ctx {
   int log_cap = 4096;
   int* mb_counter = nullptr;       // minibatch index for graph-replayed training
   float* valid_count = nullptr;
-  float* dbg = nullptr;
   std::map<int, TrainPlan> plans;
   // training inputs
   const uint8_t* t_obs = nullptr; const uint8_t* t_act = nullptr; const float* t_adv = nullptr;
@@ -107,7 +113,9 @@ struct arl_ctx {
   EnvState est{};
   TrajOut tout{};
   FrameCmd* cmd = nullptr;
-  int* rows_tab = nullptr;   // [T][B] row indices e*T+s
+  int* rows_tab = nullptr;             // [T][B] row indices e*T+s
+  __nv_bfloat16* step_obs16 = nullptr; // [B] bf16 space-to-depth mirror of step_obs
+  __nv_bfloat16* roll_obs16 = nullptr; // [N] mirror of observations
   cudaGraphExec_t rollout_graph = nullptr;
   // training graph cache
   cudaGraphExec_t train_graph = nullptr;
@@ -127,6 +135,7 @@ struct arl_ctx {
 namespace {
 
 constexpr int kLossBlocks = 64;
+constexpr int kMaxSplits = 160;
 
 template <class T>
 int dev_alloc(arl_ctx* c, T** p, size_t count) {
@@ -175,12 +184,28 @@ template <class ALoad, bool BNM>
 int launch_rowgemm_bn(arl_ctx* c, int BN, ALoad a, WeightSrc b, RowEpi e, int M, int Ntot, int num_kb, int kbps,
                       int splits, cudaStream_t st) {
   switch (BN) {
-    case 16: return launch_rowgemm<ALoad, BNM, 16>(c, a, b, e, M, Ntot, num_kb, kbps, splits, st);
-    case 32: return launch_rowgemm<ALoad, BNM, 32>(c, a, b, e, M, Ntot, num_kb, kbps, splits, st);
+    case 16: if constexpr (!BNM) return launch_rowgemm<ALoad, BNM, 16>(c, a, b, e, M, Ntot, num_kb, kbps, splits, st); break;
+    case 32: if constexpr (!BNM) return launch_rowgemm<ALoad, BNM, 32>(c, a, b, e, M, Ntot, num_kb, kbps, splits, st); break;
     case 64: return launch_rowgemm<ALoad, BNM, 64>(c, a, b, e, M, Ntot, num_kb, kbps, splits, st);
     case 128: return launch_rowgemm<ALoad, BNM, 128>(c, a, b, e, M, Ntot, num_kb, kbps, splits, st);
   }
   ARL_FAIL(c, "unsupported tile width BN=" + std::to_string(BN));
+}
+
+template <class ALoad, int BN>
+int launch_rowgemm_multi(arl_ctx* c, const RowGemmMulti<ALoad>& p, int ncls, int max_tiles, cudaStream_t st) {
+  using Cfg = RowGemmCfg<BN>;
+  static bool attr = false;
+  if (!attr) {
+    ARL_CHECK(c, cudaFuncSetAttribute(rowgemm_multi_kernel<ALoad, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      Cfg::SMEM));
+    attr = true;
+  }
+  dim3 grid(max_tiles, ncls, 1);
+  rowgemm_multi_kernel<ALoad, BN><<<grid, kGemmThreads, Cfg::SMEM, st>>>(p);
+  c->launches++;
+  ARL_CHECK(c, cudaGetLastError());
+  return 0;
 }
 
 template <class ALoad, int MT, int BN>
@@ -194,7 +219,7 @@ int launch_wgrad(arl_ctx* c, ALoad a, const __nv_bfloat16* dy, int ld_dy, int nr
     attr = true;
   }
   dim3 grid((atoms + MT * 2 - 1) / (MT * 2), ntiles, splits);
-  wgrad_kernel<ALoad, MT, BN><<<grid, kGemmThreads, Cfg::SMEM, st>>>(a, dy, ld_dy, nrows, rps, atoms, e);
+  wgrad_kernel<ALoad, MT, BN><<<grid, kWgradThreads, Cfg::SMEM, st>>>(a, dy, ld_dy, nrows, rps, atoms, e);
   c->launches++;
   ARL_CHECK(c, cudaGetLastError());
   return 0;
@@ -206,6 +231,7 @@ int launch_wgrad_conv(arl_ctx* c, ALoad a, const __nv_bfloat16* dy, int Cout, in
   int mt_need = (atoms + 1) / 2;
 #define ARL_WG(MT, BN) return launch_wgrad<ALoad, MT, BN>(c, a, dy, Cout, nrows, rps, splits, atoms, 1, e, st)
   if (Cout == 16) {
+    if (mt_need <= 1) ARL_WG(1, 16);
     if (mt_need <= 2) ARL_WG(2, 16);
     if (mt_need <= 4) ARL_WG(4, 16);
     ARL_WG(5, 16);
@@ -229,9 +255,6 @@ int plan_net(arl_ctx* c) {
   const arl_net_cfg& f = c->cfg;
   if (f.n_conv < 1 || f.n_conv > ARL_MAX_CONV) ARL_FAIL(c, "n_conv out of range");
   if (f.n_actions < 1 || f.n_actions > kMaxActions) ARL_FAIL(c, "n_actions must be in [1,18]");
-  if (f.in_h != kObsH || f.in_w != kObsW) {
-    // the conv path itself is size-generic; only the frame kernel is fixed at 104x80
-  }
   int C = f.in_c, Hh = f.in_h, Ww = f.in_w;
   long off = 0;
   for (int l = 0; l < f.n_conv; ++l) {
@@ -245,10 +268,13 @@ int plan_net(arl_ctx* c) {
     if (L.Cout != 16 && L.Cout != 32 && L.Cout != 64)
       ARL_FAIL(c, "conv layer " + std::to_string(l) + ": filters must be 16, 32 or 64");
     if (l == 0) {
-      if (L.k != 8 || L.p != 0 || (L.s % 4) || (Ww % 4))
-        ARL_FAIL(c, "first conv layer must be 8x8, pad 0, stride multiple of 4 (uint8 gather path)");
+      if (L.s != 4 || L.k != 2 * L.s || L.p != 0 || (Hh % L.s) || (Ww % L.s))
+        ARL_FAIL(c, "first conv layer must be 8x8, stride 4, pad 0 on dims divisible by 4 (space-to-depth path)");
+      L.gC = L.Cin * L.s * L.s; L.gH = Hh / L.s; L.gW = Ww / L.s; L.gk = 2; L.gs = 1; L.gp = 0;
+      c->obs16_elems = (long)L.gH * L.gW * L.gC;
     } else {
       if (L.Cin % 8) ARL_FAIL(c, "conv input channels must be a multiple of 8");
+      L.gC = L.Cin; L.gH = Hh; L.gW = Ww; L.gk = L.k; L.gs = L.s; L.gp = L.p;
     }
     L.off_W = off; off += (long)L.Cout * L.Cin * L.k * L.k;
     L.off_b = off; off += L.Cout;
@@ -274,6 +300,7 @@ int plan_net(arl_ctx* c) {
           if (d.K % 64) ARL_FAIL(c, "conv dgrad K not a multiple of 64");
           if (d.Qh > 0 && d.Qw > 0) L.dclasses.push_back(d);
         }
+      if ((int)L.dclasses.size() > kMaxMulti) ARL_FAIL(c, "conv stride > 2 is not supported in the backward pass");
     }
     c->conv.push_back(L);
     C = L.Cout; Hh = L.Ho; Ww = L.Wo;
@@ -315,8 +342,8 @@ int alloc_net(arl_ctx* c) {
     if (dev_alloc(c, &L.dact, act_elems)) return 1;
     if (dev_alloc(c, &L.wpack, (size_t)L.Cout * L.K)) return 1;
     PackJob j{};
-    j.dst = L.wpack; j.src_off = L.off_W; j.kind = (l == 0) ? PK_CONV_CHW : PK_CONV_NHWC;
-    j.rows = L.Cout; j.cols = L.K; j.Cout = L.Cout; j.C = L.Cin; j.kh = L.k; j.kw = L.k;
+    j.dst = L.wpack; j.src_off = L.off_W; j.kind = (l == 0) ? PK_CONV_S2D : PK_CONV_NHWC;
+    j.rows = L.Cout; j.cols = L.K; j.Cout = L.Cout; j.C = L.Cin; j.kh = L.k; j.kw = L.k; j.s = L.s;
     pj.push_back(j);
     for (auto& d : L.dclasses) {
       if (dev_alloc(c, &d.wpack, (size_t)L.Cin * d.K)) return 1;
@@ -326,26 +353,25 @@ int alloc_net(arl_ctx* c) {
       q.s = L.s; q.ry = d.ry; q.rx = d.rx; q.Tx = d.Tx;
       pj.push_back(q);
     }
-    // wgrad partials: splits <= 160
-    long cap = (long)160 * L.K * L.Cout;
+    long cap = (long)kMaxSplits * L.K * L.Cout;
     float* wp = nullptr;
     if (dev_alloc(c, &wp, (size_t)cap)) return 1;
     c->wgrad_partial.push_back(wp);
     c->wgrad_partial_cap.push_back(cap);
     float* bp = nullptr;
-    if (dev_alloc(c, &bp, (size_t)160 * L.Cout)) return 1;
+    if (dev_alloc(c, &bp, (size_t)kMaxSplits * L.Cout)) return 1;
     c->bias_partial.push_back(bp);
   }
-  if (dev_alloc(c, &c->wfc_pack, (size_t)c->H * c->Kfc)) return 1;
+  if (dev_alloc(c, &c->wfc_bf16, (size_t)c->H * c->Kfc)) return 1;
   {
     PackJob j{};
-    j.dst = c->wfc_pack; j.src_off = c->off_Wfc; j.kind = PK_FC; j.rows = c->H; j.cols = c->Kfc;
-    j.C = c->Clast; j.HW = c->HWlast; j.ldsrc = c->H;
+    j.dst = c->wfc_bf16; j.src_off = c->off_Wfc; j.kind = PK_CAST; j.rows = c->Kfc; j.cols = c->H;
     pj.push_back(j);
   }
   c->n_pack_jobs = (int)pj.size();
   if (dev_alloc(c, &c->pack_jobs_dev, pj.size())) return 1;
   ARL_CHECK(c, cudaMemcpy(c->pack_jobs_dev, pj.data(), pj.size() * sizeof(PackJob), cudaMemcpyHostToDevice));
+  if (dev_alloc(c, &c->obs16_stage, (size_t)R * c->obs16_elems)) return 1;
   {
     long worst = R;
     for (int n = 1; n <= R; ++n) {
@@ -384,9 +410,34 @@ RowEpi make_epi(int mode) {
   return e;
 }
 
+// forward gather geometry of layer l reading `src` (NHWC bf16), n images
+ConvGeom fwd_geom(const ConvLayer& L, const __nv_bfloat16* src, int n) {
+  ConvGeom g{};
+  g.src = src; g.Qh = L.Ho; g.Qw = L.Wo; g.Hs = L.gH; g.Ws = L.gW; g.C = L.gC;
+  g.sy = L.gs; g.y0 = -L.gp; g.dty = 1; g.sx = L.gs; g.x0 = -L.gp; g.dtx = 1; g.Tx = L.gk;
+  g.nrows = n * L.Ho * L.Wo;
+  return g;
+}
 
-// conv stack + FC partials for n observations (idx/idx_off optional gather)
-int forward_trunk(arl_ctx* c, const uint8_t* obs, const int* idx, const int* idx_off, int n, int* fc_S,
+static const char* kFwdName[4] = {"conv0_fwd", "conv1_fwd", "conv2_fwd", "conv3_fwd"};
+static const char* kWgradName[4] = {"conv0_wgrad", "conv1_wgrad", "conv2_wgrad", "conv3_wgrad"};
+static const char* kDgradName[4] = {"conv0_dgrad", "conv1_dgrad", "conv2_dgrad", "conv3_dgrad"};
+
+// uint8 CHW observations -> bf16 space-to-depth staging rows [0, n)
+int convert_obs(arl_ctx* c, const uint8_t* obs, const int* idx, int n, cudaStream_t st) {
+  const ConvLayer& L0 = c->conv[0];
+  long work = (long)n * L0.Cin * L0.Hin * (L0.Win / 4);
+  int blocks = (int)std::min<long>((work + 255) / 256, 148 * 16);
+  obs_to_s2d_kernel<<<blocks, 256, 0, st>>>(obs, idx, c->obs16_stage, n, L0.Cin, L0.Hin, L0.Win);
+  c->launches++;
+  prof_mark(c, "obs_to_s2d", st);
+  ARL_CHECK(c, cudaGetLastError());
+  return 0;
+}
+
+// conv stack + FC split-K partials for n observations given as bf16 space-to-depth images
+// (idx/idx_off: optional image gather applied by the first layer's loader)
+int forward_trunk(arl_ctx* c, const __nv_bfloat16* obs16, const int* idx, const int* idx_off, int n, int* fc_S,
                   cudaStream_t st) {
   if (n > c->cfg.max_rows) ARL_FAIL(c, "batch larger than max_rows");
   if (!c->params) ARL_FAIL(c, "parameters not bound");
@@ -395,24 +446,13 @@ int forward_trunk(arl_ctx* c, const uint8_t* obs, const int* idx, const int* idx
     int rows = n * L.Ho * L.Wo;
     RowEpi e = make_epi(EPI_BIAS_RELU_BF16);
     e.bias = c->params + L.off_b; e.out = L.act; e.ldo = L.Cout; e.M = rows;
-    WeightSrc w{L.wpack, (long)L.K, 0};
-    if (l == 0) {
-      e.scale = 1.f / c->cfg.pixel_scale;
-      ConvLoaderU8<128> a{};
-      a.g.src = obs; a.g.idx = idx; a.g.idx_off = idx_off; a.g.Qh = L.Ho; a.g.Qw = L.Wo; a.g.Hs = L.Hin; a.g.Ws = L.Win;
-      a.g.C = L.Cin; a.g.kh = L.k; a.g.stride = L.s; a.g.nrows = rows;
-      if (launch_rowgemm_bn<ConvLoaderU8<128>, false>(c, L.Cout, a, w, e, rows, L.Cout, L.K / 64, L.K / 64, 1, st))
-        return 1;
-      prof_mark(c, "conv0_fwd", st);
-    } else {
-      ConvLoader<128> a{};
-      a.g.src = c->conv[l - 1].act; a.g.Qh = L.Ho; a.g.Qw = L.Wo; a.g.Hs = L.Hin; a.g.Ws = L.Win; a.g.C = L.Cin;
-      a.g.sy = L.s; a.g.y0 = -L.p; a.g.dty = 1; a.g.sx = L.s; a.g.x0 = -L.p; a.g.dtx = 1; a.g.Tx = L.k;
-      a.g.nrows = rows;
-      if (launch_rowgemm_bn<ConvLoader<128>, false>(c, L.Cout, a, w, e, rows, L.Cout, L.K / 64, L.K / 64, 1, st))
-        return 1;
-      prof_mark(c, l == 1 ? "conv1_fwd" : (l == 2 ? "conv2_fwd" : "conv3_fwd"), st);
-    }
+    if (l == 0) e.scale = 1.f / c->cfg.pixel_scale;
+    WeightSrc w{L.wpack, (long)L.K, 0, RowPerm{0, 0}};
+    ConvLoader<128> a{};
+    a.g = fwd_geom(L, l == 0 ? obs16 : c->conv[l - 1].act, n);
+    if (l == 0) { a.g.idx = idx; a.g.idx_off = idx_off; }
+    if (launch_rowgemm_bn<ConvLoader<128>, false>(c, L.Cout, a, w, e, rows, L.Cout, L.K / 64, L.K / 64, 1, st)) return 1;
+    prof_mark(c, kFwdName[l], st);
   }
   int kbps = 0;
   int S = fc_splits(c, n, kbps);
@@ -421,8 +461,9 @@ int forward_trunk(arl_ctx* c, const uint8_t* obs, const int* idx, const int* idx
   e.partial = c->fc_partial; e.ldo = c->H; e.M = n;
   DenseLoader<128> a{};
   a.src = c->conv.back().act; a.ld = c->Kfc; a.nrows = n;
-  WeightSrc w{c->wfc_pack, (long)c->Kfc, 0};
-  if (launch_rowgemm<DenseLoader<128>, false, 64>(c, a, w, e, n, c->H, c->Kfc / 64, kbps, S, st)) return 1;
+  // B = the FC weights in the reference's (c,h,w)-row order, read N-major through the (hw,c) row permutation
+  WeightSrc w{c->wfc_bf16, (long)c->H, c->Kfc, RowPerm{c->Clast, c->HWlast}};
+  if (launch_rowgemm<DenseLoader<128>, true, 64>(c, a, w, e, n, c->H, c->Kfc / 64, kbps, S, st)) return 1;
   prof_mark(c, "fc_fwd", st);
   *fc_S = S;
   return 0;
@@ -439,10 +480,10 @@ HeadParams head_base(arl_ctx* c, int n, int S) {
   return p;
 }
 
-int policy_forward(arl_ctx* c, const uint8_t* obs, const int* idx, int n, const int* out_rows, float* prob,
-                   float* value, const double* uniforms, uint8_t* actions, cudaStream_t st) {
+int policy_forward16(arl_ctx* c, const __nv_bfloat16* obs16, int n, const int* out_rows, float* prob, float* value,
+                     const double* uniforms, uint8_t* actions, cudaStream_t st) {
   int S = 0;
-  if (forward_trunk(c, obs, idx, nullptr, n, &S, st)) return 1;
+  if (forward_trunk(c, obs16, nullptr, nullptr, n, &S, st)) return 1;
   HeadParams p = head_base(c, n, S);
   p.out_rows = out_rows; p.prob = prob; p.value = value; p.uniforms = uniforms; p.actions = uniforms ? actions : nullptr;
   int blocks = std::min((n + 7) / 8, 148 * 2);
@@ -451,6 +492,13 @@ int policy_forward(arl_ctx* c, const uint8_t* obs, const int* idx, int n, const 
   prof_mark(c, "head_sample", st);
   ARL_CHECK(c, cudaGetLastError());
   return 0;
+}
+
+int policy_forward(arl_ctx* c, const uint8_t* obs, const int* idx, int n, const int* out_rows, float* prob,
+                   float* value, const double* uniforms, uint8_t* actions, cudaStream_t st) {
+  if (n > c->cfg.max_rows) ARL_FAIL(c, "batch larger than max_rows");
+  if (convert_obs(c, obs, idx, n, st)) return 1;
+  return policy_forward16(c, c->obs16_stage, n, out_rows, prob, value, uniforms, actions, st);
 }
 
 // ---------------------------------------------------------------------------
@@ -462,27 +510,26 @@ int get_plan(arl_ctx* c, int n, TrainPlan** out) {
   TrainPlan P;
   P.n = n;
   std::vector<GradJob> jobs;
+  long max_total = 1;
   for (size_t l = 0; l < c->conv.size(); ++l) {
     ConvLayer& L = c->conv[l];
     int rows = n * L.Ho * L.Wo;
     int rps = roundup((rows + 147) / 148, 64);
     int splits = (rows + rps - 1) / rps;
-    if ((long)splits * L.K * L.Cout > c->wgrad_partial_cap[l]) ARL_FAIL(c, "wgrad partial workspace too small");
+    if (splits > kMaxSplits) ARL_FAIL(c, "wgrad partial workspace too small");
     P.conv_splits.push_back(splits); P.conv_rps.push_back(rps);
-    int rpg = std::max(64, (rows + 147) / 148);
-    int groups = (rows + rpg - 1) / rpg;
-    P.conv_groups.push_back(groups); P.conv_rpg.push_back(rpg);
     GradJob w{};
     w.src = c->wgrad_partial[l]; w.S = splits; w.sstride = (long)L.K * L.Cout; w.rows = L.K; w.cols = L.Cout;
-    w.ld = L.Cout; w.map = (l == 0) ? GM_CONV_CHW : GM_CONV_NHWC; w.scale = (l == 0) ? 1.f / c->cfg.pixel_scale : 1.f;
-    w.dst_off = L.off_W; w.C = L.Cin; w.kh = L.k; w.kw = L.k;
+    w.ld = L.Cout; w.map = (l == 0) ? GM_CONV_S2D : GM_CONV_NHWC; w.scale = (l == 0) ? 1.f / c->cfg.pixel_scale : 1.f;
+    w.dst_off = L.off_W; w.C = L.Cin; w.kh = L.k; w.kw = L.k; w.s2d = L.s;
     jobs.push_back(w);
+    max_total = std::max(max_total, (long)w.rows * w.cols);
     GradJob b{};
-    b.src = c->bias_partial[l]; b.S = groups; b.sstride = L.Cout; b.rows = 1; b.cols = L.Cout; b.ld = L.Cout;
+    b.src = c->bias_partial[l]; b.S = splits; b.sstride = L.Cout; b.rows = 1; b.cols = L.Cout; b.ld = L.Cout;
     b.map = GM_LINEAR; b.scale = 1.f; b.dst_off = L.off_b;
     jobs.push_back(b);
   }
-  P.head_rpg = std::max(32, (n + 63) / 64);
+  P.head_rpg = std::max(8, (n + 63) / 64);
   P.head_groups = (n + P.head_rpg - 1) / P.head_rpg;
   {
     GradJob hj{};
@@ -490,6 +537,7 @@ int get_plan(arl_ctx* c, int n, TrainPlan** out) {
     hj.cols = c->A + 2; hj.ld = c->A + 2; hj.map = GM_HEAD; hj.scale = 1.f; hj.dst_off = c->off_Wpi;
     hj.dst_off2 = c->off_Wv; hj.dst_off3 = c->off_bfc; hj.A = c->A;
     jobs.push_back(hj);
+    max_total = std::max(max_total, (long)hj.rows * hj.cols);
     GradJob bp{};
     bp.src = c->head_b_partial; bp.S = P.head_groups; bp.sstride = c->A + 1; bp.rows = 1; bp.cols = c->A;
     bp.ld = c->A + 1; bp.map = GM_LINEAR; bp.scale = 1.f; bp.dst_off = c->off_bpi;
@@ -499,6 +547,7 @@ int get_plan(arl_ctx* c, int n, TrainPlan** out) {
     jobs.push_back(bv);
   }
   P.n_jobs = (int)jobs.size();
+  P.fin_blocks = (int)((max_total + 255) / 256);
   ARL_CHECK(c, cudaMalloc(reinterpret_cast<void**>(&P.jobs_dev), jobs.size() * sizeof(GradJob)));
   ARL_CHECK(c, cudaMemcpy(P.jobs_dev, jobs.data(), jobs.size() * sizeof(GradJob), cudaMemcpyHostToDevice));
   auto res = c->plans.emplace(n, P);
@@ -513,8 +562,19 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
   if (!c->grad) ARL_FAIL(c, "gradient vector not bound");
   TrainPlan* P = nullptr;
   if (get_plan(c, n, &P)) return 1;
+  // first-layer input: the sampler's bf16 mirror of the rollout (gathered by the loader), or a conversion
+  // of the caller's uint8 rows into the staging buffer
+  const __nv_bfloat16* obs16;
+  const int *gidx, *gidx_off;
+  if (c->sampler_set && c->t_obs == c->sc.observations && c->roll_obs16) {
+    obs16 = c->roll_obs16; gidx = idx; gidx_off = idx_off;
+  } else {
+    if (idx_off) ARL_FAIL(c, "graph-replayed training needs the sampler's rollout buffers as training inputs");
+    if (convert_obs(c, c->t_obs, idx, n, st)) return 1;
+    obs16 = c->obs16_stage; gidx = nullptr; gidx_off = nullptr;
+  }
   int S = 0;
-  if (forward_trunk(c, c->t_obs, idx, idx_off, n, &S, st)) return 1;
+  if (forward_trunk(c, obs16, gidx, gidx_off, n, &S, st)) return 1;
   // ---- head: losses + dlogits + dh ----
   if (c->t_valids) {
     count_valids_idx_kernel<<<1, 1024, 0, st>>>(c->t_valids, idx, idx_off, n, c->valid_count);
@@ -555,68 +615,64 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
   {
     DenseLoader<128> a{};
     a.src = c->dh; a.ld = c->H; a.nrows = n;
-    WeightSrc w{c->wfc_pack, (long)c->Kfc, c->H};
+    WeightSrc w{c->wfc_bf16, (long)c->H, 0, RowPerm{c->Clast, c->HWlast}};   // K-major rows n in (hw,c) order
     RowEpi e = make_epi(EPI_MASK_BF16);
     e.out = LL.dact; e.act = LL.act; e.ldo = c->Kfc; e.M = n;
     int BN = (c->Kfc % 128 == 0) ? 128 : 64;
-    if (launch_rowgemm_bn<DenseLoader<128>, true>(c, BN, a, w, e, n, c->Kfc, c->H / 64, c->H / 64, 1, st)) return 1;
+    if (launch_rowgemm_bn<DenseLoader<128>, false>(c, BN, a, w, e, n, c->Kfc, c->H / 64, c->H / 64, 1, st)) return 1;
     prof_mark(c, "fc_dgrad", st);
   }
   // ---- conv layers, last to first ----
   for (int l = (int)c->conv.size() - 1; l >= 0; --l) {
     ConvLayer& L = c->conv[l];
     int rows = n * L.Ho * L.Wo;
-    // bias grad partials
-    colsum_kernel<<<P->conv_groups[l], 256, 0, st>>>(L.dact, rows, L.Cout, P->conv_rpg[l], c->bias_partial[l]);
-    c->launches++;
-    static const char* kColsum[4] = {"conv0_bgrad", "conv1_bgrad", "conv2_bgrad", "conv3_bgrad"};
-    static const char* kWgrad[4] = {"conv0_wgrad", "conv1_wgrad", "conv2_wgrad", "conv3_wgrad"};
-    static const char* kDgrad[4] = {"conv0_dgrad", "conv1_dgrad", "conv2_dgrad", "conv3_dgrad"};
-    prof_mark(c, kColsum[l], st);
-    ARL_CHECK(c, cudaGetLastError());
-    // wgrad partials
+    // weight-gradient partials (+ bias-gradient partials from the same pass over dY)
     WgradEpi e{};
     e.out = c->wgrad_partial[l]; e.mode = 0; e.Kvalid = L.K; e.Kp = L.K; e.ldo = L.Cout;
-    if (l == 0) {
-      ConvLoaderU8<64> a{};
-      a.g.src = c->t_obs; a.g.idx = idx; a.g.idx_off = idx_off; a.g.Qh = L.Ho; a.g.Qw = L.Wo; a.g.Hs = L.Hin;
-      a.g.Ws = L.Win; a.g.C = L.Cin; a.g.kh = L.k; a.g.stride = L.s; a.g.nrows = rows;
-      if (launch_wgrad_conv<ConvLoaderU8<64>>(c, a, L.dact, L.Cout, rows, P->conv_rps[l], P->conv_splits[l], L.K / 64, e,
-                                              st))
-        return 1;
-      prof_mark(c, kWgrad[l], st);
-    } else {
-      ConvLoader<64> a{};
-      a.g.src = c->conv[l - 1].act; a.g.Qh = L.Ho; a.g.Qw = L.Wo; a.g.Hs = L.Hin; a.g.Ws = L.Win; a.g.C = L.Cin;
-      a.g.sy = L.s; a.g.y0 = -L.p; a.g.dty = 1; a.g.sx = L.s; a.g.x0 = -L.p; a.g.dtx = 1; a.g.Tx = L.k;
-      a.g.nrows = rows;
-      if (launch_wgrad_conv<ConvLoader<64>>(c, a, L.dact, L.Cout, rows, P->conv_rps[l], P->conv_splits[l], L.K / 64, e,
-                                            st))
-        return 1;
-      prof_mark(c, kWgrad[l], st);
-      // dgrad into layer l-1's activation gradient (masked by its ReLU)
-      ConvLayer& Lp = c->conv[l - 1];
-      for (auto& d : L.dclasses) {
-        int qrows = n * d.Qh * d.Qw;
-        ConvLoader<128> g{};
-        g.g.src = L.dact; g.g.Qh = d.Qh; g.g.Qw = d.Qw; g.g.Hs = L.Ho; g.g.Ws = L.Wo; g.g.C = L.Cout;
-        g.g.sy = 1; g.g.y0 = d.qy0; g.g.dty = -1; g.g.sx = 1; g.g.x0 = d.qx0; g.g.dtx = -1; g.g.Tx = d.Tx;
-        g.g.nrows = qrows;
-        WeightSrc w{d.wpack, (long)d.K, 0};
-        RowEpi ep = make_epi(EPI_MASK_BF16);
-        ep.out = Lp.dact; ep.act = Lp.act; ep.ldo = L.Cin; ep.M = qrows;
-        ep.map_s = L.s; ep.map_y0 = L.s * d.qy0 + d.ry - L.p; ep.map_x0 = L.s * d.qx0 + d.rx - L.p;
-        ep.map_Qh = d.Qh; ep.map_Qw = d.Qw; ep.map_H = L.Hin; ep.map_W = L.Win;
-        if (L.s == 1 && ep.map_y0 == 0 && ep.map_x0 == 0 && d.Qh == L.Hin && d.Qw == L.Win) ep.map_s = 0;
-        if (launch_rowgemm_bn<ConvLoader<128>, false>(c, L.Cin, g, w, ep, qrows, L.Cin, d.K / 64, d.K / 64, 1, st))
-          return 1;
-      }
-      prof_mark(c, kDgrad[l], st);
+    e.bias_out = c->bias_partial[l];
+    ConvLoader<64> a{};
+    a.g = fwd_geom(L, l == 0 ? obs16 : c->conv[l - 1].act, n);
+    if (l == 0) { a.g.idx = gidx; a.g.idx_off = gidx_off; }
+    if (launch_wgrad_conv<ConvLoader<64>>(c, a, L.dact, L.Cout, rows, P->conv_rps[l], P->conv_splits[l], L.K / 64, e, st))
+      return 1;
+    prof_mark(c, kWgradName[l], st);
+    if (l == 0) break;
+    // dgrad into layer l-1's activation gradient (masked by its ReLU): all stride-parity classes in one launch
+    ConvLayer& Lp = c->conv[l - 1];
+    RowGemmMulti<ConvLoader<128>> mp{};
+    int ncls = 0, max_tiles = 0;
+    for (auto& d : L.dclasses) {
+      int qrows = n * d.Qh * d.Qw;
+      ConvGeom g{};
+      g.src = L.dact; g.Qh = d.Qh; g.Qw = d.Qw; g.Hs = L.Ho; g.Ws = L.Wo; g.C = L.Cout;
+      g.sy = 1; g.y0 = d.qy0; g.dty = -1; g.sx = 1; g.x0 = d.qx0; g.dtx = -1; g.Tx = d.Tx;
+      g.nrows = qrows;
+      mp.a[ncls].g = g;
+      mp.b[ncls] = WeightSrc{d.wpack, (long)d.K, 0, RowPerm{0, 0}};
+      RowEpi ep = make_epi(EPI_MASK_BF16);
+      ep.out = Lp.dact; ep.act = Lp.act; ep.ldo = L.Cin; ep.M = qrows;
+      ep.map_s = L.s; ep.map_y0 = L.s * d.qy0 + d.ry - L.p; ep.map_x0 = L.s * d.qx0 + d.rx - L.p;
+      ep.map_Qh = d.Qh; ep.map_Qw = d.Qw; ep.map_H = L.Hin; ep.map_W = L.Win;
+      if (L.s == 1 && ep.map_y0 == 0 && ep.map_x0 == 0 && d.Qh == L.Hin && d.Qw == L.Win) ep.map_s = 0;
+      mp.e[ncls] = ep;
+      mp.mtiles[ncls] = (qrows + 127) / 128;
+      mp.num_kb[ncls] = d.K / 64;
+      max_tiles = std::max(max_tiles, mp.mtiles[ncls]);
+      ++ncls;
     }
+    int rc;
+    switch (L.Cin) {
+      case 16: rc = launch_rowgemm_multi<ConvLoader<128>, 16>(c, mp, ncls, max_tiles, st); break;
+      case 32: rc = launch_rowgemm_multi<ConvLoader<128>, 32>(c, mp, ncls, max_tiles, st); break;
+      case 64: rc = launch_rowgemm_multi<ConvLoader<128>, 64>(c, mp, ncls, max_tiles, st); break;
+      default: ARL_FAIL(c, "unsupported dgrad width");
+    }
+    if (rc) return rc;
+    prof_mark(c, kDgradName[l], st);
   }
   // ---- sum partials, scatter into the flat gradient ----
   {
-    dim3 grid(64, P->n_jobs);
+    dim3 grid(P->fin_blocks, P->n_jobs);
     finalize_grads_kernel<<<grid, 256, 0, st>>>(P->jobs_dev, c->grad);
     c->launches++;
     prof_mark(c, "finalize_grads", st);
@@ -627,7 +683,7 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
 
 int pack_weights(arl_ctx* c, cudaStream_t st) {
   if (!c->params) ARL_FAIL(c, "parameters not bound");
-  dim3 grid(148, c->n_pack_jobs);
+  dim3 grid(148 * 2, c->n_pack_jobs);
   pack_weights_kernel<<<grid, 256, 0, st>>>(c->pack_jobs_dev, c->params);
   c->launches++;
   prof_mark(c, "pack_weights", st);
@@ -674,7 +730,8 @@ int launch_frame(arl_ctx* c, const uint8_t* staging, int s_next, bool to_rollout
   long items = (long)s.n_envs * 520;
   int blocks = (int)((items + 255) / 256);
   frame_kernel<<<blocks, 256, 0, st>>>(s.frame_pool, staging, c->cmd, s.step_obs, to_rollout ? s.observations : nullptr,
-                                       s.horizon, s_next, s.n_envs, s.planes);
+                                       c->step_obs16, to_rollout ? c->roll_obs16 : nullptr, s.horizon, s_next, s.n_envs,
+                                       s.planes);
   c->launches++;
   prof_mark(c, "frame", st);
   ARL_CHECK(c, cudaGetLastError());
@@ -685,10 +742,15 @@ int rollout_begin(arl_ctx* c, cudaStream_t st) {
   const arl_sampler_cfg& s = c->sc;
   int row_bytes = s.planes * kObsH * kObsW;
   long chunks = (long)s.n_envs * (row_bytes / 16);
-  // observations[e*T + 0] = step_obs[e]   (worker.py:31-32)
+  // observations[e*T + 0] = step_obs[e]   (worker.py:31-32) — and the same for the bf16 mirror
   copy_rows_kernel<<<(int)((chunks + 255) / 256), 256, 0, st>>>(s.step_obs, row_bytes, nullptr, s.observations, row_bytes,
                                                                c->rows_tab, s.n_envs, row_bytes);
-  c->launches++;
+  int row16 = (int)(c->obs16_elems * 2);
+  long chunks16 = (long)s.n_envs * (row16 / 16);
+  copy_rows_kernel<<<(int)((chunks16 + 255) / 256), 256, 0, st>>>(
+      reinterpret_cast<const uint8_t*>(c->step_obs16), row16, nullptr, reinterpret_cast<uint8_t*>(c->roll_obs16), row16,
+      c->rows_tab, s.n_envs, row16);
+  c->launches += 2;
   ARL_CHECK(c, cudaMemsetAsync(c->tout.count, 0, sizeof(int), st));
   ARL_CHECK(c, cudaGetLastError());
   return 0;
@@ -697,8 +759,8 @@ int rollout_begin(arl_ctx* c, cudaStream_t st) {
 int rollout_step(arl_ctx* c, int s_idx, const uint8_t* staging, cudaStream_t st) {
   const arl_sampler_cfg& s = c->sc;
   const int B = s.n_envs, T = s.horizon;
-  if (policy_forward(c, s.step_obs, nullptr, B, c->rows_tab + (long)s_idx * B, s.prob, s.value,
-                     s.uniforms + (long)s_idx * B, s.actions, st))
+  if (policy_forward16(c, c->step_obs16, B, c->rows_tab + (long)s_idx * B, s.prob, s.value,
+                       s.uniforms + (long)s_idx * B, s.actions, st))
     return 1;
   env_step_kernel<<<(B + 127) / 128, 128, 0, st>>>(synth_cfg(s), c->est, c->tout, c->cmd, s.rewards, s.dones,
                                                    s.raw_reward, s.need_reset, B, T, s_idx, s.max_path_length,
@@ -770,10 +832,10 @@ void arl_destroy(arl_ctx* c) {
   }
   for (auto p : c->wgrad_partial) cudaFree(p);
   for (auto p : c->bias_partial) cudaFree(p);
-  cudaFree(c->wfc_pack); cudaFree(c->pack_jobs_dev); cudaFree(c->fc_partial); cudaFree(c->h); cudaFree(c->dh);
+  cudaFree(c->wfc_bf16); cudaFree(c->obs16_stage); cudaFree(c->step_obs16); cudaFree(c->roll_obs16); cudaFree(c->pack_jobs_dev); cudaFree(c->fc_partial); cudaFree(c->h); cudaFree(c->dh);
   cudaFree(c->dlogit); cudaFree(c->head_partial); cudaFree(c->head_b_partial); cudaFree(c->loss_partial);
   cudaFree(c->sumsq_partial); cudaFree(c->hyper); cudaFree(c->step); cudaFree(c->log_slot); cudaFree(c->log_norm);
-  cudaFree(c->log_loss); cudaFree(c->mb_counter); cudaFree(c->valid_count); cudaFree(c->dbg);
+  cudaFree(c->log_loss); cudaFree(c->mb_counter); cudaFree(c->valid_count);
   for (auto& kv : c->plans) cudaFree(kv.second.jobs_dev);
   if (c->rollout_graph) cudaGraphExecDestroy(c->rollout_graph);
   if (c->train_graph) cudaGraphExecDestroy(c->train_graph);
@@ -864,6 +926,9 @@ int arl_sampler_configure(arl_ctx* c, const arl_sampler_cfg* cfg) {
   for (int s = 0; s < T; ++s)
     for (int e = 0; e < B; ++e) rt[(size_t)s * B + e] = e * T + s;
   ARL_CHECK(c, cudaMemcpy(c->rows_tab, rt.data(), rt.size() * sizeof(int), cudaMemcpyHostToDevice));
+  // bf16 space-to-depth mirrors of the step buffer and of the rollout observations (what conv layer 0 reads)
+  if (dev_alloc(c, &c->step_obs16, (size_t)B * c->obs16_elems)) return 1;
+  if (dev_alloc(c, &c->roll_obs16, (size_t)B * T * c->obs16_elems)) return 1;
   c->sampler_set = true;
   if (c->rollout_graph) { cudaGraphExecDestroy(c->rollout_graph); c->rollout_graph = nullptr; }
   return 0;
@@ -995,6 +1060,14 @@ int arl_clip_update(arl_ctx* c, float gscale, void* stream) { return clip_update
 
 int arl_train_minibatches(arl_ctx* c, const int* idx, int mb_size, int count, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  if (!(c->sampler_set && c->t_obs == c->sc.observations && c->roll_obs16)) {
+    // training inputs that are not the sampler's rollout buffers: plain launches, one minibatch at a time
+    for (int i = 0; i < count; ++i) {
+      if (grad_minibatch(c, idx + (long)i * mb_size, nullptr, mb_size, st)) return 1;
+      if (clip_update(c, 1.f, st)) return 1;
+    }
+    return 0;
+  }
   if (c->train_graph && (c->train_graph_idx != idx || c->train_graph_mb != mb_size)) {
     cudaGraphExecDestroy(c->train_graph);
     c->train_graph = nullptr;
@@ -1151,10 +1224,10 @@ int arl_test_gemm(arl_ctx* c, const uint16_t* a_bf16, const uint16_t* b_bf16, fl
   RowEpi e = make_epi(EPI_PARTIAL_F32);
   e.partial = d; e.ldo = N; e.M = M;
   if (b_nmajor) {
-    WeightSrc w{reinterpret_cast<const __nv_bfloat16*>(b_bf16), (long)N, K};
+    WeightSrc w{reinterpret_cast<const __nv_bfloat16*>(b_bf16), (long)N, K, RowPerm{0, 0}};
     return launch_rowgemm<DenseLoader<128>, true, 64>(c, a, w, e, M, N, K / 64, K / 64, 1, st);
   }
-  WeightSrc w{reinterpret_cast<const __nv_bfloat16*>(b_bf16), (long)K, 0};
+  WeightSrc w{reinterpret_cast<const __nv_bfloat16*>(b_bf16), (long)K, 0, RowPerm{0, 0}};
   return launch_rowgemm<DenseLoader<128>, false, 64>(c, a, w, e, M, N, K / 64, K / 64, 1, st);
 }
 

@@ -20,6 +20,8 @@
 namespace arl {
 
 constexpr int kProducerWarps = 8;
+constexpr int kWgradProducerWarps = 16;                    // wgrad: two groups of 8 alternate stages
+constexpr int kWgradThreads = kWgradProducerWarps * 32 + 32;
 constexpr int kProducerThreads = kProducerWarps * 32;  // 256
 constexpr int kGemmThreads = kProducerThreads + 32;    // + MMA warp
 constexpr int kBK = 64;                                // K elements per stage (128 B of bf16)
@@ -28,19 +30,32 @@ constexpr int kBK = 64;                                // K elements per stage (
 // operand loaders (run by the 256 producer threads; tid in [0,256))
 // ---------------------------------------------------------------------------
 
+// Row permutation of a dense source: logical row q (in (hw, c) order) lives at source row
+// (q % C) * HW + q / C  — the FC weight matrix is kept in the reference's (c, h, w) row order while
+// the activations are NHWC.  C == 0: identity.
+struct RowPerm {
+  int C, HW;
+};
+ARL_DEVINL int perm_row(const RowPerm& p, int q) {
+  if (p.C == 0) return q;
+  int hw = q / p.C;
+  return (q - hw * p.C) * p.HW + hw;
+}
+
 // Dense row-major bf16 source: copies R rows x ROWB bytes into a swizzled tile.
-//   tile row r  <- src[(row0 + r) * ld + col0 .. + ROWB/2)   (zero when row0+r >= nrows)
-template <int R, int ROWB>
+//   tile row r  <- src[perm(row0 + r) * ld + col0 .. + ROWB/2)   (zero when row0+r >= nrows)
+// NT = number of threads cooperating (tid in [0, NT)).
+template <int R, int ROWB, int NT = 256>
 ARL_DEVINL void fill_dense(uint32_t tile, const __nv_bfloat16* __restrict__ src, long ld, int row0, int nrows,
-                           int col0, int tid) {
+                           int col0, int tid, RowPerm perm = RowPerm{0, 0}) {
   constexpr int CH = ROWB / 16;        // 16-byte chunks per row
   constexpr int TOTAL = R * CH;        // chunks in the tile
 #pragma unroll
-  for (int i = tid; i < TOTAL; i += kProducerThreads) {
+  for (int i = tid; i < TOTAL; i += NT) {
     int r = i / CH, c = i % CH;
     uint4 v = make_uint4(0, 0, 0, 0);
     int row = row0 + r;
-    if (row < nrows) v = __ldg(reinterpret_cast<const uint4*>(src + (long)row * ld + col0 + c * 8));
+    if (row < nrows) v = __ldg(reinterpret_cast<const uint4*>(src + (long)perm_row(perm, row) * ld + col0 + c * 8));
     st_shared_v4(tile + swz_off<ROWB>(r, c), v);
   }
 }
@@ -50,6 +65,8 @@ ARL_DEVINL void fill_dense(uint32_t tile, const __nv_bfloat16* __restrict__ src,
 //   src_y = qy * sy + y0 + ty * dty,  src_x = qx * sx + x0 + tx * dtx   (out of range -> 0)
 struct ConvGeom {
   const __nv_bfloat16* src;
+  const int* idx;        // optional image gather: image b reads source image idx[off*nb + b]
+  const int* idx_off;    // optional device scalar `off` (minibatch index, graph-replayed training)
   int Qh, Qw;            // row grid per image
   int Hs, Ws, C;         // source dims
   int sy, y0, dty;
@@ -74,7 +91,9 @@ ARL_DEVINL RowInfo conv_row_info(const ConvGeom& g, int row) {
   int rem = row - b * per;
   int qy = rem / g.Qw;
   int qx = rem - qy * g.Qw;
-  ri.base = (long)b * g.Hs * g.Ws * g.C;
+  long img = b;
+  if (g.idx) img = g.idx[(g.idx_off ? (long)g.idx_off[0] * (g.nrows / per) : 0) + b];
+  ri.base = img * g.Hs * g.Ws * g.C;
   ri.ys = qy * g.sy + g.y0;
   ri.xs = qx * g.sx + g.x0;
   return ri;
@@ -106,76 +125,6 @@ struct ConvLoader {
       if (ri[i].base >= 0 && (unsigned)y < (unsigned)g.Hs && (unsigned)x < (unsigned)g.Ws) {
         const __nv_bfloat16* p = g.src + ri[i].base + ((long)(y * g.Ws + x) * g.C + cc * 8);
         v = __ldg(reinterpret_cast<const uint4*>(p));
-      }
-      st_shared_v4(tile + swz_off<128>(r, j), v);
-    }
-  }
-};
-
-// First conv layer: uint8 CHW observations (the reference's buffer layout), filter width 8,
-// no padding.  K index k' = (c * kh + ky) * 8 + kx; a 16-byte smem chunk = 8 pixels of one
-// (c, ky) patch row, converted u8 -> bf16 (exact) on the way in.  Optional batch gather
-// through idx (shuffled minibatch rows of the rollout buffer).
-struct ConvGeomU8 {
-  const uint8_t* src;   // [n, C, Hs, Ws]
-  const int* idx;       // optional row gather (nullptr = identity): image b reads row idx[off*nb + b]
-  const int* idx_off;   // optional device scalar: minibatch index `off` (graph-replayed training)
-  int Qh, Qw;           // output grid
-  int Hs, Ws, C;
-  int kh;               // filter height (width fixed at 8)
-  int stride;
-  int nrows;            // nb * Qh * Qw
-};
-
-ARL_DEVINL uint4 u8x8_to_bf16x8(uint32_t lo, uint32_t hi) {
-  // byte b -> float(2^23 + b) - 2^23 (exact), then pack pairs to bf16x2 (exact for 0..255)
-  float f[8];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    f[i] = __uint_as_float(__byte_perm(lo, 0x4B000000u, 0x7650 + i) ) - 8388608.0f;
-    f[4 + i] = __uint_as_float(__byte_perm(hi, 0x4B000000u, 0x7650 + i)) - 8388608.0f;
-  }
-  uint4 o;
-  o.x = pack_bf16x2(f[0], f[1]);
-  o.y = pack_bf16x2(f[2], f[3]);
-  o.z = pack_bf16x2(f[4], f[5]);
-  o.w = pack_bf16x2(f[6], f[7]);
-  return o;
-}
-
-template <int R>
-struct ConvLoaderU8 {
-  ConvGeomU8 g;
-  long base[R / 32];  // byte offset of (image, y0, x0) or -1
-  ARL_DEVINL void prepare(int row0, int tid) {
-    int per = g.Qh * g.Qw;
-    const int* ip = g.idx;
-    if (ip && g.idx_off) ip += (long)(*g.idx_off) * (g.nrows / per);
-#pragma unroll
-    for (int i = 0; i < R / 32; ++i) {
-      int row = row0 + (tid >> 3) + 32 * i;
-      if (row >= g.nrows) { base[i] = -1; continue; }
-      int b = row / per;
-      int rem = row - b * per;
-      int qy = rem / g.Qw;
-      int qx = rem - qy * g.Qw;
-      long img = ip ? (long)ip[b] : (long)b;
-      base[i] = img * g.C * g.Hs * g.Ws + (long)(qy * g.stride) * g.Ws + qx * g.stride;
-    }
-  }
-  ARL_DEVINL void fill(uint32_t tile, int kb, int tid) const {
-    int j = tid & 7;
-    int kc = kb * 8 + j;   // (c, ky) patch-row index
-    int c = kc / g.kh;
-    int ky = kc - c * g.kh;
-    long off = ((long)c * g.Hs + ky) * g.Ws;
-#pragma unroll
-    for (int i = 0; i < R / 32; ++i) {
-      int r = (tid >> 3) + 32 * i;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (base[i] >= 0) {
-        const uint32_t* p = reinterpret_cast<const uint32_t*>(g.src + base[i] + off);  // 4-byte aligned (stride%4==0)
-        v = u8x8_to_bf16x8(__ldg(p), __ldg(p + 1));
       }
       st_shared_v4(tile + swz_off<128>(r, j), v);
     }
@@ -315,7 +264,7 @@ ARL_DEVINL void epi_store16(const RowEpi& e, int row, int n0, const uint32_t (&r
 // ---------------------------------------------------------------------------
 template <int BN>
 struct RowGemmCfg {
-  static constexpr int STAGES = (BN <= 64) ? 4 : 3;
+  static constexpr int STAGES = 3;
   static constexpr int A_BYTES = 128 * 128;      // 128 rows x 64 bf16
   static constexpr int B_BYTES = BN * 128;       // BN rows x 64 bf16 (either major)
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -326,12 +275,13 @@ struct RowGemmCfg {
 struct WeightSrc {
   const __nv_bfloat16* w;
   long ldb;
-  int kdim;  // rows available along K (N-major) / unused (K-major)
+  int kdim;      // rows available along K (N-major) / unused (K-major)
+  RowPerm perm;  // permutation of the source rows (tile rows for K-major, k rows for N-major)
 };
 
 template <class ALoad, bool B_NMAJOR, int BN>
-__global__ void __launch_bounds__(kGemmThreads) rowgemm_kernel(ALoad aload, WeightSrc bsrc, RowEpi epi,
-                                                               int num_kb, int kb_per_split) {
+ARL_DEVINL void rowgemm_body(ALoad& aload, const WeightSrc& bsrc, const RowEpi& epi, int num_kb, int kb_per_split,
+                             int m_tile, int n_tile, int split) {
   using Cfg = RowGemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -344,9 +294,8 @@ __global__ void __launch_bounds__(kGemmThreads) rowgemm_kernel(ALoad aload, Weig
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
-  const int m0 = blockIdx.x * 128;
-  const int n0 = blockIdx.y * BN;
-  const int split = blockIdx.z;
+  const int m0 = m_tile * 128;
+  const int n0 = n_tile * BN;
   const int kb0 = split * kb_per_split;
   const int kb1 = min(num_kb, kb0 + kb_per_split);
   const int niter = kb1 - kb0;
@@ -378,11 +327,11 @@ __global__ void __launch_bounds__(kGemmThreads) rowgemm_kernel(ALoad aload, Weig
       const int kb = kb0 + it;
       aload.fill(a_tile, kb, tid);
       if (!B_NMAJOR) {
-        fill_dense<BN, 128>(b_tile, bsrc.w, bsrc.ldb, n0, 1 << 30, kb * kBK, tid);
+        fill_dense<BN, 128>(b_tile, bsrc.w, bsrc.ldb, n0, 1 << 30, kb * kBK, tid, bsrc.perm);
       } else {
 #pragma unroll
         for (int at = 0; at < BN / 64; ++at)
-          fill_dense<64, 128>(b_tile + at * 8192, bsrc.w, bsrc.ldb, kb * kBK, bsrc.kdim, n0 + at * 64, tid);
+          fill_dense<64, 128>(b_tile + at * 8192, bsrc.w, bsrc.ldb, kb * kBK, bsrc.kdim, n0 + at * 64, tid, bsrc.perm);
       }
       fence_proxy_async();
       mbar_arrive(full_bar(s));
@@ -442,6 +391,32 @@ __global__ void __launch_bounds__(kGemmThreads) rowgemm_kernel(ALoad aload, Weig
   }
 }
 
+template <class ALoad, bool B_NMAJOR, int BN>
+__global__ void __launch_bounds__(kGemmThreads) rowgemm_kernel(ALoad aload, WeightSrc bsrc, RowEpi epi,
+                                                               int num_kb, int kb_per_split) {
+  rowgemm_body<ALoad, B_NMAJOR, BN>(aload, bsrc, epi, num_kb, kb_per_split, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+// Several independent GEMMs of the same shape class in ONE launch (blockIdx.y selects the problem):
+// the stride-parity classes of a conv dgrad.
+constexpr int kMaxMulti = 4;
+template <class ALoad>
+struct RowGemmMulti {
+  ALoad a[kMaxMulti];
+  WeightSrc b[kMaxMulti];
+  RowEpi e[kMaxMulti];
+  int mtiles[kMaxMulti];
+  int num_kb[kMaxMulti];
+};
+
+template <class ALoad, int BN>
+__global__ void __launch_bounds__(kGemmThreads) rowgemm_multi_kernel(const __grid_constant__ RowGemmMulti<ALoad> p) {
+  const int cls = blockIdx.y;
+  if ((int)blockIdx.x >= p.mtiles[cls]) return;   // whole CTA exits before any barrier / TMEM use
+  ALoad aload = p.a[cls];
+  rowgemm_body<ALoad, false, BN>(aload, p.b[cls], p.e[cls], p.num_kb[cls], p.num_kb[cls], blockIdx.x, 0, 0);
+}
+
 // ---------------------------------------------------------------------------
 // wgrad: D[K' x BN] = sum over rows of A[row, K']^T * dY[row, BN]
 //   A tiles: [64 rows x 64 k'] atoms filled by the same loaders as the forward pass
@@ -449,7 +424,9 @@ __global__ void __launch_bounds__(kGemmThreads) rowgemm_kernel(ALoad aload, Weig
 //   B tile : [64 rows x BN] from the row-major dY (N-major); BN*2 bytes per row
 //            (32/64/128-byte rows -> SW32/64/128; wider rows split into 64-column atoms)
 // One CTA owns MT consecutive 128-row M-tiles of K' (starting at blockIdx.x*MT), BN columns
-// starting at blockIdx.y*BN, and the row range of split blockIdx.z.
+// starting at blockIdx.y*BN, and the row range of split blockIdx.z.  Sixteen producer warps in
+// two groups fill alternate stages (two stages' gathers in flight per SM); while copying dY the
+// producers also accumulate its column sums = the layer's bias gradient (per-split partial).
 // ---------------------------------------------------------------------------
 struct WgradEpi {
   float* out;        // fp32 destination
@@ -458,6 +435,7 @@ struct WgradEpi {
   int Kp;            // padded rows of the partial buffer
   int ldo;           // row pitch (floats)
   int fc_C, fc_HW;   // mode 1 row permutation
+  float* bias_out;   // optional [splits][BN] column sums of dY over this split's rows
 };
 
 template <int MT, int BN>
@@ -472,15 +450,17 @@ struct WgradCfg {
   static constexpr int ACC_COLS = MT * BN;
   static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
   static_assert(ACC_COLS <= 512, "accumulator does not fit TMEM");
+  static_assert(STAGES * STAGE_BYTES >= 512 * 8 * 4, "stage memory is reused as the column-sum scratch");
 };
 
 template <class ALoad64, int MT, int BN>
-__global__ void __launch_bounds__(kGemmThreads) wgrad_kernel(ALoad64 aload, const __nv_bfloat16* __restrict__ dy,
-                                                             int ld_dy, int nrows, int rows_per_split,
-                                                             int k_atoms_total, WgradEpi epi) {
+__global__ void __launch_bounds__(kWgradThreads) wgrad_kernel(ALoad64 aload, const __nv_bfloat16* __restrict__ dy,
+                                                              int ld_dy, int nrows, int rows_per_split,
+                                                              int k_atoms_total, WgradEpi epi) {
   using Cfg = WgradCfg<MT, BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
@@ -489,13 +469,16 @@ __global__ void __launch_bounds__(kGemmThreads) wgrad_kernel(ALoad64 aload, cons
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
+  const int group = warp >> 3;                    // producer group 0/1 (warp 16 = MMA warp)
+  const int gtid = tid & 255;                     // thread index inside the producer group
   const int atom0 = blockIdx.x * MT * 2;          // first k' atom (64 wide) of this CTA
   const int n0 = blockIdx.y * BN;
   const int split = blockIdx.z;
   const int r_begin = split * rows_per_split;
   const int r_end = min(nrows, r_begin + rows_per_split);
   const int niter = (r_end > r_begin) ? (r_end - r_begin + 63) / 64 : 0;
-  const int natoms = min(MT * 2, k_atoms_total - atom0);  // atoms that exist (the rest alias atom 0)
+  const int natoms = min(MT * 2, k_atoms_total - atom0);  // atoms that exist (the rest are never stored)
+  const bool want_bias = (epi.bias_out != nullptr) && (blockIdx.x == 0) && (Cfg::B_ATOMS == 1);
 
   if (tid == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
@@ -505,15 +488,16 @@ __global__ void __launch_bounds__(kGemmThreads) wgrad_kernel(ALoad64 aload, cons
     mbar_init(tmem_full_bar, 1);
     fence_mbar_init();
   }
-  if (warp == kProducerWarps) tmem_alloc(tmem_ptr_addr, Cfg::TMEM_COLS);
+  if (warp == kWgradProducerWarps) tmem_alloc(tmem_ptr_addr, Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
 
-  if (warp < kProducerWarps) {
-    for (int it = 0; it < niter; ++it) {
+  float csum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (warp < kWgradProducerWarps) {
+    for (int it = group; it < niter; it += 2) {
       const int s = it % Cfg::STAGES;
       const uint32_t ph = (it / Cfg::STAGES) & 1;
       mbar_wait(empty_bar(s), ph ^ 1, 4);
@@ -522,18 +506,32 @@ __global__ void __launch_bounds__(kGemmThreads) wgrad_kernel(ALoad64 aload, cons
       const int row0 = r_begin + it * 64;
       // rows beyond r_end must contribute zero: the loaders zero rows >= their nrows, and the
       // split boundary is enforced on the dY side (zero rows => zero products).
-      aload.prepare(row0, tid);
-      for (int at = 0; at < natoms; ++at) aload.fill(a_tile + at * 8192, atom0 + at, tid);
+      aload.prepare(row0, gtid);
+      for (int at = 0; at < natoms; ++at) aload.fill(a_tile + at * 8192, atom0 + at, gtid);
       if constexpr (Cfg::B_ATOMS == 1) {
-        fill_dense<64, Cfg::ROWB>(b_tile, dy, ld_dy, row0, r_end, n0, tid);
+        constexpr int CH = Cfg::ROWB / 16;
+#pragma unroll
+        for (int i = gtid; i < 64 * CH; i += 256) {
+          int r = i / CH, c = i % CH;
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (row0 + r < r_end) v = __ldg(reinterpret_cast<const uint4*>(dy + (long)(row0 + r) * ld_dy + n0 + c * 8));
+          st_shared_v4(b_tile + swz_off<Cfg::ROWB>(r, c), v);
+          if (want_bias) {
+            csum[0] += bf16_lo(v.x); csum[1] += bf16_hi(v.x); csum[2] += bf16_lo(v.y); csum[3] += bf16_hi(v.y);
+            csum[4] += bf16_lo(v.z); csum[5] += bf16_hi(v.z); csum[6] += bf16_lo(v.w); csum[7] += bf16_hi(v.w);
+          }
+        }
       } else {
 #pragma unroll
         for (int at = 0; at < Cfg::B_ATOMS; ++at)
-          fill_dense<64, 128>(b_tile + at * 8192, dy, ld_dy, row0, r_end, n0 + at * 64, tid);
+          fill_dense<64, 128>(b_tile + at * 8192, dy, ld_dy, row0, r_end, n0 + at * 64, gtid);
       }
       fence_proxy_async();
       mbar_arrive(full_bar(s));
     }
+  }
+  if (warp < kProducerWarps) {
+    // ===================== epilogue (group 0) =====================
     if (niter > 0) {
       mbar_wait(tmem_full_bar, 0, 5);
       tc_fence_after();
@@ -594,7 +592,7 @@ __global__ void __launch_bounds__(kGemmThreads) wgrad_kernel(ALoad64 aload, cons
       }
     }
     tc_fence_before();
-  } else if (tid == kProducerThreads) {
+  } else if (tid == kWgradProducerWarps * 32) {
     constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
     constexpr uint32_t b_layout = swz_layout_type(Cfg::ROWB);
     constexpr uint32_t b_sbo = 8 * Cfg::ROWB;
@@ -611,10 +609,9 @@ __global__ void __launch_bounds__(kGemmThreads) wgrad_kernel(ALoad64 aload, cons
         // a missing second atom (odd atom count) is left unfilled: its D rows are never stored
         if (mt * 2 >= natoms) break;
         const uint32_t a0 = a_tile + (mt * 2) * 8192;
-        const uint32_t lbo = 8192u;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          uint64_t adesc = make_smem_desc(a0 + k * 2048, lbo, 1024, 2);
+          uint64_t adesc = make_smem_desc(a0 + k * 2048, 8192, 1024, 2);
           uint64_t bdesc = make_smem_desc(b_tile + k * b_kstep, 8192, b_sbo, b_layout);
           umma_bf16(tmem_base + mt * BN, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
         }
@@ -623,10 +620,26 @@ __global__ void __launch_bounds__(kGemmThreads) wgrad_kernel(ALoad64 aload, cons
     }
     if (niter > 0) umma_commit(tmem_full_bar);
   }
-  __syncthreads();
-  if (warp == kProducerWarps) {
+  __syncthreads();   // every MMA has completed (group 0 waited on tmem_full): stage memory is free
+  if (warp == kWgradProducerWarps) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+  if (want_bias) {
+    // bias gradient partial: column sums over this split's rows (deterministic order)
+    float* scratch = reinterpret_cast<float*>(smem_gen);     // [512][8]
+    if (warp < kWgradProducerWarps) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) scratch[tid * 8 + e] = csum[e];
+    }
+    __syncthreads();
+    if (tid < BN) {
+      constexpr int CH = Cfg::ROWB / 16;
+      const int chunk = tid >> 3, e = tid & 7;
+      float t = 0.f;
+      for (int th = chunk; th < kWgradProducerWarps * 32; th += CH) t += scratch[th * 8 + e];
+      epi.bias_out[(long)split * BN + tid] = t;
+    }
   }
 }
 

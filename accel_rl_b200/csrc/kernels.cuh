@@ -207,6 +207,35 @@ ARL_DEVINL uint32_t vmax4(uint32_t a, uint32_t b) { return __vmaxu4(a, b); }
 // horizontal pair sums of 4 bytes -> two 16-bit lanes: (b0+b1) | (b2+b3)<<16
 ARL_DEVINL uint32_t pair_sum(uint32_t v) { return (v & 0x00ff00ffu) + ((v >> 8) & 0x00ff00ffu); }
 
+// 4 packed u8 -> 4 bf16 (exact): byte b -> float(2^23 + b) - 2^23, packed pairwise
+ARL_DEVINL uint2 u8x4_to_bf16x4(uint32_t w) {
+  float f0 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650)) - 8388608.0f;
+  float f1 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7651)) - 8388608.0f;
+  float f2 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7652)) - 8388608.0f;
+  float f3 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7653)) - 8388608.0f;
+  return make_uint2(pack_bf16x2(f0, f1), pack_bf16x2(f2, f3));
+}
+
+// uint8 CHW observations (the reference's buffer layout) -> bf16 space-to-depth(s) NHWC:
+//   dst[i][y/s][x/s][c*s*s + (y%s)*s + (x%s)] = src[idx ? idx[i] : i][c][y][x]       (s == 4)
+// One thread converts 4 horizontally adjacent pixels (one aligned 32-bit load, one 8-byte store).
+__global__ void __launch_bounds__(256) obs_to_s2d_kernel(const uint8_t* __restrict__ src, const int* __restrict__ idx,
+                                                         __nv_bfloat16* __restrict__ dst, int n, int C, int H, int W) {
+  const int Wb = W >> 2, Hb = H >> 2;
+  const long total = (long)n * C * H * Wb;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    int bx = (int)(t % Wb);
+    long r = t / Wb;
+    int y = (int)(r % H); r /= H;
+    int c = (int)(r % C);
+    long i = r / C;
+    long img = idx ? idx[i] : i;
+    uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(src + ((img * C + c) * H + y) * (long)W) + bx);
+    long off = ((i * Hb + (y >> 2)) * Wb + bx) * (long)(C * 16) + c * 16 + (y & 3) * 4;
+    *reinterpret_cast<uint2*>(dst + off) = u8x4_to_bf16x4(w);
+  }
+}
+
 // 16 output pixels (row oy, 16-pixel column group xc) of max(fa, fb) box-downsampled; null frame = zeros
 ARL_DEVINL uint4 frame_box16(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, int oy, int xc) {
   const int roff = (2 * oy) * kRawW + xc * 32;
@@ -241,8 +270,12 @@ ARL_DEVINL uint4 frame_box16(const uint8_t* __restrict__ fa, const uint8_t* __re
 
 __global__ void __launch_bounds__(256) frame_kernel(const uint8_t* __restrict__ pool, const uint8_t* __restrict__ staging,
                                                     const FrameCmd* __restrict__ cmd, uint8_t* __restrict__ step_obs,
-                                                    uint8_t* __restrict__ roll_obs, int T, int s_next, int n_envs,
+                                                    uint8_t* __restrict__ roll_obs, __nv_bfloat16* __restrict__ step_obs16,
+                                                    __nv_bfloat16* __restrict__ roll_obs16, int T, int s_next, int n_envs,
                                                     int planes) {
+  // step_obs16 / roll_obs16: bf16 space-to-depth(4) mirrors of the same stacks, [26][20][planes*16] per
+  // observation, channel = plane*16 + (y%4)*4 + (x%4) — the layout the first conv layer's tcgen05 tiles read
+  // (u8 -> bf16 is exact).  They are written from the registers that already hold the u8 stack.
   // step_obs [n_envs][planes][104][80] is the sampler's step buffer (updated in place: each thread
   // shifts its own 16 pixels of every plane); roll_obs row e*T + s_next receives a copy of the new
   // stack (skipped when roll_obs == nullptr, i.e. after the last step of the batch).
@@ -286,6 +319,24 @@ __global__ void __launch_bounds__(256) frame_kernel(const uint8_t* __restrict__ 
   }
   *reinterpret_cast<uint4*>(cur + (planes - 1) * plane_bytes + pix) = newest;
   if (dst) *reinterpret_cast<uint4*>(dst + (planes - 1) * plane_bytes + pix) = newest;
+  if (step_obs16) {
+    const int Cs = planes * 16;
+    const long obs16_elems = (long)(kObsH / 4) * (kObsW / 4) * Cs;
+    __nv_bfloat16* c16 = step_obs16 + (long)e * obs16_elems;
+    __nv_bfloat16* d16 = roll_obs16 ? roll_obs16 + ((long)e * T + s_next) * obs16_elems : nullptr;
+    const int by = oy >> 2, dy = oy & 3;
+    for (int p = 0; p < planes; ++p) {
+      const uint4 v = (p == planes - 1) ? newest : keep[p < 3 ? p : 2];
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const long off = ((long)(by * (kObsW / 4) + xc * 4 + b)) * Cs + p * 16 + dy * 4;
+        const uint2 o = u8x4_to_bf16x4(w[b]);
+        *reinterpret_cast<uint2*>(c16 + off) = o;
+        if (d16) *reinterpret_cast<uint2*>(d16 + off) = o;
+      }
+    }
+  }
 }
 
 // standalone frame update (arl_frame_update): item i's raw frames are raw_a[i], raw_b[i]
@@ -416,11 +467,20 @@ __global__ void __launch_bounds__(256) head_kernel(HeadParams p) {
     float v = 0.f;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      h[i] = 0.f;
+      int j = lane + 32 * i;
+      h[i] = (i < JP && j < p.H) ? s_fcb[j] : 0.f;
+    }
+    for (int s = 0; s < p.splits; ++s) {     // 16 independent loads per split: the sum is latency-bound otherwise
+      const float* ps = p.partial + ((long)s * p.M + row) * p.H + lane;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i < JP && lane + 32 * i < p.H) h[i] += ps[32 * i];
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
       int j = lane + 32 * i;
       if (i < JP && j < p.H) {
-        float acc = s_fcb[j];
-        for (int s = 0; s < p.splits; ++s) acc += p.partial[((long)s * p.M + row) * p.H + j];
+        float acc = h[i];
         acc = fmaxf(acc, 0.f);
         acc = __bfloat162float(__float2bfloat16_rn(acc));
         h[i] = acc;
@@ -594,42 +654,12 @@ __global__ void __launch_bounds__(128) head_wgrad_kernel(const __nv_bfloat16* __
   }
 }
 
-// column sums of a bf16 [rows][C] matrix over row groups: out[g][c]
-__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, int rows, int C,
-                                                      int rows_per_group, float* __restrict__ out) {
-  // block = (C/2 column pairs) x (256 / (C/2)) row lanes
-  const int cp = C >> 1;
-  const int lanes = blockDim.x / cp;
-  const int c2 = threadIdx.x % cp;
-  const int rl = threadIdx.x / cp;
-  const int g = blockIdx.x;
-  const int r0 = g * rows_per_group;
-  const int r1 = min(rows, r0 + rows_per_group);
-  float a0 = 0.f, a1 = 0.f;
-  if (rl < lanes) {
-    for (int r = r0 + rl; r < r1; r += lanes) {
-      uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(x + (long)r * C) + c2);
-      a0 += bf16_lo(v);
-      a1 += bf16_hi(v);
-    }
-  }
-  __shared__ float s[256][2];
-  s[threadIdx.x][0] = a0; s[threadIdx.x][1] = a1;
-  __syncthreads();
-  if (threadIdx.x < cp) {
-    float t0 = 0.f, t1 = 0.f;
-    for (int l = 0; l < lanes; ++l) { t0 += s[l * cp + threadIdx.x][0]; t1 += s[l * cp + threadIdx.x][1]; }
-    out[(long)g * C + 2 * threadIdx.x] = t0;
-    out[(long)g * C + 2 * threadIdx.x + 1] = t1;
-  }
-}
-
 // ===========================================================================
 // Gradient finalisation: sum split partials and scatter into the flat fp32 gradient in the
 // reference's parameter order (rllab/core/parameterized.py:74-88; Lasagne W (out,in,kh,kw),
 // flip_filters=True so correlation tap (ky,kx) is W[..., kh-1-ky, kw-1-kx]).
 // ===========================================================================
-enum GradMap { GM_LINEAR = 0, GM_CONV_NHWC = 1, GM_CONV_CHW = 2, GM_HEAD = 3 };
+enum GradMap { GM_LINEAR = 0, GM_CONV_NHWC = 1, GM_CONV_S2D = 2, GM_HEAD = 3 };
 
 struct GradJob {
   const float* src;   // [S][rows_pad][ld]
@@ -641,6 +671,7 @@ struct GradJob {
   long dst_off;       // offset into flat grad
   // conv maps: k' -> (c, ky, kx)
   int C, kh, kw;
+  int s2d;            // GM_CONV_S2D: space-to-depth factor (= stride of the first conv)
   // GM_HEAD: src [S][H][A+2]; writes w_pi (H,A) at dst_off, w_v (H) at dst_off2, fc bias (H) at dst_off3
   long dst_off2, dst_off3;
   int A;
@@ -652,10 +683,18 @@ __global__ void __launch_bounds__(256) finalize_grads_kernel(const GradJob* __re
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     int r = (int)(i / jb.cols);
     int c = (int)(i - (long)r * jb.cols);
-    float acc = 0.f;
     const float* s = jb.src + (long)r * jb.ld + c;
-    for (int k = 0; k < jb.S; ++k) acc += s[k * jb.sstride];
-    acc *= jb.scale;
+    // fixed summation order (4 interleaved chains), independent loads in flight
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int k = 0;
+    for (; k + 4 <= jb.S; k += 4) {
+      a0 += s[(long)k * jb.sstride];
+      a1 += s[(long)(k + 1) * jb.sstride];
+      a2 += s[(long)(k + 2) * jb.sstride];
+      a3 += s[(long)(k + 3) * jb.sstride];
+    }
+    for (; k < jb.S; ++k) a0 += s[(long)k * jb.sstride];
+    float acc = ((a0 + a1) + (a2 + a3)) * jb.scale;
     if (jb.map == GM_LINEAR) {
       grad[jb.dst_off + i] = acc;
     } else if (jb.map == GM_CONV_NHWC) {
@@ -664,11 +703,14 @@ __global__ void __launch_bounds__(256) finalize_grads_kernel(const GradJob* __re
       int t = r / jb.C;
       int kx = t % jb.kw, ky = t / jb.kw;
       grad[jb.dst_off + (((long)c * jb.C + ci) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx)] = acc;
-    } else if (jb.map == GM_CONV_CHW) {
-      // r = k' = (ci*kh + ky)*kw + kx
-      int kx = r % jb.kw;
-      int t = r / jb.kw;
-      int ky = t % jb.kh, ci = t / jb.kh;
+    } else if (jb.map == GM_CONV_S2D) {
+      // first layer over the space-to-depth input: r = k' = (ty*2 + tx)*(C*s*s) + ci*s*s + dy*s + dx
+      const int s2 = jb.s2d * jb.s2d, cs = jb.C * s2;
+      int ch = r % cs;
+      int t = r / cs;
+      int tx = t % 2, ty = t / 2;
+      int ci = ch / s2, dy = (ch % s2) / jb.s2d, dx = ch % jb.s2d;
+      int ky = ty * jb.s2d + dy, kx = tx * jb.s2d + dx;
       grad[jb.dst_off + (((long)c * jb.C + ci) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx)] = acc;
     } else {  // GM_HEAD: r = j, c in [0, A+2)
       if (c < jb.A) grad[jb.dst_off + (long)r * jb.A + c] = acc;
@@ -761,7 +803,36 @@ __global__ void __launch_bounds__(256) update_kernel(UpdateParams p) {
   }
   __syncthreads();
   const float scale = s_scale, alpha = s_alpha;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long)gridDim.x * blockDim.x) {
+  const long n4 = p.n >> 2;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    float4 g4 = reinterpret_cast<const float4*>(p.grad)[i];
+    float4 p4 = reinterpret_cast<float4*>(p.param)[i];
+    float4 v4 = reinterpret_cast<float4*>(p.v)[i];
+    float g[4] = {g4.x * scale, g4.y * scale, g4.z * scale, g4.w * scale};
+    float pp[4] = {p4.x, p4.y, p4.z, p4.w};
+    float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+    if (p.kind == 0) {
+      float4 m4 = reinterpret_cast<float4*>(p.m)[i];
+      float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        mm[k] = p.beta1 * mm[k] + (1.f - p.beta1) * g[k];
+        vv[k] = p.beta2 * vv[k] + (1.f - p.beta2) * g[k] * g[k];
+        pp[k] -= alpha * mm[k] / (sqrtf(vv[k]) + p.eps);
+      }
+      reinterpret_cast<float4*>(p.m)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        vv[k] = p.rho * vv[k] + (1.f - p.rho) * g[k] * g[k];
+        pp[k] -= alpha * g[k] / sqrtf(vv[k] + p.eps);
+      }
+    }
+    reinterpret_cast<float4*>(p.v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    reinterpret_cast<float4*>(p.param)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (p.n & 3)) {
+    long i = (n4 << 2) + threadIdx.x;
     float g = p.grad[i] * scale;
     if (p.kind == 0) {
       float m = p.beta1 * p.m[i] + (1.f - p.beta1) * g;
@@ -786,7 +857,7 @@ __global__ void advance_counters_kernel(int* step, int* log_slot, int* mb_counte
 // ===========================================================================
 // Weight packing: fp32 master (reference layout) -> bf16 operand matrices for the GEMM tiles
 // ===========================================================================
-enum PackKind { PK_CONV_NHWC = 0, PK_CONV_CHW = 1, PK_CONV_DGRAD = 2, PK_FC = 3 };
+enum PackKind { PK_CONV_NHWC = 0, PK_CONV_S2D = 1, PK_CONV_DGRAD = 2, PK_CAST = 3 };
 
 struct PackJob {
   __nv_bfloat16* dst;
@@ -811,17 +882,19 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const PackJob* __rest
     if (jb.kind == PK_CONV_NHWC) {          // r = cout, k = (ky*kw+kx)*C + c
       int c = k % jb.C; int t = k / jb.C; int kx = t % jb.kw, ky = t / jb.kw;
       v = W[(((long)r * jb.C + c) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx)];
-    } else if (jb.kind == PK_CONV_CHW) {    // r = cout, k = (c*kh+ky)*kw + kx
-      int kx = k % jb.kw; int t = k / jb.kw; int ky = t % jb.kh, c = t / jb.kh;
+    } else if (jb.kind == PK_CONV_S2D) {    // r = cout, k = (ty*2+tx)*(C*s*s) + c*s*s + dy*s + dx
+      const int s2 = jb.s * jb.s, cs = jb.C * s2;
+      int ch = k % cs; int t = k / cs; int tx = t % 2, ty = t / 2;
+      int c = ch / s2, dy = (ch % s2) / jb.s, dx = ch % jb.s;
+      int ky = ty * jb.s + dy, kx = tx * jb.s + dx;
       v = W[(((long)r * jb.C + c) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx)];
     } else if (jb.kind == PK_CONV_DGRAD) {  // r = cin, k = (ty*Tx+tx)*Cout + o
       int o = k % jb.Cout; int t = k / jb.Cout; int tx = t % jb.Tx, ty = t / jb.Tx;
       int ky = jb.ry + jb.s * ty, kx = jb.rx + jb.s * tx;
       if (ky < jb.kh && kx < jb.kw)
         v = W[(((long)o * jb.C + r) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx)];
-    } else {                                 // PK_FC: r = j (hidden unit), k = hw*C + c
-      int c = k % jb.C; int hw = k / jb.C;
-      v = W[((long)c * jb.HW + hw) * jb.ldsrc + r];
+    } else {                                 // PK_CAST: same layout, fp32 -> bf16 (FC weights, reference order)
+      v = W[i];
     }
     jb.dst[i] = __float2bfloat16_rn(v);
   }
