@@ -77,6 +77,16 @@ ARL_DEVINL void mbar_wait(uint32_t bar, uint32_t parity, int where) {
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma reads)
 ARL_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS); src_bytes == 0 writes 16 zero bytes (padding rows)
+ARL_DEVINL void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+// the mbarrier phase cannot complete before this thread's prior cp.async copies have landed
+// (pending count +1 now, -1 when the copies complete: pair it with a regular arrive)
+ARL_DEVINL void cp_async_mbar_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
 // 1-D bulk copy global -> shared (TMA engine, SASS UBLKCP), completion on mbarrier
 ARL_DEVINL void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile(

@@ -60,6 +60,23 @@ ARL_DEVINL void fill_dense(uint32_t tile, const __nv_bfloat16* __restrict__ src,
   }
 }
 
+// Asynchronous variant: cp.async (LDGSTS) straight into the swizzled tile, no register staging; rows past
+// nrows are zero-filled (src-size 0).  Completion is tracked by cp_async_mbar_arrive on the stage barrier.
+template <int R, int ROWB, int NT = 256>
+ARL_DEVINL void fill_dense_async(uint32_t tile, const __nv_bfloat16* __restrict__ src, long ld, int row0, int nrows,
+                                 int col0, int tid, RowPerm perm = RowPerm{0, 0}) {
+  constexpr int CH = ROWB / 16;
+  constexpr int TOTAL = R * CH;
+#pragma unroll
+  for (int i = tid; i < TOTAL; i += NT) {
+    int r = i / CH, c = i % CH;
+    int row = row0 + r;
+    bool ok = row < nrows;
+    const __nv_bfloat16* p = ok ? src + (long)perm_row(perm, row) * ld + col0 + c * 8 : src;
+    cp_async16(tile + swz_off<ROWB>(r, c), p, ok ? 16u : 0u);
+  }
+}
+
 // Gather geometry for implicit-GEMM tiles whose rows are spatial positions.
 // Rows enumerate (b, qy, qx); K index k' = (ty * Tx + tx) * C + c over an NHWC bf16 source.
 //   src_y = qy * sy + y0 + ty * dty,  src_x = qx * sx + x0 + tx * dtx   (out of range -> 0)
@@ -129,6 +146,25 @@ struct ConvLoader {
       st_shared_v4(tile + swz_off<128>(r, j), v);
     }
   }
+  // same gather with cp.async (zero-fill for padding / out-of-range rows)
+  ARL_DEVINL void fill_async(uint32_t tile, int kb, int tid) const {
+    int j = tid & 7;
+    int kc = kb * 8 + j;
+    int cpt = g.C >> 3;
+    int tap = kc / cpt;
+    int cc = kc - tap * cpt;
+    int ty = tap / g.Tx;
+    int tx = tap - ty * g.Tx;
+    int dy = ty * g.dty, dx = tx * g.dtx;
+#pragma unroll
+    for (int i = 0; i < R / 32; ++i) {
+      int r = (tid >> 3) + 32 * i;
+      int y = ri[i].ys + dy, x = ri[i].xs + dx;
+      bool ok = ri[i].base >= 0 && (unsigned)y < (unsigned)g.Hs && (unsigned)x < (unsigned)g.Ws;
+      const __nv_bfloat16* p = ok ? g.src + ri[i].base + ((long)(y * g.Ws + x) * g.C + cc * 8) : g.src;
+      cp_async16(tile + swz_off<128>(r, j), p, ok ? 16u : 0u);
+    }
+  }
 };
 
 // Dense K-major A operand (FC forward / FC dgrad: rows = batch rows of a row-major matrix)
@@ -140,6 +176,9 @@ struct DenseLoader {
   int row0;
   ARL_DEVINL void prepare(int r0, int) { row0 = r0; }
   ARL_DEVINL void fill(uint32_t tile, int kb, int tid) const { fill_dense<R, 128>(tile, src, ld, row0, nrows, kb * kBK, tid); }
+  ARL_DEVINL void fill_async(uint32_t tile, int kb, int tid) const {
+    fill_dense_async<R, 128>(tile, src, ld, row0, nrows, kb * kBK, tid);
+  }
 };
 
 // ---------------------------------------------------------------------------
@@ -325,16 +364,17 @@ ARL_DEVINL void rowgemm_body(ALoad& aload, const WeightSrc& bsrc, const RowEpi& 
       const uint32_t a_tile = smem_base + s * Cfg::STAGE_BYTES;
       const uint32_t b_tile = a_tile + Cfg::A_BYTES;
       const int kb = kb0 + it;
-      aload.fill(a_tile, kb, tid);
+      aload.fill_async(a_tile, kb, tid);
       if (!B_NMAJOR) {
-        fill_dense<BN, 128>(b_tile, bsrc.w, bsrc.ldb, n0, 1 << 30, kb * kBK, tid, bsrc.perm);
+        fill_dense_async<BN, 128>(b_tile, bsrc.w, bsrc.ldb, n0, 1 << 30, kb * kBK, tid, bsrc.perm);
       } else {
 #pragma unroll
         for (int at = 0; at < BN / 64; ++at)
-          fill_dense<64, 128>(b_tile + at * 8192, bsrc.w, bsrc.ldb, kb * kBK, bsrc.kdim, n0 + at * 64, tid, bsrc.perm);
+          fill_dense_async<64, 128>(b_tile + at * 8192, bsrc.w, bsrc.ldb, kb * kBK, bsrc.kdim, n0 + at * 64, tid,
+                                    bsrc.perm);
       }
-      fence_proxy_async();
-      mbar_arrive(full_bar(s));
+      cp_async_mbar_arrive(full_bar(s));   // phase completes only once this thread's copies have landed
+      mbar_arrive(full_bar(s));            // ... and every producer thread has issued its share
     }
     // ===================== epilogue =====================
     if (niter > 0) {
@@ -370,6 +410,7 @@ ARL_DEVINL void rowgemm_body(ALoad& aload, const WeightSrc& bsrc, const RowEpi& 
       const int s = it % Cfg::STAGES;
       const uint32_t ph = (it / Cfg::STAGES) & 1;
       mbar_wait(full_bar(s), ph, 3);
+      fence_proxy_async();                 // cp.async (generic-proxy) writes -> tcgen05 (async-proxy) reads
       tc_fence_after();
       const uint32_t a_tile = smem_base + s * Cfg::STAGE_BYTES;
       const uint32_t b_tile = a_tile + Cfg::A_BYTES;
@@ -507,26 +548,42 @@ __global__ void __launch_bounds__(kWgradThreads) wgrad_kernel(ALoad64 aload, con
       // rows beyond r_end must contribute zero: the loaders zero rows >= their nrows, and the
       // split boundary is enforced on the dY side (zero rows => zero products).
       aload.prepare(row0, gtid);
-      for (int at = 0; at < natoms; ++at) aload.fill(a_tile + at * 8192, atom0 + at, gtid);
       if constexpr (Cfg::B_ATOMS == 1) {
+        // dY goes through registers (its column sums are the bias gradient); its loads are issued first so
+        // their latency overlaps the issue of the A-operand cp.async gathers
         constexpr int CH = Cfg::ROWB / 16;
+        constexpr int NB = (64 * CH + 255) / 256;
+        uint4 bv[NB];
 #pragma unroll
-        for (int i = gtid; i < 64 * CH; i += 256) {
+        for (int q = 0; q < NB; ++q) {
+          int i = gtid + q * 256;
           int r = i / CH, c = i % CH;
-          uint4 v = make_uint4(0, 0, 0, 0);
-          if (row0 + r < r_end) v = __ldg(reinterpret_cast<const uint4*>(dy + (long)(row0 + r) * ld_dy + n0 + c * 8));
-          st_shared_v4(b_tile + swz_off<Cfg::ROWB>(r, c), v);
-          if (want_bias) {
-            csum[0] += bf16_lo(v.x); csum[1] += bf16_hi(v.x); csum[2] += bf16_lo(v.y); csum[3] += bf16_hi(v.y);
-            csum[4] += bf16_lo(v.z); csum[5] += bf16_hi(v.z); csum[6] += bf16_lo(v.w); csum[7] += bf16_hi(v.w);
+          bv[q] = make_uint4(0, 0, 0, 0);
+          if (i < 64 * CH && row0 + r < r_end)
+            bv[q] = __ldg(reinterpret_cast<const uint4*>(dy + (long)(row0 + r) * ld_dy + n0 + c * 8));
+        }
+        for (int at = 0; at < natoms; ++at) aload.fill_async(a_tile + at * 8192, atom0 + at, gtid);
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+          int i = gtid + q * 256;
+          if (i < 64 * CH) {
+            int r = i / CH, c = i % CH;
+            uint4 v = bv[q];
+            st_shared_v4(b_tile + swz_off<Cfg::ROWB>(r, c), v);
+            if (want_bias) {
+              csum[0] += bf16_lo(v.x); csum[1] += bf16_hi(v.x); csum[2] += bf16_lo(v.y); csum[3] += bf16_hi(v.y);
+              csum[4] += bf16_lo(v.z); csum[5] += bf16_hi(v.z); csum[6] += bf16_lo(v.w); csum[7] += bf16_hi(v.w);
+            }
           }
         }
+        fence_proxy_async();
       } else {
+        for (int at = 0; at < natoms; ++at) aload.fill_async(a_tile + at * 8192, atom0 + at, gtid);
 #pragma unroll
         for (int at = 0; at < Cfg::B_ATOMS; ++at)
-          fill_dense<64, 128>(b_tile + at * 8192, dy, ld_dy, row0, r_end, n0 + at * 64, gtid);
+          fill_dense_async<64, 128>(b_tile + at * 8192, dy, ld_dy, row0, r_end, n0 + at * 64, gtid);
       }
-      fence_proxy_async();
+      cp_async_mbar_arrive(full_bar(s));
       mbar_arrive(full_bar(s));
     }
   }
@@ -601,6 +658,7 @@ __global__ void __launch_bounds__(kWgradThreads) wgrad_kernel(ALoad64 aload, con
       const int s = it % Cfg::STAGES;
       const uint32_t ph = (it / Cfg::STAGES) & 1;
       mbar_wait(full_bar(s), ph, 6);
+      fence_proxy_async();
       tc_fence_after();
       const uint32_t a_tile = smem_base + s * Cfg::STAGE_BYTES;
       const uint32_t b_tile = a_tile + Cfg::A_BYTES;
