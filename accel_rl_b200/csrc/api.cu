@@ -128,13 +128,13 @@ struct arl_ctx {
   std::vector<std::string> prof_names;
   int prof_n = 0;
   long graph_rollout_nodes = 0, graph_train_nodes = 0;
+  int n_loss_rows = 0;                 // rows of the last head_kernel<1> launch (loss partial count)
   float lr_mult_host = 1.f;
   CommState comm;
 };
 
 namespace {
 
-constexpr int kLossBlocks = 64;
 constexpr int kMaxSplits = 160;
 
 template <class T>
@@ -192,20 +192,35 @@ int launch_rowgemm_bn(arl_ctx* c, int BN, ALoad a, WeightSrc b, RowEpi e, int M,
   ARL_FAIL(c, "unsupported tile width BN=" + std::to_string(BN));
 }
 
-template <class ALoad, int BN>
-int launch_rowgemm_multi(arl_ctx* c, const RowGemmMulti<ALoad>& p, int ncls, int max_tiles, cudaStream_t st) {
-  using Cfg = RowGemmCfg<BN>;
-  static bool attr = false;
-  if (!attr) {
-    ARL_CHECK(c, cudaFuncSetAttribute(rowgemm_multi_kernel<ALoad, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      Cfg::SMEM));
-    attr = true;
+template <int BN>
+int launch_conv_persist(arl_ctx* c, const RowGemmMulti<ConvLoader<128>>& p, int ncls, int K, int max_tiles,
+                        cudaStream_t st) {
+  const int smem = conv_persist_smem<BN>(K);
+  static int attr_smem = 0;
+  static int occ = 1;
+  if (smem > attr_smem) {
+    ARL_CHECK(c, cudaFuncSetAttribute(conv_gemm_persist_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
   }
-  dim3 grid(max_tiles, ncls, 1);
-  rowgemm_multi_kernel<ALoad, BN><<<grid, kGemmThreads, Cfg::SMEM, st>>>(p);
+  // two CTAs per SM when shared memory allows (registers are capped for 2 by __launch_bounds__); the tile loop is
+  // correct for any grid size, so this is only a sizing heuristic
+  occ = (2 * (smem + 1024) <= 227 * 1024) ? 2 : 1;
+  int ctas = std::min(max_tiles, std::max(1, 148 * occ / ncls));
+  dim3 grid(ctas, ncls, 1);
+  conv_gemm_persist_kernel<BN><<<grid, kPersistThreads, smem, st>>>(p);
   c->launches++;
   ARL_CHECK(c, cudaGetLastError());
   return 0;
+}
+
+int launch_conv_persist_bn(arl_ctx* c, int BN, const RowGemmMulti<ConvLoader<128>>& p, int ncls, int K, int max_tiles,
+                           cudaStream_t st) {
+  switch (BN) {
+    case 16: return launch_conv_persist<16>(c, p, ncls, K, max_tiles, st);
+    case 32: return launch_conv_persist<32>(c, p, ncls, K, max_tiles, st);
+    case 64: return launch_conv_persist<64>(c, p, ncls, K, max_tiles, st);
+  }
+  ARL_FAIL(c, "unsupported conv tile width BN=" + std::to_string(BN));
 }
 
 template <class ALoad, int MT, int BN>
@@ -215,11 +230,11 @@ int launch_wgrad(arl_ctx* c, ALoad a, const __nv_bfloat16* dy, int ld_dy, int nr
   static bool attr = false;
   if (!attr) {
     ARL_CHECK(c, cudaFuncSetAttribute(wgrad_kernel<ALoad, MT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      Cfg::SMEM));
+                                      Cfg::SMEM_TOTAL));
     attr = true;
   }
   dim3 grid((atoms + MT * 2 - 1) / (MT * 2), ntiles, splits);
-  wgrad_kernel<ALoad, MT, BN><<<grid, kWgradThreads, Cfg::SMEM, st>>>(a, dy, ld_dy, nrows, rps, atoms, e);
+  wgrad_kernel<ALoad, MT, BN><<<grid, kWgradThreads, Cfg::SMEM_TOTAL, st>>>(a, dy, ld_dy, nrows, rps, atoms, e);
   c->launches++;
   ARL_CHECK(c, cudaGetLastError());
   return 0;
@@ -387,7 +402,7 @@ int alloc_net(arl_ctx* c) {
   if (dev_alloc(c, &c->dlogit, (size_t)R * (c->A + 1))) return 1;
   if (dev_alloc(c, &c->head_partial, (size_t)64 * c->H * (c->A + 2))) return 1;
   if (dev_alloc(c, &c->head_b_partial, (size_t)64 * (c->A + 1))) return 1;
-  if (dev_alloc(c, &c->loss_partial, (size_t)kLossBlocks * 4)) return 1;
+  if (dev_alloc(c, &c->loss_partial, (size_t)R * 4)) return 1;
   if (dev_alloc(c, &c->sumsq_partial, (size_t)kSumsqBlocks)) return 1;
   if (dev_alloc(c, &c->hyper, 8)) return 1;
   float one = 1.f;
@@ -447,11 +462,14 @@ int forward_trunk(arl_ctx* c, const __nv_bfloat16* obs16, const int* idx, const 
     RowEpi e = make_epi(EPI_BIAS_RELU_BF16);
     e.bias = c->params + L.off_b; e.out = L.act; e.ldo = L.Cout; e.M = rows;
     if (l == 0) e.scale = 1.f / c->cfg.pixel_scale;
-    WeightSrc w{L.wpack, (long)L.K, 0, RowPerm{0, 0}};
-    ConvLoader<128> a{};
-    a.g = fwd_geom(L, l == 0 ? obs16 : c->conv[l - 1].act, n);
-    if (l == 0) { a.g.idx = idx; a.g.idx_off = idx_off; }
-    if (launch_rowgemm_bn<ConvLoader<128>, false>(c, L.Cout, a, w, e, rows, L.Cout, L.K / 64, L.K / 64, 1, st)) return 1;
+    RowGemmMulti<ConvLoader<128>> mp{};
+    mp.a[0].g = fwd_geom(L, l == 0 ? obs16 : c->conv[l - 1].act, n);
+    if (l == 0) { mp.a[0].g.idx = idx; mp.a[0].g.idx_off = idx_off; }
+    mp.b[0] = WeightSrc{L.wpack, (long)L.K, 0, RowPerm{0, 0}};
+    mp.e[0] = e;
+    mp.mtiles[0] = (rows + 127) / 128;
+    mp.num_kb[0] = L.K / 64;
+    if (launch_conv_persist_bn(c, L.Cout, mp, 1, L.K, mp.mtiles[0], st)) return 1;
     prof_mark(c, kFwdName[l], st);
   }
   int kbps = 0;
@@ -469,7 +487,6 @@ int forward_trunk(arl_ctx* c, const __nv_bfloat16* obs16, const int* idx, const 
   return 0;
 }
 
-size_t head_smem(arl_ctx* c) { return (size_t)(c->H * c->A + 2 * c->H + kMaxActions + 2) * sizeof(float); }
 
 HeadParams head_base(arl_ctx* c, int n, int S) {
   HeadParams p{};
@@ -486,8 +503,7 @@ int policy_forward16(arl_ctx* c, const __nv_bfloat16* obs16, int n, const int* o
   if (forward_trunk(c, obs16, nullptr, nullptr, n, &S, st)) return 1;
   HeadParams p = head_base(c, n, S);
   p.out_rows = out_rows; p.prob = prob; p.value = value; p.uniforms = uniforms; p.actions = uniforms ? actions : nullptr;
-  int blocks = std::min((n + 7) / 8, 148 * 2);
-  head_kernel<0><<<blocks, 256, head_smem(c), st>>>(p);
+  head_kernel<0><<<n, kHeadThreads, 0, st>>>(p);
   c->launches++;
   prof_mark(c, "head_sample", st);
   ARL_CHECK(c, cudaGetLastError());
@@ -586,7 +602,8 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
   p.algo = c->opt.algo; p.clip_param = c->opt.clip_param; p.v_coeff = c->opt.v_loss_coeff;
   p.ent_coeff = c->opt.ent_loss_coeff; p.inv_count = 1.f / (float)n;
   p.h_out = c->h; p.dh_out = c->dh; p.dlogit_out = c->dlogit; p.loss_partial = c->loss_partial;
-  head_kernel<1><<<kLossBlocks, 256, head_smem(c), st>>>(p);
+  c->n_loss_rows = n;
+  head_kernel<1><<<n, kHeadThreads, 0, st>>>(p);
   c->launches++;
   prof_mark(c, "head_loss", st);
   ARL_CHECK(c, cudaGetLastError());
@@ -660,14 +677,7 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
       max_tiles = std::max(max_tiles, mp.mtiles[ncls]);
       ++ncls;
     }
-    int rc;
-    switch (L.Cin) {
-      case 16: rc = launch_rowgemm_multi<ConvLoader<128>, 16>(c, mp, ncls, max_tiles, st); break;
-      case 32: rc = launch_rowgemm_multi<ConvLoader<128>, 32>(c, mp, ncls, max_tiles, st); break;
-      case 64: rc = launch_rowgemm_multi<ConvLoader<128>, 64>(c, mp, ncls, max_tiles, st); break;
-      default: ARL_FAIL(c, "unsupported dgrad width");
-    }
-    if (rc) return rc;
+    if (launch_conv_persist_bn(c, L.Cin, mp, ncls, L.dclasses[0].K, max_tiles, st)) return 1;
     prof_mark(c, kDgradName[l], st);
   }
   // ---- sum partials, scatter into the flat gradient ----
@@ -681,10 +691,13 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
   return 0;
 }
 
-int pack_weights(arl_ctx* c, cudaStream_t st) {
+// with_fc: also cast the FC weights (explicit set_params / sync path); the single-GPU update kernel refreshes
+// that copy itself.  advance: this call closes an update -> bump the device counters.
+int pack_weights(arl_ctx* c, cudaStream_t st, bool with_fc = true, bool advance = false) {
   if (!c->params) ARL_FAIL(c, "parameters not bound");
-  dim3 grid(148 * 2, c->n_pack_jobs);
-  pack_weights_kernel<<<grid, 256, 0, st>>>(c->pack_jobs_dev, c->params);
+  dim3 grid(with_fc ? 148 * 4 : 32, with_fc ? c->n_pack_jobs : c->n_pack_jobs - 1);
+  pack_weights_kernel<<<grid, 256, 0, st>>>(c->pack_jobs_dev, c->params, advance ? c->step : nullptr, c->log_slot,
+                                            c->mb_counter);
   c->launches++;
   prof_mark(c, "pack_weights", st);
   ARL_CHECK(c, cudaGetLastError());
@@ -700,19 +713,19 @@ int clip_update(arl_ctx* c, float gscale, cudaStream_t st) {
   UpdateParams u{};
   u.param = c->params; u.grad = c->grad; u.m = c->m; u.v = c->v; u.n = c->n_params;
   u.sumsq_partial = c->sumsq_partial; u.n_partial = kSumsqBlocks;
-  u.loss_partial = c->loss_partial; u.n_loss_blocks = kLossBlocks;
+  u.loss_partial = c->loss_partial; u.n_loss_blocks = c->n_loss_rows;
   u.hyper = c->hyper; u.step = c->step; u.kind = c->opt.update;
   u.lr = c->opt.learning_rate; u.beta1 = c->opt.beta1; u.beta2 = c->opt.beta2; u.eps = c->opt.epsilon;
   u.rho = c->opt.rho; u.clip = c->opt.grad_norm_clip; u.gscale = gscale;
   u.out_norm = c->log_norm; u.out_loss = c->log_loss; u.log_slot = c->log_slot; u.log_cap = c->log_cap;
+  u.shadow = c->wfc_bf16; u.shadow_begin = c->off_Wfc; u.shadow_end = c->off_Wfc + (long)c->Kfc * c->H;
+  bool fused_cast = (c->off_Wfc % 4 == 0);
+  if (!fused_cast) u.shadow = nullptr;
   update_kernel<<<148 * 4, 256, 0, st>>>(u);
   c->launches++;
   prof_mark(c, "clip_update", st);
-  advance_counters_kernel<<<1, 1, 0, st>>>(c->step, c->log_slot, c->mb_counter);
-  c->launches++;
-  prof_mark(c, "advance_counters", st);
   ARL_CHECK(c, cudaGetLastError());
-  return pack_weights(c, st);
+  return pack_weights(c, st, !fused_cast, true);
 }
 
 // ---------------------------------------------------------------------------
@@ -1150,17 +1163,15 @@ int arl_sync_allreduce_update(arl_ctx* c, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   SyncUpdateArgs a{};
   a.param = c->params; a.grad = c->grad; a.m = c->m; a.v = c->v; a.n = c->n_params;
-  a.loss_partial = c->loss_partial; a.n_loss_blocks = kLossBlocks; a.hyper = c->hyper; a.step = c->step;
+  a.loss_partial = c->loss_partial; a.n_loss_blocks = c->n_loss_rows; a.hyper = c->hyper; a.step = c->step;
   a.kind = c->opt.update; a.lr = c->opt.learning_rate; a.beta1 = c->opt.beta1; a.beta2 = c->opt.beta2;
   a.eps = c->opt.epsilon; a.rho = c->opt.rho; a.clip = c->opt.grad_norm_clip;
   a.out_norm = c->log_norm; a.out_loss = c->log_loss; a.log_slot = c->log_slot; a.log_cap = c->log_cap;
   std::string err;
   if (comm_sync_update(c->comm, a, st, err)) { c->err = err; return 5; }
-  c->launches += 2;
-  advance_counters_kernel<<<1, 1, 0, st>>>(c->step, c->log_slot, c->mb_counter);
-  c->launches++;
+  c->launches += 1;
   ARL_CHECK(c, cudaGetLastError());
-  return pack_weights(c, st);
+  return pack_weights(c, st, true, true);
 }
 
 // ---- diagnostics --------------------------------------------------------------------------

@@ -92,77 +92,86 @@ struct ConvGeom {
   int nrows;             // nb * Qh * Qw
 };
 
-struct RowInfo {
-  long base;   // element offset of image b in src (or -1 when the row is out of range)
-  int ys, xs;  // qy*sy + y0, qx*sx + x0
+// Decoded position of one GEMM row: source image, and the (y, x) of tap (0,0) in it
+struct RowPos {
+  int img;     // source image index (after the optional gather), -1 when the row is out of range
+  int ysxs;    // (qy*sy + y0) in the low 16 bits, (qx*sx + x0) in the high 16 bits (both signed)
 };
 
-ARL_DEVINL RowInfo conv_row_info(const ConvGeom& g, int row) {
-  RowInfo ri;
+ARL_DEVINL RowPos conv_row_pos(const ConvGeom& g, int row) {
+  RowPos rp;
   if (row >= g.nrows) {
-    ri.base = -1; ri.ys = 0; ri.xs = 0;
-    return ri;
+    rp.img = -1; rp.ysxs = 0;
+    return rp;
   }
   int per = g.Qh * g.Qw;
   int b = row / per;
   int rem = row - b * per;
   int qy = rem / g.Qw;
   int qx = rem - qy * g.Qw;
-  long img = b;
+  int img = b;
   if (g.idx) img = g.idx[(g.idx_off ? (long)g.idx_off[0] * (g.nrows / per) : 0) + b];
-  ri.base = img * g.Hs * g.Ws * g.C;
-  ri.ys = qy * g.sy + g.y0;
-  ri.xs = qx * g.sx + g.x0;
-  return ri;
+  rp.img = img;
+  int ys = qy * g.sy + g.y0, xs = qx * g.sx + g.x0;
+  rp.ysxs = (ys & 0xffff) | (xs << 16);
+  return rp;
 }
 
 // One [R rows x 64 k'] tile (k-block kb).  Thread owns chunk column j = tid & 7 and rows (tid>>3) + 32*i.
+// Everything that does not change from k-block to k-block is hoisted: the swizzled shared-memory offsets,
+// the per-row source pointer / origin, and a per-CTA table (shared memory) that decodes the K chunk index
+// into its tap offset — so the gather costs a handful of integer ops and one cp.async per 16 bytes.
 template <int R>
 struct ConvLoader {
+  static constexpr bool kNeedsTable = true;
   ConvGeom g;
-  RowInfo ri[R / 32];
-  ARL_DEVINL void prepare(int row0, int tid) {
-#pragma unroll
-    for (int i = 0; i < R / 32; ++i) ri[i] = conv_row_info(g, row0 + (tid >> 3) + 32 * i);
-  }
-  ARL_DEVINL void fill(uint32_t tile, int kb, int tid) const {
-    int j = tid & 7;
-    int kc = kb * 8 + j;          // global 16-byte chunk index along K
-    int cpt = g.C >> 3;           // chunks per tap
-    int tap = kc / cpt;
-    int cc = kc - tap * cpt;
-    int ty = tap / g.Tx;
-    int tx = tap - ty * g.Tx;
-    int dy = ty * g.dty, dx = tx * g.dtx;
-#pragma unroll
-    for (int i = 0; i < R / 32; ++i) {
-      int r = (tid >> 3) + 32 * i;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      int y = ri[i].ys + dy, x = ri[i].xs + dx;
-      if (ri[i].base >= 0 && (unsigned)y < (unsigned)g.Hs && (unsigned)x < (unsigned)g.Ws) {
-        const __nv_bfloat16* p = g.src + ri[i].base + ((long)(y * g.Ws + x) * g.C + cc * 8);
-        v = __ldg(reinterpret_cast<const uint4*>(p));
-      }
-      st_shared_v4(tile + swz_off<128>(r, j), v);
+  const int4* ktab;                        // [K/8] {dy, dx, element offset of (dy,dx,c0), 0} (shared memory)
+  const __nv_bfloat16* rptr[R / 32];       // image base pointer of each owned row (nullptr: row out of range)
+  int roff[R / 32];                        // element offset of the row's tap-(0,0) pixel inside its image
+  int ysxs[R / 32];
+  uint32_t soff[R / 32];                   // swizzled byte offset of (row, chunk column) inside a tile
+
+  // called by all threads of the CTA once (followed by a __syncthreads in the kernel)
+  ARL_DEVINL void build_table(int4* tab, int nchunks, int tid, int nthreads, int kc0 = 0) const {
+    const int cpt = g.C >> 3;
+    for (int i = tid; i < nchunks; i += nthreads) {
+      int kc = kc0 + i;                      // global 16-byte chunk index along K; tab is indexed locally
+      int tap = kc / cpt;
+      int cc = kc - tap * cpt;
+      int ty = tap / g.Tx;
+      int tx = tap - ty * g.Tx;
+      int dy = ty * g.dty, dx = tx * g.dtx;
+      tab[i] = make_int4(dy, dx, (dy * g.Ws + dx) * g.C + cc * 8, 0);
     }
   }
-  // same gather with cp.async (zero-fill for padding / out-of-range rows)
+  ARL_DEVINL void init_thread(const int4* tab, int tid) {
+    ktab = tab;
+#pragma unroll
+    for (int i = 0; i < R / 32; ++i) soff[i] = swz_off<128>((tid >> 3) + 32 * i, tid & 7);
+  }
+  ARL_DEVINL void set_row(int i, RowPos rp) {
+    int ys = (int)(short)(rp.ysxs & 0xffff), xs = rp.ysxs >> 16;
+    rptr[i] = rp.img >= 0 ? g.src + (long)rp.img * ((long)g.Hs * g.Ws * g.C) : nullptr;
+    roff[i] = (ys * g.Ws + xs) * g.C;
+    ysxs[i] = rp.ysxs;
+  }
+  ARL_DEVINL void prepare(int row0, int tid) {
+#pragma unroll
+    for (int i = 0; i < R / 32; ++i) set_row(i, conv_row_pos(g, row0 + (tid >> 3) + 32 * i));
+  }
+  // rows decoded earlier into a shared-memory table (wgrad: one decode per row per CTA)
+  ARL_DEVINL void prepare_tab(const RowPos* rowtab, int local_row0, int tid) {
+#pragma unroll
+    for (int i = 0; i < R / 32; ++i) set_row(i, rowtab[local_row0 + (tid >> 3) + 32 * i]);
+  }
   ARL_DEVINL void fill_async(uint32_t tile, int kb, int tid) const {
-    int j = tid & 7;
-    int kc = kb * 8 + j;
-    int cpt = g.C >> 3;
-    int tap = kc / cpt;
-    int cc = kc - tap * cpt;
-    int ty = tap / g.Tx;
-    int tx = tap - ty * g.Tx;
-    int dy = ty * g.dty, dx = tx * g.dtx;
+    const int4 e = ktab[kb * 8 + (tid & 7)];
 #pragma unroll
     for (int i = 0; i < R / 32; ++i) {
-      int r = (tid >> 3) + 32 * i;
-      int y = ri[i].ys + dy, x = ri[i].xs + dx;
-      bool ok = ri[i].base >= 0 && (unsigned)y < (unsigned)g.Hs && (unsigned)x < (unsigned)g.Ws;
-      const __nv_bfloat16* p = ok ? g.src + ri[i].base + ((long)(y * g.Ws + x) * g.C + cc * 8) : g.src;
-      cp_async16(tile + swz_off<128>(r, j), p, ok ? 16u : 0u);
+      int y = (int)(short)(ysxs[i] & 0xffff) + e.x, x = (ysxs[i] >> 16) + e.y;
+      bool ok = rptr[i] != nullptr && (unsigned)y < (unsigned)g.Hs && (unsigned)x < (unsigned)g.Ws;
+      const __nv_bfloat16* p = ok ? rptr[i] + (roff[i] + e.z) : g.src;
+      cp_async16(tile + soff[i], p, ok ? 16u : 0u);
     }
   }
 };
@@ -170,12 +179,15 @@ struct ConvLoader {
 // Dense K-major A operand (FC forward / FC dgrad: rows = batch rows of a row-major matrix)
 template <int R>
 struct DenseLoader {
+  static constexpr bool kNeedsTable = false;
   const __nv_bfloat16* src;
   long ld;
   int nrows;
   int row0;
+  ARL_DEVINL void build_table(int4*, int, int, int, int = 0) const {}
+  ARL_DEVINL void init_thread(const int4*, int) {}
   ARL_DEVINL void prepare(int r0, int) { row0 = r0; }
-  ARL_DEVINL void fill(uint32_t tile, int kb, int tid) const { fill_dense<R, 128>(tile, src, ld, row0, nrows, kb * kBK, tid); }
+  ARL_DEVINL void prepare_tab(const RowPos*, int, int) {}
   ARL_DEVINL void fill_async(uint32_t tile, int kb, int tid) const {
     fill_dense_async<R, 128>(tile, src, ld, row0, nrows, kb * kBK, tid);
   }
@@ -450,12 +462,158 @@ struct RowGemmMulti {
   int num_kb[kMaxMulti];
 };
 
-template <class ALoad, int BN>
-__global__ void __launch_bounds__(kGemmThreads) rowgemm_multi_kernel(const __grid_constant__ RowGemmMulti<ALoad> p) {
+// ---------------------------------------------------------------------------
+// conv_gemm_persist: persistent, warp-specialised implicit-GEMM conv tiles.
+//   D[128 rows x BN] = im2col(A)[128 x K] * W[BN x K]^T  for every 128-row tile of up to kMaxMulti
+//   independent problems ("classes": 1 for a forward conv, the stride-parity classes for a dgrad).
+// grid = (CTAs per class, classes); each CTA loops over the tiles of its class (tile += gridDim.x):
+//   warps 0-7  : producers — cp.async im2col gather of the A tile into a 4-stage ring
+//   warp  8    : one thread issues tcgen05.mma; accumulators ping-pong between two TMEM buffers
+//   warps 9-12 : epilogue — tcgen05.ld of the finished buffer, bias/ReLU/mask, bf16 stores, while the
+//                next tile's MMAs run
+// The whole weight matrix W (BN x K bf16, <= 72 KB) is loaded ONCE per CTA and stays resident in shared
+// memory; barriers/TMEM are set up once per CTA instead of once per tile.
+// ---------------------------------------------------------------------------
+constexpr int kPersistThreads = kProducerThreads + 32 + 128;   // 416
+constexpr int kPersistStages = 4;
+
+template <int BN>
+__host__ __device__ constexpr int conv_persist_smem(int K) {
+  return BN * K * 2 + kPersistStages * 16384 + 1024 + 256 + (K / 8) * 16;   // B, A ring, align, barriers, k-table
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kPersistThreads, 2) conv_gemm_persist_kernel(
+    const __grid_constant__ RowGemmMulti<ConvLoader<128>> p) {
   const int cls = blockIdx.y;
-  if ((int)blockIdx.x >= p.mtiles[cls]) return;   // whole CTA exits before any barrier / TMEM use
-  ALoad aload = p.a[cls];
-  rowgemm_body<ALoad, false, BN>(aload, p.b[cls], p.e[cls], p.num_kb[cls], p.num_kb[cls], blockIdx.x, 0, 0);
+  const int ntiles = p.mtiles[cls];
+  if ((int)blockIdx.x >= ntiles) return;          // whole CTA exits before any barrier / TMEM use
+  const int num_kb = p.num_kb[cls];
+  constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_base = smem_base;                                   // num_kb tiles of [BN x 128 B]
+  const uint32_t a_base = smem_base + num_kb * (BN * 128);             // (BN*128 is a multiple of 1024 for BN >= 8)
+  const uint32_t bar_base = a_base + kPersistStages * 16384;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kPersistStages + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * kPersistStages + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * kPersistStages + 2 + b); };
+  const uint32_t bfull_bar = bar_base + 8u * (2 * kPersistStages + 4);
+  const uint32_t tmem_ptr_addr = bfull_bar + 8u;
+  int4* ktab = reinterpret_cast<int4*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < kPersistStages; ++s) {
+      mbar_init(full_bar(s), kProducerThreads);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 4);
+    }
+    mbar_init(bfull_bar, kProducerThreads);
+    fence_mbar_init();
+  }
+  p.a[cls].build_table(ktab, num_kb * 8, tid, kPersistThreads);
+  if (warp == kProducerWarps) tmem_alloc(tmem_ptr_addr, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+
+  if (warp < kProducerWarps) {
+    // ===================== producers =====================
+    const WeightSrc& bsrc = p.b[cls];
+    for (int kb = 0; kb < num_kb; ++kb)
+      fill_dense_async<BN, 128>(b_base + kb * (BN * 128), bsrc.w, bsrc.ldb, 0, 1 << 30, kb * kBK, tid, bsrc.perm);
+    cp_async_mbar_arrive(bfull_bar);
+    mbar_arrive(bfull_bar);
+    ConvLoader<128> aload = p.a[cls];
+    aload.init_thread(ktab, tid);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      aload.prepare(tile * 128, tid);
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % kPersistStages;
+        const uint32_t ph = (it / kPersistStages) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1, 11);
+        aload.fill_async(a_base + s * 16384, kb, tid);
+        cp_async_mbar_arrive(full_bar(s));
+        mbar_arrive(full_bar(s));
+      }
+    }
+  } else if (warp == kProducerWarps) {
+    // ===================== MMA issuer =====================
+    if (tid == kProducerThreads) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      mbar_wait(bfull_bar, 0, 12);
+      int it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+        const int acc = tcount & 1;
+        const uint32_t aph = (tcount >> 1) & 1;
+        mbar_wait(tempty_bar(acc), aph ^ 1, 13);       // epilogue has drained this accumulator
+        tc_fence_after();
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kPersistStages;
+          const uint32_t ph = (it / kPersistStages) & 1;
+          mbar_wait(full_bar(s), ph, 14);
+          fence_proxy_async();
+          tc_fence_after();
+          const uint32_t a_tile = a_base + s * 16384;
+          const uint32_t b_tile = b_base + kb * (BN * 128);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            uint64_t adesc = make_smem_desc(a_tile + k * 32, 16, 1024, 2);
+            uint64_t bdesc = make_smem_desc(b_tile + k * 32, 16, 1024, 2);
+            umma_bf16(tmem_base + acc * BN, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(tfull_bar(acc));
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const RowEpi& epi = p.e[cls];
+    const int q = warp & 3;                         // TMEM lane quadrant this warp may access
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      const int acc = tcount & 1;
+      const uint32_t aph = (tcount >> 1) & 1;
+      mbar_wait(tfull_bar(acc), aph, 15);
+      tc_fence_after();
+      const int row = tile * 128 + q * 32 + (tid & 31);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      if constexpr (BN >= 32) {
+        uint32_t r[BN / 32][32];
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) tmem_ld32(taddr + c * 32, r[c]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(tempty_bar(acc));   // accumulator is in registers: release it
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) epi_store32(epi, row, c * 32, r[c], 0);
+      } else {
+        uint32_t r16[16];
+        tmem_ld16(taddr, r16);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(tempty_bar(acc));
+        epi_store16(epi, row, 0, r16, 0);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == kProducerWarps) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -492,6 +650,9 @@ struct WgradCfg {
   static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
   static_assert(ACC_COLS <= 512, "accumulator does not fit TMEM");
   static_assert(STAGES * STAGE_BYTES >= 512 * 8 * 4, "stage memory is reused as the column-sum scratch");
+  static constexpr int KTAB_BYTES = MT * 2 * 8 * 16;          // k-chunk decode table of this CTA's atoms
+  static constexpr int ROWTAB_ROWS = 2048;                     // decoded row positions (rows_per_split <= this)
+  static constexpr int SMEM_TOTAL = SMEM + KTAB_BYTES + ROWTAB_ROWS * 8;
 };
 
 template <class ALoad64, int MT, int BN>
@@ -507,6 +668,8 @@ __global__ void __launch_bounds__(kWgradThreads) wgrad_kernel(ALoad64 aload, con
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
   const uint32_t tmem_full_bar = bar_base + 8u * (2 * Cfg::STAGES);
   const uint32_t tmem_ptr_addr = tmem_full_bar + 8u;
+  int4* ktab = reinterpret_cast<int4*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES + 256);
+  RowPos* rowtab = reinterpret_cast<RowPos*>(reinterpret_cast<uint8_t*>(ktab) + Cfg::KTAB_BYTES);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -520,6 +683,7 @@ __global__ void __launch_bounds__(kWgradThreads) wgrad_kernel(ALoad64 aload, con
   const int niter = (r_end > r_begin) ? (r_end - r_begin + 63) / 64 : 0;
   const int natoms = min(MT * 2, k_atoms_total - atom0);  // atoms that exist (the rest are never stored)
   const bool want_bias = (epi.bias_out != nullptr) && (blockIdx.x == 0) && (Cfg::B_ATOMS == 1);
+  const bool use_rowtab = ALoad64::kNeedsTable && (rows_per_split <= Cfg::ROWTAB_ROWS);
 
   if (tid == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
@@ -528,6 +692,13 @@ __global__ void __launch_bounds__(kWgradThreads) wgrad_kernel(ALoad64 aload, con
     }
     mbar_init(tmem_full_bar, 1);
     fence_mbar_init();
+  }
+  if constexpr (ALoad64::kNeedsTable) {
+    // decode tables, built once per CTA: K-chunk -> tap offset (k' chunks are global: atom0*8 + ...),
+    // and row -> (image, origin) for every row of this split (no integer division in the stage loop)
+    aload.build_table(ktab, natoms * 8, tid, kWgradThreads, atom0 * 8);   // indexed by the CTA-local chunk
+    if (use_rowtab)
+      for (int lr = tid; lr < niter * 64; lr += kWgradThreads) rowtab[lr] = conv_row_pos(aload.g, r_begin + lr);
   }
   if (warp == kWgradProducerWarps) tmem_alloc(tmem_ptr_addr, Cfg::TMEM_COLS);
   tc_fence_before();
@@ -538,6 +709,7 @@ __global__ void __launch_bounds__(kWgradThreads) wgrad_kernel(ALoad64 aload, con
 
   float csum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (warp < kWgradProducerWarps) {
+    aload.init_thread(ktab, gtid);
     for (int it = group; it < niter; it += 2) {
       const int s = it % Cfg::STAGES;
       const uint32_t ph = (it / Cfg::STAGES) & 1;
@@ -547,7 +719,8 @@ __global__ void __launch_bounds__(kWgradThreads) wgrad_kernel(ALoad64 aload, con
       const int row0 = r_begin + it * 64;
       // rows beyond r_end must contribute zero: the loaders zero rows >= their nrows, and the
       // split boundary is enforced on the dY side (zero rows => zero products).
-      aload.prepare(row0, gtid);
+      if (use_rowtab) aload.prepare_tab(rowtab, it * 64, gtid);
+      else aload.prepare(row0, gtid);
       if constexpr (Cfg::B_ATOMS == 1) {
         // dY goes through registers (its column sums are the bias gradient); its loads are issued first so
         // their latency overlaps the issue of the A-operand cp.async gathers
@@ -562,7 +735,8 @@ __global__ void __launch_bounds__(kWgradThreads) wgrad_kernel(ALoad64 aload, con
           if (i < 64 * CH && row0 + r < r_end)
             bv[q] = __ldg(reinterpret_cast<const uint4*>(dy + (long)(row0 + r) * ld_dy + n0 + c * 8));
         }
-        for (int at = 0; at < natoms; ++at) aload.fill_async(a_tile + at * 8192, atom0 + at, gtid);
+        for (int at = 0; at < natoms; ++at)
+          aload.fill_async(a_tile + at * 8192, ALoad64::kNeedsTable ? at : atom0 + at, gtid);
 #pragma unroll
         for (int q = 0; q < NB; ++q) {
           int i = gtid + q * 256;
@@ -578,7 +752,8 @@ __global__ void __launch_bounds__(kWgradThreads) wgrad_kernel(ALoad64 aload, con
         }
         fence_proxy_async();
       } else {
-        for (int at = 0; at < natoms; ++at) aload.fill_async(a_tile + at * 8192, atom0 + at, gtid);
+        for (int at = 0; at < natoms; ++at)
+          aload.fill_async(a_tile + at * 8192, ALoad64::kNeedsTable ? at : atom0 + at, gtid);
 #pragma unroll
         for (int at = 0; at < Cfg::B_ATOMS; ++at)
           fill_dense_async<64, 128>(b_tile + at * 8192, dy, ld_dy, row0, r_end, n0 + at * 64, gtid);

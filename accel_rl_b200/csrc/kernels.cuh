@@ -439,177 +439,178 @@ struct HeadParams {
   __nv_bfloat16* h_out;     // [M][H] post-ReLU hidden (bf16)
   __nv_bfloat16* dh_out;    // [M][H] gradient w.r.t. FC pre-activation (bf16)
   float* dlogit_out;        // [M][A+1]  (last column: dV)
-  float* loss_partial;      // [gridDim.x][4]  pi, v, ent, total per block
+  float* loss_partial;      // [M][4]  pi, v, ent, total per sample row
 };
 
-template <int MODE>
-__global__ void __launch_bounds__(256) head_kernel(HeadParams p) {
-  extern __shared__ float sm_head[];   // w_pi [H*A], w_v [H], b_pi[A], b_v, fc_bias[H]
-  float* s_wpi = sm_head;
-  float* s_wv = s_wpi + p.H * p.A;
-  float* s_bpi = s_wv + p.H;
-  float* s_fcb = s_bpi + kMaxActions + 2;
-  for (int i = threadIdx.x; i < p.H * p.A; i += blockDim.x) s_wpi[i] = p.w_pi[i];
-  for (int i = threadIdx.x; i < p.H; i += blockDim.x) { s_wv[i] = p.w_v[i]; s_fcb[i] = p.fc_bias[i]; }
-  if (threadIdx.x < p.A) s_bpi[threadIdx.x] = p.b_pi[threadIdx.x];
-  if (threadIdx.x == 0) s_bpi[kMaxActions] = p.b_v[0];
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int wpb = blockDim.x >> 5;
-  float loss_pi = 0.f, loss_v = 0.f, loss_ent = 0.f;
-  const int JP = (p.H + 31) / 32;   // h values per lane (<= 16 for H <= 512)
-  for (int row = blockIdx.x * wpb + warp; row < p.M; row += gridDim.x * wpb) {
-    float h[16];
-    float logit[kMaxActions];
-#pragma unroll
-    for (int a = 0; a < kMaxActions; ++a) logit[a] = 0.f;
-    float v = 0.f;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      int j = lane + 32 * i;
-      h[i] = (i < JP && j < p.H) ? s_fcb[j] : 0.f;
-    }
-    for (int s = 0; s < p.splits; ++s) {     // 16 independent loads per split: the sum is latency-bound otherwise
-      const float* ps = p.partial + ((long)s * p.M + row) * p.H + lane;
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (i < JP && lane + 32 * i < p.H) h[i] += ps[32 * i];
-    }
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      int j = lane + 32 * i;
-      if (i < JP && j < p.H) {
-        float acc = h[i];
-        acc = fmaxf(acc, 0.f);
-        acc = __bfloat162float(__float2bfloat16_rn(acc));
-        h[i] = acc;
-        v += acc * s_wv[j];
-#pragma unroll
-        for (int a = 0; a < kMaxActions; ++a)
-          if (a < p.A) logit[a] += acc * s_wpi[j * p.A + a];
-      }
-    }
-    v = warp_sum(v) + s_bpi[kMaxActions];
-    float mx = -INFINITY;
-#pragma unroll
-    for (int a = 0; a < kMaxActions; ++a)
-      if (a < p.A) {
-        logit[a] = warp_sum(logit[a]) + s_bpi[a];
-        mx = fmaxf(mx, logit[a]);
-      }
-    float prob[kMaxActions];
-    float sum = 0.f;
-#pragma unroll
-    for (int a = 0; a < kMaxActions; ++a) {
-      prob[a] = 0.f;
-      if (a < p.A) { prob[a] = expf(logit[a] - mx); sum += prob[a]; }
-    }
-#pragma unroll
-    for (int a = 0; a < kMaxActions; ++a) prob[a] = prob[a] / sum;
+constexpr int kHeadThreads = 128;
 
-    if (MODE == 0) {
-      long orow = p.out_rows ? p.out_rows[row] : row;
-      if (lane == 0) {
-        if (p.prob) {
+// One block (4 warps) per sample row: thread t owns hidden units j = t, t+128, ... (<= 4 for H <= 512).
+// The split-K partial sums are the only HBM-latency-bound part, so every thread keeps 4 x unroll
+// independent loads in flight; logits/value are reduced over the block through shared memory and the
+// softmax / loss arithmetic is done redundantly by every thread (a handful of flops).
+template <int MODE>
+__global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadParams p) {
+  __shared__ float s_part[kHeadThreads / 32][kMaxActions + 1];
+  const int row = blockIdx.x;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  constexpr int JT = 4;
+  float h[JT];
 #pragma unroll
-          for (int a = 0; a < kMaxActions; ++a)
-            if (a < p.A) p.prob[orow * p.A + a] = prob[a];
-        }
-        if (p.value) p.value[orow] = v;
-        if (p.actions) {
-          double u = p.uniforms[row];
-          float cs = 0.f;
-          int k = 0;
+  for (int i = 0; i < JT; ++i) {
+    int j = t + kHeadThreads * i;
+    h[i] = (j < p.H) ? __ldg(p.fc_bias + j) : 0.f;
+  }
+  const float* prow = p.partial + (long)row * p.H + t;
+  const long sstride = (long)p.M * p.H;
+#pragma unroll 4
+  for (int s = 0; s < p.splits; ++s) {
 #pragma unroll
-          for (int a = 0; a < kMaxActions; ++a)
-            if (a < p.A) { cs = __fadd_rn(cs, prob[a]); k += ((double)cs < u) ? 1 : 0; }
-          p.actions[orow] = (uint8_t)min(k, p.A - 1);
-        }
-      }
-    } else {
-      const long src = p.idx ? p.idx[(p.idx_off ? (long)p.idx_off[0] * p.M : 0) + row] : row;
-      const int act = p.act_in[src];
-      const float adv = p.adv[src], ret = p.ret[src];
-      float w = p.inv_count;
-      if (p.valids) w = p.valids[src] ? (1.f / p.valid_count[0]) : 0.f;
-      const float TINY = 1e-8f;
-      float g[kMaxActions];   // dL/dprob
-      float ent = 0.f;
-      float pa = 0.f;
+    for (int i = 0; i < JT; ++i)
+      if (t + kHeadThreads * i < p.H) h[i] += prow[s * sstride + kHeadThreads * i];
+  }
+  float logit[kMaxActions];
 #pragma unroll
-      for (int a = 0; a < kMaxActions; ++a) {
-        g[a] = 0.f;
-        if (a < p.A) {
-          float lp = logf(prob[a] + TINY);
-          ent -= prob[a] * lp;
-          g[a] = p.ent_coeff * w * (lp + prob[a] / (prob[a] + TINY));
-          if (a == act) pa = prob[a];
-        }
-      }
-      float l_pi;
-      float gact;
-      if (p.algo == 0) {
-        float po = p.old_prob[src * p.A + act];
-        float ratio = (pa + TINY) / (po + TINY);
-        float cp = p.clip_param * p.hyper[0];
-        float lo = 1.f - cp, hi = 1.f + cp;
-        float clipped = fminf(fmaxf(ratio, lo), hi);
-        float s1 = ratio * adv, s2 = clipped * adv;
-        l_pi = -fminf(s1, s2);
-        float gr;
-        if (ratio < lo) gr = (adv >= 0.f) ? adv : 0.f;
-        else if (ratio > hi) gr = (adv <= 0.f) ? adv : 0.f;
-        else gr = adv;
-        gact = -w * gr / (po + TINY);
-      } else {
-        l_pi = -logf(pa + TINY) * adv;
-        gact = -w * adv / (pa + TINY);
-      }
+  for (int a = 0; a < kMaxActions; ++a) logit[a] = 0.f;
+  float v = 0.f;
+#pragma unroll
+  for (int i = 0; i < JT; ++i) {
+    int j = t + kHeadThreads * i;
+    if (j < p.H) {
+      float acc = fmaxf(h[i], 0.f);
+      acc = __bfloat162float(__float2bfloat16_rn(acc));     // the value the backward pass sees
+      h[i] = acc;
+      v += acc * __ldg(p.w_v + j);
+      const float* wr = p.w_pi + (long)j * p.A;
 #pragma unroll
       for (int a = 0; a < kMaxActions; ++a)
-        if (a == act) g[a] += gact;
-      float verr = v - ret;
-      float dv = 2.f * p.v_coeff * w * verr;
-      float dot = 0.f;
-#pragma unroll
-      for (int a = 0; a < kMaxActions; ++a) dot += prob[a] * g[a];
-      float dl[kMaxActions];
-#pragma unroll
-      for (int a = 0; a < kMaxActions; ++a) dl[a] = prob[a] * (g[a] - dot);
-      if (lane == 0) {
-        loss_pi += w * l_pi;
-        loss_v += p.v_coeff * w * verr * verr;
-        loss_ent += -p.ent_coeff * w * ent;
-#pragma unroll
-        for (int a = 0; a < kMaxActions; ++a)
-          if (a < p.A) p.dlogit_out[(long)row * (p.A + 1) + a] = dl[a];
-        p.dlogit_out[(long)row * (p.A + 1) + p.A] = dv;
-      }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        int j = lane + 32 * i;
-        if (i < JP && j < p.H) {
-          float d = dv * s_wv[j];
-#pragma unroll
-          for (int a = 0; a < kMaxActions; ++a)
-            if (a < p.A) d += dl[a] * s_wpi[j * p.A + a];
-          d = (h[i] > 0.f) ? d : 0.f;
-          p.h_out[(long)row * p.H + j] = __float2bfloat16_rn(h[i]);
-          p.dh_out[(long)row * p.H + j] = __float2bfloat16_rn(d);
-        }
-      }
+        if (a < p.A) logit[a] += acc * __ldg(wr + a);
     }
   }
-  if (MODE == 1) {
-    __shared__ float s_l[3][8];
-    if (lane == 0) { s_l[0][warp] = loss_pi; s_l[1][warp] = loss_v; s_l[2][warp] = loss_ent; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float a = 0.f, b = 0.f, c = 0.f;
-      for (int w2 = 0; w2 < wpb; ++w2) { a += s_l[0][w2]; b += s_l[1][w2]; c += s_l[2][w2]; }
-      float* o = p.loss_partial + 4 * blockIdx.x;
-      o[0] = a; o[1] = b; o[2] = c; o[3] = a + b + c;
+  v = warp_sum(v);
+#pragma unroll
+  for (int a = 0; a < kMaxActions; ++a)
+    if (a < p.A) logit[a] = warp_sum(logit[a]);
+  if (lane == 0) {
+#pragma unroll
+    for (int a = 0; a < kMaxActions; ++a)
+      if (a < p.A) s_part[warp][a] = logit[a];
+    s_part[warp][kMaxActions] = v;
+  }
+  __syncthreads();
+  v = __ldg(p.b_v);
+#pragma unroll
+  for (int w = 0; w < kHeadThreads / 32; ++w) v += s_part[w][kMaxActions];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int a = 0; a < kMaxActions; ++a)
+    if (a < p.A) {
+      float l = __ldg(p.b_pi + a);
+#pragma unroll
+      for (int w = 0; w < kHeadThreads / 32; ++w) l += s_part[w][a];
+      logit[a] = l;
+      mx = fmaxf(mx, l);
+    }
+  float prob[kMaxActions];
+  float sum = 0.f;
+#pragma unroll
+  for (int a = 0; a < kMaxActions; ++a) {
+    prob[a] = 0.f;
+    if (a < p.A) { prob[a] = expf(logit[a] - mx); sum += prob[a]; }
+  }
+#pragma unroll
+  for (int a = 0; a < kMaxActions; ++a) prob[a] = prob[a] / sum;
+
+  if (MODE == 0) {
+    if (t == 0) {
+      long orow = p.out_rows ? p.out_rows[row] : row;
+      if (p.prob) {
+#pragma unroll
+        for (int a = 0; a < kMaxActions; ++a)
+          if (a < p.A) p.prob[orow * p.A + a] = prob[a];
+      }
+      if (p.value) p.value[orow] = v;
+      if (p.actions) {
+        double u = p.uniforms[row];
+        float cs = 0.f;
+        int k = 0;
+#pragma unroll
+        for (int a = 0; a < kMaxActions; ++a)
+          if (a < p.A) { cs = __fadd_rn(cs, prob[a]); k += ((double)cs < u) ? 1 : 0; }
+        p.actions[orow] = (uint8_t)min(k, p.A - 1);
+      }
+    }
+  } else {
+    const long src = p.idx ? p.idx[(p.idx_off ? (long)p.idx_off[0] * p.M : 0) + row] : row;
+    const int act = p.act_in[src];
+    const float adv = p.adv[src], ret = p.ret[src];
+    float w = p.inv_count;
+    if (p.valids) w = p.valids[src] ? (1.f / p.valid_count[0]) : 0.f;
+    const float TINY = 1e-8f;
+    float g[kMaxActions];   // dL/dprob
+    float ent = 0.f;
+    float pa = 0.f;
+#pragma unroll
+    for (int a = 0; a < kMaxActions; ++a) {
+      g[a] = 0.f;
+      if (a < p.A) {
+        float lp = logf(prob[a] + TINY);
+        ent -= prob[a] * lp;
+        g[a] = p.ent_coeff * w * (lp + prob[a] / (prob[a] + TINY));
+        if (a == act) pa = prob[a];
+      }
+    }
+    float l_pi;
+    float gact;
+    if (p.algo == 0) {
+      float po = p.old_prob[src * p.A + act];
+      float ratio = (pa + TINY) / (po + TINY);
+      float cp = p.clip_param * p.hyper[0];
+      float lo = 1.f - cp, hi = 1.f + cp;
+      float clipped = fminf(fmaxf(ratio, lo), hi);
+      float s1 = ratio * adv, s2 = clipped * adv;
+      l_pi = -fminf(s1, s2);
+      float gr;
+      if (ratio < lo) gr = (adv >= 0.f) ? adv : 0.f;
+      else if (ratio > hi) gr = (adv <= 0.f) ? adv : 0.f;
+      else gr = adv;
+      gact = -w * gr / (po + TINY);
+    } else {
+      l_pi = -logf(pa + TINY) * adv;
+      gact = -w * adv / (pa + TINY);
+    }
+#pragma unroll
+    for (int a = 0; a < kMaxActions; ++a)
+      if (a == act) g[a] += gact;
+    float verr = v - ret;
+    float dv = 2.f * p.v_coeff * w * verr;
+    float dot = 0.f;
+#pragma unroll
+    for (int a = 0; a < kMaxActions; ++a) dot += prob[a] * g[a];
+    float dl[kMaxActions];
+#pragma unroll
+    for (int a = 0; a < kMaxActions; ++a) dl[a] = prob[a] * (g[a] - dot);
+    if (t == 0) {
+      float lp_ = w * l_pi, lv_ = p.v_coeff * w * verr * verr, le_ = -p.ent_coeff * w * ent;
+      float* o = p.loss_partial + 4 * (long)row;
+      o[0] = lp_; o[1] = lv_; o[2] = le_; o[3] = lp_ + lv_ + le_;
+#pragma unroll
+      for (int a = 0; a < kMaxActions; ++a)
+        if (a < p.A) p.dlogit_out[(long)row * (p.A + 1) + a] = dl[a];
+      p.dlogit_out[(long)row * (p.A + 1) + p.A] = dv;
+    }
+#pragma unroll
+    for (int i = 0; i < JT; ++i) {
+      int j = t + kHeadThreads * i;
+      if (j < p.H) {
+        float d = dv * __ldg(p.w_v + j);
+        const float* wr = p.w_pi + (long)j * p.A;
+#pragma unroll
+        for (int a = 0; a < kMaxActions; ++a)
+          if (a < p.A) d += dl[a] * __ldg(wr + a);
+        d = (h[i] > 0.f) ? d : 0.f;
+        p.h_out[(long)row * p.H + j] = __float2bfloat16_rn(h[i]);
+        p.dh_out[(long)row * p.H + j] = __float2bfloat16_rn(d);
+      }
     }
   }
 }
@@ -765,6 +766,7 @@ struct UpdateParams {
   float gscale;            // gradient averaging factor (1/n_gpu for sync DP)
   float* out_norm; float* out_loss;   // [cap] logs, slot = log_slot[0]
   int* log_slot; int log_cap;
+  __nv_bfloat16* shadow; long shadow_begin, shadow_end;   // bf16 copy of params[shadow_begin, shadow_end) (4-aligned)
 };
 
 __global__ void __launch_bounds__(256) update_kernel(UpdateParams p) {
@@ -793,15 +795,25 @@ __global__ void __launch_bounds__(256) update_kernel(UpdateParams p) {
     }
     if (blockIdx.x == 0) {
       int slot = p.log_slot[0];
-      if (slot < p.log_cap) {
-        p.out_norm[slot] = norm;
-        float l = 0.f;
-        for (int b = 0; b < p.n_loss_blocks; ++b) l += p.loss_partial[4 * b + 3];
-        p.out_loss[slot] = l;
-      }
+      if (slot < p.log_cap) p.out_norm[slot] = norm;
     }
   }
   __syncthreads();
+  if (blockIdx.x == 0) {
+    // loss of this update = sum of the per-row terms (fixed order: strided per thread, then tree)
+    float l = 0.f;
+    for (int b = threadIdx.x; b < p.n_loss_blocks; b += blockDim.x) l += p.loss_partial[4 * b + 3];
+    l = warp_sum(l);
+    __shared__ float s_l[8];
+    if ((threadIdx.x & 31) == 0) s_l[threadIdx.x >> 5] = l;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tl = 0.f;
+      for (int w = 0; w < 8; ++w) tl += s_l[w];
+      int slot = p.log_slot[0];
+      if (slot < p.log_cap) p.out_loss[slot] = tl;
+    }
+  }
   const float scale = s_scale, alpha = s_alpha;
   const long n4 = p.n >> 2;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
@@ -830,6 +842,11 @@ __global__ void __launch_bounds__(256) update_kernel(UpdateParams p) {
     }
     reinterpret_cast<float4*>(p.v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
     reinterpret_cast<float4*>(p.param)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+    // bf16 operand copy of the FC weights (same layout), refreshed in the same pass
+    const long e0 = i << 2;
+    if (p.shadow && e0 >= p.shadow_begin && e0 + 4 <= p.shadow_end)
+      *reinterpret_cast<uint2*>(p.shadow + (e0 - p.shadow_begin)) =
+          make_uint2(pack_bf16x2(pp[0], pp[1]), pack_bf16x2(pp[2], pp[3]));
   }
   if (blockIdx.x == 0 && threadIdx.x < (p.n & 3)) {
     long i = (n4 << 2) + threadIdx.x;
@@ -871,7 +888,12 @@ struct PackJob {
 };
 
 __global__ void __launch_bounds__(256) pack_weights_kernel(const PackJob* __restrict__ jobs,
-                                                            const float* __restrict__ params) {
+                                                            const float* __restrict__ params, int* step,
+                                                            int* log_slot, int* mb_counter) {
+  // last kernel of an update: also advances the device-side counters (Adam t, log slot, minibatch index)
+  if (step && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    step[0] += 1; log_slot[0] += 1; mb_counter[0] += 1;
+  }
   const PackJob jb = jobs[blockIdx.y];
   const long total = (long)jb.rows * jb.cols;
   const float* W = params + jb.src_off;
