@@ -48,6 +48,7 @@ struct CommState {
   CommDev dev{};
   float* grad = nullptr;                  // local views
   float* param = nullptr;
+  unsigned int gen = 0;                   // grid-barrier generation carried across launches of this context
 };
 
 struct SyncUpdateArgs {
@@ -296,9 +297,8 @@ inline int comm_barrier(CommState& s, cudaStream_t st, std::string& err) {
 inline int comm_sync_update(CommState& s, SyncUpdateArgs a, cudaStream_t st, std::string& err) {
   if (!s.ready) { err = "comm not connected"; return 1; }
   if (a.param != s.param || a.grad != s.grad) { err = "params/grad must be the comm's symmetric buffers"; return 1; }
-  static unsigned int gen_host = 0;   // grid-barrier generation carried across launches
-  unsigned int gen0 = gen_host;
-  gen_host += 4u * kSyncBlocks;       // four grid barriers per launch
+  unsigned int gen0 = s.gen;
+  s.gen += 4u * kSyncBlocks;          // four grid barriers per launch
   void* args[] = {(void*)&s.dev, (void*)&a, (void*)&gen0};
   cudaError_t e = cudaLaunchCooperativeKernel((const void*)sync_allreduce_update_kernel, dim3(kSyncBlocks),
                                               dim3(kSyncThreads), args, 0, st);
