@@ -160,6 +160,24 @@ def timed_iterations(runner, steps, warmup, world, itr0=0):
     return ms / steps, eng.launches - l0, wall, last, itr
 
 
+def phase_split(runner, itr0, reps=3):
+    """device time of the two halves of a step (CUDA events on the launching stream)"""
+    import torch
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    roll, train = 0.0, 0.0
+    itr = itr0
+    for _ in range(reps):
+        ev[0].record()
+        s, _ = runner.sampler.obtain_samples(itr)
+        ev[1].record()
+        runner.algo.optimize_policy(itr, s)
+        ev[2].record()
+        torch.cuda.synchronize()
+        roll += ev[0].elapsed_time(ev[1]); train += ev[1].elapsed_time(ev[2])
+        itr += 1
+    return {"rollout_ms": round(roll / reps, 3), "gae_update_ms": round(train / reps, 3)}
+
+
 def kernel_breakdown(runner, args):
     """CUDA-event duration of every kernel of one minibatch update and one rollout step (launched outside the
     graphs, same order, same data) -> {label: (avg ms, launches per PPO iteration)}"""
@@ -231,8 +249,9 @@ def run_ours(args):
     value = world * N / (ms_step * 1e-3)
 
     result = None
+    phases = phase_split(runner, itr)
     if rank == 0:
-        bd = kernel_breakdown(runner, args) if args.spec == 1 else {}
+        bd = kernel_breakdown(runner, args) if (args.spec == 1 and world == 1) else {}
         # dominant kernel by time per PPO iteration
         roof = None
         kernels = []
@@ -269,6 +288,7 @@ def run_ours(args):
             "roofline": roof,
             "kernels": kernels[:14],
             "host_wall_s": round(wall, 3),
+            "phases": phases,
         }
     # ---- e2e: raw frames from pinned host memory every step, results read back ----
     if not args.no_e2e:
@@ -294,7 +314,7 @@ def run_ours(args):
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         result["cpu_baseline"] = cpu_port(args, steps=1)
     if rank == 0:
-        print(json.dumps(result))
+        _emit(result)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -365,10 +385,19 @@ def run_reference(args):
            "cpu_baseline": r,
            "e2e": {"value": r["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "wall_s": round(time.time() - t0, 1)}
-    print(json.dumps(out))
+    _emit(out)
+
+
+def _emit(obj):
+    """the ONE JSON line goes to the real stdout; everything else any library prints was routed to stderr"""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
 
 
 if __name__ == "__main__":
+    # keep stdout clean for the single JSON line (NCCL / torchrun banners go to stderr)
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     a = parse()
     if a.impl == "reference":
         run_reference(a)
