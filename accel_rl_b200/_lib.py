@@ -120,6 +120,8 @@ SIGNATURES = {
     "arl_debug_activation": (C.c_int, [_P, C.c_int, _P, C.c_long, C.POINTER(C.c_long), _P]),
     "arl_kernel_launches": (C.c_long, [_P]),
     "arl_profile_begin": (C.c_int, [_P, _P]),
+    "arl_profile_graph": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_char_p, C.c_int, _P, C.c_int,
+                                    C.POINTER(C.c_int), _P]),
     "arl_profile_end": (C.c_int, [_P, C.c_char_p, C.c_int, _P, C.c_int, C.POINTER(C.c_int), _P]),
     "arl_test_gemm": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "arl_test_wgrad": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),

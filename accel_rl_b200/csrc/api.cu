@@ -124,6 +124,8 @@ struct arl_ctx {
   long launches = 0;
   // per-kernel CUDA-event profiling (arl_profile_*): events recorded after each launch when enabled
   bool prof_on = false;
+  bool prof_collect = false;             // record one label per kernel launch (arl_profile_graph)
+  std::vector<std::string> prof_labels;
   std::vector<cudaEvent_t> prof_ev;
   std::vector<std::string> prof_names;
   int prof_n = 0;
@@ -148,6 +150,7 @@ int roundup(int x, int m) { return (x + m - 1) / m * m; }
 
 // record an event after the launch that just happened (profiling mode only)
 void prof_mark(arl_ctx* c, const char* name, cudaStream_t st) {
+  if (c->prof_collect) c->prof_labels.push_back(name);
   if (!c->prof_on) return;
   if (c->prof_n >= (int)c->prof_ev.size()) {
     cudaEvent_t e;
@@ -595,6 +598,7 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
   if (c->t_valids) {
     count_valids_idx_kernel<<<1, 1024, 0, st>>>(c->t_valids, idx, idx_off, n, c->valid_count);
     c->launches++;
+    prof_mark(c, "count_valids", st);
   }
   HeadParams p = head_base(c, n, S);
   p.idx = idx; p.idx_off = idx_off; p.act_in = c->t_act; p.adv = c->t_adv; p.ret = c->t_ret; p.old_prob = c->t_oldp;
@@ -1201,6 +1205,90 @@ int arl_debug_activation(arl_ctx* c, int layer, float* out, long cap, long* n, v
 }
 
 long arl_kernel_launches(arl_ctx* c) { return c->launches; }
+
+#ifdef ARL_TRACE
+extern "C" int arl_trace_read(long long* out, int n) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * n);
+}
+#endif
+
+// Per-kernel device times of one training minibatch (kind 0) or one rollout step (kind 1).  The sequence is
+// captured into a CUDA graph exactly as the product path does; the whole graph is replayed a few times (so every
+// kernel's inputs exist and are L2-warm), then every kernel node is re-launched `reps` times back to back with its
+// captured arguments and timed with one event pair (GPU-bound: launch gaps are hidden behind the previous launch).
+int arl_profile_graph(arl_ctx* c, int kind, const int* idx, int mb_size, int reps, char* names, int names_cap,
+                      float* ms, int cap, int* n, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (kind == 0) { TrainPlan* P = nullptr; if (get_plan(c, mb_size, &P)) return 1; }
+  cudaStream_t cap_s;
+  ARL_CHECK(c, cudaStreamCreateWithFlags(&cap_s, cudaStreamNonBlocking));
+  c->prof_labels.clear();
+  c->prof_collect = true;
+  long l0 = c->launches;
+  cudaGraph_t g = nullptr;
+  ARL_CHECK(c, cudaStreamBeginCapture(cap_s, cudaStreamCaptureModeThreadLocal));
+  int rc = 0;
+  if (kind == 0) {
+    rc = grad_minibatch(c, idx, c->mb_counter, mb_size, cap_s);
+    if (!rc) rc = clip_update(c, 1.f, cap_s);
+  } else {
+    rc = rollout_step(c, 0, nullptr, cap_s);
+  }
+  cudaError_t ce = cudaStreamEndCapture(cap_s, &g);
+  c->prof_collect = false;
+  c->launches = l0;
+  if (rc) { if (g) cudaGraphDestroy(g); cudaStreamDestroy(cap_s); return rc; }
+  ARL_CHECK(c, ce);
+  cudaGraphExec_t ge = nullptr;
+  ARL_CHECK(c, cudaGraphInstantiate(&ge, g, 0));
+  ARL_CHECK(c, cudaMemsetAsync(c->mb_counter, 0, sizeof(int), st));
+  for (int i = 0; i < 3; ++i) ARL_CHECK(c, cudaGraphLaunch(ge, st));
+  ARL_CHECK(c, cudaMemsetAsync(c->mb_counter, 0, sizeof(int), st));
+  // walk the (linear) dependency chain
+  size_t nroot = 1;
+  cudaGraphNode_t node = nullptr;
+  ARL_CHECK(c, cudaGraphGetRootNodes(g, &node, &nroot));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  std::string all;
+  int cnt = 0;
+  size_t li = 0;
+  while (node && cnt < cap) {
+    cudaGraphNodeType ty;
+    ARL_CHECK(c, cudaGraphNodeGetType(node, &ty));
+    if (ty == cudaGraphNodeTypeKernel) {
+      cudaKernelNodeParams kp{};
+      ARL_CHECK(c, cudaGraphKernelNodeGetParams(node, &kp));
+      ARL_CHECK(c, cudaEventRecord(e0, st));
+      for (int r = 0; r < reps; ++r)
+        ARL_CHECK(c, cudaLaunchKernel(kp.func, kp.gridDim, kp.blockDim, kp.kernelParams, kp.sharedMemBytes, st));
+      ARL_CHECK(c, cudaEventRecord(e1, st));
+      ARL_CHECK(c, cudaStreamSynchronize(st));
+      float t = 0.f;
+      ARL_CHECK(c, cudaEventElapsedTime(&t, e0, e1));
+      ms[cnt++] = t / reps;
+      all += (li < c->prof_labels.size()) ? c->prof_labels[li] : std::string("kernel");
+      all += ';';
+      ++li;
+    }
+    size_t nd = 1;
+    cudaGraphNode_t next = nullptr;
+    cudaError_t de = cudaGraphNodeGetDependentNodes(node, &next, &nd);
+    if (de != cudaSuccess || nd == 0) break;
+    node = next;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  // the update kernels ran `reps` extra times: counters / optimizer state moved; restore the counters only
+  ARL_CHECK(c, cudaMemsetAsync(c->mb_counter, 0, sizeof(int), st));
+  ARL_CHECK(c, cudaStreamSynchronize(st));
+  *n = cnt;
+  snprintf(names, names_cap, "%s", all.c_str());
+  cudaGraphExecDestroy(ge);
+  cudaGraphDestroy(g);
+  cudaStreamDestroy(cap_s);
+  return 0;
+}
 
 int arl_profile_begin(arl_ctx* c, void* stream) {
   c->prof_on = true;

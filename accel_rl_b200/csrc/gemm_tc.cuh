@@ -475,6 +475,12 @@ struct RowGemmMulti {
 // memory; barriers/TMEM are set up once per CTA instead of once per tile.
 // ---------------------------------------------------------------------------
 constexpr int kPersistThreads = kProducerThreads + 32 + 128;   // 416
+#ifdef ARL_TRACE
+__device__ long long g_trace[4096];
+#define ARL_T(slot) do { if (blockIdx.x == 0 && blockIdx.y == 0 && (slot) < 4096) g_trace[(slot)] = clock64(); } while (0)
+#else
+#define ARL_T(slot) do {} while (0)
+#endif
 constexpr int kPersistStages = 4;
 
 template <int BN>
@@ -541,9 +547,11 @@ __global__ void __launch_bounds__(kPersistThreads, 2) conv_gemm_persist_kernel(
         const int s = it % kPersistStages;
         const uint32_t ph = (it / kPersistStages) & 1;
         mbar_wait(empty_bar(s), ph ^ 1, 11);
+        if (tid == 0) ARL_T(it * 6 + 0);
         aload.fill_async(a_base + s * 16384, kb, tid);
         cp_async_mbar_arrive(full_bar(s));
         mbar_arrive(full_bar(s));
+        if (tid == 0) ARL_T(it * 6 + 1);
       }
     }
   } else if (warp == kProducerWarps) {
@@ -561,6 +569,7 @@ __global__ void __launch_bounds__(kPersistThreads, 2) conv_gemm_persist_kernel(
           const int s = it % kPersistStages;
           const uint32_t ph = (it / kPersistStages) & 1;
           mbar_wait(full_bar(s), ph, 14);
+          ARL_T(it * 6 + 2);
           fence_proxy_async();
           tc_fence_after();
           const uint32_t a_tile = a_base + s * 16384;
@@ -572,6 +581,7 @@ __global__ void __launch_bounds__(kPersistThreads, 2) conv_gemm_persist_kernel(
             umma_bf16(tmem_base + acc * BN, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(empty_bar(s));
+          ARL_T(it * 6 + 3);
         }
         umma_commit(tfull_bar(acc));
       }
@@ -585,6 +595,7 @@ __global__ void __launch_bounds__(kPersistThreads, 2) conv_gemm_persist_kernel(
       const int acc = tcount & 1;
       const uint32_t aph = (tcount >> 1) & 1;
       mbar_wait(tfull_bar(acc), aph, 15);
+      if (warp == 9 && (tid & 31) == 0) ARL_T(tcount * 6 + 4);
       tc_fence_after();
       const int row = tile * 128 + q * 32 + (tid & 31);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
@@ -598,6 +609,7 @@ __global__ void __launch_bounds__(kPersistThreads, 2) conv_gemm_persist_kernel(
         if ((tid & 31) == 0) mbar_arrive(tempty_bar(acc));   // accumulator is in registers: release it
 #pragma unroll
         for (int c = 0; c < BN / 32; ++c) epi_store32(epi, row, c * 32, r[c], 0);
+        if (warp == 9 && (tid & 31) == 0) ARL_T(tcount * 6 + 5);
       } else {
         uint32_t r16[16];
         tmem_ld16(taddr, r16);

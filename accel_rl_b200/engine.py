@@ -187,6 +187,15 @@ class Engine(object):
     def profile_begin(self):
         self.check(self.lib.arl_profile_begin(self.ctx, self._s()))
 
+    def profile_graph(self, kind, idx=None, mb_size=0, reps=20, cap=256):
+        names = C.create_string_buffer(cap * 24)
+        ms = np.zeros(cap, np.float32)
+        n = C.c_int()
+        self.check(self.lib.arl_profile_graph(self.ctx, int(kind), L.ptr(idx), int(mb_size), int(reps), names, len(names),
+                                              ms.ctypes.data_as(C.c_void_p), cap, C.byref(n), self._s()))
+        labels = names.value.decode().split(";")[:n.value]
+        return labels, ms[:n.value].copy()
+
     def profile_end(self, cap=4096):
         names = C.create_string_buffer(cap * 24)
         ms = np.zeros(cap, np.float32)

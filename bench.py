@@ -179,39 +179,24 @@ def phase_split(runner, itr0, reps=3):
 
 
 def kernel_breakdown(runner, args):
-    """CUDA-event duration of every kernel of one minibatch update and one rollout step (launched outside the
-    graphs, same order, same data) -> {label: (avg ms, launches per PPO iteration)}"""
-    import numpy as np
+    """Device time of every kernel of one minibatch update and one rollout step, measured with CUDA events recorded
+    INSIDE a replayed CUDA graph (same launch order and data residency as the timed region, no host gaps)
+    -> {label: (ms per launch, launches per PPO iteration)}"""
     import torch
     eng = runner.policy.engine
     N = args.envs * args.horizon
-    reps = 6
-    idx = torch.randperm(N, device="cuda")[:reps * args.minibatch].to(torch.int32).contiguous()
-    acc = {}
-    for warm in (True, False):
-        for r in range(reps):
-            eng.profile_begin()
-            eng.grad_minibatch(idx[r * args.minibatch:(r + 1) * args.minibatch], args.minibatch)
-            eng.clip_update(1.0)
-            labels, ms = eng.profile_end()
-            if not warm:
-                for l, t in zip(labels, ms):
-                    acc.setdefault(l, []).append(float(t))
     n_mb = (N // args.minibatch) * args.epochs
-    out = {l: (float(np.mean(v)) * (len(v) / reps), n_mb) for l, v in acc.items()}   # dgrad classes share a label
-    acc = {}
-    eng.rollout_begin()
-    for s in range(min(12, args.horizon)):
-        eng.profile_begin()
-        eng.rollout_step(s)
-        labels, ms = eng.profile_end()
-        if s >= 4:
-            for l, t in zip(labels, ms):
-                acc.setdefault("rollout/" + l, []).append(float(t))
-    eng.rollout_end()
+    idx = torch.randperm(N, device="cuda")[:8 * args.minibatch].to(torch.int32).contiguous()
+    out = {}
+    labels, ms = eng.profile_graph(0, idx, args.minibatch, reps=24)
+    for l, t in zip(labels, ms):
+        prev = out.get(l, (0.0, n_mb))
+        out[l] = (prev[0] + float(t), n_mb)
+    labels, ms = eng.profile_graph(1, None, 0, reps=24)
+    for l, t in zip(labels, ms):
+        prev = out.get("rollout/" + l, (0.0, args.horizon))
+        out["rollout/" + l] = (prev[0] + float(t), args.horizon)
     eng.read_logs()
-    for l, v in acc.items():
-        out[l] = (float(np.mean(v)), args.horizon)
     return out
 
 

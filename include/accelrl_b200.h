@@ -158,6 +158,10 @@ long arl_kernel_launches(arl_ctx* ctx);
 /* CUDA-event timing of every kernel launched (outside graphs) between begin and end, on `stream`:
  * names = ';'-separated launch labels, ms[i] = device time of launch i */
 int arl_profile_begin(arl_ctx* ctx, void* stream);
+/* same, but measured inside a replayed CUDA graph (event-record node after every kernel): kind 0 = one training
+ * minibatch over idx[0..mb_size) (+ update), kind 1 = one rollout step; replayed `reps` times, last replay reported */
+int arl_profile_graph(arl_ctx* ctx, int kind, const int* idx, int mb_size, int reps, char* names, int names_cap, float* ms,
+                      int cap, int* n, void* stream);
 int arl_profile_end(arl_ctx* ctx, char* names, int names_cap, float* ms, int cap, int* n, void* stream);   /* launches issued (graph replays count their node count) */
 /* plain tcgen05 GEMM self-test: D[M][N] = A[M][K] * B (B K-major [N][K] or N-major [K][N]) */
 int arl_test_gemm(arl_ctx* ctx, const uint16_t* a_bf16, const uint16_t* b_bf16, float* d, int M, int N, int K,
