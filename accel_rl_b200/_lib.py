@@ -9,7 +9,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libaccelrl_b200.so")
+LIB_PATH = os.environ.get("ARL_LIB_PATH", os.path.join(CSRC, "libaccelrl_b200.so"))   # override: debug builds only
 
 ARL_MAX_CONV = 4
 IPC_HANDLE_BYTES = 64
