@@ -12,6 +12,7 @@
 #include "../../include/accelrl_b200.h"
 #include "common.cuh"
 #include "gemm_tc.cuh"
+#include "pconv.cuh"
 #include "kernels.cuh"
 #include "comm.cuh"
 
@@ -56,6 +57,25 @@ struct ConvLayer {
   __nv_bfloat16* dact;
 };
 
+// Geometry of one conv layer on the patch-resident path (pconv.cuh): the layer seen as a stride-1 T x T conv over
+// a position grid of P planes x 64 channels.
+struct PcLayer {
+  int T = 0, P = 0, Wp = 0, Hc = 0, S = 0, N = 0;
+  int ntaps = 0, shift[kPcMaxTaps] = {0};
+  int load_rows = 0, tiles_per_img = 0;
+  int s = 1, pad = 0;            // space-to-depth factor / padding of the input grid (how the layer below stores into it)
+  int ci_major = 0;              // channel order inside a cell: 1 = (ci, py, px) [layer 0: frame kernel], 0 = (py, px, ci)
+  __nv_bfloat16* in = nullptr;   // input grid [P][rows][64] (layers >= 1; layer 0 reads the obs16 buffers)
+  long in_rows = 0;              // rows per plane (max_rows * S + slack)
+  __nv_bfloat16* wpack = nullptr;
+  // backward
+  int dYpad = 0;
+  __nv_bfloat16* dY = nullptr;   // gradient w.r.t. this layer's output, in this layer's grid at offset dYpad (layer 0: pixel grid)
+  long dY_rows = 0;
+  __nv_bfloat16* dwpack = nullptr;  // data-gradient weights [T*T*Pout][P*64][64]
+  int stages_fwd = 0, stages_dgrad = 0;
+};
+
 struct TrainPlan {
   int n = 0;
   std::vector<int> conv_splits, conv_rps;
@@ -71,6 +91,9 @@ struct arl_ctx {
   std::string err;
   arl_net_cfg cfg{};
   std::vector<ConvLayer> conv;
+  std::vector<PcLayer> pc;             // patch-resident conv path (empty: geometry not supported -> gather path)
+  int pc_dy_n = 0;                     // images whose gradient-grid rows may be non-zero
+  int pc_mode = 0;                     // 0: gather path   1: pconv forward (inference)   2: pconv forward + backward
   int Kfc = 0, H = 0, A = 0, HWlast = 0, Clast = 0;
   long off_Wfc = 0, off_bfc = 0, off_Wpi = 0, off_bpi = 0, off_Wv = 0, off_bv = 0, n_params = 0;
   std::vector<long> lay_off, lay_size;
@@ -341,6 +364,251 @@ int plan_net(arl_ctx* c) {
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------
+// patch-resident conv path (pconv.cuh): geometry, buffers, launches
+// ---------------------------------------------------------------------------
+// Fills c->pc when every conv layer fits the path's constraints (otherwise c->pc stays empty and the
+// gather path of gemm_tc.cuh serves the network).
+int plan_pconv(arl_ctx* c) {
+  std::vector<PcLayer> pcs;
+  const int nl = (int)c->conv.size();
+  for (int l = 0; l < nl; ++l) {
+    const ConvLayer& L = c->conv[l];
+    PcLayer q{};
+    q.s = L.s; q.pad = L.p; q.N = L.Cout;
+    q.T = (L.k + L.s - 1) / L.s;
+    int cellc = L.Cin * L.s * L.s;
+    if (cellc % 64 || q.T * q.T > kPcMaxTaps) return 0;
+    q.P = cellc / 64;
+    if (l == 0) {
+      if (L.p != 0 || (L.Hin % L.s) || (L.Win % L.s) || q.P != 1) return 0;
+      if (L.Cout != 32 && L.Cout != 64) return 0;
+      q.ci_major = 1;
+      q.Wp = L.Win / L.s; q.Hc = L.Hin / L.s; q.S = q.Wp * q.Hc;
+      if (q.S % 8) return 0;
+      q.tiles_per_img = ((L.Ho - 1) * q.Wp + L.Wo + 127) / 128;
+    } else {
+      if (L.Cout != 64 || q.P > 2) return 0;
+      const bool shared = (L.s == 1 && L.p >= 1 && 2 * L.p == q.T - 1);   // 'same' conv: pad column/row shared with the neighbour
+      q.Wp = shared ? L.Wo + L.p : L.Wo + q.T - 1;
+      q.Hc = shared ? L.Ho + L.p : L.Ho + q.T - 1;
+      q.S = q.Wp * q.Hc;
+      // every input pixel the layer reads must land inside the grid
+      if ((L.Hin - 1 + L.p) / L.s >= q.Hc + (shared ? 1 : 0) && !shared) return 0;
+      q.dYpad = q.T - 1 - (L.s == 1 ? L.p : 0);
+      if (q.dYpad < 0 || L.Ho + q.dYpad > q.Hc || L.Wo + q.dYpad > q.Wp) return 0;
+      if (L.s > 1 && l != 1) return 0;                         // strided layers above layer 1: no unfold target
+      if (l == 1 && c->conv[0].Cout != 32) return 0;           // unfold epilogue: 32-channel pixels below
+      if (l == 1 && L.s * L.s * c->conv[0].Cout != q.P * 64) return 0;
+    }
+    q.ntaps = q.T * q.T;
+    for (int ty = 0; ty < q.T; ++ty)
+      for (int tx = 0; tx < q.T; ++tx) q.shift[ty * q.T + tx] = ty * q.Wp + tx;
+    q.load_rows = roundup(128 + (q.T - 1) * q.Wp + (q.T - 1), 8);
+    pcs.push_back(q);
+  }
+  // shared-memory budget: weights resident + at least 2 patch stages
+  for (int l = 0; l < nl; ++l) {
+    PcLayer& q = pcs[l];
+    for (q.stages_fwd = 4; q.stages_fwd >= 2; --q.stages_fwd)
+      if (pc_fwd_smem(q.N, q.ntaps, q.P, q.load_rows, q.stages_fwd) <= 227 * 1024) break;
+    if (q.stages_fwd < 2) return 0;
+    if (l >= 1) {
+      int Pout = q.N / 64;
+      for (q.stages_dgrad = 4; q.stages_dgrad >= 2; --q.stages_dgrad)
+        if (pc_fwd_smem(q.P * 64, q.ntaps, Pout, q.load_rows, q.stages_dgrad) <= 227 * 1024) break;
+      if (q.stages_dgrad < 2) return 0;
+    }
+  }
+  c->pc = pcs;
+  return 0;
+}
+
+int alloc_pconv(arl_ctx* c, std::vector<PackJob>& pj) {
+  const int R = c->cfg.max_rows;
+  for (size_t l = 0; l < c->pc.size(); ++l) {
+    PcLayer& q = c->pc[l];
+    const ConvLayer& L = c->conv[l];
+    if (l >= 1) {
+      q.in_rows = (long)R * q.S + q.load_rows + 256;
+      if (dev_alloc(c, &q.in, (size_t)q.P * q.in_rows * 64)) return 1;
+      q.dY_rows = (long)R * q.S + q.load_rows + 256;
+      if (dev_alloc(c, &q.dY, (size_t)(q.N / 64) * q.dY_rows * 64)) return 1;
+    } else {
+      // gradient w.r.t. the first layer's output PIXELS, position-aligned with the first layer's grid
+      q.dY_rows = (long)R * q.S + q.load_rows + 256;
+      if (dev_alloc(c, &q.dY, (size_t)q.dY_rows * q.N)) return 1;
+    }
+    if (dev_alloc(c, &q.wpack, (size_t)q.ntaps * q.P * q.N * 64)) return 1;
+    PackJob j{};
+    j.dst = q.wpack; j.src_off = L.off_W; j.kind = PK_PCONV; j.rows = q.ntaps * q.P * q.N; j.cols = 64;
+    j.Cout = L.Cout; j.C = L.Cin; j.kh = L.k; j.kw = L.k; j.s = L.s; j.T = q.T; j.P = q.P; j.N = q.N; j.ci_major = q.ci_major;
+    pj.push_back(j);
+    if (l >= 1) {
+      const int Pout = q.N / 64, Nd = q.P * 64;
+      if (dev_alloc(c, &q.dwpack, (size_t)q.ntaps * Pout * Nd * 64)) return 1;
+      PackJob d = j;
+      d.dst = q.dwpack; d.kind = PK_PCONV_DGRAD; d.rows = q.ntaps * Pout * Nd; d.P = Pout; d.N = Nd;
+      pj.push_back(d);
+    }
+  }
+  return 0;
+}
+
+template <int N>
+int launch_pconv(arl_ctx* c, const PcParams& p, cudaStream_t st) {
+  const int smem = pc_fwd_smem(N, p.ntaps, p.planes, p.load_rows, p.stages);
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    ARL_CHECK(c, cudaFuncSetAttribute(pconv_fwd_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
+  }
+  int ctas = std::min(p.ntiles, 148);
+  pconv_fwd_kernel<N><<<ctas, kPcThreads, smem, st>>>(p);
+  c->launches++;
+  ARL_CHECK(c, cudaGetLastError());
+  return 0;
+}
+
+int launch_pconv_n(arl_ctx* c, int N, const PcParams& p, cudaStream_t st) {
+  switch (N) {
+    case 32: return launch_pconv<32>(c, p, st);
+    case 64: return launch_pconv<64>(c, p, st);
+    case 128: return launch_pconv<128>(c, p, st);
+  }
+  ARL_FAIL(c, "unsupported pconv tile width N=" + std::to_string(N));
+}
+
+// how layer l's OUTPUT pixels are stored: into layer l+1's input grid, or dense NHWC rows for the FC layer
+void pc_out_forward(arl_ctx* c, int l, PcOut& o) {
+  const ConvLayer& L = c->conv[l];
+  o.mode = 0; o.scale = (l == 0) ? 1.f / c->cfg.pixel_scale : 1.f;
+  o.bias = c->params + L.off_b;
+  if (l + 1 < (int)c->pc.size()) {
+    const PcLayer& nx = c->pc[l + 1];
+    o.dst = nx.in; o.dst_plane_stride = nx.in_rows * 64;
+    o.dS = nx.S; o.dWp = nx.Wp; o.dHc = nx.Hc + 1; o.dpad = nx.pad; o.ds = nx.s; o.swz = 1;
+  } else {
+    o.dst = L.act; o.swz = 0; o.dense_ld = L.Cout;
+    o.dS = L.Ho * L.Wo; o.dWp = L.Wo; o.dHc = L.Ho; o.dpad = 0; o.ds = 1;
+  }
+}
+
+// conv layer l forward on the patch-resident path
+int pconv_forward_layer(arl_ctx* c, int l, const __nv_bfloat16* obs16, const int* idx, const int* idx_off, int n,
+                        cudaStream_t st) {
+  const PcLayer& q = c->pc[l];
+  const ConvLayer& L = c->conv[l];
+  PcParams p{};
+  if (l == 0) {
+    p.src = obs16; p.src_plane_stride = 0; p.idx = idx; p.idx_off = idx_off; p.nb = n;
+    p.tiles_per_img = q.tiles_per_img; p.ntiles = n * q.tiles_per_img;
+  } else {
+    p.src = q.in; p.src_plane_stride = q.in_rows * 64;
+    p.tiles_per_img = 0; p.ntiles = (int)(((long)n * q.S + 127) / 128);
+  }
+  p.planes = q.P; p.S = q.S; p.Wp = q.Wp; p.Ho = L.Ho; p.Wo = L.Wo; p.n_img = n;
+  p.ntaps = q.ntaps;
+  for (int t = 0; t < q.ntaps; ++t) p.shift[t] = q.shift[t];
+  p.load_rows = q.load_rows; p.w = q.wpack; p.stages = q.stages_fwd;
+  pc_out_forward(c, l, p.out);
+  return launch_pconv_n(c, q.N, p, st);
+}
+
+
+template <int N>
+int launch_pconv_wgrad(arl_ctx* c, const PcWgradParams& p, int ctas, cudaStream_t st) {
+  const int smem = pc_wgrad_smem(N, p.planes, p.a_rows, p.dy_rows, p.stages);
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    ARL_CHECK(c, cudaFuncSetAttribute(pconv_wgrad_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
+  }
+  pconv_wgrad_kernel<N><<<ctas, kPcThreads, smem, st>>>(p);
+  c->launches++;
+  ARL_CHECK(c, cudaGetLastError());
+  return 0;
+}
+
+int pc_wgrad_ctas(arl_ctx* c, int l, int n) {
+  const PcLayer& q = c->pc[l];
+  int ntiles = (l == 0) ? n * q.tiles_per_img : (int)(((long)n * q.S + 127) / 128);
+  return std::min(ntiles, 148);
+}
+
+// weight (+ bias) gradient partials of conv layer l on the patch-resident path
+int pconv_wgrad_layer(arl_ctx* c, int l, const __nv_bfloat16* obs16, const int* idx, const int* idx_off, int n,
+                      cudaStream_t st) {
+  const PcLayer& q = c->pc[l];
+  PcWgradParams p{};
+  if (l == 0) {
+    p.a = obs16; p.a_plane_stride = 0; p.idx = idx; p.idx_off = idx_off; p.nb = n;
+    p.tiles_per_img = q.tiles_per_img; p.ntiles = n * q.tiles_per_img; p.dy_off = 0;
+  } else {
+    p.a = q.in; p.a_plane_stride = q.in_rows * 64;
+    p.tiles_per_img = 0; p.ntiles = (int)(((long)n * q.S + 127) / 128);
+    p.dy_off = q.dYpad * q.Wp + q.dYpad;
+  }
+  p.S = q.S; p.planes = q.P; p.nblk = q.ntaps * q.P;
+  p.a_rows = q.load_rows + 8;
+  for (int t = 0; t < q.ntaps; ++t)
+    for (int pl = 0; pl < q.P; ++pl) p.blk_off[t * q.P + pl] = (pl * p.a_rows + q.shift[t]) * 128;
+  p.dy = q.dY; p.dy_rows = 128 + 8;
+  p.partial = c->wgrad_partial[l]; p.bias_partial = c->bias_partial[l];
+  for (p.stages = 4; p.stages >= 2; --p.stages)
+    if (pc_wgrad_smem(q.N, q.P, p.a_rows, p.dy_rows, p.stages) <= 227 * 1024) break;
+  if (p.stages < 2) ARL_FAIL(c, "pconv wgrad: stage does not fit shared memory");
+  int ctas = pc_wgrad_ctas(c, l, n);
+  if (q.N == 32) return launch_pconv_wgrad<32>(c, p, ctas, st);
+  if (q.N == 64) return launch_pconv_wgrad<64>(c, p, ctas, st);
+  ARL_FAIL(c, "pconv wgrad: unsupported filter count");
+}
+
+// data gradient of conv layer l (>= 1): dY_l -> gradient w.r.t. layer l-1's output, masked by that output's ReLU
+int pconv_dgrad_layer(arl_ctx* c, int l, int n, cudaStream_t st) {
+  const PcLayer& q = c->pc[l];
+  const PcLayer& lo = c->pc[l - 1];
+  const ConvLayer& L = c->conv[l];
+  PcParams p{};
+  const int Pout = q.N / 64;
+  p.src = q.dY; p.src_plane_stride = q.dY_rows * 64; p.planes = Pout;
+  p.S = q.S; p.Wp = q.Wp; p.n_img = n; p.tiles_per_img = 0;
+  p.ntiles = (int)(((long)n * q.S + 127) / 128);
+  p.ntaps = q.ntaps;
+  for (int t = 0; t < q.ntaps; ++t) p.shift[t] = q.shift[t];
+  p.load_rows = q.load_rows; p.w = q.dwpack; p.stages = q.stages_dgrad;
+  PcOut& o = p.out;
+  o.scale = 1.f; o.act = q.in; o.act_plane_stride = q.in_rows * 64;
+  o.dst = lo.dY;
+  if (L.s == 1) {
+    // rows = input pixels (i, j) at position i*Wp + j; their forward value sits pad rows/columns further
+    p.Ho = L.Hin; p.Wo = L.Win;
+    o.mode = 1; o.act_off = L.p * q.Wp + L.p;
+    o.dst_plane_stride = lo.dY_rows * 64;
+    o.dS = lo.S; o.dWp = lo.Wp; o.dHc = lo.Hc + 1; o.dpad = lo.dYpad; o.ds = 1; o.swz = 1;
+  } else {
+    // rows = space-to-depth cells: every cell is an output; unfold the sub-pixels into the pixel grid below
+    p.Ho = q.Hc; p.Wo = q.Wp;
+    o.mode = 2; o.act_off = 0;
+    o.uH = L.Hin; o.uW = L.Win; o.uWp = lo.Wp; o.uS = lo.S; o.us = L.s; o.upad = L.p; o.uC = lo.N;
+    o.dS = 1; o.dWp = 1; o.dHc = 1; o.ds = 1;
+  }
+  return launch_pconv_n(c, q.P * 64, p, st);
+}
+
+// gradient grids must be zero outside the rows the current batch writes
+int pconv_prepare_dy(arl_ctx* c, int n, cudaStream_t st) {
+  if (n >= c->pc_dy_n) { c->pc_dy_n = n; return 0; }
+  for (size_t l = 0; l < c->pc.size(); ++l) {
+    PcLayer& q = c->pc[l];
+    size_t elems = (l == 0) ? (size_t)q.dY_rows * q.N : (size_t)(q.N / 64) * q.dY_rows * 64;
+    ARL_CHECK(c, cudaMemsetAsync(q.dY, 0, elems * sizeof(__nv_bfloat16), st));
+  }
+  c->pc_dy_n = n;
+  return 0;
+}
+
 int fc_splits(arl_ctx* c, int n, int& kbps) {
   int kb = c->Kfc / 64;
   int tiles = ((n + 127) / 128) * (c->H / 64);
@@ -371,7 +639,7 @@ int alloc_net(arl_ctx* c) {
       q.s = L.s; q.ry = d.ry; q.rx = d.rx; q.Tx = d.Tx;
       pj.push_back(q);
     }
-    long cap = (long)kMaxSplits * L.K * L.Cout;
+    long cap = (long)kMaxSplits * std::max(L.K, c->pc.empty() ? 0 : c->pc[l].ntaps * c->pc[l].P * 64) * L.Cout;
     float* wp = nullptr;
     if (dev_alloc(c, &wp, (size_t)cap)) return 1;
     c->wgrad_partial.push_back(wp);
@@ -386,10 +654,17 @@ int alloc_net(arl_ctx* c) {
     j.dst = c->wfc_bf16; j.src_off = c->off_Wfc; j.kind = PK_CAST; j.rows = c->Kfc; j.cols = c->H;
     pj.push_back(j);
   }
+  // the FC cast job stays LAST (pack_weights(with_fc=false) drops it); pconv packs go before it
+  {
+    PackJob fc = pj.back();
+    pj.pop_back();
+    if (alloc_pconv(c, pj)) return 1;
+    pj.push_back(fc);
+  }
   c->n_pack_jobs = (int)pj.size();
   if (dev_alloc(c, &c->pack_jobs_dev, pj.size())) return 1;
   ARL_CHECK(c, cudaMemcpy(c->pack_jobs_dev, pj.data(), pj.size() * sizeof(PackJob), cudaMemcpyHostToDevice));
-  if (dev_alloc(c, &c->obs16_stage, (size_t)R * c->obs16_elems)) return 1;
+  if (dev_alloc(c, &c->obs16_stage, (size_t)R * c->obs16_elems + 64 * 1024)) return 1;
   {
     long worst = R;
     for (int n = 1; n <= R; ++n) {
@@ -442,11 +717,11 @@ static const char* kWgradName[4] = {"conv0_wgrad", "conv1_wgrad", "conv2_wgrad",
 static const char* kDgradName[4] = {"conv0_dgrad", "conv1_dgrad", "conv2_dgrad", "conv3_dgrad"};
 
 // uint8 CHW observations -> bf16 space-to-depth staging rows [0, n)
-int convert_obs(arl_ctx* c, const uint8_t* obs, const int* idx, int n, cudaStream_t st) {
+int convert_obs(arl_ctx* c, const uint8_t* obs, const int* idx, int n, bool swz, cudaStream_t st) {
   const ConvLayer& L0 = c->conv[0];
   long work = (long)n * L0.Cin * L0.Hin * (L0.Win / 4);
   int blocks = (int)std::min<long>((work + 255) / 256, 148 * 16);
-  obs_to_s2d_kernel<<<blocks, 256, 0, st>>>(obs, idx, c->obs16_stage, n, L0.Cin, L0.Hin, L0.Win);
+  obs_to_s2d_kernel<<<blocks, 256, 0, st>>>(obs, idx, c->obs16_stage, n, L0.Cin, L0.Hin, L0.Win, swz ? 1 : 0);
   c->launches++;
   prof_mark(c, "obs_to_s2d", st);
   ARL_CHECK(c, cudaGetLastError());
@@ -456,10 +731,16 @@ int convert_obs(arl_ctx* c, const uint8_t* obs, const int* idx, int n, cudaStrea
 // conv stack + FC split-K partials for n observations given as bf16 space-to-depth images
 // (idx/idx_off: optional image gather applied by the first layer's loader)
 int forward_trunk(arl_ctx* c, const __nv_bfloat16* obs16, const int* idx, const int* idx_off, int n, int* fc_S,
-                  cudaStream_t st) {
+                  bool pc, cudaStream_t st) {
   if (n > c->cfg.max_rows) ARL_FAIL(c, "batch larger than max_rows");
   if (!c->params) ARL_FAIL(c, "parameters not bound");
   for (size_t l = 0; l < c->conv.size(); ++l) {
+    if (pc) {
+      // patch-resident tiles: obs16 and every intermediate activation are chunk-swizzled position grids
+      if (pconv_forward_layer(c, (int)l, obs16, idx, idx_off, n, st)) return 1;
+      prof_mark(c, kFwdName[l], st);
+      continue;
+    }
     ConvLayer& L = c->conv[l];
     int rows = n * L.Ho * L.Wo;
     RowEpi e = make_epi(EPI_BIAS_RELU_BF16);
@@ -501,9 +782,9 @@ HeadParams head_base(arl_ctx* c, int n, int S) {
 }
 
 int policy_forward16(arl_ctx* c, const __nv_bfloat16* obs16, int n, const int* out_rows, float* prob, float* value,
-                     const double* uniforms, uint8_t* actions, cudaStream_t st) {
+                     const double* uniforms, uint8_t* actions, bool pc, cudaStream_t st) {
   int S = 0;
-  if (forward_trunk(c, obs16, nullptr, nullptr, n, &S, st)) return 1;
+  if (forward_trunk(c, obs16, nullptr, nullptr, n, &S, pc, st)) return 1;
   HeadParams p = head_base(c, n, S);
   p.out_rows = out_rows; p.prob = prob; p.value = value; p.uniforms = uniforms; p.actions = uniforms ? actions : nullptr;
   head_kernel<0><<<n, kHeadThreads, 0, st>>>(p);
@@ -516,8 +797,8 @@ int policy_forward16(arl_ctx* c, const __nv_bfloat16* obs16, int n, const int* o
 int policy_forward(arl_ctx* c, const uint8_t* obs, const int* idx, int n, const int* out_rows, float* prob,
                    float* value, const double* uniforms, uint8_t* actions, cudaStream_t st) {
   if (n > c->cfg.max_rows) ARL_FAIL(c, "batch larger than max_rows");
-  if (convert_obs(c, obs, idx, n, st)) return 1;
-  return policy_forward16(c, c->obs16_stage, n, out_rows, prob, value, uniforms, actions, st);
+  if (convert_obs(c, obs, idx, n, c->pc_mode >= 1, st)) return 1;
+  return policy_forward16(c, c->obs16_stage, n, out_rows, prob, value, uniforms, actions, c->pc_mode >= 1, st);
 }
 
 // ---------------------------------------------------------------------------
@@ -541,6 +822,13 @@ int get_plan(arl_ctx* c, int n, TrainPlan** out) {
     w.src = c->wgrad_partial[l]; w.S = splits; w.sstride = (long)L.K * L.Cout; w.rows = L.K; w.cols = L.Cout;
     w.ld = L.Cout; w.map = (l == 0) ? GM_CONV_S2D : GM_CONV_NHWC; w.scale = (l == 0) ? 1.f / c->cfg.pixel_scale : 1.f;
     w.dst_off = L.off_W; w.C = L.Cin; w.kh = L.k; w.kw = L.k; w.s2d = L.s;
+    if (c->pc_mode >= 2) {
+      // patch-resident wgrad: one partial per persistent CTA, K' rows in (tap, plane, channel) order
+      const PcLayer& q = c->pc[l];
+      splits = pc_wgrad_ctas(c, (int)l, n);
+      w.S = splits; w.rows = q.ntaps * q.P * 64; w.sstride = (long)w.rows * L.Cout; w.map = GM_PCONV;
+      w.T = q.T; w.P = q.P; w.ci_major = q.ci_major;
+    }
     jobs.push_back(w);
     max_total = std::max(max_total, (long)w.rows * w.cols);
     GradJob b{};
@@ -589,11 +877,13 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
     obs16 = c->roll_obs16; gidx = idx; gidx_off = idx_off;
   } else {
     if (idx_off) ARL_FAIL(c, "graph-replayed training needs the sampler's rollout buffers as training inputs");
-    if (convert_obs(c, c->t_obs, idx, n, st)) return 1;
+    if (convert_obs(c, c->t_obs, idx, n, c->pc_mode >= 2, st)) return 1;
     obs16 = c->obs16_stage; gidx = nullptr; gidx_off = nullptr;
   }
+  const bool pcb = c->pc_mode >= 2;
+  if (pcb && pconv_prepare_dy(c, n, st)) return 1;
   int S = 0;
-  if (forward_trunk(c, obs16, gidx, gidx_off, n, &S, st)) return 1;
+  if (forward_trunk(c, obs16, gidx, gidx_off, n, &S, pcb, st)) return 1;
   // ---- head: losses + dlogits + dh ----
   if (c->t_valids) {
     count_valids_idx_kernel<<<1, 1024, 0, st>>>(c->t_valids, idx, idx_off, n, c->valid_count);
@@ -639,12 +929,24 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
     WeightSrc w{c->wfc_bf16, (long)c->H, 0, RowPerm{c->Clast, c->HWlast}};   // K-major rows n in (hw,c) order
     RowEpi e = make_epi(EPI_MASK_BF16);
     e.out = LL.dact; e.act = LL.act; e.ldo = c->Kfc; e.M = n;
+    if (pcb) {
+      // scatter straight into the last conv layer's gradient grid (padded, chunk-swizzled): what its dgrad / wgrad read
+      const PcLayer& q = c->pc.back();
+      e.out = q.dY; e.sc_on = 1; e.sc_Wo = LL.Wo; e.sc_S = q.S; e.sc_Wp = q.Wp; e.sc_pad = q.dYpad;
+    }
     int BN = (c->Kfc % 128 == 0) ? 128 : 64;
     if (launch_rowgemm_bn<DenseLoader<128>, false>(c, BN, a, w, e, n, c->Kfc, c->H / 64, c->H / 64, 1, st)) return 1;
     prof_mark(c, "fc_dgrad", st);
   }
   // ---- conv layers, last to first ----
-  for (int l = (int)c->conv.size() - 1; l >= 0; --l) {
+  for (int l = (int)c->conv.size() - 1; l >= 0 && pcb; --l) {
+    if (pconv_wgrad_layer(c, l, obs16, gidx, gidx_off, n, st)) return 1;
+    prof_mark(c, kWgradName[l], st);
+    if (l == 0) break;
+    if (pconv_dgrad_layer(c, l, n, st)) return 1;
+    prof_mark(c, kDgradName[l], st);
+  }
+  for (int l = (int)c->conv.size() - 1; l >= 0 && !pcb; --l) {
     ConvLayer& L = c->conv[l];
     int rows = n * L.Ho * L.Wo;
     // weight-gradient partials (+ bias-gradient partials from the same pass over dY)
@@ -748,7 +1050,7 @@ int launch_frame(arl_ctx* c, const uint8_t* staging, int s_next, bool to_rollout
   int blocks = (int)((items + 255) / 256);
   frame_kernel<<<blocks, 256, 0, st>>>(s.frame_pool, staging, c->cmd, s.step_obs, to_rollout ? s.observations : nullptr,
                                        c->step_obs16, to_rollout ? c->roll_obs16 : nullptr, s.horizon, s_next, s.n_envs,
-                                       s.planes);
+                                       s.planes, c->pc_mode >= 2, c->pc_mode >= 2);
   c->launches++;
   prof_mark(c, "frame", st);
   ARL_CHECK(c, cudaGetLastError());
@@ -777,7 +1079,7 @@ int rollout_step(arl_ctx* c, int s_idx, const uint8_t* staging, cudaStream_t st)
   const arl_sampler_cfg& s = c->sc;
   const int B = s.n_envs, T = s.horizon;
   if (policy_forward16(c, c->step_obs16, B, c->rows_tab + (long)s_idx * B, s.prob, s.value,
-                       s.uniforms + (long)s_idx * B, s.actions, st))
+                       s.uniforms + (long)s_idx * B, s.actions, c->pc_mode >= 2, st))
     return 1;
   env_step_kernel<<<(B + 127) / 128, 128, 0, st>>>(synth_cfg(s), c->est, c->tout, c->cmd, s.rewards, s.dones,
                                                    s.raw_reward, s.need_reset, B, T, s_idx, s.max_path_length,
@@ -829,11 +1131,15 @@ int arl_create(const arl_net_cfg* cfg, arl_ctx** out) {
   }
   arl_ctx* c = new arl_ctx();
   c->cfg = *cfg;
-  if (plan_net(c) || alloc_net(c)) {
+  if (plan_net(c) || plan_pconv(c) || alloc_net(c)) {
     g_create_error = c->err;
     delete c;
     return 4;
   }
+  // conv path: the patch-resident tiles whenever the geometry allows; ARL_PCONV=0/1 forces the gather path for
+  // everything / for training only (A/B measurements)
+  c->pc_mode = c->pc.empty() ? 0 : 2;
+  if (const char* e = getenv("ARL_PCONV")) c->pc_mode = c->pc.empty() ? 0 : std::max(0, std::min(2, atoi(e)));
   *out = c;
   return 0;
 }
@@ -944,8 +1250,8 @@ int arl_sampler_configure(arl_ctx* c, const arl_sampler_cfg* cfg) {
     for (int e = 0; e < B; ++e) rt[(size_t)s * B + e] = e * T + s;
   ARL_CHECK(c, cudaMemcpy(c->rows_tab, rt.data(), rt.size() * sizeof(int), cudaMemcpyHostToDevice));
   // bf16 space-to-depth mirrors of the step buffer and of the rollout observations (what conv layer 0 reads)
-  if (dev_alloc(c, &c->step_obs16, (size_t)B * c->obs16_elems)) return 1;
-  if (dev_alloc(c, &c->roll_obs16, (size_t)B * T * c->obs16_elems)) return 1;
+  if (dev_alloc(c, &c->step_obs16, (size_t)B * c->obs16_elems + 64 * 1024)) return 1;
+  if (dev_alloc(c, &c->roll_obs16, (size_t)B * T * c->obs16_elems + 64 * 1024)) return 1;
   c->sampler_set = true;
   if (c->rollout_graph) { cudaGraphExecDestroy(c->rollout_graph); c->rollout_graph = nullptr; }
   return 0;
@@ -1232,8 +1538,12 @@ int arl_profile_graph(arl_ctx* c, int kind, const int* idx, int mb_size, int rep
   if (kind == 0) {
     rc = grad_minibatch(c, idx, c->mb_counter, mb_size, cap_s);
     if (!rc) rc = clip_update(c, 1.f, cap_s);
-  } else {
+  } else if (kind == 1) {
     rc = rollout_step(c, 0, nullptr, cap_s);
+  } else {
+    // kind 2: inference forward of the first mb_size rows of the staging buffer (filled by the last uint8 forward)
+    rc = policy_forward16(c, c->obs16_stage, mb_size, nullptr, c->dlogit, c->dlogit + (long)mb_size * c->A, nullptr, nullptr,
+                          c->pc_mode >= 1, cap_s);
   }
   cudaError_t ce = cudaStreamEndCapture(cap_s, &g);
   c->prof_collect = false;
@@ -1260,14 +1570,28 @@ int arl_profile_graph(arl_ctx* c, int kind, const int* idx, int mb_size, int rep
     if (ty == cudaGraphNodeTypeKernel) {
       cudaKernelNodeParams kp{};
       ARL_CHECK(c, cudaGraphKernelNodeGetParams(node, &kp));
+      // `reps` chained copies of this kernel node in a scratch graph: device-side launch latency only (what the
+      // product path pays inside its captured graphs), no host launch-rate floor
+      cudaGraph_t tg = nullptr;
+      ARL_CHECK(c, cudaGraphCreate(&tg, 0));
+      cudaGraphNode_t prev = nullptr;
+      for (int r = 0; r < reps; ++r) {
+        cudaGraphNode_t nd = nullptr;
+        ARL_CHECK(c, cudaGraphAddKernelNode(&nd, tg, prev ? &prev : nullptr, prev ? 1 : 0, &kp));
+        prev = nd;
+      }
+      cudaGraphExec_t te = nullptr;
+      ARL_CHECK(c, cudaGraphInstantiate(&te, tg, 0));
+      ARL_CHECK(c, cudaGraphLaunch(te, st));
       ARL_CHECK(c, cudaEventRecord(e0, st));
-      for (int r = 0; r < reps; ++r)
-        ARL_CHECK(c, cudaLaunchKernel(kp.func, kp.gridDim, kp.blockDim, kp.kernelParams, kp.sharedMemBytes, st));
+      ARL_CHECK(c, cudaGraphLaunch(te, st));
       ARL_CHECK(c, cudaEventRecord(e1, st));
       ARL_CHECK(c, cudaStreamSynchronize(st));
       float t = 0.f;
       ARL_CHECK(c, cudaEventElapsedTime(&t, e0, e1));
       ms[cnt++] = t / reps;
+      cudaGraphExecDestroy(te);
+      cudaGraphDestroy(tg);
       all += (li < c->prof_labels.size()) ? c->prof_labels[li] : std::string("kernel");
       all += ';';
       ++li;

@@ -121,6 +121,21 @@ ARL_DEVINL void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint3
       : "memory");
 }
 
+// --- warp-converged single-lane issue ----------------------------------------------------------------------
+// tcgen05.mma / tcgen05.commit / cp.async.bulk take their operands from UNIFORM registers.  Issued from inside a
+// divergent `if (lane == 0)` region, ptxas cannot prove the operands uniform and wraps every instruction in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall (~20 SASS instructions per MMA, measured: 3 400 cycles per 16-MMA
+// tile).  Keep the role warp CONVERGED, compute operands from warp-uniform values, and issue inside
+// `if (elect_one()) { ... }`: ptxas recognises the elect.sync idiom and emits straight UTCHMMA / UBLKCP sequences
+// fed by the uniform datapath.
+ARL_DEVINL uint32_t elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(p));
+  return p;
+}
+// a value every lane holds -> a value ptxas KNOWS is warp-uniform (REDUX writes a uniform register)
+ARL_DEVINL uint32_t make_uniform(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }
+
 // mbarrier arrives when all previously issued MMAs of this thread have completed
 ARL_DEVINL void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");

@@ -210,6 +210,10 @@ struct RowEpi {
   // destination-row map: identity when map_s == 0, else rows enumerate (b,qy,qx) of a
   // stride-parity class and land at (b, map_s*qy + map_y0, map_s*qx + map_x0) of an H x W grid
   int map_s, map_y0, map_x0, map_Qh, map_Qw, map_H, map_W;
+  // EPI_MASK_BF16 scatter (FC data gradient -> the last conv layer's gradient grid of pconv.cuh): GEMM row = image,
+  // column n = (i*sc_Wo + j)*64 + c  ->  position row*sc_S + (i+sc_pad)*sc_Wp + (j+sc_pad), 128-byte rows whose
+  // 16-byte chunks are XOR-swizzled by (position & 7).  The mask is still read from the dense `act`.
+  int sc_on, sc_Wo, sc_S, sc_Wp, sc_pad;
 };
 
 ARL_DEVINL long epi_dest_row(const RowEpi& e, int row) {
@@ -258,6 +262,18 @@ ARL_DEVINL void epi_store32(const RowEpi& e, int row, int n0, const uint32_t (&r
       if (relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
       packed[i] = pack_bf16x2(lo, hi);
     }
+  }
+  if (e.sc_on) {
+    const int hw = n0 >> 6, c0 = (n0 & 63) >> 3;
+    const int i = hw / e.sc_Wo, j = hw - i * e.sc_Wo;
+    const long pos = (long)row * e.sc_S + (i + e.sc_pad) * e.sc_Wp + (j + e.sc_pad);
+    __nv_bfloat16* prow = e.out + pos * 64;
+    const int x7 = (int)(pos & 7);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<uint4*>(prow + ((c0 + q) ^ x7) * 8) =
+          make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+    return;
   }
   uint4* dst = reinterpret_cast<uint4*>(e.out + drow * e.ldo + n0);
 #pragma unroll

@@ -219,8 +219,11 @@ ARL_DEVINL uint2 u8x4_to_bf16x4(uint32_t w) {
 // uint8 CHW observations (the reference's buffer layout) -> bf16 space-to-depth(s) NHWC:
 //   dst[i][y/s][x/s][c*s*s + (y%s)*s + (x%s)] = src[idx ? idx[i] : i][c][y][x]       (s == 4)
 // One thread converts 4 horizontally adjacent pixels (one aligned 32-bit load, one 8-byte store).
+// swz != 0 (C*16 == 64 only): each position's eight 16-byte chunks are XOR-swizzled by (position & 7) — the layout the
+// patch-resident conv tiles bulk-copy straight into SWIZZLE_128B shared memory (pconv.cuh)
 __global__ void __launch_bounds__(256) obs_to_s2d_kernel(const uint8_t* __restrict__ src, const int* __restrict__ idx,
-                                                         __nv_bfloat16* __restrict__ dst, int n, int C, int H, int W) {
+                                                         __nv_bfloat16* __restrict__ dst, int n, int C, int H, int W,
+                                                         int swz) {
   const int Wb = W >> 2, Hb = H >> 2;
   const long total = (long)n * C * H * Wb;
   for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
@@ -231,7 +234,8 @@ __global__ void __launch_bounds__(256) obs_to_s2d_kernel(const uint8_t* __restri
     long i = r / C;
     long img = idx ? idx[i] : i;
     uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(src + ((img * C + c) * H + y) * (long)W) + bx);
-    long off = ((i * Hb + (y >> 2)) * Wb + bx) * (long)(C * 16) + c * 16 + (y & 3) * 4;
+    const int pos = (y >> 2) * Wb + bx, ch = c * 16 + (y & 3) * 4;
+    long off = (i * Hb * Wb + pos) * (long)(C * 16) + (swz ? ((((ch >> 3) ^ (pos & 7)) << 3) | (ch & 7)) : ch);
     *reinterpret_cast<uint2*>(dst + off) = u8x4_to_bf16x4(w);
   }
 }
@@ -272,7 +276,7 @@ __global__ void __launch_bounds__(256) frame_kernel(const uint8_t* __restrict__ 
                                                     const FrameCmd* __restrict__ cmd, uint8_t* __restrict__ step_obs,
                                                     uint8_t* __restrict__ roll_obs, __nv_bfloat16* __restrict__ step_obs16,
                                                     __nv_bfloat16* __restrict__ roll_obs16, int T, int s_next, int n_envs,
-                                                    int planes) {
+                                                    int planes, int swz_step, int swz_roll) {
   // step_obs16 / roll_obs16: bf16 space-to-depth(4) mirrors of the same stacks, [26][20][planes*16] per
   // observation, channel = plane*16 + (y%4)*4 + (x%4) — the layout the first conv layer's tcgen05 tiles read
   // (u8 -> bf16 is exact).  They are written from the registers that already hold the u8 stack.
@@ -330,10 +334,12 @@ __global__ void __launch_bounds__(256) frame_kernel(const uint8_t* __restrict__ 
       const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
-        const long off = ((long)(by * (kObsW / 4) + xc * 4 + b)) * Cs + p * 16 + dy * 4;
+        const int pos = by * (kObsW / 4) + xc * 4 + b, ch = p * 16 + dy * 4;
+        const long off = (long)pos * Cs + ch;
+        const long offs = (long)pos * Cs + ((((ch >> 3) ^ (pos & 7)) << 3) | (ch & 7));   // chunk-swizzled (Cs == 64)
         const uint2 o = u8x4_to_bf16x4(w[b]);
-        *reinterpret_cast<uint2*>(c16 + off) = o;
-        if (d16) *reinterpret_cast<uint2*>(d16 + off) = o;
+        *reinterpret_cast<uint2*>(c16 + (swz_step ? offs : off)) = o;
+        if (d16) *reinterpret_cast<uint2*>(d16 + (swz_roll ? offs : off)) = o;
       }
     }
   }
@@ -660,7 +666,7 @@ __global__ void __launch_bounds__(128) head_wgrad_kernel(const __nv_bfloat16* __
 // reference's parameter order (rllab/core/parameterized.py:74-88; Lasagne W (out,in,kh,kw),
 // flip_filters=True so correlation tap (ky,kx) is W[..., kh-1-ky, kw-1-kx]).
 // ===========================================================================
-enum GradMap { GM_LINEAR = 0, GM_CONV_NHWC = 1, GM_CONV_S2D = 2, GM_HEAD = 3 };
+enum GradMap { GM_LINEAR = 0, GM_CONV_NHWC = 1, GM_CONV_S2D = 2, GM_HEAD = 3, GM_PCONV = 4 };
 
 struct GradJob {
   const float* src;   // [S][rows_pad][ld]
@@ -676,7 +682,23 @@ struct GradJob {
   // GM_HEAD: src [S][H][A+2]; writes w_pi (H,A) at dst_off, w_v (H) at dst_off2, fc bias (H) at dst_off3
   long dst_off2, dst_off3;
   int A;
+  // GM_PCONV (pconv.cuh): r = k' = ((ty*T + tx)*P + plane)*64 + ch, cell channel cc = plane*64 + ch decoded as
+  // (ci, py, px) [ci_major] or (py, px, ci); ky = ty*s2d + py, kx = tx*s2d + px
+  int T, P, ci_major;
 };
+
+// cell channel -> (ci, py, px) of a space-to-depth(s) cell over C input channels
+ARL_DEVINL void pc_decode_channel(int cc, int C, int s, int ci_major, int& ci, int& py, int& px) {
+  if (ci_major) {
+    ci = cc / (s * s);
+    int r = cc - ci * s * s;
+    py = r / s; px = r - py * s;
+  } else {
+    int sub = cc / C;
+    ci = cc - sub * C;
+    py = sub / s; px = sub - py * s;
+  }
+}
 
 __global__ void __launch_bounds__(256) finalize_grads_kernel(const GradJob* __restrict__ jobs, float* __restrict__ grad) {
   const GradJob jb = jobs[blockIdx.y];
@@ -713,6 +735,15 @@ __global__ void __launch_bounds__(256) finalize_grads_kernel(const GradJob* __re
       int ci = ch / s2, dy = (ch % s2) / jb.s2d, dx = ch % jb.s2d;
       int ky = ty * jb.s2d + dy, kx = tx * jb.s2d + dx;
       grad[jb.dst_off + (((long)c * jb.C + ci) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx)] = acc;
+    } else if (jb.map == GM_PCONV) {
+      int blk = r >> 6, ch = r & 63;
+      int t = blk / jb.P, plane = blk - t * jb.P;
+      int ty = t / jb.T, tx = t - ty * jb.T;
+      int ci, py, px;
+      pc_decode_channel(plane * 64 + ch, jb.C, jb.s2d, jb.ci_major, ci, py, px);
+      int ky = ty * jb.s2d + py, kx = tx * jb.s2d + px;
+      if (ky < jb.kh && kx < jb.kw && ci < jb.C)
+        grad[jb.dst_off + (((long)c * jb.C + ci) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx)] = acc;
     } else {  // GM_HEAD: r = j, c in [0, A+2)
       if (c < jb.A) grad[jb.dst_off + (long)r * jb.A + c] = acc;
       else if (c == jb.A) grad[jb.dst_off2 + r] = acc;
@@ -874,7 +905,7 @@ __global__ void advance_counters_kernel(int* step, int* log_slot, int* mb_counte
 // ===========================================================================
 // Weight packing: fp32 master (reference layout) -> bf16 operand matrices for the GEMM tiles
 // ===========================================================================
-enum PackKind { PK_CONV_NHWC = 0, PK_CONV_S2D = 1, PK_CONV_DGRAD = 2, PK_CAST = 3 };
+enum PackKind { PK_CONV_NHWC = 0, PK_CONV_S2D = 1, PK_CONV_DGRAD = 2, PK_CAST = 3, PK_PCONV = 4, PK_PCONV_DGRAD = 5 };
 
 struct PackJob {
   __nv_bfloat16* dst;
@@ -885,6 +916,11 @@ struct PackJob {
   int s, ry, rx, Tx;   // dgrad class (k' = (ty*Tx+tx)*Cout + o ; ky = ry + s*ty ; kx = rx + s*tx)
   int HW;              // FC: k' = hw*C + c  <- W[(c*HW + hw)][j]
   int ldsrc;           // FC: hidden size
+  // PK_PCONV / PK_PCONV_DGRAD (pconv.cuh): dst = [blocks][N][64] with 16-byte chunks XOR-swizzled by (row & 7);
+  // forward: block = (ty*T + tx)*P + plane, row = cout, column ch -> cell channel plane*64 + ch;
+  // dgrad  : block = (ey*T + ex)*P + plane_out, row = input cell channel, column ch -> cout = plane_out*64 + ch,
+  //          tap (ty, tx) = (T-1-ey, T-1-ex)
+  int T, P, N, ci_major;
 };
 
 __global__ void __launch_bounds__(256) pack_weights_kernel(const PackJob* __restrict__ jobs,
@@ -915,6 +951,21 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const PackJob* __rest
       int ky = jb.ry + jb.s * ty, kx = jb.rx + jb.s * tx;
       if (ky < jb.kh && kx < jb.kw)
         v = W[(((long)o * jb.C + r) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx)];
+    } else if (jb.kind == PK_PCONV || jb.kind == PK_PCONV_DGRAD) {
+      // rows = blocks*N, cols = 64
+      int blk = r / jb.N, n_ = r - blk * jb.N;
+      int t = blk / jb.P, pl = blk - t * jb.P;
+      int ty = t / jb.T, tx = t - ty * jb.T;
+      int co, cc;
+      if (jb.kind == PK_PCONV) { co = n_; cc = pl * 64 + k; }
+      else { co = pl * 64 + k; cc = n_; ty = jb.T - 1 - ty; tx = jb.T - 1 - tx; }
+      int ci, py, px;
+      pc_decode_channel(cc, jb.C, jb.s, jb.ci_major, ci, py, px);
+      int ky = ty * jb.s + py, kx = tx * jb.s + px;
+      if (ky < jb.kh && kx < jb.kw && ci < jb.C && co < jb.Cout)
+        v = W[(((long)co * jb.C + ci) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx)];
+      jb.dst[(long)r * 64 + ((((k >> 3) ^ (n_ & 7)) << 3) | (k & 7))] = __float2bfloat16_rn(v);
+      continue;
     } else {                                 // PK_CAST: same layout, fp32 -> bf16 (FC weights, reference order)
       v = W[i];
     }

@@ -1,0 +1,588 @@
+// Patch-resident implicit-GEMM convolution tiles (sm_100a): the B200-native conv path.
+//
+// Every conv layer of the policy network is rewritten as a STRIDE-1 convolution with T x T taps over a
+// "position grid" whose pixels are rows of 64 bf16 channels (128 bytes), split into P planes:
+//   * a stride-s layer reads the space-to-depth(s) image of its (padded) input, so (k, s) becomes
+//     T = ceil(k/s) taps over C*s*s channels (8x8/4 over 4 planes -> 2x2 over 64 ch; 4x4/2 over 32 ch ->
+//     2x2 over 128 ch = 2 planes; 3x3/1 over 64 ch -> 3x3 over 64 ch);
+//   * positions are numbered q = image*S + y*Wp + x (pitch Wp includes the zero padding column(s), S the
+//     padding row), so tap (ty,tx) of output position q is input position q + ty*Wp + tx: a pure ROW SHIFT.
+// One tile = 128 consecutive output positions.  Its input patch (128 + halo rows per plane, ~19 KB) is fetched
+// ONCE by the TMA engine (cp.async.bulk, SASS UBLKCP) into a 128B-swizzled shared-memory ring; the im2col
+// matrix is never built anywhere: each tap's A operand is the same patch addressed through a tcgen05 shared
+// memory descriptor whose start address is advanced by `shift` rows.  L2->SM traffic drops from T*T x (im2col
+// gather) to ~1.15 x the activation size, which is what lets the tensor pipe instead of LTS bound the tile.
+// Global activations are stored PRE-SWIZZLED (16-byte chunk index XOR (position & 7)) so a plain 1-D bulk copy
+// lands in the canonical UMMA SWIZZLE_128B layout (tiles start at multiples of 8 positions).
+// Positions that are not real outputs (x >= Wo, y >= Ho: the padding columns/rows) are computed and dropped by
+// the epilogue — 7-17 % extra MMA work instead of 4-9 x extra load traffic.
+//
+//   pconv_fwd_kernel<N>   conv forward and conv data-gradient (same kernel, different weight pack / epilogue)
+//   pconv_wgrad_kernel<N> weight gradient: D[(tap,plane,ch)][co] = sum_q A[q+shift][ch] * dY[q][co], both operands
+//                         MN-major straight out of the same resident patches
+// Warp roles (persistent CTAs, one per SM): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc),
+// warps 2..9 = epilogue (two warps per TMEM lane quadrant, each owning half of the N columns).
+#pragma once
+#include "common.cuh"
+
+namespace arl {
+
+constexpr int kPcThreads = 320;
+constexpr int kPcMaxTaps = 16;
+
+struct PcOut {
+  int mode;                   // 0: acc*scale + bias, ReLU -> bf16   1: acc masked by act > 0 -> bf16   2: mask + unfold
+  float scale;
+  const float* bias;          // [N] (mode 0)
+  __nv_bfloat16* dst;
+  const __nv_bfloat16* act;   // mask source (modes 1, 2)
+  long dst_plane_stride;      // elements between 64-channel planes of dst
+  long act_plane_stride;
+  int dS, dWp, dHc, dpad, ds; // destination grid: positions per image, pitch, rows, padding added to (y, x), space-to-depth
+  int act_off;                // modes 1, 2: the mask is the forward INPUT of this layer, i.e. it lives in the source grid:
+                              // position = source position + act_off, channel = output column
+  int swz;                    // 1: planes of 128-byte rows, chunk-swizzled   0: dense rows of dense_ld elements
+  int dense_ld;
+  // mode 2 (data gradient of a stride-`us` layer -> gradient w.r.t. the PIXELS of the layer below, stored
+  // position-aligned for that layer's wgrad): cell (y, x) sub-pixel (py, px) -> pixel (us*y + py - upad, ...)
+  int uH, uW, uWp, uS, us, upad, uC;
+};
+
+struct PcParams {
+  const __nv_bfloat16* src;   // plane 0, position 0
+  long src_plane_stride;      // elements
+  int planes;
+  const int* idx;             // optional image gather (per-image tiling only): image b reads idx[off*nb + b]
+  const int* idx_off;
+  int nb;
+  int S, Wp, Ho, Wo;          // source positions per image, pitch; valid output extent
+  int tiles_per_img;          // > 0: tiles never cross images (layer 0, gatherable); 0: continuous over the batch
+  int n_img, ntiles;
+  int ntaps;
+  int shift[kPcMaxTaps];      // row shift of each tap
+  int load_rows;              // 128 + halo, multiple of 8
+  const __nv_bfloat16* w;     // [ntaps*planes][N][64] bf16, rows chunk-swizzled (pack_weights_kernel PK_PCONV*)
+  int stages;
+  PcOut out;
+};
+
+__host__ __device__ inline int pc_fwd_smem(int N, int ntaps, int planes, int load_rows, int stages) {
+  return ntaps * planes * N * 128 + stages * planes * load_rows * 128 + 1024 /*align*/ + 256 /*barriers*/ + N * 4;
+}
+
+// 32 accumulator columns of one output row -> destination (modes 0 / 1)
+ARL_DEVINL void pc_store32(const PcOut& o, const float* bias_s, int col0, const uint32_t (&r)[32], long dpos, int ch0,
+                           long apos) {
+  // ch0: channel (within the destination cell) of column col0; 32 consecutive channels never straddle a plane
+  const int plane = ch0 >> 6, chunk0 = (ch0 & 63) >> 3;
+  uint32_t packed[16];
+  if (o.mode != 0) {
+    // dReLU mask: forward activation at (source position apos, channel col0..col0+31) of the swizzled source grid
+    const __nv_bfloat16* arow = o.act + (col0 >> 6) * o.act_plane_stride + apos * 64;
+    const int a7 = (int)(apos & 7), ac0 = (col0 & 63) >> 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 m = __ldg(reinterpret_cast<const uint4*>(arow + ((ac0 + j) ^ a7) * 8));
+      uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float lo = bf16_lo(mw[k]) > 0.f ? __uint_as_float(r[8 * j + 2 * k]) : 0.f;
+        float hi = bf16_hi(mw[k]) > 0.f ? __uint_as_float(r[8 * j + 2 * k + 1]) : 0.f;
+        packed[4 * j + k] = pack_bf16x2(lo, hi);
+      }
+    }
+  }
+  if (o.mode == 0) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float lo = fmaxf(__uint_as_float(r[2 * i]) * o.scale + bias_s[col0 + 2 * i], 0.f);
+      float hi = fmaxf(__uint_as_float(r[2 * i + 1]) * o.scale + bias_s[col0 + 2 * i + 1], 0.f);
+      packed[i] = pack_bf16x2(lo, hi);
+    }
+  }
+  if (o.swz) {
+    __nv_bfloat16* drow = o.dst + plane * o.dst_plane_stride + dpos * 64;
+    const int x7 = (int)(dpos & 7);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ch = ((chunk0 + j) ^ x7) * 8;
+      *reinterpret_cast<uint4*>(drow + ch) = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+    }
+  } else {
+    __nv_bfloat16* drow = o.dst + dpos * o.dense_ld + ch0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      *reinterpret_cast<uint4*>(drow + j * 8) = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+    }
+  }
+}
+
+// 16-column variant (N == 32: each epilogue warp owns 16 columns); forward mode only
+ARL_DEVINL void pc_store16(const PcOut& o, const float* bias_s, int col0, const uint32_t (&r)[16], long dpos, int ch0) {
+  const int plane = ch0 >> 6, chunk0 = (ch0 & 63) >> 3;
+  uint32_t packed[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float lo = fmaxf(__uint_as_float(r[2 * i]) * o.scale + bias_s[col0 + 2 * i], 0.f);
+    float hi = fmaxf(__uint_as_float(r[2 * i + 1]) * o.scale + bias_s[col0 + 2 * i + 1], 0.f);
+    packed[i] = pack_bf16x2(lo, hi);
+  }
+  if (o.swz) {
+    __nv_bfloat16* drow = o.dst + plane * o.dst_plane_stride + dpos * 64;
+    const int x7 = (int)(dpos & 7);
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      *reinterpret_cast<uint4*>(drow + ((chunk0 + j) ^ x7) * 8) =
+          make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+  } else {
+    __nv_bfloat16* drow = o.dst + dpos * o.dense_ld + ch0;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      *reinterpret_cast<uint4*>(drow + j * 8) = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+  }
+}
+
+// mode 2: 32 columns = one sub-pixel block (py, px) of a space-to-depth cell -> that pixel's row in the
+// position-aligned gradient buffer of the layer below ([uS positions][uC channels], uC*2-byte rows, chunk-swizzled
+// like a SWIZZLE_64B / SWIZZLE_128B tile), masked by the forward activation read from the cell layout.
+ARL_DEVINL void pc_store32_unfold(const PcOut& o, const uint32_t (&r)[32], int b, int y, int x, long cpos, int sub) {
+  const int py = sub / o.us, px = sub - py * o.us;
+  const int yy = o.us * y + py - o.upad, xx = o.us * x + px - o.upad;
+  if ((unsigned)yy >= (unsigned)o.uH || (unsigned)xx >= (unsigned)o.uW) return;
+  const int ch0 = sub * o.uC;                        // channel of this block inside the cell (uC == 32)
+  const int plane = ch0 >> 6, chunk0 = (ch0 & 63) >> 3;
+  const __nv_bfloat16* arow = o.act + plane * o.act_plane_stride + cpos * 64;
+  const int x7 = (int)(cpos & 7);
+  const long upos = (long)b * o.uS + yy * o.uWp + xx;
+  __nv_bfloat16* drow = o.dst + upos * o.uC;
+  const int sw = (o.uC == 32) ? (int)((upos >> 1) & 3) : (int)(upos & 7);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 m = __ldg(reinterpret_cast<const uint4*>(arow + ((chunk0 + j) ^ x7) * 8));
+    uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+    uint32_t pk[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float lo = bf16_lo(mw[k]) > 0.f ? __uint_as_float(r[8 * j + 2 * k]) : 0.f;
+      float hi = bf16_hi(mw[k]) > 0.f ? __uint_as_float(r[8 * j + 2 * k + 1]) : 0.f;
+      pk[k] = pack_bf16x2(lo, hi);
+    }
+    *reinterpret_cast<uint4*>(drow + (j ^ sw) * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(kPcThreads, 1) pconv_fwd_kernel(const __grid_constant__ PcParams p) {
+  static_assert(N == 32 || N == 64 || N == 128, "tile width");
+  if ((int)blockIdx.x >= p.ntiles) return;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int nblk = p.ntaps * p.planes;
+  const uint32_t w_base = smem_base;                                  // nblk tiles of [N x 128 B]
+  const uint32_t stage_bytes = (uint32_t)p.planes * p.load_rows * 128;
+  const uint32_t a_base = w_base + nblk * (N * 128);
+  const uint32_t bar_base = a_base + p.stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (16 + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (18 + b); };
+  const uint32_t wfull_bar = bar_base + 8u * 20;
+  const uint32_t tmem_ptr_addr = bar_base + 8u * 21;
+  float* bias_s = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 8);
+    }
+    mbar_init(wfull_bar, 1);
+    fence_mbar_init();
+  }
+  if (p.out.mode == 0)
+    for (int i = tid; i < N; i += kPcThreads) bias_s[i] = p.out.bias[i];
+  if (warp == 1) tmem_alloc(tmem_ptr_addr, 2 * N);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+
+  if (warp == 0) {
+    // ===================== TMA producer (converged warp, one elected lane issues) =====================
+    if (elect_one()) {
+      mbar_arrive_expect_tx(wfull_bar, (uint32_t)nblk * N * 128);
+      // one bulk copy per (tap, plane) weight tile
+      for (int b = 0; b < nblk; ++b) bulk_g2s(w_base + b * (N * 128), p.w + (long)b * N * 64, N * 128, wfull_bar);
+    }
+    __syncwarp();
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int s = it % p.stages;
+      const uint32_t ph = (it / p.stages) & 1;
+      long pos0;
+      if (p.tiles_per_img > 0) {
+        int b = tile / p.tiles_per_img;
+        int j = tile - b * p.tiles_per_img;
+        long img = p.idx ? (long)p.idx[(p.idx_off ? (long)p.idx_off[0] * p.nb : 0) + b] : b;
+        pos0 = img * p.S + (long)j * 128;
+      } else {
+        pos0 = (long)tile * 128;
+      }
+      mbar_wait(empty_bar(s), ph ^ 1, 21);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(full_bar(s), stage_bytes);
+        const uint32_t dst = a_base + s * stage_bytes;
+        for (int pl = 0; pl < p.planes; ++pl)
+          bulk_g2s(dst + pl * p.load_rows * 128, p.src + pl * p.src_plane_stride + pos0 * 64, p.load_rows * 128, full_bar(s));
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (converged warp, one elected lane issues) =====================
+    const uint32_t tmem_u = make_uniform(tmem_base);
+    constexpr uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+    // descriptor high words are constant (SBO 1024, version 1, SWIZZLE_128B); only the 14-bit address field moves
+    const uint64_t desc0 = make_smem_desc(0, 16, 1024, 2);
+    const uint32_t desc_hi32 = (uint32_t)(desc0 >> 32), desc_lo_flags = (uint32_t)desc0;   // LBO field lives in the low word
+    auto mk = [&](uint32_t lo) { return ((uint64_t)desc_hi32 << 32) | (uint64_t)lo; };
+    mbar_wait(wfull_bar, 0, 22);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int s = it % p.stages;
+      const uint32_t ph = (it / p.stages) & 1;
+      const int acc = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(tempty_bar(acc), aph ^ 1, 23);
+      mbar_wait(full_bar(s), ph, 24);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_stage = a_base + s * stage_bytes;
+        const uint32_t d_tmem = tmem_u + acc * N;
+        uint32_t first = 0;
+        uint32_t b_lo = (w_base >> 4) | desc_lo_flags;        // shared memory addresses are < 2^18: no carry into the flags
+        for (int t = 0; t < p.ntaps; ++t) {
+          uint32_t a_lo = ((a_stage + p.shift[t] * 128) >> 4) | desc_lo_flags;
+          for (int pl = 0; pl < p.planes; ++pl) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_bf16(d_tmem, mk(a_lo + 2 * k), mk(b_lo + 2 * k), idesc, first);
+              first = 1;
+            }
+            a_lo += (uint32_t)p.load_rows * 8;     // next plane: load_rows * 128 bytes
+            b_lo += N * 8;                         // next weight tile: N * 128 bytes
+          }
+        }
+        umma_commit(empty_bar(s));
+        umma_commit(tfull_bar(acc));
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const PcOut& o = p.out;
+    const int q = warp & 3;                   // TMEM lane quadrant
+    const int h = (warp - 2) >> 2;            // column half
+    constexpr int HC = N / 2;                 // columns per warp
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      // decode this thread's output row while the MMAs run
+      const int row = q * 32 + lane;
+      int b, pl_;
+      if (p.tiles_per_img > 0) {
+        b = tile / p.tiles_per_img;
+        pl_ = (tile - b * p.tiles_per_img) * 128 + row;
+      } else {
+        long qq = (long)tile * 128 + row;
+        b = (int)(qq / p.S);
+        pl_ = (int)(qq - (long)b * p.S);
+      }
+      const int y = pl_ / p.Wp, x = pl_ - y * p.Wp;
+      const bool valid = b < p.n_img && y < p.Ho && x < p.Wo;
+      mbar_wait(tfull_bar(acc), aph, 25);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * N + h * HC;
+      if constexpr (HC == 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr, r);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (valid) {
+          const int Y = y + o.dpad, X = x + o.dpad;
+          const int cy = Y / o.ds, cx = X / o.ds;
+          const int sub = (Y - cy * o.ds) * o.ds + (X - cx * o.ds);
+          const long dpos = (long)b * o.dS + cy * o.dWp + cx;
+          if (cy < o.dHc && cx < o.dWp) pc_store16(o, bias_s, h * HC, r, dpos, sub * N + h * HC);
+        }
+      } else {
+        uint32_t r[HC / 32][32];
+#pragma unroll
+        for (int c = 0; c < HC / 32; ++c) tmem_ld32(taddr + c * 32, r[c]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (valid) {
+          if (o.mode == 2) {
+            const long cpos = (long)b * p.S + pl_;
+#pragma unroll
+            for (int c = 0; c < HC / 32; ++c) pc_store32_unfold(o, r[c], b, y, x, cpos, (h * HC + c * 32) / o.uC);
+          } else {
+            const int Y = y + o.dpad, X = x + o.dpad;
+            const int cy = Y / o.ds, cx = X / o.ds;
+            const int sub = (Y - cy * o.ds) * o.ds + (X - cx * o.ds);
+            const long dpos = (long)b * o.dS + cy * o.dWp + cx;
+            const long apos = (long)b * p.S + pl_ + o.act_off;
+            if (cy < o.dHc && cx < o.dWp) {
+#pragma unroll
+              for (int c = 0; c < HC / 32; ++c)
+                pc_store32(o, bias_s, h * HC + c * 32, r[c], dpos, sub * N + h * HC + c * 32, apos);
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * N);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// pconv_wgrad: D[(tap, plane, ch)][co] = sum over output positions q of A[q + shift(tap)][plane, ch] * dY[q][co]
+// Both operands are MN-major views of resident patches: A = the layer's forward input patch (the same bulk copy
+// as the forward tile), dY = 128 rows of the output-gradient grid (zero at padding positions, so the positions the
+// forward pass drops contribute nothing).  One MMA covers 128 K' rows = TWO 64-channel blocks: (tap, plane 0/1) for
+// two-plane layers, (tap 2m, tap 2m+1) for single-plane layers — the second block is the same patch seen through
+// a different row shift, expressed as the descriptor's MN-atom stride (LBO).  Each persistent CTA accumulates all
+// its tiles in TMEM (mt*N columns) and writes ONE fp32 partial [K'][N] at the end; finalize_grads_kernel sums the
+// CTAs in a fixed order.  Four otherwise idle warps add up dY's columns from shared memory = the bias gradient.
+// ---------------------------------------------------------------------------
+constexpr int kPcMaxBlk = 2 * kPcMaxTaps;
+
+struct PcWgradParams {
+  const __nv_bfloat16* a;      // forward input grid, plane 0 position 0
+  long a_plane_stride;
+  int planes;
+  const int* idx;              // per-image gather of A (layer 0)
+  const int* idx_off;
+  int nb;
+  int S;                       // positions per image (per-image tiling)
+  int tiles_per_img;           // > 0: per-image tiling; 0: continuous
+  int ntiles;
+  int nblk;                    // 64-channel K' blocks = ntaps * planes
+  int blk_off[kPcMaxBlk];      // byte offset of block b's first row inside the A stage: (plane*a_rows + shift)*128
+  int a_rows;                  // rows per plane in the A stage (128 + halo, multiple of 8)
+  const __nv_bfloat16* dy;     // output-gradient grid [positions][N] (chunk-swizzled rows of N*2 bytes)
+  int dy_off;                  // dY row of output position q is q + dy_off (padding offset of the gradient grid)
+  int dy_rows;                 // rows per dY stage: 128 + 8
+  float* partial;              // [gridDim.x][nblk*64][N]
+  float* bias_partial;         // [gridDim.x][N]
+  int stages;
+};
+
+__host__ __device__ inline int pc_wgrad_stage_bytes(int N, int planes, int a_rows, int dy_rows) {
+  return planes * a_rows * 128 + ((dy_rows * N * 2 + 1023) / 1024) * 1024;
+}
+__host__ __device__ inline int pc_wgrad_smem(int N, int planes, int a_rows, int dy_rows, int stages) {
+  return stages * pc_wgrad_stage_bytes(N, planes, a_rows, dy_rows) + 1024 + 256 + 128 * 8 * 4;
+}
+
+template <int N>
+__global__ void __launch_bounds__(kPcThreads, 1) pconv_wgrad_kernel(const __grid_constant__ PcWgradParams p) {
+  static_assert(N == 32 || N == 64, "gradient tile width");
+  constexpr int ROWB = N * 2;                                  // bytes per dY row (64: SWIZZLE_64B, 128: SWIZZLE_128B)
+  constexpr uint32_t B_LAYOUT = (ROWB == 128) ? 2u : 4u;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_bytes = (uint32_t)p.planes * p.a_rows * 128;
+  const uint32_t stage_bytes = (uint32_t)pc_wgrad_stage_bytes(N, p.planes, p.a_rows, p.dy_rows);
+  const uint32_t bar_base = smem_base + p.stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };
+  const uint32_t done_bar = bar_base + 8u * 16;
+  const uint32_t tmem_ptr_addr = bar_base + 8u * 17;
+  float* red = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));   // [128][8] column-sum scratch
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mt = (p.nblk + 1) >> 1;
+  const int acc_cols = mt * N;
+  const uint32_t tmem_cols = acc_cols <= 32 ? 32 : acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;
+  const int my_tiles = ((int)blockIdx.x < p.ntiles) ? (p.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1 + 4);        // MMA commit + the four column-sum warps
+    }
+    mbar_init(done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_addr, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+  const int dy_sub = p.dy_off & 7;           // row of the first wanted dY row inside the 8-aligned stage
+
+  float csum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int s = it % p.stages;
+      const uint32_t ph = (it / p.stages) & 1;
+      long apos, dpos;
+      if (p.tiles_per_img > 0) {
+        int b = tile / p.tiles_per_img;
+        int j = tile - b * p.tiles_per_img;
+        long img = p.idx ? (long)p.idx[(p.idx_off ? (long)p.idx_off[0] * p.nb : 0) + b] : b;
+        apos = img * p.S + (long)j * 128;
+        dpos = (long)b * p.S + (long)j * 128;
+      } else {
+        apos = (long)tile * 128;
+        dpos = apos;
+      }
+      dpos += (p.dy_off & ~7);
+      mbar_wait(empty_bar(s), ph ^ 1, 31);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(full_bar(s), a_bytes + (uint32_t)p.dy_rows * ROWB);
+        const uint32_t dst = smem_base + s * stage_bytes;
+        for (int pl = 0; pl < p.planes; ++pl)
+          bulk_g2s(dst + pl * p.a_rows * 128, p.a + pl * p.a_plane_stride + apos * 64, p.a_rows * 128, full_bar(s));
+        bulk_g2s(dst + a_bytes, p.dy + dpos * N, p.dy_rows * ROWB, full_bar(s));
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t tmem_u = make_uniform(tmem_base);
+    constexpr uint32_t idesc = make_idesc_bf16(128, N, 1, 1);
+    const uint64_t bd0 = make_smem_desc(0, 16, 8 * ROWB, B_LAYOUT);
+    const uint32_t b_hi32 = (uint32_t)(bd0 >> 32), b_flags = (uint32_t)bd0;
+    const uint32_t a_hi32 = (uint32_t)(make_smem_desc(0, 16, 1024, 2) >> 32);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int s = it % p.stages;
+      const uint32_t ph = (it / p.stages) & 1;
+      mbar_wait(full_bar(s), ph, 32);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_stage = smem_base + s * stage_bytes;
+        const uint32_t b_lo0 = ((a_stage + a_bytes + dy_sub * ROWB) >> 4) | b_flags;
+        for (int m = 0; m < mt; ++m) {
+          const int o0 = p.blk_off[2 * m];
+          const int lbo = (2 * m + 1 < p.nblk) ? (p.blk_off[2 * m + 1] - o0) : 128;   // odd tail: any valid block
+          const uint32_t a_lo0 = ((a_stage + o0) >> 4) | (((uint32_t)lbo >> 4) << 16);
+          const uint32_t d_tmem = tmem_u + m * N;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {     // 128 positions, 16 per MMA
+            const uint64_t ad = ((uint64_t)a_hi32 << 32) | (uint64_t)(a_lo0 + kk * 128);             // 16 rows * 128 B
+            const uint64_t bd = ((uint64_t)b_hi32 << 32) | (uint64_t)(b_lo0 + kk * (ROWB));          // 16 rows * ROWB B >> 4
+            umma_bf16(d_tmem, ad, bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(empty_bar(s));
+        if (it == my_tiles - 1) umma_commit(done_bar);
+      }
+      __syncwarp();
+    }
+  } else if (warp < 6) {
+    // ===================== column sums of dY (bias gradient), warps 2..5 =====================
+    const int t4 = tid - 64;                       // 0..127
+    constexpr int CH = ROWB / 16;                  // 16-byte chunks per row
+    constexpr int RPT = 128 * CH / 128;            // rows handled per thread (= CH)
+    const int c = t4 % CH, r0 = t4 / CH;           // chunk column, first row; rows r0 + i*(128/CH)
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int s = it % p.stages;
+      const uint32_t ph = (it / p.stages) & 1;
+      mbar_wait(full_bar(s), ph, 33);
+      const uint32_t b_stage = smem_base + s * stage_bytes + a_bytes;
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        const int r = dy_sub + r0 + i * (128 / CH);
+        const uint32_t addr = b_stage + swz_off<ROWB>(r, c);
+        uint4 v;
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+        csum[0] += bf16_lo(v.x); csum[1] += bf16_hi(v.x); csum[2] += bf16_lo(v.y); csum[3] += bf16_hi(v.y);
+        csum[4] += bf16_lo(v.z); csum[5] += bf16_hi(v.z); csum[6] += bf16_lo(v.w); csum[7] += bf16_hi(v.w);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar(s));
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[t4 * 8 + e] = csum[e];
+  }
+  __syncthreads();
+  // bias partial: fixed-order sum of the 128/CH row groups per column
+  if (tid < N && p.bias_partial) {
+    constexpr int CH = ROWB / 16;
+    const int c = tid >> 3, e = tid & 7;
+    float t = 0.f;
+    for (int g = 0; g < 128 / CH; ++g) t += red[(g * CH + c) * 8 + e];
+    p.bias_partial[(long)blockIdx.x * N + tid] = t;
+  }
+  // ===================== epilogue: TMEM -> fp32 partial =====================
+  if (warp >= 2) {
+    const int q = warp & 3, h = (warp - 2) >> 2;
+    constexpr int HC = N / 2;
+    if (my_tiles > 0) {
+      mbar_wait(done_bar, 0, 34);
+      tc_fence_after();
+    }
+    const int r = q * 32 + lane;
+    for (int m = 0; m < mt; ++m) {
+      const int blk = 2 * m + (r >> 6);
+      float* dst = p.partial + ((long)blockIdx.x * p.nblk * 64 + (long)blk * 64 + (r & 63)) * N + h * HC;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + m * N + h * HC;
+      if constexpr (HC == 32) {
+        uint32_t v[32];
+        if (my_tiles > 0) { tmem_ld32(taddr, v); tmem_ld_wait(); }
+        else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0;
+        }
+        if (blk < p.nblk) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            reinterpret_cast<float4*>(dst)[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                            __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+        }
+      } else {
+        uint32_t v[16];
+        if (my_tiles > 0) { tmem_ld16(taddr, v); tmem_ld_wait(); }
+        else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = 0;
+        }
+        if (blk < p.nblk) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            reinterpret_cast<float4*>(dst)[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                            __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+}  // namespace arl
