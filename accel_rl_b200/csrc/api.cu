@@ -171,6 +171,20 @@ int dev_alloc(arl_ctx* c, T** p, size_t count) {
 
 int roundup(int x, int m) { return (x + m - 1) / m * m; }
 
+// Kernel launch with the programmatic-dependent-launch attribute (see common.cuh: pdl_wait / pdl_trigger): inside the
+// captured graphs the next kernel's prologue may overlap this kernel's tail.  Off by default; ARL_PDL=1 enables.
+bool g_pdl = false;   // measured on B200: no gain inside CUDA graphs (72.2 vs 73.1 ms/iter), early trigger slower (76.0)
+template <class... KArgs, class... Args>
+cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
+
 // record an event after the launch that just happened (profiling mode only)
 void prof_mark(arl_ctx* c, const char* name, cudaStream_t st) {
   if (c->prof_collect) c->prof_labels.push_back(name);
@@ -200,7 +214,7 @@ int launch_rowgemm(arl_ctx* c, ALoad a, WeightSrc b, RowEpi e, int M, int Ntot, 
     attr = true;
   }
   dim3 grid((M + 127) / 128, Ntot / BN, splits);
-  rowgemm_kernel<ALoad, BNM, BN><<<grid, kGemmThreads, Cfg::SMEM, st>>>(a, b, e, num_kb, kbps);
+  ARL_CHECK(c, launch_k(rowgemm_kernel<ALoad, BNM, BN>, dim3(grid), dim3(kGemmThreads), Cfg::SMEM, st, a, b, e, num_kb, kbps));
   c->launches++;
   ARL_CHECK(c, cudaGetLastError());
   return 0;
@@ -233,7 +247,7 @@ int launch_conv_persist(arl_ctx* c, const RowGemmMulti<ConvLoader<128>>& p, int 
   occ = (2 * (smem + 1024) <= 227 * 1024) ? 2 : 1;
   int ctas = std::min(max_tiles, std::max(1, 148 * occ / ncls));
   dim3 grid(ctas, ncls, 1);
-  conv_gemm_persist_kernel<BN><<<grid, kPersistThreads, smem, st>>>(p);
+  ARL_CHECK(c, launch_k(conv_gemm_persist_kernel<BN>, dim3(grid), dim3(kPersistThreads), smem, st, p));
   c->launches++;
   ARL_CHECK(c, cudaGetLastError());
   return 0;
@@ -260,7 +274,7 @@ int launch_wgrad(arl_ctx* c, ALoad a, const __nv_bfloat16* dy, int ld_dy, int nr
     attr = true;
   }
   dim3 grid((atoms + MT * 2 - 1) / (MT * 2), ntiles, splits);
-  wgrad_kernel<ALoad, MT, BN><<<grid, kWgradThreads, Cfg::SMEM_TOTAL, st>>>(a, dy, ld_dy, nrows, rps, atoms, e);
+  ARL_CHECK(c, launch_k(wgrad_kernel<ALoad, MT, BN>, dim3(grid), dim3(kWgradThreads), Cfg::SMEM_TOTAL, st, a, dy, ld_dy, nrows, rps, atoms, e));
   c->launches++;
   ARL_CHECK(c, cudaGetLastError());
   return 0;
@@ -465,7 +479,7 @@ int launch_pconv(arl_ctx* c, const PcParams& p, cudaStream_t st) {
     attr_smem = smem;
   }
   int ctas = std::min(p.ntiles, 148);
-  pconv_fwd_kernel<N><<<ctas, kPcThreads, smem, st>>>(p);
+  ARL_CHECK(c, launch_k(pconv_fwd_kernel<N>, dim3(ctas), dim3(kPcThreads), smem, st, p));
   c->launches++;
   ARL_CHECK(c, cudaGetLastError());
   return 0;
@@ -525,7 +539,7 @@ int launch_pconv_wgrad(arl_ctx* c, const PcWgradParams& p, int ctas, cudaStream_
     ARL_CHECK(c, cudaFuncSetAttribute(pconv_wgrad_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_smem = smem;
   }
-  pconv_wgrad_kernel<N><<<ctas, kPcThreads, smem, st>>>(p);
+  ARL_CHECK(c, launch_k(pconv_wgrad_kernel<N>, dim3(ctas), dim3(kPcThreads), smem, st, p));
   c->launches++;
   ARL_CHECK(c, cudaGetLastError());
   return 0;
@@ -787,7 +801,7 @@ int policy_forward16(arl_ctx* c, const __nv_bfloat16* obs16, int n, const int* o
   if (forward_trunk(c, obs16, nullptr, nullptr, n, &S, pc, st)) return 1;
   HeadParams p = head_base(c, n, S);
   p.out_rows = out_rows; p.prob = prob; p.value = value; p.uniforms = uniforms; p.actions = uniforms ? actions : nullptr;
-  head_kernel<0><<<n, kHeadThreads, 0, st>>>(p);
+  ARL_CHECK(c, launch_k(head_kernel<0>, dim3(n), dim3(kHeadThreads), 0, st, p));
   c->launches++;
   prof_mark(c, "head_sample", st);
   ARL_CHECK(c, cudaGetLastError());
@@ -886,7 +900,7 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
   if (forward_trunk(c, obs16, gidx, gidx_off, n, &S, pcb, st)) return 1;
   // ---- head: losses + dlogits + dh ----
   if (c->t_valids) {
-    count_valids_idx_kernel<<<1, 1024, 0, st>>>(c->t_valids, idx, idx_off, n, c->valid_count);
+    ARL_CHECK(c, launch_k(count_valids_idx_kernel, dim3(1), dim3(1024), 0, st, c->t_valids, idx, idx_off, n, c->valid_count));
     c->launches++;
     prof_mark(c, "count_valids", st);
   }
@@ -897,15 +911,15 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
   p.ent_coeff = c->opt.ent_loss_coeff; p.inv_count = 1.f / (float)n;
   p.h_out = c->h; p.dh_out = c->dh; p.dlogit_out = c->dlogit; p.loss_partial = c->loss_partial;
   c->n_loss_rows = n;
-  head_kernel<1><<<n, kHeadThreads, 0, st>>>(p);
+  ARL_CHECK(c, launch_k(head_kernel<1>, dim3(n), dim3(kHeadThreads), 0, st, p));
   c->launches++;
   prof_mark(c, "head_loss", st);
   ARL_CHECK(c, cudaGetLastError());
   {
     dim3 grid((c->H + 127) / 128, P->head_groups);
     size_t sm = (size_t)P->head_rpg * (c->A + 1) * sizeof(float);
-    head_wgrad_kernel<<<grid, 128, sm, st>>>(c->h, c->dh, c->dlogit, n, c->H, c->A, P->head_rpg, c->head_partial,
-                                              c->head_b_partial);
+    ARL_CHECK(c, launch_k(head_wgrad_kernel, dim3(grid), dim3(128), sm, st, c->h, c->dh, c->dlogit, n, c->H, c->A, P->head_rpg, c->head_partial,
+                                              c->head_b_partial));
     c->launches++;
     prof_mark(c, "head_wgrad", st);
     ARL_CHECK(c, cudaGetLastError());
@@ -989,7 +1003,7 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
   // ---- sum partials, scatter into the flat gradient ----
   {
     dim3 grid(P->fin_blocks, P->n_jobs);
-    finalize_grads_kernel<<<grid, 256, 0, st>>>(P->jobs_dev, c->grad);
+    ARL_CHECK(c, launch_k(finalize_grads_kernel, dim3(grid), dim3(256), 0, st, P->jobs_dev, c->grad));
     c->launches++;
     prof_mark(c, "finalize_grads", st);
     ARL_CHECK(c, cudaGetLastError());
@@ -1002,8 +1016,8 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
 int pack_weights(arl_ctx* c, cudaStream_t st, bool with_fc = true, bool advance = false) {
   if (!c->params) ARL_FAIL(c, "parameters not bound");
   dim3 grid(with_fc ? 148 * 4 : 32, with_fc ? c->n_pack_jobs : c->n_pack_jobs - 1);
-  pack_weights_kernel<<<grid, 256, 0, st>>>(c->pack_jobs_dev, c->params, advance ? c->step : nullptr, c->log_slot,
-                                            c->mb_counter);
+  ARL_CHECK(c, launch_k(pack_weights_kernel, dim3(grid), dim3(256), 0, st, c->pack_jobs_dev, c->params, advance ? c->step : nullptr, c->log_slot,
+                                            c->mb_counter));
   c->launches++;
   prof_mark(c, "pack_weights", st);
   ARL_CHECK(c, cudaGetLastError());
@@ -1013,7 +1027,7 @@ int pack_weights(arl_ctx* c, cudaStream_t st, bool with_fc = true, bool advance 
 int clip_update(arl_ctx* c, float gscale, cudaStream_t st) {
   if (!c->opt_set) ARL_FAIL(c, "optimizer not configured");
   if (!c->m || !c->v) ARL_FAIL(c, "optimizer state not bound");
-  sumsq_kernel<<<kSumsqBlocks, 256, 0, st>>>(c->grad, c->n_params, gscale, c->sumsq_partial);
+  ARL_CHECK(c, launch_k(sumsq_kernel, dim3(kSumsqBlocks), dim3(256), 0, st, c->grad, c->n_params, gscale, c->sumsq_partial));
   c->launches++;
   prof_mark(c, "grad_sumsq", st);
   UpdateParams u{};
@@ -1027,7 +1041,7 @@ int clip_update(arl_ctx* c, float gscale, cudaStream_t st) {
   u.shadow = c->wfc_bf16; u.shadow_begin = c->off_Wfc; u.shadow_end = c->off_Wfc + (long)c->Kfc * c->H;
   bool fused_cast = (c->off_Wfc % 4 == 0);
   if (!fused_cast) u.shadow = nullptr;
-  update_kernel<<<148 * 4, 256, 0, st>>>(u);
+  ARL_CHECK(c, launch_k(update_kernel, dim3(148 * 4), dim3(256), 0, st, u));
   c->launches++;
   prof_mark(c, "clip_update", st);
   ARL_CHECK(c, cudaGetLastError());
@@ -1048,9 +1062,9 @@ int launch_frame(arl_ctx* c, const uint8_t* staging, int s_next, bool to_rollout
   const arl_sampler_cfg& s = c->sc;
   long items = (long)s.n_envs * 520;
   int blocks = (int)((items + 255) / 256);
-  frame_kernel<<<blocks, 256, 0, st>>>(s.frame_pool, staging, c->cmd, s.step_obs, to_rollout ? s.observations : nullptr,
+  ARL_CHECK(c, launch_k(frame_kernel, dim3(blocks), dim3(256), 0, st, s.frame_pool, staging, c->cmd, s.step_obs, to_rollout ? s.observations : nullptr,
                                        c->step_obs16, to_rollout ? c->roll_obs16 : nullptr, s.horizon, s_next, s.n_envs,
-                                       s.planes, c->pc_mode >= 2, c->pc_mode >= 2);
+                                       s.planes, c->pc_mode >= 2, c->pc_mode >= 2));
   c->launches++;
   prof_mark(c, "frame", st);
   ARL_CHECK(c, cudaGetLastError());
@@ -1081,9 +1095,9 @@ int rollout_step(arl_ctx* c, int s_idx, const uint8_t* staging, cudaStream_t st)
   if (policy_forward16(c, c->step_obs16, B, c->rows_tab + (long)s_idx * B, s.prob, s.value,
                        s.uniforms + (long)s_idx * B, s.actions, c->pc_mode >= 2, st))
     return 1;
-  env_step_kernel<<<(B + 127) / 128, 128, 0, st>>>(synth_cfg(s), c->est, c->tout, c->cmd, s.rewards, s.dones,
+  ARL_CHECK(c, launch_k(env_step_kernel, dim3((B + 127) / 128), dim3(128), 0, st, synth_cfg(s), c->est, c->tout, c->cmd, s.rewards, s.dones,
                                                    s.raw_reward, s.need_reset, B, T, s_idx, s.max_path_length,
-                                                   s.discount, s.mid_batch_reset, s.clip_reward, s.episodic_lives);
+                                                   s.discount, s.mid_batch_reset, s.clip_reward, s.episodic_lives));
   c->launches++;
   prof_mark(c, "env_step", st);
   ARL_CHECK(c, cudaGetLastError());
@@ -1139,6 +1153,7 @@ int arl_create(const arl_net_cfg* cfg, arl_ctx** out) {
   // conv path: the patch-resident tiles whenever the geometry allows; ARL_PCONV=0/1 forces the gather path for
   // everything / for training only (A/B measurements)
   c->pc_mode = c->pc.empty() ? 0 : 2;
+  if (const char* e = getenv("ARL_PDL")) g_pdl = atoi(e) != 0;
   if (const char* e = getenv("ARL_PCONV")) c->pc_mode = c->pc.empty() ? 0 : std::max(0, std::min(2, atoi(e)));
   *out = c;
   return 0;
@@ -1533,6 +1548,10 @@ int arl_profile_graph(arl_ctx* c, int kind, const int* idx, int mb_size, int rep
   c->prof_collect = true;
   long l0 = c->launches;
   cudaGraph_t g = nullptr;
+  // plain (fully serialised) edges in this scratch graph: the node-introspection calls below cannot represent
+  // programmatic-dependent-launch edges
+  const bool pdl_saved = g_pdl;
+  g_pdl = false;
   ARL_CHECK(c, cudaStreamBeginCapture(cap_s, cudaStreamCaptureModeThreadLocal));
   int rc = 0;
   if (kind == 0) {
@@ -1546,6 +1565,7 @@ int arl_profile_graph(arl_ctx* c, int kind, const int* idx, int mb_size, int rep
                           c->pc_mode >= 1, cap_s);
   }
   cudaError_t ce = cudaStreamEndCapture(cap_s, &g);
+  g_pdl = pdl_saved;
   c->prof_collect = false;
   c->launches = l0;
   if (rc) { if (g) cudaGraphDestroy(g); cudaStreamDestroy(cap_s); return rc; }

@@ -205,6 +205,20 @@ ARL_DEVINL uint32_t swz_off(uint32_t r, uint32_t c) {
 }
 
 // ---------------------------------------------------------------------------
+// programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor drains; pdl_wait() blocks until the predecessor grid has completed and its writes are
+// visible.  Rule used everywhere: NOTHING that reads or writes global memory happens before pdl_wait() — only
+// barrier init / TMEM allocation / shared-memory setup.  pdl_trigger() lets the successor begin its own prologue.
+// Both are no-ops for a normally launched kernel.
+// ---------------------------------------------------------------------------
+ARL_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifdef ARL_NO_TRIGGER
+ARL_DEVINL void pdl_trigger() {}
+#else
+ARL_DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
+// ---------------------------------------------------------------------------
 // misc
 // ---------------------------------------------------------------------------
 ARL_DEVINL void st_shared_v4(uint32_t addr, uint4 v) {

@@ -376,6 +376,8 @@ ARL_DEVINL void rowgemm_body(ALoad& aload, const WeightSrc& bsrc, const RowEpi& 
     fence_mbar_init();
   }
   if (warp == kProducerWarps) tmem_alloc(tmem_ptr_addr, Cfg::TMEM_COLS);
+  pdl_wait();
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -541,6 +543,8 @@ __global__ void __launch_bounds__(kPersistThreads, 2) conv_gemm_persist_kernel(
   }
   p.a[cls].build_table(ktab, num_kb * 8, tid, kPersistThreads);
   if (warp == kProducerWarps) tmem_alloc(tmem_ptr_addr, TMEM_COLS);
+  pdl_wait();
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -721,6 +725,8 @@ __global__ void __launch_bounds__(kWgradThreads) wgrad_kernel(ALoad64 aload, con
     mbar_init(tmem_full_bar, 1);
     fence_mbar_init();
   }
+  pdl_wait();
+  pdl_trigger();
   if constexpr (ALoad64::kNeedsTable) {
     // decode tables, built once per CTA: K-chunk -> tap offset (k' chunks are global: atom0*8 + ...),
     // and row -> (image, origin) for every row of this split (no integer division in the stage loop)

@@ -80,6 +80,8 @@ __global__ void env_step_kernel(SynthCfg cfg, EnvState st, TrajOut tout, FrameCm
                                 float* __restrict__ raw_reward, uint8_t* __restrict__ info_need_reset,
                                 int n_envs, int T, int s, int max_path_length, float discount,
                                 int mid_batch_reset, int clip_reward, int episodic_lives) {
+  pdl_wait();
+  pdl_trigger();
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_envs) return;
   FrameCmd c;
@@ -162,6 +164,8 @@ __global__ void env_step_kernel(SynthCfg cfg, EnvState st, TrajOut tout, FrameCm
 // After the batch when mid_batch_reset == False: reset envs flagged need_reset
 // (worker.py:106-113 reset_needed_envs) — produces the first observation of the next batch.
 __global__ void env_reset_needed_kernel(SynthCfg cfg, EnvState st, FrameCmd* __restrict__ cmd, int n_envs) {
+  pdl_wait();
+  pdl_trigger();
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_envs) return;
   FrameCmd c;
@@ -224,6 +228,8 @@ ARL_DEVINL uint2 u8x4_to_bf16x4(uint32_t w) {
 __global__ void __launch_bounds__(256) obs_to_s2d_kernel(const uint8_t* __restrict__ src, const int* __restrict__ idx,
                                                          __nv_bfloat16* __restrict__ dst, int n, int C, int H, int W,
                                                          int swz) {
+  pdl_wait();
+  pdl_trigger();
   const int Wb = W >> 2, Hb = H >> 2;
   const long total = (long)n * C * H * Wb;
   for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
@@ -277,6 +283,8 @@ __global__ void __launch_bounds__(256) frame_kernel(const uint8_t* __restrict__ 
                                                     uint8_t* __restrict__ roll_obs, __nv_bfloat16* __restrict__ step_obs16,
                                                     __nv_bfloat16* __restrict__ roll_obs16, int T, int s_next, int n_envs,
                                                     int planes, int swz_step, int swz_roll) {
+  pdl_wait();
+  pdl_trigger();
   // step_obs16 / roll_obs16: bf16 space-to-depth(4) mirrors of the same stacks, [26][20][planes*16] per
   // observation, channel = plane*16 + (y%4)*4 + (x%4) — the layout the first conv layer's tcgen05 tiles read
   // (u8 -> bf16 is exact).  They are written from the registers that already hold the u8 stack.
@@ -388,6 +396,8 @@ __global__ void __launch_bounds__(256) frame_pair_kernel(const uint8_t* __restri
 __global__ void copy_rows_kernel(const uint8_t* __restrict__ src, long sstride, const int* __restrict__ srows,
                                  uint8_t* __restrict__ dst, long dstride, const int* __restrict__ drows, int n,
                                  int row_bytes) {
+  pdl_wait();
+  pdl_trigger();
   int per = row_bytes / 16;
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long)n * per) return;
@@ -456,6 +466,8 @@ constexpr int kHeadThreads = 128;
 // softmax / loss arithmetic is done redundantly by every thread (a handful of flops).
 template <int MODE>
 __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadParams p) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float s_part[kHeadThreads / 32][kMaxActions + 1];
   const int row = blockIdx.x;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -629,6 +641,8 @@ __global__ void __launch_bounds__(128) head_wgrad_kernel(const __nv_bfloat16* __
                                                           const float* __restrict__ dlogit, int M, int H, int A,
                                                           int rows_per_group, float* __restrict__ out,
                                                           float* __restrict__ out_b) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float s_dl[];   // [rows_per_group][A+1]
   const int g = blockIdx.y;
   const int r0 = g * rows_per_group;
@@ -701,6 +715,8 @@ ARL_DEVINL void pc_decode_channel(int cc, int C, int s, int ci_major, int& ci, i
 }
 
 __global__ void __launch_bounds__(256) finalize_grads_kernel(const GradJob* __restrict__ jobs, float* __restrict__ grad) {
+  pdl_wait();
+  pdl_trigger();
   const GradJob jb = jobs[blockIdx.y];
   const long total = (long)jb.rows * jb.cols;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -763,6 +779,8 @@ constexpr int kSumsqBlocks = 592;   // 4 x 148
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long n, float gscale,
                                                      double* __restrict__ partial) {
+  pdl_wait();
+  pdl_trigger();
   double acc = 0.0;
   const long n4 = n >> 2;
   const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -801,6 +819,8 @@ struct UpdateParams {
 };
 
 __global__ void __launch_bounds__(256) update_kernel(UpdateParams p) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ double s_red[8];
   __shared__ float s_scale, s_alpha;
   // every block: reduce the partial sums in the same order -> identical norm everywhere
@@ -926,6 +946,8 @@ struct PackJob {
 __global__ void __launch_bounds__(256) pack_weights_kernel(const PackJob* __restrict__ jobs,
                                                             const float* __restrict__ params, int* step,
                                                             int* log_slot, int* mb_counter) {
+  pdl_wait();
+  pdl_trigger();
   // last kernel of an update: also advances the device-side counters (Adam t, log slot, minibatch index)
   if (step && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
     step[0] += 1; log_slot[0] += 1; mb_counter[0] += 1;
@@ -1114,6 +1136,8 @@ __global__ void __launch_bounds__(1024) count_valids_kernel(const int8_t* __rest
 __global__ void __launch_bounds__(1024) count_valids_idx_kernel(const int8_t* __restrict__ valids,
                                                                 const int* __restrict__ idx,
                                                                 const int* __restrict__ idx_off, int n, float* out) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ int s[32];
   const int* ip = idx;
   if (ip && idx_off) ip += (long)idx_off[0] * n;

@@ -205,9 +205,11 @@ __global__ void __launch_bounds__(kPcThreads, 1) pconv_fwd_kernel(const __grid_c
     mbar_init(wfull_bar, 1);
     fence_mbar_init();
   }
+  if (warp == 1) tmem_alloc(tmem_ptr_addr, 2 * N);
+  pdl_wait();                                  // everything below may read what the previous kernel wrote
+  pdl_trigger();
   if (p.out.mode == 0)
     for (int i = tid; i < N; i += kPcThreads) bias_s[i] = p.out.bias[i];
-  if (warp == 1) tmem_alloc(tmem_ptr_addr, 2 * N);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -430,6 +432,8 @@ __global__ void __launch_bounds__(kPcThreads, 1) pconv_wgrad_kernel(const __grid
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr_addr, tmem_cols);
+  pdl_wait();
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
