@@ -117,6 +117,11 @@ SIGNATURES = {
     "arl_comm_connect": (C.c_int, [_P, _P]),
     "arl_sync_allreduce_update": (C.c_int, [_P, _P]),
     "arl_comm_barrier": (C.c_int, [_P, _P]),
+    "arl_async_local_init": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
+    "arl_async_connect": (C.c_int, [_P, _P]),
+    "arl_async_regions": (C.c_int, [_P]),
+    "arl_async_push_pull": (C.c_int, [_P, _P]),
+    "arl_async_read_central": (C.c_int, [_P, C.c_int, _P, C.c_long, _P]),
     "arl_debug_activation": (C.c_int, [_P, C.c_int, _P, C.c_long, C.POINTER(C.c_long), _P]),
     "arl_kernel_launches": (C.c_long, [_P]),
     "arl_profile_begin": (C.c_int, [_P, _P]),

@@ -92,6 +92,9 @@ struct arl_ctx {
   arl_net_cfg cfg{};
   std::vector<ConvLayer> conv;
   std::vector<PcLayer> pc;             // patch-resident conv path (empty: geometry not supported -> gather path)
+  cudaStream_t side = nullptr;         // weight-gradient kernels run here, overlapping the data-gradient chain
+  cudaEvent_t ev_fork[4] = {nullptr, nullptr, nullptr, nullptr}, ev_join = nullptr;
+  bool no_fork = false;                // serialise everything on the caller's stream (per-kernel profiling)
   int pc_dy_n = 0;                     // images whose gradient-grid rows may be non-zero
   int pc_mode = 0;                     // 0: gather path   1: pconv forward (inference)   2: pconv forward + backward
   int Kfc = 0, H = 0, A = 0, HWlast = 0, Clast = 0;
@@ -156,6 +159,7 @@ struct arl_ctx {
   int n_loss_rows = 0;                 // rows of the last head_kernel<1> launch (loss partial count)
   float lr_mult_host = 1.f;
   CommState comm;
+  AsyncState async_;
 };
 
 namespace {
@@ -623,10 +627,11 @@ int pconv_prepare_dy(arl_ctx* c, int n, cudaStream_t st) {
   return 0;
 }
 
+constexpr int kFcBN = 128;   // FC forward tile width: A is re-read H/kFcBN times, the weights ceil(n/128) times
 int fc_splits(arl_ctx* c, int n, int& kbps) {
   int kb = c->Kfc / 64;
-  int tiles = ((n + 127) / 128) * (c->H / 64);
-  int S = std::max(1, std::min(kb, (296 + tiles / 2) / tiles));
+  int tiles = ((n + 127) / 128) * (c->H / kFcBN);
+  int S = std::max(1, std::min(kb, (148 + tiles / 2) / tiles));
   kbps = (kb + S - 1) / S;
   S = (kb + kbps - 1) / kbps;
   return S;
@@ -644,14 +649,15 @@ int alloc_net(arl_ctx* c) {
     PackJob j{};
     j.dst = L.wpack; j.src_off = L.off_W; j.kind = (l == 0) ? PK_CONV_S2D : PK_CONV_NHWC;
     j.rows = L.Cout; j.cols = L.K; j.Cout = L.Cout; j.C = L.Cin; j.kh = L.k; j.kw = L.k; j.s = L.s;
-    pj.push_back(j);
+    const bool gather_packs = c->pc_mode < 2;   // the gather path's operand copies are dead weight in full pconv mode
+    if (gather_packs) pj.push_back(j);
     for (auto& d : L.dclasses) {
       if (dev_alloc(c, &d.wpack, (size_t)L.Cin * d.K)) return 1;
       PackJob q{};
       q.dst = d.wpack; q.src_off = L.off_W; q.kind = PK_CONV_DGRAD;
       q.rows = L.Cin; q.cols = d.K; q.Cout = L.Cout; q.C = L.Cin; q.kh = L.k; q.kw = L.k;
       q.s = L.s; q.ry = d.ry; q.rx = d.rx; q.Tx = d.Tx;
-      pj.push_back(q);
+      if (gather_packs) pj.push_back(q);
     }
     long cap = (long)kMaxSplits * std::max(L.K, c->pc.empty() ? 0 : c->pc[l].ntaps * c->pc[l].P * 64) * L.Cout;
     float* wp = nullptr;
@@ -779,7 +785,7 @@ int forward_trunk(arl_ctx* c, const __nv_bfloat16* obs16, const int* idx, const 
   a.src = c->conv.back().act; a.ld = c->Kfc; a.nrows = n;
   // B = the FC weights in the reference's (c,h,w)-row order, read N-major through the (hw,c) row permutation
   WeightSrc w{c->wfc_bf16, (long)c->H, c->Kfc, RowPerm{c->Clast, c->HWlast}};
-  if (launch_rowgemm<DenseLoader<128>, true, 64>(c, a, w, e, n, c->H, c->Kfc / 64, kbps, S, st)) return 1;
+  if (launch_rowgemm<DenseLoader<128>, true, kFcBN>(c, a, w, e, n, c->H, c->Kfc / 64, kbps, S, st)) return 1;
   prof_mark(c, "fc_fwd", st);
   *fc_S = S;
   return 0;
@@ -915,13 +921,27 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
   c->launches++;
   prof_mark(c, "head_loss", st);
   ARL_CHECK(c, cudaGetLastError());
+  // The weight-gradient kernels only feed finalize_grads at the very end: they go to a side stream and overlap the
+  // data-gradient chain (every kernel here is fixed-cost dominated at minibatch size: one kernel's ramp-up fills the
+  // SMs the other's tail leaves idle).  fork k = "the gradient grid wgrad k needs is complete".
+  cudaStream_t ws = st;
+  if (!c->no_fork && !c->prof_on && pcb) {
+    if (!c->side) {
+      ARL_CHECK(c, cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+      for (auto& e : c->ev_fork) ARL_CHECK(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ARL_CHECK(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    }
+    ws = c->side;
+    ARL_CHECK(c, cudaEventRecord(c->ev_fork[0], st));
+    ARL_CHECK(c, cudaStreamWaitEvent(ws, c->ev_fork[0], 0));
+  }
   {
     dim3 grid((c->H + 127) / 128, P->head_groups);
     size_t sm = (size_t)P->head_rpg * (c->A + 1) * sizeof(float);
-    ARL_CHECK(c, launch_k(head_wgrad_kernel, dim3(grid), dim3(128), sm, st, c->h, c->dh, c->dlogit, n, c->H, c->A, P->head_rpg, c->head_partial,
+    ARL_CHECK(c, launch_k(head_wgrad_kernel, dim3(grid), dim3(128), sm, ws, c->h, c->dh, c->dlogit, n, c->H, c->A, P->head_rpg, c->head_partial,
                                               c->head_b_partial));
     c->launches++;
-    prof_mark(c, "head_wgrad", st);
+    prof_mark(c, "head_wgrad", ws);
     ARL_CHECK(c, cudaGetLastError());
   }
   ConvLayer& LL = c->conv.back();
@@ -932,9 +952,9 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
     WgradEpi e{};
     e.out = c->grad + c->off_Wfc; e.mode = 1; e.Kvalid = c->Kfc; e.Kp = c->Kfc; e.ldo = c->H; e.fc_C = c->Clast;
     e.fc_HW = c->HWlast;
-    if (launch_wgrad<DenseLoader<64>, 1, 256>(c, a, c->dh, c->H, n, roundup(n, 64), 1, c->Kfc / 64, c->H / 256, e, st))
+    if (launch_wgrad<DenseLoader<64>, 1, 256>(c, a, c->dh, c->H, n, roundup(n, 64), 1, c->Kfc / 64, c->H / 256, e, ws))
       return 1;
-    prof_mark(c, "fc_wgrad", st);
+    prof_mark(c, "fc_wgrad", ws);
   }
   // ---- FC dgrad: da_last[n][Kfc] = dh Wfc^T, masked by a_last > 0 ----
   {
@@ -954,11 +974,23 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
   }
   // ---- conv layers, last to first ----
   for (int l = (int)c->conv.size() - 1; l >= 0 && pcb; --l) {
-    if (pconv_wgrad_layer(c, l, obs16, gidx, gidx_off, n, st)) return 1;
-    prof_mark(c, kWgradName[l], st);
+    // layer l's gradient grid was completed by the last kernel on `st` (FC dgrad or dgrad l+1); the first layer's
+    // wgrad closes the main chain itself
+    cudaStream_t wl = (l == 0) ? st : ws;
+    if (wl != st) {
+      cudaEvent_t ev = c->ev_fork[1 + (l % 3)];
+      ARL_CHECK(c, cudaEventRecord(ev, st));
+      ARL_CHECK(c, cudaStreamWaitEvent(wl, ev, 0));
+    }
+    if (pconv_wgrad_layer(c, l, obs16, gidx, gidx_off, n, wl)) return 1;
+    prof_mark(c, kWgradName[l], wl);
     if (l == 0) break;
     if (pconv_dgrad_layer(c, l, n, st)) return 1;
     prof_mark(c, kDgradName[l], st);
+  }
+  if (ws != st) {
+    ARL_CHECK(c, cudaEventRecord(c->ev_join, ws));
+    ARL_CHECK(c, cudaStreamWaitEvent(st, c->ev_join, 0));
   }
   for (int l = (int)c->conv.size() - 1; l >= 0 && !pcb; --l) {
     ConvLayer& L = c->conv[l];
@@ -1145,16 +1177,17 @@ int arl_create(const arl_net_cfg* cfg, arl_ctx** out) {
   }
   arl_ctx* c = new arl_ctx();
   c->cfg = *cfg;
-  if (plan_net(c) || plan_pconv(c) || alloc_net(c)) {
+  int rc0 = plan_net(c) || plan_pconv(c);
+  // conv path: the patch-resident tiles whenever the geometry allows; ARL_PCONV=0/1 forces the gather path for
+  // everything / for training only (A/B measurements)
+  c->pc_mode = c->pc.empty() ? 0 : 2;
+  if (const char* ev = getenv("ARL_PDL")) g_pdl = atoi(ev) != 0;
+  if (const char* ev = getenv("ARL_PCONV")) c->pc_mode = c->pc.empty() ? 0 : std::max(0, std::min(2, atoi(ev)));
+  if (rc0 || alloc_net(c)) {
     g_create_error = c->err;
     delete c;
     return 4;
   }
-  // conv path: the patch-resident tiles whenever the geometry allows; ARL_PCONV=0/1 forces the gather path for
-  // everything / for training only (A/B measurements)
-  c->pc_mode = c->pc.empty() ? 0 : 2;
-  if (const char* e = getenv("ARL_PDL")) g_pdl = atoi(e) != 0;
-  if (const char* e = getenv("ARL_PCONV")) c->pc_mode = c->pc.empty() ? 0 : std::max(0, std::min(2, atoi(e)));
   *out = c;
   return 0;
 }
@@ -1163,6 +1196,7 @@ void arl_destroy(arl_ctx* c) {
   if (!c) return;
   cudaDeviceSynchronize();
   comm_destroy(c->comm);
+  async_destroy(c->async_);
   // device workspaces are released with the context's process lifetime; free the large ones explicitly
   for (auto& L : c->conv) {
     cudaFree(L.act); cudaFree(L.dact); cudaFree(L.wpack);
@@ -1499,6 +1533,55 @@ int arl_sync_allreduce_update(arl_ctx* c, void* stream) {
   return pack_weights(c, st, true, true);
 }
 
+// ---- async DP -----------------------------------------------------------------------------
+int arl_async_local_init(arl_ctx* c, int rank, int world, int n_update_chunks, uint8_t* handle_out) {
+  if (!c->params) ARL_FAIL(c, "parameters not bound");
+  ARL_CHECK(c, cudaDeviceSynchronize());
+  if (async_local_init(c->async_, rank, world, c->n_params, n_update_chunks, c->params, handle_out, c->err)) return 1;
+  return 0;
+}
+
+int arl_async_connect(arl_ctx* c, const uint8_t* rank0_handle) {
+  if (async_connect(c->async_, c->n_params, rank0_handle, c->err)) return 1;
+  return 0;
+}
+
+int arl_async_regions(arl_ctx* c) { return c->async_.dev.n_locks; }
+
+/* local clip -> chunk-locked update of the central (p, m, v) with the local gradient -> pull the new p */
+int arl_async_push_pull(arl_ctx* c, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!c->async_.ready) ARL_FAIL(c, "async store not connected");
+  if (!c->opt_set) ARL_FAIL(c, "optimizer not configured");
+  sumsq_kernel<<<kSumsqBlocks, 256, 0, st>>>(c->grad, c->n_params, 1.f, c->sumsq_partial);
+  c->launches++;
+  UpdateParams u{};
+  u.param = c->params; u.grad = c->grad; u.m = nullptr; u.v = nullptr; u.n = c->n_params;
+  u.sumsq_partial = c->sumsq_partial; u.n_partial = kSumsqBlocks;
+  u.loss_partial = c->loss_partial; u.n_loss_blocks = c->n_loss_rows;
+  u.hyper = c->hyper; u.step = c->step; u.kind = c->opt.update;
+  u.lr = c->opt.learning_rate; u.beta1 = c->opt.beta1; u.beta2 = c->opt.beta2; u.eps = c->opt.epsilon;
+  u.rho = c->opt.rho; u.clip = c->opt.grad_norm_clip; u.gscale = 1.f;
+  u.out_norm = c->log_norm; u.out_loss = c->log_loss; u.log_slot = c->log_slot; u.log_cap = c->log_cap;
+  bool fused_cast = (c->off_Wfc % 4 == 0) && (c->async_.dev.per % 4 == 0);
+  u.shadow = fused_cast ? c->wfc_bf16 : nullptr;
+  u.shadow_begin = c->off_Wfc; u.shadow_end = c->off_Wfc + (long)c->Kfc * c->H;
+  int grid = std::min(c->async_.dev.n_locks, 148);
+  async_push_pull_kernel<<<grid, kAsyncThreads, 0, st>>>(c->async_.dev, u);
+  c->launches++;
+  ARL_CHECK(c, cudaGetLastError());
+  return pack_weights(c, st, !fused_cast, true);
+}
+
+/* test hook: copy central array `which` (0 = p, 1 = m, 2 = v / accumulator) to the host */
+int arl_async_read_central(arl_ctx* c, int which, float* host_out, long n, void* stream) {
+  if (!c->async_.ready) ARL_FAIL(c, "async store not connected");
+  ARL_CHECK(c, cudaStreamSynchronize((cudaStream_t)stream));
+  const float* src = which == 0 ? c->async_.dev.cp : which == 1 ? c->async_.dev.cm : c->async_.dev.cv;
+  ARL_CHECK(c, cudaMemcpy(host_out, src, (size_t)std::min(n, c->n_params) * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 // ---- diagnostics --------------------------------------------------------------------------
 __global__ void bf16_to_f32_kernel(const __nv_bfloat16* x, float* y, long n) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1552,6 +1635,7 @@ int arl_profile_graph(arl_ctx* c, int kind, const int* idx, int mb_size, int rep
   // programmatic-dependent-launch edges
   const bool pdl_saved = g_pdl;
   g_pdl = false;
+  c->no_fork = true;
   ARL_CHECK(c, cudaStreamBeginCapture(cap_s, cudaStreamCaptureModeThreadLocal));
   int rc = 0;
   if (kind == 0) {
@@ -1566,6 +1650,7 @@ int arl_profile_graph(arl_ctx* c, int kind, const int* idx, int mb_size, int rep
   }
   cudaError_t ce = cudaStreamEndCapture(cap_s, &g);
   g_pdl = pdl_saved;
+  c->no_fork = false;
   c->prof_collect = false;
   c->launches = l0;
   if (rc) { if (g) cudaGraphDestroy(g); cudaStreamDestroy(cap_s); return rc; }

@@ -306,4 +306,215 @@ inline int comm_sync_update(CommState& s, SyncUpdateArgs a, cudaStream_t st, std
   return 0;
 }
 
+// ===========================================================================
+// Asynchronous data parallel: central parameter / optimiser-state store with chunk-granular mutual exclusion.
+//
+// Reference behaviour (optimizers/async/base.py:59-104, chunked_updates.py:53-120, async_a2c_optimizer.py:96-109):
+//   every learner: local gradient, clipped LOCALLY -> for each chunk: take the chunk's lock, apply RMSProp/Adam
+//   with the local gradient to the CENTRAL (p, m, v)[chunk] (Adam's t is per learner), release -> copy the new
+//   central p into the local parameters.  No collective; staleness between learners is allowed.
+// Here the central store lives in rank 0's HBM (one cudaMalloc, shared with a cudaIpc handle); every learner runs
+// ONE kernel per update: a CTA takes a region's lock with a system-scope CAS over NVLink, streams the region's
+// (p, m, v) through registers with system-scope loads/stores, writes the new p both to the central store and to
+// its own parameter vector (+ the bf16 FC operand copy), and releases the lock.  A CTA never holds two locks and
+// never waits while holding one, so learners cannot deadlock.  The lock regions subdivide the reference's
+// n_update_chunks chunks (finer regions = more CTAs in flight; the exclusion the reference relies on — an
+// element's (p, m, v) triple is updated atomically — is preserved).
+// ===========================================================================
+struct AsyncDev {
+  float* cp; float* cm; float* cv;   // central params / first moment (Adam) / second moment or RMSProp accumulator
+  unsigned int* locks;               // [n_locks], 0 = free
+  int n_locks;
+  long per;                          // elements per lock region (multiple of 4)
+};
+
+struct AsyncState {
+  bool ready = false;
+  int rank = 0, world = 1;
+  void* base = nullptr;              // rank 0: owning allocation; others: opened IPC mapping
+  bool owner = false;
+  AsyncDev dev{};
+};
+
+inline size_t async_layout(long n, int n_locks, size_t* off_m, size_t* off_v, size_t* off_locks) {
+  size_t nb = ((size_t)n * 4 + 255) / 256 * 256;
+  *off_m = nb; *off_v = 2 * nb; *off_locks = 3 * nb;
+  return 3 * nb + ((size_t)n_locks * 4 + 255) / 256 * 256;
+}
+
+ARL_DEVINL float4 ld_sys_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+ARL_DEVINL void st_sys_f4(float* p, float4 v) {
+  asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+ARL_DEVINL float ld_sys_f(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+ARL_DEVINL void st_sys_f(float* p, float v) { asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+
+constexpr int kAsyncThreads = 512;
+
+__global__ void __launch_bounds__(kAsyncThreads) async_push_pull_kernel(AsyncDev d, UpdateParams p) {
+  __shared__ double s_red[kAsyncThreads / 32];
+  __shared__ float s_scale, s_alpha;
+  // local global-norm clip (optimizers/util.py:70-76) and the per-learner step size — same arithmetic as update_kernel
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < p.n_partial; i += blockDim.x) acc += p.sumsq_partial[i];
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kAsyncThreads / 32; ++w) t += s_red[w];
+    float norm = (float)sqrt(t);
+    float scale = p.gscale;
+    if (p.clip > 0.f) scale *= fminf(norm, p.clip) / (1e-7f + norm);
+    s_scale = scale;
+    int tstep = p.step[0] + 1;
+    float lr = p.lr * p.hyper[0];
+    if (p.kind == 0) {
+      double b1t = pow((double)p.beta1, (double)tstep), b2t = pow((double)p.beta2, (double)tstep);
+      s_alpha = (float)((double)lr * sqrt(1.0 - b2t) / (1.0 - b1t));
+    } else {
+      s_alpha = lr;
+    }
+    if (blockIdx.x == 0) {
+      int slot = p.log_slot[0];
+      if (slot < p.log_cap) {
+        p.out_norm[slot] = norm;
+        float l = 0.f;
+        for (int b = 0; b < p.n_loss_blocks; ++b) l += p.loss_partial[4 * b + 3];
+        p.out_loss[slot] = l;
+      }
+    }
+  }
+  __syncthreads();
+  const float scale = s_scale, alpha = s_alpha;
+  for (int c = blockIdx.x; c < d.n_locks; c += gridDim.x) {
+    const long begin = (long)c * d.per;
+    const long end = min(p.n, begin + d.per);
+    if (threadIdx.x == 0) {
+      long long t0 = clock64();
+      unsigned int backoff = 32;
+      while (atomicCAS_system(d.locks + c, 0u, 1u) != 0u) {
+        __nanosleep(backoff);
+        if (backoff < 2048) backoff <<= 1;
+        if (clock64() - t0 > 40000000000LL) dev_fail(310);     // ~20 s: a lock holder died
+      }
+      __threadfence_system();
+    }
+    __syncthreads();
+    const long n4 = (end - begin) >> 2;
+    for (long i = threadIdx.x; i < n4; i += blockDim.x) {
+      const long e0 = begin + (i << 2);
+      const float4 g4 = *reinterpret_cast<const float4*>(p.grad + e0);
+      float4 p4 = ld_sys_f4(d.cp + e0);
+      float4 v4 = ld_sys_f4(d.cv + e0);
+      float g[4] = {g4.x * scale, g4.y * scale, g4.z * scale, g4.w * scale};
+      float pp[4] = {p4.x, p4.y, p4.z, p4.w};
+      float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+      if (p.kind == 0) {
+        float4 m4 = ld_sys_f4(d.cm + e0);
+        float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          mm[k] = p.beta1 * mm[k] + (1.f - p.beta1) * g[k];
+          vv[k] = p.beta2 * vv[k] + (1.f - p.beta2) * g[k] * g[k];
+          pp[k] -= alpha * mm[k] / (sqrtf(vv[k]) + p.eps);
+        }
+        st_sys_f4(d.cm + e0, make_float4(mm[0], mm[1], mm[2], mm[3]));
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          vv[k] = p.rho * vv[k] + (1.f - p.rho) * g[k] * g[k];
+          pp[k] -= alpha * g[k] / sqrtf(vv[k] + p.eps);
+        }
+      }
+      st_sys_f4(d.cv + e0, make_float4(vv[0], vv[1], vv[2], vv[3]));
+      st_sys_f4(d.cp + e0, make_float4(pp[0], pp[1], pp[2], pp[3]));
+      *reinterpret_cast<float4*>(p.param + e0) = make_float4(pp[0], pp[1], pp[2], pp[3]);   // pull
+      if (p.shadow && e0 >= p.shadow_begin && e0 + 4 <= p.shadow_end)
+        *reinterpret_cast<uint2*>(p.shadow + (e0 - p.shadow_begin)) =
+            make_uint2(pack_bf16x2(pp[0], pp[1]), pack_bf16x2(pp[2], pp[3]));
+    }
+    // tail of the vector (n % 4 elements) belongs to the last region
+    for (long e = begin + (n4 << 2) + threadIdx.x; e < end; e += blockDim.x) {
+      float g = p.grad[e] * scale, pv = ld_sys_f(d.cp + e), vv = ld_sys_f(d.cv + e);
+      if (p.kind == 0) {
+        float mm = p.beta1 * ld_sys_f(d.cm + e) + (1.f - p.beta1) * g;
+        vv = p.beta2 * vv + (1.f - p.beta2) * g * g;
+        pv -= alpha * mm / (sqrtf(vv) + p.eps);
+        st_sys_f(d.cm + e, mm);
+      } else {
+        vv = p.rho * vv + (1.f - p.rho) * g * g;
+        pv -= alpha * g / sqrtf(vv + p.eps);
+      }
+      st_sys_f(d.cv + e, vv);
+      st_sys_f(d.cp + e, pv);
+      p.param[e] = pv;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicExch_system(d.locks + c, 0u);
+  }
+}
+
+inline int async_local_init(AsyncState& s, int rank, int world, long n, int n_update_chunks, const float* params,
+                            uint8_t* handle_out, std::string& err) {
+  if (world < 1 || world > kMaxRanks) { err = "world size must be in [1,8]"; return 1; }
+  if (n_update_chunks < 1) { err = "n_update_chunks must be >= 1"; return 1; }
+  s.rank = rank; s.world = world;
+  // reference chunk length (chunked_updates.py:61): n // n_chunks + 1, subdivided so that ~148 regions exist
+  long ppc = n / n_update_chunks + 1;
+  int sub = std::max(1, 148 / n_update_chunks);
+  long per = ((ppc + sub - 1) / sub + 3) / 4 * 4;
+  s.dev.per = per;
+  s.dev.n_locks = (int)((n + per - 1) / per);
+  memset(handle_out, 0, 64);
+  if (rank != 0) return 0;
+  size_t om, ov, ol;
+  size_t bytes = async_layout(n, s.dev.n_locks, &om, &ov, &ol);
+  cudaError_t e = cudaMalloc(&s.base, bytes);
+  if (e != cudaSuccess) { err = std::string("cudaMalloc(central): ") + cudaGetErrorString(e); return 1; }
+  cudaMemset(s.base, 0, bytes);
+  cudaMemcpy(s.base, params, (size_t)n * 4, cudaMemcpyDeviceToDevice);
+  s.owner = true;
+  if (world > 1) {
+    cudaIpcMemHandle_t h;
+    e = cudaIpcGetMemHandle(&h, s.base);
+    if (e != cudaSuccess) { err = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e); return 1; }
+    memcpy(handle_out, &h, 64);
+  }
+  return 0;
+}
+
+inline int async_connect(AsyncState& s, long n, const uint8_t* rank0_handle, std::string& err) {
+  if (s.rank != 0) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, rank0_handle, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(&s.base, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { err = std::string("cudaIpcOpenMemHandle(central): ") + cudaGetErrorString(e); return 1; }
+  }
+  size_t om, ov, ol;
+  async_layout(n, s.dev.n_locks, &om, &ov, &ol);
+  uint8_t* b = reinterpret_cast<uint8_t*>(s.base);
+  s.dev.cp = reinterpret_cast<float*>(b);
+  s.dev.cm = reinterpret_cast<float*>(b + om);
+  s.dev.cv = reinterpret_cast<float*>(b + ov);
+  s.dev.locks = reinterpret_cast<unsigned int*>(b + ol);
+  s.ready = true;
+  return 0;
+}
+
+inline void async_destroy(AsyncState& s) {
+  if (!s.base) return;
+  if (s.owner) cudaFree(s.base); else cudaIpcCloseMemHandle(s.base);
+  s.base = nullptr; s.ready = false;
+}
+
 }  // namespace arl

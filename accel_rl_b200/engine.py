@@ -228,6 +228,25 @@ class Engine(object):
     def sync_allreduce_update(self):
         self.check(self.lib.arl_sync_allreduce_update(self.ctx, self._s()))
 
+    # ---- async data parallel -----------------------------------------------------------------
+    def async_init(self, rank, world, n_update_chunks, exchange):
+        """exchange(handle_bytes) -> list of every rank's handle bytes; rank 0's entry is the central store."""
+        h = (C.c_uint8 * L.IPC_HANDLE_BYTES)()
+        self.check(self.lib.arl_async_local_init(self.ctx, int(rank), int(world), int(n_update_chunks), h))
+        handles = exchange(bytes(h))
+        buf = (C.c_uint8 * L.IPC_HANDLE_BYTES).from_buffer_copy(handles[0])
+        self.check(self.lib.arl_async_connect(self.ctx, buf))
+        return int(self.lib.arl_async_regions(self.ctx))
+
+    def async_push_pull(self):
+        self.check(self.lib.arl_async_push_pull(self.ctx, self._s()))
+
+    def async_read_central(self, which=0):
+        out = np.zeros(self.n_params, np.float32)
+        self.check(self.lib.arl_async_read_central(self.ctx, int(which), out.ctypes.data_as(C.c_void_p), self.n_params,
+                                                   self._s()))
+        return out
+
     def comm_barrier(self):
         self.check(self.lib.arl_comm_barrier(self.ctx, self._s()))
 

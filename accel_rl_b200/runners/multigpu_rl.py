@@ -77,11 +77,30 @@ class AccelRLSync(AccelRL):
         return "synchronous"
 
 
-class AccelRLAsync(AccelRL):
-    """reference: multigpu_rl.py:18-26 / multigpu_rl_base.py:161-208 — next §8 row (a11)."""
+class AccelRLAsync(AccelRLSync):
+    """reference: multigpu_rl.py:18-26 / multigpu_rl_base.py:161-208.  Same launch as AccelRLSync (one process per
+    GPU, rank r seeds with seed + 100*r, rank 0's initial parameters broadcast) but no collective on the data path:
+    every learner pushes its locally clipped gradient into the central (params, m, v) store in rank 0's HBM under
+    the chunk locks and pulls the new parameters (optimizers/async_/base.py)."""
 
-    def __init__(self, **kwargs):
-        raise NotImplementedError("asynchronous multi-learner runner is not built yet (SURVEY.md §8 row a11)")
+    def init_comm(self):
+        eng = self.policy.engine
+        if self.n_runners > 1:
+            dist.broadcast(eng.params, src=0)      # par_objs.dict["initial_param_values"] (multigpu_rl_base.py:171,189)
+            eng.pack()
+            torch.cuda.synchronize()
+
+        def exchange(handle):
+            if self.n_runners == 1:
+                return [handle]
+            out = [None] * self.n_runners
+            dist.all_gather_object(out, handle)
+            return out
+
+        self.algo.optimizer.init_comm(self.rank, self.n_runners, dict(exchange=exchange))
+        self._initial_param_vector = self.policy.get_param_values()
+        if self.n_runners > 1:
+            dist.barrier()
 
     @property
     def parallelism_tag(self):

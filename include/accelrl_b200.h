@@ -151,6 +151,18 @@ int arl_comm_connect(arl_ctx* ctx, const uint8_t* all_handles);
 int arl_sync_allreduce_update(arl_ctx* ctx, void* stream);
 int arl_comm_barrier(arl_ctx* ctx, void* stream);
 
+/* ---- asynchronous data parallel ------------------------------------------------------------------
+ * replaces BaseAsyncOptimizer / chunked_updates (accel_rl/optimizers/async/base.py:11-104,
+ * chunked_updates.py:53-120): a central (params, m, v) store in rank 0's HBM, shared by a CUDA IPC handle, updated
+ * under chunk-granular locks with each learner's LOCALLY clipped gradient; the learner then holds the new central
+ * parameters.  local_init: rank 0 allocates the store from its bound parameters and returns the 64-byte handle
+ * (zeros on the other ranks); connect: every rank passes rank 0's handle. */
+int arl_async_local_init(arl_ctx* ctx, int rank, int world, int n_update_chunks, uint8_t* handle_out);
+int arl_async_connect(arl_ctx* ctx, const uint8_t* rank0_handle);
+int arl_async_regions(arl_ctx* ctx);   /* lock regions the chunks were subdivided into */
+int arl_async_push_pull(arl_ctx* ctx, void* stream);
+int arl_async_read_central(arl_ctx* ctx, int which, float* host_out, long n, void* stream);
+
 /* ---- diagnostics / tests ---------------------------------------------------------------------- */
 /* intermediate activations of the last forward (bf16 -> fp32 copies into host-visible device buffers) */
 int arl_debug_activation(arl_ctx* ctx, int layer, float* out, long cap, long* n, void* stream);

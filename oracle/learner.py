@@ -43,3 +43,25 @@ def optimize_policy(flat, opt, buf, spec, n_actions, horizon, algo, rng, discoun
         flat = opt.step(flat, g, lr_mult)
         losses.append(loss); norms.append(norm)
     return flat, losses, norms, dict(advantages=adv, returns=ret, valids=valids, values=values, last_values=last_values)
+
+
+def async_push(central, grad, kind, t_local, lr, clip=None, beta1=0.9, beta2=0.999, epsilon=None, rho=0.9):
+    """One asynchronous learner update against the central store (test oracle).
+
+    reference: optimizers/async/async_a2c_optimizer.py:43-52,96-100 (local clip, push every chunk, copy back) and
+    optimizers/async/chunked_updates.py:53-76 (rmsprop chunk), :79-120 (adam chunk, per-process t).
+    central: dict(p=, m=, v=) float32 arrays updated in place; returns (new local params, pre-clip grad norm)."""
+    g, norm = onet.total_norm_clip(np.asarray(grad, np.float32), clip)
+    g = g.astype(np.float32)
+    f = np.float32
+    if kind == "adam":
+        eps = f(1e-8 if epsilon is None else epsilon)
+        a_t = f(lr * np.sqrt(1.0 - float(beta2) ** t_local) / (1.0 - float(beta1) ** t_local))
+        central["m"][:] = f(beta1) * central["m"] + (f(1) - f(beta1)) * g
+        central["v"][:] = f(beta2) * central["v"] + (f(1) - f(beta2)) * g * g
+        central["p"][:] = central["p"] - a_t * central["m"] / (np.sqrt(central["v"]) + eps)
+    else:
+        eps = f(1e-6 if epsilon is None else epsilon)
+        central["v"][:] = f(rho) * central["v"] + (f(1) - f(rho)) * g * g
+        central["p"][:] = central["p"] - f(lr) * g / np.sqrt(central["v"] + eps)
+    return central["p"].copy(), norm

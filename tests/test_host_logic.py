@@ -161,3 +161,21 @@ def test_logger_tabular_and_csv(tmp_path):
     txt = open(str(tmp_path / "progress.csv")).read()
     assert "Iteration" in txt and "GradNormStd" in txt
     logger.configure(None)
+
+
+def test_async_optimizer_argument_checks():
+    """async_a2c_optimizer.py:26-32: unknown update names are rejected; the tag is 'asynchronous'"""
+    import pytest
+    from accel_rl_b200.algos import mA3C, mAPPO
+    from accel_rl_b200.optimizers.async_.async_a2c_optimizer import AsyncA2cOptimizer
+    from accel_rl_b200.optimizers.async_.async_ppo_optimizer import AsyncPpoOptimizer
+    with pytest.raises(ValueError):
+        AsyncA2cOptimizer(learning_rate=1e-3, update_method_name="sgd", n_update_chunks=3)
+    with pytest.raises(ValueError):
+        AsyncA2cOptimizer(learning_rate=1e-3, update_method_name="sgd", n_update_chunks=1)
+    opt = AsyncA2cOptimizer(learning_rate=1e-3, update_method_name="adam", n_update_chunks=4)
+    assert opt.parallelism_tag == "asynchronous" and opt.n_update_chunks == 4
+    assert mA3C().optimizer.n_update_chunks == 3 and mA3C().optimizer.parallelism_tag == "asynchronous"
+    ppo = mAPPO().optimizer
+    assert isinstance(ppo, AsyncPpoOptimizer) and ppo.parallelism_tag == "asynchronous"
+    assert ppo.max_rows(10 ** 6) == 512
