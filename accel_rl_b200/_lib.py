@@ -95,6 +95,7 @@ SIGNATURES = {
     "arl_policy_forward": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, _P, _P, _P]),
     "arl_sample_actions": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "arl_frame_update": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
+    "arl_frame_update_rgb": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "arl_sampler_configure": (C.c_int, [_P, C.POINTER(SamplerCfg)]),
     "arl_sampler_reset": (C.c_int, [_P, _P]),
     "arl_rollout_begin": (C.c_int, [_P, _P]),

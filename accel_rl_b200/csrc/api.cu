@@ -1270,6 +1270,20 @@ int arl_frame_update(arl_ctx* c, const uint8_t* raw_a, const uint8_t* raw_b, con
   return 0;
 }
 
+/* north-star frame mode: RGB (210,160,3) frame pairs -> (planes,84,84) u8 stack + bf16 copy (frame_rgb_kernel) */
+int arl_frame_update_rgb(arl_ctx* c, const uint8_t* raw_a, const uint8_t* raw_b, const uint8_t* reset_mask, uint8_t* stack,
+                         uint16_t* stack_bf16, int n, int planes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n <= 0) return 0;
+  if (planes < 1 || planes > 8) ARL_FAIL(c, "planes must be in [1,8]");
+  if (!raw_b || !stack) ARL_FAIL(c, "raw_b and stack are required");
+  frame_rgb_kernel<<<n * (kNsH / 2), 192, 0, st>>>(raw_a, raw_b, reset_mask, stack, reinterpret_cast<__nv_bfloat16*>(stack_bf16),
+                                                  n, planes);
+  c->launches++;
+  ARL_CHECK(c, cudaGetLastError());
+  return 0;
+}
+
 int arl_sampler_configure(arl_ctx* c, const arl_sampler_cfg* cfg) {
   c->sc = *cfg;
   const int B = cfg->n_envs, T = cfg->horizon;

@@ -433,27 +433,31 @@ ARL_DEVINL void rowgemm_body(ALoad& aload, const WeightSrc& bsrc, const RowEpi& 
       }
       tc_fence_before();
     }
-  } else if (tid == kProducerThreads) {
-    // ===================== MMA issuer (one thread) =====================
+  } else {
+    // ===================== MMA issuer (converged warp, one elected lane issues: see common.cuh elect_one) ==========
     constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, B_NMAJOR ? 1 : 0);
+    const uint32_t tmem_u = make_uniform(tmem_base);
     for (int it = 0; it < niter; ++it) {
       const int s = it % Cfg::STAGES;
       const uint32_t ph = (it / Cfg::STAGES) & 1;
       mbar_wait(full_bar(s), ph, 3);
       fence_proxy_async();                 // cp.async (generic-proxy) writes -> tcgen05 (async-proxy) reads
       tc_fence_after();
-      const uint32_t a_tile = smem_base + s * Cfg::STAGE_BYTES;
-      const uint32_t b_tile = a_tile + Cfg::A_BYTES;
+      if (elect_one()) {
+        const uint32_t a_tile = smem_base + s * Cfg::STAGE_BYTES;
+        const uint32_t b_tile = a_tile + Cfg::A_BYTES;
 #pragma unroll
-      for (int k = 0; k < kBK / 16; ++k) {
-        uint64_t adesc = make_smem_desc(a_tile + k * 32, 16, 1024, 2);
-        uint64_t bdesc = B_NMAJOR ? make_smem_desc(b_tile + k * 2048, 8192, 1024, 2)
-                                  : make_smem_desc(b_tile + k * 32, 16, 1024, 2);
-        umma_bf16(tmem_base, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < kBK / 16; ++k) {
+          uint64_t adesc = make_smem_desc(a_tile + k * 32, 16, 1024, 2);
+          uint64_t bdesc = B_NMAJOR ? make_smem_desc(b_tile + k * 2048, 8192, 1024, 2)
+                                    : make_smem_desc(b_tile + k * 32, 16, 1024, 2);
+          umma_bf16(tmem_u, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));
+        if (it == niter - 1) umma_commit(tmem_full_bar);
       }
-      umma_commit(empty_bar(s));
+      __syncwarp();
     }
-    if (niter > 0) umma_commit(tmem_full_bar);
   }
   __syncthreads();
   if (warp == kProducerWarps) {
@@ -858,34 +862,39 @@ __global__ void __launch_bounds__(kWgradThreads) wgrad_kernel(ALoad64 aload, con
       }
     }
     tc_fence_before();
-  } else if (tid == kWgradProducerWarps * 32) {
+  } else if (warp == kWgradProducerWarps) {
+    // MMA issuer: converged warp, one elected lane issues (see common.cuh elect_one)
     constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
     constexpr uint32_t b_layout = swz_layout_type(Cfg::ROWB);
     constexpr uint32_t b_sbo = 8 * Cfg::ROWB;
     constexpr uint32_t b_kstep = 16 * Cfg::ROWB;
+    const uint32_t tmem_u = make_uniform(tmem_base);
     for (int it = 0; it < niter; ++it) {
       const int s = it % Cfg::STAGES;
       const uint32_t ph = (it / Cfg::STAGES) & 1;
       mbar_wait(full_bar(s), ph, 6);
       fence_proxy_async();
       tc_fence_after();
-      const uint32_t a_tile = smem_base + s * Cfg::STAGE_BYTES;
-      const uint32_t b_tile = a_tile + Cfg::A_BYTES;
+      if (elect_one()) {
+        const uint32_t a_tile = smem_base + s * Cfg::STAGE_BYTES;
+        const uint32_t b_tile = a_tile + Cfg::A_BYTES;
 #pragma unroll 1
-      for (int mt = 0; mt < MT; ++mt) {
-        // a missing second atom (odd atom count) is left unfilled: its D rows are never stored
-        if (mt * 2 >= natoms) break;
-        const uint32_t a0 = a_tile + (mt * 2) * 8192;
+        for (int mt = 0; mt < MT; ++mt) {
+          // a missing second atom (odd atom count) is left unfilled: its D rows are never stored
+          if (mt * 2 >= natoms) break;
+          const uint32_t a0 = a_tile + (mt * 2) * 8192;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          uint64_t adesc = make_smem_desc(a0 + k * 2048, 8192, 1024, 2);
-          uint64_t bdesc = make_smem_desc(b_tile + k * b_kstep, 8192, b_sbo, b_layout);
-          umma_bf16(tmem_base + mt * BN, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            uint64_t adesc = make_smem_desc(a0 + k * 2048, 8192, 1024, 2);
+            uint64_t bdesc = make_smem_desc(b_tile + k * b_kstep, 8192, b_sbo, b_layout);
+            umma_bf16(tmem_u + mt * BN, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
         }
+        umma_commit(empty_bar(s));
+        if (it == niter - 1) umma_commit(tmem_full_bar);
       }
-      umma_commit(empty_bar(s));
+      __syncwarp();
     }
-    if (niter > 0) umma_commit(tmem_full_bar);
   }
   __syncthreads();   // every MMA has completed (group 0 waited on tmem_full): stage memory is free
   if (warp == kWgradProducerWarps) {

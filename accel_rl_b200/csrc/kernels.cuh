@@ -353,6 +353,80 @@ __global__ void __launch_bounds__(256) frame_kernel(const uint8_t* __restrict__ 
   }
 }
 
+// ===========================================================================
+// North-star frame mode (BASELINE.json north_star; NOT in the reference, whose emulator hands out grayscale):
+//   two raw RGB frames (210,160,3) u8 -> per-channel max -> gray -> 84x84 area resize -> 4-plane stack (u8, oldest
+//   first) + the same stack as bf16 for the network, all in ONE pass.  Builder-defined arithmetic (integer, exact;
+//   frozen in oracle/frame.py:rgb_*):
+//     gray  Y = (77 R + 150 G + 29 B + 128) >> 8            (NTSC luma, 8-bit fixed point, weights sum to 256)
+//     resize: exact area average.  Rows: 210/84 = 5/2 -> output row y covers half-rows [5y, 5y+5) (input row i covers
+//             [2i, 2i+2)); columns: 160/84 = 40/21 -> output column x covers [40x, 40x+40) in units of 1/21 column (input
+//             column j covers [21j, 21j+21)).  out = (sum wy*wx*Y + 100) / 200.
+// One block = one env x two output rows = five input rows: the 2 x 5 x 480 raw bytes are read once with 16-byte loads
+// (max of the two frames in registers), gray values go to shared memory, 168 threads produce the 2 x 84 outputs and
+// shift their own pixel of the stack.  Algorithmic traffic: 2 x 100 800 B read + 7 056 B new plane.
+// ===========================================================================
+constexpr int kRgbH = 210, kRgbW = 160, kNsH = 84, kNsW = 84;
+
+__global__ void __launch_bounds__(192) frame_rgb_kernel(const uint8_t* __restrict__ raw_a, const uint8_t* __restrict__ raw_b,
+                                                        const uint8_t* __restrict__ reset_mask, uint8_t* __restrict__ stack,
+                                                        __nv_bfloat16* __restrict__ stack16, int n, int planes) {
+  __shared__ __align__(16) uint8_t s_rgb[5 * kRgbW * 3];
+  __shared__ uint8_t s_gray[5 * kRgbW];
+  const int e = blockIdx.x / (kNsH / 2);
+  const int pair = blockIdx.x - e * (kNsH / 2);
+  const int tid = threadIdx.x;
+  const bool rs = reset_mask && reset_mask[e];
+  const long fbytes = (long)kRgbH * kRgbW * 3;
+  const uint8_t* fa = (raw_a && !rs) ? raw_a + (long)e * fbytes + (long)pair * 5 * kRgbW * 3 : nullptr;
+  const uint8_t* fb = raw_b + (long)e * fbytes + (long)pair * 5 * kRgbW * 3;
+  // 5 rows x 480 bytes = 150 16-byte words per frame
+  if (tid < 150) {
+    uint4 b = __ldg(reinterpret_cast<const uint4*>(fb) + tid);
+    if (fa) {
+      uint4 a = __ldg(reinterpret_cast<const uint4*>(fa) + tid);
+      b.x = __vmaxu4(a.x, b.x); b.y = __vmaxu4(a.y, b.y); b.z = __vmaxu4(a.z, b.z); b.w = __vmaxu4(a.w, b.w);
+    }
+    reinterpret_cast<uint4*>(s_rgb)[tid] = b;
+  }
+  __syncthreads();
+  for (int i = tid; i < 5 * kRgbW; i += 192) {
+    const uint8_t* px = s_rgb + i * 3;
+    s_gray[i] = (uint8_t)((77u * px[0] + 150u * px[1] + 29u * px[2] + 128u) >> 8);
+  }
+  __syncthreads();
+  if (tid >= 2 * kNsW) return;
+  const int oy = tid / kNsW, ox = tid - oy * kNsW;
+  // rows: oy == 0 -> input rows 0,1,2 with weights 2,2,1; oy == 1 -> rows 2,3,4 with weights 1,2,2
+  const int r0 = oy * 2;
+  const int wy0 = oy ? 1 : 2, wy1 = 2, wy2 = oy ? 2 : 1;
+  // columns: [40 ox, 40 ox + 40) over input columns of width 21
+  const int c_lo = 40 * ox, c_hi = c_lo + 40;
+  const int j0 = c_lo / 21;
+  unsigned acc = 0;
+#pragma unroll
+  for (int dj = 0; dj < 3; ++dj) {
+    const int j = j0 + dj;
+    const int lo = max(c_lo, 21 * j), hi = min(c_hi, 21 * j + 21);
+    const int wx = hi - lo;
+    if (wx > 0 && j < kRgbW)
+      acc += (unsigned)wx * (wy0 * s_gray[r0 * kRgbW + j] + wy1 * s_gray[(r0 + 1) * kRgbW + j] + wy2 * s_gray[(r0 + 2) * kRgbW + j]);
+  }
+  const uint8_t newest = (uint8_t)((acc + 100u) / 200u);
+  const int Y = pair * 2 + oy;
+  const int pix = Y * kNsW + ox;
+  const int plane_px = kNsH * kNsW;
+  uint8_t* cur = stack + (long)e * planes * plane_px;
+  __nv_bfloat16* cur16 = stack16 ? stack16 + (long)e * planes * plane_px : nullptr;
+  for (int p = 0; p < planes - 1; ++p) {
+    const uint8_t v = rs ? (uint8_t)0 : cur[(p + 1) * plane_px + pix];
+    cur[p * plane_px + pix] = v;
+    if (cur16) cur16[p * plane_px + pix] = __float2bfloat16_rn((float)v);
+  }
+  cur[(planes - 1) * plane_px + pix] = newest;
+  if (cur16) cur16[(planes - 1) * plane_px + pix] = __float2bfloat16_rn((float)newest);
+}
+
 // standalone frame update (arl_frame_update): item i's raw frames are raw_a[i], raw_b[i]
 __global__ void make_cmd_kernel(FrameCmd* cmd, const uint8_t* reset_mask, int n, int has_a) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -111,6 +111,12 @@ class Engine(object):
         self.check(self.lib.arl_frame_update(self.ctx, L.ptr(raw_a), L.ptr(raw_b), L.ptr(reset_mask), L.ptr(stack), n,
                                              planes, self._s()))
 
+    def frame_update_rgb(self, raw_a, raw_b, reset_mask, stack, stack_bf16=None):
+        """north-star frame mode: RGB (n,210,160,3) pairs -> (n,planes,84,84) u8 stack (+ bf16 copy)"""
+        n, planes = int(stack.shape[0]), int(stack.shape[1])
+        self.check(self.lib.arl_frame_update_rgb(self.ctx, L.ptr(raw_a), L.ptr(raw_b), L.ptr(reset_mask), L.ptr(stack),
+                                                 L.ptr(stack_bf16), n, planes, self._s()))
+
     # ---- sampler -----------------------------------------------------------------------------
     def sampler_configure(self, cfg, keep):
         self._keep["sampler"] = keep

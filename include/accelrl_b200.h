@@ -100,6 +100,12 @@ int arl_sample_actions(arl_ctx* ctx, const float* prob, const double* uniforms, 
  * stack [n][planes][104][80] updated in place. */
 int arl_frame_update(arl_ctx* ctx, const uint8_t* raw_a, const uint8_t* raw_b, const uint8_t* reset_mask, uint8_t* stack,
                      int n, int planes, void* stream);
+/* North-star frame mode (BASELINE.json north_star; not in the reference, whose emulator returns grayscale at
+ * envs/atari_env.py:147-149): raw RGB pairs [n][210][160][3] u8 -> per-channel max -> gray (77R+150G+29B+128)>>8 ->
+ * exact-area 84x84 resize -> stack [n][planes][84][84] u8 shifted oldest->newest (+ optional bf16 copy, same shape).
+ * raw_a may be NULL (single frame); reset_mask[i] != 0 zeroes item i's stack and ignores raw_a (atari_env.py:159-163). */
+int arl_frame_update_rgb(arl_ctx* ctx, const uint8_t* raw_a, const uint8_t* raw_b, const uint8_t* reset_mask, uint8_t* stack,
+                         uint16_t* stack_bf16, int n, int planes, void* stream);
 
 /* ---- sampler: ActsrvAltOvrlpSampler.obtain_samples (sampler/.../overlap/sampler.py:97-151) --- */
 int arl_sampler_configure(arl_ctx* ctx, const arl_sampler_cfg* cfg);

@@ -41,6 +41,30 @@ def test_frame_kernel_bit_exact(pol1, golden_dir):
     assert np.array_equal(t2n(d), oframe.update_obs_batch(st, None, b, None))
 
 
+def test_frame_rgb_kernel_bit_exact(pol1, golden_dir):
+    """north-star mode (RGB -> gray -> 84x84 area resize -> stack + bf16 copy): CUDA == oracle, bit for bit"""
+    eng = pol1[0].engine
+    g = np.load(golden_dir + "/frames_rgb.npz")
+    n = g["raw_a"].shape[1]
+    d = torch.zeros(n, 4, 84, 84, dtype=torch.uint8, device="cuda")
+    d16 = torch.zeros(n, 4, 84, 84, dtype=torch.bfloat16, device="cuda")
+    for s in range(g["raw_a"].shape[0]):
+        eng.frame_update_rgb(torch.tensor(g["raw_a"][s]).cuda(), torch.tensor(g["raw_b"][s]).cuda(),
+                             torch.tensor(g["reset"][s]).cuda(), d, d16)
+        assert np.array_equal(t2n(d), g["stacks"][s])
+        assert np.array_equal(t2n(d16.float()), g["stacks"][s].astype(np.float32))
+    # random frames, ragged batch, single-frame and 1-plane variants against the oracle itself
+    rng = np.random.RandomState(3)
+    for n, planes, with_a in ((37, 4, True), (5, 1, True), (9, 4, False)):
+        a = rng.randint(0, 256, (n, 210, 160, 3), dtype=np.uint8)
+        b = rng.randint(0, 256, (n, 210, 160, 3), dtype=np.uint8)
+        st = rng.randint(0, 256, (n, planes, 84, 84), dtype=np.uint8)
+        rs = (rng.rand(n) < 0.3).astype(np.uint8)
+        d = torch.tensor(st).cuda()
+        eng.frame_update_rgb(torch.tensor(a).cuda() if with_a else None, torch.tensor(b).cuda(), torch.tensor(rs).cuda(), d)
+        assert np.array_equal(t2n(d), oframe.rgb_update_obs_batch(st, a if with_a else None, b, rs))
+
+
 @pytest.mark.parametrize("A", [4, 6, 18])
 def test_action_sampling_bit_exact(pol1, golden_dir, A):
     eng = pol1[0].engine

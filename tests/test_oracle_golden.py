@@ -111,3 +111,20 @@ def test_net_param_count_matches_reference_comment():
     # accel_rl/policies/atari_cnn_specs.py:22 "3.6M params", :10 "900k params"
     assert onet.n_params(onet.CNN_SPECS[1], (4, 104, 80), 4) == 3620005
     assert onet.n_params(onet.CNN_SPECS[0], (4, 104, 80), 4) == 898613
+
+
+def test_rgb_frame_oracle_known_answers(golden_dir):
+    """north-star RGB mode (builder-defined): the oracle reproduces its committed known-answer fixture, the area
+    weights partition every output cell exactly, and flat frames stay flat"""
+    from oracle import frame as oframe
+    g = np.load(golden_dir + "/frames_rgb.npz")
+    stack = np.zeros_like(g["stacks"][0])
+    for s in range(g["raw_a"].shape[0]):
+        stack = oframe.rgb_update_obs_batch(stack, g["raw_a"][s], g["raw_b"][s], g["reset"][s])
+        assert np.array_equal(stack, g["stacks"][s])
+    assert (oframe._WY.sum(1) == 5).all() and (oframe._WX.sum(1) == 40).all()
+    assert (oframe._WY.sum(0) == 2).all() and (oframe._WX.sum(0) == 21).all()
+    for v in (0, 1, 127, 255):
+        flat = np.full((210, 160, 3), v, np.uint8)
+        assert (oframe.rgb_downsample(oframe.rgb_to_gray(flat)) == v).all()
+    assert oframe.rgb_to_gray(np.array([[255, 0, 0], [0, 255, 0], [0, 0, 255]], np.uint8)).tolist() == [77, 149, 29]   # (w*255 + 128) >> 8
