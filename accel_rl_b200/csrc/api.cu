@@ -1277,7 +1277,7 @@ int arl_frame_update_rgb(arl_ctx* c, const uint8_t* raw_a, const uint8_t* raw_b,
   if (n <= 0) return 0;
   if (planes < 1 || planes > 8) ARL_FAIL(c, "planes must be in [1,8]");
   if (!raw_b || !stack) ARL_FAIL(c, "raw_b and stack are required");
-  frame_rgb_kernel<<<n * (kNsH / 2), 192, 0, st>>>(raw_a, raw_b, reset_mask, stack, reinterpret_cast<__nv_bfloat16*>(stack_bf16),
+  frame_rgb_kernel<<<n * (kNsH / kRgbRows), kRgbThreads, 0, st>>>(raw_a, raw_b, reset_mask, stack, reinterpret_cast<__nv_bfloat16*>(stack_bf16),
                                                   n, planes);
   c->launches++;
   ARL_CHECK(c, cudaGetLastError());

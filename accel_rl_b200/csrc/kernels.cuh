@@ -367,64 +367,76 @@ __global__ void __launch_bounds__(256) frame_kernel(const uint8_t* __restrict__ 
 // shift their own pixel of the stack.  Algorithmic traffic: 2 x 100 800 B read + 7 056 B new plane.
 // ===========================================================================
 constexpr int kRgbH = 210, kRgbW = 160, kNsH = 84, kNsW = 84;
+constexpr int kRgbRows = 4;                      // output rows per block (= 10 input rows)
+constexpr int kRgbThreads = 256;
 
-__global__ void __launch_bounds__(192) frame_rgb_kernel(const uint8_t* __restrict__ raw_a, const uint8_t* __restrict__ raw_b,
-                                                        const uint8_t* __restrict__ reset_mask, uint8_t* __restrict__ stack,
-                                                        __nv_bfloat16* __restrict__ stack16, int n, int planes) {
-  __shared__ __align__(16) uint8_t s_rgb[5 * kRgbW * 3];
-  __shared__ uint8_t s_gray[5 * kRgbW];
-  const int e = blockIdx.x / (kNsH / 2);
-  const int pair = blockIdx.x - e * (kNsH / 2);
+__global__ void __launch_bounds__(kRgbThreads) frame_rgb_kernel(const uint8_t* __restrict__ raw_a,
+                                                                const uint8_t* __restrict__ raw_b,
+                                                                const uint8_t* __restrict__ reset_mask,
+                                                                uint8_t* __restrict__ stack, __nv_bfloat16* __restrict__ stack16,
+                                                                int n, int planes) {
+  constexpr int IN_ROWS = kRgbRows * 5 / 2;      // 10
+  constexpr int WORDS = IN_ROWS * kRgbW * 3 / 16;  // 300 16-byte words per frame
+  __shared__ __align__(16) uint8_t s_rgb[IN_ROWS * kRgbW * 3];
+  __shared__ uint8_t s_gray[IN_ROWS * kRgbW];
+  __shared__ __align__(4) uint8_t s_out[kRgbRows * kNsW];
+  constexpr int GROUPS = kNsH / kRgbRows;        // 21 row groups per env
+  const int e = blockIdx.x / GROUPS;
+  const int grp = blockIdx.x - e * GROUPS;
   const int tid = threadIdx.x;
   const bool rs = reset_mask && reset_mask[e];
   const long fbytes = (long)kRgbH * kRgbW * 3;
-  const uint8_t* fa = (raw_a && !rs) ? raw_a + (long)e * fbytes + (long)pair * 5 * kRgbW * 3 : nullptr;
-  const uint8_t* fb = raw_b + (long)e * fbytes + (long)pair * 5 * kRgbW * 3;
-  // 5 rows x 480 bytes = 150 16-byte words per frame
-  if (tid < 150) {
-    uint4 b = __ldg(reinterpret_cast<const uint4*>(fb) + tid);
+  const long roff = (long)grp * IN_ROWS * kRgbW * 3;
+  const uint8_t* fa = (raw_a && !rs) ? raw_a + (long)e * fbytes + roff : nullptr;
+  const uint8_t* fb = raw_b + (long)e * fbytes + roff;
+  for (int i = tid; i < WORDS; i += kRgbThreads) {
+    uint4 b = __ldg(reinterpret_cast<const uint4*>(fb) + i);
     if (fa) {
-      uint4 a = __ldg(reinterpret_cast<const uint4*>(fa) + tid);
+      uint4 a = __ldg(reinterpret_cast<const uint4*>(fa) + i);
       b.x = __vmaxu4(a.x, b.x); b.y = __vmaxu4(a.y, b.y); b.z = __vmaxu4(a.z, b.z); b.w = __vmaxu4(a.w, b.w);
     }
-    reinterpret_cast<uint4*>(s_rgb)[tid] = b;
+    reinterpret_cast<uint4*>(s_rgb)[i] = b;
   }
   __syncthreads();
-  for (int i = tid; i < 5 * kRgbW; i += 192) {
+  for (int i = tid; i < IN_ROWS * kRgbW; i += kRgbThreads) {
     const uint8_t* px = s_rgb + i * 3;
     s_gray[i] = (uint8_t)((77u * px[0] + 150u * px[1] + 29u * px[2] + 128u) >> 8);
   }
   __syncthreads();
-  if (tid >= 2 * kNsW) return;
-  const int oy = tid / kNsW, ox = tid - oy * kNsW;
-  // rows: oy == 0 -> input rows 0,1,2 with weights 2,2,1; oy == 1 -> rows 2,3,4 with weights 1,2,2
-  const int r0 = oy * 2;
-  const int wy0 = oy ? 1 : 2, wy1 = 2, wy2 = oy ? 2 : 1;
-  // columns: [40 ox, 40 ox + 40) over input columns of width 21
-  const int c_lo = 40 * ox, c_hi = c_lo + 40;
-  const int j0 = c_lo / 21;
-  unsigned acc = 0;
+  for (int o = tid; o < kRgbRows * kNsW; o += kRgbThreads) {
+    const int oy = o / kNsW, ox = o - oy * kNsW;
+    // output rows come in pairs over 5 input rows: even row -> rows 0,1,2 (weights 2,2,1), odd row -> rows 2,3,4 (1,2,2)
+    const int odd = oy & 1;
+    const int r0 = (oy >> 1) * 5 + odd * 2;
+    const int wy0 = odd ? 1 : 2, wy2 = odd ? 2 : 1;
+    const int c_lo = 40 * ox, c_hi = c_lo + 40;
+    const int j0 = c_lo / 21;
+    unsigned acc = 0;
 #pragma unroll
-  for (int dj = 0; dj < 3; ++dj) {
-    const int j = j0 + dj;
-    const int lo = max(c_lo, 21 * j), hi = min(c_hi, 21 * j + 21);
-    const int wx = hi - lo;
-    if (wx > 0 && j < kRgbW)
-      acc += (unsigned)wx * (wy0 * s_gray[r0 * kRgbW + j] + wy1 * s_gray[(r0 + 1) * kRgbW + j] + wy2 * s_gray[(r0 + 2) * kRgbW + j]);
+    for (int dj = 0; dj < 3; ++dj) {
+      const int j = j0 + dj;
+      const int wx = min(c_hi, 21 * j + 21) - max(c_lo, 21 * j);
+      if (wx > 0 && j < kRgbW)
+        acc += (unsigned)wx * (wy0 * s_gray[r0 * kRgbW + j] + 2 * s_gray[(r0 + 1) * kRgbW + j] + wy2 * s_gray[(r0 + 2) * kRgbW + j]);
+    }
+    s_out[o] = (uint8_t)((acc + 100u) / 200u);
   }
-  const uint8_t newest = (uint8_t)((acc + 100u) / 200u);
-  const int Y = pair * 2 + oy;
-  const int pix = Y * kNsW + ox;
+  __syncthreads();
+  // stack shift + stores, 4 pixels per thread (84 = 21 words per row)
+  constexpr int WPR = kNsW / 4;
+  if (tid >= kRgbRows * WPR) return;
+  const int oy = tid / WPR, xw = tid - oy * WPR;
+  const int pix = (grp * kRgbRows + oy) * kNsW + xw * 4;
   const int plane_px = kNsH * kNsW;
-  uint8_t* cur = stack + (long)e * planes * plane_px;
-  __nv_bfloat16* cur16 = stack16 ? stack16 + (long)e * planes * plane_px : nullptr;
-  for (int p = 0; p < planes - 1; ++p) {
-    const uint8_t v = rs ? (uint8_t)0 : cur[(p + 1) * plane_px + pix];
-    cur[p * plane_px + pix] = v;
-    if (cur16) cur16[p * plane_px + pix] = __float2bfloat16_rn((float)v);
+  uint8_t* cur = stack + (long)e * planes * plane_px + pix;
+  __nv_bfloat16* cur16 = stack16 ? stack16 + (long)e * planes * plane_px + pix : nullptr;
+  const uint32_t newest = *reinterpret_cast<const uint32_t*>(s_out + oy * kNsW + xw * 4);
+  for (int p = 0; p < planes; ++p) {
+    uint32_t v = newest;
+    if (p < planes - 1) v = rs ? 0u : *reinterpret_cast<const uint32_t*>(cur + (p + 1) * plane_px);
+    *reinterpret_cast<uint32_t*>(cur + p * plane_px) = v;
+    if (cur16) *reinterpret_cast<uint2*>(cur16 + p * plane_px) = u8x4_to_bf16x4(v);
   }
-  cur[(planes - 1) * plane_px + pix] = newest;
-  if (cur16) cur16[(planes - 1) * plane_px + pix] = __float2bfloat16_rn((float)newest);
 }
 
 // standalone frame update (arl_frame_update): item i's raw frames are raw_a[i], raw_b[i]

@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-steps", type=int, default=8, help="rollout steps in the bounded CPU sample")
+    ap.add_argument("--workload", default="ppo", choices=["ppo", "frame_sweep"],
+                    help="ppo: the headline metric (default); frame_sweep: BASELINE configs[2] frame-kernel HBM GB/s sweep")
     return ap.parse_args()
 
 
@@ -353,6 +355,58 @@ def cpu_port(args, steps=1, warmup=0):
             "seconds_per_sample": round(samp + learn, 2)}
 
 
+def run_frame_sweep(args):
+    """BASELINE.json configs[2]: frame-kernel achieved HBM GB/s over env counts, reference mode (2 x 210x160 gray ->
+    104x80 stack, the rollout's frame_kernel incl. its bf16 mirror) and north-star mode (2 x 210x160x3 RGB -> 84x84).
+    Algorithmic bytes per env-step: 75 520 B / 208 656 B.  Prints one JSON line."""
+    import numpy as np
+    import torch
+    from accel_rl_b200.policies import AtariCnnPolicy, cnn_specs
+    torch.cuda.set_device(0)
+    pk = peaks()
+    out = {"metric": "frame-kernel achieved HBM GB/s", "unit": "GB/s", "peak": pk["hbm"], "peak_source": pk["src"],
+           "bytes_per_env_step": {"reference_mode": 75520, "north_star_rgb_mode": 208656}, "sweep": [], "rgb_sweep": []}
+    for B in (256, 512, 1024, 2048, 4096):
+        a = argparse.Namespace(**vars(args))
+        a.envs, a.horizon, a.minibatch, a.epochs = B, 2, 512, 1
+        runner = build_runner(a, "device", 0, 1)
+        s, _ = runner.sampler.obtain_samples(0)
+        labels, ms = runner.policy.engine.profile_graph(1, None, 0, reps=20)
+        t = float(sum(m for l, m in zip(labels, ms) if l == "frame"))
+        gbs = B * 75520 / (t * 1e-3) / 1e9
+        out["sweep"].append({"envs": B, "us": round(t * 1e3, 2), "gbs": round(gbs, 1), "frac": round(gbs / pk["hbm"], 4)})
+        runner.policy.engine.close()
+        del runner
+        torch.cuda.empty_cache()
+    pol = AtariCnnPolicy(**cnn_specs[1])
+    from accel_rl_b200.envs.atari_env import EnvSpec
+    from accel_rl_b200.spaces import Discrete, UintBox
+    pol.initialize(EnvSpec(UintBox((4, 104, 80)), Discrete(4)))
+    eng = pol.engine
+    for B in (256, 512, 1024, 2048):
+        nset = max(1, int(np.ceil(400e6 / (B * 201600))))      # rotate input sets so reads come from HBM, not L2
+        ra = [torch.randint(0, 256, (B, 210, 160, 3), dtype=torch.uint8, device="cuda") for _ in range(nset)]
+        rb = [torch.randint(0, 256, (B, 210, 160, 3), dtype=torch.uint8, device="cuda") for _ in range(nset)]
+        st = torch.zeros(B, 4, 84, 84, dtype=torch.uint8, device="cuda")
+        st16 = torch.zeros(B, 4, 84, 84, dtype=torch.bfloat16, device="cuda")
+        for i in range(3):
+            eng.frame_update_rgb(ra[i % nset], rb[i % nset], None, st, st16)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        ev0.record()
+        for i in range(reps):
+            eng.frame_update_rgb(ra[i % nset], rb[i % nset], None, st, st16)
+        ev1.record()
+        torch.cuda.synchronize()
+        t = ev0.elapsed_time(ev1) / reps
+        gbs = B * 208656 / (t * 1e-3) / 1e9
+        out["rgb_sweep"].append({"envs": B, "us": round(t * 1e3, 2), "gbs": round(gbs, 1), "frac": round(gbs / pk["hbm"], 4)})
+        del ra, rb
+        torch.cuda.empty_cache()
+    eng.close()
+    _emit(out)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -384,7 +438,9 @@ if __name__ == "__main__":
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)
     a = parse()
-    if a.impl == "reference":
+    if a.workload == "frame_sweep":
+        run_frame_sweep(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)
