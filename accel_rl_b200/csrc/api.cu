@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "gemm_tc.cuh"
 #include "pconv.cuh"
+#include "fcgemm.cuh"
 #include "kernels.cuh"
 #include "comm.cuh"
 
@@ -92,6 +93,12 @@ struct arl_ctx {
   arl_net_cfg cfg{};
   std::vector<ConvLayer> conv;
   std::vector<PcLayer> pc;             // patch-resident conv path (empty: geometry not supported -> gather path)
+  // TMA-fed FC tiles (fcgemm.cuh), used together with the patch-resident conv path (pc_mode == 2)
+  __nv_bfloat16* act_fc = nullptr;     // [HW + 2][fc_rows][64] last conv output, one plane per pixel
+  __nv_bfloat16* wfc_t = nullptr;      // [HW][H/64][64][64] FC weight tiles
+  __nv_bfloat16* dh_t = nullptr;       // [H/64][fc_rows][64]
+  int fc_rows = 0;                     // rows per plane (max_rows rounded up to 128)
+  int dh_n = 0;                        // rows of dh_t that may be non-zero
   cudaStream_t side = nullptr;         // weight-gradient kernels run here, overlapping the data-gradient chain
   cudaEvent_t ev_fork[4] = {nullptr, nullptr, nullptr, nullptr}, ev_join = nullptr;
   bool no_fork = false;                // serialise everything on the caller's stream (per-kernel profiling)
@@ -498,6 +505,8 @@ int launch_pconv_n(arl_ctx* c, int N, const PcParams& p, cudaStream_t st) {
   ARL_FAIL(c, "unsupported pconv tile width N=" + std::to_string(N));
 }
 
+bool fc_tiles_ok(arl_ctx* c);
+
 // how layer l's OUTPUT pixels are stored: into layer l+1's input grid, or dense NHWC rows for the FC layer
 void pc_out_forward(arl_ctx* c, int l, PcOut& o) {
   const ConvLayer& L = c->conv[l];
@@ -507,6 +516,10 @@ void pc_out_forward(arl_ctx* c, int l, PcOut& o) {
     const PcLayer& nx = c->pc[l + 1];
     o.dst = nx.in; o.dst_plane_stride = nx.in_rows * 64;
     o.dS = nx.S; o.dWp = nx.Wp; o.dHc = nx.Hc + 1; o.dpad = nx.pad; o.ds = nx.s; o.swz = 1;
+  } else if (fc_tiles_ok(c)) {
+    // one 64-channel plane per output pixel: the FC tiles bulk-copy [128 images x 64 ch] blocks of it
+    o.dst = c->act_fc; o.swz = 1; o.fc_rows = c->fc_rows; o.dst_plane_stride = 0;
+    o.dS = L.Ho * L.Wo; o.dWp = L.Wo; o.dHc = L.Ho; o.dpad = 0; o.ds = 1;
   } else {
     o.dst = L.act; o.swz = 0; o.dense_ld = L.Cout;
     o.dS = L.Ho * L.Wo; o.dWp = L.Wo; o.dHc = L.Ho; o.dpad = 0; o.ds = 1;
@@ -618,6 +631,7 @@ int pconv_dgrad_layer(arl_ctx* c, int l, int n, cudaStream_t st) {
 // gradient grids must be zero outside the rows the current batch writes
 int pconv_prepare_dy(arl_ctx* c, int n, cudaStream_t st) {
   if (n >= c->pc_dy_n) { c->pc_dy_n = n; return 0; }
+  if (c->dh_t) ARL_CHECK(c, cudaMemsetAsync(c->dh_t, 0, (size_t)(c->H / 64) * c->fc_rows * 64 * sizeof(__nv_bfloat16), st));
   for (size_t l = 0; l < c->pc.size(); ++l) {
     PcLayer& q = c->pc[l];
     size_t elems = (l == 0) ? (size_t)q.dY_rows * q.N : (size_t)(q.N / 64) * q.dY_rows * 64;
@@ -625,6 +639,82 @@ int pconv_prepare_dy(arl_ctx* c, int n, cudaStream_t st) {
   }
   c->pc_dy_n = n;
   return 0;
+}
+
+
+// ---------------------------------------------------------------------------
+// TMA-fed FC tiles (fcgemm.cuh)
+// ---------------------------------------------------------------------------
+template <int KIND, int BN>
+int launch_fc_gemm(arl_ctx* c, const FcParams& p, dim3 grid, cudaStream_t st) {
+  const int smem = p.stages * p.stage_bytes + 1024 + 256;
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    ARL_CHECK(c, cudaFuncSetAttribute(fc_gemm_kernel<KIND, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
+  }
+  ARL_CHECK(c, launch_k(fc_gemm_kernel<KIND, BN>, grid, dim3(kFcThreads), (size_t)smem, st, p));
+  c->launches++;
+  ARL_CHECK(c, cudaGetLastError());
+  return 0;
+}
+
+bool fc_tiles_ok(arl_ctx* c) {
+  return c->pc_mode >= 2 && c->Clast == 64 && (c->HWlast % 6 == 0) && (c->H % 256 == 0) && (c->off_Wfc % 4 == 0);
+}
+
+// forward: split-K partials [S][n][H] from act_fc planes and wfc_t tiles
+int fc_forward_tiles(arl_ctx* c, int n, int* fc_S, cudaStream_t st) {
+  const int NT = c->H / 64, HW = c->HWlast;
+  const int mt = (n + 127) / 128, nt = c->H / 128;
+  int S = std::max(1, std::min(HW, (148 + mt * nt / 2) / (mt * nt)));
+  int kbps = (HW + S - 1) / S;
+  S = (HW + kbps - 1) / kbps;
+  if ((long)S * n * c->H > c->fc_partial_cap) ARL_FAIL(c, "fc partial workspace too small");
+  const long plane = (long)c->fc_rows * 64;
+  FcParams p{};
+  p.ncopies = 2;
+  p.cp[0] = FcCopy{c->act_fc, 128 * 64, 0, (long)kbps * plane, plane, 16384, 0};
+  p.cp[1] = FcCopy{c->wfc_t, 0, 2 * 4096, (long)kbps * NT * 4096, (long)NT * 4096, 16384, 16384};
+  p.a_bytes = 16384; p.stage_bytes = 32768; p.stages = 4;
+  p.niter = kbps; p.niter_total = HW; p.M = n;
+  p.out_f32 = c->fc_partial; p.ldo = c->H;
+  *fc_S = S;
+  return launch_fc_gemm<0, 128>(c, p, dim3(mt, nt, S), st);
+}
+
+// data gradient: dh_t planes x wfc_t tiles -> masked, scattered into the last conv layer's gradient grid
+int fc_dgrad_tiles(arl_ctx* c, int n, cudaStream_t st) {
+  const int NT = c->H / 64, HW = c->HWlast;
+  const ConvLayer& LL = c->conv.back();
+  const PcLayer& q = c->pc.back();
+  constexpr int BN = 192;                                     // three pixel planes per tile: HW/3 x ceil(n/128) CTAs
+  FcParams p{};
+  p.ncopies = 4;
+  p.cp[0] = FcCopy{c->dh_t, 128 * 64, 0, 0, (long)c->fc_rows * 64, 16384, 0};
+  for (int i = 0; i < 3; ++i)
+    p.cp[1 + i] = FcCopy{c->wfc_t + (long)i * NT * 4096, 0, 3L * NT * 4096, 0, 4096, 8192, (uint32_t)(16384 + i * 8192)};
+  p.a_bytes = 16384; p.stage_bytes = 16384 + 3 * 8192; p.stages = 4;
+  p.niter = NT; p.niter_total = NT; p.M = n;
+  p.dy = q.dY; p.act = c->act_fc; p.act_plane = (long)c->fc_rows * 64;
+  p.sc_Wo = LL.Wo; p.sc_S = q.S; p.sc_Wp = q.Wp; p.sc_pad = q.dYpad;
+  return launch_fc_gemm<1, BN>(c, p, dim3((n + 127) / 128, HW / 3, 1), st);
+}
+
+// weight gradient: act_fc^T x dh_t -> fp32 rows of the flat gradient (reference row order)
+int fc_wgrad_tiles(arl_ctx* c, int n, cudaStream_t st) {
+  const int HW = c->HWlast;
+  FcParams p{};
+  p.ncopies = 6;
+  const long aplane = (long)c->fc_rows * 64;
+  p.cp[0] = FcCopy{c->act_fc, 2 * aplane, 0, 0, 64 * 64, 8192, 0};
+  p.cp[1] = FcCopy{c->act_fc + aplane, 2 * aplane, 0, 0, 64 * 64, 8192, 8192};
+  for (int i = 0; i < 4; ++i)
+    p.cp[2 + i] = FcCopy{c->dh_t + (long)i * aplane, 0, 4 * aplane, 0, 64 * 64, 8192, (uint32_t)(16384 + i * 8192)};
+  p.a_bytes = 16384; p.stage_bytes = 16384 + 4 * 8192; p.stages = 4;
+  p.niter = (n + 63) / 64; p.niter_total = p.niter; p.M = n;
+  p.out_f32 = c->grad + c->off_Wfc; p.ldo = c->H; p.fc_HW = HW;
+  return launch_fc_gemm<2, 256>(c, p, dim3(HW / 2, c->H / 256, 1), st);
 }
 
 constexpr int kFcBN = 128;   // FC forward tile width: A is re-read H/kFcBN times, the weights ceil(n/128) times
@@ -669,9 +759,17 @@ int alloc_net(arl_ctx* c) {
     c->bias_partial.push_back(bp);
   }
   if (dev_alloc(c, &c->wfc_bf16, (size_t)c->H * c->Kfc)) return 1;
+  if (c->pc_mode >= 2) {
+    c->fc_rows = roundup(R, 128);
+    if (dev_alloc(c, &c->act_fc, (size_t)(c->HWlast + 2) * c->fc_rows * 64)) return 1;
+    if (dev_alloc(c, &c->wfc_t, (size_t)c->H * c->Kfc)) return 1;
+    if (dev_alloc(c, &c->dh_t, (size_t)(c->H / 64) * c->fc_rows * 64)) return 1;
+  }
   {
+    // LAST job = the bf16 FC operand copy (skipped by pack_weights(with_fc=false) when the update kernel refreshes it)
     PackJob j{};
     j.dst = c->wfc_bf16; j.src_off = c->off_Wfc; j.kind = PK_CAST; j.rows = c->Kfc; j.cols = c->H;
+    if (c->pc_mode >= 2) { j.dst = c->wfc_t; j.kind = PK_FC_TILES; j.HW = c->HWlast; }
     pj.push_back(j);
   }
   // the FC cast job stays LAST (pack_weights(with_fc=false) drops it); pconv packs go before it
@@ -775,6 +873,11 @@ int forward_trunk(arl_ctx* c, const __nv_bfloat16* obs16, const int* idx, const 
     mp.num_kb[0] = L.K / 64;
     if (launch_conv_persist_bn(c, L.Cout, mp, 1, L.K, mp.mtiles[0], st)) return 1;
     prof_mark(c, kFwdName[l], st);
+  }
+  if (pc && fc_tiles_ok(c)) {
+    if (fc_forward_tiles(c, n, fc_S, st)) return 1;
+    prof_mark(c, "fc_fwd", st);
+    return 0;
   }
   int kbps = 0;
   int S = fc_splits(c, n, kbps);
@@ -916,6 +1019,8 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
   p.algo = c->opt.algo; p.clip_param = c->opt.clip_param; p.v_coeff = c->opt.v_loss_coeff;
   p.ent_coeff = c->opt.ent_loss_coeff; p.inv_count = 1.f / (float)n;
   p.h_out = c->h; p.dh_out = c->dh; p.dlogit_out = c->dlogit; p.loss_partial = c->loss_partial;
+  const bool fct = pcb && fc_tiles_ok(c);
+  if (fct) { p.dh_t = c->dh_t; p.dh_rows = c->fc_rows; }
   c->n_loss_rows = n;
   ARL_CHECK(c, launch_k(head_kernel<1>, dim3(n), dim3(kHeadThreads), 0, st, p));
   c->launches++;
@@ -946,7 +1051,10 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
   }
   ConvLayer& LL = c->conv.back();
   // ---- FC wgrad: dW[Kfc][H] = a_last^T dh (direct, permuted rows) ----
-  {
+  if (fct) {
+    if (fc_wgrad_tiles(c, n, ws)) return 1;
+    prof_mark(c, "fc_wgrad", ws);
+  } else {
     DenseLoader<64> a{};
     a.src = LL.act; a.ld = c->Kfc; a.nrows = n;
     WgradEpi e{};
@@ -957,7 +1065,10 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
     prof_mark(c, "fc_wgrad", ws);
   }
   // ---- FC dgrad: da_last[n][Kfc] = dh Wfc^T, masked by a_last > 0 ----
-  {
+  if (fct) {
+    if (fc_dgrad_tiles(c, n, st)) return 1;
+    prof_mark(c, "fc_dgrad", st);
+  } else {
     DenseLoader<128> a{};
     a.src = c->dh; a.ld = c->H; a.nrows = n;
     WeightSrc w{c->wfc_bf16, (long)c->H, 0, RowPerm{c->Clast, c->HWlast}};   // K-major rows n in (hw,c) order
@@ -1071,7 +1182,8 @@ int clip_update(arl_ctx* c, float gscale, cudaStream_t st) {
   u.rho = c->opt.rho; u.clip = c->opt.grad_norm_clip; u.gscale = gscale;
   u.out_norm = c->log_norm; u.out_loss = c->log_loss; u.log_slot = c->log_slot; u.log_cap = c->log_cap;
   u.shadow = c->wfc_bf16; u.shadow_begin = c->off_Wfc; u.shadow_end = c->off_Wfc + (long)c->Kfc * c->H;
-  bool fused_cast = (c->off_Wfc % 4 == 0);
+  bool fused_cast = (c->off_Wfc % 4 == 0) && (c->H % 4 == 0);
+  if (fc_tiles_ok(c)) { u.shadow = c->wfc_t; u.shadow_tiles = 1; u.shadow_HW = c->HWlast; u.shadow_H = c->H; }
   if (!fused_cast) u.shadow = nullptr;
   ARL_CHECK(c, launch_k(update_kernel, dim3(148 * 4), dim3(256), 0, st, u));
   c->launches++;
@@ -1577,8 +1689,9 @@ int arl_async_push_pull(arl_ctx* c, void* stream) {
   u.lr = c->opt.learning_rate; u.beta1 = c->opt.beta1; u.beta2 = c->opt.beta2; u.eps = c->opt.epsilon;
   u.rho = c->opt.rho; u.clip = c->opt.grad_norm_clip; u.gscale = 1.f;
   u.out_norm = c->log_norm; u.out_loss = c->log_loss; u.log_slot = c->log_slot; u.log_cap = c->log_cap;
-  bool fused_cast = (c->off_Wfc % 4 == 0) && (c->async_.dev.per % 4 == 0);
+  bool fused_cast = (c->off_Wfc % 4 == 0) && (c->async_.dev.per % 4 == 0) && (c->H % 4 == 0);
   u.shadow = fused_cast ? c->wfc_bf16 : nullptr;
+  if (fused_cast && fc_tiles_ok(c)) { u.shadow = c->wfc_t; u.shadow_tiles = 1; u.shadow_HW = c->HWlast; u.shadow_H = c->H; }
   u.shadow_begin = c->off_Wfc; u.shadow_end = c->off_Wfc + (long)c->Kfc * c->H;
   int grid = std::min(c->async_.dev.n_locks, 148);
   async_push_pull_kernel<<<grid, kAsyncThreads, 0, st>>>(c->async_.dev, u);

@@ -438,9 +438,14 @@ __global__ void __launch_bounds__(kAsyncThreads) async_push_pull_kernel(AsyncDev
       st_sys_f4(d.cv + e0, make_float4(vv[0], vv[1], vv[2], vv[3]));
       st_sys_f4(d.cp + e0, make_float4(pp[0], pp[1], pp[2], pp[3]));
       *reinterpret_cast<float4*>(p.param + e0) = make_float4(pp[0], pp[1], pp[2], pp[3]);   // pull
-      if (p.shadow && e0 >= p.shadow_begin && e0 + 4 <= p.shadow_end)
-        *reinterpret_cast<uint2*>(p.shadow + (e0 - p.shadow_begin)) =
-            make_uint2(pack_bf16x2(pp[0], pp[1]), pack_bf16x2(pp[2], pp[3]));
+      if (p.shadow && e0 >= p.shadow_begin && e0 + 4 <= p.shadow_end) {
+        long off = e0 - p.shadow_begin;
+        if (p.shadow_tiles) {
+          const unsigned ou = (unsigned)off, rr = ou / (unsigned)p.shadow_H;
+          off = fc_tile_index(rr, (int)(ou - rr * (unsigned)p.shadow_H), p.shadow_HW, p.shadow_H);
+        }
+        *reinterpret_cast<uint2*>(p.shadow + off) = make_uint2(pack_bf16x2(pp[0], pp[1]), pack_bf16x2(pp[2], pp[3]));
+      }
     }
     // tail of the vector (n % 4 elements) belongs to the last region
     for (long e = begin + (n4 << 2) + threadIdx.x; e < end; e += blockDim.x) {

@@ -540,6 +540,8 @@ struct HeadParams {
   // train outputs
   __nv_bfloat16* h_out;     // [M][H] post-ReLU hidden (bf16)
   __nv_bfloat16* dh_out;    // [M][H] gradient w.r.t. FC pre-activation (bf16)
+  __nv_bfloat16* dh_t;      // optional second copy as [H/64][dh_rows][64] planes, chunk-swizzled (fcgemm.cuh)
+  int dh_rows;
   float* dlogit_out;        // [M][A+1]  (last column: dV)
   float* loss_partial;      // [M][4]  pi, v, ent, total per sample row
 };
@@ -714,6 +716,8 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadParams p) {
         d = (h[i] > 0.f) ? d : 0.f;
         p.h_out[(long)row * p.H + j] = __float2bfloat16_rn(h[i]);
         p.dh_out[(long)row * p.H + j] = __float2bfloat16_rn(d);
+        if (p.dh_t)
+          p.dh_t[((long)(j >> 6) * p.dh_rows + row) * 64 + (((((j & 63) >> 3) ^ (row & 7)) << 3) | (j & 7))] = __float2bfloat16_rn(d);
       }
     }
   }
@@ -888,6 +892,14 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
   }
 }
 
+// FC weight element (reference row r = c*HW + hw, column j) -> element offset in wfc_t [HW][H/64][64 c][64 j]
+// (8 KB tiles, 16-byte chunks XOR-swizzled by (c & 7)); see fcgemm.cuh
+ARL_DEVINL long fc_tile_index(long r, int j, int HW, int H) {
+  const unsigned ru = (unsigned)r;                       // 32-bit division: the 64-bit one costs ~100 instructions
+  const unsigned c = ru / (unsigned)HW, hw = ru - c * (unsigned)HW;
+  return (((long)hw * (H >> 6) + (j >> 6)) * 64 + c) * 64 + (((((j & 63) >> 3) ^ (c & 7)) << 3) | (j & 7));
+}
+
 struct UpdateParams {
   float* param; const float* grad; float* m; float* v;
   long n;
@@ -902,6 +914,7 @@ struct UpdateParams {
   float* out_norm; float* out_loss;   // [cap] logs, slot = log_slot[0]
   int* log_slot; int log_cap;
   __nv_bfloat16* shadow; long shadow_begin, shadow_end;   // bf16 copy of params[shadow_begin, shadow_end) (4-aligned)
+  int shadow_tiles, shadow_HW, shadow_H;                  // != 0: the copy is the tiled wfc_t layout (H % 4 == 0)
 };
 
 __global__ void __launch_bounds__(256) update_kernel(UpdateParams p) {
@@ -981,9 +994,14 @@ __global__ void __launch_bounds__(256) update_kernel(UpdateParams p) {
     reinterpret_cast<float4*>(p.param)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
     // bf16 operand copy of the FC weights (same layout), refreshed in the same pass
     const long e0 = i << 2;
-    if (p.shadow && e0 >= p.shadow_begin && e0 + 4 <= p.shadow_end)
-      *reinterpret_cast<uint2*>(p.shadow + (e0 - p.shadow_begin)) =
-          make_uint2(pack_bf16x2(pp[0], pp[1]), pack_bf16x2(pp[2], pp[3]));
+    if (p.shadow && e0 >= p.shadow_begin && e0 + 4 <= p.shadow_end) {
+      long off = e0 - p.shadow_begin;
+      if (p.shadow_tiles) {
+        const unsigned ou = (unsigned)off, rr = ou / (unsigned)p.shadow_H;
+        off = fc_tile_index(rr, (int)(ou - rr * (unsigned)p.shadow_H), p.shadow_HW, p.shadow_H);
+      }
+      *reinterpret_cast<uint2*>(p.shadow + off) = make_uint2(pack_bf16x2(pp[0], pp[1]), pack_bf16x2(pp[2], pp[3]));
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x < (p.n & 3)) {
     long i = (n4 << 2) + threadIdx.x;
@@ -1011,7 +1029,7 @@ __global__ void advance_counters_kernel(int* step, int* log_slot, int* mb_counte
 // ===========================================================================
 // Weight packing: fp32 master (reference layout) -> bf16 operand matrices for the GEMM tiles
 // ===========================================================================
-enum PackKind { PK_CONV_NHWC = 0, PK_CONV_S2D = 1, PK_CONV_DGRAD = 2, PK_CAST = 3, PK_PCONV = 4, PK_PCONV_DGRAD = 5 };
+enum PackKind { PK_CONV_NHWC = 0, PK_CONV_S2D = 1, PK_CONV_DGRAD = 2, PK_CAST = 3, PK_PCONV = 4, PK_PCONV_DGRAD = 5, PK_FC_TILES = 6 };
 
 struct PackJob {
   __nv_bfloat16* dst;
@@ -1073,6 +1091,9 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const PackJob* __rest
       if (ky < jb.kh && kx < jb.kw && ci < jb.C && co < jb.Cout)
         v = W[(((long)co * jb.C + ci) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx)];
       jb.dst[(long)r * 64 + ((((k >> 3) ^ (n_ & 7)) << 3) | (k & 7))] = __float2bfloat16_rn(v);
+      continue;
+    } else if (jb.kind == PK_FC_TILES) {     // FC weights -> wfc_t tiles (rows = Kfc in reference order, cols = H)
+      jb.dst[fc_tile_index(r, k, jb.HW, jb.cols)] = __float2bfloat16_rn(W[i]);
       continue;
     } else {                                 // PK_CAST: same layout, fp32 -> bf16 (FC weights, reference order)
       v = W[i];

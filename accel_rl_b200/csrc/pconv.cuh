@@ -43,6 +43,7 @@ struct PcOut {
                               // position = source position + act_off, channel = output column
   int swz;                    // 1: planes of 128-byte rows, chunk-swizzled   0: dense rows of dense_ld elements
   int dense_ld;
+  int fc_rows;                // > 0: destination is act_fc [pixel][fc_rows images][64] (fcgemm.cuh): position = pixel*fc_rows + image
   // mode 2 (data gradient of a stride-`us` layer -> gradient w.r.t. the PIXELS of the layer below, stored
   // position-aligned for that layer's wgrad): cell (y, x) sub-pixel (py, px) -> pixel (us*y + py - upad, ...)
   int uH, uW, uWp, uS, us, upad, uC;
@@ -323,7 +324,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) pconv_fwd_kernel(const __grid_c
           const int Y = y + o.dpad, X = x + o.dpad;
           const int cy = Y / o.ds, cx = X / o.ds;
           const int sub = (Y - cy * o.ds) * o.ds + (X - cx * o.ds);
-          const long dpos = (long)b * o.dS + cy * o.dWp + cx;
+          const long dpos = o.fc_rows ? (long)(cy * o.dWp + cx) * o.fc_rows + b : (long)b * o.dS + cy * o.dWp + cx;
           if (cy < o.dHc && cx < o.dWp) pc_store16(o, bias_s, h * HC, r, dpos, sub * N + h * HC);
         }
       } else {
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) pconv_fwd_kernel(const __grid_c
             const int Y = y + o.dpad, X = x + o.dpad;
             const int cy = Y / o.ds, cx = X / o.ds;
             const int sub = (Y - cy * o.ds) * o.ds + (X - cx * o.ds);
-            const long dpos = (long)b * o.dS + cy * o.dWp + cx;
+            const long dpos = o.fc_rows ? (long)(cy * o.dWp + cx) * o.fc_rows + b : (long)b * o.dS + cy * o.dWp + cx;
             const long apos = (long)b * p.S + pl_ + o.act_off;
             if (cy < o.dHc && cx < o.dWp) {
 #pragma unroll
