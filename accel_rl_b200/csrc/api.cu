@@ -154,6 +154,7 @@ struct arl_ctx {
   cudaGraphExec_t train_graph = nullptr;
   const int* train_graph_idx = nullptr;
   int train_graph_mb = 0;
+  bool train_graph_sync = false, sync_graph_failed = false;
   long launches = 0;
   // per-kernel CUDA-event profiling (arl_profile_*): events recorded after each launch when enabled
   bool prof_on = false;
@@ -424,6 +425,7 @@ int plan_pconv(arl_ctx* c) {
       q.dYpad = q.T - 1 - (L.s == 1 ? L.p : 0);
       if (q.dYpad < 0 || L.Ho + q.dYpad > q.Hc || L.Wo + q.dYpad > q.Wp) return 0;
       if (L.s > 1 && l != 1) return 0;                         // strided layers above layer 1: no unfold target
+      if (L.s != 1 && L.s != 2 && L.s != 4) return 0;           // space-to-depth factors are decoded with shifts
       if (l == 1 && c->conv[0].Cout != 32) return 0;           // unfold epilogue: 32-channel pixels below
       if (l == 1 && L.s * L.s * c->conv[0].Cout != q.P * 64) return 0;
     }
@@ -543,7 +545,9 @@ int pconv_forward_layer(arl_ctx* c, int l, const __nv_bfloat16* obs16, const int
   p.ntaps = q.ntaps;
   for (int t = 0; t < q.ntaps; ++t) p.shift[t] = q.shift[t];
   p.load_rows = q.load_rows; p.w = q.wpack; p.stages = q.stages_fwd;
+  p.magic_S = pc_magic(p.S); p.magic_Wp = pc_magic(p.Wp); p.magic_tpi = pc_magic(p.tiles_per_img);
   pc_out_forward(c, l, p.out);
+  p.out.ds_shift = (p.out.ds == 2) ? 1 : (p.out.ds == 4) ? 2 : 0; p.out.us = 1;
   return launch_pconv_n(c, q.N, p, st);
 }
 
@@ -609,6 +613,7 @@ int pconv_dgrad_layer(arl_ctx* c, int l, int n, cudaStream_t st) {
   p.ntaps = q.ntaps;
   for (int t = 0; t < q.ntaps; ++t) p.shift[t] = q.shift[t];
   p.load_rows = q.load_rows; p.w = q.dwpack; p.stages = q.stages_dgrad;
+  p.magic_S = pc_magic(p.S); p.magic_Wp = pc_magic(p.Wp); p.magic_tpi = 0;
   PcOut& o = p.out;
   o.scale = 1.f; o.act = q.in; o.act_plane_stride = q.in_rows * 64;
   o.dst = lo.dY;
@@ -624,7 +629,9 @@ int pconv_dgrad_layer(arl_ctx* c, int l, int n, cudaStream_t st) {
     o.mode = 2; o.act_off = 0;
     o.uH = L.Hin; o.uW = L.Win; o.uWp = lo.Wp; o.uS = lo.S; o.us = L.s; o.upad = L.p; o.uC = lo.N;
     o.dS = 1; o.dWp = 1; o.dHc = 1; o.ds = 1;
+    o.us_shift = (L.s == 2) ? 1 : 2;
   }
+  o.ds_shift = 0; if (o.us == 0) o.us = 1;
   return launch_pconv_n(c, q.P * 64, p, st);
 }
 
@@ -1265,6 +1272,11 @@ int rollout_end(arl_ctx* c, cudaStream_t st) {
 
 }  // namespace
 
+namespace {
+int sync_update(arl_ctx* c, cudaStream_t st);
+int train_minibatches(arl_ctx* c, const int* idx, int mb_size, int count, bool sync, cudaStream_t st);
+}
+
 // ===========================================================================
 // extern "C"
 // ===========================================================================
@@ -1557,16 +1569,29 @@ int arl_grad_minibatch(arl_ctx* c, const int* idx, int mb_size, void* stream) {
 int arl_clip_update(arl_ctx* c, float gscale, void* stream) { return clip_update(c, gscale, (cudaStream_t)stream); }
 
 int arl_train_minibatches(arl_ctx* c, const int* idx, int mb_size, int count, void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  if (!(c->sampler_set && c->t_obs == c->sc.observations && c->roll_obs16)) {
+  return train_minibatches(c, idx, mb_size, count, false, (cudaStream_t)stream);
+}
+/* same loop with the synchronous data-parallel step (fused P2P all-reduce + clip + update) closing every minibatch */
+int arl_train_minibatches_sync(arl_ctx* c, const int* idx, int mb_size, int count, void* stream) {
+  if (!c->comm.ready) ARL_FAIL(c, "comm not connected");
+  return train_minibatches(c, idx, mb_size, count, true, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+namespace {
+int train_minibatches(arl_ctx* c, const int* idx, int mb_size, int count, bool sync, cudaStream_t st) {
+  auto step = [&](cudaStream_t s_) { return sync ? sync_update(c, s_) : clip_update(c, 1.f, s_); };
+  if (!(c->sampler_set && c->t_obs == c->sc.observations && c->roll_obs16) || (sync && c->sync_graph_failed)) {
     // training inputs that are not the sampler's rollout buffers: plain launches, one minibatch at a time
+    const bool replay_idx = c->sampler_set && c->t_obs == c->sc.observations && c->roll_obs16;
+    (void)replay_idx;
     for (int i = 0; i < count; ++i) {
       if (grad_minibatch(c, idx + (long)i * mb_size, nullptr, mb_size, st)) return 1;
-      if (clip_update(c, 1.f, st)) return 1;
+      if (step(st)) return 1;
     }
     return 0;
   }
-  if (c->train_graph && (c->train_graph_idx != idx || c->train_graph_mb != mb_size)) {
+  if (c->train_graph && (c->train_graph_idx != idx || c->train_graph_mb != mb_size || c->train_graph_sync != sync)) {
     cudaGraphExecDestroy(c->train_graph);
     c->train_graph = nullptr;
   }
@@ -1579,22 +1604,31 @@ int arl_train_minibatches(arl_ctx* c, const int* idx, int mb_size, int count, vo
     cudaGraph_t g = nullptr;
     ARL_CHECK(c, cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
     int rc = grad_minibatch(c, idx, c->mb_counter, mb_size, cap);
-    if (!rc) rc = clip_update(c, 1.f, cap);
+    if (!rc) rc = step(cap);
     cudaError_t ce = cudaStreamEndCapture(cap, &g);
     c->graph_train_nodes = c->launches - l0;
     c->launches = l0;
-    if (rc) { if (g) cudaGraphDestroy(g); cudaStreamDestroy(cap); return rc; }
-    ARL_CHECK(c, ce);
-    ARL_CHECK(c, cudaGraphInstantiate(&c->train_graph, g, 0));
-    cudaGraphDestroy(g);
+    if (!rc && ce == cudaSuccess) ce = cudaGraphInstantiate(&c->train_graph, g, 0);
+    if (g) cudaGraphDestroy(g);
     cudaStreamDestroy(cap);
-    c->train_graph_idx = idx; c->train_graph_mb = mb_size;
+    if (sync && (rc || ce != cudaSuccess)) {
+      // the cooperative all-reduce kernel could not be captured on this driver: plain launches instead
+      cudaGetLastError();
+      c->train_graph = nullptr;
+      c->sync_graph_failed = true;
+      return train_minibatches(c, idx, mb_size, count, sync, st);
+    }
+    if (rc) return rc;
+    ARL_CHECK(c, ce);
+    c->train_graph_idx = idx; c->train_graph_mb = mb_size; c->train_graph_sync = sync;
   }
   ARL_CHECK(c, cudaMemsetAsync(c->mb_counter, 0, sizeof(int), st));
   for (int i = 0; i < count; ++i) ARL_CHECK(c, cudaGraphLaunch(c->train_graph, st));
   c->launches += (long)count * c->graph_train_nodes;
   return 0;
 }
+}  // namespace
+extern "C" {
 
 int arl_read_logs(arl_ctx* c, float* loss, float* grad_norm, int cap, int* n, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
@@ -1643,9 +1677,12 @@ int arl_comm_barrier(arl_ctx* c, void* stream) {
   c->launches++;
   return 0;
 }
-int arl_sync_allreduce_update(arl_ctx* c, void* stream) {
+int arl_sync_allreduce_update(arl_ctx* c, void* stream) { return sync_update(c, (cudaStream_t)stream); }
+
+}  // extern "C"
+namespace {
+int sync_update(arl_ctx* c, cudaStream_t st) {
   if (!c->opt_set) ARL_FAIL(c, "optimizer not configured");
-  cudaStream_t st = (cudaStream_t)stream;
   SyncUpdateArgs a{};
   a.param = c->params; a.grad = c->grad; a.m = c->m; a.v = c->v; a.n = c->n_params;
   a.loss_partial = c->loss_partial; a.n_loss_blocks = c->n_loss_rows; a.hyper = c->hyper; a.step = c->step;
@@ -1658,6 +1695,8 @@ int arl_sync_allreduce_update(arl_ctx* c, void* stream) {
   ARL_CHECK(c, cudaGetLastError());
   return pack_weights(c, st, true, true);
 }
+}  // namespace
+extern "C" {
 
 // ---- async DP -----------------------------------------------------------------------------
 int arl_async_local_init(arl_ctx* c, int rank, int world, int n_update_chunks, uint8_t* handle_out) {

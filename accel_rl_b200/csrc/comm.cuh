@@ -160,7 +160,7 @@ ARL_DEVINL void grid_barrier(const CommDev& d, unsigned int& gen, bool cross_gpu
     if (blockIdx.x == 0) {
       // wait for every block, then (optionally) the other GPUs, then release the grid
       long long t0 = clock64();
-      while (atomicAdd(d.grid_counter, 0u) < gen) {
+      while ((int)(atomicAdd(d.grid_counter, 0u) - gen) < 0) {          // wrap-safe
         if (clock64() - t0 > 20000000000LL) dev_fail(301);
       }
       if (cross_gpu) xgpu_barrier_thread(d);
@@ -169,7 +169,7 @@ ARL_DEVINL void grid_barrier(const CommDev& d, unsigned int& gen, bool cross_gpu
     } else {
       (void)arrived;
       long long t0 = clock64();
-      while (atomicAdd(d.grid_counter + 1, 0u) < gen) {
+      while ((int)(atomicAdd(d.grid_counter + 1, 0u) - gen) < 0) {
         if (clock64() - t0 > 20000000000LL) dev_fail(302);
       }
     }
@@ -178,9 +178,12 @@ ARL_DEVINL void grid_barrier(const CommDev& d, unsigned int& gen, bool cross_gpu
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kSyncThreads) sync_allreduce_update_kernel(CommDev d, SyncUpdateArgs a,
-                                                                             unsigned int gen0) {
-  unsigned int gen = gen0;
+__global__ void __launch_bounds__(kSyncThreads) sync_allreduce_update_kernel(CommDev d, SyncUpdateArgs a) {
+  // barrier generation of this launch: kept on the DEVICE (grid_counter[2]) so the launch carries no host state and
+  // can be replayed from a CUDA graph.  Every block reads it before it can arrive at the first barrier; block 0
+  // advances it after the last one.
+  unsigned int gen = *reinterpret_cast<volatile unsigned int*>(d.grid_counter + 2);
+  const unsigned int gen_next = gen + 4u * gridDim.x;
   const long begin = (long)d.rank * d.per;
   const long end = min(d.n, begin + d.per);
   const long len = end > begin ? end - begin : 0;
@@ -280,6 +283,7 @@ __global__ void __launch_bounds__(kSyncThreads) sync_allreduce_update_kernel(Com
   }
   // 5. all parameter slices have landed everywhere
   grid_barrier(d, gen, true);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<volatile unsigned int*>(d.grid_counter + 2) = gen_next;
 }
 
 __global__ void xgpu_barrier_kernel(CommDev d) {
@@ -297,9 +301,7 @@ inline int comm_barrier(CommState& s, cudaStream_t st, std::string& err) {
 inline int comm_sync_update(CommState& s, SyncUpdateArgs a, cudaStream_t st, std::string& err) {
   if (!s.ready) { err = "comm not connected"; return 1; }
   if (a.param != s.param || a.grad != s.grad) { err = "params/grad must be the comm's symmetric buffers"; return 1; }
-  unsigned int gen0 = s.gen;
-  s.gen += 4u * kSyncBlocks;          // four grid barriers per launch
-  void* args[] = {(void*)&s.dev, (void*)&a, (void*)&gen0};
+  void* args[] = {(void*)&s.dev, (void*)&a};
   cudaError_t e = cudaLaunchCooperativeKernel((const void*)sync_allreduce_update_kernel, dim3(kSyncBlocks),
                                               dim3(kSyncThreads), args, 0, st);
   if (e != cudaSuccess) { err = std::string("cooperative launch: ") + cudaGetErrorString(e); return 1; }

@@ -38,6 +38,7 @@ struct PcOut {
   const __nv_bfloat16* act;   // mask source (modes 1, 2)
   long dst_plane_stride;      // elements between 64-channel planes of dst
   long act_plane_stride;
+  int ds_shift, us_shift;     // log2(ds), log2(us) (both are 1 or 2)
   int dS, dWp, dHc, dpad, ds; // destination grid: positions per image, pitch, rows, padding added to (y, x), space-to-depth
   int act_off;                // modes 1, 2: the mask is the forward INPUT of this layer, i.e. it lives in the source grid:
                               // position = source position + act_off, channel = output column
@@ -58,6 +59,7 @@ struct PcParams {
   int nb;
   int S, Wp, Ho, Wo;          // source positions per image, pitch; valid output extent
   int tiles_per_img;          // > 0: tiles never cross images (layer 0, gatherable); 0: continuous over the batch
+  uint32_t magic_S, magic_Wp, magic_tpi;   // floor(2^32/d)+1: q = umulhi(n, magic) replaces the integer divisions of the row decode
   int n_img, ntiles;
   int ntaps;
   int shift[kPcMaxTaps];      // row shift of each tap
@@ -71,105 +73,70 @@ __host__ __device__ inline int pc_fwd_smem(int N, int ntaps, int planes, int loa
   return ntaps * planes * N * 128 + stages * planes * load_rows * 128 + 1024 /*align*/ + 256 /*barriers*/ + N * 4;
 }
 
-// 32 accumulator columns of one output row -> destination (modes 0 / 1)
-ARL_DEVINL void pc_store32(const PcOut& o, const float* bias_s, int col0, const uint32_t (&r)[32], long dpos, int ch0,
-                           long apos) {
-  // ch0: channel (within the destination cell) of column col0; 32 consecutive channels never straddle a plane
-  const int plane = ch0 >> 6, chunk0 = (ch0 & 63) >> 3;
-  uint32_t packed[16];
-  if (o.mode != 0) {
-    // dReLU mask: forward activation at (source position apos, channel col0..col0+31) of the swizzled source grid
-    const __nv_bfloat16* arow = o.act + (col0 >> 6) * o.act_plane_stride + apos * 64;
-    const int a7 = (int)(apos & 7), ac0 = (col0 & 63) >> 3;
+// n / d for d >= 1 with magic = floor(2^32/d) + 1 (exact for n < 2^32 / d; every use here is < 2^24)
+ARL_DEVINL uint32_t pc_fdiv(uint32_t n, uint32_t d, uint32_t magic) { return d == 1 ? n : __umulhi(n, magic); }
+__host__ inline uint32_t pc_magic(uint32_t d) { return d <= 1 ? 0u : (uint32_t)(0x100000000ull / d) + 1u; }
+
+// dReLU mask of 32 output columns: forward activation at (source position apos, channel col0..col0+31) of the
+// chunk-swizzled source grid (issued BEFORE the accumulator wait, so the loads overlap the MMAs)
+ARL_DEVINL void pc_load_mask32(const PcOut& o, int col0, long apos, uint4 (&m)[4]) {
+  const __nv_bfloat16* arow = o.act + (col0 >> 6) * o.act_plane_stride + apos * 64;
+  const int a7 = (int)(apos & 7), ac0 = (col0 & 63) >> 3;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint4 m = __ldg(reinterpret_cast<const uint4*>(arow + ((ac0 + j) ^ a7) * 8));
-      uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+  for (int j = 0; j < 4; ++j) m[j] = __ldg(reinterpret_cast<const uint4*>(arow + ((ac0 + j) ^ a7) * 8));
+}
+
+// 32 (or 16) accumulator columns -> 16 (8) packed bf16 pairs: bias + ReLU (forward) or dReLU mask (gradient)
+template <int NC>
+ARL_DEVINL void pc_finish(const uint32_t* r, const float* bias_r, float scale, bool fwd, const uint4* m, uint32_t* packed) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float lo = bf16_lo(mw[k]) > 0.f ? __uint_as_float(r[8 * j + 2 * k]) : 0.f;
-        float hi = bf16_hi(mw[k]) > 0.f ? __uint_as_float(r[8 * j + 2 * k + 1]) : 0.f;
-        packed[4 * j + k] = pack_bf16x2(lo, hi);
-      }
+  for (int i = 0; i < NC / 2; ++i) {
+    float lo = __uint_as_float(r[2 * i]), hi = __uint_as_float(r[2 * i + 1]);
+    if (fwd) {
+      lo = fmaxf(lo * scale + bias_r[2 * i], 0.f);
+      hi = fmaxf(hi * scale + bias_r[2 * i + 1], 0.f);
+    } else {
+      const uint4 mm = m[i >> 2];
+      const uint32_t mw = (i & 3) == 0 ? mm.x : (i & 3) == 1 ? mm.y : (i & 3) == 2 ? mm.z : mm.w;
+      lo = bf16_lo(mw) > 0.f ? lo : 0.f;
+      hi = bf16_hi(mw) > 0.f ? hi : 0.f;
     }
-  }
-  if (o.mode == 0) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      float lo = fmaxf(__uint_as_float(r[2 * i]) * o.scale + bias_s[col0 + 2 * i], 0.f);
-      float hi = fmaxf(__uint_as_float(r[2 * i + 1]) * o.scale + bias_s[col0 + 2 * i + 1], 0.f);
-      packed[i] = pack_bf16x2(lo, hi);
-    }
-  }
-  if (o.swz) {
-    __nv_bfloat16* drow = o.dst + plane * o.dst_plane_stride + dpos * 64;
-    const int x7 = (int)(dpos & 7);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int ch = ((chunk0 + j) ^ x7) * 8;
-      *reinterpret_cast<uint4*>(drow + ch) = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-    }
-  } else {
-    __nv_bfloat16* drow = o.dst + dpos * o.dense_ld + ch0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      *reinterpret_cast<uint4*>(drow + j * 8) = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-    }
+    packed[i] = pack_bf16x2(lo, hi);
   }
 }
 
-// 16-column variant (N == 32: each epilogue warp owns 16 columns); forward mode only
-ARL_DEVINL void pc_store16(const PcOut& o, const float* bias_s, int col0, const uint32_t (&r)[16], long dpos, int ch0) {
+// NC/8 packed 16-byte chunks -> destination position dpos, channel ch0 of the destination cell
+template <int NC>
+ARL_DEVINL void pc_store(const PcOut& o, const uint32_t* packed, long dpos, int ch0) {
   const int plane = ch0 >> 6, chunk0 = (ch0 & 63) >> 3;
-  uint32_t packed[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float lo = fmaxf(__uint_as_float(r[2 * i]) * o.scale + bias_s[col0 + 2 * i], 0.f);
-    float hi = fmaxf(__uint_as_float(r[2 * i + 1]) * o.scale + bias_s[col0 + 2 * i + 1], 0.f);
-    packed[i] = pack_bf16x2(lo, hi);
-  }
   if (o.swz) {
     __nv_bfloat16* drow = o.dst + plane * o.dst_plane_stride + dpos * 64;
     const int x7 = (int)(dpos & 7);
 #pragma unroll
-    for (int j = 0; j < 2; ++j)
+    for (int j = 0; j < NC / 8; ++j)
       *reinterpret_cast<uint4*>(drow + ((chunk0 + j) ^ x7) * 8) =
           make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
   } else {
     __nv_bfloat16* drow = o.dst + dpos * o.dense_ld + ch0;
 #pragma unroll
-    for (int j = 0; j < 2; ++j)
+    for (int j = 0; j < NC / 8; ++j)
       *reinterpret_cast<uint4*>(drow + j * 8) = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
   }
 }
 
-// mode 2: 32 columns = one sub-pixel block (py, px) of a space-to-depth cell -> that pixel's row in the
-// position-aligned gradient buffer of the layer below ([uS positions][uC channels], uC*2-byte rows, chunk-swizzled
-// like a SWIZZLE_64B / SWIZZLE_128B tile), masked by the forward activation read from the cell layout.
-ARL_DEVINL void pc_store32_unfold(const PcOut& o, const uint32_t (&r)[32], int b, int y, int x, long cpos, int sub) {
-  const int py = sub / o.us, px = sub - py * o.us;
+// mode 2: 32 masked columns = one sub-pixel block (py, px) of a space-to-depth cell -> that pixel's row in the
+// position-aligned gradient buffer of the layer below ([uS positions][uC = 32 channels], 64-byte rows chunk-swizzled
+// like a SWIZZLE_64B tile)
+ARL_DEVINL void pc_store_unfold(const PcOut& o, const uint32_t* packed, int b, int y, int x, int sub) {
+  const int py = sub >> o.us_shift, px = sub & (o.us - 1);
   const int yy = o.us * y + py - o.upad, xx = o.us * x + px - o.upad;
   if ((unsigned)yy >= (unsigned)o.uH || (unsigned)xx >= (unsigned)o.uW) return;
-  const int ch0 = sub * o.uC;                        // channel of this block inside the cell (uC == 32)
-  const int plane = ch0 >> 6, chunk0 = (ch0 & 63) >> 3;
-  const __nv_bfloat16* arow = o.act + plane * o.act_plane_stride + cpos * 64;
-  const int x7 = (int)(cpos & 7);
   const long upos = (long)b * o.uS + yy * o.uWp + xx;
-  __nv_bfloat16* drow = o.dst + upos * o.uC;
-  const int sw = (o.uC == 32) ? (int)((upos >> 1) & 3) : (int)(upos & 7);
+  __nv_bfloat16* drow = o.dst + upos * 32;
+  const int sw = (int)((upos >> 1) & 3);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint4 m = __ldg(reinterpret_cast<const uint4*>(arow + ((chunk0 + j) ^ x7) * 8));
-    uint32_t mw[4] = {m.x, m.y, m.z, m.w};
-    uint32_t pk[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float lo = bf16_lo(mw[k]) > 0.f ? __uint_as_float(r[8 * j + 2 * k]) : 0.f;
-      float hi = bf16_hi(mw[k]) > 0.f ? __uint_as_float(r[8 * j + 2 * k + 1]) : 0.f;
-      pk[k] = pack_bf16x2(lo, hi);
-    }
-    *reinterpret_cast<uint4*>(drow + (j ^ sw) * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-  }
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<uint4*>(drow + (j ^ sw) * 8) = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
 }
 
 template <int N>
@@ -225,15 +192,24 @@ __global__ void __launch_bounds__(kPcThreads, 1) pconv_fwd_kernel(const __grid_c
       for (int b = 0; b < nblk; ++b) bulk_g2s(w_base + b * (N * 128), p.w + (long)b * N * 64, N * 128, wfull_bar);
     }
     __syncwarp();
+    // gathered images: the index lookups (two dependent global loads, ~1.5 us) are hoisted out of the tile loop —
+    // lane l fetches the image of this CTA's l-th tile, one round of latency per 32 tiles instead of one per tile
+    const long idx_base = (p.idx && p.idx_off) ? (long)p.idx_off[0] * p.nb : 0;
+    int img_l = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int s = it % p.stages;
       const uint32_t ph = (it / p.stages) & 1;
       long pos0;
       if (p.tiles_per_img > 0) {
-        int b = tile / p.tiles_per_img;
-        int j = tile - b * p.tiles_per_img;
-        long img = p.idx ? (long)p.idx[(p.idx_off ? (long)p.idx_off[0] * p.nb : 0) + b] : b;
+        if ((it & 31) == 0) {
+          const int tl = tile + lane * (int)gridDim.x;
+          const int bl = min(tl, p.ntiles - 1) / p.tiles_per_img;
+          img_l = p.idx ? p.idx[idx_base + bl] : bl;
+        }
+        const int b = tile / p.tiles_per_img;
+        const int j = tile - b * p.tiles_per_img;
+        const long img = __shfl_sync(0xffffffffu, img_l, it & 31);
         pos0 = img * p.S + (long)j * 128;
       } else {
         pos0 = (long)tile * 128;
@@ -293,65 +269,62 @@ __global__ void __launch_bounds__(kPcThreads, 1) pconv_fwd_kernel(const __grid_c
     const int q = warp & 3;                   // TMEM lane quadrant
     const int h = (warp - 2) >> 2;            // column half
     constexpr int HC = N / 2;                 // columns per warp
+    constexpr int NC = HC < 32 ? HC : 32;     // columns per register block
+    constexpr int NB = HC / NC;
+    const bool fwd = (o.mode == 0);
+    const uint32_t row = q * 32 + lane;
+    // forward: this thread's bias slice lives in registers for the whole kernel (N <= 64 on the forward path)
+    float bias_r[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) bias_r[i] = (fwd && NB == 1) ? bias_s[h * HC + i] : 0.f;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t aph = (it >> 1) & 1;
-      // decode this thread's output row while the MMAs run
-      const int row = q * 32 + lane;
-      int b, pl_;
+      // decode this thread's output row (and prefetch its mask) while the MMAs run
+      uint32_t b, pl_;
       if (p.tiles_per_img > 0) {
-        b = tile / p.tiles_per_img;
-        pl_ = (tile - b * p.tiles_per_img) * 128 + row;
+        b = pc_fdiv((uint32_t)tile, (uint32_t)p.tiles_per_img, p.magic_tpi);
+        pl_ = ((uint32_t)tile - b * p.tiles_per_img) * 128 + row;
       } else {
-        long qq = (long)tile * 128 + row;
-        b = (int)(qq / p.S);
-        pl_ = (int)(qq - (long)b * p.S);
+        const uint32_t qq = (uint32_t)tile * 128 + row;
+        b = pc_fdiv(qq, (uint32_t)p.S, p.magic_S);
+        pl_ = qq - b * p.S;
       }
-      const int y = pl_ / p.Wp, x = pl_ - y * p.Wp;
-      const bool valid = b < p.n_img && y < p.Ho && x < p.Wo;
+      const uint32_t y = pc_fdiv(pl_, (uint32_t)p.Wp, p.magic_Wp), x = pl_ - y * p.Wp;
+      const bool valid = (int)b < p.n_img && (int)y < p.Ho && (int)x < p.Wo;
+      const int Y = y + o.dpad, X = x + o.dpad;
+      const int cy = Y >> o.ds_shift, cx = X >> o.ds_shift;
+      const int sub = ((Y & (o.ds - 1)) << o.ds_shift) | (X & (o.ds - 1));
+      const long dpos = o.fc_rows ? (long)(cy * o.dWp + cx) * o.fc_rows + b : (long)b * o.dS + cy * o.dWp + cx;
+      const bool store = valid && (o.mode == 2 || (cy < o.dHc && cx < o.dWp));
+      uint4 mk[NB][4];
+      if (!fwd && store) {
+        const long apos = (long)b * p.S + pl_ + o.act_off;
+#pragma unroll
+        for (int c = 0; c < NB; ++c) pc_load_mask32(o, h * HC + c * 32, apos, mk[c]);
+      }
       mbar_wait(tfull_bar(acc), aph, 25);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * N + h * HC;
-      if constexpr (HC == 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr, r);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
-        if (valid) {
-          const int Y = y + o.dpad, X = x + o.dpad;
-          const int cy = Y / o.ds, cx = X / o.ds;
-          const int sub = (Y - cy * o.ds) * o.ds + (X - cx * o.ds);
-          const long dpos = o.fc_rows ? (long)(cy * o.dWp + cx) * o.fc_rows + b : (long)b * o.dS + cy * o.dWp + cx;
-          if (cy < o.dHc && cx < o.dWp) pc_store16(o, bias_s, h * HC, r, dpos, sub * N + h * HC);
-        }
+      uint32_t r[NB][NC];
+      if constexpr (NC == 16) {
+        tmem_ld16(taddr, r[0]);
       } else {
-        uint32_t r[HC / 32][32];
 #pragma unroll
-        for (int c = 0; c < HC / 32; ++c) tmem_ld32(taddr + c * 32, r[c]);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
-        if (valid) {
-          if (o.mode == 2) {
-            const long cpos = (long)b * p.S + pl_;
+        for (int c = 0; c < NB; ++c) tmem_ld32(taddr + c * 32, r[c]);
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));      // accumulator is in registers: the next tile's MMAs may start
+      if (store) {
 #pragma unroll
-            for (int c = 0; c < HC / 32; ++c) pc_store32_unfold(o, r[c], b, y, x, cpos, (h * HC + c * 32) / o.uC);
-          } else {
-            const int Y = y + o.dpad, X = x + o.dpad;
-            const int cy = Y / o.ds, cx = X / o.ds;
-            const int sub = (Y - cy * o.ds) * o.ds + (X - cx * o.ds);
-            const long dpos = o.fc_rows ? (long)(cy * o.dWp + cx) * o.fc_rows + b : (long)b * o.dS + cy * o.dWp + cx;
-            const long apos = (long)b * p.S + pl_ + o.act_off;
-            if (cy < o.dHc && cx < o.dWp) {
-#pragma unroll
-              for (int c = 0; c < HC / 32; ++c)
-                pc_store32(o, bias_s, h * HC + c * 32, r[c], dpos, sub * N + h * HC + c * 32, apos);
-            }
-          }
+        for (int c = 0; c < NB; ++c) {
+          uint32_t packed[NC / 2];
+          pc_finish<NC>(r[c], bias_r, o.scale, fwd, mk[c], packed);
+          if (o.mode == 2) pc_store_unfold(o, packed, (int)b, (int)y, (int)x, (h * HC + c * 32) >> 5);
+          else pc_store<NC>(o, packed, dpos, sub * N + h * HC + c * NC);
         }
       }
     }
@@ -445,15 +418,22 @@ __global__ void __launch_bounds__(kPcThreads, 1) pconv_wgrad_kernel(const __grid
   float csum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (warp == 0) {
     // ===================== TMA producer =====================
+    const long idx_base = (p.idx && p.idx_off) ? (long)p.idx_off[0] * p.nb : 0;
+    int img_l = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int s = it % p.stages;
       const uint32_t ph = (it / p.stages) & 1;
       long apos, dpos;
       if (p.tiles_per_img > 0) {
+        if ((it & 31) == 0) {      // hoisted index lookups, see pconv_fwd_kernel
+          const int tl = tile + lane * (int)gridDim.x;
+          const int bl = min(tl, p.ntiles - 1) / p.tiles_per_img;
+          img_l = p.idx ? p.idx[idx_base + bl] : bl;
+        }
         int b = tile / p.tiles_per_img;
         int j = tile - b * p.tiles_per_img;
-        long img = p.idx ? (long)p.idx[(p.idx_off ? (long)p.idx_off[0] * p.nb : 0) + b] : b;
+        long img = __shfl_sync(0xffffffffu, img_l, it & 31);
         apos = img * p.S + (long)j * 128;
         dpos = (long)b * p.S + (long)j * 128;
       } else {

@@ -174,9 +174,10 @@ class Engine(object):
     def clip_update(self, gscale=1.0):
         self.check(self.lib.arl_clip_update(self.ctx, float(gscale), self._s()))
 
-    def train_minibatches(self, idx, mb_size, count):
+    def train_minibatches(self, idx, mb_size, count, sync=False):
         self._keep["idx"] = idx
-        self.check(self.lib.arl_train_minibatches(self.ctx, L.ptr(idx), int(mb_size), int(count), self._s()))
+        fn = self.lib.arl_train_minibatches_sync if sync else self.lib.arl_train_minibatches
+        self.check(fn(self.ctx, L.ptr(idx), int(mb_size), int(count), self._s()))
 
     def read_logs(self, cap=4096):
         loss = np.zeros(cap, np.float32)

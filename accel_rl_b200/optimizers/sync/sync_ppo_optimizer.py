@@ -8,12 +8,8 @@ from accel_rl_b200.optimizers.sync.base import BaseSyncOptimizer
 class SyncPpoOptimizer(BaseSyncOptimizer, PpoOptimizer):
     def _do_updates(self, data_length):
         n_mb = self._upload_indices(data_length)
-        eng, mb = self._engine, self._minibatch_size
-        k = 0
-        for _ in range(self._epochs):
-            for _ in range(n_mb):
-                eng.grad_minibatch(self._idx_dev[k * mb:(k + 1) * mb], mb)   # _compute_grad
-                eng.sync_allreduce_update()                                  # _share_grad + _do_one_update
-                k += 1
-        losses, grad_norms = eng.read_logs()
+        # per minibatch: _compute_grad, then _share_grad + _do_one_update fused in one kernel — replayed as ONE CUDA
+        # graph per minibatch (every rank replays the same number of graphs, so the cross-GPU barriers line up)
+        self._engine.train_minibatches(self._idx_dev, self._minibatch_size, n_mb * self._epochs, sync=True)
+        losses, grad_norms = self._engine.read_logs()
         return list(losses), list(grad_norms)
