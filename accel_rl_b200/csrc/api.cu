@@ -492,7 +492,7 @@ int launch_pconv(arl_ctx* c, const PcParams& p, cudaStream_t st) {
     attr_smem = smem;
   }
   int ctas = std::min(p.ntiles, 148);
-  ARL_CHECK(c, launch_k(pconv_fwd_kernel<N>, dim3(ctas), dim3(kPcThreads), smem, st, p));
+  ARL_CHECK(c, launch_k(pconv_fwd_kernel<N>, dim3(ctas), dim3(kPcFwdThreads), smem, st, p));
   c->launches++;
   ARL_CHECK(c, cudaGetLastError());
   return 0;
@@ -1614,6 +1614,8 @@ int train_minibatches(arl_ctx* c, const int* idx, int mb_size, int count, bool s
     if (sync && (rc || ce != cudaSuccess)) {
       // the cooperative all-reduce kernel could not be captured on this driver: plain launches instead
       cudaGetLastError();
+      fprintf(stderr, "[accel_rl_b200] synchronous minibatch could not be graph-captured (%s); launching kernels one by one\n",
+              rc ? c->err.c_str() : cudaGetErrorString(ce));
       c->train_graph = nullptr;
       c->sync_graph_failed = true;
       return train_minibatches(c, idx, mb_size, count, sync, st);

@@ -302,9 +302,19 @@ inline int comm_sync_update(CommState& s, SyncUpdateArgs a, cudaStream_t st, std
   if (!s.ready) { err = "comm not connected"; return 1; }
   if (a.param != s.param || a.grad != s.grad) { err = "params/grad must be the comm's symmetric buffers"; return 1; }
   void* args[] = {(void*)&s.dev, (void*)&a};
-  cudaError_t e = cudaLaunchCooperativeKernel((const void*)sync_allreduce_update_kernel, dim3(kSyncBlocks),
-                                              dim3(kSyncThreads), args, 0, st);
-  if (e != cudaSuccess) { err = std::string("cooperative launch: ") + cudaGetErrorString(e); return 1; }
+  // Inside stream capture the kernel is launched plainly: 148 blocks x 512 threads are co-resident on an otherwise idle
+  // GPU (the training graph joins its side stream before this node), which is all the grid barrier needs; outside
+  // capture the cooperative launch lets the driver verify co-residency.
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cs);
+  cudaError_t e;
+  if (cs == cudaStreamCaptureStatusActive) {
+    sync_allreduce_update_kernel<<<kSyncBlocks, kSyncThreads, 0, st>>>(s.dev, a);
+    e = cudaGetLastError();
+  } else {
+    e = cudaLaunchCooperativeKernel((const void*)sync_allreduce_update_kernel, dim3(kSyncBlocks), dim3(kSyncThreads), args, 0, st);
+  }
+  if (e != cudaSuccess) { err = std::string("sync kernel launch: ") + cudaGetErrorString(e); return 1; }
   return 0;
 }
 

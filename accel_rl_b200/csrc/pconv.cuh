@@ -28,6 +28,7 @@
 namespace arl {
 
 constexpr int kPcThreads = 320;
+constexpr int kPcFwdThreads = 352;   // forward/dgrad kernel: + a second MMA-issuing warp (warp 10)
 constexpr int kPcMaxTaps = 16;
 
 struct PcOut {
@@ -139,8 +140,9 @@ ARL_DEVINL void pc_store_unfold(const PcOut& o, const uint32_t* packed, int b, i
     *reinterpret_cast<uint4*>(drow + (j ^ sw) * 8) = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
 }
 
+#define ARL_TP(slot) do { if (N == 32) ARL_T(slot); } while (0)
 template <int N>
-__global__ void __launch_bounds__(kPcThreads, 1) pconv_fwd_kernel(const __grid_constant__ PcParams p) {
+__global__ void __launch_bounds__(kPcFwdThreads, 1) pconv_fwd_kernel(const __grid_constant__ PcParams p) {
   static_assert(N == 32 || N == 64 || N == 128, "tile width");
   if ((int)blockIdx.x >= p.ntiles) return;
   extern __shared__ uint8_t smem_raw[];
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) pconv_fwd_kernel(const __grid_c
   pdl_wait();                                  // everything below may read what the previous kernel wrote
   pdl_trigger();
   if (p.out.mode == 0)
-    for (int i = tid; i < N; i += kPcThreads) bias_s[i] = p.out.bias[i];
+    for (int i = tid; i < N; i += kPcFwdThreads) bias_s[i] = p.out.bias[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -215,6 +217,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) pconv_fwd_kernel(const __grid_c
         pos0 = (long)tile * 128;
       }
       mbar_wait(empty_bar(s), ph ^ 1, 21);
+      if (lane == 0) ARL_TP(it * 6 + 0);
       if (elect_one()) {
         mbar_arrive_expect_tx(full_bar(s), stage_bytes);
         const uint32_t dst = a_base + s * stage_bytes;
@@ -222,9 +225,15 @@ __global__ void __launch_bounds__(kPcThreads, 1) pconv_fwd_kernel(const __grid_c
           bulk_g2s(dst + pl * p.load_rows * 128, p.src + pl * p.src_plane_stride + pos0 * 64, p.load_rows * 128, full_bar(s));
       }
       __syncwarp();
+      if (lane == 0) ARL_TP(it * 6 + 1);
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (converged warp, one elected lane issues) =====================
+  } else if (warp == 1 || warp == 10) {
+    // ===================== MMA issuers (converged warps, one elected lane issues) =====================
+    // Two issuing warps alternate tiles (warp 1: even tiles / accumulator 0, warp 10: odd tiles / accumulator 1).
+    // A tile's tcgen05.mma burst blocks its issuer for ~65-75 cycles per instruction (operand fetch bound, measured)
+    // and the barrier waits in front of it cost ~400 cycles: with two issuers the next tile's waits are already
+    // done when the tensor pipe frees up.
+    const int which = (warp == 10) ? 1 : 0;
     const uint32_t tmem_u = make_uniform(tmem_base);
     constexpr uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
     // descriptor high words are constant (SBO 1024, version 1, SWIZZLE_128B); only the 14-bit address field moves
@@ -232,14 +241,14 @@ __global__ void __launch_bounds__(kPcThreads, 1) pconv_fwd_kernel(const __grid_c
     const uint32_t desc_hi32 = (uint32_t)(desc0 >> 32), desc_lo_flags = (uint32_t)desc0;   // LBO field lives in the low word
     auto mk = [&](uint32_t lo) { return ((uint64_t)desc_hi32 << 32) | (uint64_t)lo; };
     mbar_wait(wfull_bar, 0, 22);
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    for (int it = which, tile = blockIdx.x + which * gridDim.x; tile < p.ntiles; tile += 2 * gridDim.x, it += 2) {
       const int s = it % p.stages;
       const uint32_t ph = (it / p.stages) & 1;
       const int acc = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       mbar_wait(tempty_bar(acc), aph ^ 1, 23);
       mbar_wait(full_bar(s), ph, 24);
+      if (lane == 0) ARL_TP(it * 6 + 2);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t a_stage = a_base + s * stage_bytes;
@@ -262,8 +271,9 @@ __global__ void __launch_bounds__(kPcThreads, 1) pconv_fwd_kernel(const __grid_c
         umma_commit(tfull_bar(acc));
       }
       __syncwarp();
+      if (lane == 0) ARL_TP(it * 6 + 3);
     }
-  } else {
+  } else if (warp >= 2 && warp < 10) {
     // ===================== epilogue warps =====================
     const PcOut& o = p.out;
     const int q = warp & 3;                   // TMEM lane quadrant
@@ -305,6 +315,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) pconv_fwd_kernel(const __grid_c
         for (int c = 0; c < NB; ++c) pc_load_mask32(o, h * HC + c * 32, apos, mk[c]);
       }
       mbar_wait(tfull_bar(acc), aph, 25);
+      if (warp == 2 && lane == 0) ARL_TP(it * 6 + 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * N + h * HC;
       uint32_t r[NB][NC];
@@ -327,6 +338,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) pconv_fwd_kernel(const __grid_c
           else pc_store<NC>(o, packed, dpos, sub * N + h * HC + c * NC);
         }
       }
+      if (warp == 2 && lane == 0) ARL_TP(it * 6 + 5);
     }
   }
   __syncthreads();

@@ -1,5 +1,5 @@
-"""dev tool: per-role clock64 timeline of CTA 0 of the last conv_gemm_persist launch (needs the -DARL_TRACE build:
-ARL_LIB_PATH=accel_rl_b200/csrc/libaccelrl_b200_trace.so python tests/trace_persist.py)"""
+"""dev tool: per-role clock64 timeline of CTA 0 of the last pconv_fwd_kernel<32> launch (conv layer 0).  Needs the
+-DARL_TRACE build:  ARL_LIB_PATH=/root/repo/accel_rl_b200/csrc/libaccelrl_b200_trace.so python tests/trace_persist.py"""
 import ctypes as C
 import os, sys
 import numpy as np, torch
@@ -18,8 +18,8 @@ eng.lib.arl_trace_read.argtypes = [C.c_void_p, C.c_int]
 eng.lib.arl_trace_read(buf, 4096)
 t = np.array(buf[:4092], dtype=np.int64).reshape(-1, 6)
 t0 = t[0, 0]
-print("conv2 fwd (last persist launch), CTA 0: cycles relative to first producer event")
-print(" it | prod:empty-ok  prod:issued | mma:full-ok  mma:committed | (tile) epi:tfull-ok  epi:stored")
-for it in range(30):
+print("conv0 fwd, CTA 0: cycles relative to the first producer event")
+print(" it | prod:empty-ok  prod:issued | mma:full-ok  mma:committed | epi:tfull-ok  epi:stored")
+for it in range(16):
     r = t[it] - t0
     print("%3d | %10d %10d | %10d %10d | %10d %10d" % (it, r[0], r[1], r[2], r[3], r[4], r[5]))
