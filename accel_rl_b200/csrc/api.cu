@@ -167,6 +167,7 @@ struct arl_ctx {
   int n_loss_rows = 0;                 // rows of the last head_kernel<1> launch (loss partial count)
   float lr_mult_host = 1.f;
   CommState comm;
+  bool shadow_in_comm = false;         // wfc_t / wfc_bf16 lives inside comm's symmetric allocation (freed with it)
   AsyncState async_;
 };
 
@@ -1328,6 +1329,7 @@ void arl_destroy(arl_ctx* c) {
   }
   for (auto p : c->wgrad_partial) cudaFree(p);
   for (auto p : c->bias_partial) cudaFree(p);
+  if (c->shadow_in_comm) { (fc_tiles_ok(c) ? c->wfc_t : c->wfc_bf16) = nullptr; }
   cudaFree(c->wfc_bf16); cudaFree(c->obs16_stage); cudaFree(c->step_obs16); cudaFree(c->roll_obs16); cudaFree(c->pack_jobs_dev); cudaFree(c->fc_partial); cudaFree(c->h); cudaFree(c->dh);
   cudaFree(c->dlogit); cudaFree(c->head_partial); cudaFree(c->head_b_partial); cudaFree(c->loss_partial);
   cudaFree(c->sumsq_partial); cudaFree(c->hyper); cudaFree(c->step); cudaFree(c->log_slot); cudaFree(c->log_norm);
@@ -1660,7 +1662,23 @@ int arl_reset_opt_state(arl_ctx* c, void* stream) {
 // ---- sync DP ------------------------------------------------------------------------------
 int arl_comm_local_init(arl_ctx* c, int rank, int world, uint8_t* handle_out) {
   std::string err;
-  if (comm_local_init(c->comm, rank, world, c->n_params, handle_out, err)) { c->err = err; return 5; }
+  // the bf16 FC operand copy moves into the symmetric allocation too: the owner of a parameter slice P2P-stores the
+  // refreshed bf16 values next to the fp32 ones, so no rank re-packs the 3.5 M FC weights after a step
+  const bool tiles = fc_tiles_ok(c);
+  const size_t shadow_elems = (c->off_Wfc % 4 == 0 && c->H % 4 == 0) ? (size_t)c->Kfc * c->H : 0;
+  if (comm_local_init(c->comm, rank, world, c->n_params, shadow_elems, handle_out, err)) { c->err = err; return 5; }
+  if (shadow_elems) {
+    __nv_bfloat16*& local = tiles ? c->wfc_t : c->wfc_bf16;
+    ARL_CHECK(c, cudaMemcpy(c->comm.shadow, local, shadow_elems * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice));
+    cudaFree(local);
+    local = c->comm.shadow;
+    c->shadow_in_comm = true;
+    // the pack job that fills this copy must follow it
+    std::vector<PackJob> pj(c->n_pack_jobs);
+    ARL_CHECK(c, cudaMemcpy(pj.data(), c->pack_jobs_dev, pj.size() * sizeof(PackJob), cudaMemcpyDeviceToHost));
+    pj.back().dst = local;
+    ARL_CHECK(c, cudaMemcpy(c->pack_jobs_dev, pj.data(), pj.size() * sizeof(PackJob), cudaMemcpyHostToDevice));
+  }
   return 0;
 }
 int arl_comm_buffers(arl_ctx* c, float** grad_out, float** params_out) {
@@ -1691,11 +1709,13 @@ int sync_update(arl_ctx* c, cudaStream_t st) {
   a.kind = c->opt.update; a.lr = c->opt.learning_rate; a.beta1 = c->opt.beta1; a.beta2 = c->opt.beta2;
   a.eps = c->opt.epsilon; a.rho = c->opt.rho; a.clip = c->opt.grad_norm_clip;
   a.out_norm = c->log_norm; a.out_loss = c->log_loss; a.log_slot = c->log_slot; a.log_cap = c->log_cap;
+  a.shadow_begin = c->off_Wfc; a.shadow_end = c->off_Wfc + (long)c->Kfc * c->H;
+  if (fc_tiles_ok(c)) { a.shadow_tiles = 1; a.shadow_HW = c->HWlast; a.shadow_H = c->H; }
   std::string err;
   if (comm_sync_update(c->comm, a, st, err)) { c->err = err; return 5; }
   c->launches += 1;
   ARL_CHECK(c, cudaGetLastError());
-  return pack_weights(c, st, true, true);
+  return pack_weights(c, st, !c->shadow_in_comm, true);
 }
 }  // namespace
 extern "C" {

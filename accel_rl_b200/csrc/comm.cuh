@@ -30,6 +30,7 @@ struct CommDev {
   float* peer_param[kMaxRanks];
   unsigned int* peer_flag[kMaxRanks];     // each rank's arrival counter (written by peers)
   double* peer_norm[kMaxRanks];           // [world] slice sums of squares, slot = writer rank
+  __nv_bfloat16* peer_shadow[kMaxRanks];  // bf16 FC operand copy (wfc_t / wfc_bf16) of every rank; nullptr: not shared
   int rank, world;
   long n, per;                            // vector length, slice length (multiple of 4)
   float* avg_slice;                       // local scratch [per]
@@ -48,31 +49,36 @@ struct CommState {
   CommDev dev{};
   float* grad = nullptr;                  // local views
   float* param = nullptr;
+  __nv_bfloat16* shadow = nullptr;        // local bf16 FC operand copy inside the symmetric allocation
+  size_t shadow_elems = 0;
   unsigned int gen = 0;                   // grid-barrier generation carried across launches of this context
 };
 
 struct SyncUpdateArgs {
   float* param; float* grad; float* m; float* v; long n;
+  long shadow_begin, shadow_end; int shadow_tiles, shadow_HW, shadow_H;   // see UpdateParams
   const float* loss_partial; int n_loss_blocks;
   const float* hyper; int* step;
   int kind; float lr, beta1, beta2, eps, rho, clip;
   float* out_norm; float* out_loss; int* log_slot; int log_cap;
 };
 
-// symmetric layout (bytes): [grad n f32][param n f32][norm kMaxRanks f64][flag u32 .. pad]
-inline size_t comm_layout(long n, size_t* off_param, size_t* off_norm, size_t* off_flag) {
+// symmetric layout (bytes): [grad n f32][param n f32][norm kMaxRanks f64][flag u32 .. pad][shadow bf16]
+inline size_t comm_layout(long n, size_t shadow_elems, size_t* off_param, size_t* off_norm, size_t* off_flag, size_t* off_shadow) {
   size_t nb = ((size_t)n * 4 + 255) / 256 * 256;
   *off_param = nb;
   *off_norm = 2 * nb;
   *off_flag = 2 * nb + 256;
-  return 2 * nb + 512;
+  *off_shadow = 2 * nb + 512;
+  return 2 * nb + 512 + (shadow_elems * 2 + 255) / 256 * 256;
 }
 
-inline int comm_local_init(CommState& s, int rank, int world, long n, uint8_t* handle_out, std::string& err) {
+inline int comm_local_init(CommState& s, int rank, int world, long n, size_t shadow_elems, uint8_t* handle_out, std::string& err) {
   if (world < 1 || world > kMaxRanks) { err = "world size must be in [1,8]"; return 1; }
   s.rank = rank; s.world = world; s.n = n;
-  size_t op, on, of;
-  s.bytes = comm_layout(n, &op, &on, &of);
+  size_t op, on, of, os;
+  s.shadow_elems = shadow_elems;
+  s.bytes = comm_layout(n, shadow_elems, &op, &on, &of, &os);
   cudaError_t e = cudaMalloc(&s.base, s.bytes);
   if (e != cudaSuccess) { err = std::string("cudaMalloc(sym): ") + cudaGetErrorString(e); return 1; }
   cudaMemset(s.base, 0, s.bytes);
@@ -83,12 +89,13 @@ inline int comm_local_init(CommState& s, int rank, int world, long n, uint8_t* h
   memcpy(handle_out, &h, 64);
   s.grad = reinterpret_cast<float*>(s.base);
   s.param = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s.base) + op);
+  s.shadow = shadow_elems ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(s.base) + os) : nullptr;
   return 0;
 }
 
 inline int comm_connect(CommState& s, const uint8_t* all_handles, std::string& err) {
-  size_t op, on, of;
-  comm_layout(s.n, &op, &on, &of);
+  size_t op, on, of, os;
+  comm_layout(s.n, s.shadow_elems, &op, &on, &of, &os);
   s.peer_base.assign(s.world, nullptr);
   for (int r = 0; r < s.world; ++r) {
     if (r == s.rank) { s.peer_base[r] = s.base; continue; }
@@ -106,6 +113,7 @@ inline int comm_connect(CommState& s, const uint8_t* all_handles, std::string& e
     d.peer_param[r] = reinterpret_cast<float*>(b + op);
     d.peer_norm[r] = reinterpret_cast<double*>(b + on);
     d.peer_flag[r] = reinterpret_cast<unsigned int*>(b + of);
+    d.peer_shadow[r] = s.shadow_elems ? reinterpret_cast<__nv_bfloat16*>(b + os) : nullptr;
   }
   cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&d.avg_slice), (size_t)d.per * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d.block_partial), kSyncBlocks * sizeof(double));
@@ -151,7 +159,7 @@ ARL_DEVINL void xgpu_barrier_thread(const CommDev& d) {
 }
 
 // grid-wide barrier for a co-resident (cooperative) grid; optional cross-GPU barrier by block 0
-ARL_DEVINL void grid_barrier(const CommDev& d, unsigned int& gen, bool cross_gpu) {
+ARL_DEVINL void grid_barrier(const CommDev& d, unsigned int& gen, bool cross_gpu, bool publish_norm = false) {
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -162,6 +170,12 @@ ARL_DEVINL void grid_barrier(const CommDev& d, unsigned int& gen, bool cross_gpu
       long long t0 = clock64();
       while ((int)(atomicAdd(d.grid_counter, 0u) - gen) < 0) {          // wrap-safe
         if (clock64() - t0 > 20000000000LL) dev_fail(301);
+      }
+      if (publish_norm) {
+        __threadfence();
+        double t = 0.0;
+        for (int b = 0; b < (int)gridDim.x; ++b) t += reinterpret_cast<volatile double*>(d.block_partial)[b];
+        for (int r = 0; r < d.world; ++r) d.peer_norm[r][d.rank] = t;
       }
       if (cross_gpu) xgpu_barrier_thread(d);
       __threadfence();
@@ -183,7 +197,7 @@ __global__ void __launch_bounds__(kSyncThreads) sync_allreduce_update_kernel(Com
   // can be replayed from a CUDA graph.  Every block reads it before it can arrive at the first barrier; block 0
   // advances it after the last one.
   unsigned int gen = *reinterpret_cast<volatile unsigned int*>(d.grid_counter + 2);
-  const unsigned int gen_next = gen + 4u * gridDim.x;
+  const unsigned int gen_next = gen + 3u * gridDim.x;
   const long begin = (long)d.rank * d.per;
   const long end = min(d.n, begin + d.per);
   const long len = end > begin ? end - begin : 0;
@@ -196,26 +210,42 @@ __global__ void __launch_bounds__(kSyncThreads) sync_allreduce_update_kernel(Com
   // 1. all gradients complete on every GPU
   grid_barrier(d, gen, true);
 
-  // 2. reduce my slice over peers (P2P loads), average, local scratch + sum of squares
+  // 2. reduce my slice over peers (P2P loads), average, local scratch + sum of squares.  Four independent float4
+  //    groups per thread are in flight at once: a peer load is ~2-3 us of NVLink latency, the loop is latency bound.
   const float inv_world = 1.f / (float)d.world;
   double acc = 0.0;
-  for (long i = gtid; i < len4; i += gsz) {
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long i0 = gtid; i0 < len4; i0 += 4 * gsz) {
+    float4 sum[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) sum[u] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int r = 0; r < d.world; ++r) {
-      const float4 g = *reinterpret_cast<const float4*>(d.peer_grad[r] + begin + 4 * i);
-      s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
+      float4 g[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long i = i0 + u * gsz;
+        g[u] = (i < len4) ? *reinterpret_cast<const float4*>(d.peer_grad[r] + begin + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { sum[u].x += g[u].x; sum[u].y += g[u].y; sum[u].z += g[u].z; sum[u].w += g[u].w; }
     }
-    s.x *= inv_world; s.y *= inv_world; s.z *= inv_world; s.w *= inv_world;
-    reinterpret_cast<float4*>(d.avg_slice)[i] = s;
-    acc += (double)(s.x * s.x + s.y * s.y) + (double)(s.z * s.z + s.w * s.w);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long i = i0 + u * gsz;
+      if (i < len4) {
+        float4 t = sum[u];
+        t.x *= inv_world; t.y *= inv_world; t.z *= inv_world; t.w *= inv_world;
+        reinterpret_cast<float4*>(d.avg_slice)[i] = t;
+        acc += (double)(t.x * t.x + t.y * t.y) + (double)(t.z * t.z + t.w * t.w);
+      }
+    }
   }
   if (gtid == 0) {
     for (long i = len4 << 2; i < len; ++i) {
-      float s = 0.f;
-      for (int r = 0; r < d.world; ++r) s += d.peer_grad[r][begin + i];
-      s *= inv_world;
-      d.avg_slice[i] = s;
-      acc += (double)s * s;
+      float t = 0.f;
+      for (int r = 0; r < d.world; ++r) t += d.peer_grad[r][begin + i];
+      t *= inv_world;
+      d.avg_slice[i] = t;
+      acc += (double)t * t;
     }
   }
   acc = warp_sum_d(acc);
@@ -226,17 +256,11 @@ __global__ void __launch_bounds__(kSyncThreads) sync_allreduce_update_kernel(Com
     for (int w = 0; w < kSyncThreads / 32; ++w) t += s_red[w];
     d.block_partial[blockIdx.x] = t;
   }
-  grid_barrier(d, gen, false);
+  // 3. ONE barrier: when every block has arrived, block 0 adds up the block partials (fixed order), publishes this
+  //    slice's sum of squares to every peer, runs the cross-GPU barrier and only then releases the grid
+  grid_barrier(d, gen, true, true);
 
-  // 3. publish my slice's sum of squares to every peer, then barrier across GPUs
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    double t = 0.0;
-    for (int b = 0; b < (int)gridDim.x; ++b) t += d.block_partial[b];
-    for (int r = 0; r < d.world; ++r) d.peer_norm[r][d.rank] = t;
-  }
-  grid_barrier(d, gen, true);
-
-  // 4. global norm (rank order), clip, update my slice, P2P-store new params to every peer
+  // 4. global norm (rank order), clip, update my slice, P2P-store new params (+ bf16 FC operand copy) to every peer
   if (threadIdx.x == 0) {
     double t = 0.0;
     const volatile double* np = d.peer_norm[d.rank];
@@ -265,21 +289,62 @@ __global__ void __launch_bounds__(kSyncThreads) sync_allreduce_update_kernel(Com
   }
   __syncthreads();
   const float scale = s_scale, alpha = s_alpha;
-  for (long i = gtid; i < len; i += gsz) {
-    const long gi = begin + i;
-    float g = d.avg_slice[i] * scale;
-    float p = a.param[gi];
+  const bool share_shadow = d.peer_shadow[0] != nullptr;
+  for (long i = gtid; i < len4; i += gsz) {
+    const long gi = begin + 4 * i;                      // begin is a multiple of 4
+    const float4 g4 = reinterpret_cast<const float4*>(d.avg_slice)[i];
+    const float4 p4 = *reinterpret_cast<const float4*>(a.param + gi);
+    const float4 v4 = *reinterpret_cast<const float4*>(a.v + gi);
+    float g[4] = {g4.x * scale, g4.y * scale, g4.z * scale, g4.w * scale};
+    float pp[4] = {p4.x, p4.y, p4.z, p4.w};
+    float vv[4] = {v4.x, v4.y, v4.z, v4.w};
     if (a.kind == 0) {
-      float m = a.beta1 * a.m[gi] + (1.f - a.beta1) * g;
-      float v = a.beta2 * a.v[gi] + (1.f - a.beta2) * g * g;
-      a.m[gi] = m; a.v[gi] = v;
-      p -= alpha * m / (sqrtf(v) + a.eps);
+      const float4 m4 = *reinterpret_cast<const float4*>(a.m + gi);
+      float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        mm[k] = a.beta1 * mm[k] + (1.f - a.beta1) * g[k];
+        vv[k] = a.beta2 * vv[k] + (1.f - a.beta2) * g[k] * g[k];
+        pp[k] -= alpha * mm[k] / (sqrtf(vv[k]) + a.eps);
+      }
+      *reinterpret_cast<float4*>(a.m + gi) = make_float4(mm[0], mm[1], mm[2], mm[3]);
     } else {
-      float ac = a.rho * a.v[gi] + (1.f - a.rho) * g * g;
-      a.v[gi] = ac;
-      p -= alpha * g / sqrtf(ac + a.eps);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        vv[k] = a.rho * vv[k] + (1.f - a.rho) * g[k] * g[k];
+        pp[k] -= alpha * g[k] / sqrtf(vv[k] + a.eps);
+      }
     }
-    for (int r = 0; r < d.world; ++r) d.peer_param[r][gi] = p;
+    *reinterpret_cast<float4*>(a.v + gi) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    const float4 pn = make_float4(pp[0], pp[1], pp[2], pp[3]);
+    for (int r = 0; r < d.world; ++r) *reinterpret_cast<float4*>(d.peer_param[r] + gi) = pn;
+    if (share_shadow && gi >= a.shadow_begin && gi + 4 <= a.shadow_end) {
+      long off = gi - a.shadow_begin;
+      if (a.shadow_tiles) {
+        const unsigned ou = (unsigned)off, rr = ou / (unsigned)a.shadow_H;
+        off = fc_tile_index(rr, (int)(ou - rr * (unsigned)a.shadow_H), a.shadow_HW, a.shadow_H);
+      }
+      const uint2 pk = make_uint2(pack_bf16x2(pp[0], pp[1]), pack_bf16x2(pp[2], pp[3]));
+      for (int r = 0; r < d.world; ++r) *reinterpret_cast<uint2*>(d.peer_shadow[r] + off) = pk;
+    }
+  }
+  if (gtid == 0) {
+    for (long i = len4 << 2; i < len; ++i) {
+      const long gi = begin + i;
+      float g = d.avg_slice[i] * scale;
+      float p = a.param[gi];
+      if (a.kind == 0) {
+        float m = a.beta1 * a.m[gi] + (1.f - a.beta1) * g;
+        float v = a.beta2 * a.v[gi] + (1.f - a.beta2) * g * g;
+        a.m[gi] = m; a.v[gi] = v;
+        p -= alpha * m / (sqrtf(v) + a.eps);
+      } else {
+        float ac = a.rho * a.v[gi] + (1.f - a.rho) * g * g;
+        a.v[gi] = ac;
+        p -= alpha * g / sqrtf(ac + a.eps);
+      }
+      for (int r = 0; r < d.world; ++r) d.peer_param[r][gi] = p;
+    }
   }
   // 5. all parameter slices have landed everywhere
   grid_barrier(d, gen, true);
