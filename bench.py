@@ -27,6 +27,16 @@ sys.path.insert(0, ROOT)
 # per-sample MACs of preset 1 @ (4,104,80), A=4
 MACS = {"conv0": 3891200, "conv1": 3538944, "conv2": 3981312, "fc": 3538944}
 FLOP_PER_ENV_STEP_PPO = 357.9e6     # 1 act-fwd + 1/128 bootstrap fwd + 4 x train (81.936 MFLOP)
+FLOP_PER_ENV_STEP_CONV = 265.7e6    # conv tiles only: the north-star's "conv-tile roofline" numerator
+
+
+def ncu_traffic(label):
+    """DRAM bytes per launch of `label` from the committed ncu --set full capture (None when not captured)"""
+    p = os.path.join(ROOT, "profiles", "r1b_traffic.json")
+    try:
+        return json.load(open(p))["kernels"].get(label)
+    except Exception:
+        return None
 
 
 def parse():
@@ -252,7 +262,9 @@ def run_ours(args):
         for k in kernels:
             if k["tflops"] is not None:
                 roof = {"bound": "tensor", "kernel": k["kernel"], "achieved": k["tflops"], "peak": pk["tf_sustained"],
-                        "unit": "TFLOP/s", "frac": round(k["tflops"] / pk["tf_sustained"], 4), "traffic": None,
+                        "unit": "TFLOP/s", "frac": round(k["tflops"] / pk["tf_sustained"], 4),
+                        "traffic": ncu_traffic(k["kernel"]),
+                        "traffic_note": "DRAM bytes per launch, ncu --set full with cold caches (profiles/r1b_full.md)",
                         "peak_source": pk["src"] + " (sustained bf16, kernel timed inside a long step)",
                         "share_of_step": k["share"]}
                 break
@@ -272,8 +284,10 @@ def run_ours(args):
             "model_flops_per_env_step": FLOP_PER_ENV_STEP_PPO if args.spec == 1 else None,
             "tensor_roofline_frac_whole_step": round(value / world * FLOP_PER_ENV_STEP_PPO / (pk["tf_sustained"] * 1e12), 4)
             if args.spec == 1 else None,
+            "conv_tile_roofline_frac": round(value / world * FLOP_PER_ENV_STEP_CONV / (pk["tf_sustained"] * 1e12), 4)
+            if args.spec == 1 else None,
             "roofline": roof,
-            "kernels": kernels[:14],
+            "kernels": kernels[:16],
             "host_wall_s": round(wall, 3),
             "phases": phases,
         }
