@@ -112,6 +112,7 @@ SIGNATURES = {
     "arl_clip_update": (C.c_int, [_P, C.c_float, _P]),
     "arl_train_minibatches": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
     "arl_train_minibatches_sync": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
+    "arl_train_minibatches_async": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
     "arl_read_logs": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(C.c_int), _P]),
     "arl_reset_opt_state": (C.c_int, [_P, _P]),
     "arl_comm_local_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),

@@ -126,6 +126,7 @@ struct arl_ctx {
   float* head_b_partial = nullptr; // [G][A+1]
   float* loss_partial = nullptr;   // [kLossBlocks][4]
   double* sumsq_partial = nullptr;
+  unsigned long long* ticket = nullptr; // grid-barrier ticket of update_fused_kernel
   float* hyper = nullptr;          // [0] lr_mult
   int* step = nullptr;             // Adam t
   int* log_slot = nullptr;
@@ -154,7 +155,8 @@ struct arl_ctx {
   cudaGraphExec_t train_graph = nullptr;
   const int* train_graph_idx = nullptr;
   int train_graph_mb = 0;
-  bool train_graph_sync = false, sync_graph_failed = false;
+  int train_graph_sync = 0;
+  bool sync_graph_failed = false;
   long launches = 0;
   // per-kernel CUDA-event profiling (arl_profile_*): events recorded after each launch when enabled
   bool prof_on = false;
@@ -808,6 +810,7 @@ int alloc_net(arl_ctx* c) {
   if (dev_alloc(c, &c->head_b_partial, (size_t)64 * (c->A + 1))) return 1;
   if (dev_alloc(c, &c->loss_partial, (size_t)R * 4)) return 1;
   if (dev_alloc(c, &c->sumsq_partial, (size_t)kSumsqBlocks)) return 1;
+  if (dev_alloc(c, &c->ticket, 4)) return 1;
   if (dev_alloc(c, &c->hyper, 8)) return 1;
   float one = 1.f;
   ARL_CHECK(c, cudaMemcpy(c->hyper, &one, sizeof(float), cudaMemcpyHostToDevice));
@@ -913,10 +916,11 @@ HeadParams head_base(arl_ctx* c, int n, int S) {
 }
 
 int policy_forward16(arl_ctx* c, const __nv_bfloat16* obs16, int n, const int* out_rows, float* prob, float* value,
-                     const double* uniforms, uint8_t* actions, bool pc, cudaStream_t st) {
+                     const double* uniforms, uint8_t* actions, bool pc, cudaStream_t st, const EnvStepArgs* es = nullptr) {
   int S = 0;
   if (forward_trunk(c, obs16, nullptr, nullptr, n, &S, pc, st)) return 1;
   HeadParams p = head_base(c, n, S);
+  if (es) { p.es = *es; p.es_on = 1; }
   p.out_rows = out_rows; p.prob = prob; p.value = value; p.uniforms = uniforms; p.actions = uniforms ? actions : nullptr;
   ARL_CHECK(c, launch_k(head_kernel<0>, dim3(n), dim3(kHeadThreads), 0, st, p));
   c->launches++;
@@ -1178,9 +1182,6 @@ int pack_weights(arl_ctx* c, cudaStream_t st, bool with_fc = true, bool advance 
 int clip_update(arl_ctx* c, float gscale, cudaStream_t st) {
   if (!c->opt_set) ARL_FAIL(c, "optimizer not configured");
   if (!c->m || !c->v) ARL_FAIL(c, "optimizer state not bound");
-  ARL_CHECK(c, launch_k(sumsq_kernel, dim3(kSumsqBlocks), dim3(256), 0, st, c->grad, c->n_params, gscale, c->sumsq_partial));
-  c->launches++;
-  prof_mark(c, "grad_sumsq", st);
   UpdateParams u{};
   u.param = c->params; u.grad = c->grad; u.m = c->m; u.v = c->v; u.n = c->n_params;
   u.sumsq_partial = c->sumsq_partial; u.n_partial = kSumsqBlocks;
@@ -1193,7 +1194,16 @@ int clip_update(arl_ctx* c, float gscale, cudaStream_t st) {
   bool fused_cast = (c->off_Wfc % 4 == 0) && (c->H % 4 == 0);
   if (fc_tiles_ok(c)) { u.shadow = c->wfc_t; u.shadow_tiles = 1; u.shadow_HW = c->HWlast; u.shadow_H = c->H; }
   if (!fused_cast) u.shadow = nullptr;
-  ARL_CHECK(c, launch_k(update_kernel, dim3(148 * 4), dim3(256), 0, st, u));
+  // norm + clip + update in one launch (update_fused_kernel); ARL_FUSED_UPDATE=0 keeps the two-kernel form
+  static const bool fused = !(getenv("ARL_FUSED_UPDATE") && atoi(getenv("ARL_FUSED_UPDATE")) == 0);
+  if (fused) {
+    ARL_CHECK(c, launch_k(update_fused_kernel, dim3(kSumsqBlocks), dim3(256), 0, st, u, c->sumsq_partial, c->ticket));
+  } else {
+    ARL_CHECK(c, launch_k(sumsq_kernel, dim3(kSumsqBlocks), dim3(256), 0, st, c->grad, c->n_params, gscale, c->sumsq_partial));
+    c->launches++;
+    prof_mark(c, "grad_sumsq", st);
+    ARL_CHECK(c, launch_k(update_kernel, dim3(148 * 4), dim3(256), 0, st, u));
+  }
   c->launches++;
   prof_mark(c, "clip_update", st);
   ARL_CHECK(c, cudaGetLastError());
@@ -1244,15 +1254,12 @@ int rollout_begin(arl_ctx* c, cudaStream_t st) {
 int rollout_step(arl_ctx* c, int s_idx, const uint8_t* staging, cudaStream_t st) {
   const arl_sampler_cfg& s = c->sc;
   const int B = s.n_envs, T = s.horizon;
+  // the env step of env e runs in the head kernel's block e right after its action is sampled
+  EnvStepArgs es{synth_cfg(s), c->est, c->tout, c->cmd, s.rewards, s.dones, s.raw_reward, s.need_reset, B, T, s_idx,
+                 s.max_path_length, s.discount, s.mid_batch_reset, s.clip_reward, s.episodic_lives};
   if (policy_forward16(c, c->step_obs16, B, c->rows_tab + (long)s_idx * B, s.prob, s.value,
-                       s.uniforms + (long)s_idx * B, s.actions, c->pc_mode >= 2, st))
+                       s.uniforms + (long)s_idx * B, s.actions, c->pc_mode >= 2, st, &es))
     return 1;
-  ARL_CHECK(c, launch_k(env_step_kernel, dim3((B + 127) / 128), dim3(128), 0, st, synth_cfg(s), c->est, c->tout, c->cmd, s.rewards, s.dones,
-                                                   s.raw_reward, s.need_reset, B, T, s_idx, s.max_path_length,
-                                                   s.discount, s.mid_batch_reset, s.clip_reward, s.episodic_lives));
-  c->launches++;
-  prof_mark(c, "env_step", st);
-  ARL_CHECK(c, cudaGetLastError());
   return launch_frame(c, staging, s_idx + 1, s_idx + 1 < T, st);
 }
 
@@ -1275,7 +1282,8 @@ int rollout_end(arl_ctx* c, cudaStream_t st) {
 
 namespace {
 int sync_update(arl_ctx* c, cudaStream_t st);
-int train_minibatches(arl_ctx* c, const int* idx, int mb_size, int count, bool sync, cudaStream_t st);
+int train_minibatches(arl_ctx* c, const int* idx, int mb_size, int count, int sync, cudaStream_t st);
+int async_push_pull(arl_ctx* c, cudaStream_t st);
 }
 
 // ===========================================================================
@@ -1571,18 +1579,24 @@ int arl_grad_minibatch(arl_ctx* c, const int* idx, int mb_size, void* stream) {
 int arl_clip_update(arl_ctx* c, float gscale, void* stream) { return clip_update(c, gscale, (cudaStream_t)stream); }
 
 int arl_train_minibatches(arl_ctx* c, const int* idx, int mb_size, int count, void* stream) {
-  return train_minibatches(c, idx, mb_size, count, false, (cudaStream_t)stream);
+  return train_minibatches(c, idx, mb_size, count, 0, (cudaStream_t)stream);
 }
 /* same loop with the synchronous data-parallel step (fused P2P all-reduce + clip + update) closing every minibatch */
 int arl_train_minibatches_sync(arl_ctx* c, const int* idx, int mb_size, int count, void* stream) {
   if (!c->comm.ready) ARL_FAIL(c, "comm not connected");
-  return train_minibatches(c, idx, mb_size, count, true, (cudaStream_t)stream);
+  return train_minibatches(c, idx, mb_size, count, 1, (cudaStream_t)stream);
+}
+/* ... and for the asynchronous learner: every minibatch ends with arl_async_push_pull */
+int arl_train_minibatches_async(arl_ctx* c, const int* idx, int mb_size, int count, void* stream) {
+  if (!c->async_.ready) ARL_FAIL(c, "async store not connected");
+  return train_minibatches(c, idx, mb_size, count, 2, (cudaStream_t)stream);
 }
 
 }  // extern "C"
 namespace {
-int train_minibatches(arl_ctx* c, const int* idx, int mb_size, int count, bool sync, cudaStream_t st) {
-  auto step = [&](cudaStream_t s_) { return sync ? sync_update(c, s_) : clip_update(c, 1.f, s_); };
+int train_minibatches(arl_ctx* c, const int* idx, int mb_size, int count, int sync, cudaStream_t st) {
+  // sync: 0 = local clip + update, 1 = synchronous DP step, 2 = asynchronous push/pull
+  auto step = [&](cudaStream_t s_) { return sync == 1 ? sync_update(c, s_) : sync == 2 ? async_push_pull(c, s_) : clip_update(c, 1.f, s_); };
   if (!(c->sampler_set && c->t_obs == c->sc.observations && c->roll_obs16) || (sync && c->sync_graph_failed)) {
     // training inputs that are not the sampler's rollout buffers: plain launches, one minibatch at a time
     const bool replay_idx = c->sampler_set && c->t_obs == c->sc.observations && c->roll_obs16;
@@ -1736,8 +1750,11 @@ int arl_async_connect(arl_ctx* c, const uint8_t* rank0_handle) {
 int arl_async_regions(arl_ctx* c) { return c->async_.dev.n_locks; }
 
 /* local clip -> chunk-locked update of the central (p, m, v) with the local gradient -> pull the new p */
-int arl_async_push_pull(arl_ctx* c, void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
+int arl_async_push_pull(arl_ctx* c, void* stream) { return async_push_pull(c, (cudaStream_t)stream); }
+
+}  // extern "C"
+namespace {
+int async_push_pull(arl_ctx* c, cudaStream_t st) {
   if (!c->async_.ready) ARL_FAIL(c, "async store not connected");
   if (!c->opt_set) ARL_FAIL(c, "optimizer not configured");
   sumsq_kernel<<<kSumsqBlocks, 256, 0, st>>>(c->grad, c->n_params, 1.f, c->sumsq_partial);
@@ -1760,6 +1777,8 @@ int arl_async_push_pull(arl_ctx* c, void* stream) {
   ARL_CHECK(c, cudaGetLastError());
   return pack_weights(c, st, !fused_cast, true);
 }
+}  // namespace
+extern "C" {
 
 /* test hook: copy central array `which` (0 = p, 1 = m, 2 = v / accumulator) to the host */
 int arl_async_read_central(arl_ctx* c, int which, float* host_out, long n, void* stream) {

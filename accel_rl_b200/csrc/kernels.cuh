@@ -75,15 +75,31 @@ struct FrameCmd {
 // One thread per env.  Mirrors AtariEnv.step (envs/atari_env.py:65-78), _done_episodic_lives
 // (:185-191), reset (:93-100) and ResetCollector/NonResetCollector.collect
 // (sampler/act_server/alternating/overlap/worker.py:25-113) for step s of the batch.
-__global__ void env_step_kernel(SynthCfg cfg, EnvState st, TrajOut tout, FrameCmd* __restrict__ cmd,
-                                float* __restrict__ rewards, uint8_t* __restrict__ dones,
-                                float* __restrict__ raw_reward, uint8_t* __restrict__ info_need_reset,
-                                int n_envs, int T, int s, int max_path_length, float discount,
-                                int mid_batch_reset, int clip_reward, int episodic_lives) {
+struct EnvStepArgs {
+  SynthCfg cfg; EnvState st; TrajOut tout; FrameCmd* cmd;
+  float* rewards; uint8_t* dones; float* raw_reward; uint8_t* info_need_reset;
+  int n_envs, T, s, max_path_length; float discount; int mid_batch_reset, clip_reward, episodic_lives;
+};
+
+ARL_DEVINL void env_step_one(const EnvStepArgs& a, int e);
+
+__global__ void env_step_kernel(EnvStepArgs a) {
   pdl_wait();
   pdl_trigger();
   int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_envs) return;
+  if (e >= a.n_envs) return;
+  env_step_one(a, e);
+}
+
+// one env, one thread: also called by thread 0 of head_kernel<0> right after it sampled env e's action (the rollout
+// step then needs no separate env-step launch)
+ARL_DEVINL void env_step_one(const EnvStepArgs& a, int e) {
+  const SynthCfg& cfg = a.cfg; const EnvState& st = a.st; const TrajOut& tout = a.tout; FrameCmd* cmd = a.cmd;
+  float* rewards = a.rewards; uint8_t* dones = a.dones; float* raw_reward = a.raw_reward;
+  uint8_t* info_need_reset = a.info_need_reset;
+  const int T = a.T, s = a.s, max_path_length = a.max_path_length, mid_batch_reset = a.mid_batch_reset;
+  const int clip_reward = a.clip_reward, episodic_lives = a.episodic_lives;
+  const float discount = a.discount;
   FrameCmd c;
   c.flags = 0;
   if (!mid_batch_reset && st.need_reset[e]) {
@@ -540,6 +556,7 @@ struct HeadParams {
   // train outputs
   __nv_bfloat16* h_out;     // [M][H] post-ReLU hidden (bf16)
   __nv_bfloat16* dh_out;    // [M][H] gradient w.r.t. FC pre-activation (bf16)
+  EnvStepArgs es; int es_on;   // mode 0: run the env step of env `row` after sampling its action
   __nv_bfloat16* dh_t;      // optional second copy as [H/64][dh_rows][64] planes, chunk-swizzled (fcgemm.cuh)
   int dh_rows;
   float* dlogit_out;        // [M][A+1]  (last column: dV)
@@ -644,6 +661,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadParams p) {
           if (a < p.A) { cs = __fadd_rn(cs, prob[a]); k += ((double)cs < u) ? 1 : 0; }
         p.actions[orow] = (uint8_t)min(k, p.A - 1);
       }
+      if (p.es_on) env_step_one(p.es, row);
     }
   } else {
     const long src = p.idx ? p.idx[(p.idx_off ? (long)p.idx_off[0] * p.M : 0) + row] : row;
@@ -867,8 +885,14 @@ __global__ void __launch_bounds__(256) finalize_grads_kernel(const GradJob* __re
 // ===========================================================================
 constexpr int kSumsqBlocks = 592;   // 4 x 148
 
+ARL_DEVINL void sumsq_body(const float* __restrict__ g, long n, float gscale, double* __restrict__ partial);
+
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long n, float gscale,
                                                      double* __restrict__ partial) {
+  sumsq_body(g, n, gscale, partial);
+}
+
+ARL_DEVINL void sumsq_body(const float* __restrict__ g, long n, float gscale, double* __restrict__ partial) {
   pdl_wait();
   pdl_trigger();
   double acc = 0.0;
@@ -917,9 +941,38 @@ struct UpdateParams {
   int shadow_tiles, shadow_HW, shadow_H;                  // != 0: the copy is the tiled wfc_t layout (H % 4 == 0)
 };
 
+ARL_DEVINL void update_body(const UpdateParams& p);
+
 __global__ void __launch_bounds__(256) update_kernel(UpdateParams p) {
   pdl_wait();
   pdl_trigger();
+  update_body(p);
+}
+
+// sum of squares + clip + update in ONE launch: phase 1 = sumsq_kernel's arithmetic (same grid, same partials, same
+// order), a grid-wide ticket barrier (all kSumsqBlocks blocks are co-resident: 4 per SM), phase 2 = update_kernel's.
+// The ticket counter only grows (64-bit), so the launch carries no host state and replays from a CUDA graph.
+__global__ void __launch_bounds__(256, 4) update_fused_kernel(UpdateParams p, double* __restrict__ partial,
+                                                              unsigned long long* __restrict__ ticket) {
+  pdl_wait();
+  pdl_trigger();
+  sumsq_body(p.grad, p.n, p.gscale, partial);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long t = atomicAdd(ticket, 1ULL);
+    const unsigned long long target = (t / gridDim.x + 1ULL) * gridDim.x;
+    long long t0 = clock64();
+    while (atomicAdd(ticket, 0ULL) < target) {
+      if (clock64() - t0 > 20000000000LL) dev_fail(320);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  update_body(p);
+}
+
+ARL_DEVINL void update_body(const UpdateParams& p) {
   __shared__ double s_red[8];
   __shared__ float s_scale, s_alpha;
   // every block: reduce the partial sums in the same order -> identical norm everywhere

@@ -176,7 +176,8 @@ class Engine(object):
 
     def train_minibatches(self, idx, mb_size, count, sync=False):
         self._keep["idx"] = idx
-        fn = self.lib.arl_train_minibatches_sync if sync else self.lib.arl_train_minibatches
+        fn = {False: self.lib.arl_train_minibatches, True: self.lib.arl_train_minibatches_sync, "sync": self.lib.arl_train_minibatches_sync,
+              "async": self.lib.arl_train_minibatches_async}[sync]
         self.check(fn(self.ctx, L.ptr(idx), int(mb_size), int(count), self._s()))
 
     def read_logs(self, cap=4096):

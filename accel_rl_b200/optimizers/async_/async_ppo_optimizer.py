@@ -22,14 +22,9 @@ class AsyncPpoOptimizer(BaseAsyncOptimizer, PpoOptimizer):
 
     def _do_updates(self, data_length):
         n_mb = self._upload_indices(data_length)
-        eng, mb = self._engine, self._minibatch_size
-        k = 0
-        for _ in range(self._epochs):
-            for _ in range(n_mb):
-                eng.grad_minibatch(self._idx_dev[k * mb:(k + 1) * mb], mb)
-                eng.async_push_pull()
-                k += 1
-        losses, grad_norms = eng.read_logs()
+        # per minibatch: local gradient -> chunk-locked push into the central state -> pull (one CUDA graph each)
+        self._engine.train_minibatches(self._idx_dev, self._minibatch_size, n_mb * self._epochs, sync="async")
+        losses, grad_norms = self._engine.read_logs()
         return list(losses), list(grad_norms)
 
     @property

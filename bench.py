@@ -54,6 +54,10 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-steps", type=int, default=8, help="rollout steps in the bounded CPU sample")
+    ap.add_argument("--algo", default="ppo", choices=["ppo", "a2c"],
+                    help="a2c: BASELINE configs[2]-style A2C (one full-batch RMSProp step per rollout; use --envs 1024 --horizon 5)")
+    ap.add_argument("--parallelism", default="sync", choices=["sync", "async"],
+                    help="multi-GPU learner: sync (configs[3], fused all-reduce) or async (configs[4], central store + chunk locks)")
     ap.add_argument("--workload", default="ppo", choices=["ppo", "frame_sweep"],
                     help="ppo: the headline metric (default); frame_sweep: BASELINE configs[2] frame-kernel HBM GB/s sweep")
     return ap.parse_args()
@@ -121,15 +125,21 @@ def build_runner(args, frame_feed, rank, world):
         EnvCls=AtariEnv, env_args=dict(game="breakout", max_start_noops=0, synth_rules=rules),
         horizon=args.horizon, n_parallel=args.envs // 8, envs_per=4, max_path_length=27000, mid_batch_reset=True,
         max_decorrelation_steps=0, frame_feed=frame_feed)
-    opt_args = dict(minibatch_size=args.minibatch, epochs=args.epochs)
+    from accel_rl_b200.algos import A2C, mA2C, mA3C, mAPPO
+    from accel_rl_b200.runners import AccelRLAsync
+    a2c = getattr(args, "algo", "ppo") == "a2c"
+    asyn = getattr(args, "parallelism", "sync") == "async"
+    opt_args = dict() if a2c else dict(minibatch_size=args.minibatch, epochs=args.epochs)
     policy = AtariCnnPolicy(**cnn_specs[args.spec])
     n_steps = args.envs * args.horizon * 10 ** 6
-    if world > 1:
-        runner = AccelRLSync(algo=mPPO(optimizer_args=opt_args), policy=policy, sampler=sampler, n_steps=n_steps, seed=0,
-                             affinities=[dict(gpu=torch.cuda.current_device())] * world, log_interval_steps=10 ** 12)
+    if world > 1 or asyn:
+        Algo = (mA3C if a2c else mAPPO) if asyn else (mA2C if a2c else mPPO)
+        Runner = AccelRLAsync if asyn else AccelRLSync
+        runner = Runner(algo=Algo(optimizer_args=opt_args), policy=policy, sampler=sampler, n_steps=n_steps, seed=0,
+                        affinities=[dict(gpu=torch.cuda.current_device())] * world, log_interval_steps=10 ** 12)
     else:
-        runner = AccelRL(algo=PPO(optimizer_args=opt_args), policy=policy, sampler=sampler, n_steps=n_steps, seed=0,
-                         affinities=dict(), log_interval_steps=10 ** 12)
+        runner = AccelRL(algo=(A2C if a2c else PPO)(optimizer_args=opt_args), policy=policy, sampler=sampler,
+                         n_steps=n_steps, seed=0, affinities=dict(), log_interval_steps=10 ** 12)
     runner.startup()
     return runner
 
@@ -248,7 +258,8 @@ def run_ours(args):
     result = None
     phases = phase_split(runner, itr)
     if rank == 0:
-        bd = kernel_breakdown(runner, args) if (args.spec == 1 and world == 1) else {}
+        bd = kernel_breakdown(runner, args) if (args.spec == 1 and world == 1 and args.algo == "ppo" and
+                                                args.parallelism == "sync") else {}
         # dominant kernel by time per PPO iteration
         roof = None
         kernels = []
@@ -268,24 +279,30 @@ def run_ours(args):
                         "peak_source": pk["src"] + " (sustained bf16, kernel timed inside a long step)",
                         "share_of_step": k["share"]}
                 break
+        # per-env-step model FLOPs: PPO = fwd + fwd/T + epochs*train; A2C = fwd + fwd/T + train
+        fwd, train, cfwd, ctrain = 29.906e6, 81.936e6, 22.823e6, 60.686e6
+        k_train = args.epochs if args.algo == "ppo" else 1
+        flop_step = (fwd * (1 + 1.0 / args.horizon) + k_train * train) if args.spec == 1 else None
+        flop_conv = (cfwd * (1 + 1.0 / args.horizon) + k_train * ctrain) if args.spec == 1 else None
         result = {
-            "metric": "env-steps/sec (PPO Atari, 256 envs/GPU)", "value": round(value, 1), "unit": "env-steps/s",
+            "metric": "env-steps/sec (%s Atari, %d envs/GPU)" % (args.algo.upper(), args.envs), "value": round(value, 1),
+            "unit": "env-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "PPO Breakout-shaped, %d envs/GPU x %d-step rollout, cnn preset %d @ (4,104,80), "
                                    "%d epochs x mb %d, Adam; synthetic 210x160 grayscale emulator frames"
                                    % (args.envs, args.horizon, args.spec, args.epochs, args.minibatch),
+                       "algo": args.algo, "learner": ("single" if world == 1 and args.parallelism == "sync" else args.parallelism),
                        "envs_per_gpu": args.envs, "horizon": args.horizon, "parallelism": "dp%d" % world,
                        "l2_policy": "inputs larger than L2 (1.09 GB rollout buffer, %d MB frame pool)" %
                                     (args.pool_frames * 33600 // 2 ** 20),
                        "step": "one full PPO iteration"},
             "clocks": clk,
             "gpu_launches": int(launches),
-            "model_flops_per_env_step": FLOP_PER_ENV_STEP_PPO if args.spec == 1 else None,
-            "tensor_roofline_frac_whole_step": round(value / world * FLOP_PER_ENV_STEP_PPO / (pk["tf_sustained"] * 1e12), 4)
-            if args.spec == 1 else None,
-            "conv_tile_roofline_frac": round(value / world * FLOP_PER_ENV_STEP_CONV / (pk["tf_sustained"] * 1e12), 4)
-            if args.spec == 1 else None,
+            "model_flops_per_env_step": flop_step,
+            "tensor_roofline_frac_whole_step": round(value / world * flop_step / (pk["tf_sustained"] * 1e12), 4)
+            if flop_step else None,
+            "conv_tile_roofline_frac": round(value / world * flop_conv / (pk["tf_sustained"] * 1e12), 4) if flop_conv else None,
             "roofline": roof,
             "kernels": kernels[:16],
             "host_wall_s": round(wall, 3),

@@ -143,6 +143,8 @@ int arl_train_minibatches(arl_ctx* ctx, const int* idx, int mb_size, int count, 
 /* the same loop for the synchronous multi-GPU learner: every minibatch ends with arl_sync_allreduce_update instead of
  * the local clip+update (sync_ppo_optimizer.py:56-72); one CUDA graph per minibatch incl. the cooperative all-reduce */
 int arl_train_minibatches_sync(arl_ctx* ctx, const int* idx, int mb_size, int count, void* stream);
+/* the asynchronous learner's PPO loop: every minibatch ends with arl_async_push_pull (one CUDA graph per minibatch) */
+int arl_train_minibatches_async(arl_ctx* ctx, const int* idx, int mb_size, int count, void* stream);
 /* per-update logs since the last call: losses and pre-clip grad norms (host arrays) */
 int arl_read_logs(arl_ctx* ctx, float* loss, float* grad_norm, int cap, int* n, void* stream);
 int arl_reset_opt_state(arl_ctx* ctx, void* stream);
