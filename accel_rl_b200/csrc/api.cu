@@ -102,6 +102,10 @@ struct arl_ctx {
   cudaStream_t side = nullptr;         // weight-gradient kernels run here, overlapping the data-gradient chain
   cudaEvent_t ev_fork[4] = {nullptr, nullptr, nullptr, nullptr}, ev_join = nullptr;
   bool no_fork = false;                // serialise everything on the caller's stream (per-kernel profiling)
+  // CTA caps while a data-gradient and a weight-gradient kernel share the GPU (0 = all SMs).  Measured (B200, C2):
+  // wgrad capped at 56..96 CTAs lets the concurrent dgrad chain start on the free SMs and shrinks the per-CTA partial
+  // traffic: 62.6 -> 60.4 ms per iteration; capping the dgrad side as well does not help.
+  int dgrad_ctas = 0, wgrad_ctas = 80;
   int pc_dy_n = 0;                     // images whose gradient-grid rows may be non-zero
   int pc_mode = 0;                     // 0: gather path   1: pconv forward (inference)   2: pconv forward + backward
   int Kfc = 0, H = 0, A = 0, HWlast = 0, Clast = 0;
@@ -495,6 +499,7 @@ int launch_pconv(arl_ctx* c, const PcParams& p, cudaStream_t st) {
     attr_smem = smem;
   }
   int ctas = std::min(p.ntiles, 148);
+  if (p.out.mode != 0 && c->dgrad_ctas > 0) ctas = std::min(ctas, c->dgrad_ctas);   // data gradient sharing the GPU with a wgrad
   ARL_CHECK(c, launch_k(pconv_fwd_kernel<N>, dim3(ctas), dim3(kPcFwdThreads), smem, st, p));
   c->launches++;
   ARL_CHECK(c, cudaGetLastError());
@@ -572,7 +577,8 @@ int launch_pconv_wgrad(arl_ctx* c, const PcWgradParams& p, int ctas, cudaStream_
 int pc_wgrad_ctas(arl_ctx* c, int l, int n) {
   const PcLayer& q = c->pc[l];
   int ntiles = (l == 0) ? n * q.tiles_per_img : (int)(((long)n * q.S + 127) / 128);
-  return std::min(ntiles, 148);
+  int cap = (l > 0 && c->wgrad_ctas > 0) ? c->wgrad_ctas : 148;    // layer 0's wgrad runs alone at the end of the chain
+  return std::min(ntiles, cap);
 }
 
 // weight (+ bias) gradient partials of conv layer l on the patch-resident path
@@ -1315,6 +1321,8 @@ int arl_create(const arl_net_cfg* cfg, arl_ctx** out) {
   // everything / for training only (A/B measurements)
   c->pc_mode = c->pc.empty() ? 0 : 2;
   if (const char* ev = getenv("ARL_PDL")) g_pdl = atoi(ev) != 0;
+  if (const char* ev = getenv("ARL_DGRAD_CTAS")) c->dgrad_ctas = atoi(ev);
+  if (const char* ev = getenv("ARL_WGRAD_CTAS")) c->wgrad_ctas = atoi(ev);
   if (const char* ev = getenv("ARL_PCONV")) c->pc_mode = c->pc.empty() ? 0 : std::max(0, std::min(2, atoi(ev)));
   if (rc0 || alloc_net(c)) {
     g_create_error = c->err;
