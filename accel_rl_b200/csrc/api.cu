@@ -99,13 +99,15 @@ struct arl_ctx {
   __nv_bfloat16* dh_t = nullptr;       // [H/64][fc_rows][64]
   int fc_rows = 0;                     // rows per plane (max_rows rounded up to 128)
   int dh_n = 0;                        // rows of dh_t that may be non-zero
+  cudaStream_t side2 = nullptr;        // second forked stream: conv weight gradients (side: head + FC weight gradients)
+  cudaEvent_t ev_join2 = nullptr;
   cudaStream_t side = nullptr;         // weight-gradient kernels run here, overlapping the data-gradient chain
   cudaEvent_t ev_fork[4] = {nullptr, nullptr, nullptr, nullptr}, ev_join = nullptr;
   bool no_fork = false;                // serialise everything on the caller's stream (per-kernel profiling)
   // CTA caps while a data-gradient and a weight-gradient kernel share the GPU (0 = all SMs).  Measured (B200, C2):
   // wgrad capped at 56..96 CTAs lets the concurrent dgrad chain start on the free SMs and shrinks the per-CTA partial
   // traffic: 62.6 -> 60.4 ms per iteration; capping the dgrad side as well does not help.
-  int dgrad_ctas = 0, wgrad_ctas = 80;
+  int dgrad_ctas = 0, wgrad_ctas = 64;
   int pc_dy_n = 0;                     // images whose gradient-grid rows may be non-zero
   int pc_mode = 0;                     // 0: gather path   1: pconv forward (inference)   2: pconv forward + backward
   int Kfc = 0, H = 0, A = 0, HWlast = 0, Clast = 0;
@@ -1053,6 +1055,8 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
       ARL_CHECK(c, cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
       for (auto& e : c->ev_fork) ARL_CHECK(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       ARL_CHECK(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+      ARL_CHECK(c, cudaStreamCreateWithFlags(&c->side2, cudaStreamNonBlocking));
+      ARL_CHECK(c, cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming));
     }
     ws = c->side;
     ARL_CHECK(c, cudaEventRecord(c->ev_fork[0], st));
@@ -1105,7 +1109,7 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
   for (int l = (int)c->conv.size() - 1; l >= 0 && pcb; --l) {
     // layer l's gradient grid was completed by the last kernel on `st` (FC dgrad or dgrad l+1); the first layer's
     // wgrad closes the main chain itself
-    cudaStream_t wl = (l == 0) ? st : ws;
+    cudaStream_t wl = (l == 0 || ws == st) ? st : c->side2;
     if (wl != st) {
       cudaEvent_t ev = c->ev_fork[1 + (l % 3)];
       ARL_CHECK(c, cudaEventRecord(ev, st));
@@ -1120,6 +1124,10 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
   if (ws != st) {
     ARL_CHECK(c, cudaEventRecord(c->ev_join, ws));
     ARL_CHECK(c, cudaStreamWaitEvent(st, c->ev_join, 0));
+    if (c->conv.size() > 1) {
+      ARL_CHECK(c, cudaEventRecord(c->ev_join2, c->side2));
+      ARL_CHECK(c, cudaStreamWaitEvent(st, c->ev_join2, 0));
+    }
   }
   for (int l = (int)c->conv.size() - 1; l >= 0 && !pcb; --l) {
     ConvLayer& L = c->conv[l];
