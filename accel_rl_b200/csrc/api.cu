@@ -206,6 +206,30 @@ cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
   return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
 }
 
+// Cooperative launch (also inside stream capture): the driver guarantees that every block of the grid is resident at
+// the same time, which is what a kernel with a grid-wide barrier needs.  Falls back to a plain launch if the driver
+// refuses the attribute (the grids used here are sized to one wave anyway).
+template <class... KArgs, class... Args>
+cudaError_t launch_coop(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  static bool coop_ok = true;
+  if (coop_ok) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+    if (e == cudaSuccess) return e;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    if (cs != cudaStreamCaptureStatusNone) return e;      // a failed call inside capture invalidates it: report
+    cudaGetLastError();
+    coop_ok = false;
+  }
+  return launch_k(kern, grid, block, smem, st, std::forward<Args>(args)...);
+}
+
 // record an event after the launch that just happened (profiling mode only)
 void prof_mark(arl_ctx* c, const char* name, cudaStream_t st) {
   if (c->prof_collect) c->prof_labels.push_back(name);
@@ -1211,7 +1235,7 @@ int clip_update(arl_ctx* c, float gscale, cudaStream_t st) {
   // norm + clip + update in one launch (update_fused_kernel); ARL_FUSED_UPDATE=0 keeps the two-kernel form
   static const bool fused = !(getenv("ARL_FUSED_UPDATE") && atoi(getenv("ARL_FUSED_UPDATE")) == 0);
   if (fused) {
-    ARL_CHECK(c, launch_k(update_fused_kernel, dim3(kSumsqBlocks), dim3(256), 0, st, u, c->sumsq_partial, c->ticket));
+    ARL_CHECK(c, launch_coop(update_fused_kernel, dim3(kSumsqBlocks), dim3(256), 0, st, u, c->sumsq_partial, c->ticket));
   } else {
     ARL_CHECK(c, launch_k(sumsq_kernel, dim3(kSumsqBlocks), dim3(256), 0, st, c->grad, c->n_params, gscale, c->sumsq_partial));
     c->launches++;

@@ -383,15 +383,19 @@ inline int comm_sync_update(CommState& s, SyncUpdateArgs a, cudaStream_t st, std
   if (!s.ready) { err = "comm not connected"; return 1; }
   if (a.param != s.param || a.grad != s.grad) { err = "params/grad must be the comm's symmetric buffers"; return 1; }
   void* args[] = {(void*)&s.dev, (void*)&a};
-  // Inside stream capture the kernel is launched plainly: 148 blocks x 512 threads are co-resident on an otherwise idle
-  // GPU (the training graph joins its side stream before this node), which is all the grid barrier needs; outside
-  // capture the cooperative launch lets the driver verify co-residency.
+  // Cooperative launch in both cases (attribute form inside stream capture): the driver guarantees co-residency of the
+  // 148 blocks, which is what the grid barrier needs.
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(st, &cs);
   cudaError_t e;
   if (cs == cudaStreamCaptureStatusActive) {
-    sync_allreduce_update_kernel<<<kSyncBlocks, kSyncThreads, 0, st>>>(s.dev, a);
-    e = cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(kSyncBlocks); cfg.blockDim = dim3(kSyncThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, sync_allreduce_update_kernel, s.dev, a);
   } else {
     e = cudaLaunchCooperativeKernel((const void*)sync_allreduce_update_kernel, dim3(kSyncBlocks), dim3(kSyncThreads), args, 0, st);
   }
