@@ -831,17 +831,24 @@ __global__ void __launch_bounds__(256) finalize_grads_kernel(const GradJob* __re
     int r = (int)(i / jb.cols);
     int c = (int)(i - (long)r * jb.cols);
     const float* s = jb.src + (long)r * jb.ld + c;
-    // fixed summation order (4 interleaved chains), independent loads in flight
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    // fixed summation order: 16 interleaved chains (16 independent L2 loads in flight per thread — the loop is pure
+    // latency: 64..148 partials, each a separate 4-byte load), then a fixed tree
+    float a[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) a[u] = 0.f;
     int k = 0;
-    for (; k + 4 <= jb.S; k += 4) {
-      a0 += s[(long)k * jb.sstride];
-      a1 += s[(long)(k + 1) * jb.sstride];
-      a2 += s[(long)(k + 2) * jb.sstride];
-      a3 += s[(long)(k + 3) * jb.sstride];
+    for (; k + 16 <= jb.S; k += 16) {
+#pragma unroll
+      for (int u = 0; u < 16; ++u) a[u] += s[(long)(k + u) * jb.sstride];
     }
-    for (; k < jb.S; ++k) a0 += s[(long)k * jb.sstride];
-    float acc = ((a0 + a1) + (a2 + a3)) * jb.scale;
+#pragma unroll
+    for (int u = 0; u < 16; ++u)
+      if (k + u < jb.S) a[u] += s[(long)(k + u) * jb.sstride];
+#pragma unroll
+    for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+      for (int u = 0; u < w; ++u) a[u] += a[u + w];
+    float acc = a[0] * jb.scale;
     if (jb.map == GM_LINEAR) {
       grad[jb.dst_off + i] = acc;
     } else if (jb.map == GM_CONV_NHWC) {
@@ -1100,6 +1107,8 @@ struct PackJob {
   int T, P, N, ci_major;
 };
 
+ARL_DEVINL void pack_job_body(const PackJob& jb, const float* __restrict__ params, long first, long stride);
+
 __global__ void __launch_bounds__(256) pack_weights_kernel(const PackJob* __restrict__ jobs,
                                                             const float* __restrict__ params, int* step,
                                                             int* log_slot, int* mb_counter) {
@@ -1110,26 +1119,32 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const PackJob* __rest
     step[0] += 1; log_slot[0] += 1; mb_counter[0] += 1;
   }
   const PackJob jb = jobs[blockIdx.y];
+  pack_job_body(jb, params, (long)blockIdx.x * blockDim.x + threadIdx.x, (long)gridDim.x * blockDim.x);
+}
+
+// parameter reads bypass L1 (__ldcg): inside step_fused_kernel the values were written by other SMs earlier in the
+// same launch
+ARL_DEVINL void pack_job_body(const PackJob& jb, const float* __restrict__ params, long first, long stride) {
   const long total = (long)jb.rows * jb.cols;
   const float* W = params + jb.src_off;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+  for (long i = first; i < total; i += stride) {
     int r = (int)(i / jb.cols);
     int k = (int)(i - (long)r * jb.cols);
     float v = 0.f;
     if (jb.kind == PK_CONV_NHWC) {          // r = cout, k = (ky*kw+kx)*C + c
       int c = k % jb.C; int t = k / jb.C; int kx = t % jb.kw, ky = t / jb.kw;
-      v = W[(((long)r * jb.C + c) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx)];
+      v = __ldcg(W + ((((long)r * jb.C + c) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx)));
     } else if (jb.kind == PK_CONV_S2D) {    // r = cout, k = (ty*2+tx)*(C*s*s) + c*s*s + dy*s + dx
       const int s2 = jb.s * jb.s, cs = jb.C * s2;
       int ch = k % cs; int t = k / cs; int tx = t % 2, ty = t / 2;
       int c = ch / s2, dy = (ch % s2) / jb.s, dx = ch % jb.s;
       int ky = ty * jb.s + dy, kx = tx * jb.s + dx;
-      v = W[(((long)r * jb.C + c) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx)];
+      v = __ldcg(W + ((((long)r * jb.C + c) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx)));
     } else if (jb.kind == PK_CONV_DGRAD) {  // r = cin, k = (ty*Tx+tx)*Cout + o
       int o = k % jb.Cout; int t = k / jb.Cout; int tx = t % jb.Tx, ty = t / jb.Tx;
       int ky = jb.ry + jb.s * ty, kx = jb.rx + jb.s * tx;
       if (ky < jb.kh && kx < jb.kw)
-        v = W[(((long)o * jb.C + r) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx)];
+        v = __ldcg(W + ((((long)o * jb.C + r) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx)));
     } else if (jb.kind == PK_PCONV || jb.kind == PK_PCONV_DGRAD) {
       // rows = blocks*N, cols = 64
       int blk = r / jb.N, n_ = r - blk * jb.N;
@@ -1142,18 +1157,38 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const PackJob* __rest
       pc_decode_channel(cc, jb.C, jb.s, jb.ci_major, ci, py, px);
       int ky = ty * jb.s + py, kx = tx * jb.s + px;
       if (ky < jb.kh && kx < jb.kw && ci < jb.C && co < jb.Cout)
-        v = W[(((long)co * jb.C + ci) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx)];
+        v = __ldcg(W + ((((long)co * jb.C + ci) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx)));
       jb.dst[(long)r * 64 + ((((k >> 3) ^ (n_ & 7)) << 3) | (k & 7))] = __float2bfloat16_rn(v);
       continue;
     } else if (jb.kind == PK_FC_TILES) {     // FC weights -> wfc_t tiles (rows = Kfc in reference order, cols = H)
       jb.dst[fc_tile_index(r, k, jb.HW, jb.cols)] = __float2bfloat16_rn(W[i]);
       continue;
     } else {                                 // PK_CAST: same layout, fp32 -> bf16 (FC weights, reference order)
-      v = W[i];
+      v = __ldcg(W + (i));
     }
     jb.dst[i] = __float2bfloat16_rn(v);
   }
 }
+
+// Grid-wide ticket barrier for a co-resident (cooperatively launched) grid.  The 64-bit ticket only grows, so a launch
+// carries no host state and replays from a CUDA graph.
+ARL_DEVINL void ticket_barrier(unsigned long long* ticket, int code) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long t = atomicAdd(ticket, 1ULL);
+    const unsigned long long target = (t / gridDim.x + 1ULL) * gridDim.x;
+    long long t0 = clock64();
+    while (atomicAdd(ticket, 0ULL) < target) {
+      if (clock64() - t0 > 20000000000LL) dev_fail(code);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// (a variant that also folded the conv operand re-pack behind a second barrier was measured: 30.0 us against
+// 22.4 + 5 us for update_fused_kernel + pack_weights_kernel — no gain, dropped)
 
 // ===========================================================================
 // GAE / discounted returns — algos/pg/util.py:6-37, aac_base.py:108-145.
