@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Dev check: patch-resident conv forward (ARL_PCONV>=1) against the oracle, with per-kernel CUDA-event times."""
+"""Dev check (run by hand, not collected by pytest): patch-resident conv forward (ARL_PCONV>=1) against the oracle, with per-kernel CUDA-event times."""
 import os, sys, json
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Dev check: per-tensor gradient error of one minibatch against the oracle (patch-resident backward)."""
+"""Dev check (run by hand, not collected by pytest): per-tensor gradient error of one minibatch against the oracle (patch-resident backward)."""
 import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -228,3 +228,47 @@ def test_clip_and_update_rules(kind, clip):
         np.testing.assert_allclose(got, p, rtol=1e-6, atol=1e-7)
     finally:
         eng.close()
+
+
+def test_nature_cnn_84x84_geometry_vs_oracle():
+    """the classic 84x84 Nature-CNN geometry (8x8/4, 4x4/2, 3x3/1, no padding): forward and per-tensor gradients against
+    the oracle.  Its 21x21 space-to-depth grid is not a multiple of 8 positions, so this exercises the im2col-gather
+    tiles (gemm_tc.cuh) that serve every geometry the patch-resident path does not take."""
+    from accel_rl_b200.policies import AtariCnnPolicy
+    from accel_rl_b200.envs.atari_env import EnvSpec
+    from accel_rl_b200.spaces import Discrete, UintBox
+    spec = dict(conv_filter_sizes=[8, 4, 3], conv_filters=[32, 64, 64], conv_strides=[4, 2, 1], conv_pads=[0, 0, 0],
+                hidden_sizes=[512])
+    A, n = 6, 48
+    flat = onet.init_params(spec, (4, 84, 84), A, np.random.RandomState(0), np.random.RandomState(1))
+    flat = flat + np.float32(0.01) * np.random.RandomState(2).randn(flat.size).astype(np.float32) * (flat == 0)
+    pol = AtariCnnPolicy(initial_param_values=flat, max_rows=n, conv_filter_sizes=[8, 4, 3], conv_filters=[32, 64, 64],
+                         conv_strides=[4, 2, 1], conv_pads=[(0, 0), (0, 0), (0, 0)], hidden_sizes=[512])
+    pol.initialize(EnvSpec(UintBox((4, 84, 84)), Discrete(A)))
+    eng = pol.engine
+    try:
+        rng = np.random.RandomState(11)
+        obs = rng.randint(0, 256, (n, 4, 84, 84), dtype=np.uint8)
+        prob = torch.zeros(n, A, device="cuda"); val = torch.zeros(n, device="cuda")
+        eng.forward(torch.tensor(obs).cuda(), prob=prob, value=val)
+        p_ref, v_ref = onet.forward(torch.tensor(flat), torch.tensor(obs), spec, A, True)
+        assert relerr(t2n(prob), p_ref.numpy()) < 2e-3 and relerr(t2n(val), v_ref.numpy()) < 5e-3
+        act = rng.randint(0, A, n).astype(np.uint8)
+        adv = rng.randn(n).astype(np.float32); ret = rng.randn(n).astype(np.float32)
+        oldp = rng.dirichlet(np.ones(A), n).astype(np.float32); oldv = rng.randn(n).astype(np.float32)
+        eng.opt_configure(algo=0, clip_param=0.2, v_loss_coeff=1.0, ent_loss_coeff=0.01, update=0, learning_rate=1e-3,
+                          beta1=0.9, beta2=0.999, epsilon=1e-5, rho=0.9, grad_norm_clip=-1.0)
+        eng.bind_train_inputs(*[torch.tensor(x).cuda() for x in (obs, act, adv, ret, oldv, oldp)], valids=None)
+        eng.grad_minibatch(torch.arange(n, dtype=torch.int32, device="cuda"), n)
+        torch.cuda.synchronize()
+        g = t2n(eng.grad)
+        _, g_ref, _ = onet.loss_and_grad(flat, obs, act, adv, ret, oldp, spec, A, "ppo", emulate_bf16=True, v_coeff=1.0,
+                                         valids=None)
+        i = 0
+        for k, s in enumerate(onet.param_shapes(spec, (4, 84, 84), A)):
+            m = int(np.prod(s))
+            assert relerr(g[i:i + m], g_ref[i:i + m]) < 1e-2, "tensor %d %s" % (k, s)
+            i += m
+        assert eng.device_error() == 0
+    finally:
+        eng.close()
