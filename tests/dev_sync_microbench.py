@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Dev tool (2+ GPUs under torch.distributed.run): device time of the fused all-reduce + update step alone."""
+"""Dev tool, run by hand (2+ GPUs under torch.distributed.run): device time of the fused all-reduce + update step alone."""
 import os, sys
 import numpy as np, torch, torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
