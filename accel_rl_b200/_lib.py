@@ -78,6 +78,7 @@ class SamplerCfg(C.Structure):
         ("reward_mod", C.c_int),
         ("frame_stride", C.c_int),
         ("traj_cap", C.c_int),
+        ("frame_mode", C.c_int),
     ]
 
 

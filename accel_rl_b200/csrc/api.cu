@@ -444,9 +444,13 @@ int plan_pconv(arl_ctx* c) {
       if (L.p != 0 || (L.Hin % L.s) || (L.Win % L.s) || q.P != 1) return 0;
       if (L.Cout != 32 && L.Cout != 64) return 0;
       q.ci_major = 1;
-      q.Wp = L.Win / L.s; q.Hc = L.Hin / L.s; q.S = q.Wp * q.Hc;
-      if (q.S % 8) return 0;
+      q.Wp = L.Win / L.s; q.Hc = L.Hin / L.s;
+      q.S = roundup(q.Wp * q.Hc, 8);       // image stride in positions: tiles must start at multiples of 8 rows
+                                            // (the padding positions are never written: zero)
       q.tiles_per_img = ((L.Ho - 1) * q.Wp + L.Wo + 127) / 128;
+      // the weight gradient multiplies whole 128-position tiles of the gradient grid: a tile must not run into the next
+      // image's rows (in the forward pass those outputs are simply dropped)
+      if (q.tiles_per_img * 128 > q.S) q.S = q.tiles_per_img * 128;
     } else {
       if (L.Cout != 64 || q.P > 2) return 0;
       const bool shared = (L.s == 1 && L.p >= 1 && 2 * L.p == q.T - 1);   // 'same' conv: pad column/row shared with the neighbour
@@ -702,7 +706,7 @@ int launch_fc_gemm(arl_ctx* c, const FcParams& p, dim3 grid, cudaStream_t st) {
 }
 
 bool fc_tiles_ok(arl_ctx* c) {
-  return c->pc_mode >= 2 && c->Clast == 64 && (c->HWlast % 6 == 0) && (c->H % 256 == 0) && (c->off_Wfc % 4 == 0);
+  return c->pc_mode >= 2 && c->Clast == 64 && (c->HWlast % 2 == 0) && (c->H % 256 == 0) && (c->off_Wfc % 4 == 0);
 }
 
 // forward: split-K partials [S][n][H] from act_fc planes and wfc_t tiles
@@ -730,17 +734,19 @@ int fc_dgrad_tiles(arl_ctx* c, int n, cudaStream_t st) {
   const int NT = c->H / 64, HW = c->HWlast;
   const ConvLayer& LL = c->conv.back();
   const PcLayer& q = c->pc.back();
-  constexpr int BN = 192;                                     // three pixel planes per tile: HW/3 x ceil(n/128) CTAs
+  // three pixel planes per tile (HW/3 x ceil(n/128) CTAs) when HW allows, else two
+  const int PL = (HW % 3 == 0) ? 3 : 2;
   FcParams p{};
-  p.ncopies = 4;
+  p.ncopies = 1 + PL;
   p.cp[0] = FcCopy{c->dh_t, 128 * 64, 0, 0, (long)c->fc_rows * 64, 16384, 0};
-  for (int i = 0; i < 3; ++i)
-    p.cp[1 + i] = FcCopy{c->wfc_t + (long)i * NT * 4096, 0, 3L * NT * 4096, 0, 4096, 8192, (uint32_t)(16384 + i * 8192)};
-  p.a_bytes = 16384; p.stage_bytes = 16384 + 3 * 8192; p.stages = 4;
+  for (int i = 0; i < PL; ++i)
+    p.cp[1 + i] = FcCopy{c->wfc_t + (long)i * NT * 4096, 0, (long)PL * NT * 4096, 0, 4096, 8192, (uint32_t)(16384 + i * 8192)};
+  p.a_bytes = 16384; p.stage_bytes = 16384 + PL * 8192; p.stages = 4;
   p.niter = NT; p.niter_total = NT; p.M = n;
   p.dy = q.dY; p.act = c->act_fc; p.act_plane = (long)c->fc_rows * 64;
   p.sc_Wo = LL.Wo; p.sc_S = q.S; p.sc_Wp = q.Wp; p.sc_pad = q.dYpad;
-  return launch_fc_gemm<1, BN>(c, p, dim3((n + 127) / 128, HW / 3, 1), st);
+  if (PL == 3) return launch_fc_gemm<1, 192>(c, p, dim3((n + 127) / 128, HW / 3, 1), st);
+  return launch_fc_gemm<1, 128>(c, p, dim3((n + 127) / 128, HW / 2, 1), st);
 }
 
 // weight gradient: act_fc^T x dh_t -> fp32 rows of the flat gradient (reference row order)
@@ -801,7 +807,7 @@ int alloc_net(arl_ctx* c) {
     c->bias_partial.push_back(bp);
   }
   if (dev_alloc(c, &c->wfc_bf16, (size_t)c->H * c->Kfc)) return 1;
-  if (c->pc_mode >= 2) {
+  if (fc_tiles_ok(c)) {
     c->fc_rows = roundup(R, 128);
     if (dev_alloc(c, &c->act_fc, (size_t)(c->HWlast + 2) * c->fc_rows * 64)) return 1;
     if (dev_alloc(c, &c->wfc_t, (size_t)c->H * c->Kfc)) return 1;
@@ -811,7 +817,7 @@ int alloc_net(arl_ctx* c) {
     // LAST job = the bf16 FC operand copy (skipped by pack_weights(with_fc=false) when the update kernel refreshes it)
     PackJob j{};
     j.dst = c->wfc_bf16; j.src_off = c->off_Wfc; j.kind = PK_CAST; j.rows = c->Kfc; j.cols = c->H;
-    if (c->pc_mode >= 2) { j.dst = c->wfc_t; j.kind = PK_FC_TILES; j.HW = c->HWlast; }
+    if (fc_tiles_ok(c)) { j.dst = c->wfc_t; j.kind = PK_FC_TILES; j.HW = c->HWlast; }
     pj.push_back(j);
   }
   // the FC cast job stays LAST (pack_weights(with_fc=false) drops it); pconv packs go before it
@@ -882,7 +888,7 @@ int convert_obs(arl_ctx* c, const uint8_t* obs, const int* idx, int n, bool swz,
   const ConvLayer& L0 = c->conv[0];
   long work = (long)n * L0.Cin * L0.Hin * (L0.Win / 4);
   int blocks = (int)std::min<long>((work + 255) / 256, 148 * 16);
-  obs_to_s2d_kernel<<<blocks, 256, 0, st>>>(obs, idx, c->obs16_stage, n, L0.Cin, L0.Hin, L0.Win, swz ? 1 : 0);
+  obs_to_s2d_kernel<<<blocks, 256, 0, st>>>(obs, idx, c->obs16_stage, n, L0.Cin, L0.Hin, L0.Win, swz ? 1 : 0, c->obs16_elems);
   c->launches++;
   prof_mark(c, "obs_to_s2d", st);
   ARL_CHECK(c, cudaGetLastError());
@@ -1260,6 +1266,17 @@ SynthCfg synth_cfg(const arl_sampler_cfg& s) {
 
 int launch_frame(arl_ctx* c, const uint8_t* staging, int s_next, bool to_rollout, cudaStream_t st) {
   const arl_sampler_cfg& s = c->sc;
+  if (s.frame_mode == 1) {
+    // north-star frames: RGB pool / staging -> gray -> 84x84 (frame_rgb_roll_kernel)
+    ARL_CHECK(c, launch_k(frame_rgb_roll_kernel, dim3(s.n_envs * (kNsH / kRgbRows)), dim3(kRgbThreads), 0, st, s.frame_pool, staging,
+                          c->cmd, s.step_obs, to_rollout ? s.observations : nullptr, c->step_obs16,
+                          to_rollout ? c->roll_obs16 : nullptr, s.horizon, s_next, s.n_envs, s.planes, c->pc_mode >= 2,
+                          c->pc_mode >= 2, c->obs16_elems));
+    c->launches++;
+    prof_mark(c, "frame", st);
+    ARL_CHECK(c, cudaGetLastError());
+    return 0;
+  }
   long items = (long)s.n_envs * 520;
   int blocks = (int)((items + 255) / 256);
   ARL_CHECK(c, launch_k(frame_kernel, dim3(blocks), dim3(256), 0, st, s.frame_pool, staging, c->cmd, s.step_obs, to_rollout ? s.observations : nullptr,
@@ -1273,7 +1290,7 @@ int launch_frame(arl_ctx* c, const uint8_t* staging, int s_next, bool to_rollout
 
 int rollout_begin(arl_ctx* c, cudaStream_t st) {
   const arl_sampler_cfg& s = c->sc;
-  int row_bytes = s.planes * kObsH * kObsW;
+  int row_bytes = s.planes * c->cfg.in_h * c->cfg.in_w;
   long chunks = (long)s.n_envs * (row_bytes / 16);
   // observations[e*T + 0] = step_obs[e]   (worker.py:31-32) — and the same for the bf16 mirror
   copy_rows_kernel<<<(int)((chunks + 255) / 256), 256, 0, st>>>(s.step_obs, row_bytes, nullptr, s.observations, row_bytes,
@@ -1304,7 +1321,7 @@ int rollout_step(arl_ctx* c, int s_idx, const uint8_t* staging, cudaStream_t st)
 int rollout_end(arl_ctx* c, cudaStream_t st) {
   const arl_sampler_cfg& s = c->sc;
   if (s.extra_observations) {
-    size_t bytes = (size_t)s.n_envs * s.planes * kObsH * kObsW;
+    size_t bytes = (size_t)s.n_envs * s.planes * c->cfg.in_h * c->cfg.in_w;
     ARL_CHECK(c, cudaMemcpyAsync(s.extra_observations, s.step_obs, bytes, cudaMemcpyDeviceToDevice, st));
   }
   if (!s.mid_batch_reset) {
@@ -1356,6 +1373,11 @@ int arl_create(const arl_net_cfg* cfg, arl_ctx** out) {
   if (const char* ev = getenv("ARL_DGRAD_CTAS")) c->dgrad_ctas = atoi(ev);
   if (const char* ev = getenv("ARL_WGRAD_CTAS")) c->wgrad_ctas = atoi(ev);
   if (const char* ev = getenv("ARL_PCONV")) c->pc_mode = c->pc.empty() ? 0 : std::max(0, std::min(2, atoi(ev)));
+  if (!c->pc.empty() && c->pc[0].S * 64L != c->obs16_elems) {
+    // the patch-resident path pads the first layer's image stride; the gather tiles cannot read that layout
+    if (c->pc_mode == 1) c->pc_mode = 0;
+    if (c->pc_mode == 2) c->obs16_elems = c->pc[0].S * 64L;
+  }
   if (rc0 || alloc_net(c)) {
     g_create_error = c->err;
     delete c;
@@ -1462,7 +1484,12 @@ int arl_sampler_configure(arl_ctx* c, const arl_sampler_cfg* cfg) {
   c->sc = *cfg;
   const int B = cfg->n_envs, T = cfg->horizon;
   if (cfg->planes != c->cfg.in_c) ARL_FAIL(c, "sampler planes != network input channels");
-  if (c->cfg.in_h != kObsH || c->cfg.in_w != kObsW) ARL_FAIL(c, "sampler requires 104x80 observations");
+  if (cfg->frame_mode == 0 && (c->cfg.in_h != kObsH || c->cfg.in_w != kObsW))
+    ARL_FAIL(c, "frame_mode 0 (reference frames) produces 104x80 observations");
+  if (cfg->frame_mode == 1 && (c->cfg.in_h != kNsH || c->cfg.in_w != kNsW))
+    ARL_FAIL(c, "frame_mode 1 (RGB frames) produces 84x84 observations");
+  if (cfg->frame_mode != 0 && cfg->frame_mode != 1) ARL_FAIL(c, "frame_mode must be 0 or 1");
+  if ((cfg->planes * c->cfg.in_h * c->cfg.in_w) % 16) ARL_FAIL(c, "observation bytes must be a multiple of 16");
   if (B > c->cfg.max_rows) ARL_FAIL(c, "n_envs larger than max_rows");
   // env state block: 4 int arrays + ... allocate separately for clarity
   int* iblock = nullptr;
@@ -1847,6 +1874,9 @@ int arl_debug_activation(arl_ctx* c, int layer, float* out, long cap, long* n, v
   else if (layer >= nc && layer < 2 * nc) { auto& L = c->conv[layer - nc]; src = L.dact; cnt = R * L.Ho * L.Wo * L.Cout; }
   else if (layer == 100) { src = c->h; cnt = R * c->H; }
   else if (layer == 101) { src = c->dh; cnt = R * c->H; }
+  else if (layer >= 200 && layer < 200 + (int)c->pc.size() && layer > 200) {   // raw input grid of pconv layer (plane 0)
+    src = c->pc[layer - 200].in; cnt = c->pc[layer - 200].in_rows * 64;
+  }
   else ARL_FAIL(c, "bad layer id");
   cnt = std::min(cnt, cap);
   *n = cnt;

@@ -243,7 +243,7 @@ ARL_DEVINL uint2 u8x4_to_bf16x4(uint32_t w) {
 // patch-resident conv tiles bulk-copy straight into SWIZZLE_128B shared memory (pconv.cuh)
 __global__ void __launch_bounds__(256) obs_to_s2d_kernel(const uint8_t* __restrict__ src, const int* __restrict__ idx,
                                                          __nv_bfloat16* __restrict__ dst, int n, int C, int H, int W,
-                                                         int swz) {
+                                                         int swz, long img_elems) {
   pdl_wait();
   pdl_trigger();
   const int Wb = W >> 2, Hb = H >> 2;
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(256) obs_to_s2d_kernel(const uint8_t* __restri
     long img = idx ? idx[i] : i;
     uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(src + ((img * C + c) * H + y) * (long)W) + bx);
     const int pos = (y >> 2) * Wb + bx, ch = c * 16 + (y & 3) * 4;
-    long off = (i * Hb * Wb + pos) * (long)(C * 16) + (swz ? ((((ch >> 3) ^ (pos & 7)) << 3) | (ch & 7)) : ch);
+    long off = i * img_elems + (long)pos * (C * 16) + (swz ? ((((ch >> 3) ^ (pos & 7)) << 3) | (ch & 7)) : ch);   // img_elems >= Hb*Wb*C*16
     *reinterpret_cast<uint2*>(dst + off) = u8x4_to_bf16x4(w);
   }
 }
@@ -452,6 +452,102 @@ __global__ void __launch_bounds__(kRgbThreads) frame_rgb_kernel(const uint8_t* _
     if (p < planes - 1) v = rs ? 0u : *reinterpret_cast<const uint32_t*>(cur + (p + 1) * plane_px);
     *reinterpret_cast<uint32_t*>(cur + p * plane_px) = v;
     if (cur16) *reinterpret_cast<uint2*>(cur16 + p * plane_px) = u8x4_to_bf16x4(v);
+  }
+}
+
+// The same pipeline inside the rollout (arl_rollout_step, frame_mode 1): frames come from the RGB pool (or the
+// host-fed staging pair) as directed by the env step's FrameCmd; writes the sampler's step buffer in place, the rollout
+// row e*T + s_next, and the bf16 space-to-depth(4) mirrors the first conv layer reads ((84/4)^2 = 441 positions x
+// planes*16 channels per observation, image stride img16 elements, optionally chunk-swizzled).
+__global__ void __launch_bounds__(kRgbThreads) frame_rgb_roll_kernel(
+    const uint8_t* __restrict__ pool, const uint8_t* __restrict__ staging, const FrameCmd* __restrict__ cmd,
+    uint8_t* __restrict__ step_obs, uint8_t* __restrict__ roll_obs, __nv_bfloat16* __restrict__ step_obs16,
+    __nv_bfloat16* __restrict__ roll_obs16, int T, int s_next, int n_envs, int planes, int swz_step, int swz_roll,
+    long img16) {
+  pdl_wait();
+  pdl_trigger();
+  constexpr int IN_ROWS = kRgbRows * 5 / 2;
+  constexpr int WORDS = IN_ROWS * kRgbW * 3 / 16;
+  __shared__ __align__(16) uint8_t s_rgb[IN_ROWS * kRgbW * 3];
+  __shared__ uint8_t s_gray[IN_ROWS * kRgbW];
+  __shared__ __align__(4) uint8_t s_out[kRgbRows * kNsW];
+  constexpr int GROUPS = kNsH / kRgbRows;
+  const int e = blockIdx.x / GROUPS;
+  const int grp = blockIdx.x - e * GROUPS;
+  const int tid = threadIdx.x;
+  const FrameCmd c = cmd[e];
+  if (c.flags & 2) return;                       // env not stepped: rows keep their stale contents
+  const bool rs = (c.flags & 1) != 0;
+  const long fbytes = (long)kRgbH * kRgbW * 3;
+  const long roff = (long)grp * IN_ROWS * kRgbW * 3;
+  const uint8_t* fa = nullptr;
+  const uint8_t* fb = nullptr;
+  if (staging) {
+    if (c.src_a >= 0) fa = staging + ((long)e * 2 + 0) * fbytes + roff;
+    if (c.src_b >= 0) fb = staging + ((long)e * 2 + 1) * fbytes + roff;
+  } else {
+    if (c.src_a >= 0) fa = pool + (long)c.src_a * fbytes + roff;
+    if (c.src_b >= 0) fb = pool + (long)c.src_b * fbytes + roff;
+  }
+  for (int i = tid; i < WORDS; i += kRgbThreads) {
+    uint4 b = fb ? __ldg(reinterpret_cast<const uint4*>(fb) + i) : make_uint4(0, 0, 0, 0);
+    if (fa) {
+      uint4 a = __ldg(reinterpret_cast<const uint4*>(fa) + i);
+      b.x = __vmaxu4(a.x, b.x); b.y = __vmaxu4(a.y, b.y); b.z = __vmaxu4(a.z, b.z); b.w = __vmaxu4(a.w, b.w);
+    }
+    reinterpret_cast<uint4*>(s_rgb)[i] = b;
+  }
+  __syncthreads();
+  for (int i = tid; i < IN_ROWS * kRgbW; i += kRgbThreads) {
+    const uint8_t* px = s_rgb + i * 3;
+    s_gray[i] = (uint8_t)((77u * px[0] + 150u * px[1] + 29u * px[2] + 128u) >> 8);
+  }
+  __syncthreads();
+  for (int o = tid; o < kRgbRows * kNsW; o += kRgbThreads) {
+    const int oy = o / kNsW, ox = o - oy * kNsW;
+    const int odd = oy & 1;
+    const int r0 = (oy >> 1) * 5 + odd * 2;
+    const int wy0 = odd ? 1 : 2, wy2 = odd ? 2 : 1;
+    const int c_lo = 40 * ox, c_hi = c_lo + 40;
+    const int j0 = c_lo / 21;
+    unsigned acc = 0;
+#pragma unroll
+    for (int dj = 0; dj < 3; ++dj) {
+      const int j = j0 + dj;
+      const int wx = min(c_hi, 21 * j + 21) - max(c_lo, 21 * j);
+      if (wx > 0 && j < kRgbW)
+        acc += (unsigned)wx * (wy0 * s_gray[r0 * kRgbW + j] + 2 * s_gray[(r0 + 1) * kRgbW + j] + wy2 * s_gray[(r0 + 2) * kRgbW + j]);
+    }
+    s_out[o] = (uint8_t)((acc + 100u) / 200u);
+  }
+  __syncthreads();
+  constexpr int WPR = kNsW / 4;
+  if (tid >= kRgbRows * WPR) return;
+  const int oy = tid / WPR, xw = tid - oy * WPR;
+  const int Y = grp * kRgbRows + oy;
+  const int pix = Y * kNsW + xw * 4;
+  const int plane_px = kNsH * kNsW;
+  const long obs_bytes = (long)planes * plane_px;
+  uint8_t* cur = step_obs + (long)e * obs_bytes + pix;
+  uint8_t* dst = roll_obs ? roll_obs + ((long)e * T + s_next) * obs_bytes + pix : nullptr;
+  __nv_bfloat16* c16 = step_obs16 ? step_obs16 + (long)e * img16 : nullptr;
+  __nv_bfloat16* d16 = (step_obs16 && roll_obs16) ? roll_obs16 + ((long)e * T + s_next) * img16 : nullptr;
+  const int Cs = planes * 16;
+  const int pos = (Y >> 2) * (kNsW / 4) + xw;
+  const uint32_t newest = *reinterpret_cast<const uint32_t*>(s_out + oy * kNsW + xw * 4);
+  for (int p = 0; p < planes; ++p) {
+    uint32_t v = newest;
+    if (p < planes - 1) v = rs ? 0u : *reinterpret_cast<const uint32_t*>(cur + (p + 1) * plane_px);
+    *reinterpret_cast<uint32_t*>(cur + p * plane_px) = v;
+    if (dst) *reinterpret_cast<uint32_t*>(dst + p * plane_px) = v;
+    if (c16) {
+      const int ch = p * 16 + (Y & 3) * 4;
+      const long off = (long)pos * Cs + ch;
+      const long offs = (long)pos * Cs + ((((ch >> 3) ^ (pos & 7)) << 3) | (ch & 7));
+      const uint2 o2 = u8x4_to_bf16x4(v);
+      *reinterpret_cast<uint2*>(c16 + (swz_step ? offs : off)) = o2;
+      if (d16) *reinterpret_cast<uint2*>(d16 + (swz_roll ? offs : off)) = o2;
+    }
   }
 }
 

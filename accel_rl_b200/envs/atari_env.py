@@ -34,7 +34,12 @@ class AtariEnv(object):
     device_resident = True
 
     def __init__(self, game="pong", frame_skip=4, num_img_obs=4, clip_reward=True, episodic_lives=True,
-                 max_start_noops=30, repeat_action_probability=0., synth_rules=None, n_actions=None):
+                 max_start_noops=30, repeat_action_probability=0., synth_rules=None, n_actions=None, frame_mode="gray"):
+        # frame_mode "gray": the reference pipeline (grayscale 210x160 screens -> 104x80, atari_env.py:147-157);
+        # "rgb": the north-star pipeline (RGB 210x160x3 screens -> gray -> 84x84), builder-defined (oracle/frame.py:rgb_*)
+        if frame_mode not in ("gray", "rgb"):
+            raise ValueError("frame_mode must be 'gray' or 'rgb'")
+        self.frame_mode = frame_mode
         if frame_skip != 4:
             raise NotImplementedError("device env implements frame_skip=4 (atari_env.py:19 default)")
         if num_img_obs not in (1, 4):
@@ -51,7 +56,8 @@ class AtariEnv(object):
             self.synth_rules.update(synth_rules)
         n = n_actions if n_actions is not None else MINIMAL_ACTIONS.get(game, 4)
         self._action_space = Discrete(n)
-        self._observation_space = UintBox(shape=(num_img_obs, H, W), bits=8)
+        obs_hw = (H, W) if frame_mode == "gray" else (84, 84)
+        self._observation_space = UintBox(shape=(num_img_obs,) + obs_hw, bits=8)
         # the reference ctor ends with self.reset(), whose start no-ops draw from the global stream
         # (atari_env.py:63,97); keep the draw so master-process RNG consumption stays identical
         self._draw_start_noops()
@@ -76,6 +82,7 @@ class AtariEnv(object):
     repeat_action_probability = property(lambda self: self._repeat_action_probability)
 
 
-def make_frame_pool(pool_frames, seed=0):
-    """Synthetic grayscale emulator frames (pool_frames, 210, 160) uint8 — same generator as the oracle."""
-    return np.random.RandomState(seed).randint(0, 256, (pool_frames, 210, 160), dtype=np.uint8)
+def make_frame_pool(pool_frames, seed=0, channels=1):
+    """Synthetic emulator frames (pool_frames, 210, 160[, 3]) uint8 — same generator as the oracle."""
+    shape = (pool_frames, 210, 160) if channels == 1 else (pool_frames, 210, 160, channels)
+    return np.random.RandomState(seed).randint(0, 256, shape, dtype=np.uint8)

@@ -108,7 +108,9 @@ class ActsrvAltOvrlpSampler(BaseMbSampler):
         env, buf = self._env, self.samples_buf
         B, T = self._total_n_envs, self.horizon
         rules = env.synth_rules
-        pool_np = make_frame_pool(rules["pool_frames"], rules.get("pool_seed", 0))
+        rgb = getattr(env, "frame_mode", "gray") == "rgb"
+        self._frame_channels = 3 if rgb else 1
+        pool_np = make_frame_pool(rules["pool_frames"], rules.get("pool_seed", 0), channels=self._frame_channels)
         self._pool_host = pool_np
         self.frame_pool = torch.from_numpy(pool_np).to(self.device)
         self._uniforms_host = torch.empty((T, B), dtype=torch.float64).pin_memory()
@@ -145,6 +147,7 @@ class ActsrvAltOvrlpSampler(BaseMbSampler):
         cfg.episodic_lives = int(bool(env.episodic_lives))
         for k in ("lives0", "life_base", "life_mul", "life_mod", "reward_mod", "frame_stride"):
             setattr(cfg, k, int(rules[k]))
+        cfg.frame_mode = 1 if rgb else 0
         cfg.traj_cap = max(4 * B, 1024)
         self._traj_cap = cfg.traj_cap
         eng.sampler_configure(cfg, keep=(buf, self.step_buf, self.frame_pool, self._uniforms, self._extra_obs))
@@ -159,8 +162,9 @@ class ActsrvAltOvrlpSampler(BaseMbSampler):
         B = self._total_n_envs
         S = self.host_ring_steps
         rng = np.random.RandomState(1234)
-        self._ring_host = torch.from_numpy(rng.randint(0, 256, (S, B, 2, 210, 160), dtype=np.uint8)).pin_memory()
-        self._staging = torch.zeros((2, B, 2, 210, 160), dtype=torch.uint8, device=self.device)
+        fshape = (210, 160) if self._frame_channels == 1 else (210, 160, 3)
+        self._ring_host = torch.from_numpy(rng.randint(0, 256, (S, B, 2) + fshape, dtype=np.uint8)).pin_memory()
+        self._staging = torch.zeros((2, B, 2) + fshape, dtype=torch.uint8, device=self.device)
         self._copy_stream = torch.cuda.Stream(self.device)
         self._copied = [torch.cuda.Event() for _ in range(2)]
         self._consumed = [torch.cuda.Event() for _ in range(2)]
@@ -210,7 +214,7 @@ class ActsrvAltOvrlpSampler(BaseMbSampler):
             # actions of this step go back to the host (what emulator workers would consume)
             self._act_host[s].copy_(self.samples_buf.actions[s::T], non_blocking=True)
         eng.rollout_end()
-        self.h2d_bytes += T * B * 2 * 210 * 160
+        self.h2d_bytes += T * B * 2 * 210 * 160 * self._frame_channels
         self.d2h_bytes += T * B
 
     def shutdown(self):

@@ -68,6 +68,9 @@ typedef struct {
   /* synthetic emulator rules (oracle/synth_ale.py implements the same) */
   int lives0, life_base, life_mul, life_mod, reward_mod, frame_stride;
   int traj_cap;                 /* capacity of the completed-trajectory record buffer */
+  int frame_mode;               /* 0: reference frames (210,160) gray -> (planes,104,80), atari_env.py:151-157;
+                                 * 1: north-star frames (210,160,3) RGB -> gray -> (planes,84,84) (see arl_frame_update_rgb);
+                                 *    frame_pool / staging then hold RGB frames */
 } arl_sampler_cfg;
 
 /* ---- lifetime ------------------------------------------------------------------------- */

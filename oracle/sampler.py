@@ -49,9 +49,13 @@ class SynthAtariEnv(object):
         self.P, self.frame_skip = num_img_obs, frame_skip
         self.clip_reward, self.episodic_lives = clip_reward, episodic_lives
         self.f = 0
-        self.obs = np.zeros((num_img_obs, oframe.H, oframe.W), np.uint8)
-        self.raw1 = np.zeros((210, 160), np.uint8)
-        self.raw2 = np.zeros((210, 160), np.uint8)
+        # north-star mode (RGB pool, trailing channel axis): same env logic, frames go through oracle.frame.rgb_*
+        self.rgb = pool.ndim == 4
+        self.raw_shape = pool.shape[1:]
+        self.hw = (oframe.NS_H, oframe.NS_W) if self.rgb else (oframe.H, oframe.W)
+        self.obs = np.zeros((num_img_obs,) + self.hw, np.uint8)
+        self.raw1 = np.zeros(self.raw_shape, np.uint8)
+        self.raw2 = np.zeros(self.raw_shape, np.uint8)
         self.lives_seen = 0
 
     # --- emulator ---
@@ -68,12 +72,16 @@ class SynthAtariEnv(object):
     # --- AtariEnv ---
     def _update_obs(self):
         self.raw2 = self._screen()
-        self.obs = oframe.update_obs(self.obs, self.raw1, self.raw2)
+        if self.rgb:
+            img = oframe.rgb_downsample(oframe.rgb_to_gray(np.maximum(self.raw1, self.raw2)))
+            self.obs = np.concatenate([self.obs[1:], img[np.newaxis]])
+        else:
+            self.obs = oframe.update_obs(self.obs, self.raw1, self.raw2)
 
     def _reset_obs(self):
         self.obs = np.zeros_like(self.obs)
-        self.raw1 = np.zeros((210, 160), np.uint8)
-        self.raw2 = np.zeros((210, 160), np.uint8)
+        self.raw1 = np.zeros(self.raw_shape, np.uint8)
+        self.raw2 = np.zeros(self.raw_shape, np.uint8)
 
     def _life_reset(self):
         self._act()          # act(0)
@@ -124,13 +132,18 @@ class OracleSampler(object):
         self.discount, self.mid_batch_reset, self.max_path_length = discount, mid_batch_reset, max_path_length
         self.envs = [SynthAtariEnv(e, pool, rules, num_img_obs, 4, clip_reward, episodic_lives) for e in range(n_envs)]
         N, P = n_envs * horizon, num_img_obs
+        oh, ow = self.envs[0].hw
+
+        class _HW(object):
+            H, W = oh, ow
+        oframe_hw = _HW
         self.buf = dict(
-            observations=np.zeros((N, P, oframe.H, oframe.W), np.uint8),
+            observations=np.zeros((N, P, oframe_hw.H, oframe_hw.W), np.uint8),
             rewards=np.zeros(N, np.float32), dones=np.zeros(N, bool),
             raw_reward=np.zeros(N, np.float32), need_reset=np.zeros(N, bool),
             actions=np.zeros(N, np.uint8), prob=np.zeros((N, n_actions), np.float32), value=np.zeros(N, np.float32),
-            extra_observations=np.zeros((n_envs, P, oframe.H, oframe.W), np.uint8))
-        self.step_obs = np.zeros((n_envs, P, oframe.H, oframe.W), np.uint8)
+            extra_observations=np.zeros((n_envs, P, oh, ow), np.uint8))
+        self.step_obs = np.zeros((n_envs, P, oh, ow), np.uint8)
         self.traj = [TrajInfo(discount) for _ in range(n_envs)]
         self.need = [False] * n_envs
         for e, env in enumerate(self.envs):            # start_envs

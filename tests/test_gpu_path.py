@@ -126,6 +126,56 @@ def test_device_sampler_vs_oracle_larger_batch():
         pol.engine.close()
 
 
+
+@pytest.mark.parametrize("mbr", [True, False])
+def test_device_sampler_rgb_mode_vs_oracle(mbr):
+    """north-star frame mode inside the sampler: RGB 210x160x3 emulator frames -> gray -> 84x84 stacks.  Device rollout
+    buffers == the oracle sampler run over the same RGB pool (oracle/frame.py:rgb_*, builder-defined arithmetic), with
+    resets, life losses and (mbr False) envs that stop stepping; then two PPO iterations run on those buffers."""
+    from accel_rl_b200.algos import PPO
+    from accel_rl_b200.util.seeding import set_seed
+    rules = dict(synth_ale.DEFAULT_RULES, pool_frames=64, life_base=10, life_mod=7, reward_mod=5, pool_seed=0)
+    set_seed(3)
+    B, T = 16, 12
+    sampler = _make_sampler(4, 2, T, mid_batch_reset=mbr, rules=rules, env_kw=dict(frame_mode="rgb"))
+    env_spec, sample_size, horizon, _ = sampler.initialize(seed=4, affinities=dict(), discount=0.99, need_extra_obs=True)
+    assert env_spec.observation_space.shape == (4, 84, 84)
+    pol, flat, spec = make_policy(1, hw=(84, 84))
+    algo = PPO(optimizer_args=dict(minibatch_size=64, epochs=1))
+    algo.initialize(pol, env_spec, sample_size, horizon, mbr)
+    sampler.policy_init(pol)
+    algo.set_n_itr(10)
+    pool = synth_ale.make_pool(64, seed=0, channels=3)
+    orc = osampler.OracleSampler(B, T, pool, {k: v for k, v in rules.items() if k != "pool_seed"}, 4, 0.99,
+                                 mid_batch_reset=mbr)
+    try:
+        for itr in range(3):
+            buf, infos = sampler.obtain_samples(itr)
+            b = _buf_np(buf)
+            u = sampler._uniforms_host.numpy().copy()
+            gp = b["prob"].reshape(B, T, 4); gv = b["value"].reshape(B, T)
+            calls = {"k": 0}
+
+            def policy_fn(obs):
+                k = calls["k"]; calls["k"] += 1
+                s, j = divmod(k, 2)
+                lo, hi = j * B // 2, (j + 1) * B // 2
+                return gp[lo:hi, s], gv[lo:hi, s]
+            ob, oinf = orc.obtain_samples(policy_fn, u)
+            for k in ("observations", "extra_observations", "rewards", "dones", "raw_reward", "need_reset", "actions"):
+                assert np.array_equal(b[k], ob[k]), (k, itr)
+            assert len(infos) == len(oinf)
+            # the policy saw exactly these observations: forward of the buffered rows reproduces the stored probabilities
+            if mbr:
+                p_ref, _ = onet.forward(torch.tensor(pol.get_param_values()), torch.tensor(ob["observations"][:32]), spec, 4, True)
+                assert relerr(b["prob"][:32], p_ref.numpy()) < 2e-3
+            opt_data, info = algo.optimize_policy(itr, buf)
+            assert np.isfinite(info["GradNorm"]).all()
+        assert pol.engine.device_error() == 0
+    finally:
+        pol.engine.close()
+
+
 def _run_iteration(algo_name, B, T, spec_id, mbr, mb, epochs, standardize=False, itrs=2):
     from accel_rl_b200.algos import PPO, A2C
     from accel_rl_b200.util.seeding import set_seed
