@@ -384,72 +384,131 @@ __global__ void __launch_bounds__(256) frame_kernel(const uint8_t* __restrict__ 
 // ===========================================================================
 constexpr int kRgbH = 210, kRgbW = 160, kNsH = 84, kNsW = 84;
 constexpr int kRgbRows = 4;                      // output rows per block (= 10 input rows)
-constexpr int kRgbThreads = 256;
+constexpr int kRgbThreads = 128;
+constexpr int kRgbInRows = kRgbRows * 5 / 2;     // 10
+constexpr int kRgbGrayWords = kRgbInRows * kRgbW / 4;   // 400 words of gray per slab (+1 pad word: the last column's
+                                                        // zero-weight third tap reads one byte past the row)
+
+// gray value of pixel K (0..15) of a 48-byte group held in 12 words: the pixel's R,G,B bytes are moved to byte lanes
+// 0..2 (byte lane 3 carries weight 0) and one dp4a forms 77 R + 150 G + 29 B + 128
+template <int K>
+ARL_DEVINL uint32_t rgb_gray_px(const uint32_t (&w)[12]) {
+  constexpr int b = 3 * K, wi = b >> 2, sh = b & 3;
+  uint32_t v;
+  if constexpr (sh == 0) v = w[wi];
+  else if constexpr (sh == 1) v = w[wi] >> 8;
+  else if constexpr (sh == 2) v = __byte_perm(w[wi], w[(wi + 1) % 12], 0x4432);
+  else v = __byte_perm(w[wi], w[(wi + 1) % 12], 0x5543);
+  return __dp4a(v, 0x001D964Du, 128u) >> 8;
+}
+
+template <int I>
+ARL_DEVINL uint32_t rgb_gray_word(const uint32_t (&w)[12]) {
+  return rgb_gray_px<4 * I>(w) | (rgb_gray_px<4 * I + 1>(w) << 8) | (rgb_gray_px<4 * I + 2>(w) << 16) |
+         (rgb_gray_px<4 * I + 3>(w) << 24);
+}
+
+// One slab = 10 input rows of an RGB frame pair (4800 bytes each, 16-byte aligned) -> 4 output rows of 84 pixels in
+// s_out.  Phase A: 100 threads each own 48 bytes = 16 pixels: six 16-byte loads in flight, per-channel max and the gray
+// conversion in registers, one 16-byte store of gray.  Phase B: thread x < 84 owns output column x: its three input
+// columns start at j0 = 40x/21; per input row ONE dp4a over the (unaligned) byte triple with the packed column
+// weights, then the four output rows are 3-row combinations (2,2,1 / 1,2,2).  Ends with a __syncthreads().
+ARL_DEVINL void rgb_slab_to_rows(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, uint32_t* s_gray,
+                                 uint8_t* s_out, int tid) {
+  constexpr int GROUPS48 = kRgbInRows * kRgbW * 3 / 48;   // 100
+  if (tid < GROUPS48) {
+    uint32_t w[12];
+    if (fb) {
+      const uint4* pb = reinterpret_cast<const uint4*>(fb) + tid * 3;
+      uint4 b0 = __ldg(pb), b1 = __ldg(pb + 1), b2 = __ldg(pb + 2);
+      if (fa) {
+        const uint4* pa = reinterpret_cast<const uint4*>(fa) + tid * 3;
+        uint4 a0 = __ldg(pa), a1 = __ldg(pa + 1), a2 = __ldg(pa + 2);
+        b0.x = __vmaxu4(a0.x, b0.x); b0.y = __vmaxu4(a0.y, b0.y); b0.z = __vmaxu4(a0.z, b0.z); b0.w = __vmaxu4(a0.w, b0.w);
+        b1.x = __vmaxu4(a1.x, b1.x); b1.y = __vmaxu4(a1.y, b1.y); b1.z = __vmaxu4(a1.z, b1.z); b1.w = __vmaxu4(a1.w, b1.w);
+        b2.x = __vmaxu4(a2.x, b2.x); b2.y = __vmaxu4(a2.y, b2.y); b2.z = __vmaxu4(a2.z, b2.z); b2.w = __vmaxu4(a2.w, b2.w);
+      }
+      w[0] = b0.x; w[1] = b0.y; w[2] = b0.z; w[3] = b0.w; w[4] = b1.x; w[5] = b1.y; w[6] = b1.z; w[7] = b1.w;
+      w[8] = b2.x; w[9] = b2.y; w[10] = b2.z; w[11] = b2.w;
+    } else if (fa) {
+      const uint4* pa = reinterpret_cast<const uint4*>(fa) + tid * 3;
+      uint4 a0 = __ldg(pa), a1 = __ldg(pa + 1), a2 = __ldg(pa + 2);
+      w[0] = a0.x; w[1] = a0.y; w[2] = a0.z; w[3] = a0.w; w[4] = a1.x; w[5] = a1.y; w[6] = a1.z; w[7] = a1.w;
+      w[8] = a2.x; w[9] = a2.y; w[10] = a2.z; w[11] = a2.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 12; ++i) w[i] = 0u;
+    }
+    uint4 g;
+    g.x = rgb_gray_word<0>(w); g.y = rgb_gray_word<1>(w); g.z = rgb_gray_word<2>(w); g.w = rgb_gray_word<3>(w);
+    reinterpret_cast<uint4*>(s_gray)[tid] = g;
+  }
+  if (tid == kRgbThreads - 1) s_gray[kRgbGrayWords] = 0u;
+  __syncthreads();
+  if (tid < kNsW) {
+    const int c_lo = 40 * tid;
+    const int j0 = c_lo / 21;
+    const int w0 = 21 * (j0 + 1) - c_lo;          // 1..21
+    const int w1 = min(21, 40 - w0);
+    const int w2 = 40 - w0 - w1;                  // 0 for the columns whose window spans two input columns only
+    const uint32_t wpack = (uint32_t)w0 | ((uint32_t)w1 << 8) | ((uint32_t)w2 << 16);
+    const int wbase = j0 >> 2;
+    const uint32_t sh = (uint32_t)(j0 & 3) * 8u;
+    uint32_t h[kRgbInRows];
+#pragma unroll
+    for (int r = 0; r < kRgbInRows; ++r) {
+      const uint32_t lo = s_gray[r * (kRgbW / 4) + wbase], hi = s_gray[r * (kRgbW / 4) + wbase + 1];
+      h[r] = __dp4a(__funnelshift_r(lo, hi, sh), wpack, 0u);
+    }
+    // output rows come in pairs over 5 input rows: even row -> rows 0,1,2 (weights 2,2,1), odd row -> rows 2,3,4 (1,2,2)
+#pragma unroll
+    for (int q = 0; q < kRgbRows / 2; ++q) {
+      const uint32_t ev = 2u * h[5 * q] + 2u * h[5 * q + 1] + h[5 * q + 2];
+      const uint32_t od = h[5 * q + 2] + 2u * h[5 * q + 3] + 2u * h[5 * q + 4];
+      s_out[(2 * q) * kNsW + tid] = (uint8_t)((ev + 100u) / 200u);
+      s_out[(2 * q + 1) * kNsW + tid] = (uint8_t)((od + 100u) / 200u);
+    }
+  }
+  __syncthreads();
+}
 
 __global__ void __launch_bounds__(kRgbThreads) frame_rgb_kernel(const uint8_t* __restrict__ raw_a,
                                                                 const uint8_t* __restrict__ raw_b,
                                                                 const uint8_t* __restrict__ reset_mask,
                                                                 uint8_t* __restrict__ stack, __nv_bfloat16* __restrict__ stack16,
                                                                 int n, int planes) {
-  constexpr int IN_ROWS = kRgbRows * 5 / 2;      // 10
-  constexpr int WORDS = IN_ROWS * kRgbW * 3 / 16;  // 300 16-byte words per frame
-  __shared__ __align__(16) uint8_t s_rgb[IN_ROWS * kRgbW * 3];
-  __shared__ uint8_t s_gray[IN_ROWS * kRgbW];
+  __shared__ __align__(16) uint32_t s_gray[kRgbGrayWords + 4];
   __shared__ __align__(4) uint8_t s_out[kRgbRows * kNsW];
   constexpr int GROUPS = kNsH / kRgbRows;        // 21 row groups per env
+  constexpr int WPR = kNsW / 4;                  // 21 words per output row
   const int e = blockIdx.x / GROUPS;
   const int grp = blockIdx.x - e * GROUPS;
   const int tid = threadIdx.x;
   const bool rs = reset_mask && reset_mask[e];
   const long fbytes = (long)kRgbH * kRgbW * 3;
-  const long roff = (long)grp * IN_ROWS * kRgbW * 3;
+  const long roff = (long)grp * kRgbInRows * kRgbW * 3;
   const uint8_t* fa = (raw_a && !rs) ? raw_a + (long)e * fbytes + roff : nullptr;
   const uint8_t* fb = raw_b + (long)e * fbytes + roff;
-  for (int i = tid; i < WORDS; i += kRgbThreads) {
-    uint4 b = __ldg(reinterpret_cast<const uint4*>(fb) + i);
-    if (fa) {
-      uint4 a = __ldg(reinterpret_cast<const uint4*>(fa) + i);
-      b.x = __vmaxu4(a.x, b.x); b.y = __vmaxu4(a.y, b.y); b.z = __vmaxu4(a.z, b.z); b.w = __vmaxu4(a.w, b.w);
-    }
-    reinterpret_cast<uint4*>(s_rgb)[i] = b;
-  }
-  __syncthreads();
-  for (int i = tid; i < IN_ROWS * kRgbW; i += kRgbThreads) {
-    const uint8_t* px = s_rgb + i * 3;
-    s_gray[i] = (uint8_t)((77u * px[0] + 150u * px[1] + 29u * px[2] + 128u) >> 8);
-  }
-  __syncthreads();
-  for (int o = tid; o < kRgbRows * kNsW; o += kRgbThreads) {
-    const int oy = o / kNsW, ox = o - oy * kNsW;
-    // output rows come in pairs over 5 input rows: even row -> rows 0,1,2 (weights 2,2,1), odd row -> rows 2,3,4 (1,2,2)
-    const int odd = oy & 1;
-    const int r0 = (oy >> 1) * 5 + odd * 2;
-    const int wy0 = odd ? 1 : 2, wy2 = odd ? 2 : 1;
-    const int c_lo = 40 * ox, c_hi = c_lo + 40;
-    const int j0 = c_lo / 21;
-    unsigned acc = 0;
-#pragma unroll
-    for (int dj = 0; dj < 3; ++dj) {
-      const int j = j0 + dj;
-      const int wx = min(c_hi, 21 * j + 21) - max(c_lo, 21 * j);
-      if (wx > 0 && j < kRgbW)
-        acc += (unsigned)wx * (wy0 * s_gray[r0 * kRgbW + j] + 2 * s_gray[(r0 + 1) * kRgbW + j] + wy2 * s_gray[(r0 + 2) * kRgbW + j]);
-    }
-    s_out[o] = (uint8_t)((acc + 100u) / 200u);
-  }
-  __syncthreads();
-  // stack shift + stores, 4 pixels per thread (84 = 21 words per row)
-  constexpr int WPR = kNsW / 4;
-  if (tid >= kRgbRows * WPR) return;
+  // stack shift + stores, 4 pixels per thread; the older planes are fetched before the frame work so their latency hides
+  const bool outp = tid < kRgbRows * WPR;
   const int oy = tid / WPR, xw = tid - oy * WPR;
   const int pix = (grp * kRgbRows + oy) * kNsW + xw * 4;
   const int plane_px = kNsH * kNsW;
   uint8_t* cur = stack + (long)e * planes * plane_px + pix;
+  uint32_t older[3] = {0u, 0u, 0u};
+  if (outp && !rs) {
+#pragma unroll
+    for (int p = 1; p < 4; ++p)
+      if (p < planes) older[p - 1] = *reinterpret_cast<const uint32_t*>(cur + p * plane_px);
+  }
+  rgb_slab_to_rows(fa, fb, s_gray, s_out, tid);
+  if (!outp) return;
   __nv_bfloat16* cur16 = stack16 ? stack16 + (long)e * planes * plane_px + pix : nullptr;
   const uint32_t newest = *reinterpret_cast<const uint32_t*>(s_out + oy * kNsW + xw * 4);
-  for (int p = 0; p < planes; ++p) {
-    uint32_t v = newest;
-    if (p < planes - 1) v = rs ? 0u : *reinterpret_cast<const uint32_t*>(cur + (p + 1) * plane_px);
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    if (p >= planes) break;
+    const uint32_t v = (p < planes - 1) ? older[p < 3 ? p : 2] : newest;
     *reinterpret_cast<uint32_t*>(cur + p * plane_px) = v;
     if (cur16) *reinterpret_cast<uint2*>(cur16 + p * plane_px) = u8x4_to_bf16x4(v);
   }
@@ -466,12 +525,10 @@ __global__ void __launch_bounds__(kRgbThreads) frame_rgb_roll_kernel(
     long img16) {
   pdl_wait();
   pdl_trigger();
-  constexpr int IN_ROWS = kRgbRows * 5 / 2;
-  constexpr int WORDS = IN_ROWS * kRgbW * 3 / 16;
-  __shared__ __align__(16) uint8_t s_rgb[IN_ROWS * kRgbW * 3];
-  __shared__ uint8_t s_gray[IN_ROWS * kRgbW];
+  __shared__ __align__(16) uint32_t s_gray[kRgbGrayWords + 4];
   __shared__ __align__(4) uint8_t s_out[kRgbRows * kNsW];
   constexpr int GROUPS = kNsH / kRgbRows;
+  constexpr int WPR = kNsW / 4;
   const int e = blockIdx.x / GROUPS;
   const int grp = blockIdx.x - e * GROUPS;
   const int tid = threadIdx.x;
@@ -479,7 +536,7 @@ __global__ void __launch_bounds__(kRgbThreads) frame_rgb_roll_kernel(
   if (c.flags & 2) return;                       // env not stepped: rows keep their stale contents
   const bool rs = (c.flags & 1) != 0;
   const long fbytes = (long)kRgbH * kRgbW * 3;
-  const long roff = (long)grp * IN_ROWS * kRgbW * 3;
+  const long roff = (long)grp * kRgbInRows * kRgbW * 3;
   const uint8_t* fa = nullptr;
   const uint8_t* fb = nullptr;
   if (staging) {
@@ -489,55 +546,31 @@ __global__ void __launch_bounds__(kRgbThreads) frame_rgb_roll_kernel(
     if (c.src_a >= 0) fa = pool + (long)c.src_a * fbytes + roff;
     if (c.src_b >= 0) fb = pool + (long)c.src_b * fbytes + roff;
   }
-  for (int i = tid; i < WORDS; i += kRgbThreads) {
-    uint4 b = fb ? __ldg(reinterpret_cast<const uint4*>(fb) + i) : make_uint4(0, 0, 0, 0);
-    if (fa) {
-      uint4 a = __ldg(reinterpret_cast<const uint4*>(fa) + i);
-      b.x = __vmaxu4(a.x, b.x); b.y = __vmaxu4(a.y, b.y); b.z = __vmaxu4(a.z, b.z); b.w = __vmaxu4(a.w, b.w);
-    }
-    reinterpret_cast<uint4*>(s_rgb)[i] = b;
-  }
-  __syncthreads();
-  for (int i = tid; i < IN_ROWS * kRgbW; i += kRgbThreads) {
-    const uint8_t* px = s_rgb + i * 3;
-    s_gray[i] = (uint8_t)((77u * px[0] + 150u * px[1] + 29u * px[2] + 128u) >> 8);
-  }
-  __syncthreads();
-  for (int o = tid; o < kRgbRows * kNsW; o += kRgbThreads) {
-    const int oy = o / kNsW, ox = o - oy * kNsW;
-    const int odd = oy & 1;
-    const int r0 = (oy >> 1) * 5 + odd * 2;
-    const int wy0 = odd ? 1 : 2, wy2 = odd ? 2 : 1;
-    const int c_lo = 40 * ox, c_hi = c_lo + 40;
-    const int j0 = c_lo / 21;
-    unsigned acc = 0;
-#pragma unroll
-    for (int dj = 0; dj < 3; ++dj) {
-      const int j = j0 + dj;
-      const int wx = min(c_hi, 21 * j + 21) - max(c_lo, 21 * j);
-      if (wx > 0 && j < kRgbW)
-        acc += (unsigned)wx * (wy0 * s_gray[r0 * kRgbW + j] + 2 * s_gray[(r0 + 1) * kRgbW + j] + wy2 * s_gray[(r0 + 2) * kRgbW + j]);
-    }
-    s_out[o] = (uint8_t)((acc + 100u) / 200u);
-  }
-  __syncthreads();
-  constexpr int WPR = kNsW / 4;
-  if (tid >= kRgbRows * WPR) return;
+  const bool outp = tid < kRgbRows * WPR;
   const int oy = tid / WPR, xw = tid - oy * WPR;
   const int Y = grp * kRgbRows + oy;
   const int pix = Y * kNsW + xw * 4;
   const int plane_px = kNsH * kNsW;
   const long obs_bytes = (long)planes * plane_px;
   uint8_t* cur = step_obs + (long)e * obs_bytes + pix;
+  uint32_t older[3] = {0u, 0u, 0u};
+  if (outp && !rs) {
+#pragma unroll
+    for (int p = 1; p < 4; ++p)
+      if (p < planes) older[p - 1] = *reinterpret_cast<const uint32_t*>(cur + p * plane_px);
+  }
+  rgb_slab_to_rows(fa, fb, s_gray, s_out, tid);
+  if (!outp) return;
   uint8_t* dst = roll_obs ? roll_obs + ((long)e * T + s_next) * obs_bytes + pix : nullptr;
   __nv_bfloat16* c16 = step_obs16 ? step_obs16 + (long)e * img16 : nullptr;
   __nv_bfloat16* d16 = (step_obs16 && roll_obs16) ? roll_obs16 + ((long)e * T + s_next) * img16 : nullptr;
   const int Cs = planes * 16;
   const int pos = (Y >> 2) * (kNsW / 4) + xw;
   const uint32_t newest = *reinterpret_cast<const uint32_t*>(s_out + oy * kNsW + xw * 4);
-  for (int p = 0; p < planes; ++p) {
-    uint32_t v = newest;
-    if (p < planes - 1) v = rs ? 0u : *reinterpret_cast<const uint32_t*>(cur + (p + 1) * plane_px);
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    if (p >= planes) break;
+    const uint32_t v = (p < planes - 1) ? older[p < 3 ? p : 2] : newest;
     *reinterpret_cast<uint32_t*>(cur + p * plane_px) = v;
     if (dst) *reinterpret_cast<uint32_t*>(dst + p * plane_px) = v;
     if (c16) {

@@ -26,6 +26,12 @@ sys.path.insert(0, ROOT)
 
 # per-sample MACs of preset 1 @ (4,104,80), A=4
 MACS = {"conv0": 3891200, "conv1": 3538944, "conv2": 3981312, "fc": 3538944}
+# --frames rgb (north-star mode): classic Nature-CNN @ (4,84,84), no padding: 20x20x32, 9x9x64, 7x7x64, FC 3136->512
+MACS_NATURE84 = {"conv0": 3276800, "conv1": 2654208, "conv2": 1806336, "fc": 1605632}
+NATURE84_SPEC = dict(conv_filter_sizes=[8, 4, 3], conv_filters=[32, 64, 64], conv_strides=[4, 2, 1],
+                     conv_pads=[(0, 0), (0, 0), (0, 0)], hidden_sizes=[512])
+# per-sample FLOPs: (fwd, train, conv-only fwd, conv-only train)
+FLOPS = {"gray": (29.906e6, 81.936e6, 22.823e6, 60.686e6), "rgb": (18.69e6, 49.52e6, 15.475e6, 39.870e6)}
 FLOP_PER_ENV_STEP_PPO = 357.9e6     # 1 act-fwd + 1/128 bootstrap fwd + 4 x train (81.936 MFLOP)
 FLOP_PER_ENV_STEP_CONV = 265.7e6    # conv tiles only: the north-star's "conv-tile roofline" numerator
 
@@ -58,6 +64,9 @@ def parse():
                     help="a2c: BASELINE configs[2]-style A2C (one full-batch RMSProp step per rollout; use --envs 1024 --horizon 5)")
     ap.add_argument("--parallelism", default="sync", choices=["sync", "async"],
                     help="multi-GPU learner: sync (configs[3], fused all-reduce) or async (configs[4], central store + chunk locks)")
+    ap.add_argument("--frames", default="gray", choices=["gray", "rgb"],
+                    help="gray: the reference's pipeline, 210x160 grayscale screens -> (4,104,80), cnn preset 1 (default, parity "
+                         "pinned); rgb: north-star mode, 210x160x3 RGB screens -> gray -> (4,84,84), classic Nature-CNN")
     ap.add_argument("--workload", default="ppo", choices=["ppo", "frame_sweep"],
                     help="ppo: the headline metric (default); frame_sweep: BASELINE configs[2] frame-kernel HBM GB/s sweep")
     return ap.parse_args()
@@ -121,8 +130,10 @@ def build_runner(args, frame_feed, rank, world):
     from accel_rl_b200.util import logger
     logger.configure(None, quiet=True)
     rules = dict(pool_frames=args.pool_frames)
+    rgb = getattr(args, "frames", "gray") == "rgb"
     sampler = ActsrvAltOvrlpSampler(
-        EnvCls=AtariEnv, env_args=dict(game="breakout", max_start_noops=0, synth_rules=rules),
+        EnvCls=AtariEnv, env_args=dict(game="breakout", max_start_noops=0, synth_rules=rules,
+                                       frame_mode="rgb" if rgb else "gray"),
         horizon=args.horizon, n_parallel=args.envs // 8, envs_per=4, max_path_length=27000, mid_batch_reset=True,
         max_decorrelation_steps=0, frame_feed=frame_feed)
     from accel_rl_b200.algos import A2C, mA2C, mA3C, mAPPO
@@ -130,7 +141,7 @@ def build_runner(args, frame_feed, rank, world):
     a2c = getattr(args, "algo", "ppo") == "a2c"
     asyn = getattr(args, "parallelism", "sync") == "async"
     opt_args = dict() if a2c else dict(minibatch_size=args.minibatch, epochs=args.epochs)
-    policy = AtariCnnPolicy(**cnn_specs[args.spec])
+    policy = AtariCnnPolicy(**(NATURE84_SPEC if rgb else cnn_specs[args.spec]))
     n_steps = args.envs * args.horizon * 10 ** 6
     if world > 1 or asyn:
         Algo = (mA3C if a2c else mAPPO) if asyn else (mA2C if a2c else mPPO)
@@ -225,11 +236,12 @@ def kernel_breakdown(runner, args):
 def kernel_flops(label, n, args):
     """algorithmic FLOPs of one launch processing n samples (None for non-GEMM kernels)"""
     base = label.split("/")[-1]
+    macs = MACS_NATURE84 if getattr(args, "frames", "gray") == "rgb" else MACS
     for k in ("conv0", "conv1", "conv2"):
         if base.startswith(k + "_") and base.split("_")[1] in ("fwd", "wgrad", "dgrad"):
-            return 2.0 * MACS[k] * n
+            return 2.0 * macs[k] * n
     if base in ("fc_fwd", "fc_wgrad", "fc_dgrad"):
-        return 2.0 * MACS["fc"] * n
+        return 2.0 * macs["fc"] * n
     return None
 
 
@@ -280,7 +292,8 @@ def run_ours(args):
                         "share_of_step": k["share"]}
                 break
         # per-env-step model FLOPs: PPO = fwd + fwd/T + epochs*train; A2C = fwd + fwd/T + train
-        fwd, train, cfwd, ctrain = 29.906e6, 81.936e6, 22.823e6, 60.686e6
+        fwd, train, cfwd, ctrain = FLOPS[args.frames]
+        rgb = args.frames == "rgb"
         k_train = args.epochs if args.algo == "ppo" else 1
         flop_step = (fwd * (1 + 1.0 / args.horizon) + k_train * train) if args.spec == 1 else None
         flop_conv = (cfwd * (1 + 1.0 / args.horizon) + k_train * ctrain) if args.spec == 1 else None
@@ -289,13 +302,17 @@ def run_ours(args):
             "unit": "env-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "PPO Breakout-shaped, %d envs/GPU x %d-step rollout, cnn preset %d @ (4,104,80), "
-                                   "%d epochs x mb %d, Adam; synthetic 210x160 grayscale emulator frames"
-                                   % (args.envs, args.horizon, args.spec, args.epochs, args.minibatch),
+            "config": {"workload": ("PPO Breakout-shaped, %d envs/GPU x %d-step rollout, %s, "
+                                    "%d epochs x mb %d, Adam; synthetic %s emulator frames"
+                                    % (args.envs, args.horizon,
+                                       "classic Nature-CNN @ (4,84,84)" if rgb else "cnn preset %d @ (4,104,80)" % args.spec,
+                                       args.epochs, args.minibatch, "210x160x3 RGB" if rgb else "210x160 grayscale")),
+                       "frames": args.frames,
                        "algo": args.algo, "learner": ("single" if world == 1 and args.parallelism == "sync" else args.parallelism),
                        "envs_per_gpu": args.envs, "horizon": args.horizon, "parallelism": "dp%d" % world,
-                       "l2_policy": "inputs larger than L2 (1.09 GB rollout buffer, %d MB frame pool)" %
-                                    (args.pool_frames * 33600 // 2 ** 20),
+                       "l2_policy": "inputs larger than L2 (%.2f GB rollout buffer, %d MB frame pool)" %
+                                    (N * 4 * (84 * 84 if rgb else 104 * 80) / 1e9,
+                                     args.pool_frames * (100800 if rgb else 33600) // 2 ** 20),
                        "step": "one full PPO iteration"},
             "clocks": clk,
             "gpu_launches": int(launches),
@@ -326,8 +343,9 @@ def run_ours(args):
                              "h2d_bytes_per_step": int((smp.h2d_bytes - h0) / n_it + idx_bytes),
                              "d2h_bytes_per_step": int((smp.d2h_bytes - d0) / n_it + log_bytes),
                              "ms_per_step": round(ms2, 3),
-                             "note": "raw emulator frames (2 x 210x160 u8 per env-step) H2D from pinned memory on a copy "
-                                     "stream, actions D2H every step, losses/grad norms D2H every iteration"}
+                             "note": "raw emulator frames (2 x %s u8 per env-step) H2D from pinned memory on a copy "
+                                     "stream, actions D2H every step, losses/grad norms D2H every iteration"
+                                     % ("210x160x3" if args.frames == "rgb" else "210x160")}
         r2.policy.engine.close()
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         result["cpu_baseline"] = cpu_port(args, steps=1)
@@ -351,10 +369,12 @@ def cpu_port(args, steps=1, warmup=0):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     B, Ts = args.envs, args.cpu_sample_steps
-    spec = onet.CNN_SPECS[args.spec]
+    rgb = getattr(args, "frames", "gray") == "rgb"
+    spec = dict(NATURE84_SPEC, conv_pads=[0, 0, 0]) if rgb else onet.CNN_SPECS[args.spec]
     rules = dict(synth_ale.DEFAULT_RULES, pool_frames=256)
-    pool = synth_ale.make_pool(256, seed=0)
-    flat = onet.init_params(spec, (4, 104, 80), 4, np.random.RandomState(0), np.random.RandomState(1))
+    pool = synth_ale.make_pool(256, seed=0, channels=3) if rgb else synth_ale.make_pool(256, seed=0)
+    flat = onet.init_params(spec, (4, 84, 84) if rgb else (4, 104, 80), 4, np.random.RandomState(0),
+                            np.random.RandomState(1))
     smp = osampler.OracleSampler(B, Ts, pool, rules, 4, 0.99)
     opt = onet.Adam(flat.size, 1e-3, epsilon=1e-5)
     rng = np.random.RandomState(0)
@@ -449,9 +469,12 @@ def run_reference(args):
            "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": round(1e3 * N / r["value"], 1), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "PPO Breakout-shaped, %d envs x %d-step rollout, cnn preset %d @ (4,104,80), %d epochs x "
+           "config": {"workload": "PPO Breakout-shaped, %d envs x %d-step rollout, %s, %d epochs x "
                                   "mb %d (CPU port of the reference path; ms_per_step extrapolated from the bounded sample)"
-                                  % (args.envs, args.horizon, args.spec, args.epochs, args.minibatch)},
+                                  % (args.envs, args.horizon,
+                                     "classic Nature-CNN @ (4,84,84), RGB frames" if args.frames == "rgb"
+                                     else "cnn preset %d @ (4,104,80)" % args.spec, args.epochs, args.minibatch),
+                      "frames": args.frames},
            "cpu_baseline": r,
            "e2e": {"value": r["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "wall_s": round(time.time() - t0, 1)}
