@@ -98,6 +98,7 @@ SIGNATURES = {
     "arl_frame_update": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "arl_frame_update_rgb": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "arl_sampler_configure": (C.c_int, [_P, C.POINTER(SamplerCfg)]),
+    "arl_sampler_select": (C.c_int, [_P, C.c_int]),
     "arl_sampler_reset": (C.c_int, [_P, _P]),
     "arl_rollout_begin": (C.c_int, [_P, _P]),
     "arl_rollout_step": (C.c_int, [_P, C.c_int, _P, _P]),
@@ -116,6 +117,8 @@ SIGNATURES = {
     "arl_train_minibatches_async": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
     "arl_read_logs": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(C.c_int), _P]),
     "arl_reset_opt_state": (C.c_int, [_P, _P]),
+    "arl_opt_step_get": (C.c_int, [_P, C.POINTER(C.c_int), _P]),
+    "arl_opt_step_set": (C.c_int, [_P, C.c_int, _P]),
     "arl_comm_local_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "arl_comm_buffers": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
     "arl_comm_connect": (C.c_int, [_P, _P]),

@@ -57,6 +57,15 @@ class AdvActorCriticBase(RLAlgorithm):
     def set_n_itr(self, n_itr):
         self.n_itr = n_itr
 
+    # AccelRLEval calls these around sampler.evaluate_policy (runners/accel_rl.py:137-139); in the reference only DQN
+    # defines them (algos/dqn/dqn.py:209-216: swap in the eval epsilon).  A policy-gradient policy samples from its own
+    # distribution in evaluation too, so there is nothing to switch.
+    def prep_eval(self, itr):
+        pass
+
+    def post_eval(self, itr):
+        pass
+
     def optimize_policy(self, itr, samples_data):
         opt_data = self.process_samples(itr, samples_data)
         opt_input_values = self.prep_opt_inputs(itr, samples_data, opt_data)

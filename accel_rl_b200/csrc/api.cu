@@ -157,6 +157,22 @@ struct arl_ctx {
   __nv_bfloat16* step_obs16 = nullptr; // [B] bf16 space-to-depth mirror of step_obs
   __nv_bfloat16* roll_obs16 = nullptr; // [N] mirror of observations
   cudaGraphExec_t rollout_graph = nullptr;
+  // the fields above are the ACTIVE sampler; arl_sampler_select parks them here and loads the other slot
+  // (slot 0: training sampler, slot 1: evaluation sampler — its own envs, step buffer and trajectory records)
+  struct SamplerSlot {
+    arl_sampler_cfg sc{};
+    bool set = false;
+    EnvState est{};
+    TrajOut tout{};
+    FrameCmd* cmd = nullptr;
+    int* rows_tab = nullptr;
+    __nv_bfloat16* step_obs16 = nullptr;
+    __nv_bfloat16* roll_obs16 = nullptr;
+    cudaGraphExec_t rollout_graph = nullptr;
+    long graph_rollout_nodes = 0;
+  };
+  SamplerSlot slots[2];
+  int cur_slot = 0;
   // training graph cache
   cudaGraphExec_t train_graph = nullptr;
   const int* train_graph_idx = nullptr;
@@ -1293,14 +1309,16 @@ int rollout_begin(arl_ctx* c, cudaStream_t st) {
   int row_bytes = s.planes * c->cfg.in_h * c->cfg.in_w;
   long chunks = (long)s.n_envs * (row_bytes / 16);
   // observations[e*T + 0] = step_obs[e]   (worker.py:31-32) — and the same for the bf16 mirror
-  copy_rows_kernel<<<(int)((chunks + 255) / 256), 256, 0, st>>>(s.step_obs, row_bytes, nullptr, s.observations, row_bytes,
-                                                               c->rows_tab, s.n_envs, row_bytes);
-  int row16 = (int)(c->obs16_elems * 2);
-  long chunks16 = (long)s.n_envs * (row16 / 16);
-  copy_rows_kernel<<<(int)((chunks16 + 255) / 256), 256, 0, st>>>(
-      reinterpret_cast<const uint8_t*>(c->step_obs16), row16, nullptr, reinterpret_cast<uint8_t*>(c->roll_obs16), row16,
-      c->rows_tab, s.n_envs, row16);
-  c->launches += 2;
+  if (s.observations) {
+    copy_rows_kernel<<<(int)((chunks + 255) / 256), 256, 0, st>>>(s.step_obs, row_bytes, nullptr, s.observations, row_bytes,
+                                                                 c->rows_tab, s.n_envs, row_bytes);
+    int row16 = (int)(c->obs16_elems * 2);
+    long chunks16 = (long)s.n_envs * (row16 / 16);
+    copy_rows_kernel<<<(int)((chunks16 + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const uint8_t*>(c->step_obs16), row16, nullptr, reinterpret_cast<uint8_t*>(c->roll_obs16), row16,
+        c->rows_tab, s.n_envs, row16);
+    c->launches += 2;
+  }
   ARL_CHECK(c, cudaMemsetAsync(c->tout.count, 0, sizeof(int), st));
   ARL_CHECK(c, cudaGetLastError());
   return 0;
@@ -1408,6 +1426,12 @@ void arl_destroy(arl_ctx* c) {
   if (c->rollout_graph) cudaGraphExecDestroy(c->rollout_graph);
   if (c->train_graph) cudaGraphExecDestroy(c->train_graph);
   cudaFree(c->est.f); cudaFree(c->cmd); cudaFree(c->rows_tab); cudaFree(c->tout.count);
+  {
+    arl_ctx::SamplerSlot& o = c->slots[1 - c->cur_slot];     // the parked sampler
+    if (o.rollout_graph) cudaGraphExecDestroy(o.rollout_graph);
+    cudaFree(o.est.f); cudaFree(o.cmd); cudaFree(o.rows_tab); cudaFree(o.tout.count);
+    cudaFree(o.step_obs16); cudaFree(o.roll_obs16);
+  }
   delete c;
 }
 
@@ -1432,6 +1456,8 @@ int arl_bind_params(arl_ctx* c, float* params, float* grad, float* m, float* v) 
   c->params = params; c->grad = grad; c->m = m; c->v = v;
   if (c->train_graph) { cudaGraphExecDestroy(c->train_graph); c->train_graph = nullptr; }
   if (c->rollout_graph) { cudaGraphExecDestroy(c->rollout_graph); c->rollout_graph = nullptr; }
+  for (auto& o : c->slots)
+    if (o.rollout_graph) { cudaGraphExecDestroy(o.rollout_graph); o.rollout_graph = nullptr; }
   return 0;
 }
 
@@ -1515,9 +1541,26 @@ int arl_sampler_configure(arl_ctx* c, const arl_sampler_cfg* cfg) {
   ARL_CHECK(c, cudaMemcpy(c->rows_tab, rt.data(), rt.size() * sizeof(int), cudaMemcpyHostToDevice));
   // bf16 space-to-depth mirrors of the step buffer and of the rollout observations (what conv layer 0 reads)
   if (dev_alloc(c, &c->step_obs16, (size_t)B * c->obs16_elems + 64 * 1024)) return 1;
-  if (dev_alloc(c, &c->roll_obs16, (size_t)B * T * c->obs16_elems + 64 * 1024)) return 1;
+  // a sampler without an observations buffer (evaluation: nothing is stored, sampler_with_eval.py:36-38) has no mirror
+  c->roll_obs16 = nullptr;
+  if (cfg->observations && dev_alloc(c, &c->roll_obs16, (size_t)B * T * c->obs16_elems + 64 * 1024)) return 1;
   c->sampler_set = true;
   if (c->rollout_graph) { cudaGraphExecDestroy(c->rollout_graph); c->rollout_graph = nullptr; }
+  return 0;
+}
+
+int arl_sampler_select(arl_ctx* c, int slot) {
+  if (slot != 0 && slot != 1) ARL_FAIL(c, "sampler slot must be 0 (training) or 1 (evaluation)");
+  if (slot == c->cur_slot) return 0;
+  arl_ctx::SamplerSlot& o = c->slots[c->cur_slot];
+  o.sc = c->sc; o.set = c->sampler_set; o.est = c->est; o.tout = c->tout; o.cmd = c->cmd; o.rows_tab = c->rows_tab;
+  o.step_obs16 = c->step_obs16; o.roll_obs16 = c->roll_obs16; o.rollout_graph = c->rollout_graph;
+  o.graph_rollout_nodes = c->graph_rollout_nodes;
+  const arl_ctx::SamplerSlot& n = c->slots[slot];
+  c->sc = n.sc; c->sampler_set = n.set; c->est = n.est; c->tout = n.tout; c->cmd = n.cmd; c->rows_tab = n.rows_tab;
+  c->step_obs16 = n.step_obs16; c->roll_obs16 = n.roll_obs16; c->rollout_graph = n.rollout_graph;
+  c->graph_rollout_nodes = n.graph_rollout_nodes;
+  c->cur_slot = slot;
   return 0;
 }
 
@@ -1737,6 +1780,21 @@ int arl_reset_opt_state(arl_ctx* c, void* stream) {
   ARL_CHECK(c, cudaMemsetAsync(c->log_slot, 0, sizeof(int), st));
   if (c->m) ARL_CHECK(c, cudaMemsetAsync(c->m, 0, c->n_params * sizeof(float), st));
   if (c->v) ARL_CHECK(c, cudaMemsetAsync(c->v, 0, c->n_params * sizeof(float), st));
+  return 0;
+}
+
+int arl_opt_step_get(arl_ctx* c, int* t, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  ARL_CHECK(c, cudaMemcpyAsync(t, c->step, sizeof(int), cudaMemcpyDeviceToHost, st));
+  ARL_CHECK(c, cudaStreamSynchronize(st));
+  return 0;
+}
+
+int arl_opt_step_set(arl_ctx* c, int t, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (t < 0) ARL_FAIL(c, "optimizer step count must be >= 0");
+  ARL_CHECK(c, cudaMemcpyAsync(c->step, &t, sizeof(int), cudaMemcpyHostToDevice, st));
+  ARL_CHECK(c, cudaStreamSynchronize(st));
   return 0;
 }
 

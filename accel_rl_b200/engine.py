@@ -57,6 +57,7 @@ class Engine(object):
         self.v = torch.zeros_like(self.params)
         self._keep = {}
         self._sym = None
+        self._dp_mode = None            # "synchronous" / "asynchronous" once comm_init / async_init ran
         self.bind()
 
     # ---- plumbing ----------------------------------------------------------------------------
@@ -118,8 +119,13 @@ class Engine(object):
                                                  L.ptr(stack_bf16), n, planes, self._s()))
 
     # ---- sampler -----------------------------------------------------------------------------
+    def sampler_select(self, slot):
+        """0: training sampler (default), 1: evaluation sampler"""
+        self._sampler_slot = int(slot)
+        self.check(self.lib.arl_sampler_select(self.ctx, int(slot)))
+
     def sampler_configure(self, cfg, keep):
-        self._keep["sampler"] = keep
+        self._keep["sampler%d" % getattr(self, "_sampler_slot", 0)] = keep
         self.check(self.lib.arl_sampler_configure(self.ctx, C.byref(cfg)))
 
     def sampler_reset(self):
@@ -191,6 +197,26 @@ class Engine(object):
     def reset_opt_state(self):
         self.check(self.lib.arl_reset_opt_state(self.ctx, self._s()))
 
+    def get_opt_state(self):
+        """-> dict(m, v, step): first/second moment vectors (RMSProp keeps its accumulator in v) and the update count"""
+        if self._dp_mode is not None:
+            raise NotImplementedError("optimizer-state snapshots cover the single-GPU learner (the %s learner keeps m "
+                                      "and v %s)" % (self._dp_mode, "sharded across ranks" if self._dp_mode == "synchronous"
+                                                     else "in the central store"))
+        t = C.c_int()
+        self.check(self.lib.arl_opt_step_get(self.ctx, C.byref(t), self._s()))
+        return dict(m=self.m.detach().cpu().numpy().copy(), v=self.v.detach().cpu().numpy().copy(), step=int(t.value))
+
+    def set_opt_state(self, state):
+        if self._dp_mode is not None:
+            raise NotImplementedError("optimizer-state restore covers the single-GPU learner")
+        for k in ("m", "v"):
+            a = np.ascontiguousarray(np.asarray(state[k], dtype=np.float32)).reshape(-1)
+            if a.size != self.n_params:
+                raise ValueError("optimizer state '%s' has %d entries, expected %d" % (k, a.size, self.n_params))
+            getattr(self, k).copy_(torch.from_numpy(a))
+        self.check(self.lib.arl_opt_step_set(self.ctx, int(state["step"]), self._s()))
+
     # ---- profiling ---------------------------------------------------------------------------
     def profile_begin(self):
         self.check(self.lib.arl_profile_begin(self.ctx, self._s()))
@@ -217,6 +243,7 @@ class Engine(object):
     def comm_init(self, rank, world, exchange):
         """exchange(handle_bytes) -> list of every rank's handle bytes (e.g. torch.distributed all_gather)."""
         h = (C.c_uint8 * L.IPC_HANDLE_BYTES)()
+        self._dp_mode = "synchronous"
         self.check(self.lib.arl_comm_local_init(self.ctx, int(rank), int(world), h))
         g, p = C.c_void_p(), C.c_void_p()
         self.check(self.lib.arl_comm_buffers(self.ctx, C.byref(g), C.byref(p)))
@@ -240,6 +267,7 @@ class Engine(object):
     def async_init(self, rank, world, n_update_chunks, exchange):
         """exchange(handle_bytes) -> list of every rank's handle bytes; rank 0's entry is the central store."""
         h = (C.c_uint8 * L.IPC_HANDLE_BYTES)()
+        self._dp_mode = "asynchronous"
         self.check(self.lib.arl_async_local_init(self.ctx, int(rank), int(world), int(n_update_chunks), h))
         handles = exchange(bytes(h))
         buf = (C.c_uint8 * L.IPC_HANDLE_BYTES).from_buffer_copy(handles[0])

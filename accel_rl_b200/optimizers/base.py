@@ -46,6 +46,13 @@ class BaseOptimizer(object):
     def set_lr_mult(self, lr_mult):
         self._engine.set_lr_mult(lr_mult)
 
+    # ---- snapshot / resume (the reference's snapshot holds parameters only) ---------
+    def get_state(self):
+        return self._engine.get_opt_state()
+
+    def set_state(self, state):
+        self._engine.set_opt_state(state)
+
     def _bind_inputs(self, inputs):
         obs, act, adv, ret, old_value, old_prob = inputs[:6]
         valids = inputs[6] if len(inputs) > 6 else None

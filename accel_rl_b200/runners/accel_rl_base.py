@@ -14,9 +14,13 @@ from accel_rl_b200.util.seeding import set_seed
 
 
 class AccelRLBase(Runner):
-    def __init__(self, algo, policy, sampler, n_steps, seed=None, affinities=None, use_gpu=True):
+    def __init__(self, algo, policy, sampler, n_steps, seed=None, affinities=None, use_gpu=True, resume_from=None):
+        # resume_from (not in the reference, whose resume path is AtariCnnPolicy(initial_param_values=...) only):
+        # a snapshot dict or the path of one written by save_itr_snapshot — restores parameters, optimizer state
+        # (m, v, update count) and the iteration counter (so a linear lr schedule continues where it stopped)
         n_steps = int(n_steps)
         save_args(vars(), underscore=False)
+        self._start_itr = 0
         if affinities is None:
             self.affinities = dict()
         if algo.optimizer.parallelism_tag != self.parallelism_tag:
@@ -38,6 +42,8 @@ class AccelRLBase(Runner):
         self.algo.initialize(policy=self.policy, env_spec=env_spec, sample_size=sample_size, horizon=horizon,
                              mid_batch_reset=mid_batch_reset)
         self.sampler.policy_init(self.policy)
+        if self.resume_from is not None:
+            self.load_snapshot(self.resume_from)
         if master:
             n_itr = self.get_n_itr(sample_size)
             self.algo.set_n_itr(n_itr)
@@ -83,7 +89,25 @@ class AccelRLBase(Runner):
         self.sampler.shutdown()
 
     def get_itr_snapshot(self, itr):
-        return dict(itr=itr, cum_samples=itr * self._sample_size, policy_param_values=self.policy.get_param_values())
+        # itr, cum_samples, policy_param_values: the reference's snapshot (accel_rl_base.py:108-113);
+        # optimizer_state: what a bit-exact resume additionally needs
+        snap = dict(itr=itr, cum_samples=itr * self._sample_size, policy_param_values=self.policy.get_param_values())
+        try:
+            snap["optimizer_state"] = self.algo.optimizer.get_state()
+        except NotImplementedError:
+            pass
+        return snap
+
+    def load_snapshot(self, snapshot):
+        """restore parameters (+ optimizer state when the snapshot has it); training continues at snapshot itr + 1"""
+        if isinstance(snapshot, str):
+            import joblib
+            snapshot = joblib.load(snapshot)
+        self.policy.set_param_values(snapshot["policy_param_values"])
+        if "optimizer_state" in snapshot:
+            self.algo.optimizer.set_state(snapshot["optimizer_state"])
+        self._start_itr = int(snapshot["itr"]) + 1
+        logger.log("Resumed from the snapshot of iteration {}".format(snapshot["itr"]))
 
     def save_itr_snapshot(self, itr):
         logger.save_itr_params(itr, self.get_itr_snapshot(itr))

@@ -112,6 +112,11 @@ int arl_frame_update_rgb(arl_ctx* ctx, const uint8_t* raw_a, const uint8_t* raw_
 
 /* ---- sampler: ActsrvAltOvrlpSampler.obtain_samples (sampler/.../overlap/sampler.py:97-151) --- */
 int arl_sampler_configure(arl_ctx* ctx, const arl_sampler_cfg* cfg);
+/* Two sampler slots per context: 0 = training envs (default), 1 = evaluation envs (AAOEvalSampler's eval_envs /
+ * eval_step_bufs, overlap/sampler_with_eval.py:6-54, worker_with_eval.py:66-99).  configure / reset / rollout_* /
+ * traj_read act on the selected slot; a slot configured with observations == NULL stores no observations (evaluation
+ * keeps only rewards/dones/actions/agent infos rows and the TrajInfo records). */
+int arl_sampler_select(arl_ctx* ctx, int slot);
 int arl_sampler_reset(arl_ctx* ctx, void* stream);                  /* start_envs (sampler/util.py:26-57) */
 int arl_rollout_begin(arl_ctx* ctx, void* stream);
 /* one serve+step: forward on step_obs, sample, env step, frame update.  staging (optional):
@@ -151,6 +156,10 @@ int arl_train_minibatches_async(arl_ctx* ctx, const int* idx, int mb_size, int c
 /* per-update logs since the last call: losses and pre-clip grad norms (host arrays) */
 int arl_read_logs(arl_ctx* ctx, float* loss, float* grad_norm, int cap, int* n, void* stream);
 int arl_reset_opt_state(arl_ctx* ctx, void* stream);
+/* the update count t of Adam's bias correction (update_methods_stats.py:70-73), for snapshot / resume of the optimizer
+ * state next to the caller-owned m and v vectors (the reference snapshots parameters only, accel_rl_base.py:108-113) */
+int arl_opt_step_get(arl_ctx* ctx, int* t, void* stream);
+int arl_opt_step_set(arl_ctx* ctx, int t, void* stream);
 
 /* ---- sync data parallel: optimizers/sync/base.py:8-24 + sync_ppo_optimizer.py:13-78 ----------- */
 #define ARL_IPC_HANDLE_BYTES 64

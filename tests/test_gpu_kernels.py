@@ -230,6 +230,61 @@ def test_clip_and_update_rules(kind, clip):
         eng.close()
 
 
+@pytest.mark.parametrize("kind", ["adam", "rmsprop"])
+def test_optimizer_state_snapshot_resume_is_bit_exact(kind):
+    """snapshot / resume of the optimizer state: parameters + (m, v, update count) moved into a
+    fresh engine continue the update sequence bit for bit, and match the oracle's Adam / RMSProp after 5 steps"""
+    rng = np.random.RandomState(9)
+    cfg = dict(algo=0, clip_param=0.2, v_loss_coeff=1.0, ent_loss_coeff=0.01, update=0 if kind == "adam" else 1,
+               learning_rate=1e-3 if kind == "adam" else 7e-4, beta1=0.9, beta2=0.999,
+               epsilon=1e-5 if kind == "adam" else 1e-6, rho=0.9, grad_norm_clip=0.5)
+    pol, flat, spec = make_policy(0, max_rows=8)
+    n = flat.size
+    grads = [(rng.randn(n) * 0.01).astype(np.float32) for _ in range(5)]
+
+    def run(eng, gs):
+        for g in gs:
+            eng.grad.copy_(torch.tensor(g))
+            eng.clip_update(1.0)
+        eng.read_logs()
+        return eng.get_params()
+    eng = pol.engine
+    try:
+        eng.opt_configure(**cfg)
+        eng.reset_opt_state()
+        straight = run(eng, grads)
+    finally:
+        eng.close()
+    pol2, _, _ = make_policy(0, max_rows=8)
+    eng2 = pol2.engine
+    try:
+        eng2.opt_configure(**cfg)
+        eng2.reset_opt_state()
+        mid = run(eng2, grads[:2])
+        state = eng2.get_opt_state()
+        assert state["step"] == 2 and state["m"].shape == (n,) and state["v"].shape == (n,)
+    finally:
+        eng2.close()
+    pol3, _, _ = make_policy(0, max_rows=8, seed=5)           # different initial parameters: everything comes from the snapshot
+    eng3 = pol3.engine
+    try:
+        eng3.opt_configure(**cfg)
+        eng3.reset_opt_state()
+        eng3.set_params(mid)
+        eng3.set_opt_state(state)
+        resumed = run(eng3, grads[2:])
+        assert eng3.get_opt_state()["step"] == 5
+    finally:
+        eng3.close()
+    assert np.array_equal(resumed, straight)
+    opt = onet.Adam(n, 1e-3, epsilon=1e-5) if kind == "adam" else onet.RMSProp(n, 7e-4)
+    p = flat.copy()
+    for g in grads:
+        gc, _ = onet.total_norm_clip(g, 0.5)
+        p = opt.step(p, gc, 1.0)
+    np.testing.assert_allclose(straight, p, rtol=1e-6, atol=1e-7)
+
+
 def test_nature_cnn_84x84_geometry_vs_oracle():
     """the classic 84x84 Nature-CNN geometry (8x8/4, 4x4/2, 3x3/1, no padding): forward and per-tensor gradients against
     the oracle.  Its 21x21 space-to-depth grid is not a multiple of 8 positions, so this exercises the im2col-gather

@@ -176,6 +176,73 @@ def test_device_sampler_rgb_mode_vs_oracle(mbr):
         pol.engine.close()
 
 
+def test_eval_sampler_vs_oracle_and_training_envs_untouched():
+    """AAOEvalSampler.evaluate_policy (sampler_with_eval.py:20-33, worker_with_eval.py:66-99): the evaluation envs are
+    reset at the start of every evaluation, run eval_horizon steps, and return exactly the trajectories the oracle
+    sampler completes on fresh envs with the same probabilities and uniforms; the training rollouts before and after
+    are those of a sampler that never evaluated (its envs and step buffer are untouched)."""
+    from accel_rl_b200.sampler import AAOEvalSampler
+    from accel_rl_b200.envs import AtariEnv
+    from accel_rl_b200.util.seeding import set_seed
+    rules = dict(synth_ale.DEFAULT_RULES, pool_frames=128, life_base=9, life_mod=5, reward_mod=7, pool_seed=0)
+    orules = {k: v for k, v in rules.items() if k != "pool_seed"}
+    set_seed(5)
+    B, T = 16, 8
+    Be, eval_steps = 8, 8 * 60
+    sampler = AAOEvalSampler(eval_steps, 1, EnvCls=AtariEnv,
+                             env_args=dict(game="breakout", max_start_noops=0, synth_rules=rules), horizon=T,
+                             n_parallel=4, envs_per=2, max_path_length=27000, mid_batch_reset=True,
+                             max_decorrelation_steps=0)
+    assert sampler.eval_horizon == 60 and sampler._total_n_eval_envs == Be
+    sampler.initialize(seed=2, affinities=dict(), discount=0.99, need_extra_obs=True)
+    pol, flat, spec = make_policy(1, max_rows=B)
+    sampler.policy_init(pol)
+    pool = synth_ale.make_pool(128, seed=0)
+    orc = osampler.OracleSampler(B, T, pool, orules, 4, 0.99)
+
+    def feeder(prob, val, n, horizon):
+        calls = {"k": 0}
+
+        def policy_fn(obs):
+            k = calls["k"]; calls["k"] += 1
+            s, j = divmod(k, 2)
+            lo, hi = j * n // 2, (j + 1) * n // 2
+            return prob[lo:hi, s], val[lo:hi, s]
+        return policy_fn
+
+    def key(ti):
+        return (ti["env"], ti["Length"], round(float(ti["Return"]), 4), round(float(ti["RawReturn"]), 4),
+                ti["NonzeroRewards"], round(float(ti["DiscountedReturn"]), 3))
+    try:
+        n_eval_traj = 0
+        for itr in range(3):
+            # --- evaluation: fresh oracle envs every time ---
+            infos = sampler.evaluate_policy(itr)
+            eb = sampler.eval_buf
+            Te = sampler.eval_horizon
+            ue = sampler._eval_uniforms_host.numpy().copy()
+            ep = t2n(eb.prob).reshape(Be, Te, 4); ev = t2n(eb.value).reshape(Be, Te)
+            eorc = osampler.OracleSampler(Be, Te, pool, orules, 4, 0.99)
+            ob, oinf = eorc.obtain_samples(feeder(ep, ev, Be, Te), ue)
+            for k in ("rewards", "dones", "raw_reward", "need_reset", "actions"):
+                assert np.array_equal(t2n(getattr(eb, k)), ob[k]), ("eval", k, itr)
+            assert sorted(key(t) for t in infos) == sorted(key(t) for t in oinf)
+            n_eval_traj += len(infos)
+            # --- training rollout continues as if no evaluation had happened ---
+            buf, tinfos = sampler.obtain_samples(itr)
+            b = _buf_np(buf)
+            u = sampler._uniforms_host.numpy().copy()
+            gp = b["prob"].reshape(B, T, 4); gv = b["value"].reshape(B, T)
+            ob, oinf = orc.obtain_samples(feeder(gp, gv, B, T), u)
+            for k in ("observations", "extra_observations", "rewards", "dones", "raw_reward", "need_reset", "actions"):
+                assert np.array_equal(b[k], ob[k]), ("train", k, itr)
+            assert len(tinfos) == len(oinf)
+        assert n_eval_traj > 0
+        assert pol.engine.device_error() == 0
+    finally:
+        pol.engine.close()
+
+
 def _run_iteration(algo_name, B, T, spec_id, mbr, mb, epochs, standardize=False, itrs=2):
     from accel_rl_b200.algos import PPO, A2C
     from accel_rl_b200.util.seeding import set_seed
@@ -277,6 +344,51 @@ def test_runner_trains_and_logs(tmp_path):
     assert row["NormFromInit"] > 0 and np.isfinite(row["GradNormAverage"])
     assert os.path.exists(os.path.join(str(tmp_path), "progress.csv"))
     policy.engine.close()
+    logger.configure(None)
+
+
+def test_eval_runner_snapshot_and_resume(tmp_path):
+    """AccelRLEval + AAOEvalSampler (runners/accel_rl.py:108-180): evaluation rows in progress.csv, a 'last' snapshot
+    with parameters AND optimizer state, and a second runner resuming from it at the next iteration."""
+    import joblib
+    from accel_rl_b200.algos import PPO
+    from accel_rl_b200.envs import AtariEnv
+    from accel_rl_b200.policies import AtariCnnPolicy, cnn_specs
+    from accel_rl_b200.runners import AccelRLEval
+    from accel_rl_b200.sampler import AAOEvalSampler
+    from accel_rl_b200.util import logger
+    rules = dict(synth_ale.DEFAULT_RULES, pool_frames=128, life_base=9, life_mod=5, reward_mod=7, pool_seed=0)
+
+    def make(resume=None):
+        sampler = AAOEvalSampler(16 * 50, 2, EnvCls=AtariEnv,
+                                 env_args=dict(game="breakout", max_start_noops=0, synth_rules=rules), horizon=16,
+                                 n_parallel=4, envs_per=4, mid_batch_reset=True, max_decorrelation_steps=0)
+        algo = PPO(optimizer_args=dict(minibatch_size=128, epochs=2), lr_schedule="linear")
+        policy = AtariCnnPolicy(**cnn_specs[0])
+        return AccelRLEval(algo=algo, policy=policy, sampler=sampler, n_steps=32 * 16 * 4, seed=0,
+                           eval_interval_steps=32 * 16 * 2, resume_from=resume), policy
+    logger.configure(str(tmp_path), snapshot_mode="last", quiet=True)
+    runner, policy = make()
+    runner.train()
+    row = dict(logger.last_row)
+    for k in ("Iteration", "CumCompletedSteps", "StepsInEval", "TrajsInEval", "LengthAverage", "ReturnAverage",
+              "GradNormAverage", "CumTrainTime", "CumEvalTime", "SamplesPerSecond"):
+        assert k in row, k
+    assert row["TrajsInEval"] > 0 and row["StepsInEval"] > 0
+    snap_path = os.path.join(str(tmp_path), "params.pkl")
+    snap = joblib.load(snap_path)
+    assert snap["itr"] == row["Iteration"] and "optimizer_state" in snap
+    assert snap["optimizer_state"]["step"] == snap["itr"] * 2 * (32 * 16 // 128)
+    assert snap["optimizer_state"]["m"].any() and snap["optimizer_state"]["v"].any()
+    policy.engine.close()
+    # resume: parameters and optimizer state come from the snapshot, iterations continue after it
+    runner2, policy2 = make(resume=snap_path)
+    n_itr = runner2.startup()
+    assert runner2._start_itr == snap["itr"] + 1 <= n_itr
+    assert np.array_equal(policy2.get_param_values(), snap["policy_param_values"])
+    st = runner2.algo.optimizer.get_state()
+    assert st["step"] == snap["optimizer_state"]["step"] and np.array_equal(st["m"], snap["optimizer_state"]["m"])
+    policy2.engine.close()
     logger.configure(None)
 
 
