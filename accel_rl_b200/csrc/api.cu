@@ -132,6 +132,10 @@ struct arl_ctx {
   float* head_b_partial = nullptr; // [G][A+1]
   float* loss_partial = nullptr;   // [kLossBlocks][4]
   double* sumsq_partial = nullptr;
+  double* sumsq_partial_fc = nullptr;  // update_range_kernel's per-block sums of squares (early FC update)
+  bool train_step_active = false;      // grad_minibatch is followed by the local clip_update (train_minibatches, sync == 0)
+  bool early_fc_done = false;          // this minibatch's FC weights were updated by update_range_kernel
+  cudaEvent_t ev_fcd = nullptr;        // "FC data gradient has read the FC weights"
   unsigned long long* ticket = nullptr; // grid-barrier ticket of update_fused_kernel
   float* hyper = nullptr;          // [0] lr_mult
   int* step = nullptr;             // Adam t
@@ -864,6 +868,7 @@ int alloc_net(arl_ctx* c) {
   if (dev_alloc(c, &c->head_b_partial, (size_t)64 * (c->A + 1))) return 1;
   if (dev_alloc(c, &c->loss_partial, (size_t)R * 4)) return 1;
   if (dev_alloc(c, &c->sumsq_partial, (size_t)kSumsqBlocks)) return 1;
+  if (dev_alloc(c, &c->sumsq_partial_fc, (size_t)kEarlyBlocks)) return 1;
   if (dev_alloc(c, &c->ticket, 4)) return 1;
   if (dev_alloc(c, &c->hyper, 8)) return 1;
   float one = 1.f;
@@ -1051,6 +1056,9 @@ int get_plan(arl_ctx* c, int n, TrainPlan** out) {
   return 0;
 }
 
+bool early_fc_ok(arl_ctx* c);
+int early_fc_update(arl_ctx* c, cudaStream_t st);
+
 // forward + loss + backward for one minibatch -> flat grad
 int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaStream_t st) {
   if (!c->opt_set) ARL_FAIL(c, "optimizer not configured");
@@ -1103,6 +1111,7 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
       ARL_CHECK(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
       ARL_CHECK(c, cudaStreamCreateWithFlags(&c->side2, cudaStreamNonBlocking));
       ARL_CHECK(c, cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming));
+      ARL_CHECK(c, cudaEventCreateWithFlags(&c->ev_fcd, cudaEventDisableTiming));
     }
     ws = c->side;
     ARL_CHECK(c, cudaEventRecord(c->ev_fork[0], st));
@@ -1136,6 +1145,16 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
   if (fct) {
     if (fc_dgrad_tiles(c, n, st)) return 1;
     prof_mark(c, "fc_dgrad", st);
+    if (early_fc_ok(c)) {
+      // both FC gradient kernels are issued: once the data gradient has read the weights (and the weight gradient,
+      // earlier on ws, has written its rows of the flat gradient) the FC weights take their Adam/RMSProp step while
+      // the conv gradient chain runs
+      if (ws != st) {
+        ARL_CHECK(c, cudaEventRecord(c->ev_fcd, st));
+        ARL_CHECK(c, cudaStreamWaitEvent(ws, c->ev_fcd, 0));
+      }
+      if (early_fc_update(c, ws)) return 1;
+    }
   } else {
     DenseLoader<128> a{};
     a.src = c->dh; a.ld = c->H; a.nrows = n;
@@ -1239,9 +1258,35 @@ int pack_weights(arl_ctx* c, cudaStream_t st, bool with_fc = true, bool advance 
   return 0;
 }
 
-int clip_update(arl_ctx* c, float gscale, cudaStream_t st) {
-  if (!c->opt_set) ARL_FAIL(c, "optimizer not configured");
-  if (!c->m || !c->v) ARL_FAIL(c, "optimizer state not bound");
+UpdateParams update_params(arl_ctx* c, float gscale, bool* fused_cast_out);
+
+// the FC weights can be updated before the rest of the backward pass finishes when nothing couples them to the other
+// gradients: no global-norm clipping, local update, operand copy refreshed by the update kernel itself.
+// OFF by default (ARL_EARLY_FC=1 enables): bit-identical results (tests/test_gpu_path.py), but measured SLOWER on B200 —
+// 61.8 vs 60.5 ms per PPO iteration.  The minibatch is bound by total SM time, not by its critical path: every GEMM
+// kernel is a persistent 1-CTA/SM grid, so the update kernel taken off the tail only time-slices the same SMs, and
+// the split costs a second launch (22.7 us range update + 8.9 us rest, against 22.4 us for the single fused update).
+bool early_fc_ok(arl_ctx* c) {
+  static const bool on = getenv("ARL_EARLY_FC") && atoi(getenv("ARL_EARLY_FC")) != 0;
+  static const bool fused = !(getenv("ARL_FUSED_UPDATE") && atoi(getenv("ARL_FUSED_UPDATE")) == 0);
+  return on && fused && c->train_step_active && c->opt_set && c->opt.grad_norm_clip <= 0.f && c->m && c->v &&
+         c->pc_mode >= 2 && fc_tiles_ok(c) && (c->off_Wfc % 4 == 0) && (((long)c->Kfc * c->H) % 4 == 0);
+}
+
+int early_fc_update(arl_ctx* c, cudaStream_t st) {
+  bool fused_cast = false;
+  UpdateParams u = update_params(c, 1.f, &fused_cast);
+  if (!fused_cast) ARL_FAIL(c, "early FC update needs the fused operand copy");
+  ARL_CHECK(c, launch_k(update_range_kernel, dim3(kEarlyBlocks), dim3(256), 0, st, u, c->off_Wfc / 4, (long)c->Kfc * c->H / 4,
+                        c->sumsq_partial_fc));
+  c->launches++;
+  prof_mark(c, "fc_update", st);
+  ARL_CHECK(c, cudaGetLastError());
+  c->early_fc_done = true;
+  return 0;
+}
+
+UpdateParams update_params(arl_ctx* c, float gscale, bool* fused_cast_out) {
   UpdateParams u{};
   u.param = c->params; u.grad = c->grad; u.m = c->m; u.v = c->v; u.n = c->n_params;
   u.sumsq_partial = c->sumsq_partial; u.n_partial = kSumsqBlocks;
@@ -1254,6 +1299,21 @@ int clip_update(arl_ctx* c, float gscale, cudaStream_t st) {
   bool fused_cast = (c->off_Wfc % 4 == 0) && (c->H % 4 == 0);
   if (fc_tiles_ok(c)) { u.shadow = c->wfc_t; u.shadow_tiles = 1; u.shadow_HW = c->HWlast; u.shadow_H = c->H; }
   if (!fused_cast) u.shadow = nullptr;
+  *fused_cast_out = fused_cast;
+  return u;
+}
+
+int clip_update(arl_ctx* c, float gscale, cudaStream_t st) {
+  if (!c->opt_set) ARL_FAIL(c, "optimizer not configured");
+  if (!c->m || !c->v) ARL_FAIL(c, "optimizer state not bound");
+  bool fused_cast = false;
+  UpdateParams u = update_params(c, gscale, &fused_cast);
+  if (c->early_fc_done) {
+    // the FC range is done (update_range_kernel): norm over the rest + its partials, update the rest
+    u.skip4_begin = c->off_Wfc / 4; u.skip4_len = (long)c->Kfc * c->H / 4;
+    u.sumsq_partial2 = c->sumsq_partial_fc; u.n_partial2 = kEarlyBlocks;
+    c->early_fc_done = false;
+  }
   // norm + clip + update in one launch (update_fused_kernel); ARL_FUSED_UPDATE=0 keeps the two-kernel form
   static const bool fused = !(getenv("ARL_FUSED_UPDATE") && atoi(getenv("ARL_FUSED_UPDATE")) == 0);
   if (fused) {
@@ -1420,7 +1480,7 @@ void arl_destroy(arl_ctx* c) {
   if (c->shadow_in_comm) { (fc_tiles_ok(c) ? c->wfc_t : c->wfc_bf16) = nullptr; }
   cudaFree(c->wfc_bf16); cudaFree(c->obs16_stage); cudaFree(c->step_obs16); cudaFree(c->roll_obs16); cudaFree(c->pack_jobs_dev); cudaFree(c->fc_partial); cudaFree(c->h); cudaFree(c->dh);
   cudaFree(c->dlogit); cudaFree(c->head_partial); cudaFree(c->head_b_partial); cudaFree(c->loss_partial);
-  cudaFree(c->sumsq_partial); cudaFree(c->hyper); cudaFree(c->step); cudaFree(c->log_slot); cudaFree(c->log_norm);
+  cudaFree(c->sumsq_partial); cudaFree(c->sumsq_partial_fc); cudaFree(c->hyper); cudaFree(c->step); cudaFree(c->log_slot); cudaFree(c->log_norm);
   cudaFree(c->log_loss); cudaFree(c->mb_counter); cudaFree(c->valid_count);
   for (auto& kv : c->plans) cudaFree(kv.second.jobs_dev);
   if (c->rollout_graph) cudaGraphExecDestroy(c->rollout_graph);
@@ -1707,6 +1767,11 @@ namespace {
 int train_minibatches(arl_ctx* c, const int* idx, int mb_size, int count, int sync, cudaStream_t st) {
   // sync: 0 = local clip + update, 1 = synchronous DP step, 2 = asynchronous push/pull
   auto step = [&](cudaStream_t s_) { return sync == 1 ? sync_update(c, s_) : sync == 2 ? async_push_pull(c, s_) : clip_update(c, 1.f, s_); };
+  struct Active {      // grad_minibatch may update the FC weights early only when the local clip_update follows it
+    arl_ctx* c;
+    Active(arl_ctx* c_, bool on) : c(c_) { c->train_step_active = on; }
+    ~Active() { c->train_step_active = false; c->early_fc_done = false; }
+  } active(c, sync == 0);
   if (!(c->sampler_set && c->t_obs == c->sc.observations && c->roll_obs16) || (sync && c->sync_graph_failed)) {
     // training inputs that are not the sampler's rollout buffers: plain launches, one minibatch at a time
     const bool replay_idx = c->sampler_set && c->t_obs == c->sc.observations && c->roll_obs16;
@@ -1974,8 +2039,11 @@ int arl_profile_graph(arl_ctx* c, int kind, const int* idx, int mb_size, int rep
   ARL_CHECK(c, cudaStreamBeginCapture(cap_s, cudaStreamCaptureModeThreadLocal));
   int rc = 0;
   if (kind == 0) {
+    c->train_step_active = true;
     rc = grad_minibatch(c, idx, c->mb_counter, mb_size, cap_s);
     if (!rc) rc = clip_update(c, 1.f, cap_s);
+    c->train_step_active = false;
+    c->early_fc_done = false;
   } else if (kind == 1) {
     rc = rollout_step(c, 0, nullptr, cap_s);
   } else {

@@ -1020,27 +1020,33 @@ __global__ void __launch_bounds__(256) finalize_grads_kernel(const GradJob* __re
 //                  applies avg -> clip -> Adam/RMSProp; block 0 records grad_norm and loss.
 // ===========================================================================
 constexpr int kSumsqBlocks = 592;   // 4 x 148
+constexpr int kEarlyBlocks = 296;   // update_range_kernel grid: 2 x 148
 
-ARL_DEVINL void sumsq_body(const float* __restrict__ g, long n, float gscale, double* __restrict__ partial);
+ARL_DEVINL void sumsq_body(const float* __restrict__ g, long n, float gscale, double* __restrict__ partial,
+                           long skip4_begin = 0, long skip4_len = 0);
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long n, float gscale,
                                                      double* __restrict__ partial) {
   sumsq_body(g, n, gscale, partial);
 }
 
-ARL_DEVINL void sumsq_body(const float* __restrict__ g, long n, float gscale, double* __restrict__ partial) {
+// float4 groups [skip4_begin, skip4_begin + skip4_len) are left out (their sum of squares was taken by
+// update_range_kernel); the remaining groups are walked in index order
+ARL_DEVINL void sumsq_body(const float* __restrict__ g, long n, float gscale, double* __restrict__ partial,
+                           long skip4_begin, long skip4_len) {
   pdl_wait();
   pdl_trigger();
   double acc = 0.0;
-  const long n4 = n >> 2;
+  const long n4 = (n >> 2) - skip4_len;
   const float4* g4 = reinterpret_cast<const float4*>(g);
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+  for (long j = (long)blockIdx.x * blockDim.x + threadIdx.x; j < n4; j += (long)gridDim.x * blockDim.x) {
+    const long i = j < skip4_begin ? j : j + skip4_len;
     float4 v = g4[i];
     float a = v.x * gscale, b = v.y * gscale, c = v.z * gscale, d = v.w * gscale;
     acc += (double)(a * a + b * b) + (double)(c * c + d * d);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0)
-    for (long i = n4 << 2; i < n; ++i) { float a = g[i] * gscale; acc += (double)a * a; }
+    for (long i = (n >> 2) << 2; i < n; ++i) { float a = g[i] * gscale; acc += (double)a * a; }
   __shared__ double s[8];
   acc = warp_sum_d(acc);
   if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
@@ -1075,6 +1081,10 @@ struct UpdateParams {
   int* log_slot; int log_cap;
   __nv_bfloat16* shadow; long shadow_begin, shadow_end;   // bf16 copy of params[shadow_begin, shadow_end) (4-aligned)
   int shadow_tiles, shadow_HW, shadow_H;                  // != 0: the copy is the tiled wfc_t layout (H % 4 == 0)
+  // float4 groups [skip4_begin, skip4_begin + skip4_len) were already updated by update_range_kernel (no clipping:
+  // the update does not depend on the norm); their sum of squares arrives in sumsq_partial2
+  long skip4_begin, skip4_len;
+  const double* sumsq_partial2; int n_partial2;
 };
 
 ARL_DEVINL void update_body(const UpdateParams& p);
@@ -1092,7 +1102,7 @@ __global__ void __launch_bounds__(256, 4) update_fused_kernel(UpdateParams p, do
                                                               unsigned long long* __restrict__ ticket) {
   pdl_wait();
   pdl_trigger();
-  sumsq_body(p.grad, p.n, p.gscale, partial);
+  sumsq_body(p.grad, p.n, p.gscale, partial, p.skip4_begin, p.skip4_len);
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -1108,12 +1118,90 @@ __global__ void __launch_bounds__(256, 4) update_fused_kernel(UpdateParams p, do
   update_body(p);
 }
 
+// Adam / RMSProp on float4 group i (+ the bf16 operand copy of the FC weights, refreshed in the same pass)
+ARL_DEVINL void update_vec4(const UpdateParams& p, long i, float scale, float alpha) {
+  float4 g4 = reinterpret_cast<const float4*>(p.grad)[i];
+  float4 p4 = reinterpret_cast<float4*>(p.param)[i];
+  float4 v4 = reinterpret_cast<float4*>(p.v)[i];
+  float g[4] = {g4.x * scale, g4.y * scale, g4.z * scale, g4.w * scale};
+  float pp[4] = {p4.x, p4.y, p4.z, p4.w};
+  float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+  if (p.kind == 0) {
+    float4 m4 = reinterpret_cast<float4*>(p.m)[i];
+    float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      mm[k] = p.beta1 * mm[k] + (1.f - p.beta1) * g[k];
+      vv[k] = p.beta2 * vv[k] + (1.f - p.beta2) * g[k] * g[k];
+      pp[k] -= alpha * mm[k] / (sqrtf(vv[k]) + p.eps);
+    }
+    reinterpret_cast<float4*>(p.m)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      vv[k] = p.rho * vv[k] + (1.f - p.rho) * g[k] * g[k];
+      pp[k] -= alpha * g[k] / sqrtf(vv[k] + p.eps);
+    }
+  }
+  reinterpret_cast<float4*>(p.v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+  reinterpret_cast<float4*>(p.param)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+  const long e0 = i << 2;
+  if (p.shadow && e0 >= p.shadow_begin && e0 + 4 <= p.shadow_end) {
+    long off = e0 - p.shadow_begin;
+    if (p.shadow_tiles) {
+      const unsigned ou = (unsigned)off, rr = ou / (unsigned)p.shadow_H;
+      off = fc_tile_index(rr, (int)(ou - rr * (unsigned)p.shadow_H), p.shadow_HW, p.shadow_H);
+    }
+    *reinterpret_cast<uint2*>(p.shadow + off) = make_uint2(pack_bf16x2(pp[0], pp[1]), pack_bf16x2(pp[2], pp[3]));
+  }
+}
+
+// step size of this update: lr * lr_mult, with Adam's bias correction for update count step + 1
+ARL_DEVINL float update_alpha(const UpdateParams& p) {
+  const int tstep = p.step[0] + 1;
+  const float lr = p.lr * p.hyper[0];
+  if (p.kind != 0) return lr;
+  const double b1t = pow((double)p.beta1, (double)tstep), b2t = pow((double)p.beta2, (double)tstep);
+  return (float)((double)lr * sqrt(1.0 - b2t) / (1.0 - b1t));
+}
+
+// Early update of one parameter range (the FC weights: 98 % of the vector) as soon as its gradient is final, while the
+// conv data/weight-gradient chain is still running.  Only legal without global-norm clipping (PPO's default,
+// algos/pg/ppo.py:29): the update then depends on nothing but its own gradient; the norm is still reported, from the
+// per-block sums of squares left in `partial` for update_fused_kernel.  Does not advance the update count.
+__global__ void __launch_bounds__(256) update_range_kernel(UpdateParams p, long begin4, long len4, double* __restrict__ partial) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float s_alpha;
+  __shared__ double s[8];
+  if (threadIdx.x == 0) s_alpha = update_alpha(p);
+  __syncthreads();
+  const float alpha = s_alpha, scale = p.gscale;
+  double acc = 0.0;
+  for (long j = (long)blockIdx.x * blockDim.x + threadIdx.x; j < len4; j += (long)gridDim.x * blockDim.x) {
+    const long i = begin4 + j;
+    const float4 v = reinterpret_cast<const float4*>(p.grad)[i];
+    const float a = v.x * scale, b = v.y * scale, c = v.z * scale, d = v.w * scale;
+    acc += (double)(a * a + b * b) + (double)(c * c + d * d);
+    update_vec4(p, i, scale, alpha);
+  }
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s[w];
+    partial[blockIdx.x] = t;
+  }
+}
+
 ARL_DEVINL void update_body(const UpdateParams& p) {
   __shared__ double s_red[8];
   __shared__ float s_scale, s_alpha;
   // every block: reduce the partial sums in the same order -> identical norm everywhere
   double acc = 0.0;
   for (int i = threadIdx.x; i < p.n_partial; i += blockDim.x) acc += p.sumsq_partial[i];
+  for (int i = threadIdx.x; i < p.n_partial2; i += blockDim.x) acc += p.sumsq_partial2[i];
   acc = warp_sum_d(acc);
   if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
   __syncthreads();
@@ -1124,14 +1212,7 @@ ARL_DEVINL void update_body(const UpdateParams& p) {
     float scale = p.gscale;
     if (p.clip > 0.f) scale *= fminf(norm, p.clip) / (1e-7f + norm);
     s_scale = scale;
-    int tstep = p.step[0] + 1;
-    float lr = p.lr * p.hyper[0];
-    if (p.kind == 0) {
-      double b1t = pow((double)p.beta1, (double)tstep), b2t = pow((double)p.beta2, (double)tstep);
-      s_alpha = (float)((double)lr * sqrt(1.0 - b2t) / (1.0 - b1t));
-    } else {
-      s_alpha = lr;
-    }
+    s_alpha = update_alpha(p);
     if (blockIdx.x == 0) {
       int slot = p.log_slot[0];
       if (slot < p.log_cap) p.out_norm[slot] = norm;
@@ -1154,46 +1235,11 @@ ARL_DEVINL void update_body(const UpdateParams& p) {
     }
   }
   const float scale = s_scale, alpha = s_alpha;
-  const long n4 = p.n >> 2;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
-    float4 g4 = reinterpret_cast<const float4*>(p.grad)[i];
-    float4 p4 = reinterpret_cast<float4*>(p.param)[i];
-    float4 v4 = reinterpret_cast<float4*>(p.v)[i];
-    float g[4] = {g4.x * scale, g4.y * scale, g4.z * scale, g4.w * scale};
-    float pp[4] = {p4.x, p4.y, p4.z, p4.w};
-    float vv[4] = {v4.x, v4.y, v4.z, v4.w};
-    if (p.kind == 0) {
-      float4 m4 = reinterpret_cast<float4*>(p.m)[i];
-      float mm[4] = {m4.x, m4.y, m4.z, m4.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        mm[k] = p.beta1 * mm[k] + (1.f - p.beta1) * g[k];
-        vv[k] = p.beta2 * vv[k] + (1.f - p.beta2) * g[k] * g[k];
-        pp[k] -= alpha * mm[k] / (sqrtf(vv[k]) + p.eps);
-      }
-      reinterpret_cast<float4*>(p.m)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
-    } else {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        vv[k] = p.rho * vv[k] + (1.f - p.rho) * g[k] * g[k];
-        pp[k] -= alpha * g[k] / sqrtf(vv[k] + p.eps);
-      }
-    }
-    reinterpret_cast<float4*>(p.v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
-    reinterpret_cast<float4*>(p.param)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
-    // bf16 operand copy of the FC weights (same layout), refreshed in the same pass
-    const long e0 = i << 2;
-    if (p.shadow && e0 >= p.shadow_begin && e0 + 4 <= p.shadow_end) {
-      long off = e0 - p.shadow_begin;
-      if (p.shadow_tiles) {
-        const unsigned ou = (unsigned)off, rr = ou / (unsigned)p.shadow_H;
-        off = fc_tile_index(rr, (int)(ou - rr * (unsigned)p.shadow_H), p.shadow_HW, p.shadow_H);
-      }
-      *reinterpret_cast<uint2*>(p.shadow + off) = make_uint2(pack_bf16x2(pp[0], pp[1]), pack_bf16x2(pp[2], pp[3]));
-    }
-  }
+  const long n4 = (p.n >> 2) - p.skip4_len;
+  for (long j = (long)blockIdx.x * blockDim.x + threadIdx.x; j < n4; j += (long)gridDim.x * blockDim.x)
+    update_vec4(p, j < p.skip4_begin ? j : j + p.skip4_len, scale, alpha);
   if (blockIdx.x == 0 && threadIdx.x < (p.n & 3)) {
-    long i = (n4 << 2) + threadIdx.x;
+    long i = ((p.n >> 2) << 2) + threadIdx.x;
     float g = p.grad[i] * scale;
     if (p.kind == 0) {
       float m = p.beta1 * p.m[i] + (1.f - p.beta1) * g;

@@ -308,6 +308,29 @@ def test_ppo_iteration_vs_oracle(standardize):
         assert cos > 0.99
 
 
+def test_early_fc_update_is_bit_identical():
+    """Without global-norm clipping (PPO's default) the FC weights are updated as soon as their gradient is final, while
+    the conv gradient chain still runs (update_range_kernel).  Same arithmetic per element: parameters and optimizer
+    state after two PPO iterations are bit-identical to the single end-of-minibatch update; the logged norms agree to
+    fp32 rounding (the partial sums are grouped differently)."""
+    import json
+    import subprocess
+    import sys
+    res = {}
+    for flag in ("0", "1"):
+        env = dict(os.environ, ARL_EARLY_FC=flag)
+        p = subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), "early_fc_worker.py")], env=env,
+                           capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")][-1]
+        res[flag] = json.loads(line[len("RESULT "):])
+    a, b = res["0"], res["1"]
+    assert a["device_error"] == 0 and b["device_error"] == 0
+    assert a["step"] == b["step"] == 2 * 2 * 4
+    assert a["params"] == b["params"] and a["m"] == b["m"] and a["v"] == b["v"]
+    np.testing.assert_allclose(a["norms"], b["norms"], rtol=2e-6)
+
+
 def test_a2c_nonreset_iteration_vs_oracle():
     """A2C as shipped by the reference example: mid_batch_reset=False -> valids mask, zero_after_reset,
     valids-weighted loss means (SURVEY.md §8 a6')."""
