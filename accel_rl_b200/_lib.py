@@ -78,8 +78,15 @@ class SamplerCfg(C.Structure):
         ("reward_mod", C.c_int),
         ("frame_stride", C.c_int),
         ("traj_cap", C.c_int),
+        ("ext_emulator", C.c_int),
         ("frame_mode", C.c_int),
     ]
+
+
+class ExtStep(C.Structure):
+    """arl_ext_step"""
+    _fields_ = [("reward", C.c_float), ("raw_reward", C.c_float), ("done", C.c_uint8), ("need_reset", C.c_uint8),
+                ("flags", C.c_uint8), ("pad", C.c_uint8)]
 
 
 # name -> (restype, argtypes); must list every symbol include/accelrl_b200.h declares
@@ -104,6 +111,11 @@ SIGNATURES = {
     "arl_rollout_step": (C.c_int, [_P, C.c_int, _P, _P]),
     "arl_rollout_end": (C.c_int, [_P, _P]),
     "arl_rollout_run": (C.c_int, [_P, _P]),
+    "arl_rollout_serve": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
+    "arl_rollout_ingest": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "arl_host_register": (C.c_int, [_P, C.c_size_t]),
+    "arl_host_unregister": (C.c_int, [_P]),
+    "arl_copy_async": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_int, _P]),
     "arl_traj_read": (C.c_int, [_P, C.POINTER(C.c_int), _P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "arl_peek_frame_cmds": (C.c_int, [_P, _P, C.c_int, _P]),
     "arl_gae": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_float, C.c_float, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),

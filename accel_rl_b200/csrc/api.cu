@@ -1340,24 +1340,34 @@ SynthCfg synth_cfg(const arl_sampler_cfg& s) {
   return k;
 }
 
-int launch_frame(arl_ctx* c, const uint8_t* staging, int s_next, bool to_rollout, cudaStream_t st) {
+// frame pipeline for envs [e0, e0 + n) (n < 0: all).  The kernels index everything by env, so a sub-range is the same
+// launch over base pointers advanced by e0 envs (staging is the base of the whole [B][2][frame] block).
+int launch_frame(arl_ctx* c, const uint8_t* staging, int s_next, bool to_rollout, cudaStream_t st, int e0 = 0, int n = -1) {
   const arl_sampler_cfg& s = c->sc;
+  if (n < 0) n = s.n_envs - e0;
+  const long T = s.horizon;
+  const long obs_bytes = (long)s.planes * c->cfg.in_h * c->cfg.in_w;
+  const long fbytes = (long)kRawH * kRawW * (s.frame_mode == 1 ? 3 : 1);
+  const uint8_t* stg = staging ? staging + (long)e0 * 2 * fbytes : nullptr;
+  const FrameCmd* cmd = c->cmd + e0;
+  uint8_t* step_obs = s.step_obs + (long)e0 * obs_bytes;
+  uint8_t* roll_obs = (to_rollout && s.observations) ? s.observations + (long)e0 * T * obs_bytes : nullptr;
+  __nv_bfloat16* step16 = c->step_obs16 ? c->step_obs16 + (long)e0 * c->obs16_elems : nullptr;
+  __nv_bfloat16* roll16 = (to_rollout && c->roll_obs16) ? c->roll_obs16 + (long)e0 * T * c->obs16_elems : nullptr;
   if (s.frame_mode == 1) {
     // north-star frames: RGB pool / staging -> gray -> 84x84 (frame_rgb_roll_kernel)
-    ARL_CHECK(c, launch_k(frame_rgb_roll_kernel, dim3(s.n_envs * (kNsH / kRgbRows)), dim3(kRgbThreads), 0, st, s.frame_pool, staging,
-                          c->cmd, s.step_obs, to_rollout ? s.observations : nullptr, c->step_obs16,
-                          to_rollout ? c->roll_obs16 : nullptr, s.horizon, s_next, s.n_envs, s.planes, c->pc_mode >= 2,
+    ARL_CHECK(c, launch_k(frame_rgb_roll_kernel, dim3(n * (kNsH / kRgbRows)), dim3(kRgbThreads), 0, st, s.frame_pool, stg,
+                          cmd, step_obs, roll_obs, step16, roll16, s.horizon, s_next, n, s.planes, c->pc_mode >= 2,
                           c->pc_mode >= 2, c->obs16_elems));
     c->launches++;
     prof_mark(c, "frame", st);
     ARL_CHECK(c, cudaGetLastError());
     return 0;
   }
-  long items = (long)s.n_envs * 520;
+  long items = (long)n * 520;
   int blocks = (int)((items + 255) / 256);
-  ARL_CHECK(c, launch_k(frame_kernel, dim3(blocks), dim3(256), 0, st, s.frame_pool, staging, c->cmd, s.step_obs, to_rollout ? s.observations : nullptr,
-                                       c->step_obs16, to_rollout ? c->roll_obs16 : nullptr, s.horizon, s_next, s.n_envs,
-                                       s.planes, c->pc_mode >= 2, c->pc_mode >= 2));
+  ARL_CHECK(c, launch_k(frame_kernel, dim3(blocks), dim3(256), 0, st, s.frame_pool, stg, cmd, step_obs, roll_obs, step16, roll16,
+                        s.horizon, s_next, n, s.planes, c->pc_mode >= 2, c->pc_mode >= 2));
   c->launches++;
   prof_mark(c, "frame", st);
   ARL_CHECK(c, cudaGetLastError());
@@ -1402,7 +1412,7 @@ int rollout_end(arl_ctx* c, cudaStream_t st) {
     size_t bytes = (size_t)s.n_envs * s.planes * c->cfg.in_h * c->cfg.in_w;
     ARL_CHECK(c, cudaMemcpyAsync(s.extra_observations, s.step_obs, bytes, cudaMemcpyDeviceToDevice, st));
   }
-  if (!s.mid_batch_reset) {
+  if (!s.mid_batch_reset && !s.ext_emulator) {   // (external emulators: the workers reset, then arl_rollout_ingest(s = T))
     env_reset_needed_kernel<<<(s.n_envs + 127) / 128, 128, 0, st>>>(synth_cfg(s), c->est, c->cmd, s.n_envs);
     c->launches++;
     ARL_CHECK(c, cudaGetLastError());
@@ -1645,6 +1655,48 @@ int arl_rollout_step(arl_ctx* c, int s, const uint8_t* staging, void* stream) {
 int arl_rollout_end(arl_ctx* c, void* stream) {
   if (!c->sampler_set) ARL_FAIL(c, "sampler not configured");
   return rollout_end(c, (cudaStream_t)stream);
+}
+
+int arl_rollout_serve(arl_ctx* c, int s, int e0, int n, void* stream) {
+  if (!c->sampler_set) ARL_FAIL(c, "sampler not configured");
+  const arl_sampler_cfg& sc = c->sc;
+  if (s < 0 || s >= sc.horizon) ARL_FAIL(c, "serve step out of range");
+  if (n < 0) n = sc.n_envs - e0;
+  if (e0 < 0 || n < 1 || e0 + n > sc.n_envs) ARL_FAIL(c, "serve env range out of bounds");
+  return policy_forward16(c, c->step_obs16 + (long)e0 * c->obs16_elems, n, c->rows_tab + (long)s * sc.n_envs + e0, sc.prob,
+                          sc.value, sc.uniforms + (long)s * sc.n_envs + e0, sc.actions, c->pc_mode >= 2,
+                          (cudaStream_t)stream, nullptr);
+}
+
+int arl_rollout_ingest(arl_ctx* c, int s, int e0, int n, const uint8_t* staging, const arl_ext_step* ext, void* stream) {
+  if (!c->sampler_set) ARL_FAIL(c, "sampler not configured");
+  if (!c->sc.ext_emulator) ARL_FAIL(c, "sampler was not configured for external emulators");
+  if (!staging || !ext) ARL_FAIL(c, "ingest needs the staged frame pairs and the step records");
+  static_assert(sizeof(ExtStep) == sizeof(arl_ext_step) && sizeof(ExtStep) == 12, "ext step record layout");
+  cudaStream_t st = (cudaStream_t)stream;
+  const arl_sampler_cfg& sc = c->sc;
+  const long T = sc.horizon;
+  if (s < -1 || s > T) ARL_FAIL(c, "ingest step out of range");
+  if (n < 0) n = sc.n_envs - e0;
+  if (e0 < 0 || n < 1 || e0 + n > sc.n_envs) ARL_FAIL(c, "ingest env range out of bounds");
+  ext_apply_kernel<<<(n + 127) / 128, 128, 0, st>>>(reinterpret_cast<const ExtStep*>(ext) + e0, c->cmd + e0, sc.rewards + e0 * T,
+                                                   sc.dones + e0 * T, sc.raw_reward + e0 * T, sc.need_reset + e0 * T, n, (int)T, s,
+                                                   sc.clip_reward, sc.episodic_lives);
+  c->launches++;
+  ARL_CHECK(c, cudaGetLastError());
+  // s in [0, T): the step's new observation goes to the step buffer and to rollout row s + 1;
+  // s == -1 (start_envs) and s == T (reset_needed_envs after the batch): step buffer only
+  const bool in_batch = s >= 0 && s < T;
+  return launch_frame(c, staging, in_batch ? s + 1 : 0, in_batch && s + 1 < T, st, e0, n);
+}
+
+int arl_host_register(void* ptr, size_t bytes) {
+  return cudaHostRegister(ptr, bytes, cudaHostRegisterPortable) == cudaSuccess ? 0 : 1;
+}
+int arl_host_unregister(void* ptr) { return cudaHostUnregister(ptr) == cudaSuccess ? 0 : 1; }
+int arl_copy_async(arl_ctx* c, void* dst, const void* src, size_t bytes, int to_device, void* stream) {
+  ARL_CHECK(c, cudaMemcpyAsync(dst, src, bytes, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return 0;
 }
 
 int arl_rollout_run(arl_ctx* c, void* stream) {

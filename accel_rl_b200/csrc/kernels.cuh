@@ -177,6 +177,44 @@ ARL_DEVINL void env_step_one(const EnvStepArgs& a, int e) {
   cmd[e] = c;
 }
 
+// External-emulator feed: the emulators, AtariEnv's emulator control and the collector logic run in
+// host worker processes (sampler/host_emulator.py, the reference's worker.py:116-153 + envs/atari_env.py:65-100); each
+// step they hand over, per env, one record + the raw frame pair.  This kernel files the record into the rollout rows
+// and turns its flags into the frame kernel's command (frames come from the staging pair, so src_* only say
+// "present" (0) or "zeros" (-1)).
+struct ExtStep {          // mirrors arl_ext_step (include/accelrl_b200.h)
+  float reward;           // clipped when clip_reward
+  float raw_reward;
+  uint8_t done;
+  uint8_t need_reset;     // env_info["need_reset"]
+  uint8_t flags;          // bit0: zero the older planes and use zeros for frame 1 (reset / life loss);
+                          // bit1: observation not advanced; bit2: env not stepped (nothing recorded)
+  uint8_t pad;
+};
+
+__global__ void ext_apply_kernel(const ExtStep* __restrict__ ext, FrameCmd* __restrict__ cmd, float* __restrict__ rewards,
+                                 uint8_t* __restrict__ dones, float* __restrict__ raw_reward,
+                                 uint8_t* __restrict__ info_need_reset, int n_envs, int T, int s, int clip_reward,
+                                 int episodic_lives) {
+  pdl_wait();
+  pdl_trigger();
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_envs) return;
+  const ExtStep x = ext[e];
+  FrameCmd c;
+  c.flags = x.flags & 3;
+  c.src_a = (x.flags & 3) ? -1 : 0;
+  c.src_b = (x.flags & 2) ? -1 : 0;
+  cmd[e] = c;
+  if (s >= 0 && s < T && !(x.flags & 4)) {
+    const long row = (long)e * T + s;
+    rewards[row] = x.reward;
+    dones[row] = x.done;
+    if (clip_reward) raw_reward[row] = x.raw_reward;
+    if (episodic_lives) info_need_reset[row] = x.need_reset;
+  }
+}
+
 // After the batch when mid_batch_reset == False: reset envs flagged need_reset
 // (worker.py:106-113 reset_needed_envs) — produces the first observation of the next batch.
 __global__ void env_reset_needed_kernel(SynthCfg cfg, EnvState st, FrameCmd* __restrict__ cmd, int n_envs) {

@@ -143,6 +143,18 @@ class Engine(object):
     def rollout_end(self):
         self.check(self.lib.arl_rollout_end(self.ctx, self._s()))
 
+    # external-emulator feed: forward + sample, then file what the host workers produced and run the frame pipeline
+    def rollout_serve(self, s, e0=0, n=-1):
+        self.check(self.lib.arl_rollout_serve(self.ctx, int(s), int(e0), int(n), self._s()))
+
+    def rollout_ingest(self, s, staging, ext, e0=0, n=-1):
+        self.check(self.lib.arl_rollout_ingest(self.ctx, int(s), int(e0), int(n), L.ptr(staging), L.ptr(ext), self._s()))
+
+    def copy_async(self, dst_ptr, src_ptr, nbytes, to_device, stream=None):
+        st = self._s() if stream is None else C.c_void_p(stream.cuda_stream)
+        self.check(self.lib.arl_copy_async(self.ctx, C.c_void_p(dst_ptr), C.c_void_p(src_ptr), int(nbytes),
+                                           1 if to_device else 0, st))
+
     def traj_read(self, cap):
         n = C.c_int()
         env = np.zeros(cap, np.int32); ln = np.zeros(cap, np.int32); nz = np.zeros(cap, np.int32)

@@ -1,0 +1,90 @@
+"""Emulator worker process of the host-fed sampler.
+
+The reference's simulator worker (sampler/act_server/alternating/overlap/worker.py:23-153) with the observation
+handling removed: per step it waits for its envs' actions, steps the emulators (HostAtariEnv), and writes — into memory
+shared with the master and page-locked for DMA — the two raw screens and one 12-byte record per env
+(reward, raw_reward, done, need_reset, flags); the GPU does everything that touches pixels.  ResetCollector /
+NonResetCollector semantics (worker.py:25-113): an env is reset when the game is over or the trajectory is longer than
+max_path_length; with mid_batch_reset == False a finished env is not stepped again in the batch (FLAG_SKIP) and is
+reset on CMD_RESET_NEEDED after it.  Completed TrajInfos (sampler/util.py:75-101) go to a queue.
+numpy + stdlib only.
+"""
+import numpy as np
+
+from accel_rl_b200.hostsim.atari_env import HostAtariEnv, FLAG_RESET, FLAG_SKIP, FLAG_NO_RECORD
+
+CMD_STEP, CMD_RESET_NEEDED, CMD_QUIT = 0, 1, 2
+
+EXT_DTYPE = np.dtype([("reward", np.float32), ("raw_reward", np.float32), ("done", np.uint8), ("need_reset", np.uint8),
+                      ("flags", np.uint8), ("pad", np.uint8)])      # arl_ext_step
+
+
+def _new_traj():
+    return dict(Length=0, Return=0., RawReturn=0., NonzeroRewards=0, DiscountedReturn=0., _cur=1.)
+
+
+def views(shared, n_envs, frame_shape):
+    """numpy views of the shared blocks: frames [B][2][frame], ext [B] records, act [B]"""
+    frames = np.frombuffer(shared["frames"], dtype=np.uint8).reshape((n_envs, 2) + tuple(frame_shape))
+    ext = np.frombuffer(shared["ext"], dtype=EXT_DTYPE)
+    act = np.frombuffer(shared["act"], dtype=np.uint8)
+    return frames, ext, act
+
+
+def worker_main(rank, env_lo, env_hi, n_envs, emu_factory, env_kwargs, frame_shape, shared, cmd, act_ready, step_done,
+                infos_queue, seed, mid_batch_reset, max_path_length, discount):
+    np.random.seed(seed)                                   # initialize_worker: seed + rank (sampler/util.py:60-72)
+    frames, ext, act = views(shared, n_envs, frame_shape)
+    envs = [HostAtariEnv(emu_factory(e), **env_kwargs) for e in range(env_lo, env_hi)]
+    trajs = [_new_traj() for _ in envs]
+    need = [False] * len(envs)
+    # start_envs (max_decorrelation_steps == 0): reset every env
+    for i, env in enumerate(envs):
+        e = env_lo + i
+        fl = env.reset(frames[e, 1])
+        ext[e] = (0., 0., 0, 0, fl, 0)
+    step_done.release()
+    while True:
+        act_ready.acquire()
+        c = cmd.value
+        if c == CMD_QUIT:
+            break
+        if c == CMD_RESET_NEEDED:                          # worker.py:106-113
+            for i, env in enumerate(envs):
+                e = env_lo + i
+                if need[i]:
+                    fl = env.reset(frames[e, 1])
+                    ext[e] = (0., 0., 0, 0, fl, 0)
+                    need[i] = False
+                else:
+                    ext[e] = (0., 0., 0, 0, FLAG_SKIP | FLAG_NO_RECORD, 0)
+            step_done.release()
+            continue
+        for i, env in enumerate(envs):                     # one step of collect()
+            e = env_lo + i
+            if need[i]:
+                ext[e] = (0., 0., 0, 0, FLAG_SKIP | FLAG_NO_RECORD, 0)
+                continue
+            r, raw, d, info_need_reset, fl = env.step(int(act[e]), frames[e, 0], frames[e, 1])
+            t = trajs[i]
+            t["Length"] += 1
+            t["Return"] += float(r)
+            t["RawReturn"] += float(raw)
+            t["NonzeroRewards"] += int(r != 0)
+            t["DiscountedReturn"] += t["_cur"] * float(r)
+            t["_cur"] *= discount
+            over_length = t["Length"] > max_path_length
+            nr = info_need_reset
+            if over_length or (d and (True if nr is None else nr)):
+                d = True
+                if over_length and nr is not None:
+                    nr = True
+                infos_queue.put((e, t["Length"], t["Return"], t["RawReturn"], t["NonzeroRewards"], t["DiscountedReturn"]))
+                trajs[i] = _new_traj()
+                if mid_batch_reset:
+                    fl = env.reset(frames[e, 1])
+                else:
+                    need[i] = True
+                    fl = FLAG_SKIP                          # this step's reward/done ARE recorded, the obs is not advanced
+            ext[e] = (r, raw, int(bool(d)), int(bool(nr)), fl, 0)
+        step_done.release()

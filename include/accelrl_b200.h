@@ -68,6 +68,7 @@ typedef struct {
   /* synthetic emulator rules (oracle/synth_ale.py implements the same) */
   int lives0, life_base, life_mul, life_mod, reward_mod, frame_stride;
   int traj_cap;                 /* capacity of the completed-trajectory record buffer */
+  int ext_emulator;             /* != 0: emulators run in host worker processes; steps arrive through arl_rollout_ingest */
   int frame_mode;               /* 0: reference frames (210,160) gray -> (planes,104,80), atari_env.py:151-157;
                                  * 1: north-star frames (210,160,3) RGB -> gray -> (planes,84,84) (see arl_frame_update_rgb);
                                  *    frame_pool / staging then hold RGB frames */
@@ -123,6 +124,34 @@ int arl_rollout_begin(arl_ctx* ctx, void* stream);
  * host-fed raw frames [B][2][210][160] already on the device for this step */
 int arl_rollout_step(arl_ctx* ctx, int s, const uint8_t* staging, void* stream);
 int arl_rollout_end(arl_ctx* ctx, void* stream);
+/* External-emulator feed (reference: the simulator workers of overlap/worker.py:116-153 running envs/atari_env.py:65-100
+ * on host cores).  Per env-step the workers hand over one record and the raw frame pair; the device keeps the pixels
+ * (frame pipeline), the policy and the rollout buffers.
+ *   arl_rollout_serve(s):   policy forward on the step buffer + action sampling -> rows e*T+s of actions/prob/value
+ *   arl_rollout_ingest(s, staging [B][2][210][160(x3)] u8 DEVICE, ext [B] DEVICE): files reward/done/infos into rows
+ *                            e*T+s and runs the frame pipeline into the step buffer and row s+1.  s == -1: the frames of
+ *                            start_envs (sampler/util.py:26-57); s == horizon: those of reset_needed_envs
+ *                            (worker.py:106-113) — step buffer only. */
+typedef struct {
+  float reward;                 /* clipped when clip_reward */
+  float raw_reward;
+  uint8_t done;
+  uint8_t need_reset;           /* env_info["need_reset"] */
+  uint8_t flags;                /* bit0: reset / life loss: older planes zeroed, frame 1 = zeros (atari_env.py:159-163);
+                                 * bit1: observation not advanced (NonResetCollector: the env finished, worker.py:84-95);
+                                 * bit2: env not stepped at all, nothing is recorded (worker.py:78) */
+  uint8_t pad;
+} arl_ext_step;
+/* both act on envs [e0, e0 + n) (n < 0: through the last env): the two alternating groups of the reference sampler are
+ * served one after the other, so one group's emulators run while the other group is on the GPU.  staging / ext are the
+ * bases of the whole-batch blocks. */
+int arl_rollout_serve(arl_ctx* ctx, int s, int e0, int n, void* stream);
+int arl_rollout_ingest(arl_ctx* ctx, int s, int e0, int n, const uint8_t* staging, const arl_ext_step* ext, void* stream);
+/* page-lock / unlock host memory the workers share with the master (POSIX shared memory), and plain async copies on a
+ * stream, so raw frames go pinned-host -> HBM without a bounce buffer */
+int arl_host_register(void* ptr, size_t bytes);
+int arl_host_unregister(void* ptr);
+int arl_copy_async(arl_ctx* ctx, void* dst, const void* src, size_t bytes, int to_device, void* stream);
 /* begin + horizon steps + end, replayed from a CUDA graph (resident frame pool) */
 int arl_rollout_run(arl_ctx* ctx, void* stream);
 /* completed TrajInfo records (sampler/util.py:75-101); host arrays of capacity cap; returns count via *n */

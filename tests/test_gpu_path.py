@@ -176,6 +176,59 @@ def test_device_sampler_rgb_mode_vs_oracle(mbr):
         pol.engine.close()
 
 
+@pytest.mark.parametrize("mbr,frame_mode", [(True, "gray"), (False, "gray"), (True, "rgb")])
+def test_host_emulator_sampler_vs_oracle(mbr, frame_mode):
+    """Emulators in host worker processes (two alternating groups, raw screens through pinned shared memory, pixels on
+    the GPU): with the oracle's synthetic ALE inside the workers the rollout buffers and the TrajInfos equal the oracle
+    sampler's (= the device-resident sampler's), incl. life losses, game overs, and envs that stop stepping."""
+    from functools import partial
+    from accel_rl_b200.envs import AtariEnv
+    from accel_rl_b200.sampler import HostEmulatorSampler
+    from accel_rl_b200.util.seeding import set_seed
+    from tests import fake_ale
+    rgb = frame_mode == "rgb"
+    rules = dict(synth_ale.DEFAULT_RULES, pool_frames=64, life_base=9, life_mod=5, reward_mod=7)
+    set_seed(1)
+    B, T = 16, 10
+    sampler = HostEmulatorSampler(emu_factory=partial(fake_ale.make, rules=rules, pool_seed=0, channels=3 if rgb else 1),
+                                  EnvCls=AtariEnv, env_args=dict(game="breakout", max_start_noops=0, frame_mode=frame_mode),
+                                  horizon=T, n_parallel=2, envs_per=4, max_path_length=27000, mid_batch_reset=mbr,
+                                  max_decorrelation_steps=0)
+    sampler.initialize(seed=2, affinities=dict(), discount=0.99, need_extra_obs=True)
+    pol, flat, spec = make_policy(1, max_rows=B, hw=(84, 84) if rgb else (104, 80))
+    pool = synth_ale.make_pool(64, seed=0, channels=3 if rgb else 1)
+    orc = osampler.OracleSampler(B, T, pool, rules, 4, 0.99, mid_batch_reset=mbr)
+
+    def key(ti):
+        return (ti["env"], ti["Length"], round(float(ti["Return"]), 4), round(float(ti["RawReturn"]), 4),
+                ti["NonzeroRewards"], round(float(ti["DiscountedReturn"]), 3))
+    try:
+        sampler.policy_init(pol)
+        n_traj = 0
+        for itr in range(4):
+            buf, infos = sampler.obtain_samples(itr)
+            b = _buf_np(buf)
+            u = sampler._uniforms_host.numpy().copy()
+            gp = b["prob"].reshape(B, T, 4); gv = b["value"].reshape(B, T)
+            calls = {"k": 0}
+
+            def policy_fn(obs):
+                k = calls["k"]; calls["k"] += 1
+                s, j = divmod(k, 2)
+                lo, hi = j * B // 2, (j + 1) * B // 2
+                return gp[lo:hi, s], gv[lo:hi, s]
+            ob, oinf = orc.obtain_samples(policy_fn, u)
+            for k in ("observations", "extra_observations", "rewards", "dones", "raw_reward", "need_reset", "actions"):
+                assert np.array_equal(b[k], ob[k]), (k, itr)
+            assert sorted(key(t) for t in infos) == sorted(key(t) for t in oinf)
+            n_traj += len(infos)
+        assert n_traj > 0 and sampler.h2d_bytes > 4 * T * B * 2 * 33600
+        assert pol.engine.device_error() == 0
+    finally:
+        sampler.shutdown()
+        pol.engine.close()
+
+
 def test_eval_sampler_vs_oracle_and_training_envs_untouched():
     """AAOEvalSampler.evaluate_policy (sampler_with_eval.py:20-33, worker_with_eval.py:66-99): the evaluation envs are
     reset at the start of every evaluation, run eval_horizon steps, and return exactly the trajectories the oracle

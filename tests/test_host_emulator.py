@@ -1,0 +1,145 @@
+"""Host half of the emulator-fed sampler (accel_rl_b200/hostsim): no GPU needed.
+
+HostAtariEnv + the worker's collector logic must export, per env-step, exactly the raw frame pair, flags and scalars
+from which the oracle's AtariEnv restatement (oracle/sampler.py:SynthAtariEnv, pinned to the reference's real AtariEnv
+by tests/golden) builds its observations and step results."""
+import ctypes as C
+import multiprocessing as mp
+from functools import partial
+
+import numpy as np
+import pytest
+
+from accel_rl_b200.hostsim import worker as W
+from accel_rl_b200.hostsim.atari_env import HostAtariEnv, FLAG_RESET, FLAG_SKIP, FLAG_NO_RECORD
+from oracle import frame as oframe, sampler as osampler, synth_ale
+from tests import fake_ale
+
+RULES = dict(synth_ale.DEFAULT_RULES, pool_frames=32, life_base=9, life_mod=5, reward_mod=7)
+
+
+def _apply(obs, f1, f2, flags):
+    """what the device does with one exported step (frame_kernel): -> new stack"""
+    if flags & FLAG_RESET:
+        obs = np.zeros_like(obs)
+        f1 = np.zeros_like(f2)
+    return oframe.update_obs(obs, f1, f2)
+
+
+@pytest.mark.parametrize("episodic", [True, False])
+def test_host_atari_env_exports_what_the_oracle_env_consumes(episodic):
+    pool = synth_ale.make_pool(32, seed=0)
+    for e in (0, 3):
+        host = HostAtariEnv(fake_ale.make(e, RULES), clip_reward=True, episodic_lives=episodic, max_start_noops=0)
+        orc = osampler.SynthAtariEnv(e, pool, RULES, 4, 4, True, episodic)
+        f1, f2 = np.zeros((210, 160), np.uint8), np.zeros((210, 160), np.uint8)
+        obs = np.zeros((4, oframe.H, oframe.W), np.uint8)
+        fl = host.reset(f2)
+        assert fl == FLAG_RESET
+        obs = _apply(obs, f1, f2, fl)
+        assert np.array_equal(obs, orc.reset())
+        rng = np.random.RandomState(e)
+        saw_life = saw_over = False
+        for _ in range(120):
+            a = int(rng.randint(0, 4))
+            r, raw, d, nr, fl = host.step(a, f1, f2)
+            o2, r2, d2, info = orc.step(a)
+            obs = _apply(obs, f1, f2, fl)
+            assert np.array_equal(obs, o2)
+            assert r == r2 and raw == info["raw_reward"] and bool(d) == bool(d2)
+            assert (nr if episodic else None) == info.get("need_reset")
+            saw_life |= bool(fl & FLAG_RESET)
+            game_over = info.get("need_reset", d2)
+            if game_over:
+                saw_over = True
+                fl = host.reset(f2)
+                obs = _apply(obs, f1, f2, fl)
+                assert np.array_equal(obs, orc.reset())
+        assert saw_over and (saw_life or not episodic)
+
+
+@pytest.mark.parametrize("mbr", [True, False])
+def test_worker_processes_follow_the_collector_protocol(mbr):
+    """two spawned workers (one per group) driven through the semaphore protocol for two batches: records and frames
+    equal those of in-process HostAtariEnvs run through the reference collector rules (worker.py:25-113)"""
+    ctx = mp.get_context("spawn")
+    B, per, T = 4, 2, 14
+    shape = (210, 160)
+    fb = 210 * 160
+    shared = dict(frames=ctx.RawArray(C.c_uint8, B * 2 * fb), ext=ctx.RawArray(C.c_uint8, B * W.EXT_DTYPE.itemsize),
+                  act=ctx.RawArray(C.c_uint8, B))
+    frames, ext, act = W.views(shared, B, shape)
+    cmd = ctx.Value("i", W.CMD_STEP, lock=False)
+    ready = [ctx.Semaphore(0) for _ in range(2)]
+    done = [ctx.Semaphore(0) for _ in range(2)]
+    q = ctx.Queue()
+    env_kwargs = dict(frame_skip=4, clip_reward=True, episodic_lives=True, max_start_noops=0, rgb=False)
+    factory = partial(fake_ale.make, rules=RULES)
+    procs = [ctx.Process(target=W.worker_main, daemon=True,
+                         args=(w, w * per, (w + 1) * per, B, factory, env_kwargs, shape, shared, cmd, ready[w], done[w], q,
+                               5 + w, mbr, 27000, 0.99)) for w in range(2)]
+    for p in procs:
+        p.start()
+    try:
+        ref = [HostAtariEnv(fake_ale.make(e, RULES), **env_kwargs) for e in range(B)]
+        g1, g2 = np.zeros(shape, np.uint8), np.zeros(shape, np.uint8)
+        for w in range(2):
+            assert done[w].acquire(timeout=120)
+        for e in range(B):
+            assert ref[e].reset(g2) == ext[e]["flags"] == FLAG_RESET and np.array_equal(frames[e, 1], g2)
+        rng = np.random.RandomState(0)
+        lengths = [0] * B
+        finished = []
+        for batch in range(2):
+            need = [False] * B
+            for s in range(T):
+                act[:] = rng.randint(0, 4, B).astype(np.uint8)
+                cmd.value = W.CMD_STEP
+                for w in range(2):
+                    ready[w].release()
+                for w in range(2):
+                    assert done[w].acquire(timeout=120)
+                for e in range(B):
+                    x = ext[e]
+                    if need[e]:
+                        assert x["flags"] == FLAG_SKIP | FLAG_NO_RECORD
+                        continue
+                    r, raw, d, nr, fl = ref[e].step(int(act[e]), g1, g2)
+                    lengths[e] += 1
+                    if d and nr:
+                        finished.append((e, lengths[e]))
+                        lengths[e] = 0
+                        if mbr:
+                            fl = ref[e].reset(g2)
+                        else:
+                            need[e] = True
+                            fl = FLAG_SKIP
+                    rec = (x["reward"], x["raw_reward"], bool(x["done"]), bool(x["need_reset"]), x["flags"])
+                    assert rec == (r, raw, bool(d), bool(nr), fl), (batch, s, e)
+                    if not (fl & FLAG_SKIP):
+                        assert np.array_equal(frames[e, 1], g2)
+                        if not (fl & FLAG_RESET):
+                            assert np.array_equal(frames[e, 0], g1)
+            if not mbr:
+                cmd.value = W.CMD_RESET_NEEDED
+                for w in range(2):
+                    ready[w].release()
+                for w in range(2):
+                    assert done[w].acquire(timeout=120)
+                for e in range(B):
+                    if need[e]:
+                        assert ref[e].reset(g2) == ext[e]["flags"] == FLAG_RESET and np.array_equal(frames[e, 1], g2)
+                    else:
+                        assert ext[e]["flags"] == FLAG_SKIP | FLAG_NO_RECORD
+        got = []
+        while len(got) < len(finished):
+            got.append(q.get(timeout=30))
+        assert sorted((g[0], g[1]) for g in got) == sorted(finished) and len(finished) > 0
+    finally:
+        cmd.value = W.CMD_QUIT
+        for w in range(2):
+            ready[w].release()
+        for p in procs:
+            p.join(timeout=20)
+            if p.is_alive():
+                p.terminate()
