@@ -67,8 +67,10 @@ def parse():
     ap.add_argument("--frames", default="gray", choices=["gray", "rgb"],
                     help="gray: the reference's pipeline, 210x160 grayscale screens -> (4,104,80), cnn preset 1 (default, parity "
                          "pinned); rgb: north-star mode, 210x160x3 RGB screens -> gray -> (4,84,84), classic Nature-CNN")
-    ap.add_argument("--workload", default="ppo", choices=["ppo", "frame_sweep"],
-                    help="ppo: the headline metric (default); frame_sweep: BASELINE configs[2] frame-kernel HBM GB/s sweep")
+    ap.add_argument("--workload", default="ppo", choices=["ppo", "frame_sweep", "host_emulators"],
+                    help="ppo: the headline metric (default); frame_sweep: BASELINE configs[2] frame-kernel HBM GB/s sweep; "
+                         "host_emulators: the same PPO iteration with the emulators stepped by worker processes on the "
+                         "host cores (HostEmulatorSampler: raw screens over PCIe, two alternating groups)")
     return ap.parse_args()
 
 
@@ -131,11 +133,21 @@ def build_runner(args, frame_feed, rank, world):
     logger.configure(None, quiet=True)
     rules = dict(pool_frames=args.pool_frames)
     rgb = getattr(args, "frames", "gray") == "rgb"
-    sampler = ActsrvAltOvrlpSampler(
-        EnvCls=AtariEnv, env_args=dict(game="breakout", max_start_noops=0, synth_rules=rules,
-                                       frame_mode="rgb" if rgb else "gray"),
-        horizon=args.horizon, n_parallel=args.envs // 8, envs_per=4, max_path_length=27000, mid_batch_reset=True,
-        max_decorrelation_steps=0, frame_feed=frame_feed)
+    env_args = dict(game="breakout", max_start_noops=0, synth_rules=rules, frame_mode="rgb" if rgb else "gray")
+    if frame_feed == "workers":
+        from functools import partial
+        from accel_rl_b200.hostsim import synth_emulator
+        from accel_rl_b200.sampler import HostEmulatorSampler
+        n_par = host_workers(args) // 2
+        sampler = HostEmulatorSampler(
+            emu_factory=partial(synth_emulator.make, rules=rules, channels=3 if rgb else 1), EnvCls=AtariEnv, env_args=env_args,
+            horizon=args.horizon, n_parallel=n_par, envs_per=args.envs // (2 * n_par), max_path_length=27000,
+            mid_batch_reset=True, max_decorrelation_steps=0)
+    else:
+        sampler = ActsrvAltOvrlpSampler(
+            EnvCls=AtariEnv, env_args=env_args,
+            horizon=args.horizon, n_parallel=args.envs // 8, envs_per=4, max_path_length=27000, mid_batch_reset=True,
+            max_decorrelation_steps=0, frame_feed=frame_feed)
     from accel_rl_b200.algos import A2C, mA2C, mA3C, mAPPO
     from accel_rl_b200.runners import AccelRLAsync
     a2c = getattr(args, "algo", "ppo") == "a2c"
@@ -153,6 +165,49 @@ def build_runner(args, frame_feed, rank, world):
                          n_steps=n_steps, seed=0, affinities=dict(), log_interval_steps=10 ** 12)
     runner.startup()
     return runner
+
+
+def host_workers(args):
+    """worker processes of the host-emulator workload: the largest power of two <= host cores that divides the envs"""
+    cores = os.cpu_count() or 2
+    w = 2
+    while w * 2 <= cores and args.envs % (w * 2) == 0:
+        w *= 2
+    return w
+
+
+def run_host_emulators(args):
+    """PPO iterations with the emulators in host worker processes (one JSON line)"""
+    import torch
+    torch.cuda.set_device(0)
+    args.pool_frames = min(args.pool_frames, 256)      # every worker process builds its own copy of the frame pool
+    runner = build_runner(args, "workers", 0, 1)
+    smp = runner.sampler
+    try:
+        N = args.envs * args.horizon
+        h0, d0 = smp.h2d_bytes, smp.d2h_bytes
+        steps, warm = max(2, args.steps // 2), max(1, args.warmup // 2)
+        clocks = ClockSampler(0)
+        clocks.start()
+        ms, launches, wall, _, itr = timed_iterations(runner, steps, warm, 1)
+        clk = clocks.summary()
+        phases = phase_split(runner, itr, reps=2)
+        n_it = steps + warm + 2
+        out = {"metric": "env-steps/sec (PPO Atari, %d envs/GPU)" % args.envs, "value": round(N / (ms * 1e-3), 1),
+               "unit": "env-steps/s", "n_gpus": 1, "steps": steps, "warmup": warm, "ms_per_step": round(ms, 3),
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+               "config": {"workload": "PPO Breakout-shaped, %d envs x %d-step rollout, %d epochs x mb %d; emulators (host mirror "
+                                      "of the synthetic emulator, Python) stepped by %d worker processes in two alternating "
+                                      "groups on %d host cores, raw %s screens H2D from pinned shared memory every step"
+                                      % (args.envs, args.horizon, args.epochs, args.minibatch, host_workers(args),
+                                         os.cpu_count() or 1, "210x160x3" if args.frames == "rgb" else "210x160"),
+                          "frames": args.frames, "workers": host_workers(args)},
+               "clocks": clk, "gpu_launches": int(launches), "phases": phases,
+               "h2d_bytes_per_step": int((smp.h2d_bytes - h0) / n_it), "d2h_bytes_per_step": int((smp.d2h_bytes - d0) / n_it)}
+    finally:
+        smp.shutdown()
+        runner.policy.engine.close()
+    _emit(out)
 
 
 def timed_iterations(runner, steps, warmup, world, itr0=0):
@@ -494,6 +549,8 @@ if __name__ == "__main__":
     a = parse()
     if a.workload == "frame_sweep":
         run_frame_sweep(a)
+    elif a.workload == "host_emulators":
+        run_host_emulators(a)
     elif a.impl == "reference":
         run_reference(a)
     else:

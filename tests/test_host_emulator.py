@@ -143,3 +143,21 @@ def test_worker_processes_follow_the_collector_protocol(mbr):
             p.join(timeout=20)
             if p.is_alive():
                 p.terminate()
+
+
+def test_product_synthetic_emulator_follows_the_oracle_rules():
+    """accel_rl_b200/hostsim/synth_emulator.py (host mirror of the device's synthetic emulator, used by
+    bench.py --workload host_emulators) == oracle/synth_ale.py rule for rule"""
+    from accel_rl_b200.hostsim import synth_emulator as se
+    pool = synth_ale.make_pool(32, seed=0)
+    for e in (0, 5, 77):
+        em = se.SynthEmulator(e, RULES)
+        buf = np.zeros((210, 160), np.uint8)
+        for f in range(1, 150):
+            assert em.act(0) == synth_ale.synth_reward(RULES, e, f)
+            assert em.lives() == synth_ale.synth_lives(RULES, e, f)
+            assert em.game_over() == (synth_ale.synth_lives(RULES, e, f) == 0)
+            em.getScreenGrayscale(buf)
+            assert np.array_equal(buf, pool[synth_ale.frame_index(RULES, e, f)])
+        em.reset_game()
+        assert em.f == 0
