@@ -127,6 +127,74 @@ def test_device_sampler_vs_oracle_larger_batch():
 
 
 
+def test_full_size_c2_rollout_bit_exact_and_update_properties():
+    """BASELINE.json configs[1] at FULL size: 256 envs x 128 steps, preset 1, PPO 4 epochs x 64 minibatches of 512.
+    (1) every integer/byte buffer of the 1.09 GB rollout equals the oracle sampler's, bit for bit (sampled actions
+    included, given the device's probabilities and the master's uniforms); (2) size-independent properties of the
+    learner: the minibatch gradient is linear in its rows (g(512 rows) == mean of the two 256-row halves' gradients,
+    both scaled by exact powers of two), 256 updates are taken, every loss / gradient norm is finite, the Adam count
+    matches, and an iteration with lr_mult = 0 leaves the parameters untouched (idempotence)."""
+    from accel_rl_b200.algos import PPO
+    from accel_rl_b200.util.seeding import set_seed
+    rules = dict(synth_ale.DEFAULT_RULES, pool_frames=512, life_base=60, life_mod=31, reward_mod=41, pool_seed=0)
+    orules = {k: v for k, v in rules.items() if k != "pool_seed"}
+    set_seed(11)
+    B, T = 256, 128
+    sampler = _make_sampler(32, 4, T, rules=rules)
+    env_spec, sample_size, horizon, mbr = sampler.initialize(seed=12, affinities=dict(), discount=0.99, need_extra_obs=True)
+    assert sample_size == B * T
+    pol, flat, spec = make_policy(1)
+    algo = PPO(optimizer_args=dict(minibatch_size=512, epochs=4))
+    algo.initialize(pol, env_spec, sample_size, horizon, mbr)
+    sampler.policy_init(pol)
+    algo.set_n_itr(10)
+    eng = pol.engine
+    orc = osampler.OracleSampler(B, T, synth_ale.make_pool(512, seed=0), orules, 4, 0.99)
+    try:
+        buf, infos = sampler.obtain_samples(0)
+        b = _buf_np(buf)
+        u = sampler._uniforms_host.numpy().copy()
+        gp = b["prob"].reshape(B, T, 4); gv = b["value"].reshape(B, T)
+        calls = {"k": 0}
+
+        def policy_fn(obs):
+            k = calls["k"]; calls["k"] += 1
+            s, j = divmod(k, 2)
+            lo, hi = j * B // 2, (j + 1) * B // 2
+            return gp[lo:hi, s], gv[lo:hi, s]
+        ob, oinf = orc.obtain_samples(policy_fn, u)
+        for k in ("observations", "extra_observations", "rewards", "dones", "raw_reward", "need_reset", "actions"):
+            assert np.array_equal(b[k], ob[k]), k
+        assert len(infos) == len(oinf) and b["dones"].any()
+        np.testing.assert_allclose(b["prob"].sum(1), 1.0, atol=1e-5)
+        # ---- gradient linearity at the full minibatch size ----
+        opt_data, info = algo.optimize_policy(0, buf)            # binds the training inputs; a real iteration
+        losses_n = len(info["GradNorm"])
+        assert losses_n == 4 * (B * T // 512) == 256 and np.isfinite(info["GradNorm"]).all()
+        assert eng.get_opt_state()["step"] == 256
+        rows = torch.randperm(B * T, device="cuda")[:512].to(torch.int32).contiguous()
+        eng.grad_minibatch(rows, 512)
+        torch.cuda.synchronize()
+        g_full = t2n(eng.grad).copy()
+        halves = []
+        for h in range(2):
+            eng.grad_minibatch(rows[h * 256:(h + 1) * 256].contiguous(), 256)
+            torch.cuda.synchronize()
+            halves.append(t2n(eng.grad).copy())
+        g_mean = 0.5 * (halves[0] + halves[1])
+        assert relerr(g_full, g_mean) < 2e-4
+        # ---- idempotence: a zero step size changes nothing ----
+        before = pol.get_param_values()
+        algo._lr_mult = 0.0
+        eng.set_lr_mult(0.0)
+        eng.train_minibatches(algo.optimizer._idx_dev, 512, 4)
+        torch.cuda.synchronize()
+        assert np.array_equal(pol.get_param_values(), before)
+        assert eng.device_error() == 0
+    finally:
+        eng.close()
+
+
 @pytest.mark.parametrize("mbr", [True, False])
 def test_device_sampler_rgb_mode_vs_oracle(mbr):
     """north-star frame mode inside the sampler: RGB 210x160x3 emulator frames -> gray -> 84x84 stacks.  Device rollout
