@@ -773,8 +773,21 @@ int fc_dgrad_tiles(arl_ctx* c, int n, cudaStream_t st) {
 int fc_wgrad_tiles(arl_ctx* c, int n, cudaStream_t st) {
   const int HW = c->HWlast;
   FcParams p{};
-  p.ncopies = 6;
   const long aplane = (long)c->fc_rows * 64;
+  static const bool quad = !(getenv("ARL_FC_WGRAD_QUAD") && atoi(getenv("ARL_FC_WGRAD_QUAD")) == 0);
+  if (quad && HW % 4 == 0) {
+    // four pixel planes per CTA: 256 x 256 tiles in two accumulators, 64 KB stages (4 x 8 KB act planes + 4 x 8 KB dh planes)
+    p.ncopies = 8;
+    for (int i = 0; i < 4; ++i) {
+      p.cp[i] = FcCopy{c->act_fc + (long)i * aplane, 4 * aplane, 0, 0, 64 * 64, 8192, (uint32_t)(i * 8192)};
+      p.cp[4 + i] = FcCopy{c->dh_t + (long)i * aplane, 0, 4 * aplane, 0, 64 * 64, 8192, (uint32_t)(32768 + i * 8192)};
+    }
+    p.a_bytes = 32768; p.stage_bytes = 65536; p.stages = 3;
+    p.niter = (n + 63) / 64; p.niter_total = p.niter; p.M = n;
+    p.out_f32 = c->grad + c->off_Wfc; p.ldo = c->H; p.fc_HW = HW;
+    return launch_fc_gemm<3, 256>(c, p, dim3(HW / 4, c->H / 256, 1), st);
+  }
+  p.ncopies = 6;
   p.cp[0] = FcCopy{c->act_fc, 2 * aplane, 0, 0, 64 * 64, 8192, 0};
   p.cp[1] = FcCopy{c->act_fc + aplane, 2 * aplane, 0, 0, 64 * 64, 8192, 8192};
   for (int i = 0; i < 4; ++i)

@@ -234,6 +234,36 @@ ARL_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
 ARL_DEVINL float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 ARL_DEVINL float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
+// Coalesced fp32 row stores for TMEM epilogues.  After tcgen05.ld (32x32b) every lane holds 32 consecutive columns of
+// ITS OWN row; storing them directly makes each warp instruction touch 32 different 128-byte lines (32 LSU wavefronts,
+// measured: the FC weight-gradient tile spent 8 200 of its 37 500 cycles in these stores).  Here the 32 x 32 block is
+// transposed through a per-warp shared-memory scratch (32 rows x 36 floats: conflict-free for 16-byte accesses) so
+// that one store instruction writes four rows x 128 contiguous bytes.  `dst` = this lane's row pointer (16-byte
+// aligned, 32 floats stored), `valid` = whether the lane's row exists; scratch = 4608 bytes of shared memory per warp.
+constexpr int kRowStoreScratch = 32 * 36 * 4;
+ARL_DEVINL void store_rows32_coalesced(uint32_t scratch, const uint32_t (&v)[32], float* dst, bool valid, int lane) {
+  const uint32_t my = scratch + (uint32_t)lane * 144u;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(my + 16u * j), "r"(v[4 * j]), "r"(v[4 * j + 1]),
+                 "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                 : "memory");
+  __syncwarp();
+  const unsigned long long dp = reinterpret_cast<unsigned long long>(dst);
+  const int sub = lane >> 3, ch = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = 4 * i + sub;
+    const unsigned long long rp = __shfl_sync(0xffffffffu, dp, row);
+    const int ok = __shfl_sync(0xffffffffu, valid ? 1 : 0, row);
+    uint4 x;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w)
+                 : "r"(scratch + (uint32_t)row * 144u + 16u * ch));
+    if (ok) *reinterpret_cast<uint4*>(reinterpret_cast<float*>(rp) + 4 * ch) = x;
+  }
+  __syncwarp();
+}
+
 ARL_DEVINL float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

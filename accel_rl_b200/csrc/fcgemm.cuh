@@ -12,6 +12,9 @@
 //   KIND 0  forward : part[split][n][H]   = act[n][K] * W[K][H]          A K-major, B N-major, split-K over pixels
 //   KIND 1  dgrad   : dY[n][(hw,c)]       = dh[n][H] * W^T, masked by act > 0, scattered into the conv gradient grid
 //   KIND 2  wgrad   : dW[(c,hw)][H] (fp32) = act^T[K][n] * dh[n][H]      both MN-major, two pixel planes per tile
+//   KIND 3  wgrad, FOUR pixel planes per tile: two M = 128 accumulators (all 512 TMEM columns) fed by the same dh stage —
+//           the kernel is bound by L2 -> shared-memory operand traffic (128 x 256 tiles re-read dh_t 54 times), so
+//           a 256 x 256 tile moves 2/3 of the bytes per FLOP and occupies half the SMs
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM), warps 2..9 = epilogue.
 #pragma once
 #include "common.cuh"
@@ -19,7 +22,7 @@
 namespace arl {
 
 constexpr int kFcThreads = 320;
-constexpr int kFcMaxCopies = 6;
+constexpr int kFcMaxCopies = 8;
 
 struct FcCopy {
   const __nv_bfloat16* base;
@@ -49,8 +52,10 @@ struct FcParams {
 
 template <int KIND, int BN>
 __global__ void __launch_bounds__(kFcThreads, 1) fc_gemm_kernel(const __grid_constant__ FcParams p) {
-  constexpr bool A_MN = (KIND == 2), B_MN = (KIND != 1);
-  constexpr int TMEM_COLS = BN <= 128 ? 128 : 256;
+  constexpr bool A_MN = (KIND >= 2), B_MN = (KIND != 1);
+  constexpr int NACC = (KIND == 3) ? 2 : 1;                // accumulators (M = 128 each) sharing one B stage
+  constexpr int TMEM_COLS = NACC * BN <= 128 ? 128 : (NACC * BN <= 256 ? 256 : 512);
+  static_assert(NACC * BN <= 512, "TMEM columns");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + p.stages * p.stage_bytes;
@@ -109,9 +114,13 @@ __global__ void __launch_bounds__(kFcThreads, 1) fc_gemm_kernel(const __grid_con
         const uint32_t b_tile = a_tile + p.a_bytes;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint64_t ad = A_MN ? make_smem_desc(a_tile + k * 2048, 8192, 1024, 2) : make_smem_desc(a_tile + k * 32, 16, 1024, 2);
           const uint64_t bd = B_MN ? make_smem_desc(b_tile + k * 2048, 8192, 1024, 2) : make_smem_desc(b_tile + k * 32, 16, 1024, 2);
-          umma_bf16(tmem_u, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+          for (int a = 0; a < NACC; ++a) {    // accumulator a: pixel planes 2a, 2a+1 of the stage (16 KB apart)
+            const uint64_t ad = A_MN ? make_smem_desc(a_tile + a * 16384 + k * 2048, 8192, 1024, 2)
+                                     : make_smem_desc(a_tile + k * 32, 16, 1024, 2);
+            umma_bf16(tmem_u + a * BN, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
         }
         umma_commit(empty_bar(s));
         if (it == niter - 1) umma_commit(done_bar);
@@ -128,10 +137,14 @@ __global__ void __launch_bounds__(kFcThreads, 1) fc_gemm_kernel(const __grid_con
       tc_fence_after();
     }
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + h * HC;
+    // all MMAs are complete (done_bar): the operand stages are free -> per-warp transpose scratch for the row stores
+    const uint32_t scratch = smem_base + (uint32_t)(warp - 2) * kRowStoreScratch;
 #pragma unroll 1
-    for (int c0 = 0; c0 < HC; c0 += 32) {
+    for (int cc0 = 0; cc0 < NACC * HC; cc0 += 32) {
+      const int acc = cc0 / HC;               // KIND 3: second accumulator = planes 2, 3 of the tile
+      const int c0 = cc0 - acc * HC;
       uint32_t v[32];
-      if (niter > 0) { tmem_ld32(taddr + c0, v); tmem_ld_wait(); }
+      if (niter > 0) { tmem_ld32(taddr + acc * BN + c0, v); tmem_ld_wait(); }
       else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = 0;
@@ -139,13 +152,8 @@ __global__ void __launch_bounds__(kFcThreads, 1) fc_gemm_kernel(const __grid_con
       const int col = h * HC + c0;            // first of 32 tile columns
       if (KIND == 0) {
         const int row = blockIdx.x * 128 + r;
-        if (row < p.M) {
-          float4* dst = reinterpret_cast<float4*>(p.out_f32 + ((long)blockIdx.z * p.M + row) * p.ldo + blockIdx.y * BN + col);
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                                 __uint_as_float(v[4 * i + 3]));
-        }
+        float* dst = p.out_f32 + ((long)blockIdx.z * p.M + row) * p.ldo + blockIdx.y * BN + col;
+        store_rows32_coalesced(scratch, v, dst, row < p.M, lane);
       } else if (KIND == 1) {
         const int row = blockIdx.x * 128 + r;   // image
         if (row < p.M) {
@@ -172,15 +180,10 @@ __global__ void __launch_bounds__(kFcThreads, 1) fc_gemm_kernel(const __grid_con
           }
         }
       } else {
-        // D row r of this tile = (plane blockIdx.x*2 + r/64, channel r%64) -> gradient row c*HW + hw
-        const int hw = blockIdx.x * 2 + (r >> 6), c = r & 63;
-        if (hw < p.fc_HW) {
-          float4* dst = reinterpret_cast<float4*>(p.out_f32 + ((long)c * p.fc_HW + hw) * p.ldo + blockIdx.y * BN + col);
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                                 __uint_as_float(v[4 * i + 3]));
-        }
+        // D row r of accumulator acc = (plane blockIdx.x*2*NACC + 2*acc + r/64, channel r%64) -> gradient row c*HW + hw
+        const int hw = blockIdx.x * 2 * NACC + 2 * acc + (r >> 6), c = r & 63;
+        float* dst = p.out_f32 + ((long)c * p.fc_HW + hw) * p.ldo + blockIdx.y * BN + col;
+        store_rows32_coalesced(scratch, v, dst, hw < p.fc_HW, lane);
       }
     }
     tc_fence_before();

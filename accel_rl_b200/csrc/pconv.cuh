@@ -552,12 +552,8 @@ __global__ void __launch_bounds__(kPcThreads, 1) pconv_wgrad_kernel(const __grid
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0;
         }
-        if (blk < p.nblk) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            reinterpret_cast<float4*>(dst)[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                                            __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
-        }
+        // (all MMAs and column sums are done: the operand stages serve as the per-warp transpose scratch)
+        store_rows32_coalesced(smem_base + (uint32_t)(warp - 2) * kRowStoreScratch, v, dst, blk < p.nblk, lane);
       } else {
         uint32_t v[16];
         if (my_tiles > 0) { tmem_ld16(taddr, v); tmem_ld_wait(); }
