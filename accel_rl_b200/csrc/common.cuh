@@ -264,6 +264,59 @@ ARL_DEVINL void store_rows32_coalesced(uint32_t scratch, const uint32_t (&v)[32]
   __syncwarp();
 }
 
+// the same for 16 words per lane (64-byte row pieces): one store instruction writes eight rows x 64 bytes.
+// perm: the lane's 16-byte chunk j lands at chunk position j ^ perm of its piece (chunk-swizzled destinations).
+ARL_DEVINL void store_rows16_coalesced(uint32_t scratch, const uint32_t (&v)[16], void* dst, bool valid, int lane,
+                                       uint32_t perm = 0) {
+  const uint32_t my = scratch + (uint32_t)lane * 80u;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(my + 16u * ((uint32_t)j ^ perm)), "r"(v[4 * j]),
+                 "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                 : "memory");
+  __syncwarp();
+  const unsigned long long dp = reinterpret_cast<unsigned long long>(dst);
+  const int sub = lane >> 2, ch = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = 8 * i + sub;
+    const unsigned long long rp = __shfl_sync(0xffffffffu, dp, row);
+    const int ok = __shfl_sync(0xffffffffu, valid ? 1 : 0, row);
+    uint4 x;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w)
+                 : "r"(scratch + (uint32_t)row * 80u + 16u * ch));
+    if (ok) *(reinterpret_cast<uint4*>(rp) + ch) = x;
+  }
+  __syncwarp();
+}
+
+// and the mirror image for loads: every lane ends up with the 64-byte piece at ITS pointer (chunk j taken from chunk
+// position j ^ perm), fetched eight rows x 64 bytes per load instruction
+ARL_DEVINL void load_rows16_coalesced(uint32_t scratch, uint32_t (&v)[16], const void* src, bool valid, int lane,
+                                      uint32_t perm = 0) {
+  const unsigned long long sp = reinterpret_cast<unsigned long long>(src);
+  const int sub = lane >> 2, ch = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = 8 * i + sub;
+    const unsigned long long rp = __shfl_sync(0xffffffffu, sp, row);
+    const int ok = __shfl_sync(0xffffffffu, valid ? 1 : 0, row);
+    uint4 x = make_uint4(0u, 0u, 0u, 0u);
+    if (ok) x = __ldg(reinterpret_cast<const uint4*>(rp) + ch);
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(scratch + (uint32_t)row * 80u + 16u * ch), "r"(x.x),
+                 "r"(x.y), "r"(x.z), "r"(x.w)
+                 : "memory");
+  }
+  __syncwarp();
+  const uint32_t my = scratch + (uint32_t)lane * 80u;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v[4 * j]), "=r"(v[4 * j + 1]), "=r"(v[4 * j + 2]), "=r"(v[4 * j + 3])
+                 : "r"(my + 16u * ((uint32_t)j ^ perm)));
+  __syncwarp();
+}
+
 ARL_DEVINL float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

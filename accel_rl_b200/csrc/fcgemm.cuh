@@ -155,6 +155,9 @@ __global__ void __launch_bounds__(kFcThreads, 1) fc_gemm_kernel(const __grid_con
         float* dst = p.out_f32 + ((long)blockIdx.z * p.M + row) * p.ldo + blockIdx.y * BN + col;
         store_rows32_coalesced(scratch, v, dst, row < p.M, lane);
       } else if (KIND == 1) {
+        // (a shared-memory-transposed variant of these 64-byte row pieces — load_rows16_coalesced / store_rows16_coalesced
+        // with the swizzle as a chunk permutation — was measured: 10.1 vs 9.6 us, the extra shuffles and shared-memory
+        // round trips cost more than the LSU wavefronts they save; the direct form stays)
         const int row = blockIdx.x * 128 + r;   // image
         if (row < p.M) {
           const int n0 = blockIdx.y * BN + col; // GEMM column = hw*64 + c

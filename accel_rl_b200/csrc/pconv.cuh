@@ -561,12 +561,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) pconv_wgrad_kernel(const __grid
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = 0;
         }
-        if (blk < p.nblk) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            reinterpret_cast<float4*>(dst)[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                                            __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
-        }
+        store_rows16_coalesced(smem_base + (uint32_t)(warp - 2) * kRowStoreScratch, v, dst, blk < p.nblk, lane);
       }
     }
     tc_fence_before();
