@@ -987,6 +987,15 @@ HeadParams head_base(arl_ctx* c, int n, int S) {
   return p;
 }
 
+// the head kernel is instantiated for action-count bounds 4 / 6 / 9 / 18 (its per-action loops are unrolled)
+template <int MODE>
+cudaError_t launch_head(const HeadParams& p, int n, cudaStream_t st) {
+  if (p.A <= 4) return launch_k(head_kernel<MODE, 4>, dim3(n), dim3(kHeadThreads), 0, st, p);
+  if (p.A <= 6) return launch_k(head_kernel<MODE, 6>, dim3(n), dim3(kHeadThreads), 0, st, p);
+  if (p.A <= 9) return launch_k(head_kernel<MODE, 9>, dim3(n), dim3(kHeadThreads), 0, st, p);
+  return launch_k(head_kernel<MODE, kMaxActions>, dim3(n), dim3(kHeadThreads), 0, st, p);
+}
+
 int policy_forward16(arl_ctx* c, const __nv_bfloat16* obs16, int n, const int* out_rows, float* prob, float* value,
                      const double* uniforms, uint8_t* actions, bool pc, cudaStream_t st, const EnvStepArgs* es = nullptr) {
   int S = 0;
@@ -994,7 +1003,7 @@ int policy_forward16(arl_ctx* c, const __nv_bfloat16* obs16, int n, const int* o
   HeadParams p = head_base(c, n, S);
   if (es) { p.es = *es; p.es_on = 1; }
   p.out_rows = out_rows; p.prob = prob; p.value = value; p.uniforms = uniforms; p.actions = uniforms ? actions : nullptr;
-  ARL_CHECK(c, launch_k(head_kernel<0>, dim3(n), dim3(kHeadThreads), 0, st, p));
+  ARL_CHECK(c, launch_head<0>(p, n, st));
   c->launches++;
   prof_mark(c, "head_sample", st);
   ARL_CHECK(c, cudaGetLastError());
@@ -1109,7 +1118,7 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
   const bool fct = pcb && fc_tiles_ok(c);
   if (fct) { p.dh_t = c->dh_t; p.dh_rows = c->fc_rows; }
   c->n_loss_rows = n;
-  ARL_CHECK(c, launch_k(head_kernel<1>, dim3(n), dim3(kHeadThreads), 0, st, p));
+  ARL_CHECK(c, launch_head<1>(p, n, st));
   c->launches++;
   prof_mark(c, "head_loss", st);
   ARL_CHECK(c, cudaGetLastError());

@@ -736,11 +736,14 @@ constexpr int kHeadThreads = 128;
 // The split-K partial sums are the only HBM-latency-bound part, so every thread keeps 4 x unroll
 // independent loads in flight; logits/value are reduced over the block through shared memory and the
 // softmax / loss arithmetic is done redundantly by every thread (a handful of flops).
-template <int MODE>
+// AMAX: compile-time bound on the action count (4 / 6 / 9 / 18).  Every per-action loop is fully unrolled over AMAX with
+// a runtime `a < A` guard, and predicated-off instructions still issue: with one 18-wide instantiation a 4-action game
+// executed 2 565 warp instructions per row (ncu), 3/4 of them dead.
+template <int MODE, int AMAX>
 __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadParams p) {
   pdl_wait();
   pdl_trigger();
-  __shared__ float s_part[kHeadThreads / 32][kMaxActions + 1];
+  __shared__ float s_part[kHeadThreads / 32][AMAX + 1];
   const int row = blockIdx.x;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   constexpr int JT = 4;
@@ -750,6 +753,22 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadParams p) {
     int j = t + kHeadThreads * i;
     h[i] = (j < p.H) ? __ldg(p.fc_bias + j) : 0.f;
   }
+  // MODE 1: the per-sample training inputs hang off a dependent chain (index -> row -> action -> old probability);
+  // start it now so its DRAM round trips overlap the split-K loads and the head arithmetic
+  long src = 0;
+  int act = 0;
+  float adv = 0.f, ret = 0.f, w_row = 0.f;
+  float old_p[AMAX];
+  if (MODE == 1) {
+    src = p.idx ? p.idx[(p.idx_off ? (long)p.idx_off[0] * p.M : 0) + row] : row;
+    act = p.act_in[src];
+    adv = p.adv[src];
+    ret = p.ret[src];
+    w_row = p.inv_count;
+    if (p.valids) w_row = p.valids[src] ? (1.f / p.valid_count[0]) : 0.f;
+#pragma unroll
+    for (int a = 0; a < AMAX; ++a) old_p[a] = (p.algo == 0 && a < p.A) ? p.old_prob[src * p.A + a] : 0.f;
+  }
   const float* prow = p.partial + (long)row * p.H + t;
   const long sstride = (long)p.M * p.H;
 #pragma unroll 4
@@ -758,9 +777,9 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadParams p) {
     for (int i = 0; i < JT; ++i)
       if (t + kHeadThreads * i < p.H) h[i] += prow[s * sstride + kHeadThreads * i];
   }
-  float logit[kMaxActions];
+  float logit[AMAX];
 #pragma unroll
-  for (int a = 0; a < kMaxActions; ++a) logit[a] = 0.f;
+  for (int a = 0; a < AMAX; ++a) logit[a] = 0.f;
   float v = 0.f;
 #pragma unroll
   for (int i = 0; i < JT; ++i) {
@@ -772,27 +791,27 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadParams p) {
       v += acc * __ldg(p.w_v + j);
       const float* wr = p.w_pi + (long)j * p.A;
 #pragma unroll
-      for (int a = 0; a < kMaxActions; ++a)
+      for (int a = 0; a < AMAX; ++a)
         if (a < p.A) logit[a] += acc * __ldg(wr + a);
     }
   }
   v = warp_sum(v);
 #pragma unroll
-  for (int a = 0; a < kMaxActions; ++a)
+  for (int a = 0; a < AMAX; ++a)
     if (a < p.A) logit[a] = warp_sum(logit[a]);
   if (lane == 0) {
 #pragma unroll
-    for (int a = 0; a < kMaxActions; ++a)
+    for (int a = 0; a < AMAX; ++a)
       if (a < p.A) s_part[warp][a] = logit[a];
-    s_part[warp][kMaxActions] = v;
+    s_part[warp][AMAX] = v;
   }
   __syncthreads();
   v = __ldg(p.b_v);
 #pragma unroll
-  for (int w = 0; w < kHeadThreads / 32; ++w) v += s_part[w][kMaxActions];
+  for (int w = 0; w < kHeadThreads / 32; ++w) v += s_part[w][AMAX];
   float mx = -INFINITY;
 #pragma unroll
-  for (int a = 0; a < kMaxActions; ++a)
+  for (int a = 0; a < AMAX; ++a)
     if (a < p.A) {
       float l = __ldg(p.b_pi + a);
 #pragma unroll
@@ -800,22 +819,22 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadParams p) {
       logit[a] = l;
       mx = fmaxf(mx, l);
     }
-  float prob[kMaxActions];
+  float prob[AMAX];
   float sum = 0.f;
 #pragma unroll
-  for (int a = 0; a < kMaxActions; ++a) {
+  for (int a = 0; a < AMAX; ++a) {
     prob[a] = 0.f;
     if (a < p.A) { prob[a] = expf(logit[a] - mx); sum += prob[a]; }
   }
 #pragma unroll
-  for (int a = 0; a < kMaxActions; ++a) prob[a] = prob[a] / sum;
+  for (int a = 0; a < AMAX; ++a) prob[a] = prob[a] / sum;
 
   if (MODE == 0) {
     if (t == 0) {
       long orow = p.out_rows ? p.out_rows[row] : row;
       if (p.prob) {
 #pragma unroll
-        for (int a = 0; a < kMaxActions; ++a)
+        for (int a = 0; a < AMAX; ++a)
           if (a < p.A) p.prob[orow * p.A + a] = prob[a];
       }
       if (p.value) p.value[orow] = v;
@@ -824,24 +843,20 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadParams p) {
         float cs = 0.f;
         int k = 0;
 #pragma unroll
-        for (int a = 0; a < kMaxActions; ++a)
+        for (int a = 0; a < AMAX; ++a)
           if (a < p.A) { cs = __fadd_rn(cs, prob[a]); k += ((double)cs < u) ? 1 : 0; }
         p.actions[orow] = (uint8_t)min(k, p.A - 1);
       }
       if (p.es_on) env_step_one(p.es, row);
     }
   } else {
-    const long src = p.idx ? p.idx[(p.idx_off ? (long)p.idx_off[0] * p.M : 0) + row] : row;
-    const int act = p.act_in[src];
-    const float adv = p.adv[src], ret = p.ret[src];
-    float w = p.inv_count;
-    if (p.valids) w = p.valids[src] ? (1.f / p.valid_count[0]) : 0.f;
+    const float w = w_row;
     const float TINY = 1e-8f;
-    float g[kMaxActions];   // dL/dprob
+    float g[AMAX];   // dL/dprob
     float ent = 0.f;
     float pa = 0.f;
 #pragma unroll
-    for (int a = 0; a < kMaxActions; ++a) {
+    for (int a = 0; a < AMAX; ++a) {
       g[a] = 0.f;
       if (a < p.A) {
         float lp = logf(prob[a] + TINY);
@@ -853,7 +868,10 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadParams p) {
     float l_pi;
     float gact;
     if (p.algo == 0) {
-      float po = p.old_prob[src * p.A + act];
+      float po = 0.f;
+#pragma unroll
+      for (int a = 0; a < AMAX; ++a)
+        if (a == act) po = old_p[a];
       float ratio = (pa + TINY) / (po + TINY);
       float cp = p.clip_param * p.hyper[0];
       float lo = 1.f - cp, hi = 1.f + cp;
@@ -870,22 +888,22 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadParams p) {
       gact = -w * adv / (pa + TINY);
     }
 #pragma unroll
-    for (int a = 0; a < kMaxActions; ++a)
+    for (int a = 0; a < AMAX; ++a)
       if (a == act) g[a] += gact;
     float verr = v - ret;
     float dv = 2.f * p.v_coeff * w * verr;
     float dot = 0.f;
 #pragma unroll
-    for (int a = 0; a < kMaxActions; ++a) dot += prob[a] * g[a];
-    float dl[kMaxActions];
+    for (int a = 0; a < AMAX; ++a) dot += prob[a] * g[a];
+    float dl[AMAX];
 #pragma unroll
-    for (int a = 0; a < kMaxActions; ++a) dl[a] = prob[a] * (g[a] - dot);
+    for (int a = 0; a < AMAX; ++a) dl[a] = prob[a] * (g[a] - dot);
     if (t == 0) {
       float lp_ = w * l_pi, lv_ = p.v_coeff * w * verr * verr, le_ = -p.ent_coeff * w * ent;
       float* o = p.loss_partial + 4 * (long)row;
       o[0] = lp_; o[1] = lv_; o[2] = le_; o[3] = lp_ + lv_ + le_;
 #pragma unroll
-      for (int a = 0; a < kMaxActions; ++a)
+      for (int a = 0; a < AMAX; ++a)
         if (a < p.A) p.dlogit_out[(long)row * (p.A + 1) + a] = dl[a];
       p.dlogit_out[(long)row * (p.A + 1) + p.A] = dv;
     }
@@ -896,7 +914,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadParams p) {
         float d = dv * __ldg(p.w_v + j);
         const float* wr = p.w_pi + (long)j * p.A;
 #pragma unroll
-        for (int a = 0; a < kMaxActions; ++a)
+        for (int a = 0; a < AMAX; ++a)
           if (a < p.A) d += dl[a] * __ldg(wr + a);
         d = (h[i] > 0.f) ? d : 0.f;
         p.h_out[(long)row * p.H + j] = __float2bfloat16_rn(h[i]);
