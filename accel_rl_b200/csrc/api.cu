@@ -135,6 +135,7 @@ struct arl_ctx {
   double* sumsq_partial_fc = nullptr;  // update_range_kernel's per-block sums of squares (early FC update)
   bool train_step_active = false;      // grad_minibatch is followed by the local clip_update (train_minibatches, sync == 0)
   bool early_fc_done = false;          // this minibatch's FC weights were updated by update_range_kernel
+  const void* pending_fin = nullptr;   // TrainPlan whose gradient finalisation clip_update must fold into its update kernel
   cudaEvent_t ev_fcd = nullptr;        // "FC data gradient has read the FC weights"
   unsigned long long* ticket = nullptr; // grid-barrier ticket of update_fused_kernel
   float* hyper = nullptr;          // [0] lr_mult
@@ -1080,6 +1081,7 @@ int get_plan(arl_ctx* c, int n, TrainPlan** out) {
 
 bool early_fc_ok(arl_ctx* c);
 int early_fc_update(arl_ctx* c, cudaStream_t st);
+bool merge_finalize_ok(arl_ctx* c, bool fct);
 
 // forward + loss + backward for one minibatch -> flat grad
 int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaStream_t st) {
@@ -1257,7 +1259,9 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
     prof_mark(c, kDgradName[l], st);
   }
   // ---- sum partials, scatter into the flat gradient ----
-  {
+  if (merge_finalize_ok(c, fct)) {
+    c->pending_fin = P;        // clip_update folds it into phase 1 of update_fused_kernel (one launch, one pass less)
+  } else {
     dim3 grid(P->fin_blocks, P->n_jobs);
     ARL_CHECK(c, launch_k(finalize_grads_kernel, dim3(grid), dim3(256), 0, st, P->jobs_dev, c->grad));
     c->launches++;
@@ -1295,6 +1299,19 @@ bool early_fc_ok(arl_ctx* c) {
          c->pc_mode >= 2 && fc_tiles_ok(c) && (c->off_Wfc % 4 == 0) && (((long)c->Kfc * c->H) % 4 == 0);
 }
 
+// grad_minibatch leaves the gradient finalisation to the update kernel when the local fused update follows it and the
+// FC weight gradient is written straight into the flat vector (so the finalisation jobs cover exactly "everything else").
+// OFF by default (ARL_MERGE_FINALIZE=1 enables; results identical): measured slower — 40.7 us for the merged kernel
+// against 5.3 + 22.8 us for finalize_grads + update_fused, 57.4 vs 55.6 ms per iteration.  The partial sums are long
+// dependent load chains (64..148 partials per element) that want many more threads in flight than the 592 x 256
+// co-resident ones the grid barrier allows, and every block waits at the barrier for the slowest chain.
+bool merge_finalize_ok(arl_ctx* c, bool fct) {
+  static const bool on = getenv("ARL_MERGE_FINALIZE") && atoi(getenv("ARL_MERGE_FINALIZE")) != 0;
+  static const bool fused = !(getenv("ARL_FUSED_UPDATE") && atoi(getenv("ARL_FUSED_UPDATE")) == 0);
+  return on && fused && fct && c->train_step_active && c->opt_set && c->m && c->v && (c->off_Wfc % 4 == 0) &&
+         (((long)c->Kfc * c->H) % 4 == 0);
+}
+
 int early_fc_update(arl_ctx* c, cudaStream_t st) {
   bool fused_cast = false;
   UpdateParams u = update_params(c, 1.f, &fused_cast);
@@ -1319,9 +1336,13 @@ UpdateParams update_params(arl_ctx* c, float gscale, bool* fused_cast_out) {
   u.out_norm = c->log_norm; u.out_loss = c->log_loss; u.log_slot = c->log_slot; u.log_cap = c->log_cap;
   u.shadow = c->wfc_bf16; u.shadow_begin = c->off_Wfc; u.shadow_end = c->off_Wfc + (long)c->Kfc * c->H;
   bool fused_cast = (c->off_Wfc % 4 == 0) && (c->H % 4 == 0);
-  if (fc_tiles_ok(c)) { u.shadow = c->wfc_t; u.shadow_tiles = 1; u.shadow_HW = c->HWlast; u.shadow_H = c->H; }
+  if (fc_tiles_ok(c)) {
+    u.shadow = c->wfc_t; u.shadow_tiles = 1; u.shadow_HW = c->HWlast; u.shadow_H = c->H;
+    u.shadow_H_magic = pc_magic((uint32_t)c->H); u.shadow_HW_magic = pc_magic((uint32_t)c->HWlast);
+    if ((long)c->Kfc * c->H >= (1L << 32) / c->H) u.shadow = nullptr;   // outside the exact range of the magic division
+  }
   if (!fused_cast) u.shadow = nullptr;
-  *fused_cast_out = fused_cast;
+  *fused_cast_out = fused_cast && (u.shadow != nullptr || !fc_tiles_ok(c));
   return u;
 }
 
@@ -1335,6 +1356,12 @@ int clip_update(arl_ctx* c, float gscale, cudaStream_t st) {
     u.skip4_begin = c->off_Wfc / 4; u.skip4_len = (long)c->Kfc * c->H / 4;
     u.sumsq_partial2 = c->sumsq_partial_fc; u.n_partial2 = kEarlyBlocks;
     c->early_fc_done = false;
+  }
+  if (c->pending_fin) {
+    const TrainPlan* P = static_cast<const TrainPlan*>(c->pending_fin);
+    u.fin_jobs = P->jobs_dev; u.n_fin_jobs = P->n_jobs;
+    u.fc4_begin = c->off_Wfc / 4; u.fc4_len = (long)c->Kfc * c->H / 4;
+    c->pending_fin = nullptr;
   }
   // norm + clip + update in one launch (update_fused_kernel); ARL_FUSED_UPDATE=0 keeps the two-kernel form
   static const bool fused = !(getenv("ARL_FUSED_UPDATE") && atoi(getenv("ARL_FUSED_UPDATE")) == 0);
@@ -1844,7 +1871,7 @@ int train_minibatches(arl_ctx* c, const int* idx, int mb_size, int count, int sy
   struct Active {      // grad_minibatch may update the FC weights early only when the local clip_update follows it
     arl_ctx* c;
     Active(arl_ctx* c_, bool on) : c(c_) { c->train_step_active = on; }
-    ~Active() { c->train_step_active = false; c->early_fc_done = false; }
+    ~Active() { c->train_step_active = false; c->early_fc_done = false; c->pending_fin = nullptr; }
   } active(c, sync == 0);
   if (!(c->sampler_set && c->t_obs == c->sc.observations && c->roll_obs16) || (sync && c->sync_graph_failed)) {
     // training inputs that are not the sampler's rollout buffers: plain launches, one minibatch at a time
@@ -2118,6 +2145,7 @@ int arl_profile_graph(arl_ctx* c, int kind, const int* idx, int mb_size, int rep
     if (!rc) rc = clip_update(c, 1.f, cap_s);
     c->train_step_active = false;
     c->early_fc_done = false;
+    c->pending_fin = nullptr;
   } else if (kind == 1) {
     rc = rollout_step(c, 0, nullptr, cap_s);
   } else {

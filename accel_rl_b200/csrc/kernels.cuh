@@ -1007,64 +1007,73 @@ ARL_DEVINL void pc_decode_channel(int cc, int C, int s, int ci_major, int& ci, i
   }
 }
 
+// one element of one job: sums its partials in a fixed order, writes it to its place in the flat gradient;
+// -> false when the element is a padding tap / channel that has no parameter (nothing written)
+ARL_DEVINL bool finalize_elem(const GradJob& jb, long i, float* __restrict__ grad, float& acc_out) {
+  int r = (int)(i / jb.cols);
+  int c = (int)(i - (long)r * jb.cols);
+  const float* s = jb.src + (long)r * jb.ld + c;
+  // fixed summation order: 16 interleaved chains (16 independent L2 loads in flight per thread — the loop is pure
+  // latency: 64..148 partials, each a separate 4-byte load), then a fixed tree
+  float a[16];
+#pragma unroll
+  for (int u = 0; u < 16; ++u) a[u] = 0.f;
+  int k = 0;
+  for (; k + 16 <= jb.S; k += 16) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) a[u] += s[(long)(k + u) * jb.sstride];
+  }
+#pragma unroll
+  for (int u = 0; u < 16; ++u)
+    if (k + u < jb.S) a[u] += s[(long)(k + u) * jb.sstride];
+#pragma unroll
+  for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+    for (int u = 0; u < w; ++u) a[u] += a[u + w];
+  const float acc = a[0] * jb.scale;
+  acc_out = acc;
+  if (jb.map == GM_LINEAR) {
+    grad[jb.dst_off + i] = acc;
+  } else if (jb.map == GM_CONV_NHWC) {
+    // r = k' = (ky*kw + kx)*C + ci ; c = cout
+    int ci = r % jb.C;
+    int t = r / jb.C;
+    int kx = t % jb.kw, ky = t / jb.kw;
+    grad[jb.dst_off + (((long)c * jb.C + ci) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx)] = acc;
+  } else if (jb.map == GM_CONV_S2D) {
+    // first layer over the space-to-depth input: r = k' = (ty*2 + tx)*(C*s*s) + ci*s*s + dy*s + dx
+    const int s2 = jb.s2d * jb.s2d, cs = jb.C * s2;
+    int ch = r % cs;
+    int t = r / cs;
+    int tx = t % 2, ty = t / 2;
+    int ci = ch / s2, dy = (ch % s2) / jb.s2d, dx = ch % jb.s2d;
+    int ky = ty * jb.s2d + dy, kx = tx * jb.s2d + dx;
+    grad[jb.dst_off + (((long)c * jb.C + ci) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx)] = acc;
+  } else if (jb.map == GM_PCONV) {
+    int blk = r >> 6, ch = r & 63;
+    int t = blk / jb.P, plane = blk - t * jb.P;
+    int ty = t / jb.T, tx = t - ty * jb.T;
+    int ci, py, px;
+    pc_decode_channel(plane * 64 + ch, jb.C, jb.s2d, jb.ci_major, ci, py, px);
+    int ky = ty * jb.s2d + py, kx = tx * jb.s2d + px;
+    if (!(ky < jb.kh && kx < jb.kw && ci < jb.C)) return false;
+    grad[jb.dst_off + (((long)c * jb.C + ci) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx)] = acc;
+  } else {  // GM_HEAD: r = j, c in [0, A+2)
+    if (c < jb.A) grad[jb.dst_off + (long)r * jb.A + c] = acc;
+    else if (c == jb.A) grad[jb.dst_off2 + r] = acc;
+    else grad[jb.dst_off3 + r] = acc;
+  }
+  return true;
+}
+
 __global__ void __launch_bounds__(256) finalize_grads_kernel(const GradJob* __restrict__ jobs, float* __restrict__ grad) {
   pdl_wait();
   pdl_trigger();
   const GradJob jb = jobs[blockIdx.y];
   const long total = (long)jb.rows * jb.cols;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    int r = (int)(i / jb.cols);
-    int c = (int)(i - (long)r * jb.cols);
-    const float* s = jb.src + (long)r * jb.ld + c;
-    // fixed summation order: 16 interleaved chains (16 independent L2 loads in flight per thread — the loop is pure
-    // latency: 64..148 partials, each a separate 4-byte load), then a fixed tree
-    float a[16];
-#pragma unroll
-    for (int u = 0; u < 16; ++u) a[u] = 0.f;
-    int k = 0;
-    for (; k + 16 <= jb.S; k += 16) {
-#pragma unroll
-      for (int u = 0; u < 16; ++u) a[u] += s[(long)(k + u) * jb.sstride];
-    }
-#pragma unroll
-    for (int u = 0; u < 16; ++u)
-      if (k + u < jb.S) a[u] += s[(long)(k + u) * jb.sstride];
-#pragma unroll
-    for (int w = 8; w >= 1; w >>= 1)
-#pragma unroll
-      for (int u = 0; u < w; ++u) a[u] += a[u + w];
-    float acc = a[0] * jb.scale;
-    if (jb.map == GM_LINEAR) {
-      grad[jb.dst_off + i] = acc;
-    } else if (jb.map == GM_CONV_NHWC) {
-      // r = k' = (ky*kw + kx)*C + ci ; c = cout
-      int ci = r % jb.C;
-      int t = r / jb.C;
-      int kx = t % jb.kw, ky = t / jb.kw;
-      grad[jb.dst_off + (((long)c * jb.C + ci) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx)] = acc;
-    } else if (jb.map == GM_CONV_S2D) {
-      // first layer over the space-to-depth input: r = k' = (ty*2 + tx)*(C*s*s) + ci*s*s + dy*s + dx
-      const int s2 = jb.s2d * jb.s2d, cs = jb.C * s2;
-      int ch = r % cs;
-      int t = r / cs;
-      int tx = t % 2, ty = t / 2;
-      int ci = ch / s2, dy = (ch % s2) / jb.s2d, dx = ch % jb.s2d;
-      int ky = ty * jb.s2d + dy, kx = tx * jb.s2d + dx;
-      grad[jb.dst_off + (((long)c * jb.C + ci) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx)] = acc;
-    } else if (jb.map == GM_PCONV) {
-      int blk = r >> 6, ch = r & 63;
-      int t = blk / jb.P, plane = blk - t * jb.P;
-      int ty = t / jb.T, tx = t - ty * jb.T;
-      int ci, py, px;
-      pc_decode_channel(plane * 64 + ch, jb.C, jb.s2d, jb.ci_major, ci, py, px);
-      int ky = ty * jb.s2d + py, kx = tx * jb.s2d + px;
-      if (ky < jb.kh && kx < jb.kw && ci < jb.C)
-        grad[jb.dst_off + (((long)c * jb.C + ci) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx)] = acc;
-    } else {  // GM_HEAD: r = j, c in [0, A+2)
-      if (c < jb.A) grad[jb.dst_off + (long)r * jb.A + c] = acc;
-      else if (c == jb.A) grad[jb.dst_off2 + r] = acc;
-      else grad[jb.dst_off3 + r] = acc;
-    }
+    float acc;
+    finalize_elem(jb, i, grad, acc);
   }
 }
 
@@ -1141,6 +1150,12 @@ struct UpdateParams {
   // the update does not depend on the norm); their sum of squares arrives in sumsq_partial2
   long skip4_begin, skip4_len;
   const double* sumsq_partial2; int n_partial2;
+  // n_fin_jobs > 0: gradient finalisation folded into phase 1 of update_fused_kernel — the blocks first sum the split
+  // partials of every tensor except the FC weights (finalize_elem; each thread squares what it writes), then take the
+  // sum of squares of the FC-weight range [fc4_begin, +fc4_len) float4 groups, which fc_gemm_kernel wrote directly
+  const GradJob* fin_jobs; int n_fin_jobs;
+  long fc4_begin, fc4_len;
+  uint32_t shadow_H_magic, shadow_HW_magic;   // floor(2^32/d) + 1: the tile index needs two divisions per float4 group
 };
 
 ARL_DEVINL void update_body(const UpdateParams& p);
@@ -1158,7 +1173,54 @@ __global__ void __launch_bounds__(256, 4) update_fused_kernel(UpdateParams p, do
                                                               unsigned long long* __restrict__ ticket) {
   pdl_wait();
   pdl_trigger();
-  sumsq_body(p.grad, p.n, p.gscale, partial, p.skip4_begin, p.skip4_len);
+  if (p.n_fin_jobs > 0) {
+    double acc = 0.0;
+    const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x, gsize = (long)gridDim.x * blockDim.x;
+    float* grad = const_cast<float*>(p.grad);
+    // All jobs' elements form one index space, dealt out in groups of 32 consecutive elements (coalesced partial loads)
+    // to warps numbered block-interleaved, so every block gets the same share and no thread more than one element —
+    // an unbalanced phase 1 leaves most blocks spinning on the barrier below while a few walk several jobs.
+    {
+      const int lane = threadIdx.x & 31;
+      const long wslot = (long)(threadIdx.x >> 5) * gridDim.x + blockIdx.x;      // 0 .. 8*gridDim.x - 1
+      const long nwarps = (long)(blockDim.x >> 5) * gridDim.x;
+      long total_all = 0;
+      for (int jn = 0; jn < p.n_fin_jobs; ++jn) total_all += (long)p.fin_jobs[jn].rows * p.fin_jobs[jn].cols;
+      for (long v0 = wslot * 32; v0 < total_all; v0 += nwarps * 32) {
+        long v = v0 + lane;
+        if (v < total_all) {
+          int jn = 0;
+          for (; jn < p.n_fin_jobs; ++jn) {
+            const long t = (long)p.fin_jobs[jn].rows * p.fin_jobs[jn].cols;
+            if (v < t) break;
+            v -= t;
+          }
+          const GradJob jb = p.fin_jobs[jn];
+          float g;
+          if (finalize_elem(jb, v, grad, g)) { g *= p.gscale; acc += (double)(g * g); }
+        }
+      }
+    }
+    if (p.skip4_len == 0) {      // (an early FC update has already squared this range)
+      const float4* g4 = reinterpret_cast<const float4*>(p.grad) + p.fc4_begin;
+      for (long j = gtid; j < p.fc4_len; j += gsize) {
+        float4 v = g4[j];
+        float a = v.x * p.gscale, b = v.y * p.gscale, c = v.z * p.gscale, d = v.w * p.gscale;
+        acc += (double)(a * a + b * b) + (double)(c * c + d * d);
+      }
+    }
+    __shared__ double s1[8];
+    acc = warp_sum_d(acc);
+    if ((threadIdx.x & 31) == 0) s1[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += s1[w];
+      partial[blockIdx.x] = t;
+    }
+  } else {
+    sumsq_body(p.grad, p.n, p.gscale, partial, p.skip4_begin, p.skip4_len);
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -1166,6 +1228,7 @@ __global__ void __launch_bounds__(256, 4) update_fused_kernel(UpdateParams p, do
     const unsigned long long target = (t / gridDim.x + 1ULL) * gridDim.x;
     long long t0 = clock64();
     while (atomicAdd(ticket, 0ULL) < target) {
+      __nanosleep(40);
       if (clock64() - t0 > 20000000000LL) dev_fail(320);
     }
     __threadfence();
@@ -1205,8 +1268,11 @@ ARL_DEVINL void update_vec4(const UpdateParams& p, long i, float scale, float al
   if (p.shadow && e0 >= p.shadow_begin && e0 + 4 <= p.shadow_end) {
     long off = e0 - p.shadow_begin;
     if (p.shadow_tiles) {
-      const unsigned ou = (unsigned)off, rr = ou / (unsigned)p.shadow_H;
-      off = fc_tile_index(rr, (int)(ou - rr * (unsigned)p.shadow_H), p.shadow_HW, p.shadow_H);
+      // row r = off / H, column j = off % H, r = c*HW + hw  (magic-number division: exact for off < 2^32 / H)
+      const unsigned ou = (unsigned)off, rr = __umulhi(ou, p.shadow_H_magic);
+      const int j = (int)(ou - rr * (unsigned)p.shadow_H);
+      const unsigned c = __umulhi(rr, p.shadow_HW_magic), hw = rr - c * (unsigned)p.shadow_HW;
+      off = (((long)hw * (p.shadow_H >> 6) + (j >> 6)) * 64 + c) * 64 + (((((j & 63) >> 3) ^ (c & 7)) << 3) | (j & 7));
     }
     *reinterpret_cast<uint2*>(p.shadow + off) = make_uint2(pack_bf16x2(pp[0], pp[1]), pack_bf16x2(pp[2], pp[3]));
   }

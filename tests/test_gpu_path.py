@@ -429,6 +429,46 @@ def test_ppo_iteration_vs_oracle(standardize):
         assert cos > 0.99
 
 
+def test_operand_copies_refreshed_by_the_update_match_a_fresh_pack():
+    """The update kernel rewrites the bf16 FC operand tiles (and pack_weights the conv tap tiles) after every step.  After
+    a PPO iteration the trained engine's forward pass must equal, bit for bit, that of a fresh engine loaded with the
+    same fp32 parameters (whose operand copies come from the independent pack_weights path)."""
+    from accel_rl_b200.policies import AtariCnnPolicy, cnn_specs
+    from accel_rl_b200.envs.atari_env import EnvSpec
+    from accel_rl_b200.spaces import Discrete, UintBox
+    res_obs = np.random.RandomState(3).randint(0, 256, (64, 4, 104, 80), dtype=np.uint8)
+    from accel_rl_b200.algos import PPO
+    from accel_rl_b200.util.seeding import set_seed
+    rules = dict(synth_ale.DEFAULT_RULES, pool_frames=128, life_base=24, life_mod=11, reward_mod=7, pool_seed=0)
+    set_seed(7)
+    sampler = _make_sampler(4, 2, 16, rules=rules)
+    env_spec, sample_size, horizon, mbr = sampler.initialize(seed=8, affinities=dict(), discount=0.99, need_extra_obs=True)
+    pol, flat, spec = make_policy(1)
+    algo = PPO(optimizer_args=dict(minibatch_size=64, epochs=2))
+    algo.initialize(pol, env_spec, sample_size, horizon, mbr)
+    sampler.policy_init(pol)
+    algo.set_n_itr(10)
+    try:
+        buf, _ = sampler.obtain_samples(0)
+        algo.optimize_policy(0, buf)
+        trained = pol.get_param_values()
+        assert not np.array_equal(trained, flat)
+        obs = torch.tensor(res_obs).cuda()
+        p1 = torch.zeros(64, 4, device="cuda"); v1 = torch.zeros(64, device="cuda")
+        pol.engine.forward(obs, prob=p1, value=v1)
+        fresh = AtariCnnPolicy(initial_param_values=trained, max_rows=64, **cnn_specs[1])
+        fresh.initialize(EnvSpec(UintBox((4, 104, 80)), Discrete(4)))
+        try:
+            p2 = torch.zeros(64, 4, device="cuda"); v2 = torch.zeros(64, device="cuda")
+            fresh.engine.forward(obs, prob=p2, value=v2)
+            torch.cuda.synchronize()
+            assert torch.equal(p1, p2) and torch.equal(v1, v2)
+        finally:
+            fresh.engine.close()
+    finally:
+        pol.engine.close()
+
+
 def test_early_fc_update_is_bit_identical():
     """Without global-norm clipping (PPO's default) the FC weights are updated as soon as their gradient is final, while
     the conv gradient chain still runs (update_range_kernel).  Same arithmetic per element: parameters and optimizer
