@@ -106,8 +106,9 @@ struct arl_ctx {
   bool no_fork = false;                // serialise everything on the caller's stream (per-kernel profiling)
   // CTA caps while a data-gradient and a weight-gradient kernel share the GPU (0 = all SMs).  Measured (B200, C2):
   // wgrad capped at 56..96 CTAs lets the concurrent dgrad chain start on the free SMs and shrinks the per-CTA partial
-  // traffic: 62.6 -> 60.4 ms per iteration; capping the dgrad side as well does not help.
-  int dgrad_ctas = 0, wgrad_ctas = 64;
+  // traffic: 62.6 -> 60.4 ms per iteration; capping the dgrad side as well does not help.  Re-swept after the coalesced
+  // epilogues (ms per iteration at 24/32/40/48/64/80/100/148 CTAs: 56.6/56.6/55.1/54.9/55.7/55.5/56.9/59.1): 48.
+  int dgrad_ctas = 0, wgrad_ctas = 48;
   int pc_dy_n = 0;                     // images whose gradient-grid rows may be non-zero
   int pc_mode = 0;                     // 0: gather path   1: pconv forward (inference)   2: pconv forward + backward
   int Kfc = 0, H = 0, A = 0, HWlast = 0, Clast = 0;
