@@ -38,11 +38,12 @@ FLOP_PER_ENV_STEP_CONV = 265.7e6    # conv tiles only: the nort
 
 def ncu_traffic(label):
     """DRAM bytes per launch of `label` from the committed ncu --set full capture (None when not captured)"""
-    p = os.path.join(ROOT, "profiles", "r1c_traffic.json")
-    try:
-        return json.load(open(p))["kernels"].get(label)
-    except Exception:
-        return None
+    for name in ("r1e_traffic.json", "r1c_traffic.json"):
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", name)))["kernels"].get(label)
+        except Exception:
+            continue
+    return None
 
 
 def parse():
@@ -342,7 +343,7 @@ def run_ours(args):
                 roof = {"bound": "tensor", "kernel": k["kernel"], "achieved": k["tflops"], "peak": pk["tf_sustained"],
                         "unit": "TFLOP/s", "frac": round(k["tflops"] / pk["tf_sustained"], 4),
                         "traffic": ncu_traffic(k["kernel"]),
-                        "traffic_note": "DRAM bytes per launch, ncu --set full with cold caches (profiles/r1c_full.md)",
+                        "traffic_note": "DRAM bytes per launch, ncu --set full with cold caches (profiles/r1e_full.md)",
                         "peak_source": pk["src"] + " (sustained bf16, kernel timed inside a long step)",
                         "share_of_step": k["share"]}
                 break
