@@ -1627,6 +1627,15 @@ int arl_frame_update_rgb(arl_ctx* c, const uint8_t* raw_a, const uint8_t* raw_b,
 }
 
 int arl_sampler_configure(arl_ctx* c, const arl_sampler_cfg* cfg) {
+  if (c->sampler_set) {
+    // re-configuring the selected slot: release what the previous configuration allocated
+    if (c->rollout_graph) { cudaGraphExecDestroy(c->rollout_graph); c->rollout_graph = nullptr; }
+    cudaFree(c->est.f); cudaFree(c->cmd); cudaFree(c->rows_tab); cudaFree(c->tout.count);
+    cudaFree(c->step_obs16); cudaFree(c->roll_obs16);
+    c->est = EnvState{}; c->tout = TrajOut{}; c->cmd = nullptr; c->rows_tab = nullptr;
+    c->step_obs16 = nullptr; c->roll_obs16 = nullptr;
+    c->sampler_set = false;
+  }
   c->sc = *cfg;
   const int B = cfg->n_envs, T = cfg->horizon;
   if (cfg->planes != c->cfg.in_c) ARL_FAIL(c, "sampler planes != network input channels");

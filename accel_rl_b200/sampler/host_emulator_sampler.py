@@ -126,9 +126,13 @@ class HostEmulatorSampler(ActsrvAltOvrlpSampler):
 
     def _wait_group(self, g, timeout=300):
         for w in self._group_workers(g):
-            if not self._step_done[w].acquire(timeout=timeout):
-                raise RuntimeError("emulator worker %d did not answer within %d s (alive: %s)"
-                                   % (w, timeout, self._procs[w].is_alive()))
+            waited = 0
+            while not self._step_done[w].acquire(timeout=2):
+                waited += 2
+                if not self._procs[w].is_alive():
+                    raise RuntimeError("emulator worker %d died (exit code %s)" % (w, self._procs[w].exitcode))
+                if waited >= timeout:
+                    raise RuntimeError("emulator worker %d did not answer within %d s" % (w, timeout))
 
     def _release_group(self, g, cmd=W.CMD_STEP):
         self._cmd.value = cmd
