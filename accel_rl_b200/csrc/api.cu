@@ -77,6 +77,9 @@ struct PcLayer {
   int stages_fwd = 0, stages_dgrad = 0;
 };
 
+constexpr int kSsFinCap = 4096;   // finalize blocks that own elements (preset 1: ~320)
+constexpr int kSsFcCap = 4096;    // FC weight-gradient CTAs x 8 epilogue warps (preset 1: 54 x 8)
+
 struct TrainPlan {
   int n = 0;
   std::vector<int> conv_splits, conv_rps;
@@ -84,6 +87,7 @@ struct TrainPlan {
   GradJob* jobs_dev = nullptr;
   int n_jobs = 0;
   int fin_blocks = 1;
+  int n_ss = 0;                 // per-block sum-of-squares slots the finalize kernel fills (GradJob::ss_off)
 };
 
 }  // namespace
@@ -134,6 +138,9 @@ struct arl_ctx {
   float* loss_partial = nullptr;   // [kLossBlocks][4]
   double* sumsq_partial = nullptr;
   double* sumsq_partial_fc = nullptr;  // update_range_kernel's per-block sums of squares (early FC update)
+  double* ss_fin = nullptr;            // [kSsFinCap] finalize_grads_kernel's per-block sums of squares
+  double* ss_fc = nullptr;             // [kSsFcCap]  FC weight-gradient tiles' per-warp sums of squares
+  int pending_ss_fin = 0, pending_ss_fc = 0;   // > 0: this minibatch's global-norm partials came from the producers
   bool train_step_active = false;      // grad_minibatch is followed by the local clip_update (train_minibatches, sync == 0)
   bool early_fc_done = false;          // this minibatch's FC weights were updated by update_range_kernel
   const void* pending_fin = nullptr;   // TrainPlan whose gradient finalisation clip_update must fold into its update kernel
@@ -772,9 +779,10 @@ int fc_dgrad_tiles(arl_ctx* c, int n, cudaStream_t st) {
 }
 
 // weight gradient: act_fc^T x dh_t -> fp32 rows of the flat gradient (reference row order)
-int fc_wgrad_tiles(arl_ctx* c, int n, cudaStream_t st) {
+int fc_wgrad_tiles(arl_ctx* c, int n, cudaStream_t st, bool want_ss = false) {
   const int HW = c->HWlast;
   FcParams p{};
+  c->pending_ss_fc = 0;
   const long aplane = (long)c->fc_rows * 64;
   static const bool quad = !(getenv("ARL_FC_WGRAD_QUAD") && atoi(getenv("ARL_FC_WGRAD_QUAD")) == 0);
   if (quad && HW % 4 == 0) {
@@ -787,6 +795,7 @@ int fc_wgrad_tiles(arl_ctx* c, int n, cudaStream_t st) {
     p.a_bytes = 32768; p.stage_bytes = 65536; p.stages = 3;
     p.niter = (n + 63) / 64; p.niter_total = p.niter; p.M = n;
     p.out_f32 = c->grad + c->off_Wfc; p.ldo = c->H; p.fc_HW = HW;
+    if (want_ss && (HW / 4) * (c->H / 256) * 8 <= kSsFcCap) { p.ss_out = c->ss_fc; c->pending_ss_fc = (HW / 4) * (c->H / 256) * 8; }
     return launch_fc_gemm<3, 256>(c, p, dim3(HW / 4, c->H / 256, 1), st);
   }
   p.ncopies = 6;
@@ -797,6 +806,7 @@ int fc_wgrad_tiles(arl_ctx* c, int n, cudaStream_t st) {
   p.a_bytes = 16384; p.stage_bytes = 16384 + 4 * 8192; p.stages = 4;
   p.niter = (n + 63) / 64; p.niter_total = p.niter; p.M = n;
   p.out_f32 = c->grad + c->off_Wfc; p.ldo = c->H; p.fc_HW = HW;
+  if (want_ss && (HW / 2) * (c->H / 256) * 8 <= kSsFcCap) { p.ss_out = c->ss_fc; c->pending_ss_fc = (HW / 2) * (c->H / 256) * 8; }
   return launch_fc_gemm<2, 256>(c, p, dim3(HW / 2, c->H / 256, 1), st);
 }
 
@@ -884,6 +894,8 @@ int alloc_net(arl_ctx* c) {
   if (dev_alloc(c, &c->loss_partial, (size_t)R * 4)) return 1;
   if (dev_alloc(c, &c->sumsq_partial, (size_t)kSumsqBlocks)) return 1;
   if (dev_alloc(c, &c->sumsq_partial_fc, (size_t)kEarlyBlocks)) return 1;
+  if (dev_alloc(c, &c->ss_fin, (size_t)kSsFinCap)) return 1;
+  if (dev_alloc(c, &c->ss_fc, (size_t)kSsFcCap)) return 1;
   if (dev_alloc(c, &c->ticket, 4)) return 1;
   if (dev_alloc(c, &c->hyper, 8)) return 1;
   float one = 1.f;
@@ -1073,6 +1085,11 @@ int get_plan(arl_ctx* c, int n, TrainPlan** out) {
   }
   P.n_jobs = (int)jobs.size();
   P.fin_blocks = (int)((max_total + 255) / 256);
+  for (auto& jb : jobs) {       // one slot per finalize block that owns elements of the job
+    jb.ss_off = P.n_ss;
+    P.n_ss += (int)(((long)jb.rows * jb.cols + 255) / 256);
+  }
+  if (P.n_ss > kSsFinCap) ARL_FAIL(c, "sum-of-squares slot table too small");
   ARL_CHECK(c, cudaMalloc(reinterpret_cast<void**>(&P.jobs_dev), jobs.size() * sizeof(GradJob)));
   ARL_CHECK(c, cudaMemcpy(P.jobs_dev, jobs.data(), jobs.size() * sizeof(GradJob), cudaMemcpyHostToDevice));
   auto res = c->plans.emplace(n, P);
@@ -1083,6 +1100,7 @@ int get_plan(arl_ctx* c, int n, TrainPlan** out) {
 bool early_fc_ok(arl_ctx* c);
 int early_fc_update(arl_ctx* c, cudaStream_t st);
 bool merge_finalize_ok(arl_ctx* c, bool fct);
+bool producer_sumsq_ok(arl_ctx* c, bool fct);
 
 // forward + loss + backward for one minibatch -> flat grad
 int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaStream_t st) {
@@ -1153,8 +1171,10 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
   }
   ConvLayer& LL = c->conv.back();
   // ---- FC wgrad: dW[Kfc][H] = a_last^T dh (direct, permuted rows) ----
+  const bool prod_ss = producer_sumsq_ok(c, fct);
+  c->pending_ss_fin = 0;
   if (fct) {
-    if (fc_wgrad_tiles(c, n, ws)) return 1;
+    if (fc_wgrad_tiles(c, n, ws, prod_ss)) return 1;
     prof_mark(c, "fc_wgrad", ws);
   } else {
     DenseLoader<64> a{};
@@ -1264,7 +1284,10 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
     c->pending_fin = P;        // clip_update folds it into phase 1 of update_fused_kernel (one launch, one pass less)
   } else {
     dim3 grid(P->fin_blocks, P->n_jobs);
-    ARL_CHECK(c, launch_k(finalize_grads_kernel, dim3(grid), dim3(256), 0, st, P->jobs_dev, c->grad));
+    const bool ss = prod_ss && c->pending_ss_fc > 0;
+    if (ss) ARL_CHECK(c, launch_k(finalize_grads_ss_kernel, dim3(grid), dim3(256), 0, st, P->jobs_dev, c->grad, c->ss_fin));
+    else ARL_CHECK(c, launch_k(finalize_grads_kernel, dim3(grid), dim3(256), 0, st, P->jobs_dev, c->grad));
+    c->pending_ss_fin = ss ? P->n_ss : 0;
     c->launches++;
     prof_mark(c, "finalize_grads", st);
     ARL_CHECK(c, cudaGetLastError());
@@ -1311,6 +1334,18 @@ bool merge_finalize_ok(arl_ctx* c, bool fct) {
   static const bool fused = !(getenv("ARL_FUSED_UPDATE") && atoi(getenv("ARL_FUSED_UPDATE")) == 0);
   return on && fused && fct && c->train_step_active && c->opt_set && c->m && c->v && (c->off_Wfc % 4 == 0) &&
          (((long)c->Kfc * c->H) % 4 == 0);
+}
+
+// The kernels that write the flat gradient (FC weight-gradient tiles, finalize_grads) also leave the sums of squares of
+// what they wrote, so the local update that follows needs no pass over the gradient and no grid barrier for the norm.
+// Only inside train_minibatches (nobody can touch the gradient between the two), fused-update configuration.
+// OFF by default (ARL_PRODUCER_SUMSQ=1 enables; all parity tests pass with it): measured 56.6 vs 54.5 ms per iteration —
+// the update kernel drops from 21.8 to 18.7 us, but the finalize kernel with the block reduction takes 11.9 us instead
+// of 5.6 us.
+bool producer_sumsq_ok(arl_ctx* c, bool fct) {
+  static const bool on = getenv("ARL_PRODUCER_SUMSQ") && atoi(getenv("ARL_PRODUCER_SUMSQ")) != 0;
+  static const bool fused = !(getenv("ARL_FUSED_UPDATE") && atoi(getenv("ARL_FUSED_UPDATE")) == 0);
+  return on && fused && fct && c->train_step_active && !early_fc_ok(c) && !merge_finalize_ok(c, fct);
 }
 
 int early_fc_update(arl_ctx* c, cudaStream_t st) {
@@ -1366,7 +1401,13 @@ int clip_update(arl_ctx* c, float gscale, cudaStream_t st) {
   }
   // norm + clip + update in one launch (update_fused_kernel); ARL_FUSED_UPDATE=0 keeps the two-kernel form
   static const bool fused = !(getenv("ARL_FUSED_UPDATE") && atoi(getenv("ARL_FUSED_UPDATE")) == 0);
-  if (fused) {
+  if (c->pending_ss_fin > 0 && c->pending_ss_fc > 0 && gscale == 1.f && u.n_fin_jobs == 0 && u.skip4_len == 0) {
+    // global-norm partials already produced (producer_sumsq_ok): one plain launch, no sum-of-squares pass, no barrier
+    u.sumsq_partial = c->ss_fin; u.n_partial = c->pending_ss_fin;
+    u.sumsq_partial2 = c->ss_fc; u.n_partial2 = c->pending_ss_fc;
+    c->pending_ss_fin = c->pending_ss_fc = 0;
+    ARL_CHECK(c, launch_k(update_kernel, dim3(148 * 4), dim3(256), 0, st, u));
+  } else if (fused) {
     ARL_CHECK(c, launch_coop(update_fused_kernel, dim3(kSumsqBlocks), dim3(256), 0, st, u, c->sumsq_partial, c->ticket));
   } else {
     ARL_CHECK(c, launch_k(sumsq_kernel, dim3(kSumsqBlocks), dim3(256), 0, st, c->grad, c->n_params, gscale, c->sumsq_partial));
@@ -1540,7 +1581,7 @@ void arl_destroy(arl_ctx* c) {
   if (c->shadow_in_comm) { (fc_tiles_ok(c) ? c->wfc_t : c->wfc_bf16) = nullptr; }
   cudaFree(c->wfc_bf16); cudaFree(c->obs16_stage); cudaFree(c->step_obs16); cudaFree(c->roll_obs16); cudaFree(c->pack_jobs_dev); cudaFree(c->fc_partial); cudaFree(c->h); cudaFree(c->dh);
   cudaFree(c->dlogit); cudaFree(c->head_partial); cudaFree(c->head_b_partial); cudaFree(c->loss_partial);
-  cudaFree(c->sumsq_partial); cudaFree(c->sumsq_partial_fc); cudaFree(c->hyper); cudaFree(c->step); cudaFree(c->log_slot); cudaFree(c->log_norm);
+  cudaFree(c->sumsq_partial); cudaFree(c->sumsq_partial_fc); cudaFree(c->ss_fin); cudaFree(c->ss_fc); cudaFree(c->hyper); cudaFree(c->step); cudaFree(c->log_slot); cudaFree(c->log_norm);
   cudaFree(c->log_loss); cudaFree(c->mb_counter); cudaFree(c->valid_count);
   for (auto& kv : c->plans) cudaFree(kv.second.jobs_dev);
   if (c->rollout_graph) cudaGraphExecDestroy(c->rollout_graph);
@@ -1881,7 +1922,10 @@ int train_minibatches(arl_ctx* c, const int* idx, int mb_size, int count, int sy
   struct Active {      // grad_minibatch may update the FC weights early only when the local clip_update follows it
     arl_ctx* c;
     Active(arl_ctx* c_, bool on) : c(c_) { c->train_step_active = on; }
-    ~Active() { c->train_step_active = false; c->early_fc_done = false; c->pending_fin = nullptr; }
+    ~Active() {
+      c->train_step_active = false; c->early_fc_done = false; c->pending_fin = nullptr;
+      c->pending_ss_fin = c->pending_ss_fc = 0;
+    }
   } active(c, sync == 0);
   if (!(c->sampler_set && c->t_obs == c->sc.observations && c->roll_obs16) || (sync && c->sync_graph_failed)) {
     // training inputs that are not the sampler's rollout buffers: plain launches, one minibatch at a time
@@ -2156,6 +2200,7 @@ int arl_profile_graph(arl_ctx* c, int kind, const int* idx, int mb_size, int rep
     c->train_step_active = false;
     c->early_fc_done = false;
     c->pending_fin = nullptr;
+    c->pending_ss_fin = c->pending_ss_fc = 0;
   } else if (kind == 1) {
     rc = rollout_step(c, 0, nullptr, cap_s);
   } else {

@@ -46,8 +46,10 @@ struct FcParams {
   const __nv_bfloat16* act;    // act_fc planes (mask source), plane stride act_plane
   long act_plane;
   int sc_Wo, sc_S, sc_Wp, sc_pad;
-  // KIND 2
+  // KIND 2 / 3
   int fc_HW;                   // D row (hw, c) -> gradient row c*HW + hw
+  double* ss_out;              // optional: per-epilogue-warp sums of squares of the gradient rows written,
+                               // [(blockIdx.y * gridDim.x + blockIdx.x) * 8 + warp - 2] (global-norm partials)
 };
 
 template <int KIND, int BN>
@@ -139,6 +141,7 @@ __global__ void __launch_bounds__(kFcThreads, 1) fc_gemm_kernel(const __grid_con
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + h * HC;
     // all MMAs are complete (done_bar): the operand stages are free -> per-warp transpose scratch for the row stores
     const uint32_t scratch = smem_base + (uint32_t)(warp - 2) * kRowStoreScratch;
+    double ssq = 0.0;
 #pragma unroll 1
     for (int cc0 = 0; cc0 < NACC * HC; cc0 += 32) {
       const int acc = cc0 / HC;               // KIND 3: second accumulator = planes 2, 3 of the tile
@@ -187,7 +190,17 @@ __global__ void __launch_bounds__(kFcThreads, 1) fc_gemm_kernel(const __grid_con
         const int hw = blockIdx.x * 2 * NACC + 2 * acc + (r >> 6), c = r & 63;
         float* dst = p.out_f32 + ((long)c * p.fc_HW + hw) * p.ldo + blockIdx.y * BN + col;
         store_rows32_coalesced(scratch, v, dst, hw < p.fc_HW, lane);
+        if (p.ss_out && hw < p.fc_HW) {
+          float s32 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s32 = fmaf(__uint_as_float(v[i]), __uint_as_float(v[i]), s32);
+          ssq += (double)s32;
+        }
       }
+    }
+    if (KIND >= 2 && p.ss_out) {
+      ssq = warp_sum_d(ssq);
+      if (lane == 0) p.ss_out[((long)blockIdx.y * gridDim.x + blockIdx.x) * 8 + (warp - 2)] = ssq;
     }
     tc_fence_before();
   }

@@ -992,6 +992,7 @@ struct GradJob {
   // GM_PCONV (pconv.cuh): r = k' = ((ty*T + tx)*P + plane)*64 + ch, cell channel cc = plane*64 + ch decoded as
   // (ci, py, px) [ci_major] or (py, px, ci); ky = ty*s2d + py, kx = tx*s2d + px
   int T, P, ci_major;
+  int ss_off;         // first slot of this job's per-block sums of squares (finalize_grads_kernel ss_out), see below
 };
 
 // cell channel -> (ci, py, px) of a space-to-depth(s) cell over C input channels
@@ -1074,6 +1075,33 @@ __global__ void __launch_bounds__(256) finalize_grads_kernel(const GradJob* __re
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     float acc;
     finalize_elem(jb, i, grad, acc);
+  }
+}
+
+// Variant that also leaves the sum of squares of what each block wrote in ss_out[jb.ss_off + blockIdx.x] (blocks
+// blockIdx.x < ceil(rows*cols / 256) — the others have no element), so the update kernel that follows needs neither its
+// own pass over the gradient nor a grid-wide barrier for the global norm (ARL_PRODUCER_SUMSQ=1, see api.cu).
+__global__ void __launch_bounds__(256) finalize_grads_ss_kernel(const GradJob* __restrict__ jobs, float* __restrict__ grad,
+                                                                double* __restrict__ ss_out) {
+  pdl_wait();
+  pdl_trigger();
+  const GradJob jb = jobs[blockIdx.y];
+  const long total = (long)jb.rows * jb.cols;
+  double ss = 0.0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    float acc;
+    if (finalize_elem(jb, i, grad, acc)) ss += (double)(acc * acc);
+  }
+  if ((long)blockIdx.x * blockDim.x < total) {
+    __shared__ double s_ss[8];
+    ss = warp_sum_d(ss);
+    if ((threadIdx.x & 31) == 0) s_ss[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += s_ss[w];
+      ss_out[jb.ss_off + blockIdx.x] = t;
+    }
   }
 }
 
