@@ -123,6 +123,8 @@ struct arl_ctx {
   __nv_bfloat16* wfc_bf16 = nullptr;   // [Kfc][H] bf16 copy of the FC weights in the reference's row order
   PackJob* pack_jobs_dev = nullptr;
   int n_pack_jobs = 0;
+  long conv_pack_end = 0;              // > 0: every conv pack job is a pconv tap-tile pack; conv weights end here (flat index)
+  unsigned long long* pk_slots = nullptr;   // [conv_pack_end][2] bf16 slot addresses of each conv weight (0 = none)
   // bound vectors
   float *params = nullptr, *grad = nullptr, *m = nullptr, *v = nullptr;
   // workspaces
@@ -873,6 +875,34 @@ int alloc_net(arl_ctx* c) {
     pj.push_back(fc);
   }
   c->n_pack_jobs = (int)pj.size();
+  {
+    long end = 0;
+    bool all_pconv = pj.size() >= 2;
+    for (size_t i = 0; i + 1 < pj.size(); ++i) {
+      all_pconv = all_pconv && (pj[i].kind == PK_PCONV || pj[i].kind == PK_PCONV_DGRAD);
+      end = std::max(end, pj[i].src_off + (long)pj[i].Cout * pj[i].C * pj[i].kh * pj[i].kw);
+    }
+    end = (end + 3) / 4 * 4;        // whole float4 groups (the elements after the last conv weight are biases: no slot)
+    c->conv_pack_end = (all_pconv && end <= c->n_params) ? end : 0;
+    if (c->conv_pack_end > 0) {
+      // element -> bf16 slot addresses in the forward / data-gradient packs (inverse of pack_job_body, see pack_slot_of)
+      std::vector<unsigned long long> tab((size_t)c->conv_pack_end * 2, 0ULL);
+      for (long e = 0; e < c->conv_pack_end; ++e) {
+        int nslot = 0;
+        for (size_t i = 0; i + 1 < pj.size(); ++i) {
+          const long d = pack_slot_of(pj[i], e);
+          if (d < 0) continue;
+          if (nslot >= 2) { c->conv_pack_end = 0; break; }     // more than two packs hold this weight: keep the pack launch
+          tab[(size_t)e * 2 + nslot++] = (unsigned long long)(uintptr_t)(pj[i].dst + d);
+        }
+        if (c->conv_pack_end == 0) break;
+      }
+      if (c->conv_pack_end > 0) {
+        if (dev_alloc(c, &c->pk_slots, tab.size())) return 1;
+        ARL_CHECK(c, cudaMemcpy(c->pk_slots, tab.data(), tab.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+      }
+    }
+  }
   if (dev_alloc(c, &c->pack_jobs_dev, pj.size())) return 1;
   ARL_CHECK(c, cudaMemcpy(c->pack_jobs_dev, pj.data(), pj.size() * sizeof(PackJob), cudaMemcpyHostToDevice));
   if (dev_alloc(c, &c->obs16_stage, (size_t)R * c->obs16_elems + 64 * 1024)) return 1;
@@ -1385,7 +1415,7 @@ UpdateParams update_params(arl_ctx* c, float gscale, bool* fused_cast_out) {
 int clip_update(arl_ctx* c, float gscale, cudaStream_t st) {
   if (!c->opt_set) ARL_FAIL(c, "optimizer not configured");
   if (!c->m || !c->v) ARL_FAIL(c, "optimizer state not bound");
-  bool fused_cast = false;
+  bool fused_cast = false, scattered = false;
   UpdateParams u = update_params(c, gscale, &fused_cast);
   if (c->early_fc_done) {
     // the FC range is done (update_range_kernel): norm over the rest + its partials, update the rest
@@ -1408,6 +1438,14 @@ int clip_update(arl_ctx* c, float gscale, cudaStream_t st) {
     c->pending_ss_fin = c->pending_ss_fc = 0;
     ARL_CHECK(c, launch_k(update_kernel, dim3(148 * 4), dim3(256), 0, st, u));
   } else if (fused) {
+    // conv operand packs refreshed by the update itself + counters advanced by its last block: no pack launch at all
+    static const bool scatter_on = !(getenv("ARL_SCATTER_PACK") && atoi(getenv("ARL_SCATTER_PACK")) == 0);
+    if (scatter_on && fused_cast && c->pc_mode >= 2 && c->n_pack_jobs >= 2 && c->conv_pack_end > 0 && c->pk_slots) {
+      u.pk_slots = c->pk_slots; u.n_pk_jobs = c->n_pack_jobs - 1;       // (the last job is the FC copy: fused_cast)
+      u.conv_end = c->conv_pack_end;
+      u.adv_done = c->ticket + 1; u.adv_log_slot = c->log_slot; u.adv_mb = c->mb_counter;
+      scattered = true;
+    }
     ARL_CHECK(c, launch_coop(update_fused_kernel, dim3(kSumsqBlocks), dim3(256), 0, st, u, c->sumsq_partial, c->ticket));
   } else {
     ARL_CHECK(c, launch_k(sumsq_kernel, dim3(kSumsqBlocks), dim3(256), 0, st, c->grad, c->n_params, gscale, c->sumsq_partial));
@@ -1418,6 +1456,7 @@ int clip_update(arl_ctx* c, float gscale, cudaStream_t st) {
   c->launches++;
   prof_mark(c, "clip_update", st);
   ARL_CHECK(c, cudaGetLastError());
+  if (scattered) return 0;
   return pack_weights(c, st, !fused_cast, true);
 }
 
@@ -1581,6 +1620,7 @@ void arl_destroy(arl_ctx* c) {
   if (c->shadow_in_comm) { (fc_tiles_ok(c) ? c->wfc_t : c->wfc_bf16) = nullptr; }
   cudaFree(c->wfc_bf16); cudaFree(c->obs16_stage); cudaFree(c->step_obs16); cudaFree(c->roll_obs16); cudaFree(c->pack_jobs_dev); cudaFree(c->fc_partial); cudaFree(c->h); cudaFree(c->dh);
   cudaFree(c->dlogit); cudaFree(c->head_partial); cudaFree(c->head_b_partial); cudaFree(c->loss_partial);
+  cudaFree(c->pk_slots);
   cudaFree(c->sumsq_partial); cudaFree(c->sumsq_partial_fc); cudaFree(c->ss_fin); cudaFree(c->ss_fc); cudaFree(c->hyper); cudaFree(c->step); cudaFree(c->log_slot); cudaFree(c->log_norm);
   cudaFree(c->log_loss); cudaFree(c->mb_counter); cudaFree(c->valid_count);
   for (auto& kv : c->plans) cudaFree(kv.second.jobs_dev);

@@ -1159,6 +1159,24 @@ ARL_DEVINL long fc_tile_index(long r, int j, int HW, int H) {
   return (((long)hw * (H >> 6) + (j >> 6)) * 64 + c) * 64 + (((((j & 63) >> 3) ^ (c & 7)) << 3) | (j & 7));
 }
 
+enum PackKind { PK_CONV_NHWC = 0, PK_CONV_S2D = 1, PK_CONV_DGRAD = 2, PK_CAST = 3, PK_PCONV = 4, PK_PCONV_DGRAD = 5, PK_FC_TILES = 6 };
+
+struct PackJob {
+  __nv_bfloat16* dst;
+  long src_off;        // offset of W in the flat params
+  int kind;
+  int rows, cols;      // dst is [rows][cols]
+  int Cout, C, kh, kw; // conv dims
+  int s, ry, rx, Tx;   // dgrad class (k' = (ty*Tx+tx)*Cout + o ; ky = ry + s*ty ; kx = rx + s*tx)
+  int HW;              // FC: k' = hw*C + c  <- W[(c*HW + hw)][j]
+  int ldsrc;           // FC: hidden size
+  // PK_PCONV / PK_PCONV_DGRAD (pconv.cuh): dst = [blocks][N][64] with 16-byte chunks XOR-swizzled by (row & 7);
+  // forward: block = (ty*T + tx)*P + plane, row = cout, column ch -> cell channel plane*64 + ch;
+  // dgrad  : block = (ey*T + ex)*P + plane_out, row = input cell channel, column ch -> cout = plane_out*64 + ch,
+  //          tap (ty, tx) = (T-1-ey, T-1-ex)
+  int T, P, N, ci_major;
+};
+
 struct UpdateParams {
   float* param; const float* grad; float* m; float* v;
   long n;
@@ -1184,7 +1202,51 @@ struct UpdateParams {
   const GradJob* fin_jobs; int n_fin_jobs;
   long fc4_begin, fc4_len;
   uint32_t shadow_H_magic, shadow_HW_magic;   // floor(2^32/d) + 1: the tile index needs two divisions per float4 group
+  // n_pk_jobs > 0: the conv operand packs (pconv.cuh tap tiles, forward and data-gradient variants) are refreshed by
+  // the thread that updates the weight — a scatter through the inverse of pack_weights_kernel's index map — instead of
+  // a separate pack launch; elements >= conv_end are never conv weights
+  const unsigned long long* pk_slots; int n_pk_jobs; long conv_end;   // pk_slots: [conv_end][2] device addresses
+  // adv_done != nullptr: the last block to finish advances the device-side counters (what pack_weights_kernel did)
+  unsigned long long* adv_done; int* adv_log_slot; int* adv_mb;
 };
+
+// inverse of pack_job_body's PK_PCONV / PK_PCONV_DGRAD map, evaluated ONCE on the host (pack_slot_of, api.cu) into a
+// table of device addresses: element e of the flat vector -> the (at most two) bf16 slots that hold it, 0 = none.
+// (Computing the inverse in the kernel was measured: the ~20 K float4 groups of conv weights sit in the first 79 blocks
+// and their integer divisions made the update kernel 10 us slower than the pack launch it replaced.)
+__host__ __device__ inline long pack_slot_of(const PackJob& jb, long e) {
+  const long rel = e - jb.src_off;
+  if (rel < 0 || rel >= (long)jb.Cout * jb.C * jb.kh * jb.kw) return -1;
+  // W[co][ci][kyf][kxf], filters stored flipped: correlation tap (ky, kx) = (kh-1-kyf, kw-1-kxf)
+  const int kxf = (int)(rel % jb.kw);
+  long t = rel / jb.kw;
+  const int kyf = (int)(t % jb.kh);
+  t /= jb.kh;
+  const int ci = (int)(t % jb.C), co = (int)(t / jb.C);
+  const int ky = jb.kh - 1 - kyf, kx = jb.kw - 1 - kxf;
+  const int ty = ky / jb.s, py = ky - ty * jb.s, tx = kx / jb.s, px = kx - tx * jb.s;
+  const int cc = jb.ci_major ? (ci * jb.s * jb.s + py * jb.s + px) : ((py * jb.s + px) * jb.C + ci);   // pc_decode_channel^-1
+  int pl, k, n_, blk;
+  if (jb.kind == PK_PCONV) { pl = cc >> 6; k = cc & 63; n_ = co; blk = (ty * jb.T + tx) * jb.P + pl; }
+  else { pl = co >> 6; k = co & 63; n_ = cc; blk = ((jb.T - 1 - ty) * jb.T + (jb.T - 1 - tx)) * jb.P + pl; }
+  const long r = (long)blk * jb.N + n_;
+  if (pl >= jb.P || n_ >= jb.N || r >= jb.rows) return -1;
+  return r * 64 + ((((k >> 3) ^ (n_ & 7)) << 3) | (k & 7));
+}
+
+// float4 group i of the (just updated) parameters -> its bf16 slots; 8 addresses = 64 contiguous bytes of the table
+ARL_DEVINL void scatter_conv_pack4(const UpdateParams& p, long i) {
+  const float4 w = reinterpret_cast<const float4*>(p.param)[i];
+  const float pp[4] = {w.x, w.y, w.z, w.w};
+  const ulonglong2* tab = reinterpret_cast<const ulonglong2*>(p.pk_slots + 8 * i);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const ulonglong2 a = __ldg(tab + k);
+    const __nv_bfloat16 v = __float2bfloat16_rn(pp[k]);
+    if (a.x) *reinterpret_cast<__nv_bfloat16*>(a.x) = v;
+    if (a.y) *reinterpret_cast<__nv_bfloat16*>(a.y) = v;
+  }
+}
 
 ARL_DEVINL void update_body(const UpdateParams& p);
 
@@ -1263,6 +1325,16 @@ __global__ void __launch_bounds__(256, 4) update_fused_kernel(UpdateParams p, do
   }
   __syncthreads();
   update_body(p);
+  if (p.adv_done) {
+    // every block read the update count / log slot in update_body before it gets here: the LAST block to arrive may
+    // advance them (the 64-bit arrival counter only grows, so the launch replays from a CUDA graph)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned long long t = atomicAdd(p.adv_done, 1ULL);
+      if ((t + 1ULL) % gridDim.x == 0ULL) { p.step[0] += 1; p.adv_log_slot[0] += 1; p.adv_mb[0] += 1; }
+    }
+  }
 }
 
 // Adam / RMSProp on float4 group i (+ the bf16 operand copy of the FC weights, refreshed in the same pass)
@@ -1388,6 +1460,15 @@ ARL_DEVINL void update_body(const UpdateParams& p) {
   const long n4 = (p.n >> 2) - p.skip4_len;
   for (long j = (long)blockIdx.x * blockDim.x + threadIdx.x; j < n4; j += (long)gridDim.x * blockDim.x)
     update_vec4(p, j < p.skip4_begin ? j : j + p.skip4_len, scale, alpha);
+  if (p.n_pk_jobs > 0) {
+    // conv operand packs: every thread re-reads the conv-weight groups IT just updated (same index walk, own writes)
+    // and scatters them through the slot table — a separate loop, so the main loop's registers are not squeezed
+    for (long j = (long)blockIdx.x * blockDim.x + threadIdx.x; j < n4; j += (long)gridDim.x * blockDim.x) {
+      const long i = j < p.skip4_begin ? j : j + p.skip4_len;
+      if ((i << 2) + 4 > p.conv_end) break;          // i grows with j: nothing further is a conv weight
+      scatter_conv_pack4(p, i);
+    }
+  }
   if (blockIdx.x == 0 && threadIdx.x < (p.n & 3)) {
     long i = ((p.n >> 2) << 2) + threadIdx.x;
     float g = p.grad[i] * scale;
@@ -1414,24 +1495,6 @@ __global__ void advance_counters_kernel(int* step, int* log_slot, int* mb_counte
 // ===========================================================================
 // Weight packing: fp32 master (reference layout) -> bf16 operand matrices for the GEMM tiles
 // ===========================================================================
-enum PackKind { PK_CONV_NHWC = 0, PK_CONV_S2D = 1, PK_CONV_DGRAD = 2, PK_CAST = 3, PK_PCONV = 4, PK_PCONV_DGRAD = 5, PK_FC_TILES = 6 };
-
-struct PackJob {
-  __nv_bfloat16* dst;
-  long src_off;        // offset of W in the flat params
-  int kind;
-  int rows, cols;      // dst is [rows][cols]
-  int Cout, C, kh, kw; // conv dims
-  int s, ry, rx, Tx;   // dgrad class (k' = (ty*Tx+tx)*Cout + o ; ky = ry + s*ty ; kx = rx + s*tx)
-  int HW;              // FC: k' = hw*C + c  <- W[(c*HW + hw)][j]
-  int ldsrc;           // FC: hidden size
-  // PK_PCONV / PK_PCONV_DGRAD (pconv.cuh): dst = [blocks][N][64] with 16-byte chunks XOR-swizzled by (row & 7);
-  // forward: block = (ty*T + tx)*P + plane, row = cout, column ch -> cell channel plane*64 + ch;
-  // dgrad  : block = (ey*T + ex)*P + plane_out, row = input cell channel, column ch -> cout = plane_out*64 + ch,
-  //          tap (ty, tx) = (T-1-ey, T-1-ex)
-  int T, P, N, ci_major;
-};
-
 ARL_DEVINL void pack_job_body(const PackJob& jb, const float* __restrict__ params, long first, long stride);
 
 __global__ void __launch_bounds__(256) pack_weights_kernel(const PackJob* __restrict__ jobs,

@@ -463,6 +463,21 @@ def test_operand_copies_refreshed_by_the_update_match_a_fresh_pack():
             fresh.engine.forward(obs, prob=p2, value=v2)
             torch.cuda.synchronize()
             assert torch.equal(p1, p2) and torch.equal(v1, v2)
+            # ... and the data-gradient operand packs: the same minibatch gradient, bit for bit
+            rng = np.random.RandomState(5)
+            n = 64
+            act = rng.randint(0, 4, n).astype(np.uint8)
+            adv = rng.randn(n).astype(np.float32); ret = rng.randn(n).astype(np.float32)
+            oldp = rng.dirichlet(np.ones(4), n).astype(np.float32); oldv = rng.randn(n).astype(np.float32)
+            grads = []
+            for e in (pol.engine, fresh.engine):
+                e.opt_configure(algo=0, clip_param=0.2, v_loss_coeff=1.0, ent_loss_coeff=0.01, update=0, learning_rate=1e-3,
+                                beta1=0.9, beta2=0.999, epsilon=1e-5, rho=0.9, grad_norm_clip=-1.0)
+                e.bind_train_inputs(*[torch.tensor(x).cuda() for x in (res_obs, act, adv, ret, oldv, oldp)], valids=None)
+                e.grad_minibatch(torch.arange(n, dtype=torch.int32, device="cuda"), n)
+                torch.cuda.synchronize()
+                grads.append(t2n(e.grad).copy())
+            assert np.array_equal(grads[0], grads[1])
         finally:
             fresh.engine.close()
     finally:
