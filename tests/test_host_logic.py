@@ -179,3 +179,31 @@ def test_async_optimizer_argument_checks():
     ppo = mAPPO().optimizer
     assert isinstance(ppo, AsyncPpoOptimizer) and ppo.parallelism_tag == "asynchronous"
     assert ppo.max_rows(10 ** 6) == 512
+
+
+def test_eval_sampler_constructor_arithmetic():
+    """AAOEvalSampler: eval_horizon = eval_steps // (eval_envs_per * n_parallel * 2) (sampler_with_eval.py:8-14); no GPU
+    is touched before initialize()"""
+    from accel_rl_b200.envs import AtariEnv
+    from accel_rl_b200.sampler import AAOEvalSampler
+    smp = AAOEvalSampler(125000, 2, EnvCls=AtariEnv, env_args=dict(game="pong"), horizon=5, n_parallel=8, envs_per=4)
+    assert smp._total_n_eval_envs == 32 and smp.eval_horizon == 125000 // 32
+    assert smp.total_n_envs == 64 and smp.alternating
+    with pytest.raises(ValueError):
+        AAOEvalSampler(10, 2, EnvCls=AtariEnv, env_args=dict(game="pong"), horizon=5, n_parallel=8, envs_per=4)
+
+
+def test_pg_algorithms_accept_the_eval_runner_hooks():
+    """AccelRLEval calls algo.prep_eval / post_eval (runners/accel_rl.py:137-139); A2C/PPO define them as no-ops"""
+    from accel_rl_b200.algos import A2C, PPO
+    for algo in (A2C(), PPO()):
+        assert algo.prep_eval(0) is None and algo.post_eval(0) is None
+
+
+def test_bench_host_worker_count_divides_the_envs():
+    import argparse
+    import os
+    import bench
+    for envs in (256, 64, 48):
+        w = bench.host_workers(argparse.Namespace(envs=envs))
+        assert w >= 2 and envs % w == 0 and w <= max(2, (os.cpu_count() or 2))
