@@ -1626,6 +1626,13 @@ void arl_destroy(arl_ctx* c) {
   for (auto& kv : c->plans) cudaFree(kv.second.jobs_dev);
   if (c->rollout_graph) cudaGraphExecDestroy(c->rollout_graph);
   if (c->train_graph) cudaGraphExecDestroy(c->train_graph);
+  // forked streams / fork-join events of the training step (created lazily by grad_minibatch)
+  for (auto& e : c->ev_fork) if (e) cudaEventDestroy(e);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->ev_join2) cudaEventDestroy(c->ev_join2);
+  if (c->ev_fcd) cudaEventDestroy(c->ev_fcd);
+  if (c->side) cudaStreamDestroy(c->side);
+  if (c->side2) cudaStreamDestroy(c->side2);
   cudaFree(c->est.f); cudaFree(c->cmd); cudaFree(c->rows_tab); cudaFree(c->tout.count);
   {
     arl_ctx::SamplerSlot& o = c->slots[1 - c->cur_slot];     // the parked sampler
