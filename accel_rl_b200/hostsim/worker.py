@@ -88,3 +88,14 @@ def worker_main(rank, env_lo, env_hi, n_envs, emu_factory, env_kwargs, frame_sha
                     fl = FLAG_SKIP                          # this step's reward/done ARE recorded, the obs is not advanced
             ext[e] = (r, raw, int(bool(d)), int(bool(nr)), fl, 0)
         step_done.release()
+
+
+def profiling_worker(profile_pathname, rank, *args):
+    """worker_main under cProfile, dumped to <profile_pathname>_sim_<rank>.prof when the worker quits
+    (reference: sampler/util.py:10-19 profiling_process, enabled by the sampler's profile_pathname argument)"""
+    import cProfile
+    prof = cProfile.Profile()
+    try:
+        prof.runcall(worker_main, rank, *args)
+    finally:
+        prof.dump_stats("{}_sim_{}.prof".format(profile_pathname, rank))

@@ -105,10 +105,13 @@ class HostEmulatorSampler(ActsrvAltOvrlpSampler):
                           max_start_noops=int(env.max_start_noops), rgb=len(self._frame_shape) == 3)
         for w in range(n_workers):
             lo, hi = w * self.envs_per, (w + 1) * self.envs_per
-            pr = ctx.Process(target=W.worker_main, daemon=True,
-                             args=(w, lo, hi, B, factory, env_kwargs, self._frame_shape, self._shared, self._cmd,
-                                   self._act_ready[w], self._step_done[w], self._infos_queue, self.seed + w,
-                                   bool(self.mid_batch_reset), self.max_path_length, float(self.discount)))
+            args = (w, lo, hi, B, factory, env_kwargs, self._frame_shape, self._shared, self._cmd,
+                    self._act_ready[w], self._step_done[w], self._infos_queue, self.seed + w,
+                    bool(self.mid_batch_reset), self.max_path_length, float(self.discount))
+            if self.profile_pathname is not None:        # cProfile per simulator worker (sampler/util.py:10-19)
+                pr = ctx.Process(target=W.profiling_worker, daemon=True, args=(self.profile_pathname,) + args)
+            else:
+                pr = ctx.Process(target=W.worker_main, daemon=True, args=args)
             pr.start()
             self._procs.append(pr)
         # start_envs: every worker resets its envs and hands over the first screens

@@ -161,3 +161,34 @@ def test_product_synthetic_emulator_follows_the_oracle_rules():
             assert np.array_equal(buf, pool[synth_ale.frame_index(RULES, e, f)])
         em.reset_game()
         assert em.f == 0
+
+
+def test_profiling_worker_dumps_a_profile(tmp_path):
+    """profile_pathname (sampler/base.py:32-43, sampler/util.py:10-19): the worker runs under cProfile and leaves
+    <path>_sim_<rank>.prof when it quits"""
+    import pstats
+    ctx = mp.get_context("spawn")
+    B, shape, fb = 2, (210, 160), 210 * 160
+    shared = dict(frames=ctx.RawArray(C.c_uint8, B * 2 * fb), ext=ctx.RawArray(C.c_uint8, B * W.EXT_DTYPE.itemsize),
+                  act=ctx.RawArray(C.c_uint8, B))
+    cmd = ctx.Value("i", W.CMD_STEP, lock=False)
+    ready, done, q = ctx.Semaphore(0), ctx.Semaphore(0), ctx.Queue()
+    env_kwargs = dict(frame_skip=4, clip_reward=True, episodic_lives=True, max_start_noops=0, rgb=False)
+    path = str(tmp_path / "prof")
+    p = ctx.Process(target=W.profiling_worker, daemon=True,
+                    args=(path, 0, 0, B, B, partial(fake_ale.make, rules=RULES), env_kwargs, shape, shared, cmd, ready, done, q,
+                          3, True, 27000, 0.99))
+    p.start()
+    try:
+        assert done.acquire(timeout=120)
+        for _ in range(3):
+            cmd.value = W.CMD_STEP
+            ready.release()
+            assert done.acquire(timeout=120)
+    finally:
+        cmd.value = W.CMD_QUIT
+        ready.release()
+        p.join(timeout=30)
+    assert p.exitcode == 0
+    st = pstats.Stats(path + "_sim_0.prof")
+    assert any("worker_main" in str(k) for k in st.stats)
