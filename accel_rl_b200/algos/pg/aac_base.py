@@ -16,6 +16,14 @@ import numpy as np
 LR_SCHEDULES = ["linear"]
 
 
+def with_defaults(optimizer_args, defaults):
+    """the user's optimizer_args win; anything they leave out comes from the algorithm's defaults
+    (the reference fills the caller's dict in place, a2c.py:30-36 / ppo.py:32-37; a copy is returned here)"""
+    merged = dict(defaults)
+    merged.update(optimizer_args or {})
+    return merged
+
+
 class AdvActorCriticBase(RLAlgorithm):
     def __init__(self, discount, gae_lambda, v_loss_coeff=1, ent_loss_coeff=0.01, standardize_adv=False,
                  lr_schedule=None):

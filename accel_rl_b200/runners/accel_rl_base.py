@@ -65,17 +65,12 @@ class AccelRLBase(Runner):
             flat_params.size, *nbytes_unit(flat_params.nbytes)))
 
     def get_n_itr(self, sample_size):
+        """iterations to run: n_steps / sample_size rounded to the nearest whole number of log intervals (ties round
+        down), plus one so the last interval is logged (accel_rl_base.py:84-97)"""
         self._sample_size = sample_size
-        self._log_interval_itrs = max(self._log_steps // sample_size, 1)
-        n_itr = max(self.n_steps // sample_size, 1)
-        itr_rem = n_itr % self._log_interval_itrs
-        if itr_rem <= self._log_interval_itrs / 2.:
-            n_itr -= itr_rem
-        else:
-            n_itr += (self._log_interval_itrs - itr_rem)
-        assert n_itr % self._log_interval_itrs == 0
-        n_itr += 1
-        self._n_itr = n_itr
+        interval = self._log_interval_itrs = max(self._log_steps // sample_size, 1)
+        whole, rem = divmod(max(self.n_steps // sample_size, 1), interval)
+        self._n_itr = n_itr = interval * (whole + (1 if 2 * rem > interval else 0)) + 1
         logger.log("Iterations to run: {}".format(n_itr))
         return n_itr
 
@@ -113,20 +108,18 @@ class AccelRLBase(Runner):
         logger.save_itr_params(itr, self.get_itr_snapshot(itr))
 
     def _log_infos(self, traj_infos=None):
-        if traj_infos is None:
-            traj_infos = self._traj_infos
-        if traj_infos:
-            for k in traj_infos[0]:
-                if not k.startswith("_") and k != "env":
-                    logger.record_tabular_misc_stat(k, [info[k] for info in traj_infos])
-        if self._opt_infos:
-            for k, v in self._opt_infos.items():
-                logger.record_tabular_misc_stat(k, v)
-        self._opt_infos = {k: list() for k in self._opt_infos}
-        new_param_vector = self.policy.get_param_values()
-        logger.record_tabular("ParamsNorm", np.sqrt(np.sum(new_param_vector ** 2)))
-        params_diff = new_param_vector - self._initial_param_vector
-        logger.record_tabular("NormFromInit", np.sqrt(np.sum(params_diff ** 2)))
+        """Average/Std/Median/Min/Max of every public TrajInfo field and of every optimizer diagnostic collected since
+        the last log, then the parameter norms (accel_rl_base.py:122-146)"""
+        traj_infos = self._traj_infos if traj_infos is None else traj_infos
+        fields = [k for k in (traj_infos[0] if traj_infos else ()) if not k.startswith("_") and k != "env"]
+        for k in fields:
+            logger.record_tabular_misc_stat(k, [info[k] for info in traj_infos])
+        for k, values in (self._opt_infos or {}).items():
+            logger.record_tabular_misc_stat(k, values)
+            self._opt_infos[k] = list()
+        params = self.policy.get_param_values()
+        for name, vec in (("ParamsNorm", params), ("NormFromInit", params - self._initial_param_vector)):
+            logger.record_tabular(name, np.sqrt(np.sum(vec ** 2)))
 
     @property
     def parallelism_tag(self):
