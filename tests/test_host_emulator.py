@@ -12,7 +12,7 @@ import pytest
 
 from accel_rl_b200.hostsim import worker as W
 from accel_rl_b200.hostsim.atari_env import HostAtariEnv, FLAG_RESET, FLAG_SKIP, FLAG_NO_RECORD
-from oracle import frame as oframe, sampler as osampler, synth_ale
+from oracle import frame as oframe, ref_harness, sampler as osampler, synth_ale
 from tests import fake_ale
 
 RULES = dict(synth_ale.DEFAULT_RULES, pool_frames=32, life_base=9, life_mod=5, reward_mod=7)
@@ -192,3 +192,45 @@ def test_profiling_worker_dumps_a_profile(tmp_path):
     assert p.exitcode == 0
     st = pstats.Stats(path + "_sim_0.prof")
     assert any("worker_main" in str(k) for k in st.stats)
+
+
+@pytest.mark.skipif(not ref_harness.available(), reason="the reference tree only exists in the build container")
+@pytest.mark.parametrize("episodic,noops", [(True, 0), (False, 0), (True, 7)])
+def test_host_atari_env_vs_the_real_reference_atari_env(episodic, noops):
+    """HostAtariEnv next to the REFERENCE'S OWN AtariEnv (accel_rl/envs/atari_env.py, imported unmodified through
+    oracle/ref_harness.py with the synthetic ALE as `atari_py`): same emulator calls in the same order — checked through
+    the emulator's frame counter — same rewards / dones / infos, and the exported frame pair + flag rebuild the
+    reference's observation bit for bit (its cv2.resize included), with start no-ops drawn from the same numpy state."""
+    pool = synth_ale.make_pool(32, seed=0)
+    ref_harness.install(pool=pool, rules=RULES)
+    env_mod = ref_harness.ref("accel_rl.envs.atari_env")
+    for e in (0, 3):
+        synth_ale.SynthALE.next_env_id = e
+        np.random.seed(100 + e)
+        renv = env_mod.AtariEnv(game="breakout", clip_reward=True, episodic_lives=episodic, max_start_noops=noops)
+        assert renv.ale.env_id == e
+        emu = fake_ale.make(e, RULES)
+        host = HostAtariEnv(emu, clip_reward=True, episodic_lives=episodic, max_start_noops=noops)
+        f1, f2 = np.zeros((210, 160), np.uint8), np.zeros((210, 160), np.uint8)
+        np.random.seed(100 + e)                       # the reference ctor ends with reset(): same no-op draw
+        obs = _apply(np.zeros((4, oframe.H, oframe.W), np.uint8), f1, f2, host.reset(f2))
+        assert emu.f == renv.ale.f and np.array_equal(obs, renv.get_obs())
+        rng = np.random.RandomState(e)
+        overs = 0
+        for k in range(150):
+            a = int(rng.randint(0, 4))
+            o2, r2, d2, info = renv.step(a)
+            r, raw, d, nr, fl = host.step(a, f1, f2)
+            obs = _apply(obs, f1, f2, fl)
+            assert emu.f == renv.ale.f, k
+            assert np.array_equal(obs, o2), k
+            assert r == r2 and raw == info["raw_reward"] and bool(d) == bool(d2)
+            assert (nr if episodic else None) == info.get("need_reset")
+            if info.get("need_reset", d2):             # the collector's reset (worker.py:43-45)
+                overs += 1
+                np.random.seed(1000 + k)
+                o3 = renv.reset()
+                np.random.seed(1000 + k)
+                obs = _apply(obs, f1, f2, host.reset(f2))
+                assert emu.f == renv.ale.f and np.array_equal(obs, o3)
+        assert overs > 0
