@@ -31,62 +31,82 @@ def views(shared, n_envs, frame_shape):
     return frames, ext, act
 
 
+class Collector(object):
+    """The envs of one worker and the collector rules applied to them (worker.py:25-113): `start` = start_envs,
+    `step` = one time step of collect(), `reset_needed` = reset_needed_envs.  Every call leaves, for each env e it
+    owns, the record ext[e] and — unless the record says the observation does not advance — the raw screens
+    frames[e, 0] / frames[e, 1]; completed TrajInfos are handed to `emit`."""
+
+    def __init__(self, env_lo, env_hi, emu_factory, env_kwargs, frames, ext, act, emit, mid_batch_reset,
+                 max_path_length, discount):
+        self.env_lo, self.frames, self.ext, self.act, self.emit = env_lo, frames, ext, act, emit
+        self.mid_batch_reset, self.max_path_length, self.discount = mid_batch_reset, max_path_length, discount
+        self.envs = [HostAtariEnv(emu_factory(e), **env_kwargs) for e in range(env_lo, env_hi)]
+        self.trajs = [_new_traj() for _ in self.envs]
+        self.need = [False] * len(self.envs)
+
+    def _reset(self, i):
+        e = self.env_lo + i
+        self.ext[e] = (0., 0., 0, 0, self.envs[i].reset(self.frames[e, 1]), 0)
+
+    def start(self):
+        for i in range(len(self.envs)):
+            self._reset(i)
+
+    def reset_needed(self):                                # worker.py:106-113
+        for i in range(len(self.envs)):
+            if self.need[i]:
+                self._reset(i)
+                self.need[i] = False
+            else:
+                self.ext[self.env_lo + i] = (0., 0., 0, 0, FLAG_SKIP | FLAG_NO_RECORD, 0)
+
+    def step(self):
+        for i, env in enumerate(self.envs):
+            e = self.env_lo + i
+            if self.need[i]:                               # finished earlier in this batch: not stepped (worker.py:78)
+                self.ext[e] = (0., 0., 0, 0, FLAG_SKIP | FLAG_NO_RECORD, 0)
+                continue
+            r, raw, d, nr, fl = env.step(int(self.act[e]), self.frames[e, 0], self.frames[e, 1])
+            t = self.trajs[i]
+            t["Length"] += 1
+            t["Return"] += float(r)
+            t["RawReturn"] += float(raw)
+            t["NonzeroRewards"] += int(r != 0)
+            t["DiscountedReturn"] += t["_cur"] * float(r)
+            t["_cur"] *= self.discount
+            over_length = t["Length"] > self.max_path_length
+            if over_length or (d and (True if nr is None else nr)):
+                d = True
+                if over_length and nr is not None:
+                    nr = True
+                self.emit((e, t["Length"], t["Return"], t["RawReturn"], t["NonzeroRewards"], t["DiscountedReturn"]))
+                self.trajs[i] = _new_traj()
+                if self.mid_batch_reset:
+                    fl = env.reset(self.frames[e, 1])
+                else:
+                    self.need[i] = True
+                    fl = FLAG_SKIP                          # this step's reward/done ARE recorded, the obs is not advanced
+            self.ext[e] = (r, raw, int(bool(d)), int(bool(nr)), fl, 0)
+
+
 def worker_main(rank, env_lo, env_hi, n_envs, emu_factory, env_kwargs, frame_shape, shared, cmd, act_ready, step_done,
                 infos_queue, seed, mid_batch_reset, max_path_length, discount):
     np.random.seed(seed)                                   # initialize_worker: seed + rank (sampler/util.py:60-72)
     frames, ext, act = views(shared, n_envs, frame_shape)
-    envs = [HostAtariEnv(emu_factory(e), **env_kwargs) for e in range(env_lo, env_hi)]
-    trajs = [_new_traj() for _ in envs]
-    need = [False] * len(envs)
-    # start_envs (max_decorrelation_steps == 0): reset every env
-    for i, env in enumerate(envs):
-        e = env_lo + i
-        fl = env.reset(frames[e, 1])
-        ext[e] = (0., 0., 0, 0, fl, 0)
+    col = Collector(env_lo, env_hi, emu_factory, env_kwargs, frames, ext, act, infos_queue.put, mid_batch_reset,
+                    max_path_length, discount)
+    col.start()                                            # start_envs (max_decorrelation_steps == 0)
     step_done.release()
     while True:
         act_ready.acquire()
         c = cmd.value
         if c == CMD_QUIT:
             break
-        if c == CMD_RESET_NEEDED:                          # worker.py:106-113
-            for i, env in enumerate(envs):
-                e = env_lo + i
-                if need[i]:
-                    fl = env.reset(frames[e, 1])
-                    ext[e] = (0., 0., 0, 0, fl, 0)
-                    need[i] = False
-                else:
-                    ext[e] = (0., 0., 0, 0, FLAG_SKIP | FLAG_NO_RECORD, 0)
-            step_done.release()
-            continue
-        for i, env in enumerate(envs):                     # one step of collect()
-            e = env_lo + i
-            if need[i]:
-                ext[e] = (0., 0., 0, 0, FLAG_SKIP | FLAG_NO_RECORD, 0)
-                continue
-            r, raw, d, info_need_reset, fl = env.step(int(act[e]), frames[e, 0], frames[e, 1])
-            t = trajs[i]
-            t["Length"] += 1
-            t["Return"] += float(r)
-            t["RawReturn"] += float(raw)
-            t["NonzeroRewards"] += int(r != 0)
-            t["DiscountedReturn"] += t["_cur"] * float(r)
-            t["_cur"] *= discount
-            over_length = t["Length"] > max_path_length
-            nr = info_need_reset
-            if over_length or (d and (True if nr is None else nr)):
-                d = True
-                if over_length and nr is not None:
-                    nr = True
-                infos_queue.put((e, t["Length"], t["Return"], t["RawReturn"], t["NonzeroRewards"], t["DiscountedReturn"]))
-                trajs[i] = _new_traj()
-                if mid_batch_reset:
-                    fl = env.reset(frames[e, 1])
-                else:
-                    need[i] = True
-                    fl = FLAG_SKIP                          # this step's reward/done ARE recorded, the obs is not advanced
-            ext[e] = (r, raw, int(bool(d)), int(bool(nr)), fl, 0)
+        if c == CMD_RESET_NEEDED:
+            col.reset_needed()
+        else:
+            col.step()
         step_done.release()
 
 

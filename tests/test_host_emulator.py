@@ -234,3 +234,65 @@ def test_host_atari_env_vs_the_real_reference_atari_env(episodic, noops):
                 obs = _apply(obs, f1, f2, host.reset(f2))
                 assert emu.f == renv.ale.f and np.array_equal(obs, o3)
         assert overs > 0
+
+
+@pytest.mark.parametrize("tag,mbr", [("reset", True), ("nonreset", False), ("overlength", True)])
+def test_collector_replays_the_real_reference_samplers_buffers(golden_dir, tag, mbr):
+    """The golden sampler fixtures were produced by the reference's REAL multi-process ActsrvAltOvrlpSampler
+    (tests/golden/make_golden.py).  Feeding its recorded actions to hostsim's Collector, and doing on the CPU what the
+    device does with the exported records and screens (ext_apply_kernel + frame_kernel, restated with oracle/frame.py),
+    must reproduce its buffers: rewards, dones, raw rewards, need_reset, every observation row (CRC), the bootstrap
+    observations and the completed trajectories — for the reset collector, the non-reset collector (envs that stop
+    stepping, stale rows) and over-length cuts."""
+    import os
+    import zlib
+    from tests.golden.make_golden import RULES as GRULES, POOL_FRAMES
+    g = np.load(os.path.join(golden_dir, "sampler_%s.npz" % tag))
+    B, T, itrs = int(g["n_envs"]), int(g["horizon"]), int(g["itrs"])
+    frames = np.zeros((B, 2, 210, 160), np.uint8)
+    ext = np.zeros(B, W.EXT_DTYPE)
+    act = np.zeros(B, np.uint8)
+    done_trajs = []
+    rules = dict(GRULES)
+    env_kwargs = dict(frame_skip=4, clip_reward=True, episodic_lives=True, max_start_noops=0, rgb=False)
+    col = W.Collector(0, B, partial(fake_ale.make, rules=rules), env_kwargs, frames, ext, act, done_trajs.append, mbr,
+                      int(g["max_path_length"]), 0.99)
+    assert rules["pool_frames"] == POOL_FRAMES
+    step_obs = np.zeros((B, 4, oframe.H, oframe.W), np.uint8)
+    obs = np.zeros((B * T, 4, oframe.H, oframe.W), np.uint8)
+    rew = np.zeros(B * T, np.float32); raw = np.zeros(B * T, np.float32)
+    don = np.zeros(B * T, bool); nrs = np.zeros(B * T, bool)
+
+    def ingest(s):
+        for e in range(B):
+            x = ext[e]
+            if 0 <= s < T and not (x["flags"] & FLAG_NO_RECORD):
+                rew[e * T + s], raw[e * T + s] = x["reward"], x["raw_reward"]
+                don[e * T + s], nrs[e * T + s] = bool(x["done"]), bool(x["need_reset"])
+            if not (x["flags"] & FLAG_SKIP):
+                step_obs[e] = _apply(step_obs[e], frames[e, 0], frames[e, 1], int(x["flags"]))
+                if 0 <= s and s + 1 < T:
+                    obs[e * T + s + 1] = step_obs[e]
+    col.start()
+    ingest(-1)
+    for itr in range(itrs):
+        del done_trajs[:]
+        for e in range(B):
+            obs[e * T] = step_obs[e]
+        for s in range(T):
+            act[:] = g["act_%d" % itr][s::T]
+            col.step()
+            ingest(s)
+        extra = step_obs.copy()
+        if not mbr:
+            col.reset_needed()
+            ingest(T)
+        for name, mine in (("rew", rew), ("done", don), ("raw", raw), ("nr", nrs), ("extra", extra)):
+            assert np.array_equal(mine, g["%s_%d" % (name, itr)]), (name, itr)
+        crc = np.array([zlib.crc32(r.tobytes()) for r in obs], dtype=np.uint32)
+        assert np.array_equal(crc, g["obscrc_%d" % itr]), itr
+        mine = sorted((t[1], float(t[2]), float(t[3]), int(t[4]), float(t[5])) for t in done_trajs)
+        want = [tuple(r) for r in g["traj_%d" % itr]]
+        assert len(mine) == len(want)
+        for a, b in zip(mine, want):
+            np.testing.assert_allclose(a, b, rtol=1e-6)
