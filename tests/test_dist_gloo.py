@@ -123,3 +123,69 @@ def test_oracle_virtual_ranks_average_equals_concatenated_batch():
     _, g_all, _ = onet.loss_and_grad(flat, obs, act, adv, ret, oldp, spec, 4, "ppo")
     avg = 0.5 * (gs[0] + gs[1])
     assert np.linalg.norm(avg - g_all) / np.linalg.norm(g_all) < 1e-4
+
+
+def _async_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.cuda.synchronize = lambda *a, **k: None          # no device in this test
+    from accel_rl_b200.runners.multigpu_rl import AccelRLAsync
+    from accel_rl_b200.optimizers.async_.base import BaseAsyncOptimizer
+
+    class Eng(_FakeEngine):
+        def async_init(self, rank, world, n_update_chunks, exchange):
+            self.handles = exchange(bytes([10 + rank]) * 64)
+            self.calls.append(("async_init", rank, world, n_update_chunks))
+            return 148
+
+    class Opt(BaseAsyncOptimizer):
+        def __init__(self, eng):
+            self._engine = eng
+            self.n_update_chunks = 3
+
+    class Algo(object):
+        need_extra_obs = True
+        opt_info_keys = ["GradNorm"]
+
+    class Pol(object):
+        def __init__(self, eng):
+            self.engine = eng
+
+        def get_param_values(self):
+            return self.engine.params.numpy().copy()
+
+    eng = Eng()
+    eng.params += float(rank + 1)
+    algo = Algo()
+    algo.optimizer = Opt(eng)
+    r = AccelRLAsync(algo=algo, policy=Pol(eng), sampler=None, n_steps=1e6, seed=7, log_interval_steps=1e5,
+                     affinities=[dict(gpu=0), dict(gpu=1)])
+    r.init_comm()
+    out[rank] = dict(tag=r.parallelism_tag, params=eng.params.numpy().copy(), handles=[h[0] for h in eng.handles],
+                     calls=eng.calls, regions=algo.optimizer.n_lock_regions, rank=algo.optimizer._rank,
+                     n=algo.optimizer._n_runners)
+    dist.destroy_process_group()
+
+
+def test_async_runner_host_logic_two_ranks():
+    """AccelRLAsync.init_comm (multigpu_rl_base.py:161-208, optimizers/async/base.py:13-41): rank 0's parameters are
+    broadcast, the IPC handles are all-gathered in rank order (rank 0's entry is the central store), the optimizer
+    learns its rank / world size / chunk count"""
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_async_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    r0, r1 = out[0], out[1]
+    assert r0["tag"] == r1["tag"] == "asynchronous"
+    assert np.array_equal(r0["params"], r1["params"]) and r0["params"][0] == 1.0
+    assert r0["handles"] == r1["handles"] == [10, 11]
+    assert ("async_init", 0, 2, 3) in r0["calls"] and ("async_init", 1, 2, 3) in r1["calls"]
+    assert ("pack",) in r1["calls"]
+    assert (r0["regions"], r1["rank"], r1["n"]) == (148, 1, 2)
