@@ -79,6 +79,7 @@ struct PcLayer {
 
 constexpr int kSsFinCap = 4096;   // finalize blocks that own elements (preset 1: ~320)
 constexpr int kSsFcCap = 4096;    // FC weight-gradient CTAs x 8 epilogue warps (preset 1: 54 x 8)
+constexpr int kStreamPartials = 4096;   // block partials of update_stream_kernel (preset 1: 317 + 592 blocks)
 
 struct TrainPlan {
   int n = 0;
@@ -88,6 +89,7 @@ struct TrainPlan {
   int n_jobs = 0;
   int fin_blocks = 1;
   int n_ss = 0;                 // per-block sum-of-squares slots the finalize kernel fills (GradJob::ss_off)
+  long fin_total = 0;           // elements of all jobs (update_stream_kernel's part-A index space)
 };
 
 }  // namespace
@@ -146,6 +148,7 @@ struct arl_ctx {
   bool train_step_active = false;      // grad_minibatch is followed by the local clip_update (train_minibatches, sync == 0)
   bool early_fc_done = false;          // this minibatch's FC weights were updated by update_range_kernel
   const void* pending_fin = nullptr;   // TrainPlan whose gradient finalisation clip_update must fold into its update kernel
+  bool pending_stream = false;         // ... and the folding kernel is update_stream_kernel (no clipping: no barrier)
   cudaEvent_t ev_fcd = nullptr;        // "FC data gradient has read the FC weights"
   unsigned long long* ticket = nullptr; // grid-barrier ticket of update_fused_kernel
   float* hyper = nullptr;          // [0] lr_mult
@@ -193,6 +196,7 @@ struct arl_ctx {
   const int* train_graph_idx = nullptr;
   int train_graph_mb = 0;
   int train_graph_sync = 0;
+  int train_graph_per = 1;
   bool sync_graph_failed = false;
   long launches = 0;
   // per-kernel CUDA-event profiling (arl_profile_*): events recorded after each launch when enabled
@@ -922,7 +926,7 @@ int alloc_net(arl_ctx* c) {
   if (dev_alloc(c, &c->head_partial, (size_t)64 * c->H * (c->A + 2))) return 1;
   if (dev_alloc(c, &c->head_b_partial, (size_t)64 * (c->A + 1))) return 1;
   if (dev_alloc(c, &c->loss_partial, (size_t)R * 4)) return 1;
-  if (dev_alloc(c, &c->sumsq_partial, (size_t)kSumsqBlocks)) return 1;
+  if (dev_alloc(c, &c->sumsq_partial, (size_t)kStreamPartials)) return 1;
   if (dev_alloc(c, &c->sumsq_partial_fc, (size_t)kEarlyBlocks)) return 1;
   if (dev_alloc(c, &c->ss_fin, (size_t)kSsFinCap)) return 1;
   if (dev_alloc(c, &c->ss_fc, (size_t)kSsFcCap)) return 1;
@@ -1115,6 +1119,7 @@ int get_plan(arl_ctx* c, int n, TrainPlan** out) {
   }
   P.n_jobs = (int)jobs.size();
   P.fin_blocks = (int)((max_total + 255) / 256);
+  for (auto& jb : jobs) P.fin_total += (long)jb.rows * jb.cols;
   for (auto& jb : jobs) {       // one slot per finalize block that owns elements of the job
     jb.ss_off = P.n_ss;
     P.n_ss += (int)(((long)jb.rows * jb.cols + 255) / 256);
@@ -1131,6 +1136,7 @@ bool early_fc_ok(arl_ctx* c);
 int early_fc_update(arl_ctx* c, cudaStream_t st);
 bool merge_finalize_ok(arl_ctx* c, bool fct);
 bool producer_sumsq_ok(arl_ctx* c, bool fct);
+bool stream_update_ok(arl_ctx* c, bool fct);
 
 // forward + loss + backward for one minibatch -> flat grad
 int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaStream_t st) {
@@ -1310,7 +1316,10 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
     prof_mark(c, kDgradName[l], st);
   }
   // ---- sum partials, scatter into the flat gradient ----
-  if (merge_finalize_ok(c, fct)) {
+  if (stream_update_ok(c, fct)) {
+    c->pending_fin = P;        // clip_update: update_stream_kernel sums the partials and updates in the same pass
+    c->pending_stream = true;
+  } else if (merge_finalize_ok(c, fct)) {
     c->pending_fin = P;        // clip_update folds it into phase 1 of update_fused_kernel (one launch, one pass less)
   } else {
     dim3 grid(P->fin_blocks, P->n_jobs);
@@ -1378,6 +1387,19 @@ bool producer_sumsq_ok(arl_ctx* c, bool fct) {
   return on && fused && fct && c->train_step_active && !early_fc_ok(c) && !merge_finalize_ok(c, fct);
 }
 
+// Without global-norm clipping nothing in the update depends on the norm: finalisation, update, operand refresh and
+// the logs go into ONE plain launch (update_stream_kernel).  Needs the local fused step to follow (train_minibatches /
+// the profiling graph), the FC weight gradient written straight into the flat vector, and the slot table that lets the
+// updating thread refresh the conv operand packs.  ARL_STREAM_UPDATE=0 restores finalize_grads + update_fused.
+bool stream_update_ok(arl_ctx* c, bool fct) {
+  static const bool on = !(getenv("ARL_STREAM_UPDATE") && atoi(getenv("ARL_STREAM_UPDATE")) == 0);
+  if (!(on && fct && c->train_step_active && c->opt_set && c->m && c->v && c->opt.grad_norm_clip <= 0.f)) return false;
+  if ((c->off_Wfc % 4) || (((long)c->Kfc * c->H) % 4)) return false;
+  bool fused_cast = false;
+  UpdateParams u = update_params(c, 1.f, &fused_cast);
+  return fused_cast && u.shadow && c->pc_mode >= 2 && c->n_pack_jobs >= 2 && c->conv_pack_end > 0 && c->pk_slots;
+}
+
 int early_fc_update(arl_ctx* c, cudaStream_t st) {
   bool fused_cast = false;
   UpdateParams u = update_params(c, 1.f, &fused_cast);
@@ -1423,11 +1445,34 @@ int clip_update(arl_ctx* c, float gscale, cudaStream_t st) {
     u.sumsq_partial2 = c->sumsq_partial_fc; u.n_partial2 = kEarlyBlocks;
     c->early_fc_done = false;
   }
+  long P_total = 0;
   if (c->pending_fin) {
     const TrainPlan* P = static_cast<const TrainPlan*>(c->pending_fin);
+    P_total = P->fin_total;
     u.fin_jobs = P->jobs_dev; u.n_fin_jobs = P->n_jobs;
     u.fc4_begin = c->off_Wfc / 4; u.fc4_len = (long)c->Kfc * c->H / 4;
     c->pending_fin = nullptr;
+  }
+  if (c->pending_stream) {
+    c->pending_stream = false;
+    if (gscale != 1.f || u.n_fin_jobs == 0) ARL_FAIL(c, "update_stream: unexpected configuration");
+    u.pk_slots = c->pk_slots; u.n_pk_jobs = c->n_pack_jobs - 1; u.conv_end = c->conv_pack_end;
+    u.adv_done = c->ticket + 1; u.adv_log_slot = c->log_slot; u.adv_mb = c->mb_counter;
+    // blocks [0, nA) sum the split partials and update everything except the FC weights, the other 4 x 148 stream the FC range
+    const int nA = (int)((P_total + 255) / 256);
+    int nB = kSumsqBlocks;
+    if (u.skip4_len > 0) {
+      // the FC range already took its step (update_range_kernel, beside the conv gradient chain): only part A is left
+      if (u.skip4_begin != u.fc4_begin || u.skip4_len != u.fc4_len) ARL_FAIL(c, "update_stream: early range is not the FC range");
+      u.fc4_len = 0; nB = 0;
+    }
+    if (nA + nB > kStreamPartials) ARL_FAIL(c, "update_stream: partial buffer too small");
+    u.adv_done = c->ticket + 2;                 // (its own arrival counter: the grid size differs from update_fused_kernel's)
+    ARL_CHECK(c, launch_k(update_stream_kernel, dim3(nA + nB), dim3(256), 0, st, u, c->sumsq_partial, nA, P_total));
+    c->launches++;
+    prof_mark(c, "clip_update", st);
+    ARL_CHECK(c, cudaGetLastError());
+    return 0;
   }
   // norm + clip + update in one launch (update_fused_kernel); ARL_FUSED_UPDATE=0 keeps the two-kernel form
   static const bool fused = !(getenv("ARL_FUSED_UPDATE") && atoi(getenv("ARL_FUSED_UPDATE")) == 0);
@@ -1970,7 +2015,7 @@ int train_minibatches(arl_ctx* c, const int* idx, int mb_size, int count, int sy
     arl_ctx* c;
     Active(arl_ctx* c_, bool on) : c(c_) { c->train_step_active = on; }
     ~Active() {
-      c->train_step_active = false; c->early_fc_done = false; c->pending_fin = nullptr;
+      c->train_step_active = false; c->early_fc_done = false; c->pending_fin = nullptr; c->pending_stream = false;
       c->pending_ss_fin = c->pending_ss_fc = 0;
     }
   } active(c, sync == 0);
@@ -1984,7 +2029,14 @@ int train_minibatches(arl_ctx* c, const int* idx, int mb_size, int count, int sy
     }
     return 0;
   }
-  if (c->train_graph && (c->train_graph_idx != idx || c->train_graph_mb != mb_size || c->train_graph_sync != sync)) {
+  // ONE graph holds `per` consecutive minibatches (all of them when count <= ARL_GRAPH_MB, default 512): the device-side
+  // minibatch counter selects each one's index slice, so an iteration's 4 epochs x N/mb updates are one cudaGraphLaunch
+  // instead of 256 (ARL_GRAPH_MB=1: one graph per minibatch, the round-1 behaviour)
+  static const int graph_mb_cap = getenv("ARL_GRAPH_MB") ? std::max(1, atoi(getenv("ARL_GRAPH_MB"))) : 512;
+  int per = std::min(count, graph_mb_cap);
+  if (per < 1 || count % per != 0) per = 1;
+  if (c->train_graph && (c->train_graph_idx != idx || c->train_graph_mb != mb_size || c->train_graph_sync != sync ||
+                         c->train_graph_per != per)) {
     cudaGraphExecDestroy(c->train_graph);
     c->train_graph = nullptr;
   }
@@ -1996,8 +2048,11 @@ int train_minibatches(arl_ctx* c, const int* idx, int mb_size, int count, int sy
     long l0 = c->launches;
     cudaGraph_t g = nullptr;
     ARL_CHECK(c, cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
-    int rc = grad_minibatch(c, idx, c->mb_counter, mb_size, cap);
-    if (!rc) rc = step(cap);
+    int rc = 0;
+    for (int k = 0; k < per && !rc; ++k) {
+      rc = grad_minibatch(c, idx, c->mb_counter, mb_size, cap);
+      if (!rc) rc = step(cap);
+    }
     cudaError_t ce = cudaStreamEndCapture(cap, &g);
     c->graph_train_nodes = c->launches - l0;
     c->launches = l0;
@@ -2015,11 +2070,11 @@ int train_minibatches(arl_ctx* c, const int* idx, int mb_size, int count, int sy
     }
     if (rc) return rc;
     ARL_CHECK(c, ce);
-    c->train_graph_idx = idx; c->train_graph_mb = mb_size; c->train_graph_sync = sync;
+    c->train_graph_idx = idx; c->train_graph_mb = mb_size; c->train_graph_sync = sync; c->train_graph_per = per;
   }
   ARL_CHECK(c, cudaMemsetAsync(c->mb_counter, 0, sizeof(int), st));
-  for (int i = 0; i < count; ++i) ARL_CHECK(c, cudaGraphLaunch(c->train_graph, st));
-  c->launches += (long)count * c->graph_train_nodes;
+  for (int i = 0; i < count / per; ++i) ARL_CHECK(c, cudaGraphLaunch(c->train_graph, st));
+  c->launches += (long)(count / per) * c->graph_train_nodes;
   return 0;
 }
 }  // namespace
@@ -2246,7 +2301,7 @@ int arl_profile_graph(arl_ctx* c, int kind, const int* idx, int mb_size, int rep
     if (!rc) rc = clip_update(c, 1.f, cap_s);
     c->train_step_active = false;
     c->early_fc_done = false;
-    c->pending_fin = nullptr;
+    c->pending_fin = nullptr; c->pending_stream = false;
     c->pending_ss_fin = c->pending_ss_fc = 0;
   } else if (kind == 1) {
     rc = rollout_step(c, 0, nullptr, cap_s);

@@ -311,25 +311,19 @@ __global__ void __launch_bounds__(kSyncThreads) sync_allreduce_update_kernel(Com
     const float4 g4 = reinterpret_cast<const float4*>(d.avg_slice)[i];
     const float4 p4 = *reinterpret_cast<const float4*>(a.param + gi);
     const float4 v4 = *reinterpret_cast<const float4*>(a.v + gi);
-    float g[4] = {g4.x * scale, g4.y * scale, g4.z * scale, g4.w * scale};
+    float g[4] = {__fmul_rn(g4.x, scale), __fmul_rn(g4.y, scale), __fmul_rn(g4.z, scale), __fmul_rn(g4.w, scale)};
     float pp[4] = {p4.x, p4.y, p4.z, p4.w};
     float vv[4] = {v4.x, v4.y, v4.z, v4.w};
     if (a.kind == 0) {
       const float4 m4 = *reinterpret_cast<const float4*>(a.m + gi);
       float mm[4] = {m4.x, m4.y, m4.z, m4.w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        mm[k] = a.beta1 * mm[k] + (1.f - a.beta1) * g[k];
-        vv[k] = a.beta2 * vv[k] + (1.f - a.beta2) * g[k] * g[k];
-        pp[k] -= alpha * mm[k] / (sqrtf(vv[k]) + a.eps);
-      }
+      for (int k = 0; k < 4; ++k) opt_step_raw(0, a.beta1, a.beta2, a.eps, a.rho, pp[k], mm[k], vv[k], g[k], alpha);
       *reinterpret_cast<float4*>(a.m + gi) = make_float4(mm[0], mm[1], mm[2], mm[3]);
     } else {
+      float dummy = 0.f;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        vv[k] = a.rho * vv[k] + (1.f - a.rho) * g[k] * g[k];
-        pp[k] -= alpha * g[k] / sqrtf(vv[k] + a.eps);
-      }
+      for (int k = 0; k < 4; ++k) opt_step_raw(1, a.beta1, a.beta2, a.eps, a.rho, pp[k], dummy, vv[k], g[k], alpha);
     }
     *reinterpret_cast<float4*>(a.v + gi) = make_float4(vv[0], vv[1], vv[2], vv[3]);
     const float4 pn = make_float4(pp[0], pp[1], pp[2], pp[3]);
@@ -347,18 +341,11 @@ __global__ void __launch_bounds__(kSyncThreads) sync_allreduce_update_kernel(Com
   if (gtid == 0) {
     for (long i = len4 << 2; i < len; ++i) {
       const long gi = begin + i;
-      float g = d.avg_slice[i] * scale;
-      float p = a.param[gi];
-      if (a.kind == 0) {
-        float m = a.beta1 * a.m[gi] + (1.f - a.beta1) * g;
-        float v = a.beta2 * a.v[gi] + (1.f - a.beta2) * g * g;
-        a.m[gi] = m; a.v[gi] = v;
-        p -= alpha * m / (sqrtf(v) + a.eps);
-      } else {
-        float ac = a.rho * a.v[gi] + (1.f - a.rho) * g * g;
-        a.v[gi] = ac;
-        p -= alpha * g / sqrtf(ac + a.eps);
-      }
+      float g = __fmul_rn(d.avg_slice[i], scale);
+      float p = a.param[gi], m = (a.kind == 0) ? a.m[gi] : 0.f, v = a.v[gi];
+      opt_step_raw(a.kind, a.beta1, a.beta2, a.eps, a.rho, p, m, v, g, alpha);
+      if (a.kind == 0) a.m[gi] = m;
+      a.v[gi] = v;
       for (int r = 0; r < d.world; ++r) d.peer_param[r][gi] = p;
     }
   }
@@ -512,25 +499,19 @@ __global__ void __launch_bounds__(kAsyncThreads) async_push_pull_kernel(AsyncDev
       const float4 g4 = *reinterpret_cast<const float4*>(p.grad + e0);
       float4 p4 = ld_sys_f4(d.cp + e0);
       float4 v4 = ld_sys_f4(d.cv + e0);
-      float g[4] = {g4.x * scale, g4.y * scale, g4.z * scale, g4.w * scale};
+      float g[4] = {__fmul_rn(g4.x, scale), __fmul_rn(g4.y, scale), __fmul_rn(g4.z, scale), __fmul_rn(g4.w, scale)};
       float pp[4] = {p4.x, p4.y, p4.z, p4.w};
       float vv[4] = {v4.x, v4.y, v4.z, v4.w};
       if (p.kind == 0) {
         float4 m4 = ld_sys_f4(d.cm + e0);
         float mm[4] = {m4.x, m4.y, m4.z, m4.w};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          mm[k] = p.beta1 * mm[k] + (1.f - p.beta1) * g[k];
-          vv[k] = p.beta2 * vv[k] + (1.f - p.beta2) * g[k] * g[k];
-          pp[k] -= alpha * mm[k] / (sqrtf(vv[k]) + p.eps);
-        }
+        for (int k = 0; k < 4; ++k) opt_step1(p, pp[k], mm[k], vv[k], g[k], alpha);
         st_sys_f4(d.cm + e0, make_float4(mm[0], mm[1], mm[2], mm[3]));
       } else {
+        float dummy = 0.f;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          vv[k] = p.rho * vv[k] + (1.f - p.rho) * g[k] * g[k];
-          pp[k] -= alpha * g[k] / sqrtf(vv[k] + p.eps);
-        }
+        for (int k = 0; k < 4; ++k) opt_step1(p, pp[k], dummy, vv[k], g[k], alpha);
       }
       st_sys_f4(d.cv + e0, make_float4(vv[0], vv[1], vv[2], vv[3]));
       st_sys_f4(d.cp + e0, make_float4(pp[0], pp[1], pp[2], pp[3]));
@@ -546,16 +527,10 @@ __global__ void __launch_bounds__(kAsyncThreads) async_push_pull_kernel(AsyncDev
     }
     // tail of the vector (n % 4 elements) belongs to the last region
     for (long e = begin + (n4 << 2) + threadIdx.x; e < end; e += blockDim.x) {
-      float g = p.grad[e] * scale, pv = ld_sys_f(d.cp + e), vv = ld_sys_f(d.cv + e);
-      if (p.kind == 0) {
-        float mm = p.beta1 * ld_sys_f(d.cm + e) + (1.f - p.beta1) * g;
-        vv = p.beta2 * vv + (1.f - p.beta2) * g * g;
-        pv -= alpha * mm / (sqrtf(vv) + p.eps);
-        st_sys_f(d.cm + e, mm);
-      } else {
-        vv = p.rho * vv + (1.f - p.rho) * g * g;
-        pv -= alpha * g / sqrtf(vv + p.eps);
-      }
+      float g = __fmul_rn(p.grad[e], scale), pv = ld_sys_f(d.cp + e), vv = ld_sys_f(d.cv + e);
+      float mm = (p.kind == 0) ? ld_sys_f(d.cm + e) : 0.f;
+      opt_step1(p, pv, mm, vv, g, alpha);
+      if (p.kind == 0) st_sys_f(d.cm + e, mm);
       st_sys_f(d.cv + e, vv);
       st_sys_f(d.cp + e, pv);
       p.param[e] = pv;

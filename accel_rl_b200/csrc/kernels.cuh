@@ -1010,7 +1010,8 @@ ARL_DEVINL void pc_decode_channel(int cc, int C, int s, int ci_major, int& ci, i
 
 // one element of one job: sums its partials in a fixed order, writes it to its place in the flat gradient;
 // -> false when the element is a padding tap / channel that has no parameter (nothing written)
-ARL_DEVINL bool finalize_elem(const GradJob& jb, long i, float* __restrict__ grad, float& acc_out) {
+// (finalize_elem_dst: the same, returning the element's index in the flat vector, -1 = no parameter)
+ARL_DEVINL long finalize_elem_dst(const GradJob& jb, long i, float* __restrict__ grad, float& acc_out) {
   int r = (int)(i / jb.cols);
   int c = (int)(i - (long)r * jb.cols);
   const float* s = jb.src + (long)r * jb.ld + c;
@@ -1033,14 +1034,15 @@ ARL_DEVINL bool finalize_elem(const GradJob& jb, long i, float* __restrict__ gra
     for (int u = 0; u < w; ++u) a[u] += a[u + w];
   const float acc = a[0] * jb.scale;
   acc_out = acc;
+  long dst;
   if (jb.map == GM_LINEAR) {
-    grad[jb.dst_off + i] = acc;
+    dst = jb.dst_off + i;
   } else if (jb.map == GM_CONV_NHWC) {
     // r = k' = (ky*kw + kx)*C + ci ; c = cout
     int ci = r % jb.C;
     int t = r / jb.C;
     int kx = t % jb.kw, ky = t / jb.kw;
-    grad[jb.dst_off + (((long)c * jb.C + ci) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx)] = acc;
+    dst = jb.dst_off + (((long)c * jb.C + ci) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx);
   } else if (jb.map == GM_CONV_S2D) {
     // first layer over the space-to-depth input: r = k' = (ty*2 + tx)*(C*s*s) + ci*s*s + dy*s + dx
     const int s2 = jb.s2d * jb.s2d, cs = jb.C * s2;
@@ -1049,7 +1051,7 @@ ARL_DEVINL bool finalize_elem(const GradJob& jb, long i, float* __restrict__ gra
     int tx = t % 2, ty = t / 2;
     int ci = ch / s2, dy = (ch % s2) / jb.s2d, dx = ch % jb.s2d;
     int ky = ty * jb.s2d + dy, kx = tx * jb.s2d + dx;
-    grad[jb.dst_off + (((long)c * jb.C + ci) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx)] = acc;
+    dst = jb.dst_off + (((long)c * jb.C + ci) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx);
   } else if (jb.map == GM_PCONV) {
     int blk = r >> 6, ch = r & 63;
     int t = blk / jb.P, plane = blk - t * jb.P;
@@ -1057,14 +1059,18 @@ ARL_DEVINL bool finalize_elem(const GradJob& jb, long i, float* __restrict__ gra
     int ci, py, px;
     pc_decode_channel(plane * 64 + ch, jb.C, jb.s2d, jb.ci_major, ci, py, px);
     int ky = ty * jb.s2d + py, kx = tx * jb.s2d + px;
-    if (!(ky < jb.kh && kx < jb.kw && ci < jb.C)) return false;
-    grad[jb.dst_off + (((long)c * jb.C + ci) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx)] = acc;
+    if (!(ky < jb.kh && kx < jb.kw && ci < jb.C)) return -1;
+    dst = jb.dst_off + (((long)c * jb.C + ci) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx);
   } else {  // GM_HEAD: r = j, c in [0, A+2)
-    if (c < jb.A) grad[jb.dst_off + (long)r * jb.A + c] = acc;
-    else if (c == jb.A) grad[jb.dst_off2 + r] = acc;
-    else grad[jb.dst_off3 + r] = acc;
+    if (c < jb.A) dst = jb.dst_off + (long)r * jb.A + c;
+    else if (c == jb.A) dst = jb.dst_off2 + r;
+    else dst = jb.dst_off3 + r;
   }
-  return true;
+  grad[dst] = acc;
+  return dst;
+}
+ARL_DEVINL bool finalize_elem(const GradJob& jb, long i, float* __restrict__ grad, float& acc_out) {
+  return finalize_elem_dst(jb, i, grad, acc_out) >= 0;
 }
 
 __global__ void __launch_bounds__(256) finalize_grads_kernel(const GradJob* __restrict__ jobs, float* __restrict__ grad) {
@@ -1337,30 +1343,51 @@ __global__ void __launch_bounds__(256, 4) update_fused_kernel(UpdateParams p, do
   }
 }
 
+// One Adam / RMSProp element step (optimizers/update_methods_stats.py:11-32, :55-87).  The division and the square root
+// use the approximate hardware forms (MUFU.RCP / MUFU.SQRT / MUFU.RSQ, <= 2 ulp each): the IEEE sequences cost ~40
+// instructions per element and made the update kernel issue-bound (ncu: ~400 warp instructions per float4 group); the
+// error they add to a parameter is < 3e-7 of ONE step's change, far below the fp32 spacing of the parameter itself.
+ARL_DEVINL float fast_sqrt(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+ARL_DEVINL float fast_rsqrt(float x) { float r; asm("rsqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// Every operation is an explicit intrinsic: the compiler may not re-contract them, so every kernel that inlines this
+// (single-GPU, early-FC range, stream, synchronous slice, asynchronous central update) rounds identically — the
+// bit-exactness tests between those paths rely on it.
+ARL_DEVINL void opt_step_raw(int kind, float beta1, float beta2, float eps, float rho, float& pp, float& mm, float& vv,
+                             float g, float alpha) {
+  if (kind == 0) {
+    mm = __fmaf_rn(beta1, mm, __fmul_rn(1.f - beta1, g));
+    vv = __fmaf_rn(beta2, vv, __fmul_rn(__fmul_rn(1.f - beta2, g), g));
+    pp = __fsub_rn(pp, __fdividef(__fmul_rn(alpha, mm), __fadd_rn(fast_sqrt(vv), eps)));
+  } else {
+    vv = __fmaf_rn(rho, vv, __fmul_rn(__fmul_rn(1.f - rho, g), g));
+    pp = __fsub_rn(pp, __fmul_rn(__fmul_rn(alpha, g), fast_rsqrt(__fadd_rn(vv, eps))));
+  }
+}
+ARL_DEVINL void opt_step1(const UpdateParams& p, float& pp, float& mm, float& vv, float g, float alpha) {
+  opt_step_raw(p.kind, p.beta1, p.beta2, p.eps, p.rho, pp, mm, vv, g, alpha);
+}
+
 // Adam / RMSProp on float4 group i (+ the bf16 operand copy of the FC weights, refreshed in the same pass)
+ARL_DEVINL void update_vec4_g(const UpdateParams& p, long i, float4 g4, float scale, float alpha);
 ARL_DEVINL void update_vec4(const UpdateParams& p, long i, float scale, float alpha) {
-  float4 g4 = reinterpret_cast<const float4*>(p.grad)[i];
+  update_vec4_g(p, i, reinterpret_cast<const float4*>(p.grad)[i], scale, alpha);
+}
+ARL_DEVINL void update_vec4_g(const UpdateParams& p, long i, float4 g4, float scale, float alpha) {
   float4 p4 = reinterpret_cast<float4*>(p.param)[i];
   float4 v4 = reinterpret_cast<float4*>(p.v)[i];
-  float g[4] = {g4.x * scale, g4.y * scale, g4.z * scale, g4.w * scale};
+  float g[4] = {__fmul_rn(g4.x, scale), __fmul_rn(g4.y, scale), __fmul_rn(g4.z, scale), __fmul_rn(g4.w, scale)};
   float pp[4] = {p4.x, p4.y, p4.z, p4.w};
   float vv[4] = {v4.x, v4.y, v4.z, v4.w};
   if (p.kind == 0) {
     float4 m4 = reinterpret_cast<float4*>(p.m)[i];
     float mm[4] = {m4.x, m4.y, m4.z, m4.w};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      mm[k] = p.beta1 * mm[k] + (1.f - p.beta1) * g[k];
-      vv[k] = p.beta2 * vv[k] + (1.f - p.beta2) * g[k] * g[k];
-      pp[k] -= alpha * mm[k] / (sqrtf(vv[k]) + p.eps);
-    }
+    for (int k = 0; k < 4; ++k) opt_step1(p, pp[k], mm[k], vv[k], g[k], alpha);
     reinterpret_cast<float4*>(p.m)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
   } else {
+    float dummy = 0.f;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      vv[k] = p.rho * vv[k] + (1.f - p.rho) * g[k] * g[k];
-      pp[k] -= alpha * g[k] / sqrtf(vv[k] + p.eps);
-    }
+    for (int k = 0; k < 4; ++k) opt_step1(p, pp[k], dummy, vv[k], g[k], alpha);
   }
   reinterpret_cast<float4*>(p.v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
   reinterpret_cast<float4*>(p.param)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
@@ -1471,17 +1498,116 @@ ARL_DEVINL void update_body(const UpdateParams& p) {
   }
   if (blockIdx.x == 0 && threadIdx.x < (p.n & 3)) {
     long i = ((p.n >> 2) << 2) + threadIdx.x;
-    float g = p.grad[i] * scale;
-    if (p.kind == 0) {
-      float m = p.beta1 * p.m[i] + (1.f - p.beta1) * g;
-      float v = p.beta2 * p.v[i] + (1.f - p.beta2) * g * g;
-      p.m[i] = m; p.v[i] = v;
-      p.param[i] -= alpha * m / (sqrtf(v) + p.eps);
-    } else {
-      float a = p.rho * p.v[i] + (1.f - p.rho) * g * g;
-      p.v[i] = a;
-      p.param[i] -= alpha * g / sqrtf(a + p.eps);
+    float g = __fmul_rn(p.grad[i], scale);
+    float pv = p.param[i], m = (p.kind == 0) ? p.m[i] : 0.f, v = p.v[i];
+    opt_step1(p, pv, m, v, g, alpha);
+    if (p.kind == 0) p.m[i] = m;
+    p.v[i] = v;
+    p.param[i] = pv;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// update_stream_kernel: gradient finalisation + Adam/RMSProp + operand refresh + logs in ONE plain launch, for updates
+// WITHOUT global-norm clipping (PPO's default, algos/pg/ppo.py:29: the norm is only reported, so nothing in the update
+// waits for it).  Replaces finalize_grads_kernel -> update_fused_kernel {pass over the gradient, grid barrier, update}:
+//   part A  every tensor except the FC weights (~2 % of the vector): the thread that sums an element's split partials
+//           (finalize_elem_dst) also takes its optimiser step and refreshes its bf16 operand slots;
+//   part B  the FC weight range, float4 groups straight from the flat gradient the FC tiles wrote;
+//   every thread squares what it consumed; block partials in `partial`; the LAST block to finish (ticket) adds them up
+//   in index order (bit-reproducible), writes the norm / loss logs and advances the device counters.
+// No grid barrier, no cooperative launch, one pass over the 101 MB of (g, p, m, v).
+// ---------------------------------------------------------------------------------------------------------------
+ARL_DEVINL void update_scalar(const UpdateParams& p, long i, float g, float alpha) {
+  float pv = p.param[i], m = (p.kind == 0) ? p.m[i] : 0.f, v = p.v[i];
+  opt_step1(p, pv, m, v, g, alpha);
+  if (p.kind == 0) p.m[i] = m;
+  p.v[i] = v;
+  p.param[i] = pv;
+  if (p.n_pk_jobs > 0 && i < p.conv_end) {
+    const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2*>(p.pk_slots + 2 * i));
+    const __nv_bfloat16 b = __float2bfloat16_rn(pv);
+    if (a.x) *reinterpret_cast<__nv_bfloat16*>(a.x) = b;
+    if (a.y) *reinterpret_cast<__nv_bfloat16*>(a.y) = b;
+  }
+}
+
+__global__ void __launch_bounds__(256, 4) update_stream_kernel(UpdateParams p, double* __restrict__ partial, int nA,
+                                                              long total_all) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float s_alpha;
+  __shared__ double s_red[8];
+  __shared__ int s_last;
+  if (threadIdx.x == 0) s_alpha = update_alpha(p);
+  __syncthreads();
+  const float alpha = s_alpha;
+  double acc = 0.0;
+  if ((int)blockIdx.x < nA) {
+    // part A (blocks [0, nA): scheduled first): ONE element per thread, consecutive threads = consecutive elements of the
+    // concatenated job index space (coalesced partial loads).  A separate set of blocks from part B: the partial sums are
+    // 48..148 dependent-latency loads per element — ncu (profiles/r2_update_stream.md) showed warps that carried both
+    // parts holding their whole block at the final barrier for 40 % of the kernel
+    float* grad = const_cast<float*>(p.grad);
+    long v = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < total_all) {
+      int jn = 0;
+      for (; jn < p.n_fin_jobs; ++jn) {
+        const long t = (long)p.fin_jobs[jn].rows * p.fin_jobs[jn].cols;
+        if (v < t) break;
+        v -= t;
+      }
+      const GradJob& jb = p.fin_jobs[jn];      // (fields fetched where used: a register copy of the struct spills)
+      float g;
+      const long dst = finalize_elem_dst(jb, v, grad, g);
+      if (dst >= 0) {
+        acc += (double)(g * g);
+        update_scalar(p, dst, g, alpha);
+      }
     }
+  } else {
+    // part B: the FC weights
+    const long gtid = (long)((int)blockIdx.x - nA) * blockDim.x + threadIdx.x, gsize = (long)((int)gridDim.x - nA) * blockDim.x;
+    const float4* g4p = reinterpret_cast<const float4*>(p.grad) + p.fc4_begin;
+    for (long j = gtid; j < p.fc4_len; j += gsize) {
+      const float4 g4 = g4p[j];
+      acc += (double)(g4.x * g4.x + g4.y * g4.y) + (double)(g4.z * g4.z + g4.w * g4.w);
+      update_vec4_g(p, p.fc4_begin + j, g4, 1.f, alpha);
+    }
+  }
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_red[w];
+    partial[blockIdx.x] = t;
+    __threadfence();
+    const unsigned long long tk = atomicAdd(p.adv_done, 1ULL);
+    s_last = ((tk + 1ULL) % gridDim.x == 0ULL) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  // last block: every other block has published its partial and read the update count / log slot
+  __threadfence();
+  double a2 = 0.0;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) a2 += __ldcg(partial + i);
+  for (int i = threadIdx.x; i < p.n_partial2; i += blockDim.x) a2 += __ldcg(p.sumsq_partial2 + i);   // early FC update's share
+  a2 = warp_sum_d(a2);
+  float l = 0.f;
+  for (int b = threadIdx.x; b < p.n_loss_blocks; b += blockDim.x) l += p.loss_partial[4 * b + 3];
+  l = warp_sum(l);
+  __shared__ float s_l[8];
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { s_red[threadIdx.x >> 5] = a2; s_l[threadIdx.x >> 5] = l; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    float tl = 0.f;
+    for (int w = 0; w < 8; ++w) { t += s_red[w]; tl += s_l[w]; }
+    const int slot = p.log_slot[0];
+    if (slot < p.log_cap) { p.out_norm[slot] = (float)sqrt(t); p.out_loss[slot] = tl; }
+    p.step[0] += 1; p.adv_log_slot[0] += 1; p.adv_mb[0] += 1;
   }
 }
 

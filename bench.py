@@ -301,6 +301,24 @@ def kernel_flops(label, n, args):
     return None
 
 
+def workload_config(args, world):
+    """the `config` object both arms print (the reference arm times the SAME workload on the host cores)"""
+    rgb = args.frames == "rgb"
+    N = args.envs * args.horizon
+    return {"workload": ("PPO Breakout-shaped, %d envs/GPU x %d-step rollout, %s, "
+                         "%d epochs x mb %d, Adam; synthetic %s emulator frames"
+                         % (args.envs, args.horizon,
+                            "classic Nature-CNN @ (4,84,84)" if rgb else "cnn preset %d @ (4,104,80)" % args.spec,
+                            args.epochs, args.minibatch, "210x160x3 RGB" if rgb else "210x160 grayscale")),
+            "frames": args.frames,
+            "algo": args.algo, "learner": ("single" if world == 1 and args.parallelism == "sync" else args.parallelism),
+            "envs_per_gpu": args.envs, "horizon": args.horizon, "parallelism": "dp%d" % world,
+            "l2_policy": "inputs larger than L2 (%.2f GB rollout buffer, %d MB frame pool)" %
+                         (N * 4 * (84 * 84 if rgb else 104 * 80) / 1e9,
+                          args.pool_frames * (100800 if rgb else 33600) // 2 ** 20),
+            "step": "one full PPO iteration"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -365,18 +383,7 @@ def run_ours(args):
             "unit": "env-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": ("PPO Breakout-shaped, %d envs/GPU x %d-step rollout, %s, "
-                                    "%d epochs x mb %d, Adam; synthetic %s emulator frames"
-                                    % (args.envs, args.horizon,
-                                       "classic Nature-CNN @ (4,84,84)" if rgb else "cnn preset %d @ (4,104,80)" % args.spec,
-                                       args.epochs, args.minibatch, "210x160x3 RGB" if rgb else "210x160 grayscale")),
-                       "frames": args.frames,
-                       "algo": args.algo, "learner": ("single" if world == 1 and args.parallelism == "sync" else args.parallelism),
-                       "envs_per_gpu": args.envs, "horizon": args.horizon, "parallelism": "dp%d" % world,
-                       "l2_policy": "inputs larger than L2 (%.2f GB rollout buffer, %d MB frame pool)" %
-                                    (N * 4 * (84 * 84 if rgb else 104 * 80) / 1e9,
-                                     args.pool_frames * (100800 if rgb else 33600) // 2 ** 20),
-                       "step": "one full PPO iteration"},
+            "config": workload_config(args, world),
             "clocks": clk,
             "gpu_launches": int(launches),
             "model_flops_per_env_step": flop_step,
@@ -422,15 +429,23 @@ def run_ours(args):
 # =============================================================================================
 # CPU port of the reference path (oracle/): --impl reference and the cpu_baseline leg
 # =============================================================================================
+def ref_n_parallel(envs, cores):
+    """simulator processes per alternating group: the largest divisor of envs/2 that is <= (cores - 1) // 2
+    (SURVEY.md 8d / BASELINE.md 3: 2*n_parallel workers + the master)"""
+    cap = max(1, (cores - 1) // 2)
+    return max(d for d in range(1, cap + 1) if (envs // 2) % d == 0)
+
+
 def cpu_port(args, steps=1, warmup=0):
-    """The reference's CPU implementation of the path, restated (oracle/): vectorised-sampler semantics with the
-    synthetic emulator + fp32 policy on the CPU + GAE + PPO epochs, on a BOUNDED sample of the workload:
-    `--cpu-sample-steps` rollout steps of all envs, trained for the same epochs x minibatch ratio."""
+    """The reference's CPU implementation of the path, restated (oracle/): the MULTI-PROCESS sampler structure of
+    ActsrvAltOvrlpSampler (oracle/mp_sampler.py: 2*n_parallel simulator processes in two alternating groups, shared
+    buffers, semaphores; the master serves actions from an fp32 torch-CPU policy) + GAE + PPO epochs on all host threads,
+    on a BOUNDED sample of the workload per step: `--cpu-sample-steps` rollout steps of all envs, trained for the same
+    epochs x minibatch ratio.  -> per-step records (what was actually timed)"""
     import numpy as np
     import torch
-    from oracle import net as onet, sampler as osampler, learner as olearner, synth_ale
+    from oracle import net as onet, mp_sampler, learner as olearner, synth_ale
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     B, Ts = args.envs, args.cpu_sample_steps
     rgb = getattr(args, "frames", "gray") == "rgb"
     spec = dict(NATURE84_SPEC, conv_pads=[0, 0, 0]) if rgb else onet.CNN_SPECS[args.spec]
@@ -438,35 +453,43 @@ def cpu_port(args, steps=1, warmup=0):
     pool = synth_ale.make_pool(256, seed=0, channels=3) if rgb else synth_ale.make_pool(256, seed=0)
     flat = onet.init_params(spec, (4, 84, 84) if rgb else (4, 104, 80), 4, np.random.RandomState(0),
                             np.random.RandomState(1))
-    smp = osampler.OracleSampler(B, Ts, pool, rules, 4, 0.99)
+    n_par = ref_n_parallel(B, cores)
+    master_threads = max(1, cores - 2 * n_par)
+    smp = mp_sampler.MpOracleSampler(n_par, B // (2 * n_par), Ts, pool, rules, 4, 0.99)
     opt = onet.Adam(flat.size, 1e-3, epsilon=1e-5)
     rng = np.random.RandomState(0)
 
     def policy_fn(obs):
         with torch.no_grad():
-            p, v = onet.forward(torch.from_numpy(flat), torch.from_numpy(obs), spec, 4)
+            p, v = onet.forward(torch.from_numpy(flat), torch.from_numpy(np.ascontiguousarray(obs)), spec, 4)
         return p.numpy(), v.numpy()
 
     mb = min(args.minibatch, B * Ts)
     times = []
-    for it in range(warmup + steps):
-        t0 = time.time()
-        buf, _ = smp.obtain_samples(policy_fn, rng.rand(Ts, B))
-        t1 = time.time()
-        flat, _, _, _ = olearner.optimize_policy(flat, opt, buf, spec, 4, Ts, "ppo", rng, epochs=args.epochs,
-                                                 minibatch_size=mb, emulate_bf16=False)
-        t2 = time.time()
-        if it >= warmup:
-            times.append((t1 - t0, t2 - t1))
+    try:
+        for it in range(warmup + steps):
+            torch.set_num_threads(master_threads)        # the simulator processes own the other cores while sampling
+            t0 = time.time()
+            buf, _ = smp.obtain_samples(policy_fn, rng.rand(Ts, B))
+            t1 = time.time()
+            torch.set_num_threads(cores)
+            flat, _, _, _ = olearner.optimize_policy(flat, opt, buf, spec, 4, Ts, "ppo", rng, epochs=args.epochs,
+                                                     minibatch_size=mb, emulate_bf16=False)
+            t2 = time.time()
+            if it >= warmup:
+                times.append((t1 - t0, t2 - t1))
+    finally:
+        smp.shutdown()
     samp = float(np.mean([a for a, _ in times]))
     learn = float(np.mean([b for _, b in times]))
     n = B * Ts
     return {"value": round(n / (samp + learn), 1), "unit": "env-steps/s", "cores": cores, "kind": "port",
-            "sample": "%d envs x %d rollout steps (%d env-steps) + GAE + %d epochs x mb %d on them; oracle/ port: Theano "
-                      "replaced by an fp32 torch-CPU restatement (%d threads), ALE by the synthetic emulator"
-                      % (B, Ts, n, args.epochs, mb, cores),
+            "sample": "per step: %d envs x %d rollout steps (%d env-steps) through %d simulator processes (two alternating "
+                      "groups of %d) + master, then GAE + %d epochs x mb %d on them; oracle/ port: Theano replaced by an fp32 "
+                      "torch-CPU restatement (%d threads serving actions, %d for the learner), ALE by the synthetic emulator"
+                      % (B, Ts, n, 2 * n_par, n_par, args.epochs, mb, master_threads, cores),
             "sampler_env_steps_per_s": round(n / samp, 1), "learner_env_steps_per_s": round(n / learn, 1),
-            "seconds_per_sample": round(samp + learn, 2)}
+            "seconds_per_sample": round(samp + learn, 3), "sample_env_steps": n, "sim_processes": 2 * n_par}
 
 
 def run_frame_sweep(args):
@@ -522,24 +545,22 @@ def run_frame_sweep(args):
 
 
 def run_reference(args):
+    """reference arm: the reference's own CPU implementation of the path (oracle port, see cpu_port) on the host cores, on
+    OUR arm's metric / unit / config.  One "step" = one bounded sample of the workload; ms_per_step is what was actually
+    timed per step, value = env-steps of the sample / that time (a rate: no extrapolation enters it)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     t0 = time.time()
-    r = cpu_port(args, steps=max(1, args.steps), warmup=min(1, args.warmup))
-    N = args.envs * args.horizon
-    out = {"impl": "reference", "metric": "env-steps/sec (PPO Atari, 256 envs/GPU)", "value": r["value"],
-           "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": round(1e3 * N / r["value"], 1), "higher_is_better": True, "scaling": "weak",
+    r = cpu_port(args, steps=max(1, args.steps), warmup=max(0, args.warmup))
+    out = {"impl": "reference", "metric": "env-steps/sec (%s Atari, %d envs/GPU)" % (args.algo.upper(), args.envs),
+           "value": r["value"], "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": round(1e3 * r["seconds_per_sample"], 1), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "PPO Breakout-shaped, %d envs x %d-step rollout, %s, %d epochs x "
-                                  "mb %d (CPU port of the reference path; ms_per_step extrapolated from the bounded sample)"
-                                  % (args.envs, args.horizon,
-                                     "classic Nature-CNN @ (4,84,84), RGB frames" if args.frames == "rgb"
-                                     else "cnn preset %d @ (4,104,80)" % args.spec, args.epochs, args.minibatch),
-                      "frames": args.frames},
+           "config": workload_config(args, args.gpus),
            "cpu_baseline": r,
            "e2e": {"value": r["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0,
            "wall_s": round(time.time() - t0, 1)}
     _emit(out)
 

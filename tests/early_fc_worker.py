@@ -41,6 +41,8 @@ def main():
     st = eng.get_opt_state()
     out = dict(params=dig(eng.get_params()), m=dig(st["m"]), v=dig(st["v"]), step=st["step"], norms=norms,
                device_error=eng.device_error())
+    if os.environ.get("ARL_AB_DUMP"):        # dev aid: keep the arrays themselves
+        np.savez(os.environ["ARL_AB_DUMP"], params=eng.get_params(), m=st["m"], v=st["v"], layout=np.array(eng.layout))
     eng.close()
     print("RESULT " + json.dumps(out))
 

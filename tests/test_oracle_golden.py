@@ -128,3 +128,41 @@ def test_rgb_frame_oracle_known_answers(golden_dir):
         flat = np.full((210, 160, 3), v, np.uint8)
         assert (oframe.rgb_downsample(oframe.rgb_to_gray(flat)) == v).all()
     assert oframe.rgb_to_gray(np.array([[255, 0, 0], [0, 255, 0], [0, 0, 255]], np.uint8)).tolist() == [77, 149, 29]   # (w*255 + 128) >> 8
+
+
+@pytest.mark.parametrize("kind", ["adam", "rmsprop"])
+def test_update_rules_match_executed_reference(golden_dir, kind):
+    """oracle Adam / RMSProp vs OUTPUTS of the reference's own statement of the rules: update_methods_stats.py:11-32,
+    :55-87 executed unmodified under oracle/theano_shim.py (tests/golden/make_golden_updates.py), six steps with a
+    changing lr_mult and exact-zero gradients.  Differences are 1-2 ulp of the parameter (float32 vs float64
+    evaluation of Adam's bias-correction scalar)."""
+    g = _load(golden_dir, "update_rules.npz")
+    n = g["p0"].size
+    opt = onet.Adam(n, 1e-3, epsilon=1e-5) if kind == "adam" else onet.RMSProp(n, 7e-4)
+    p = g["p0"].copy()
+    for t in range(len(g["grads"])):
+        p = opt.step(p, g["grads"][t], float(g["lr_mults"][t]))
+        assert p.dtype == np.float32
+        np.testing.assert_allclose(p, g[kind][t], rtol=1e-6, atol=3e-8)
+        upd, want = p - g["p0"], g[kind][t] - g["p0"]
+        assert np.abs(upd - want).max() <= 2e-5 * np.abs(want).max()
+
+
+def test_theano_shim_update_semantics():
+    """the eager stand-in applies a function's updates simultaneously and keeps its shared state across steps"""
+    from collections import OrderedDict
+    from oracle import theano_shim as S
+    sess = S.Session()
+
+    def fn(g, p):
+        acc = sess.shared(np.zeros(2, np.float32))
+        new_acc = acc + g
+        up = OrderedDict()
+        up[acc] = new_acc
+        up[p] = p - new_acc          # uses the NEW accumulator expression, evaluated from pre-update values
+        return up, []
+    p = S.Shared(np.array([1.0, 2.0], np.float32))
+    for _ in range(3):
+        sess.step(fn, np.array([0.5, 1.0], np.float32), p)
+    assert len(sess.vars) == 1 and np.array_equal(sess.vars[0].value, [1.5, 3.0])
+    assert np.array_equal(p.value, np.array([1.0 - 0.5 - 1.0 - 1.5, 2.0 - 1.0 - 2.0 - 3.0], np.float32))
