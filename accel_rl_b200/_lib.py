@@ -107,6 +107,7 @@ SIGNATURES = {
     "arl_sampler_configure": (C.c_int, [_P, C.POINTER(SamplerCfg)]),
     "arl_sampler_select": (C.c_int, [_P, C.c_int]),
     "arl_sampler_reset": (C.c_int, [_P, _P]),
+    "arl_sampler_warmup": (C.c_int, [_P, _P, C.c_int, _P]),
     "arl_rollout_begin": (C.c_int, [_P, _P]),
     "arl_rollout_step": (C.c_int, [_P, C.c_int, _P, _P]),
     "arl_rollout_end": (C.c_int, [_P, _P]),

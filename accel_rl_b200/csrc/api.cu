@@ -1574,7 +1574,7 @@ int rollout_step(arl_ctx* c, int s_idx, const uint8_t* staging, cudaStream_t st)
   const int B = s.n_envs, T = s.horizon;
   // the env step of env e runs in the head kernel's block e right after its action is sampled
   EnvStepArgs es{synth_cfg(s), c->est, c->tout, c->cmd, s.rewards, s.dones, s.raw_reward, s.need_reset, B, T, s_idx,
-                 s.max_path_length, s.discount, s.mid_batch_reset, s.clip_reward, s.episodic_lives};
+                 s.max_path_length, s.discount, s.mid_batch_reset, s.clip_reward, s.episodic_lives, nullptr, 0};
   if (policy_forward16(c, c->step_obs16, B, c->rows_tab + (long)s_idx * B, s.prob, s.value,
                        s.uniforms + (long)s_idx * B, s.actions, c->pc_mode >= 2, st, &es))
     return 1;
@@ -1834,6 +1834,25 @@ int arl_sampler_reset(arl_ctx* c, void* stream) {
   c->launches++;
   ARL_CHECK(c, cudaGetLastError());
   return launch_frame(c, nullptr, 0, false, st);
+}
+
+/* start_envs decorrelation (sampler/util.py:26-57): after arl_sampler_reset, env e takes n_steps[e] warm-up steps (device
+   array [n_envs]; the synthetic emulator ignores actions, so the reference's random actions need no counterpart), is reset
+   whenever its trajectory ends, and starts the first rollout from the observation it reached.  max_steps >= max n_steps. */
+int arl_sampler_warmup(arl_ctx* c, const int* n_steps, int max_steps, void* stream) {
+  if (!c->sampler_set) ARL_FAIL(c, "sampler not configured");
+  if (c->sc.ext_emulator) ARL_FAIL(c, "external emulators decorrelate in their worker processes");
+  cudaStream_t st = (cudaStream_t)stream;
+  const arl_sampler_cfg& s = c->sc;
+  for (int k = 0; k < max_steps; ++k) {
+    EnvStepArgs es{synth_cfg(s), c->est, c->tout, c->cmd, s.rewards, s.dones, s.raw_reward, s.need_reset, s.n_envs, s.horizon, 0,
+                   s.max_path_length, s.discount, /*mid_batch_reset=*/1, s.clip_reward, s.episodic_lives, n_steps, k};
+    env_step_kernel<<<(s.n_envs + 127) / 128, 128, 0, st>>>(es);
+    c->launches++;
+    ARL_CHECK(c, cudaGetLastError());
+    if (launch_frame(c, nullptr, 0, false, st)) return 1;
+  }
+  return 0;
 }
 
 int arl_rollout_begin(arl_ctx* c, void* stream) {

@@ -79,6 +79,9 @@ struct EnvStepArgs {
   SynthCfg cfg; EnvState st; TrajOut tout; FrameCmd* cmd;
   float* rewards; uint8_t* dones; float* raw_reward; uint8_t* info_need_reset;
   int n_envs, T, s, max_path_length; float discount; int mid_batch_reset, clip_reward, episodic_lives;
+  // start_envs decorrelation (sampler/util.py:33-55): warm_n != nullptr -> warm-up step number warm_k; env e takes it
+  // only while warm_k < warm_n[e], is reset at once when its trajectory ends, and nothing is recorded
+  const int* warm_n; int warm_k;
 };
 
 ARL_DEVINL void env_step_one(const EnvStepArgs& a, int e);
@@ -102,6 +105,13 @@ ARL_DEVINL void env_step_one(const EnvStepArgs& a, int e) {
   const float discount = a.discount;
   FrameCmd c;
   c.flags = 0;
+  const bool warm = a.warm_n != nullptr;
+  if (warm && a.warm_k >= a.warm_n[e]) {
+    c.src_a = c.src_b = -1;
+    c.flags = 2;
+    cmd[e] = c;
+    return;
+  }
   if (!mid_batch_reset && st.need_reset[e]) {
     c.src_a = c.src_b = -1;
     c.flags = 2;  // stale rows stay as they are (worker.py:78 `if not need_reset[i]`)
@@ -148,10 +158,12 @@ ARL_DEVINL void env_step_one(const EnvStepArgs& a, int e) {
   if (over_length || (done && env_says_reset)) {
     done = true;
     if (over_length && episodic_lives) need_reset_info = true;
-    int slot = atomicAdd(tout.count, 1);
-    if (slot < tout.cap) {
-      tout.env[slot] = e; tout.len[slot] = len; tout.ret[slot] = tret; tout.raw[slot] = traw;
-      tout.nz[slot] = tnz; tout.disc[slot] = tdisc;
+    if (!warm) {
+      int slot = atomicAdd(tout.count, 1);
+      if (slot < tout.cap) {
+        tout.env[slot] = e; tout.len[slot] = len; tout.ret[slot] = tret; tout.raw[slot] = traw;
+        tout.nz[slot] = tnz; tout.disc[slot] = tdisc;
+      }
     }
     len = 0; tret = 0.f; traw = 0.f; tnz = 0; tdisc = 0.f; cur = 1.f;
     if (mid_batch_reset) {
@@ -169,6 +181,8 @@ ARL_DEVINL void env_step_one(const EnvStepArgs& a, int e) {
   st.f[e] = f;
   st.traj_len[e] = len; st.traj_ret[e] = tret; st.traj_raw[e] = traw; st.traj_nz[e] = tnz;
   st.traj_disc[e] = tdisc; st.traj_cur[e] = cur;
+  cmd[e] = c;
+  if (warm) return;
   long row = (long)e * T + s;
   rewards[row] = r;
   dones[row] = done ? 1 : 0;

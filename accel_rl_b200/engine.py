@@ -131,6 +131,12 @@ class Engine(object):
     def sampler_reset(self):
         self.check(self.lib.arl_sampler_reset(self.ctx, self._s()))
 
+    def sampler_warmup(self, n_steps):
+        """start_envs decorrelation: env e takes n_steps[e] warm-up steps (int32 device tensor [n_envs])"""
+        mx = int(n_steps.max().item()) if n_steps.numel() else 0
+        if mx > 0:
+            self.check(self.lib.arl_sampler_warmup(self.ctx, L.ptr(n_steps), mx, self._s()))
+
     def rollout_run(self):
         self.check(self.lib.arl_rollout_run(self.ctx, self._s()))
 

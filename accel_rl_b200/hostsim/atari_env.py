@@ -120,5 +120,10 @@ def make_ale(game="pong", repeat_action_probability=0.):
     ale = ale_py.ALEInterface()
     ale.setFloat("repeat_action_probability", repeat_action_probability)
     import ale_py.roms as roms
-    ale.loadROM(getattr(roms, game.capitalize()))
+    ale.loadROM(getattr(roms, rom_attr(game)))
     return ale
+
+
+def rom_attr(game):
+    """ale_py names its ROMs in CamelCase: 'space_invaders' -> 'SpaceInvaders' (atari_py uses the snake_case name)"""
+    return "".join(part.capitalize() for part in str(game).split("_"))

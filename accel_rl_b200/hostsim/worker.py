@@ -13,7 +13,7 @@ import numpy as np
 
 from accel_rl_b200.hostsim.atari_env import HostAtariEnv, FLAG_RESET, FLAG_SKIP, FLAG_NO_RECORD
 
-CMD_STEP, CMD_RESET_NEEDED, CMD_QUIT = 0, 1, 2
+CMD_STEP, CMD_RESET_NEEDED, CMD_QUIT, CMD_WARM = 0, 1, 2, 3
 
 EXT_DTYPE = np.dtype([("reward", np.float32), ("raw_reward", np.float32), ("done", np.uint8), ("need_reset", np.uint8),
                       ("flags", np.uint8), ("pad", np.uint8)])      # arl_ext_step
@@ -49,9 +49,31 @@ class Collector(object):
         e = self.env_lo + i
         self.ext[e] = (0., 0., 0, 0, self.envs[i].reset(self.frames[e, 1]), 0)
 
-    def start(self):
+    def start(self, max_decorrelation_steps=0):
+        """start_envs (sampler/util.py:26-57): reset every env; with max_decorrelation_steps > 0 also draw, per env, how
+        many random-action warm-up steps it takes (the reference derives the fraction from the wall clock,
+        sampler/util.py:22-23; here it comes from the worker's seeded numpy stream) -> the largest count"""
         for i in range(len(self.envs)):
             self._reset(i)
+        self.warm_n = [int(np.random.rand() * max_decorrelation_steps) if max_decorrelation_steps > 0 else 0
+                       for _ in self.envs]
+        return max(self.warm_n) if self.warm_n else 0
+
+    def warm_step(self, k):
+        """warm-up step k of start_envs (sampler/util.py:44-53): envs with warm_n > k take a uniformly random action
+        (action_space.sample), are reset at once when their trajectory ends; nothing is recorded or reported"""
+        for i, env in enumerate(self.envs):
+            e = self.env_lo + i
+            if k >= self.warm_n[i]:
+                self.ext[e] = (0., 0., 0, 0, FLAG_SKIP | FLAG_NO_RECORD, 0)
+                continue
+            r, raw, d, nr, fl = env.step(int(np.random.randint(env.n_actions)), self.frames[e, 0], self.frames[e, 1])
+            t = self.trajs[i]
+            t["Length"] += 1
+            if t["Length"] > self.max_path_length or (d and (True if nr is None else nr)):
+                self.trajs[i] = _new_traj()
+                fl = env.reset(self.frames[e, 1])
+            self.ext[e] = (0., 0., 0, 0, fl | FLAG_NO_RECORD, 0)
 
     def reset_needed(self):                                # worker.py:106-113
         for i in range(len(self.envs)):
@@ -91,12 +113,15 @@ class Collector(object):
 
 
 def worker_main(rank, env_lo, env_hi, n_envs, emu_factory, env_kwargs, frame_shape, shared, cmd, act_ready, step_done,
-                infos_queue, seed, mid_batch_reset, max_path_length, discount):
+                infos_queue, seed, mid_batch_reset, max_path_length, discount, max_decorrelation_steps=0):
     np.random.seed(seed)                                   # initialize_worker: seed + rank (sampler/util.py:60-72)
     frames, ext, act = views(shared, n_envs, frame_shape)
     col = Collector(env_lo, env_hi, emu_factory, env_kwargs, frames, ext, act, infos_queue.put, mid_batch_reset,
                     max_path_length, discount)
-    col.start()                                            # start_envs (max_decorrelation_steps == 0)
+    # what the master checks before the first step: the emulators' action count and this worker's warm-up length
+    report = np.frombuffer(shared["report"], dtype=np.int32).reshape(-1, 2)
+    report[rank, 0] = col.envs[0].n_actions if all(e.n_actions == col.envs[0].n_actions for e in col.envs) else -1
+    report[rank, 1] = col.start(max_decorrelation_steps)   # start_envs
     step_done.release()
     while True:
         act_ready.acquire()
@@ -105,6 +130,8 @@ def worker_main(rank, env_lo, env_hi, n_envs, emu_factory, env_kwargs, frame_sha
             break
         if c == CMD_RESET_NEEDED:
             col.reset_needed()
+        elif c == CMD_WARM:
+            col.warm_step(int(shared["arg"][0]))
         else:
             col.step()
         step_done.release()

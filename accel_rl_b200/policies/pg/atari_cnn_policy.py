@@ -98,15 +98,13 @@ class AtariCnnPolicy(object):
 
     # ------------------------------------------------------------------ engine ---------------
     def reserve(self, rows):
-        """Tell the policy the largest batch it will see (sampler envs, training minibatch)."""
+        """Tell the policy the largest batch it will see (sampler envs, training minibatch).  Only BEFORE the engine
+        exists does this size the workspaces; a live engine is never re-created (the optimizer, the sampler and the
+        multi-GPU learners hold state inside it) — larger inference batches are simply served in slices of
+        engine.max_rows (see _forward / get_actions)."""
         rows = int(rows)
-        if rows > self._reserve:
+        if self._engine is None and rows > self._reserve:
             self._reserve = rows
-            if self._engine is not None and rows > self._engine.max_rows:
-                params = self._engine.get_params()
-                self._engine.close()
-                self._engine = None
-                self._host_params = params
 
     @property
     def engine(self):
@@ -122,18 +120,22 @@ class AtariCnnPolicy(object):
         return self._engine
 
     # ------------------------------------------------------------------ inference ------------
-    def _forward(self, observations, want_prob=True, want_value=True):
+    def _forward(self, observations, want_prob=True, want_value=True, uniforms=None, actions=None):
         eng = self.engine
         is_np = not torch.is_tensor(observations)
         obs = torch.as_tensor(np.ascontiguousarray(observations)) if is_np else observations
         obs = obs.to(eng.device, non_blocking=True).contiguous()
         n = obs.shape[0]
-        if n > eng.max_rows:
-            self.reserve(n)
-            eng = self.engine
         prob = torch.empty((n, eng.n_actions), dtype=torch.float32, device=eng.device) if want_prob else None
         value = torch.empty((n,), dtype=torch.float32, device=eng.device) if want_value else None
-        eng.forward(obs, n=n, prob=prob, value=value)
+        # batches larger than the engine's workspaces (e.g. a diagnostic dist_info over the whole rollout) go through in
+        # slices: rows are independent, so the result is the same
+        for lo in range(0, n, eng.max_rows):
+            hi = min(n, lo + eng.max_rows)
+            eng.forward(obs[lo:hi], n=hi - lo, prob=None if prob is None else prob[lo:hi],
+                        value=None if value is None else value[lo:hi],
+                        uniforms=None if uniforms is None else uniforms[lo:hi],
+                        actions=None if actions is None else actions[lo:hi])
         if is_np:
             prob = prob.cpu().numpy() if prob is not None else None
             value = value.cpu().numpy() if value is not None else None
@@ -163,19 +165,12 @@ class AtariCnnPolicy(object):
         global legacy stream exactly like weighted_sample_n, the comparison runs on the device."""
         eng = self.engine
         is_np = not torch.is_tensor(observations)
-        obs = torch.as_tensor(np.ascontiguousarray(observations)) if is_np else observations
-        obs = obs.to(eng.device).contiguous()
-        n = obs.shape[0]
-        if n > eng.max_rows:
-            self.reserve(n)
-            eng = self.engine
-        prob = torch.empty((n, eng.n_actions), dtype=torch.float32, device=eng.device)
-        value = torch.empty((n,), dtype=torch.float32, device=eng.device)
+        n = len(observations)
         u = torch.from_numpy(np.random.rand(n)).to(eng.device)
         act = torch.empty((n,), dtype=torch.uint8, device=eng.device)
-        eng.forward(obs, n=n, prob=prob, value=value, uniforms=u, actions=act)
+        prob, value = self._forward(observations, uniforms=u, actions=act)
         if is_np:
-            return act.cpu().numpy(), dict(prob=prob.cpu().numpy(), value=value.cpu().numpy())
+            return act.cpu().numpy(), dict(prob=prob, value=value)
         return act, dict(prob=prob, value=value)
 
     def reset(self, n_batch=None):

@@ -151,10 +151,27 @@ class ActsrvAltOvrlpSampler(BaseMbSampler):
         cfg.traj_cap = max(4 * B, 1024)
         self._traj_cap = cfg.traj_cap
         eng.sampler_configure(cfg, keep=(buf, self.step_buf, self.frame_pool, self._uniforms, self._extra_obs))
-        eng.sampler_reset()                                # start_envs, max_decorrelation_steps == 0
+        eng.sampler_reset()                                # start_envs (sampler/util.py:26-57): env.reset() for every env
+        self._decorrelate(eng, B)
         if self.frame_feed == "host":
             self._init_host_feed()
         torch.cuda.synchronize(self.device)
+
+    def _decorrelate(self, eng, B):
+        """start_envs with max_decorrelation_steps > 0 (sampler/util.py:33-55): every env takes
+        int(fraction * max_decorrelation_steps) warm-up steps and is reset whenever its trajectory ends, so episodes do not
+        end in lockstep.  The reference takes `fraction` from the wall clock inside each worker process
+        (get_random_fraction, sampler/util.py:22-23); here it comes from a RandomState seeded by the sampler seed, which
+        keeps runs reproducible and stays off the master's global stream (as the workers' draws do)."""
+        mds = int(self.max_decorrelation_steps or 0)
+        self.decorrelation_steps = np.zeros(B, np.int32)
+        if mds <= 0:
+            return
+        if self.frame_feed == "host":
+            raise NotImplementedError("frame_feed='host' replays a fixed ring of raw frames; use max_decorrelation_steps=0")
+        rng = np.random.RandomState((int(self.seed) * 7919 + 17) % (2 ** 31 - 1))
+        self.decorrelation_steps = (rng.rand(B) * mds).astype(np.int32)
+        eng.sampler_warmup(torch.from_numpy(self.decorrelation_steps).to(self.device))
 
     def _init_host_feed(self):
         """Pinned ring of raw-frame step batches (what CPU emulator workers would have written) + a

@@ -82,7 +82,8 @@ class HostEmulatorSampler(ActsrvAltOvrlpSampler):
         ctx = mp.get_context("spawn")            # never fork a process that holds a CUDA context
         fbytes = int(np.prod(self._frame_shape))
         self._shared = dict(frames=ctx.RawArray(C.c_uint8, B * 2 * fbytes), ext=ctx.RawArray(C.c_uint8, B * W.EXT_DTYPE.itemsize),
-                            act=ctx.RawArray(C.c_uint8, B))
+                            act=ctx.RawArray(C.c_uint8, B), report=ctx.RawArray(C.c_int32, 2 * n_workers),
+                            arg=ctx.RawArray(C.c_int32, 1))
         self._frames_np, self._ext_np, self._act_np = W.views(self._shared, B, self._frame_shape)
         # page-lock the shared blocks so the copies below are real DMA transfers
         self._pinned = []
@@ -107,7 +108,8 @@ class HostEmulatorSampler(ActsrvAltOvrlpSampler):
             lo, hi = w * self.envs_per, (w + 1) * self.envs_per
             args = (w, lo, hi, B, factory, env_kwargs, self._frame_shape, self._shared, self._cmd,
                     self._act_ready[w], self._step_done[w], self._infos_queue, self.seed + w,
-                    bool(self.mid_batch_reset), self.max_path_length, float(self.discount))
+                    bool(self.mid_batch_reset), self.max_path_length, float(self.discount),
+                    int(self.max_decorrelation_steps or 0))
             if self.profile_pathname is not None:        # cProfile per simulator worker (sampler/util.py:10-19)
                 pr = ctx.Process(target=W.profiling_worker, daemon=True, args=(self.profile_pathname,) + args)
             else:
@@ -118,6 +120,24 @@ class HostEmulatorSampler(ActsrvAltOvrlpSampler):
         for g in range(2):
             self._wait_group(g)
             self._ingest_group(-1, g)
+        report = np.frombuffer(self._shared["report"], dtype=np.int32).reshape(-1, 2)
+        # the policy's action count must be the emulators' (the workers index getMinimalActionSet() with it)
+        A = self.env_spec.action_space.n
+        bad = [(w, int(a)) for w, a in enumerate(report[:, 0]) if int(a) != A]
+        if bad:
+            self.shutdown()
+            raise ValueError("the env spec has %d actions but emulator worker(s) %s report a minimal action set of %s: "
+                             "pass n_actions / game to EnvCls so both agree" % (A, [w for w, _ in bad], [a for _, a in bad]))
+        # start_envs decorrelation (sampler/util.py:33-55): warm-up rounds, every env for its own number of steps
+        self.decorrelation_rounds = int(report[:, 1].max())
+        for k in range(self.decorrelation_rounds):
+            self._shared["arg"][0] = k
+            torch.cuda.current_stream(self.device).synchronize()    # the previous round's frames have been consumed
+            for g in range(2):
+                self._release_group(g, W.CMD_WARM)
+            for g in range(2):
+                self._wait_group(g)
+                self._ingest_group(-1, g)
         self._pending = [False, False]           # no emulation outstanding
 
     def _group_range(self, g):

@@ -319,6 +319,59 @@ def workload_config(args, world):
             "step": "one full PPO iteration"}
 
 
+def sync_parity(runner, rank, world):
+    """Proof carried by every multi-GPU bench line (checked on the ranks that were just timed, after the timed region):
+    (1) the parameter vectors of all ranks are bit-identical after the training iterations; (2) one synchronous step
+    (fused P2P all-reduce + average + Adam, csrc/comm.cuh) from a known state equals the closed-form first Adam step
+    (optimizers/update_methods_stats.py:55-87) on the NCCL-averaged gradient — what optimizers/sync/base.py:22-24 +
+    optimizers/util.py:63-67 compute; (3) ... and leaves bit-identical parameters on every rank.  Raises on failure."""
+    import torch
+    import torch.distributed as dist
+    eng = runner.policy.engine
+    out = {}
+
+    def identical():
+        mine = eng.params.clone()
+        ref = mine.clone()
+        dist.broadcast(ref, src=0)
+        ok = torch.tensor([1 if torch.equal(mine, ref) else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        return bool(ok.item())
+    torch.cuda.synchronize()
+    out["ranks_bit_identical_after_training"] = identical()
+    cfg = eng.opt_cfg
+    if int(cfg.update) == 0:
+        eng.reset_opt_state()
+        eng.set_lr_mult(1.0)
+        eng.read_logs()
+        p0 = eng.params.clone()
+        g = torch.randn(eng.n_params, device="cuda", generator=torch.Generator("cuda").manual_seed(1000 + rank)) * 0.01
+        eng.grad.copy_(g)
+        gavg = g.clone()
+        dist.all_reduce(gavg)
+        gavg /= world
+        torch.cuda.synchronize()
+        dist.barrier()
+        eng.sync_allreduce_update()
+        torch.cuda.synchronize()
+        b1, b2, eps, lr = float(cfg.beta1), float(cfg.beta2), float(cfg.epsilon), float(cfg.learning_rate)
+        norm = float(gavg.double().norm())
+        if float(cfg.grad_norm_clip) > 0:
+            gavg = gavg * (min(norm, float(cfg.grad_norm_clip)) / (1e-7 + norm))
+        a_t = lr * (1.0 - b2) ** 0.5 / (1.0 - b1)
+        want = p0 - a_t * ((1 - b1) * gavg) / (((1 - b2) * gavg * gavg).sqrt() + eps)
+        err = (eng.params - want).abs()
+        tol = 2e-7 + 2e-6 * want.abs()
+        _, norms = eng.read_logs()
+        out["sync_step_max_abs_err_vs_adam"] = float(err.max())
+        out["sync_step_within_tolerance"] = bool((err <= tol).all().item()) and abs(float(norms[0]) - norm) <= 1e-5 * norm
+        out["ranks_bit_identical_after_sync_step"] = identical()
+    out["world"] = world
+    if not all(v for k, v in out.items() if isinstance(v, bool)):
+        raise SystemExit("sync data-parallel parity check FAILED on rank %d: %s" % (rank, out))
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -343,6 +396,7 @@ def run_ours(args):
 
     result = None
     phases = phase_split(runner, itr)
+    parity = sync_parity(runner, rank, world) if (world > 1 and args.parallelism == "sync") else None
     if rank == 0:
         bd = kernel_breakdown(runner, args) if (args.spec == 1 and world == 1 and args.algo == "ppo" and
                                                 args.parallelism == "sync") else {}
@@ -395,6 +449,8 @@ def run_ours(args):
             "host_wall_s": round(wall, 3),
             "phases": phases,
         }
+        if parity is not None:
+            result["parity"] = parity
     # ---- e2e: raw frames from pinned host memory every step, results read back ----
     if not args.no_e2e:
         runner.policy.engine.close()

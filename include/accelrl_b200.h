@@ -119,6 +119,10 @@ int arl_sampler_configure(arl_ctx* ctx, const arl_sampler_cfg* cfg);
  * keeps only rewards/dones/actions/agent infos rows and the TrajInfo records). */
 int arl_sampler_select(arl_ctx* ctx, int slot);
 int arl_sampler_reset(arl_ctx* ctx, void* stream);                  /* start_envs (sampler/util.py:26-57) */
+/* start_envs with max_decorrelation_steps > 0 (sampler/util.py:33-55): after arl_sampler_reset env e takes n_steps[e]
+   (device int array [n_envs], each <= max_steps) warm-up steps, is reset whenever its trajectory ends (no TrajInfo is
+   reported, nothing is recorded) and starts the first rollout from the observation it reached */
+int arl_sampler_warmup(arl_ctx* ctx, const int* n_steps, int max_steps, void* stream);
 int arl_rollout_begin(arl_ctx* ctx, void* stream);
 /* one serve+step: forward on step_obs, sample, env step, frame update.  staging (optional):
  * host-fed raw frames [B][2][210][160] already on the device for this step */

@@ -149,6 +149,23 @@ class OracleSampler(object):
         for e, env in enumerate(self.envs):            # start_envs
             self.step_obs[e] = env.reset()
 
+    def decorrelate(self, n_steps):
+        """start_envs with max_decorrelation_steps > 0 (sampler/util.py:33-55) for GIVEN per-env warm-up step counts (the
+        reference draws them from the wall clock): env e takes n_steps[e] steps, is reset at once whenever its trajectory
+        ends (need_reset / over-length), and its running TrajInfo carries into the first rollout.  The synthetic
+        emulator ignores actions, so the reference's random actions need no counterpart."""
+        for e, env in enumerate(self.envs):
+            traj = TrajInfo(self.discount)
+            o = self.step_obs[e]
+            for _ in range(int(n_steps[e])):
+                o, r, d, info = env.step(0)
+                traj.step(float(r), float(info.get("raw_reward", r)))
+                if traj["Length"] > self.max_path_length or (d and info.get("need_reset", True)):
+                    o = env.reset()
+                    traj = TrajInfo(self.discount)
+            self.step_obs[e] = o
+            self.traj[e] = traj
+
     def obtain_samples(self, policy_fn, uniforms):
         """policy_fn(obs (n,P,104,80) u8) -> (prob (n,A) f32, value (n,) f32); uniforms (T, B) float64 in the
         master's consumption order (step-major, group 0 half then group 1 half)."""

@@ -200,12 +200,13 @@ def test_loss_and_gradient_vs_oracle(spec_id, algo, n, valids):
             errs.append(relerr(g[i:i + m], g_ref[i:i + m]))
             i += m
         print("PER-TENSOR spec=%d algo=%s n=%d valids=%s %s" % (spec_id, algo, n, valids, " ".join("%.1e" % e for e in errs)))
-        # activation gradients are stored in bf16 between layers: per-tensor relative error bound 1e-2 (rounding noise:
-        # 1.5e-2 when fewer than 50 samples carry weight — measured 1.2e-2 at 45 valid rows, 4e-3 at 512)
+        # activation gradients are stored in bf16 between layers: their rounding noise averages out over the samples that
+        # carry weight, so the per-tensor relative error falls like 1/sqrt(n_eff) — measured 1.2e-2 at 45 valid rows,
+        # < 1e-2 at 64, 4.4e-3 at the PPO minibatch of 512.  Bounds: 0.12/sqrt(n_eff) per tensor, 0.10/sqrt(n_eff) overall
         n_eff = int(vsub.sum()) if valids else n
         for k, s in enumerate(shapes):
-            assert errs[k] < (1e-2 if n_eff >= 50 else 1.5e-2), "tensor %d %s: %.3e" % (k, s, errs[k])
-        assert relerr(g, g_ref) < (5e-3 if n_eff >= 50 else 1.2e-2)
+            assert errs[k] < 0.12 / np.sqrt(n_eff), "tensor %d %s: %.3e (n_eff %d)" % (k, s, errs[k], n_eff)
+        assert relerr(g, g_ref) < 0.10 / np.sqrt(n_eff)
         # loss value (north-star: within 1e-4 relative of the bf16-mirrored graph ... 1e-3 abs floor)
         eng.clip_update(1.0)
         losses, norms = eng.read_logs()

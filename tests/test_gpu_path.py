@@ -24,7 +24,7 @@ def _make_sampler(n_parallel, envs_per, T, mid_batch_reset=True, max_path_length
         env_args.update(env_kw)
     return ActsrvAltOvrlpSampler(EnvCls=AtariEnv, env_args=env_args, horizon=T, n_parallel=n_parallel, envs_per=envs_per,
                                  max_path_length=max_path_length, mid_batch_reset=mid_batch_reset,
-                                 max_decorrelation_steps=0, **kw)
+                                 max_decorrelation_steps=kw.pop("max_decorrelation_steps", 0), **kw)
 
 
 def _buf_np(buf):
@@ -125,6 +125,53 @@ def test_device_sampler_vs_oracle_larger_batch():
     finally:
         pol.engine.close()
 
+
+
+@pytest.mark.parametrize("mbr,mpl", [(True, 27000), (False, 27000), (True, 11)])
+def test_decorrelated_start_vs_oracle(mbr, mpl):
+    """start_envs with max_decorrelation_steps > 0 (sampler/util.py:33-55): every env takes its own number of warm-up
+    steps before the first rollout (reset whenever its trajectory ends, running TrajInfo carried over).  The device
+    warm-up (arl_sampler_warmup) against the oracle's restatement with the same per-env step counts: all later rollout
+    buffers and trajectory records bit-exact."""
+    from accel_rl_b200.util.seeding import set_seed
+    rules = dict(synth_ale.DEFAULT_RULES, pool_frames=128, life_base=9, life_mod=5, reward_mod=7, pool_seed=0)
+    set_seed(11)
+    B, T = 16, 8
+    sampler = _make_sampler(4, 2, T, mid_batch_reset=mbr, max_path_length=mpl, rules=rules, max_decorrelation_steps=60)
+    sampler.initialize(seed=5, affinities=dict(), discount=0.99, need_extra_obs=True)
+    pol, flat, spec = make_policy(1, max_rows=B)
+    sampler.policy_init(pol)
+    n_steps = sampler.decorrelation_steps
+    assert n_steps.shape == (B,) and n_steps.max() < 60 and len(set(n_steps.tolist())) > B // 2
+    orc = osampler.OracleSampler(B, T, synth_ale.make_pool(128, seed=0), {k: v for k, v in rules.items() if k != "pool_seed"},
+                                 4, 0.99, mid_batch_reset=mbr, max_path_length=mpl)
+    orc.decorrelate(n_steps)
+    key = lambda t: (t["env"], t["Length"], round(float(t["Return"]), 4), t["NonzeroRewards"])
+    dkey = lambda t: (t.env, t.Length, round(float(t.Return), 4), t.NonzeroRewards)
+    try:
+        assert np.array_equal(t2n(sampler.step_buf.obs), orc.step_obs)
+        n_traj = 0
+        for itr in range(3):
+            buf, infos = sampler.obtain_samples(itr)
+            b = _buf_np(buf)
+            u = sampler._uniforms_host.numpy().copy()
+            gp = b["prob"].reshape(B, T, 4); gv = b["value"].reshape(B, T)
+            calls = {"k": 0}
+
+            def policy_fn(obs):
+                k = calls["k"]; calls["k"] += 1
+                s, j = divmod(k, 2)
+                lo, hi = j * B // 2, (j + 1) * B // 2
+                return gp[lo:hi, s], gv[lo:hi, s]
+            ob, oinf = orc.obtain_samples(policy_fn, u)
+            for k in ("observations", "extra_observations", "rewards", "dones", "raw_reward", "need_reset"):
+                assert np.array_equal(b[k], ob[k]), (k, itr)
+            assert sorted(dkey(t) for t in infos) == sorted(key(t) for t in oinf)
+            n_traj += len(infos)
+        assert n_traj > 0
+        assert pol.engine.device_error() == 0
+    finally:
+        pol.engine.close()
 
 
 def test_full_size_c2_rollout_bit_exact_and_update_properties():

@@ -67,7 +67,7 @@ def test_worker_processes_follow_the_collector_protocol(mbr):
     shape = (210, 160)
     fb = 210 * 160
     shared = dict(frames=ctx.RawArray(C.c_uint8, B * 2 * fb), ext=ctx.RawArray(C.c_uint8, B * W.EXT_DTYPE.itemsize),
-                  act=ctx.RawArray(C.c_uint8, B))
+                  act=ctx.RawArray(C.c_uint8, B), report=ctx.RawArray(C.c_int32, 2 * 2), arg=ctx.RawArray(C.c_int32, 1))
     frames, ext, act = W.views(shared, B, shape)
     cmd = ctx.Value("i", W.CMD_STEP, lock=False)
     ready = [ctx.Semaphore(0) for _ in range(2)]
@@ -85,6 +85,8 @@ def test_worker_processes_follow_the_collector_protocol(mbr):
         g1, g2 = np.zeros(shape, np.uint8), np.zeros(shape, np.uint8)
         for w in range(2):
             assert done[w].acquire(timeout=120)
+        # what each worker reports before the first step: its emulators' action count, its warm-up length (none here)
+        assert np.frombuffer(shared["report"], dtype=np.int32).tolist() == [4, 0, 4, 0]
         for e in range(B):
             assert ref[e].reset(g2) == ext[e]["flags"] == FLAG_RESET and np.array_equal(frames[e, 1], g2)
         rng = np.random.RandomState(0)
@@ -170,7 +172,7 @@ def test_profiling_worker_dumps_a_profile(tmp_path):
     ctx = mp.get_context("spawn")
     B, shape, fb = 2, (210, 160), 210 * 160
     shared = dict(frames=ctx.RawArray(C.c_uint8, B * 2 * fb), ext=ctx.RawArray(C.c_uint8, B * W.EXT_DTYPE.itemsize),
-                  act=ctx.RawArray(C.c_uint8, B))
+                  act=ctx.RawArray(C.c_uint8, B), report=ctx.RawArray(C.c_int32, 2 * 2), arg=ctx.RawArray(C.c_int32, 1))
     cmd = ctx.Value("i", W.CMD_STEP, lock=False)
     ready, done, q = ctx.Semaphore(0), ctx.Semaphore(0), ctx.Queue()
     env_kwargs = dict(frame_skip=4, clip_reward=True, episodic_lives=True, max_start_noops=0, rgb=False)
@@ -296,3 +298,60 @@ def test_collector_replays_the_real_reference_samplers_buffers(golden_dir, tag, 
         assert len(mine) == len(want)
         for a, b in zip(mine, want):
             np.testing.assert_allclose(a, b, rtol=1e-6)
+
+
+@pytest.mark.skipif(not ref_harness.available(), reason="the reference tree only exists in the build container")
+@pytest.mark.parametrize("mpl", [27000, 7])
+def test_decorrelated_start_vs_the_real_reference_start_envs(mpl):
+    """start_envs with max_decorrelation_steps > 0: hostsim's Collector (start + warm_step) AND the oracle's
+    OracleSampler.decorrelate next to the REFERENCE'S OWN start_envs (accel_rl/sampler/util.py:26-57, imported unmodified,
+    its wall-clock fraction replaced by a fixed sequence): same first observations, same running TrajInfos."""
+    pool = synth_ale.make_pool(32, seed=0)
+    rules = dict(RULES, life_base=9, life_mod=5)
+    ref_harness.install(pool=pool, rules=rules)
+    env_mod = ref_harness.ref("accel_rl.envs.atari_env")
+    util = ref_harness.ref("accel_rl.sampler.util")
+    B, max_steps = 6, 50
+    fracs = [0.0, 0.13, 0.5, 0.77, 0.99, 0.31]
+    want_n = [int(f * max_steps) for f in fracs]
+    # --- the reference ---
+    synth_ale.SynthALE.next_env_id = 0
+    renvs = [env_mod.AtariEnv(game="breakout", max_start_noops=0) for _ in range(B)]
+    it = iter(fracs)
+    saved = util.get_random_fraction
+    util.get_random_fraction = lambda: next(it)
+    try:
+        robs, rinfos = util.start_envs(renvs, max_steps, mpl, 0.99, unique_ID=1)
+    finally:
+        util.get_random_fraction = saved
+    # --- hostsim Collector: exported frames + flags, stacked on the CPU the way the device does ---
+    frames = np.zeros((B, 2, 210, 160), np.uint8)
+    ext = np.zeros(B, W.EXT_DTYPE)
+    act = np.zeros(B, np.uint8)
+    env_kwargs = dict(frame_skip=4, clip_reward=True, episodic_lives=True, max_start_noops=0, rgb=False)
+    col = W.Collector(0, B, partial(fake_ale.make, rules=rules), env_kwargs, frames, ext, act, None, True, mpl, 0.99)
+    step_obs = np.zeros((B, 4, oframe.H, oframe.W), np.uint8)
+
+    def ingest():
+        for e in range(B):
+            if not (ext[e]["flags"] & FLAG_SKIP):
+                step_obs[e] = _apply(step_obs[e], frames[e, 0], frames[e, 1], int(ext[e]["flags"]))
+    np.random.seed(1)
+    col.start(max_steps)
+    col.warm_n = list(want_n)                        # (the worker draws these from its own stream)
+    ingest()
+    for k in range(max(want_n)):
+        col.warm_step(k)
+        ingest()
+    for e in range(B):
+        assert np.array_equal(step_obs[e], robs[e]), e
+        assert col.trajs[e]["Length"] == rinfos[e].Length
+    # --- the oracle restatement ---
+    orc = osampler.OracleSampler(B, 4, pool, rules, 4, 0.99, max_path_length=mpl)
+    orc.decorrelate(want_n)
+    for e in range(B):
+        assert np.array_equal(orc.step_obs[e], robs[e]), e
+        t, r = orc.traj[e], rinfos[e]
+        assert (t["Length"], t["NonzeroRewards"]) == (r.Length, r.NonzeroRewards)
+        np.testing.assert_allclose([t["Return"], t["RawReturn"], t["DiscountedReturn"]],
+                                   [r.Return, r.RawReturn, r.DiscountedReturn], rtol=1e-6)
