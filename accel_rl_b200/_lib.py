@@ -136,6 +136,7 @@ SIGNATURES = {
     "arl_comm_buffers": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
     "arl_comm_connect": (C.c_int, [_P, _P]),
     "arl_sync_allreduce_update": (C.c_int, [_P, _P]),
+    "arl_comm_trace": (C.c_int, [_P, _P, C.c_int, _P]),
     "arl_comm_barrier": (C.c_int, [_P, _P]),
     "arl_async_local_init": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
     "arl_async_connect": (C.c_int, [_P, _P]),

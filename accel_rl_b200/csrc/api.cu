@@ -210,6 +210,11 @@ struct arl_ctx {
   int n_loss_rows = 0;                 // rows of the last head_kernel<1> launch (loss partial count)
   float lr_mult_host = 1.f;
   CommState comm;
+  // overlapped synchronous step (comm.cuh): the FC slice exchange runs on `cs` beside the conv gradient chain
+  cudaStream_t cs = nullptr;
+  cudaEvent_t ev_cs_in[2] = {nullptr, nullptr}, ev_cs_done = nullptr;
+  bool sync_overlap_active = false;
+  double* sync_tail_partial = nullptr;
   bool shadow_in_comm = false;         // wfc_t / wfc_bf16 lives inside comm's symmetric allocation (freed with it)
   AsyncState async_;
 };
@@ -1118,13 +1123,8 @@ int get_plan(arl_ctx* c, int n, TrainPlan** out) {
     jobs.push_back(bv);
   }
   P.n_jobs = (int)jobs.size();
-  P.fin_blocks = (int)((max_total + 255) / 256);
+  P.fin_blocks = (int)((max_total + kFinPerBlock - 1) / kFinPerBlock);
   for (auto& jb : jobs) P.fin_total += (long)jb.rows * jb.cols;
-  for (auto& jb : jobs) {       // one slot per finalize block that owns elements of the job
-    jb.ss_off = P.n_ss;
-    P.n_ss += (int)(((long)jb.rows * jb.cols + 255) / 256);
-  }
-  if (P.n_ss > kSsFinCap) ARL_FAIL(c, "sum-of-squares slot table too small");
   ARL_CHECK(c, cudaMalloc(reinterpret_cast<void**>(&P.jobs_dev), jobs.size() * sizeof(GradJob)));
   ARL_CHECK(c, cudaMemcpy(P.jobs_dev, jobs.data(), jobs.size() * sizeof(GradJob), cudaMemcpyHostToDevice));
   auto res = c->plans.emplace(n, P);
@@ -1134,9 +1134,8 @@ int get_plan(arl_ctx* c, int n, TrainPlan** out) {
 
 bool early_fc_ok(arl_ctx* c);
 int early_fc_update(arl_ctx* c, cudaStream_t st);
-bool merge_finalize_ok(arl_ctx* c, bool fct);
-bool producer_sumsq_ok(arl_ctx* c, bool fct);
 bool stream_update_ok(arl_ctx* c, bool fct);
+int sync_fc_exchange(arl_ctx* c, cudaStream_t ws, cudaStream_t st);
 
 // forward + loss + backward for one minibatch -> flat grad
 int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaStream_t st) {
@@ -1207,11 +1206,10 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
   }
   ConvLayer& LL = c->conv.back();
   // ---- FC wgrad: dW[Kfc][H] = a_last^T dh (direct, permuted rows) ----
-  const bool prod_ss = producer_sumsq_ok(c, fct);
-  c->pending_ss_fin = 0;
   if (fct) {
-    if (fc_wgrad_tiles(c, n, ws, prod_ss)) return 1;
+    if (fc_wgrad_tiles(c, n, ws)) return 1;
     prof_mark(c, "fc_wgrad", ws);
+    if (c->sync_overlap_active) ARL_CHECK(c, cudaEventRecord(c->ev_cs_in[0], ws));
   } else {
     DenseLoader<64> a{};
     a.src = LL.act; a.ld = c->Kfc; a.nrows = n;
@@ -1226,6 +1224,9 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
   if (fct) {
     if (fc_dgrad_tiles(c, n, st)) return 1;
     prof_mark(c, "fc_dgrad", st);
+    // synchronous learners: the FC gradient is final and the FC weights have been consumed -> its slice exchange + update
+    // starts now on its own stream, beside the conv gradient chain
+    if (c->sync_overlap_active && sync_fc_exchange(c, ws, st)) return 1;
     if (early_fc_ok(c)) {
       // both FC gradient kernels are issued: once the data gradient has read the weights (and the weight gradient,
       // earlier on ws, has written its rows of the flat gradient) the FC weights take their Adam/RMSProp step while
@@ -1267,6 +1268,7 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
     if (pconv_dgrad_layer(c, l, n, st)) return 1;
     prof_mark(c, kDgradName[l], st);
   }
+  if (c->sync_overlap_active) ARL_CHECK(c, cudaStreamWaitEvent(st, c->ev_cs_done, 0));
   if (ws != st) {
     ARL_CHECK(c, cudaEventRecord(c->ev_join, ws));
     ARL_CHECK(c, cudaStreamWaitEvent(st, c->ev_join, 0));
@@ -1319,14 +1321,9 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
   if (stream_update_ok(c, fct)) {
     c->pending_fin = P;        // clip_update: update_stream_kernel sums the partials and updates in the same pass
     c->pending_stream = true;
-  } else if (merge_finalize_ok(c, fct)) {
-    c->pending_fin = P;        // clip_update folds it into phase 1 of update_fused_kernel (one launch, one pass less)
   } else {
     dim3 grid(P->fin_blocks, P->n_jobs);
-    const bool ss = prod_ss && c->pending_ss_fc > 0;
-    if (ss) ARL_CHECK(c, launch_k(finalize_grads_ss_kernel, dim3(grid), dim3(256), 0, st, P->jobs_dev, c->grad, c->ss_fin));
-    else ARL_CHECK(c, launch_k(finalize_grads_kernel, dim3(grid), dim3(256), 0, st, P->jobs_dev, c->grad));
-    c->pending_ss_fin = ss ? P->n_ss : 0;
+    ARL_CHECK(c, launch_k(finalize_grads_kernel, dim3(grid), dim3(256), 0, st, P->jobs_dev, c->grad));
     c->launches++;
     prof_mark(c, "finalize_grads", st);
     ARL_CHECK(c, cudaGetLastError());
@@ -1360,31 +1357,6 @@ bool early_fc_ok(arl_ctx* c) {
   static const bool fused = !(getenv("ARL_FUSED_UPDATE") && atoi(getenv("ARL_FUSED_UPDATE")) == 0);
   return on && fused && c->train_step_active && c->opt_set && c->opt.grad_norm_clip <= 0.f && c->m && c->v &&
          c->pc_mode >= 2 && fc_tiles_ok(c) && (c->off_Wfc % 4 == 0) && (((long)c->Kfc * c->H) % 4 == 0);
-}
-
-// grad_minibatch leaves the gradient finalisation to the update kernel when the local fused update follows it and the
-// FC weight gradient is written straight into the flat vector (so the finalisation jobs cover exactly "everything else").
-// OFF by default (ARL_MERGE_FINALIZE=1 enables; results identical): measured slower — 40.7 us for the merged kernel
-// against 5.3 + 22.8 us for finalize_grads + update_fused, 57.4 vs 55.6 ms per iteration.  The partial sums are long
-// dependent load chains (64..148 partials per element) that want many more threads in flight than the 592 x 256
-// co-resident ones the grid barrier allows, and every block waits at the barrier for the slowest chain.
-bool merge_finalize_ok(arl_ctx* c, bool fct) {
-  static const bool on = getenv("ARL_MERGE_FINALIZE") && atoi(getenv("ARL_MERGE_FINALIZE")) != 0;
-  static const bool fused = !(getenv("ARL_FUSED_UPDATE") && atoi(getenv("ARL_FUSED_UPDATE")) == 0);
-  return on && fused && fct && c->train_step_active && c->opt_set && c->m && c->v && (c->off_Wfc % 4 == 0) &&
-         (((long)c->Kfc * c->H) % 4 == 0);
-}
-
-// The kernels that write the flat gradient (FC weight-gradient tiles, finalize_grads) also leave the sums of squares of
-// what they wrote, so the local update that follows needs no pass over the gradient and no grid barrier for the norm.
-// Only inside train_minibatches (nobody can touch the gradient between the two), fused-update configuration.
-// OFF by default (ARL_PRODUCER_SUMSQ=1 enables; all parity tests pass with it): measured 56.6 vs 54.5 ms per iteration —
-// the update kernel drops from 21.8 to 18.7 us, but the finalize kernel with the block reduction takes 11.9 us instead
-// of 5.6 us.
-bool producer_sumsq_ok(arl_ctx* c, bool fct) {
-  static const bool on = getenv("ARL_PRODUCER_SUMSQ") && atoi(getenv("ARL_PRODUCER_SUMSQ")) != 0;
-  static const bool fused = !(getenv("ARL_FUSED_UPDATE") && atoi(getenv("ARL_FUSED_UPDATE")) == 0);
-  return on && fused && fct && c->train_step_active && !early_fc_ok(c) && !merge_finalize_ok(c, fct);
 }
 
 // Without global-norm clipping nothing in the update depends on the norm: finalisation, update, operand refresh and
@@ -1459,7 +1431,7 @@ int clip_update(arl_ctx* c, float gscale, cudaStream_t st) {
     u.pk_slots = c->pk_slots; u.n_pk_jobs = c->n_pack_jobs - 1; u.conv_end = c->conv_pack_end;
     u.adv_done = c->ticket + 1; u.adv_log_slot = c->log_slot; u.adv_mb = c->mb_counter;
     // blocks [0, nA) sum the split partials and update everything except the FC weights, the other 4 x 148 stream the FC range
-    const int nA = (int)((P_total + 255) / 256);
+    const int nA = (int)((P_total + kFinPerBlock - 1) / kFinPerBlock);
     int nB = kSumsqBlocks;
     if (u.skip4_len > 0) {
       // the FC range already took its step (update_range_kernel, beside the conv gradient chain): only part A is left
@@ -1476,13 +1448,7 @@ int clip_update(arl_ctx* c, float gscale, cudaStream_t st) {
   }
   // norm + clip + update in one launch (update_fused_kernel); ARL_FUSED_UPDATE=0 keeps the two-kernel form
   static const bool fused = !(getenv("ARL_FUSED_UPDATE") && atoi(getenv("ARL_FUSED_UPDATE")) == 0);
-  if (c->pending_ss_fin > 0 && c->pending_ss_fc > 0 && gscale == 1.f && u.n_fin_jobs == 0 && u.skip4_len == 0) {
-    // global-norm partials already produced (producer_sumsq_ok): one plain launch, no sum-of-squares pass, no barrier
-    u.sumsq_partial = c->ss_fin; u.n_partial = c->pending_ss_fin;
-    u.sumsq_partial2 = c->ss_fc; u.n_partial2 = c->pending_ss_fc;
-    c->pending_ss_fin = c->pending_ss_fc = 0;
-    ARL_CHECK(c, launch_k(update_kernel, dim3(148 * 4), dim3(256), 0, st, u));
-  } else if (fused) {
+  if (fused) {
     // conv operand packs refreshed by the update itself + counters advanced by its last block: no pack launch at all
     static const bool scatter_on = !(getenv("ARL_SCATTER_PACK") && atoi(getenv("ARL_SCATTER_PACK")) == 0);
     if (scatter_on && fused_cast && c->pc_mode >= 2 && c->n_pack_jobs >= 2 && c->conv_pack_end > 0 && c->pk_slots) {
@@ -1600,6 +1566,9 @@ int rollout_end(arl_ctx* c, cudaStream_t st) {
 
 namespace {
 int sync_update(arl_ctx* c, cudaStream_t st);
+bool sync_overlap_ok(arl_ctx* c);
+int sync_overlap_prepare(arl_ctx* c);
+int sync_tail(arl_ctx* c, cudaStream_t st);
 int train_minibatches(arl_ctx* c, const int* idx, int mb_size, int count, int sync, cudaStream_t st);
 int async_push_pull(arl_ctx* c, cudaStream_t st);
 }
@@ -1676,6 +1645,10 @@ void arl_destroy(arl_ctx* c) {
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->ev_join2) cudaEventDestroy(c->ev_join2);
   if (c->ev_fcd) cudaEventDestroy(c->ev_fcd);
+  for (auto& e : c->ev_cs_in) if (e) cudaEventDestroy(e);
+  if (c->ev_cs_done) cudaEventDestroy(c->ev_cs_done);
+  if (c->cs) cudaStreamDestroy(c->cs);
+  if (c->sync_tail_partial) cudaFree(c->sync_tail_partial);
   if (c->side) cudaStreamDestroy(c->side);
   if (c->side2) cudaStreamDestroy(c->side2);
   cudaFree(c->est.f); cudaFree(c->cmd); cudaFree(c->rows_tab); cudaFree(c->tout.count);
@@ -2029,15 +2002,20 @@ int arl_train_minibatches_async(arl_ctx* c, const int* idx, int mb_size, int cou
 namespace {
 int train_minibatches(arl_ctx* c, const int* idx, int mb_size, int count, int sync, cudaStream_t st) {
   // sync: 0 = local clip + update, 1 = synchronous DP step, 2 = asynchronous push/pull
-  auto step = [&](cudaStream_t s_) { return sync == 1 ? sync_update(c, s_) : sync == 2 ? async_push_pull(c, s_) : clip_update(c, 1.f, s_); };
+  const bool overlap = sync == 1 && sync_overlap_ok(c);
+  if (overlap && sync_overlap_prepare(c)) return 1;
+  auto step = [&](cudaStream_t s_) {
+    return sync == 1 ? (overlap ? sync_tail(c, s_) : sync_update(c, s_)) : sync == 2 ? async_push_pull(c, s_) : clip_update(c, 1.f, s_);
+  };
   struct Active {      // grad_minibatch may update the FC weights early only when the local clip_update follows it
     arl_ctx* c;
-    Active(arl_ctx* c_, bool on) : c(c_) { c->train_step_active = on; }
+    Active(arl_ctx* c_, bool on, bool ov) : c(c_) { c->train_step_active = on; c->sync_overlap_active = ov; }
     ~Active() {
+      c->sync_overlap_active = false;
       c->train_step_active = false; c->early_fc_done = false; c->pending_fin = nullptr; c->pending_stream = false;
       c->pending_ss_fin = c->pending_ss_fc = 0;
     }
-  } active(c, sync == 0);
+  } active(c, sync == 0, overlap);
   if (!(c->sampler_set && c->t_obs == c->sc.observations && c->roll_obs16) || (sync && c->sync_graph_failed)) {
     // training inputs that are not the sampler's rollout buffers: plain launches, one minibatch at a time
     const bool replay_idx = c->sampler_set && c->t_obs == c->sc.observations && c->roll_obs16;
@@ -2179,6 +2157,21 @@ int arl_comm_barrier(arl_ctx* c, void* stream) {
 }
 int arl_sync_allreduce_update(arl_ctx* c, void* stream) { return sync_update(c, (cudaStream_t)stream); }
 
+/* device timeline of the overlapped synchronous step since the last reset: out[0..5] = average microseconds per step of
+   {FC exchange: wait for peers, FC exchange: reduce + update + publish, tail: wait for peers, tail: average + update,
+   slack between the end of the FC exchange and the start of the tail (> 0: fully hidden)}, out[5] = steps */
+int arl_comm_trace(arl_ctx* c, double* out, int reset, void* stream) {
+  if (!c->comm.ready) ARL_FAIL(c, "comm not connected");
+  ARL_CHECK(c, cudaStreamSynchronize((cudaStream_t)stream));
+  unsigned long long h[16];
+  ARL_CHECK(c, cudaMemcpy(h, c->comm.dev.trace, sizeof(h), cudaMemcpyDeviceToHost));
+  const double n = h[TR_COUNT] ? (double)h[TR_COUNT] : 1.0;
+  out[0] = h[TR_FC_WAIT] / n * 1e-3; out[1] = h[TR_FC_WORK] / n * 1e-3; out[2] = h[TR_TAIL_WAIT] / n * 1e-3;
+  out[3] = h[TR_TAIL_WORK] / n * 1e-3; out[4] = (double)(long long)h[TR_SLACK] / n * 1e-3; out[5] = (double)h[TR_COUNT];
+  if (reset) ARL_CHECK(c, cudaMemset(c->comm.dev.trace, 0, sizeof(h)));
+  return 0;
+}
+
 }  // extern "C"
 namespace {
 int sync_update(arl_ctx* c, cudaStream_t st) {
@@ -2196,6 +2189,76 @@ int sync_update(arl_ctx* c, cudaStream_t st) {
   c->launches += 1;
   ARL_CHECK(c, cudaGetLastError());
   return pack_weights(c, st, !c->shadow_in_comm, true);
+}
+
+// The overlapped synchronous step (comm.cuh) serves the same configuration as update_stream_kernel on one GPU: no
+// global-norm clipping, FC weight gradient written straight into the flat vector, bf16 FC operand tiles inside the
+// symmetric allocation, conv operand packs refreshed through the slot table.  ARL_SYNC_OVERLAP=0 keeps the monolithic kernel.
+bool sync_overlap_ok(arl_ctx* c) {
+  static const bool on = !(getenv("ARL_SYNC_OVERLAP") && atoi(getenv("ARL_SYNC_OVERLAP")) == 0);
+  return on && c->comm.ready && c->shadow_in_comm && c->opt_set && c->opt.grad_norm_clip <= 0.f && c->m && c->v &&
+         c->pc_mode >= 2 && fc_tiles_ok(c) && (c->off_Wfc % 4 == 0) && (((long)c->Kfc * c->H) % 4 == 0) &&
+         c->n_pack_jobs >= 2 && c->conv_pack_end > 0 && c->pk_slots && c->params == c->comm.param && c->grad == c->comm.grad;
+}
+
+// stream, events and scratch of the overlapped step: created OUTSIDE stream capture (train_minibatches calls this first)
+int sync_overlap_prepare(arl_ctx* c) {
+  if (!c->cs) {
+    ARL_CHECK(c, cudaStreamCreateWithFlags(&c->cs, cudaStreamNonBlocking));
+    for (auto& e : c->ev_cs_in) ARL_CHECK(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ARL_CHECK(c, cudaEventCreateWithFlags(&c->ev_cs_done, cudaEventDisableTiming));
+  }
+  if (!c->sync_tail_partial) {
+    const long n_small = c->n_params - (long)c->Kfc * c->H;
+    if (dev_alloc(c, &c->sync_tail_partial, (size_t)((n_small + 255) / 256))) return 1;
+  }
+  return 0;
+}
+
+int sync_fc_exchange(arl_ctx* c, cudaStream_t ws, cudaStream_t st) {
+  (void)ws;                                              // ev_cs_in[0] was recorded on it right after the FC weight gradient
+  ARL_CHECK(c, cudaEventRecord(c->ev_cs_in[1], st));
+  ARL_CHECK(c, cudaStreamWaitEvent(c->cs, c->ev_cs_in[0], 0));
+  ARL_CHECK(c, cudaStreamWaitEvent(c->cs, c->ev_cs_in[1], 0));
+  const CommDev& d = c->comm.dev;
+  ARL_CHECK(c, launch_k(sync_signal_kernel, dim3(1), dim3(32), 0, c->cs, d, (int)FLAG_A));
+  SyncFcArgs a{};
+  a.param = c->params; a.m = c->m; a.v = c->v;
+  a.fc_begin = c->off_Wfc; a.fc_len = (long)c->Kfc * c->H;
+  a.per = ((a.fc_len + d.world - 1) / d.world + 3) / 4 * 4;
+  a.shadow_tiles = 1; a.shadow_HW = c->HWlast; a.shadow_H = c->H;
+  a.hyper = c->hyper; a.step = c->step; a.kind = c->opt.update;
+  a.lr = c->opt.learning_rate; a.beta1 = c->opt.beta1; a.beta2 = c->opt.beta2; a.eps = c->opt.epsilon; a.rho = c->opt.rho;
+  if (d.world <= 2) ARL_CHECK(c, launch_k(sync_fc_kernel<2>, dim3(kSyncFcBlocks), dim3(kSyncFcThreads), 0, c->cs, d, a));
+  else if (d.world <= 4) ARL_CHECK(c, launch_k(sync_fc_kernel<4>, dim3(kSyncFcBlocks), dim3(kSyncFcThreads), 0, c->cs, d, a));
+  else ARL_CHECK(c, launch_k(sync_fc_kernel<kMaxRanks>, dim3(kSyncFcBlocks), dim3(kSyncFcThreads), 0, c->cs, d, a));
+  c->launches += 2;
+  prof_mark(c, "sync_fc", c->cs);
+  ARL_CHECK(c, cudaGetLastError());
+  ARL_CHECK(c, cudaEventRecord(c->ev_cs_done, c->cs));
+  return 0;
+}
+
+int sync_tail(arl_ctx* c, cudaStream_t st) {
+  const CommDev& d = c->comm.dev;
+  const long n_small = c->n_params - (long)c->Kfc * c->H;
+  const int blocks = (int)((n_small + 255) / 256);
+  ARL_CHECK(c, launch_k(sync_signal_kernel, dim3(1), dim3(32), 0, st, d, (int)FLAG_2));
+  SyncTailArgs a{};
+  a.param = c->params; a.m = c->m; a.v = c->v; a.n = c->n_params;
+  a.fc_begin = c->off_Wfc; a.fc_len = (long)c->Kfc * c->H;
+  a.loss_partial = c->loss_partial; a.n_loss_blocks = c->n_loss_rows; a.hyper = c->hyper; a.step = c->step;
+  a.kind = c->opt.update; a.lr = c->opt.learning_rate; a.beta1 = c->opt.beta1; a.beta2 = c->opt.beta2;
+  a.eps = c->opt.epsilon; a.rho = c->opt.rho;
+  a.out_norm = c->log_norm; a.out_loss = c->log_loss; a.log_slot = c->log_slot; a.log_cap = c->log_cap; a.mb_counter = c->mb_counter;
+  a.pk_slots = c->pk_slots; a.conv_end = c->conv_pack_end; a.partial = c->sync_tail_partial;
+  if (d.world <= 2) ARL_CHECK(c, launch_k(sync_tail_kernel<2>, dim3(blocks), dim3(256), 0, st, d, a));
+  else if (d.world <= 4) ARL_CHECK(c, launch_k(sync_tail_kernel<4>, dim3(blocks), dim3(256), 0, st, d, a));
+  else ARL_CHECK(c, launch_k(sync_tail_kernel<kMaxRanks>, dim3(blocks), dim3(256), 0, st, d, a));
+  c->launches += 2;
+  prof_mark(c, "sync_tail", st);
+  ARL_CHECK(c, cudaGetLastError());
+  return 0;
 }
 }  // namespace
 extern "C" {

@@ -37,6 +37,7 @@ struct CommDev {
   double* block_partial;                  // [kSyncBlocks]
   unsigned int* grid_counter;             // local grid barrier
   unsigned int* epoch;                    // local: number of cross-GPU barriers completed
+  unsigned long long* trace;              // local [16]: device-timeline accumulators of the overlapped step (ns), see sync_trace
 };
 
 struct CommState {
@@ -121,6 +122,8 @@ inline int comm_connect(CommState& s, const uint8_t* all_handles, std::string& e
   if (e != cudaSuccess) { err = std::string("cudaMalloc(comm scratch): ") + cudaGetErrorString(e); return 1; }
   cudaMemset(d.grid_counter, 0, 256);
   d.epoch = d.grid_counter + 16;
+  if (cudaMalloc(reinterpret_cast<void**>(&d.trace), 16 * sizeof(unsigned long long)) != cudaSuccess) { err = "cudaMalloc(trace)"; return 1; }
+  cudaMemset(d.trace, 0, 16 * sizeof(unsigned long long));
   s.ready = true;
   return 0;
 }
@@ -129,7 +132,7 @@ inline void comm_destroy(CommState& s) {
   if (!s.base) return;
   for (int r = 0; r < (int)s.peer_base.size(); ++r)
     if (r != s.rank && s.peer_base[r]) cudaIpcCloseMemHandle(s.peer_base[r]);
-  cudaFree(s.dev.avg_slice); cudaFree(s.dev.block_partial); cudaFree(s.dev.grid_counter);
+  cudaFree(s.dev.avg_slice); cudaFree(s.dev.block_partial); cudaFree(s.dev.grid_counter); cudaFree(s.dev.trace);
   cudaFree(s.base);
   s.base = nullptr; s.ready = false;
 }
@@ -352,6 +355,270 @@ __global__ void __launch_bounds__(kSyncThreads) sync_allreduce_update_kernel(Com
   // 5. all parameter slices have landed everywhere
   grid_barrier(d, gen, true);
   if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<volatile unsigned int*>(d.grid_counter + 2) = gen_next;
+}
+
+// ===========================================================================
+// OVERLAPPED synchronous step (no global-norm clipping: PPO's default).  The monolithic kernel above starts after the
+// whole backward pass and runs three cross-GPU barriers back to back; here the exchange of the FC weight gradient —
+// 97.8 % of the vector, final right after the FC weight-gradient tiles, i.e. BEFORE the conv gradient chain — runs on its
+// own stream beside that chain, and only the ~80 k other elements are exchanged on the critical path.  Plain launches
+// only (no cooperative grid, no intra-grid barrier): every block polls a LOCAL flag word that peers advance.
+//
+//   sync_signal_kernel(A)   after this rank's fc_wgrad + fc_dgrad: "my FC gradient is final and my FC weights have been
+//                           consumed" -> flag A of every peer
+//   sync_fc_kernel          blocks wait for flag A from all ranks; rank r reduces slice r of the FC range by P2P loads
+//                           (rank order: bit-identical everywhere), averages, Adam/RMSProp on the slice (its m, v live
+//                           here only), P2P-stores the new fp32 weights + bf16 operand tiles to every rank; the LAST
+//                           block publishes the slice's sum of squares to every rank, then flag B ("slice r published,
+//                           my reads of your gradients are done")
+//   finalize_grads_kernel   (main stream, as on one GPU) the other tensors' local gradients -> flat vector
+//   sync_signal_kernel(2)   "my small gradients are final" -> flag 2 of every peer
+//   sync_tail_kernel        blocks wait for flag 2 and flag B from all ranks; EVERY rank averages the small gradients of
+//                           all ranks (P2P loads, rank order) and applies the update to its own replica (identical
+//                           inputs, identical arithmetic -> bit-identical parameters, no broadcast), refreshes its conv
+//                           operand packs; the last block logs norm / loss and advances the device counters + epochs.
+// Reuse safety follows from stream order: a rank signals A(k+1) only after its tail(k), so nobody overwrites a gradient
+// or a norm slot a peer may still be reading.
+// ===========================================================================
+// small CTAs (256 threads, <= 64 registers) so they co-reside with the persistent conv CTAs (352 threads x 118 registers)
+constexpr int kSyncFcBlocks = 96;
+constexpr int kSyncFcThreads = 256;
+enum { FLAG_OLD = 0, FLAG_A = 16, FLAG_B = 32, FLAG_2 = 48 };           // u32 word offsets inside a rank's flag block
+enum { EP_A = 20, EP_B = 21, EP_2 = 22, TK_FC = 24, TK_TAIL = 26 };     // words of the local counter block (grid_counter)
+
+ARL_DEVINL unsigned long long gtimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+// device timeline of the overlapped step, accumulated by thread 0 of block 0 of each kernel (ns, %globaltimer):
+//   [0] sync_fc: wait for flag A    [1] sync_fc: reduce + update + publish (block 0)   [2] sync_tail: wait for flags 2 / B
+//   [3] sync_tail: average + update (block 0)   [4] steps   [5] slack = tail start - FC exchange end (signed; > 0: the FC
+//   exchange was over before the tail began, i.e. fully hidden behind the conv gradient chain)   [8] last FC end stamp
+enum { TR_FC_WAIT = 0, TR_FC_WORK = 1, TR_TAIL_WAIT = 2, TR_TAIL_WORK = 3, TR_COUNT = 4, TR_SLACK = 5, TR_FC_END = 8 };
+
+__global__ void sync_signal_kernel(CommDev d, int flag_word) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    __threadfence_system();
+    for (int r = 0; r < d.world; ++r) st_relaxed_sys_add(d.peer_flag[r] + flag_word);
+  }
+}
+
+// one thread: wait until every rank has signalled `flag_word` for the epoch after `epoch_word`
+ARL_DEVINL void sync_wait_flag(const CommDev& d, int flag_word, int epoch_word, int code) {
+  const unsigned int ep = reinterpret_cast<volatile unsigned int*>(d.grid_counter)[epoch_word] + 1u;
+  const unsigned int target = ep * (unsigned int)d.world;
+  long long t0 = clock64();
+  while ((int)(ld_acquire_sys(d.peer_flag[d.rank] + flag_word) - target) < 0) {
+    __nanosleep(64);
+    if (clock64() - t0 > 20000000000LL) dev_fail(code);
+  }
+}
+
+struct SyncFcArgs {
+  float* param; float* m; float* v;
+  long fc_begin, fc_len;                 // FC weight range of the flat vector (both multiples of 4)
+  long per;                              // slice length per rank (multiple of 4)
+  int shadow_tiles, shadow_HW, shadow_H;
+  const float* hyper; const int* step;
+  int kind; float lr, beta1, beta2, eps, rho;
+};
+
+template <int W>
+__global__ void __launch_bounds__(kSyncFcThreads, 4) sync_fc_kernel(CommDev d, SyncFcArgs a) {
+  __shared__ double s_red[kSyncFcThreads / 32];
+  __shared__ float s_alpha;
+  __shared__ int s_last;
+  unsigned long long tr0 = 0, tr1 = 0;
+  if (threadIdx.x == 0) {
+    tr0 = gtimer_ns();
+    sync_wait_flag(d, FLAG_A, EP_A, 330);
+    tr1 = gtimer_ns();
+    const int tstep = a.step[0] + 1;
+    const float lr = a.lr * a.hyper[0];
+    if (a.kind == 0) {
+      const double b1t = pow((double)a.beta1, (double)tstep), b2t = pow((double)a.beta2, (double)tstep);
+      s_alpha = (float)((double)lr * sqrt(1.0 - b2t) / (1.0 - b1t));
+    } else {
+      s_alpha = lr;
+    }
+  }
+  __syncthreads();
+  const float alpha = s_alpha;
+  const float inv_world = 1.f / (float)d.world;
+  const long begin = a.fc_begin + (long)d.rank * a.per;
+  const long end = min(a.fc_begin + a.fc_len, begin + a.per);
+  const long len4 = end > begin ? (end - begin) >> 2 : 0;
+  const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x, gsz = (long)gridDim.x * blockDim.x;
+  constexpr int U = 8 / W;                 // W x U = 8 independent 16-byte loads in flight per thread
+  double acc = 0.0;
+  for (long i0 = gtid; i0 < len4; i0 += U * gsz) {
+    float4 g[W][U];
+#pragma unroll
+    for (int r = 0; r < W; ++r)
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long i = i0 + u * gsz;
+        g[r][u] = (r < d.world && i < len4) ? *reinterpret_cast<const float4*>(d.peer_grad[r] + begin + 4 * i)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long i = i0 + u * gsz;
+      if (i >= len4) continue;
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < W; ++r)
+        if (r < d.world) { t.x += g[r][u].x; t.y += g[r][u].y; t.z += g[r][u].z; t.w += g[r][u].w; }
+      t.x *= inv_world; t.y *= inv_world; t.z *= inv_world; t.w *= inv_world;
+      acc += (double)(t.x * t.x + t.y * t.y) + (double)(t.z * t.z + t.w * t.w);
+      const long gi = begin + 4 * i;
+      const float4 p4 = *reinterpret_cast<const float4*>(a.param + gi);
+      const float4 v4 = *reinterpret_cast<const float4*>(a.v + gi);
+      float gg[4] = {t.x, t.y, t.z, t.w};
+      float pp[4] = {p4.x, p4.y, p4.z, p4.w};
+      float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+      if (a.kind == 0) {
+        const float4 m4 = *reinterpret_cast<const float4*>(a.m + gi);
+        float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) opt_step_raw(0, a.beta1, a.beta2, a.eps, a.rho, pp[k], mm[k], vv[k], gg[k], alpha);
+        *reinterpret_cast<float4*>(a.m + gi) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+      } else {
+        float dummy = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) opt_step_raw(1, a.beta1, a.beta2, a.eps, a.rho, pp[k], dummy, vv[k], gg[k], alpha);
+      }
+      *reinterpret_cast<float4*>(a.v + gi) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+      const float4 pn = make_float4(pp[0], pp[1], pp[2], pp[3]);
+      long off = gi - a.fc_begin;
+      if (a.shadow_tiles) {
+        const unsigned ou = (unsigned)off, rr = ou / (unsigned)a.shadow_H;
+        off = fc_tile_index(rr, (int)(ou - rr * (unsigned)a.shadow_H), a.shadow_HW, a.shadow_H);
+      }
+      const uint2 pk = make_uint2(pack_bf16x2(pp[0], pp[1]), pack_bf16x2(pp[2], pp[3]));
+      for (int r = 0; r < d.world; ++r) {
+        *reinterpret_cast<float4*>(d.peer_param[r] + gi) = pn;
+        *reinterpret_cast<uint2*>(d.peer_shadow[r] + off) = pk;
+      }
+    }
+  }
+  __threadfence_system();                  // this thread's peer stores are ordered before the ticket below
+  if (blockIdx.x == 0 && threadIdx.x == 0) { d.trace[TR_FC_WAIT] += tr1 - tr0; d.trace[TR_FC_WORK] += gtimer_ns() - tr1; }
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kSyncFcThreads / 32; ++w) t += s_red[w];
+    d.block_partial[blockIdx.x] = t;
+    __threadfence();
+    const unsigned int tk = atomicAdd(d.grid_counter + TK_FC, 1u);
+    s_last = ((tk + 1u) % gridDim.x == 0u) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    double t = 0.0;
+    for (int b = 0; b < (int)gridDim.x; ++b) t += __ldcg(d.block_partial + b);
+    for (int r = 0; r < d.world; ++r) d.peer_norm[r][d.rank] = t;         // slot = writer rank
+    reinterpret_cast<volatile unsigned int*>(d.grid_counter)[EP_A] += 1u;  // every block passed its flag-A wait
+    __threadfence_system();
+    for (int r = 0; r < d.world; ++r) st_relaxed_sys_add(d.peer_flag[r] + FLAG_B);
+    d.trace[TR_FC_END] = gtimer_ns();
+  }
+}
+
+struct SyncTailArgs {
+  float* param; float* m; float* v; long n;
+  long fc_begin, fc_len;                 // excluded range (done by sync_fc_kernel)
+  const float* loss_partial; int n_loss_blocks;
+  const float* hyper; int* step;
+  int kind; float lr, beta1, beta2, eps, rho;
+  float* out_norm; float* out_loss; int* log_slot; int log_cap; int* mb_counter;
+  const unsigned long long* pk_slots; long conv_end;      // conv operand slot table (UpdateParams::pk_slots)
+  double* partial;                       // [gridDim.x] block sums of squares
+};
+
+// element j of the "everything but the FC weights" index space -> index in the flat vector
+ARL_DEVINL long sync_small_index(long j, long fc_begin, long fc_len) { return j < fc_begin ? j : j + fc_len; }
+
+template <int W>
+__global__ void __launch_bounds__(256) sync_tail_kernel(CommDev d, SyncTailArgs a) {
+  __shared__ double s_red[8];
+  __shared__ float s_alpha;
+  __shared__ int s_last;
+  unsigned long long tr0 = 0, tr1 = 0;
+  if (threadIdx.x == 0) {
+    tr0 = gtimer_ns();
+    sync_wait_flag(d, FLAG_2, EP_2, 331);
+    sync_wait_flag(d, FLAG_B, EP_B, 332);
+    tr1 = gtimer_ns();
+    const int tstep = a.step[0] + 1;
+    const float lr = a.lr * a.hyper[0];
+    if (a.kind == 0) {
+      const double b1t = pow((double)a.beta1, (double)tstep), b2t = pow((double)a.beta2, (double)tstep);
+      s_alpha = (float)((double)lr * sqrt(1.0 - b2t) / (1.0 - b1t));
+    } else {
+      s_alpha = lr;
+    }
+  }
+  __syncthreads();
+  const float alpha = s_alpha;
+  const float inv_world = 1.f / (float)d.world;
+  const long n_small = a.n - a.fc_len;
+  double acc = 0.0;
+  for (long j = (long)blockIdx.x * blockDim.x + threadIdx.x; j < n_small; j += (long)gridDim.x * blockDim.x) {
+    const long i = sync_small_index(j, a.fc_begin, a.fc_len);
+    float gr[W];
+#pragma unroll
+    for (int r = 0; r < W; ++r) gr[r] = (r < d.world) ? d.peer_grad[r][i] : 0.f;
+    float g = 0.f;
+#pragma unroll
+    for (int r = 0; r < W; ++r)
+      if (r < d.world) g += gr[r];
+    g *= inv_world;
+    acc += (double)(g * g);
+    float pv = a.param[i], mm = (a.kind == 0) ? a.m[i] : 0.f, vv = a.v[i];
+    opt_step_raw(a.kind, a.beta1, a.beta2, a.eps, a.rho, pv, mm, vv, g, alpha);
+    if (a.kind == 0) a.m[i] = mm;
+    a.v[i] = vv;
+    a.param[i] = pv;
+    if (a.pk_slots && i < a.conv_end) {
+      const ulonglong2 sl = __ldg(reinterpret_cast<const ulonglong2*>(a.pk_slots + 2 * i));
+      const __nv_bfloat16 b = __float2bfloat16_rn(pv);
+      if (sl.x) *reinterpret_cast<__nv_bfloat16*>(sl.x) = b;
+      if (sl.y) *reinterpret_cast<__nv_bfloat16*>(sl.y) = b;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    d.trace[TR_TAIL_WAIT] += tr1 - tr0; d.trace[TR_TAIL_WORK] += gtimer_ns() - tr1; d.trace[TR_COUNT] += 1ULL;
+    d.trace[TR_SLACK] += tr0 - d.trace[TR_FC_END];        // two's complement: read back as signed
+  }
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_red[w];
+    a.partial[blockIdx.x] = t;
+    __threadfence();
+    const unsigned int tk = atomicAdd(d.grid_counter + TK_TAIL, 1u);
+    s_last = ((tk + 1u) % gridDim.x == 0u) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    double t = 0.0;
+    for (int b = 0; b < (int)gridDim.x; ++b) t += __ldcg(a.partial + b);
+    const volatile double* np = d.peer_norm[d.rank];
+    for (int r = 0; r < d.world; ++r) t += np[r];                           // FC slices, rank order
+    float l = 0.f;
+    for (int b = 0; b < a.n_loss_blocks; ++b) l += a.loss_partial[4 * b + 3];
+    const int slot = a.log_slot[0];
+    if (slot < a.log_cap) { a.out_norm[slot] = (float)sqrt(t); a.out_loss[slot] = l; }
+    a.step[0] += 1; a.log_slot[0] += 1; a.mb_counter[0] += 1;
+    volatile unsigned int* gc = reinterpret_cast<volatile unsigned int*>(d.grid_counter);
+    gc[EP_2] += 1u; gc[EP_B] += 1u;
+  }
 }
 
 __global__ void xgpu_barrier_kernel(CommDev d) {

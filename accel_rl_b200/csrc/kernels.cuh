@@ -1022,42 +1022,51 @@ ARL_DEVINL void pc_decode_channel(int cc, int C, int s, int ci_major, int& ci, i
   }
 }
 
-// one element of one job: sums its partials in a fixed order, writes it to its place in the flat gradient;
-// -> false when the element is a padding tap / channel that has no parameter (nothing written)
-// (finalize_elem_dst: the same, returning the element's index in the flat vector, -1 = no parameter)
-ARL_DEVINL long finalize_elem_dst(const GradJob& jb, long i, float* __restrict__ grad, float& acc_out) {
-  int r = (int)(i / jb.cols);
-  int c = (int)(i - (long)r * jb.cols);
-  const float* s = jb.src + (long)r * jb.ld + c;
-  // fixed summation order: 16 interleaved chains (16 independent L2 loads in flight per thread — the loop is pure
-  // latency: 64..148 partials, each a separate 4-byte load), then a fixed tree
+// Partial sums of one element, taken by a TEAM of four lanes: lanes q*8 + e (q = 0..3) of a warp hold element e of the
+// warp's group of 8 consecutive elements; lane q sums partials k = q, q+4, q+8, ... with 16 independent loads in flight,
+// then two butterfly shuffles combine the four sub-sums ((s_q + s_q^1) + (s_q^2 + s_q^3): the same bits in every lane).
+// One thread per element with a 148-long dependent chain (ncu: profiles/r2_update_stream.md, 18 us) was pure latency;
+// the team form shortens the chain 4x and keeps 32-byte-sector loads.  `valid` = the lane's element exists (all 32
+// lanes must call: the shuffles are warp-wide).  The summation order is part of the parity contract between the
+// training paths (single GPU / stream / synchronous), which all come through here.
+ARL_DEVINL float finalize_sum4(const GradJob& jb, int r, int c, int q, bool valid) {
   float a[16];
 #pragma unroll
   for (int u = 0; u < 16; ++u) a[u] = 0.f;
-  int k = 0;
-  for (; k + 16 <= jb.S; k += 16) {
+  if (valid) {
+    const float* s = jb.src + (long)r * jb.ld + c;
+    const int S = jb.S;
+    const long ss = jb.sstride;
+    int k = q;
+    for (; k + 60 < S; k += 64) {
 #pragma unroll
-    for (int u = 0; u < 16; ++u) a[u] += s[(long)(k + u) * jb.sstride];
+      for (int u = 0; u < 16; ++u) a[u] += s[(long)(k + 4 * u) * ss];
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u)
+      if (k + 4 * u < S) a[u] += s[(long)(k + 4 * u) * ss];
   }
-#pragma unroll
-  for (int u = 0; u < 16; ++u)
-    if (k + u < jb.S) a[u] += s[(long)(k + u) * jb.sstride];
 #pragma unroll
   for (int w = 8; w >= 1; w >>= 1)
 #pragma unroll
     for (int u = 0; u < w; ++u) a[u] += a[u + w];
-  const float acc = a[0] * jb.scale;
-  acc_out = acc;
-  long dst;
-  if (jb.map == GM_LINEAR) {
-    dst = jb.dst_off + i;
-  } else if (jb.map == GM_CONV_NHWC) {
+  float t = a[0];
+  t += __shfl_xor_sync(0xffffffffu, t, 8);
+  t += __shfl_xor_sync(0xffffffffu, t, 16);
+  return t * jb.scale;
+}
+
+// where element (r, c) of job jb lives in the flat vector (-1: a padding tap / channel without a parameter)
+ARL_DEVINL long finalize_dst(const GradJob& jb, int r, int c) {
+  if (jb.map == GM_LINEAR) return jb.dst_off + (long)r * jb.cols + c;
+  if (jb.map == GM_CONV_NHWC) {
     // r = k' = (ky*kw + kx)*C + ci ; c = cout
     int ci = r % jb.C;
     int t = r / jb.C;
     int kx = t % jb.kw, ky = t / jb.kw;
-    dst = jb.dst_off + (((long)c * jb.C + ci) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx);
-  } else if (jb.map == GM_CONV_S2D) {
+    return jb.dst_off + (((long)c * jb.C + ci) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx);
+  }
+  if (jb.map == GM_CONV_S2D) {
     // first layer over the space-to-depth input: r = k' = (ty*2 + tx)*(C*s*s) + ci*s*s + dy*s + dx
     const int s2 = jb.s2d * jb.s2d, cs = jb.C * s2;
     int ch = r % cs;
@@ -1065,8 +1074,9 @@ ARL_DEVINL long finalize_elem_dst(const GradJob& jb, long i, float* __restrict__
     int tx = t % 2, ty = t / 2;
     int ci = ch / s2, dy = (ch % s2) / jb.s2d, dx = ch % jb.s2d;
     int ky = ty * jb.s2d + dy, kx = tx * jb.s2d + dx;
-    dst = jb.dst_off + (((long)c * jb.C + ci) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx);
-  } else if (jb.map == GM_PCONV) {
+    return jb.dst_off + (((long)c * jb.C + ci) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx);
+  }
+  if (jb.map == GM_PCONV) {
     int blk = r >> 6, ch = r & 63;
     int t = blk / jb.P, plane = blk - t * jb.P;
     int ty = t / jb.T, tx = t - ty * jb.T;
@@ -1074,54 +1084,37 @@ ARL_DEVINL long finalize_elem_dst(const GradJob& jb, long i, float* __restrict__
     pc_decode_channel(plane * 64 + ch, jb.C, jb.s2d, jb.ci_major, ci, py, px);
     int ky = ty * jb.s2d + py, kx = tx * jb.s2d + px;
     if (!(ky < jb.kh && kx < jb.kw && ci < jb.C)) return -1;
-    dst = jb.dst_off + (((long)c * jb.C + ci) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx);
-  } else {  // GM_HEAD: r = j, c in [0, A+2)
-    if (c < jb.A) dst = jb.dst_off + (long)r * jb.A + c;
-    else if (c == jb.A) dst = jb.dst_off2 + r;
-    else dst = jb.dst_off3 + r;
+    return jb.dst_off + (((long)c * jb.C + ci) * jb.kh + (jb.kh - 1 - ky)) * jb.kw + (jb.kw - 1 - kx);
   }
-  grad[dst] = acc;
-  return dst;
+  // GM_HEAD: r = j, c in [0, A+2)
+  if (c < jb.A) return jb.dst_off + (long)r * jb.A + c;
+  if (c == jb.A) return jb.dst_off2 + r;
+  return jb.dst_off3 + r;
 }
-ARL_DEVINL bool finalize_elem(const GradJob& jb, long i, float* __restrict__ grad, float& acc_out) {
-  return finalize_elem_dst(jb, i, grad, acc_out) >= 0;
+
+// element v of job jb for the calling lane's team -> (gradient value in every lane, flat index or -1); the team's lane
+// q == 0 is the one that should consume it.  v >= rows*cols: not an element (returns -1, still joins the shuffles)
+ARL_DEVINL long finalize_team(const GradJob& jb, long v, int q, float& g_out) {
+  const long total = (long)jb.rows * jb.cols;
+  const bool valid = v < total;
+  const int r = valid ? (int)(v / jb.cols) : 0;
+  const int c = valid ? (int)(v - (long)r * jb.cols) : 0;
+  g_out = finalize_sum4(jb, r, c, q, valid);
+  return valid ? finalize_dst(jb, r, c) : -1;
 }
+
+constexpr int kFinPerBlock = 64;     // elements per 256-thread block: 8 warps x 8 teams of 4 lanes
 
 __global__ void __launch_bounds__(256) finalize_grads_kernel(const GradJob* __restrict__ jobs, float* __restrict__ grad) {
   pdl_wait();
   pdl_trigger();
-  const GradJob jb = jobs[blockIdx.y];
+  const GradJob& jb = jobs[blockIdx.y];
   const long total = (long)jb.rows * jb.cols;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    float acc;
-    finalize_elem(jb, i, grad, acc);
-  }
-}
-
-// Variant that also leaves the sum of squares of what each block wrote in ss_out[jb.ss_off + blockIdx.x] (blocks
-// blockIdx.x < ceil(rows*cols / 256) — the others have no element), so the update kernel that follows needs neither its
-// own pass over the gradient nor a grid-wide barrier for the global norm (ARL_PRODUCER_SUMSQ=1, see api.cu).
-__global__ void __launch_bounds__(256) finalize_grads_ss_kernel(const GradJob* __restrict__ jobs, float* __restrict__ grad,
-                                                                double* __restrict__ ss_out) {
-  pdl_wait();
-  pdl_trigger();
-  const GradJob jb = jobs[blockIdx.y];
-  const long total = (long)jb.rows * jb.cols;
-  double ss = 0.0;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    float acc;
-    if (finalize_elem(jb, i, grad, acc)) ss += (double)(acc * acc);
-  }
-  if ((long)blockIdx.x * blockDim.x < total) {
-    __shared__ double s_ss[8];
-    ss = warp_sum_d(ss);
-    if ((threadIdx.x & 31) == 0) s_ss[threadIdx.x >> 5] = ss;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double t = 0.0;
-      for (int w = 0; w < 8; ++w) t += s_ss[w];
-      ss_out[jb.ss_off + blockIdx.x] = t;
-    }
+  const int lane = threadIdx.x & 31, q = lane >> 3;
+  for (long v0 = (long)blockIdx.x * kFinPerBlock; v0 < total; v0 += (long)gridDim.x * kFinPerBlock) {
+    float g;
+    const long dst = finalize_team(jb, v0 + (threadIdx.x >> 5) * 8 + (lane & 7), q, g);
+    if (q == 0 && dst >= 0) grad[dst] = g;
   }
 }
 
@@ -1216,9 +1209,8 @@ struct UpdateParams {
   // the update does not depend on the norm); their sum of squares arrives in sumsq_partial2
   long skip4_begin, skip4_len;
   const double* sumsq_partial2; int n_partial2;
-  // n_fin_jobs > 0: gradient finalisation folded into phase 1 of update_fused_kernel — the blocks first sum the split
-  // partials of every tensor except the FC weights (finalize_elem; each thread squares what it writes), then take the
-  // sum of squares of the FC-weight range [fc4_begin, +fc4_len) float4 groups, which fc_gemm_kernel wrote directly
+  // update_stream_kernel: fin_jobs = the split partials of every tensor except the FC weights (summed by the kernel's
+  // part-A blocks), [fc4_begin, +fc4_len) = the FC-weight range in float4 groups, which fc_gemm_kernel wrote directly
   const GradJob* fin_jobs; int n_fin_jobs;
   long fc4_begin, fc4_len;
   uint32_t shadow_H_magic, shadow_HW_magic;   // floor(2^32/d) + 1: the tile index needs two divisions per float4 group
@@ -1283,54 +1275,7 @@ __global__ void __launch_bounds__(256, 4) update_fused_kernel(UpdateParams p, do
                                                               unsigned long long* __restrict__ ticket) {
   pdl_wait();
   pdl_trigger();
-  if (p.n_fin_jobs > 0) {
-    double acc = 0.0;
-    const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x, gsize = (long)gridDim.x * blockDim.x;
-    float* grad = const_cast<float*>(p.grad);
-    // All jobs' elements form one index space, dealt out in groups of 32 consecutive elements (coalesced partial loads)
-    // to warps numbered block-interleaved, so every block gets the same share and no thread more than one element —
-    // an unbalanced phase 1 leaves most blocks spinning on the barrier below while a few walk several jobs.
-    {
-      const int lane = threadIdx.x & 31;
-      const long wslot = (long)(threadIdx.x >> 5) * gridDim.x + blockIdx.x;      // 0 .. 8*gridDim.x - 1
-      const long nwarps = (long)(blockDim.x >> 5) * gridDim.x;
-      long total_all = 0;
-      for (int jn = 0; jn < p.n_fin_jobs; ++jn) total_all += (long)p.fin_jobs[jn].rows * p.fin_jobs[jn].cols;
-      for (long v0 = wslot * 32; v0 < total_all; v0 += nwarps * 32) {
-        long v = v0 + lane;
-        if (v < total_all) {
-          int jn = 0;
-          for (; jn < p.n_fin_jobs; ++jn) {
-            const long t = (long)p.fin_jobs[jn].rows * p.fin_jobs[jn].cols;
-            if (v < t) break;
-            v -= t;
-          }
-          const GradJob jb = p.fin_jobs[jn];
-          float g;
-          if (finalize_elem(jb, v, grad, g)) { g *= p.gscale; acc += (double)(g * g); }
-        }
-      }
-    }
-    if (p.skip4_len == 0) {      // (an early FC update has already squared this range)
-      const float4* g4 = reinterpret_cast<const float4*>(p.grad) + p.fc4_begin;
-      for (long j = gtid; j < p.fc4_len; j += gsize) {
-        float4 v = g4[j];
-        float a = v.x * p.gscale, b = v.y * p.gscale, c = v.z * p.gscale, d = v.w * p.gscale;
-        acc += (double)(a * a + b * b) + (double)(c * c + d * d);
-      }
-    }
-    __shared__ double s1[8];
-    acc = warp_sum_d(acc);
-    if ((threadIdx.x & 31) == 0) s1[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double t = 0.0;
-      for (int w = 0; w < 8; ++w) t += s1[w];
-      partial[blockIdx.x] = t;
-    }
-  } else {
-    sumsq_body(p.grad, p.n, p.gscale, partial, p.skip4_begin, p.skip4_len);
-  }
+  sumsq_body(p.grad, p.n, p.gscale, partial, p.skip4_begin, p.skip4_len);
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -1526,7 +1471,7 @@ ARL_DEVINL void update_body(const UpdateParams& p) {
 // WITHOUT global-norm clipping (PPO's default, algos/pg/ppo.py:29: the norm is only reported, so nothing in the update
 // waits for it).  Replaces finalize_grads_kernel -> update_fused_kernel {pass over the gradient, grid barrier, update}:
 //   part A  every tensor except the FC weights (~2 % of the vector): the thread that sums an element's split partials
-//           (finalize_elem_dst) also takes its optimiser step and refreshes its bf16 operand slots;
+//           (finalize_team) also takes its optimiser step and refreshes its bf16 operand slots;
 //   part B  the FC weight range, float4 groups straight from the flat gradient the FC tiles wrote;
 //   every thread squares what it consumed; block partials in `partial`; the LAST block to finish (ticket) adds them up
 //   in index order (bit-reproducible), writes the norm / loss logs and advances the device counters.
@@ -1558,26 +1503,30 @@ __global__ void __launch_bounds__(256, 4) update_stream_kernel(UpdateParams p, d
   const float alpha = s_alpha;
   double acc = 0.0;
   if ((int)blockIdx.x < nA) {
-    // part A (blocks [0, nA): scheduled first): ONE element per thread, consecutive threads = consecutive elements of the
-    // concatenated job index space (coalesced partial loads).  A separate set of blocks from part B: the partial sums are
+    // part A (blocks [0, nA): scheduled first): 64 elements per block, a team of four lanes per element (finalize_sum4),
+    // elements numbered through the concatenated job index space.  A separate set of blocks from part B: the partial sums are
     // 48..148 dependent-latency loads per element — ncu (profiles/r2_update_stream.md) showed warps that carried both
     // parts holding their whole block at the final barrier for 40 % of the kernel
     float* grad = const_cast<float*>(p.grad);
-    long v = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, q = lane >> 3;
+    long v = (long)blockIdx.x * kFinPerBlock + (threadIdx.x >> 5) * 8 + (lane & 7);
+    int jn = 0;
     if (v < total_all) {
-      int jn = 0;
       for (; jn < p.n_fin_jobs; ++jn) {
         const long t = (long)p.fin_jobs[jn].rows * p.fin_jobs[jn].cols;
         if (v < t) break;
         v -= t;
       }
-      const GradJob& jb = p.fin_jobs[jn];      // (fields fetched where used: a register copy of the struct spills)
-      float g;
-      const long dst = finalize_elem_dst(jb, v, grad, g);
-      if (dst >= 0) {
-        acc += (double)(g * g);
-        update_scalar(p, dst, g, alpha);
-      }
+    } else {
+      v = 0x7fffffffffffL;                     // no element: the lane only joins the team shuffles
+    }
+    const GradJob& jb = p.fin_jobs[jn < p.n_fin_jobs ? jn : 0];      // (fields fetched where used: a register copy spills)
+    float g;
+    const long dst = finalize_team(jb, v, q, g);
+    if (q == 0 && dst >= 0) {
+      grad[dst] = g;
+      acc += (double)(g * g);
+      update_scalar(p, dst, g, alpha);
     }
   } else {
     // part B: the FC weights

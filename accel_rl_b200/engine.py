@@ -278,6 +278,14 @@ class Engine(object):
         self.check(self.lib.arl_comm_connect(self.ctx, buf))
         self.pack()
 
+    def comm_trace(self, reset=True):
+        """device timeline of the overlapped synchronous step (microseconds per step), see arl_comm_trace"""
+        out = (C.c_double * 8)()
+        self.check(self.lib.arl_comm_trace(self.ctx, out, 1 if reset else 0, self._s()))
+        keys = ("fc_wait_peers_us", "fc_reduce_update_publish_us", "tail_wait_peers_us", "tail_average_update_us",
+                "slack_fc_end_to_tail_start_us", "steps")
+        return {k: round(float(out[i]), 2) for i, k in enumerate(keys)}
+
     def sync_allreduce_update(self):
         self.check(self.lib.arl_sync_allreduce_update(self.ctx, self._s()))
 

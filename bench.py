@@ -395,6 +395,12 @@ def run_ours(args):
     value = world * N / (ms_step * 1e-3)
 
     result = None
+    timeline = None
+    if world > 1 and args.parallelism == "sync":
+        try:
+            timeline = runner.policy.engine.comm_trace(reset=True)       # accumulated over warm-up + timed iterations
+        except Exception:
+            timeline = None
     phases = phase_split(runner, itr)
     parity = sync_parity(runner, rank, world) if (world > 1 and args.parallelism == "sync") else None
     if rank == 0:
@@ -451,6 +457,8 @@ def run_ours(args):
         }
         if parity is not None:
             result["parity"] = parity
+        if timeline is not None:
+            result["sync_timeline"] = timeline
     # ---- e2e: raw frames from pinned host memory every step, results read back ----
     if not args.no_e2e:
         runner.policy.engine.close()

@@ -205,6 +205,11 @@ int arl_comm_connect(arl_ctx* ctx, const uint8_t* all_handles);
 /* fused: reduce my slice of the flat gradient over peers by P2P loads, average, global-norm
  * clip, Adam/RMSProp on the slice, P2P-store the new params to every peer. */
 int arl_sync_allreduce_update(arl_ctx* ctx, void* stream);
+/* device-side timeline (%globaltimer) of the overlapped synchronous step since the last reset, microseconds per step:
+   out[0] FC exchange waiting for peers, out[1] FC exchange reduce + update + publish, out[2] tail waiting for peers,
+   out[3] tail average + update, out[4] slack between FC exchange end and tail start (> 0: hidden behind the conv gradient
+   chain), out[5] number of steps */
+int arl_comm_trace(arl_ctx* ctx, double* out, int reset, void* stream);
 int arl_comm_barrier(arl_ctx* ctx, void* stream);
 
 /* ---- asynchronous data parallel ------------------------------------------------------------------

@@ -94,9 +94,15 @@ def main():
     dist.broadcast(b, src=0)
     if rank == 1:
         assert not torch.equal(a, b)
+    import hashlib
+    digest = hashlib.sha256(np.ascontiguousarray(policy.get_param_values()).tobytes()).hexdigest()
+    norms = [float(x) for x in info["GradNorm"]]
+    assert policy.engine.device_error() == 0
     policy.engine.close()
     dist.barrier()
     if rank == 0:
+        import json
+        print("SYNC_DIGEST " + json.dumps(dict(params=digest, norms=norms)))
         print("SYNC_OK world=%d" % world)
     dist.destroy_process_group()
 
