@@ -142,10 +142,12 @@ SIGNATURES = {
     "arl_async_connect": (C.c_int, [_P, _P]),
     "arl_async_regions": (C.c_int, [_P]),
     "arl_async_push_pull": (C.c_int, [_P, _P]),
+    "arl_async_pull": (C.c_int, [_P, _P]),
     "arl_async_read_central": (C.c_int, [_P, C.c_int, _P, C.c_long, _P]),
     "arl_debug_activation": (C.c_int, [_P, C.c_int, _P, C.c_long, C.POINTER(C.c_long), _P]),
     "arl_kernel_launches": (C.c_long, [_P]),
     "arl_profile_begin": (C.c_int, [_P, _P]),
+    "arl_profile_timeline": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_char_p, C.c_int, _P, C.c_int, _P, _P]),
     "arl_profile_graph": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_char_p, C.c_int, _P, C.c_int,
                                     C.POINTER(C.c_int), _P]),
     "arl_profile_end": (C.c_int, [_P, C.c_char_p, C.c_int, _P, C.c_int, C.POINTER(C.c_int), _P]),

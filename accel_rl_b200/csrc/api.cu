@@ -89,7 +89,10 @@ struct TrainPlan {
   int n_jobs = 0;
   int fin_blocks = 1;
   int n_ss = 0;                 // per-block sum-of-squares slots the finalize kernel fills (GradJob::ss_off)
-  long fin_total = 0;           // elements of all jobs (update_stream_kernel's part-A index space)
+  long fin_total = 0;           // elements of all jobs
+  std::vector<long> job_total;  // rows * cols per job
+  int early_jobs = 0;           // > 0: jobs [2, n_jobs) are finalised on the side streams as soon as their partials exist;
+                                // only layer 0's two jobs are left for the end of the chain
 };
 
 }  // namespace
@@ -109,6 +112,7 @@ struct arl_ctx {
   cudaEvent_t ev_join2 = nullptr;
   cudaStream_t side = nullptr;         // weight-gradient kernels run here, overlapping the data-gradient chain
   cudaEvent_t ev_fork[4] = {nullptr, nullptr, nullptr, nullptr}, ev_join = nullptr;
+  cudaEvent_t ev_fin[2] = {nullptr, nullptr};   // "conv weight-gradient partials of layer l are complete" (side2 -> side)
   bool no_fork = false;                // serialise everything on the caller's stream (per-kernel profiling)
   // CTA caps while a data-gradient and a weight-gradient kernel share the GPU (0 = all SMs).  Measured (B200, C2):
   // wgrad capped at 56..96 CTAs lets the concurrent dgrad chain start on the free SMs and shrinks the per-CTA partial
@@ -202,6 +206,8 @@ struct arl_ctx {
   // per-kernel CUDA-event profiling (arl_profile_*): events recorded after each launch when enabled
   bool prof_on = false;
   bool prof_collect = false;             // record one label per kernel launch (arl_profile_graph)
+  bool prof_timeline = false;            // stamp %globaltimer after every launch INSIDE the captured, forked minibatch graph
+  unsigned long long* tl_buf = nullptr;  // [96] stamps
   std::vector<std::string> prof_labels;
   std::vector<cudaEvent_t> prof_ev;
   std::vector<std::string> prof_names;
@@ -270,9 +276,35 @@ cudaError_t launch_coop(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sm
   return launch_k(kern, grid, block, smem, st, std::forward<Args>(args)...);
 }
 
+__global__ void stamp_kernel(unsigned long long* slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  *slot = t;
+}
+
+// The main chain of a captured training graph runs at the highest stream priority (kernel nodes inherit it), the forked
+// weight-gradient / exchange streams at the default (lowest): when an SM frees up, pending CTAs of the data-gradient chain
+// — the critical path — are placed before those of the side kernels, which have slack until the join.
+cudaError_t create_main_stream(cudaStream_t* s) {
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  static const bool prio = !(getenv("ARL_STREAM_PRIO") && atoi(getenv("ARL_STREAM_PRIO")) == 0);
+  return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, prio ? hi : lo);
+}
+
 // record an event after the launch that just happened (profiling mode only)
 void prof_mark(arl_ctx* c, const char* name, cudaStream_t st) {
   if (c->prof_collect) c->prof_labels.push_back(name);
+  if (c->prof_timeline) {
+    // inside a captured graph events carry no timestamps: a one-thread kernel writes %globaltimer behind the launch
+    if (c->prof_n < 96 && c->tl_buf) {
+      if ((int)c->prof_names.size() <= c->prof_n) c->prof_names.resize(c->prof_n + 1);
+      c->prof_names[c->prof_n] = name;
+      stamp_kernel<<<1, 1, 0, st>>>(c->tl_buf + c->prof_n);
+      c->prof_n++;
+    }
+    return;
+  }
   if (!c->prof_on) return;
   if (c->prof_n >= (int)c->prof_ev.size()) {
     cudaEvent_t e;
@@ -1124,7 +1156,8 @@ int get_plan(arl_ctx* c, int n, TrainPlan** out) {
   }
   P.n_jobs = (int)jobs.size();
   P.fin_blocks = (int)((max_total + kFinPerBlock - 1) / kFinPerBlock);
-  for (auto& jb : jobs) P.fin_total += (long)jb.rows * jb.cols;
+  for (auto& jb : jobs) { P.fin_total += (long)jb.rows * jb.cols; P.job_total.push_back((long)jb.rows * jb.cols); }
+  P.early_jobs = (c->pc_mode >= 2 && fc_tiles_ok(c) && c->conv.size() >= 2) ? 1 : 0;
   ARL_CHECK(c, cudaMalloc(reinterpret_cast<void**>(&P.jobs_dev), jobs.size() * sizeof(GradJob)));
   ARL_CHECK(c, cudaMemcpy(P.jobs_dev, jobs.data(), jobs.size() * sizeof(GradJob), cudaMemcpyHostToDevice));
   auto res = c->plans.emplace(n, P);
@@ -1134,6 +1167,18 @@ int get_plan(arl_ctx* c, int n, TrainPlan** out) {
 
 bool early_fc_ok(arl_ctx* c);
 int early_fc_update(arl_ctx* c, cudaStream_t st);
+
+// split partials of jobs [first, first + count) -> their places in the flat gradient
+int launch_finalize(arl_ctx* c, const TrainPlan* P, int first, int count, const char* label, cudaStream_t st) {
+  long mx = 1;
+  for (int j = first; j < first + count; ++j) mx = std::max(mx, P->job_total[j]);
+  dim3 grid((unsigned)((mx + kFinPerBlock - 1) / kFinPerBlock), (unsigned)count);
+  ARL_CHECK(c, launch_k(finalize_grads_kernel, dim3(grid), dim3(256), 0, st, P->jobs_dev + first, c->grad));
+  c->launches++;
+  prof_mark(c, label, st);
+  ARL_CHECK(c, cudaGetLastError());
+  return 0;
+}
 bool stream_update_ok(arl_ctx* c, bool fct);
 int sync_fc_exchange(arl_ctx* c, cudaStream_t ws, cudaStream_t st);
 
@@ -1190,6 +1235,7 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
       ARL_CHECK(c, cudaStreamCreateWithFlags(&c->side2, cudaStreamNonBlocking));
       ARL_CHECK(c, cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming));
       ARL_CHECK(c, cudaEventCreateWithFlags(&c->ev_fcd, cudaEventDisableTiming));
+      for (auto& e : c->ev_fin) ARL_CHECK(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     ws = c->side;
     ARL_CHECK(c, cudaEventRecord(c->ev_fork[0], st));
@@ -1210,6 +1256,8 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
     if (fc_wgrad_tiles(c, n, ws)) return 1;
     prof_mark(c, "fc_wgrad", ws);
     if (c->sync_overlap_active) ARL_CHECK(c, cudaEventRecord(c->ev_cs_in[0], ws));
+    // head / FC-bias gradients: their partials exist (head_wgrad, earlier on ws) -> flat vector, beside the main chain
+    if (P->early_jobs && launch_finalize(c, P, 2 * (int)c->conv.size(), 3, "finalize_head", ws)) return 1;
   } else {
     DenseLoader<64> a{};
     a.src = LL.act; a.ld = c->Kfc; a.nrows = n;
@@ -1265,6 +1313,16 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
     if (pconv_wgrad_layer(c, l, obs16, gidx, gidx_off, n, wl)) return 1;
     prof_mark(c, kWgradName[l], wl);
     if (l == 0) break;
+    if (P->early_jobs) {
+      // its partials -> flat vector, on the head / FC side stream (idle by now), NOT inside side2's chain: the next
+      // layer's weight gradient is the longest path to the join (timeline: profiles/r2_timeline.md)
+      cudaStream_t fs = (wl != st && ws != st) ? ws : wl;
+      if (fs != wl) {
+        ARL_CHECK(c, cudaEventRecord(c->ev_fin[l & 1], wl));
+        ARL_CHECK(c, cudaStreamWaitEvent(fs, c->ev_fin[l & 1], 0));
+      }
+      if (launch_finalize(c, P, 2 * l, 2, "finalize_conv", fs)) return 1;
+    }
     if (pconv_dgrad_layer(c, l, n, st)) return 1;
     prof_mark(c, kDgradName[l], st);
   }
@@ -1322,11 +1380,7 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
     c->pending_fin = P;        // clip_update: update_stream_kernel sums the partials and updates in the same pass
     c->pending_stream = true;
   } else {
-    dim3 grid(P->fin_blocks, P->n_jobs);
-    ARL_CHECK(c, launch_k(finalize_grads_kernel, dim3(grid), dim3(256), 0, st, P->jobs_dev, c->grad));
-    c->launches++;
-    prof_mark(c, "finalize_grads", st);
-    ARL_CHECK(c, cudaGetLastError());
+    if (launch_finalize(c, P, 0, (pcb && P->early_jobs) ? 2 : P->n_jobs, "finalize_grads", st)) return 1;
   }
   return 0;
 }
@@ -1422,6 +1476,12 @@ int clip_update(arl_ctx* c, float gscale, cudaStream_t st) {
     const TrainPlan* P = static_cast<const TrainPlan*>(c->pending_fin);
     P_total = P->fin_total;
     u.fin_jobs = P->jobs_dev; u.n_fin_jobs = P->n_jobs;
+    if (P->early_jobs) {
+      // everything but layer 0 was finalised on the side streams: part A sums layer 0's partials, part A2 takes the
+      // other small tensors from the flat gradient
+      u.n_fin_jobs = 2; P_total = P->job_total[0] + P->job_total[1];
+      u.a2_begin = c->conv[1].off_W; u.a2_mid = c->off_Wfc; u.a2_resume = c->off_Wfc + (long)c->Kfc * c->H;
+    }
     u.fc4_begin = c->off_Wfc / 4; u.fc4_len = (long)c->Kfc * c->H / 4;
     c->pending_fin = nullptr;
   }
@@ -1432,15 +1492,17 @@ int clip_update(arl_ctx* c, float gscale, cudaStream_t st) {
     u.adv_done = c->ticket + 1; u.adv_log_slot = c->log_slot; u.adv_mb = c->mb_counter;
     // blocks [0, nA) sum the split partials and update everything except the FC weights, the other 4 x 148 stream the FC range
     const int nA = (int)((P_total + kFinPerBlock - 1) / kFinPerBlock);
+    const long n_a2 = u.a2_resume > 0 ? (u.a2_mid - u.a2_begin) + (c->n_params - u.a2_resume) : 0;
+    const int nA2 = (int)((n_a2 + 255) / 256);
     int nB = kSumsqBlocks;
     if (u.skip4_len > 0) {
       // the FC range already took its step (update_range_kernel, beside the conv gradient chain): only part A is left
       if (u.skip4_begin != u.fc4_begin || u.skip4_len != u.fc4_len) ARL_FAIL(c, "update_stream: early range is not the FC range");
       u.fc4_len = 0; nB = 0;
     }
-    if (nA + nB > kStreamPartials) ARL_FAIL(c, "update_stream: partial buffer too small");
+    if (nA + nA2 + nB > kStreamPartials) ARL_FAIL(c, "update_stream: partial buffer too small");
     u.adv_done = c->ticket + 2;                 // (its own arrival counter: the grid size differs from update_fused_kernel's)
-    ARL_CHECK(c, launch_k(update_stream_kernel, dim3(nA + nB), dim3(256), 0, st, u, c->sumsq_partial, nA, P_total));
+    ARL_CHECK(c, launch_k(update_stream_kernel, dim3(nA + nA2 + nB), dim3(256), 0, st, u, c->sumsq_partial, nA, nA2, P_total));
     c->launches++;
     prof_mark(c, "clip_update", st);
     ARL_CHECK(c, cudaGetLastError());
@@ -1645,6 +1707,7 @@ void arl_destroy(arl_ctx* c) {
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->ev_join2) cudaEventDestroy(c->ev_join2);
   if (c->ev_fcd) cudaEventDestroy(c->ev_fcd);
+  for (auto& e : c->ev_fin) if (e) cudaEventDestroy(e);
   for (auto& e : c->ev_cs_in) if (e) cudaEventDestroy(e);
   if (c->ev_cs_done) cudaEventDestroy(c->ev_cs_done);
   if (c->cs) cudaStreamDestroy(c->cs);
@@ -2041,7 +2104,7 @@ int train_minibatches(arl_ctx* c, const int* idx, int mb_size, int count, int sy
     TrainPlan* P = nullptr;
     if (get_plan(c, mb_size, &P)) return 1;   // allocations happen outside capture
     cudaStream_t cap;
-    ARL_CHECK(c, cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+    ARL_CHECK(c, create_main_stream(&cap));
     long l0 = c->launches;
     cudaGraph_t g = nullptr;
     ARL_CHECK(c, cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
@@ -2309,6 +2372,23 @@ int async_push_pull(arl_ctx* c, cudaStream_t st) {
 }  // namespace
 extern "C" {
 
+/* pull only: central parameters -> local parameters + operand copies (ActsrvAltOvrlpPollSampler, poll_sampler.py:29-39) */
+int arl_async_pull(arl_ctx* c, void* stream) {
+  if (!c->async_.ready) ARL_FAIL(c, "async store not connected");
+  cudaStream_t st = (cudaStream_t)stream;
+  UpdateParams u{};
+  u.param = c->params; u.n = c->n_params;
+  bool fused_cast = (c->off_Wfc % 4 == 0) && (c->async_.dev.per % 4 == 0) && (c->H % 4 == 0);
+  u.shadow = fused_cast ? c->wfc_bf16 : nullptr;
+  if (fused_cast && fc_tiles_ok(c)) { u.shadow = c->wfc_t; u.shadow_tiles = 1; u.shadow_HW = c->HWlast; u.shadow_H = c->H; }
+  u.shadow_begin = c->off_Wfc; u.shadow_end = c->off_Wfc + (long)c->Kfc * c->H;
+  int grid = std::min(c->async_.dev.n_locks, 148);
+  async_pull_kernel<<<grid, kAsyncThreads, 0, st>>>(c->async_.dev, u);
+  c->launches++;
+  ARL_CHECK(c, cudaGetLastError());
+  return pack_weights(c, st, !fused_cast, false);
+}
+
 /* test hook: copy central array `which` (0 = p, 1 = m, 2 = v / accumulator) to the host */
 int arl_async_read_central(arl_ctx* c, int which, float* host_out, long n, void* stream) {
   if (!c->async_.ready) ARL_FAIL(c, "async store not connected");
@@ -2457,6 +2537,60 @@ int arl_profile_graph(arl_ctx* c, int kind, const int* idx, int mb_size, int rep
   ARL_CHECK(c, cudaStreamSynchronize(st));
   *n = cnt;
   snprintf(names, names_cap, "%s", all.c_str());
+  cudaGraphExecDestroy(ge);
+  cudaGraphDestroy(g);
+  cudaStreamDestroy(cap_s);
+  return 0;
+}
+
+/* Completion time of every kernel of ONE training minibatch inside the product's own forked graph (all streams), in
+   microseconds after the graph's first node: events are captured behind every launch, the graph is replayed a few times and
+   the events of the last replay are read.  kind 0: local update (clip_update), 1: synchronous step. */
+int arl_profile_timeline(arl_ctx* c, int kind, const int* idx, int mb_size, char* names, int names_cap, float* us, int cap,
+                         int* n, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TrainPlan* P = nullptr;
+  if (get_plan(c, mb_size, &P)) return 1;
+  const bool overlap = kind == 1 && sync_overlap_ok(c);
+  if (overlap && sync_overlap_prepare(c)) return 1;
+  cudaStream_t cap_s;
+  ARL_CHECK(c, create_main_stream(&cap_s));
+  if (!c->tl_buf && dev_alloc(c, &c->tl_buf, 96)) return 1;
+  c->prof_n = 0;
+  c->prof_timeline = true;
+  long l0 = c->launches;
+  cudaGraph_t g = nullptr;
+  ARL_CHECK(c, cudaStreamBeginCapture(cap_s, cudaStreamCaptureModeThreadLocal));
+  prof_mark(c, "begin", cap_s);
+  c->train_step_active = (kind == 0);
+  c->sync_overlap_active = overlap;
+  int rc = grad_minibatch(c, idx, c->mb_counter, mb_size, cap_s);
+  if (!rc) rc = kind == 1 ? (overlap ? sync_tail(c, cap_s) : sync_update(c, cap_s)) : clip_update(c, 1.f, cap_s);
+  c->train_step_active = false; c->sync_overlap_active = false; c->early_fc_done = false; c->pending_fin = nullptr;
+  c->pending_stream = false;
+  cudaError_t ce = cudaStreamEndCapture(cap_s, &g);
+  c->prof_timeline = false;
+  c->launches = l0;
+  if (rc) { if (g) cudaGraphDestroy(g); cudaStreamDestroy(cap_s); return rc; }
+  ARL_CHECK(c, ce);
+  cudaGraphExec_t ge = nullptr;
+  ARL_CHECK(c, cudaGraphInstantiate(&ge, g, 0));
+  ARL_CHECK(c, cudaMemsetAsync(c->mb_counter, 0, sizeof(int), st));
+  for (int i = 0; i < 4; ++i) ARL_CHECK(c, cudaGraphLaunch(ge, st));
+  ARL_CHECK(c, cudaMemsetAsync(c->mb_counter, 0, sizeof(int), st));
+  ARL_CHECK(c, cudaStreamSynchronize(st));
+  std::string all;
+  int cnt = 0;
+  unsigned long long h[96];
+  ARL_CHECK(c, cudaMemcpy(h, c->tl_buf, sizeof(h), cudaMemcpyDeviceToHost));
+  for (int i = 1; i < c->prof_n && cnt < cap; ++i) {
+    us[cnt++] = (float)((double)(long long)(h[i] - h[0]) * 1e-3);
+    all += c->prof_names[i];
+    all += ';';
+  }
+  *n = cnt;
+  snprintf(names, names_cap, "%s", all.c_str());
+  c->prof_n = 0;
   cudaGraphExecDestroy(ge);
   cudaGraphDestroy(g);
   cudaStreamDestroy(cap_s);

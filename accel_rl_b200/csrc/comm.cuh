@@ -808,6 +808,45 @@ __global__ void __launch_bounds__(kAsyncThreads) async_push_pull_kernel(AsyncDev
   }
 }
 
+// Pull only (ActsrvAltOvrlpPollSampler, poll_sampler.py:29-39: the sampler refreshes its policy from the central
+// parameters every poll_horizon rollout steps): per lock region {lock, copy central p -> local p (+ the bf16 FC operand
+// copy), unlock} — the same mutual exclusion a pushing learner takes, so a region is never read half-updated.
+__global__ void __launch_bounds__(kAsyncThreads) async_pull_kernel(AsyncDev d, UpdateParams p) {
+  for (int c = blockIdx.x; c < d.n_locks; c += gridDim.x) {
+    const long begin = (long)c * d.per;
+    const long end = min(p.n, begin + d.per);
+    if (threadIdx.x == 0) {
+      long long t0 = clock64();
+      unsigned int backoff = 32;
+      while (atomicCAS_system(d.locks + c, 0u, 1u) != 0u) {
+        __nanosleep(backoff);
+        if (backoff < 2048) backoff <<= 1;
+        if (clock64() - t0 > 40000000000LL) dev_fail(311);
+      }
+      __threadfence_system();
+    }
+    __syncthreads();
+    const long n4 = (end - begin) >> 2;
+    for (long i = threadIdx.x; i < n4; i += blockDim.x) {
+      const long e0 = begin + (i << 2);
+      const float4 p4 = ld_sys_f4(d.cp + e0);
+      *reinterpret_cast<float4*>(p.param + e0) = p4;
+      if (p.shadow && e0 >= p.shadow_begin && e0 + 4 <= p.shadow_end) {
+        long off = e0 - p.shadow_begin;
+        if (p.shadow_tiles) {
+          const unsigned ou = (unsigned)off, rr = ou / (unsigned)p.shadow_H;
+          off = fc_tile_index(rr, (int)(ou - rr * (unsigned)p.shadow_H), p.shadow_HW, p.shadow_H);
+        }
+        *reinterpret_cast<uint2*>(p.shadow + off) = make_uint2(pack_bf16x2(p4.x, p4.y), pack_bf16x2(p4.z, p4.w));
+      }
+    }
+    for (long e = begin + (n4 << 2) + threadIdx.x; e < end; e += blockDim.x) p.param[e] = ld_sys_f(d.cp + e);
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicExch_system(d.locks + c, 0u);
+  }
+}
+
 inline int async_local_init(AsyncState& s, int rank, int world, long n, int n_update_chunks, const float* params,
                             uint8_t* handle_out, std::string& err) {
   if (world < 1 || world > kMaxRanks) { err = "world size must be in [1,8]"; return 1; }

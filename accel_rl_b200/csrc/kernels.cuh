@@ -1213,6 +1213,9 @@ struct UpdateParams {
   // part-A blocks), [fc4_begin, +fc4_len) = the FC-weight range in float4 groups, which fc_gemm_kernel wrote directly
   const GradJob* fin_jobs; int n_fin_jobs;
   long fc4_begin, fc4_len;
+  // a2_resume > 0: elements [a2_begin, a2_mid) and [a2_resume, n) already sit in the flat gradient (finalised on the side
+  // streams while the conv gradient chain ran): update_stream_kernel's part-A2 blocks update them one element per thread
+  long a2_begin, a2_mid, a2_resume;
   uint32_t shadow_H_magic, shadow_HW_magic;   // floor(2^32/d) + 1: the tile index needs two divisions per float4 group
   // n_pk_jobs > 0: the conv operand packs (pconv.cuh tap tiles, forward and data-gradient variants) are refreshed by
   // the thread that updates the weight — a scatter through the inverse of pack_weights_kernel's index map — instead of
@@ -1492,7 +1495,7 @@ ARL_DEVINL void update_scalar(const UpdateParams& p, long i, float g, float alph
 }
 
 __global__ void __launch_bounds__(256, 4) update_stream_kernel(UpdateParams p, double* __restrict__ partial, int nA,
-                                                              long total_all) {
+                                                              int nA2, long total_all) {
   pdl_wait();
   pdl_trigger();
   __shared__ float s_alpha;
@@ -1528,9 +1531,20 @@ __global__ void __launch_bounds__(256, 4) update_stream_kernel(UpdateParams p, d
       acc += (double)(g * g);
       update_scalar(p, dst, g, alpha);
     }
+  } else if ((int)blockIdx.x < nA + nA2) {
+    // part A2: small tensors whose gradient is already in the flat vector
+    const long j = (long)((int)blockIdx.x - nA) * blockDim.x + threadIdx.x;
+    const long len0 = p.a2_mid - p.a2_begin;
+    const long i = j < len0 ? p.a2_begin + j : p.a2_resume + (j - len0);
+    if (i < p.n) {
+      const float g = p.grad[i];
+      acc += (double)(g * g);
+      update_scalar(p, i, g, alpha);
+    }
   } else {
     // part B: the FC weights
-    const long gtid = (long)((int)blockIdx.x - nA) * blockDim.x + threadIdx.x, gsize = (long)((int)gridDim.x - nA) * blockDim.x;
+    const int nAA = nA + nA2;
+    const long gtid = (long)((int)blockIdx.x - nAA) * blockDim.x + threadIdx.x, gsize = (long)((int)gridDim.x - nAA) * blockDim.x;
     const float4* g4p = reinterpret_cast<const float4*>(p.grad) + p.fc4_begin;
     for (long j = gtid; j < p.fc4_len; j += gsize) {
       const float4 g4 = g4p[j];

@@ -215,6 +215,12 @@ class Engine(object):
     def reset_opt_state(self):
         self.check(self.lib.arl_reset_opt_state(self.ctx, self._s()))
 
+    def get_opt_step(self):
+        """the optimizer's update count (Adam t) on this learner"""
+        t = C.c_int()
+        self.check(self.lib.arl_opt_step_get(self.ctx, C.byref(t), self._s()))
+        return int(t.value)
+
     def get_opt_state(self):
         """-> dict(m, v, step): first/second moment vectors (RMSProp keeps its accumulator in v) and the update count"""
         if self._dp_mode is not None:
@@ -247,6 +253,16 @@ class Engine(object):
                                               ms.ctypes.data_as(C.c_void_p), cap, C.byref(n), self._s()))
         labels = names.value.decode().split(";")[:n.value]
         return labels, ms[:n.value].copy()
+
+    def profile_timeline(self, kind, idx, mb_size, cap=96):
+        """-> [(label, completion time in us after the minibatch graph's first node)] over all streams"""
+        names = C.create_string_buffer(cap * 24)
+        us = np.zeros(cap, np.float32)
+        n = C.c_int()
+        self.check(self.lib.arl_profile_timeline(self.ctx, int(kind), L.ptr(idx), int(mb_size), names, len(names),
+                                                 us.ctypes.data_as(C.c_void_p), cap, C.byref(n), self._s()))
+        labels = names.value.decode().split(";")[:n.value]
+        return list(zip(labels, [float(x) for x in us[:n.value]]))
 
     def profile_end(self, cap=4096):
         names = C.create_string_buffer(cap * 24)
@@ -302,6 +318,10 @@ class Engine(object):
 
     def async_push_pull(self):
         self.check(self.lib.arl_async_push_pull(self.ctx, self._s()))
+
+    def async_pull(self):
+        """central parameters -> local parameters + operand copies (poll sampler)"""
+        self.check(self.lib.arl_async_pull(self.ctx, self._s()))
 
     def async_read_central(self, which=0):
         out = np.zeros(self.n_params, np.float32)

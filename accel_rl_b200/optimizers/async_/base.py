@@ -47,5 +47,12 @@ class BaseAsyncOptimizer(BaseOptimizer):
         return self._engine.async_read_central(0)
 
     @property
+    def central_params_handle(self):
+        """what ActsrvAltOvrlpPollSampler.poll_init takes as `central_shared_params`: pulls the central parameters into
+        this learner's policy on the device (poll_sampler.py:29-39)"""
+        from accel_rl_b200.sampler.poll_sampler import CentralParams
+        return CentralParams(self._engine)
+
+    @property
     def central_params_lock(self):
         raise NotImplementedError("the chunk locks live on the device (csrc/comm.cuh); read central_shared_params instead")

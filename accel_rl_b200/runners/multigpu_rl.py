@@ -98,6 +98,9 @@ class AccelRLAsync(AccelRLSync):
             return out
 
         self.algo.optimizer.init_comm(self.rank, self.n_runners, dict(exchange=exchange))
+        if hasattr(self.sampler, "poll_init"):
+            # the reference leaves this call to the experiment script (nothing in its tree makes it)
+            self.sampler.poll_init(self.algo.optimizer.central_params_handle, None)
         self._initial_param_vector = self.policy.get_param_values()
         if self.n_runners > 1:
             dist.barrier()

@@ -200,6 +200,9 @@ class ActsrvAltOvrlpSampler(BaseMbSampler):
             eng.rollout_run()
         else:
             self._rollout_host_fed(eng)
+        return self._finish_rollout(eng)
+
+    def _finish_rollout(self, eng):
         env, ln, ret, raw, nz, disc = eng.traj_read(self._traj_cap)   # synchronises the stream
         self.d2h_bytes += 4 + 24 * len(env)
         if eng.device_error():

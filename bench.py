@@ -65,6 +65,12 @@ def parse():
                     help="a2c: BASELINE configs[2]-style A2C (one full-batch RMSProp step per rollout; use --envs 1024 --horizon 5)")
     ap.add_argument("--parallelism", default="sync", choices=["sync", "async"],
                     help="multi-GPU learner: sync (configs[3], fused all-reduce) or async (configs[4], central store + chunk locks)")
+    ap.add_argument("--game", default="breakout",
+                    help="names the action count of the synthetic envs (ALE minimal action sets: breakout 4, pong / "
+                         "space_invaders 6, beam_rider 9, seaquest 18); BASELINE configs[4] is space_invaders")
+    ap.add_argument("--poll-horizon", type=int, default=0,
+                    help="async learners: ActsrvAltOvrlpPollSampler refreshing the policy from the central store every this "
+                         "many rollout steps (0: plain sampler)")
     ap.add_argument("--frames", default="gray", choices=["gray", "rgb"],
                     help="gray: the reference's pipeline, 210x160 grayscale screens -> (4,104,80), cnn preset 1 (default, parity "
                          "pinned); rgb: north-star mode, 210x160x3 RGB screens -> gray -> (4,84,84), classic Nature-CNN")
@@ -134,7 +140,8 @@ def build_runner(args, frame_feed, rank, world):
     logger.configure(None, quiet=True)
     rules = dict(pool_frames=args.pool_frames)
     rgb = getattr(args, "frames", "gray") == "rgb"
-    env_args = dict(game="breakout", max_start_noops=0, synth_rules=rules, frame_mode="rgb" if rgb else "gray")
+    env_args = dict(game=getattr(args, "game", "breakout"), max_start_noops=0, synth_rules=rules,
+                    frame_mode="rgb" if rgb else "gray")
     if frame_feed == "workers":
         from functools import partial
         from accel_rl_b200.hostsim import synth_emulator
@@ -144,6 +151,12 @@ def build_runner(args, frame_feed, rank, world):
             emu_factory=partial(synth_emulator.make, rules=rules, channels=3 if rgb else 1), EnvCls=AtariEnv, env_args=env_args,
             horizon=args.horizon, n_parallel=n_par, envs_per=args.envs // (2 * n_par), max_path_length=27000,
             mid_batch_reset=True, max_decorrelation_steps=0)
+    elif getattr(args, "poll_horizon", 0) > 0 and getattr(args, "parallelism", "sync") == "async":
+        from accel_rl_b200.sampler import ActsrvAltOvrlpPollSampler
+        sampler = ActsrvAltOvrlpPollSampler(
+            poll_horizon=args.poll_horizon, EnvCls=AtariEnv, env_args=env_args,
+            horizon=args.horizon, n_parallel=args.envs // 8, envs_per=4, max_path_length=27000, mid_batch_reset=True,
+            max_decorrelation_steps=0, frame_feed=frame_feed)
     else:
         sampler = ActsrvAltOvrlpSampler(
             EnvCls=AtariEnv, env_args=env_args,
@@ -310,7 +323,8 @@ def workload_config(args, world):
                          % (args.envs, args.horizon,
                             "classic Nature-CNN @ (4,84,84)" if rgb else "cnn preset %d @ (4,104,80)" % args.spec,
                             args.epochs, args.minibatch, "210x160x3 RGB" if rgb else "210x160 grayscale")),
-            "frames": args.frames,
+            "frames": args.frames, "game": getattr(args, "game", "breakout"),
+            "poll_horizon": getattr(args, "poll_horizon", 0),
             "algo": args.algo, "learner": ("single" if world == 1 and args.parallelism == "sync" else args.parallelism),
             "envs_per_gpu": args.envs, "horizon": args.horizon, "parallelism": "dp%d" % world,
             "l2_policy": "inputs larger than L2 (%.2f GB rollout buffer, %d MB frame pool)" %
@@ -372,6 +386,63 @@ def sync_parity(runner, rank, world):
     return out
 
 
+def async_parity(runner, rank, world):
+    """Proof carried by every asynchronous multi-GPU bench line (after the timed region): learners push in turn (a
+    barrier between turns); after learner k's push the central (p, m, v) in rank 0's HBM must equal the closed-form
+    Adam / RMSProp chunk update (optimizers/async/chunked_updates.py:53-120, per-learner step count) of the central state
+    read before the push, with learner k's gradient, and learner k's local parameters must BE the central ones
+    (optimizers/async/base.py:59-104 push then pull).  Raises on failure."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    eng = runner.policy.engine
+    cfg = eng.opt_cfg
+    b1, b2, eps, lr, rho = (float(cfg.beta1), float(cfg.beta2), float(cfg.epsilon), float(cfg.learning_rate), float(cfg.rho))
+    clip = float(cfg.grad_norm_clip)
+    eng.set_lr_mult(1.0)
+    eng.read_logs()
+    worst = 0.0
+    ok = True
+    for k in range(world):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        if rank == k:
+            p0, m0, v0 = (eng.async_read_central(i).astype(np.float64) for i in range(3))
+            t = eng.get_opt_step() + 1
+            g = (np.random.RandomState(500 + k).randn(eng.n_params) * 0.01).astype(np.float32)
+            eng.grad.copy_(torch.from_numpy(g))
+            eng.async_push_pull()
+            torch.cuda.synchronize()
+            g = g.astype(np.float64)
+            norm = np.sqrt((g * g).sum())
+            if clip > 0:
+                g = g * (min(norm, clip) / (1e-7 + norm))
+            if int(cfg.update) == 0:
+                m1 = b1 * m0 + (1 - b1) * g
+                v1 = b2 * v0 + (1 - b2) * g * g
+                want = p0 - lr * np.sqrt(1 - b2 ** t) / (1 - b1 ** t) * m1 / (np.sqrt(v1) + eps)
+            else:
+                v1 = rho * v0 + (1 - rho) * g * g
+                want = p0 - lr * g / np.sqrt(v1 + eps)
+            got = eng.async_read_central(0).astype(np.float64)
+            err = np.abs(got - want)
+            worst = max(worst, float(err.max()))
+            ok = ok and bool((err <= 2e-7 + 2e-6 * np.abs(want)).all())
+            ok = ok and bool(np.array_equal(eng.get_params(), got.astype(np.float32)))
+        if world > 1:
+            dist.barrier()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    w = torch.tensor([worst], device="cuda")
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        dist.all_reduce(w, op=dist.ReduceOp.MAX)
+    out = {"world": world, "turn_by_turn_push_matches_chunk_update": bool(flag.item()), "max_abs_err": float(w.item())}
+    if not out["turn_by_turn_push_matches_chunk_update"]:
+        raise SystemExit("async data-parallel parity check FAILED: %s" % out)
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -403,6 +474,8 @@ def run_ours(args):
             timeline = None
     phases = phase_split(runner, itr)
     parity = sync_parity(runner, rank, world) if (world > 1 and args.parallelism == "sync") else None
+    if args.parallelism == "async":
+        parity = async_parity(runner, rank, world)
     if rank == 0:
         bd = kernel_breakdown(runner, args) if (args.spec == 1 and world == 1 and args.algo == "ppo" and
                                                 args.parallelism == "sync") else {}

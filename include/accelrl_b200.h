@@ -222,6 +222,9 @@ int arl_async_local_init(arl_ctx* ctx, int rank, int world, int n_update_chunks,
 int arl_async_connect(arl_ctx* ctx, const uint8_t* rank0_handle);
 int arl_async_regions(arl_ctx* ctx);   /* lock regions the chunks were subdivided into */
 int arl_async_push_pull(arl_ctx* ctx, void* stream);
+/* pull only: central parameters -> local parameters + operand copies, per lock region under its lock
+   (ActsrvAltOvrlpPollSampler: the sampler refreshes its policy every poll_horizon rollout steps, poll_sampler.py:29-39) */
+int arl_async_pull(arl_ctx* ctx, void* stream);
 int arl_async_read_central(arl_ctx* ctx, int which, float* host_out, long n, void* stream);
 
 /* ---- diagnostics / tests ---------------------------------------------------------------------- */
@@ -235,6 +238,10 @@ int arl_profile_begin(arl_ctx* ctx, void* stream);
  * minibatch over idx[0..mb_size) (+ update), kind 1 = one rollout step; replayed `reps` times, last replay reported */
 int arl_profile_graph(arl_ctx* ctx, int kind, const int* idx, int mb_size, int reps, char* names, int names_cap, float* ms,
                       int cap, int* n, void* stream);
+/* completion time (microseconds after the first node) of every kernel of ONE training minibatch inside the product's own
+ * forked multi-stream graph: kind 0 = local update, 1 = synchronous data-parallel step */
+int arl_profile_timeline(arl_ctx* ctx, int kind, const int* idx, int mb_size, char* names, int names_cap, float* us, int cap,
+                         int* n, void* stream);
 int arl_profile_end(arl_ctx* ctx, char* names, int names_cap, float* ms, int cap, int* n, void* stream);   /* launches issued (graph replays count their node count) */
 /* plain tcgen05 GEMM self-test: D[M][N] = A[M][K] * B (B K-major [N][K] or N-major [K][N]) */
 int arl_test_gemm(arl_ctx* ctx, const uint16_t* a_bf16, const uint16_t* b_bf16, float* d, int M, int N, int K,

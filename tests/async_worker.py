@@ -115,6 +115,44 @@ def main():
         assert policy.engine.device_error() == 0
         barrier()
         policy.engine.close()
+    # ---- ActsrvAltOvrlpPollSampler (poll_sampler.py:6-56): the policy is refreshed from the central store every
+    #      poll_horizon rollout steps; with a refresh the rollout acts on the central parameters from that step on ----
+    from accel_rl_b200.sampler import ActsrvAltOvrlpPollSampler
+    T, ph = 12, 4
+    smp = ActsrvAltOvrlpPollSampler(poll_horizon=ph, EnvCls=AtariEnv, env_args=dict(game="breakout", max_start_noops=0, synth_rules=rules),
+                                    horizon=T, n_parallel=2, envs_per=2, max_decorrelation_steps=0)
+    algo = mAPPO(optimizer_args=dict(minibatch_size=32, epochs=1, n_update_chunks=3))
+    policy = AtariCnnPolicy(**cnn_specs[1])
+    runner = AccelRLAsync(algo=algo, policy=policy, sampler=smp, n_steps=8 * T * 4 * world, seed=5,
+                          affinities=[dict(gpu=i) for i in range(world)], log_interval_steps=8 * T * 2 * world)
+    runner.startup()
+    eng = policy.engine
+    samples, _ = smp.obtain_samples(0)
+    assert smp.n_polls == T // ph
+    runner.algo.optimize_policy(0, samples)
+    barrier()
+    torch.cuda.synchronize()
+    # make the local parameters stale on purpose; the central store keeps the trained ones
+    central = eng.async_read_central(0).copy()
+    stale = central + np.float32(0.05) * np.random.RandomState(3).randn(central.size).astype(np.float32)
+    eng.set_params(stale)
+    samples, _ = smp.obtain_samples(1)
+    torch.cuda.synchronize()
+    barrier()
+    from oracle import net as onet
+    obs = samples.observations.cpu().numpy()
+    prob = samples.agent_infos.prob.cpu().numpy()
+    B = smp.total_n_envs
+    rows = lambda s: np.arange(B) * T + s
+    if world == 1:     # (with other learners pushing meanwhile the central vector keeps moving)
+        p_stale, _ = onet.forward(torch.tensor(stale), torch.tensor(obs[rows(0)]), onet.CNN_SPECS[1], 4, True)
+        p_fresh, _ = onet.forward(torch.tensor(central), torch.tensor(obs[rows(ph - 1)]), onet.CNN_SPECS[1], 4, True)
+        np.testing.assert_allclose(prob[rows(0)], p_stale.numpy(), rtol=2e-3, atol=2e-5)          # before the first poll
+        np.testing.assert_allclose(prob[rows(ph - 1)], p_fresh.numpy(), rtol=2e-3, atol=2e-5)     # from step ph-1 on
+        np.testing.assert_array_equal(eng.get_params(), central)
+    assert eng.device_error() == 0
+    barrier()
+    eng.close()
     if rank == 0:
         print("ASYNC_OK world=%d" % world)
     if world > 1:
