@@ -72,6 +72,7 @@ struct PcLayer {
   // backward
   int dYpad = 0;
   __nv_bfloat16* dY = nullptr;   // gradient w.r.t. this layer's output, in this layer's grid at offset dYpad (layer 0: pixel grid)
+  __nv_bfloat16* dY_base = nullptr;   // layer 0: the allocation (dY = dY_base + 64 rows)
   long dY_rows = 0;
   __nv_bfloat16* dwpack = nullptr;  // data-gradient weights [T*T*Pout][P*64][64]
   int stages_fwd = 0, stages_dgrad = 0;
@@ -572,9 +573,11 @@ int alloc_pconv(arl_ctx* c, std::vector<PackJob>& pj) {
       q.dY_rows = (long)R * q.S + q.load_rows + 256;
       if (dev_alloc(c, &q.dY, (size_t)(q.N / 64) * q.dY_rows * 64)) return 1;
     } else {
-      // gradient w.r.t. the first layer's output PIXELS, position-aligned with the first layer's grid
+      // gradient w.r.t. the first layer's output PIXELS, position-aligned with the first layer's grid; 64 zero rows in
+      // front: the wide weight-gradient tiles read dY[q - tx] from one row before the first position
       q.dY_rows = (long)R * q.S + q.load_rows + 256;
-      if (dev_alloc(c, &q.dY, (size_t)q.dY_rows * q.N)) return 1;
+      if (dev_alloc(c, &q.dY_base, (size_t)(q.dY_rows + 64) * q.N)) return 1;
+      q.dY = q.dY_base + (size_t)64 * q.N;
     }
     if (dev_alloc(c, &q.wpack, (size_t)q.ntaps * q.P * q.N * 64)) return 1;
     PackJob j{};
@@ -701,6 +704,28 @@ int pconv_wgrad_layer(arl_ctx* c, int l, const __nv_bfloat16* obs16, const int* 
   for (int t = 0; t < q.ntaps; ++t)
     for (int pl = 0; pl < q.P; ++pl) p.blk_off[t * q.P + pl] = (pl * p.a_rows + q.shift[t]) * 128;
   p.dy = q.dY; p.dy_rows = 128 + 8;
+  static const bool wide_on = !(getenv("ARL_WGRAD_WIDE") && atoi(getenv("ARL_WGRAD_WIDE")) == 0);
+  // wide form: the taps of one row on the N axis (pconv.cuh).  Needs: T * Cout <= 256 columns per MMA, one or two MMAs
+  // per K step ((T+1)/2 tap-row pairs for single-plane layers, T tap rows for two-plane layers), the accumulators in
+  // 512 TMEM columns, and dY rows in front of the tile (dy_off >= T-1, or the zero prefix of layer 0's grid)
+  const int n_mma = (q.P == 2) ? q.T : (q.T + 1) / 2;
+  if (wide_on && q.T * q.N <= 256 && n_mma <= 2 && n_mma * q.T * q.N <= 512 && (q.P == 1 || q.P == 2) &&
+      (l == 0 || p.dy_off >= q.T - 1)) {
+    p.wide = 1; p.n_mma = n_mma; p.nb_atoms = q.T; p.T = q.T;
+    p.dy_rows = 128 + 16;
+    for (int i = 0; i < n_mma; ++i) {
+      if (q.P == 2) {            // A atoms = the two planes, MMA i = tap row i
+        p.a_off[i] = i * q.Wp * 128; p.a_lbo[i] = p.a_rows * 128;
+        p.ty0[i] = i; p.ty_step[i] = 0; p.pl_step[i] = 1;
+      } else {                   // A atoms = tap rows 2i, 2i+1 (Wp rows apart)
+        p.a_off[i] = 2 * i * q.Wp * 128; p.a_lbo[i] = q.Wp * 128;
+        p.ty0[i] = 2 * i; p.ty_step[i] = 1; p.pl_step[i] = 0;
+      }
+    }
+    // the second A atom of the last MMA may be a padding tap row (ty = T): its rows must still lie inside the stage
+    const int max_row = 127 + ((q.P == 2) ? (q.T - 1) : (2 * (n_mma - 1) + 1)) * q.Wp;
+    if (max_row >= p.a_rows) p.wide = 0;
+  }
   p.partial = c->wgrad_partial[l]; p.bias_partial = c->bias_partial[l];
   for (p.stages = 4; p.stages >= 2; --p.stages)
     if (pc_wgrad_smem(q.N, q.P, p.a_rows, p.dy_rows, p.stages) <= 227 * 1024) break;
@@ -1694,6 +1719,9 @@ void arl_destroy(arl_ctx* c) {
   for (auto p : c->wgrad_partial) cudaFree(p);
   for (auto p : c->bias_partial) cudaFree(p);
   if (c->shadow_in_comm) { (fc_tiles_ok(c) ? c->wfc_t : c->wfc_bf16) = nullptr; }
+  // patch-resident conv grids / operand packs and the FC tile planes
+  for (auto& q : c->pc) { cudaFree(q.in); cudaFree(q.dY_base ? q.dY_base : q.dY); cudaFree(q.wpack); cudaFree(q.dwpack); }
+  cudaFree(c->act_fc); cudaFree(c->wfc_t); cudaFree(c->dh_t); cudaFree(c->tl_buf);
   cudaFree(c->wfc_bf16); cudaFree(c->obs16_stage); cudaFree(c->step_obs16); cudaFree(c->roll_obs16); cudaFree(c->pack_jobs_dev); cudaFree(c->fc_partial); cudaFree(c->h); cudaFree(c->dh);
   cudaFree(c->dlogit); cudaFree(c->head_partial); cudaFree(c->head_b_partial); cudaFree(c->loss_partial);
   cudaFree(c->pk_slots);

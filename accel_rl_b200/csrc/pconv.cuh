@@ -379,6 +379,17 @@ struct PcWgradParams {
   float* partial;              // [gridDim.x][nblk*64][N]
   float* bias_partial;         // [gridDim.x][N]
   int stages;
+  // ---- wide form (wide = 1): the taps of one row, tx = T-1 .. 0, ride on the N axis -----------------------------------
+  //   D_i[(a, ch)][(j, co)] = sum_q'' A[q'' + ty*Wp][plane, ch] * dY[q'' - tx][co]   (= dW[ty][tx][plane, ch][co], q = q'' - tx)
+  // B = the SAME dY patch seen through `nb_atoms` MN-atoms one row apart (descriptor LBO = one dY row), so one MMA is
+  // M = 128 x N = nb_atoms*Cout and reads its 4 KB A slice once for T taps: 105 / 89 / 73 issue cycles for 96 / 64 / 32
+  // cycles of math instead of 73 / 65 for 32 / 16 (pconv.cuh header).  MMA i of a K step takes A atoms (a = 0, 1) at byte
+  // offsets a_off[i], a_off[i] + a_lbo[i] of the stage (two planes, or two tap rows ty = ty0[i] + a*ty_step[i]).
+  int wide, n_mma, nb_atoms, T;
+  int a_off[2], a_lbo[2];
+  int ty0[2], ty_step[2];      // tap row of A atom a of MMA i: ty0[i] + a*ty_step[i] (>= T: padding, dropped)
+  int pl_step[2];              // plane of A atom a of MMA i: a*pl_step[i]
+  int dy_bias_sub;             // stage row of dY[q0] (bias column sums); dy_sub = stage row of dY[q0 - (T-1)]
 };
 
 __host__ __device__ inline int pc_wgrad_stage_bytes(int N, int planes, int a_rows, int dy_rows) {
@@ -405,8 +416,9 @@ __global__ void __launch_bounds__(kPcThreads, 1) pconv_wgrad_kernel(const __grid
   float* red = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));   // [128][8] column-sum scratch
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int mt = (p.nblk + 1) >> 1;
-  const int acc_cols = mt * N;
+  const int mt = p.wide ? p.n_mma : (p.nblk + 1) >> 1;
+  const int NW = p.wide ? p.nb_atoms * N : N;                  // accumulator width of one MMA
+  const int acc_cols = mt * NW;
   const uint32_t tmem_cols = acc_cols <= 32 ? 32 : acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;
   const int my_tiles = ((int)blockIdx.x < p.ntiles) ? (p.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   if (tid == 0) {
@@ -425,7 +437,10 @@ __global__ void __launch_bounds__(kPcThreads, 1) pconv_wgrad_kernel(const __grid
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
-  const int dy_sub = p.dy_off & 7;           // row of the first wanted dY row inside the 8-aligned stage
+  // row of the first wanted dY row inside the 8-aligned stage (wide: the row of dY[q0 - (T-1)])
+  const int dy_first = p.wide ? p.dy_off - (p.T - 1) : p.dy_off;
+  const int dy_sub = dy_first & 7;
+  const int dy_bias_sub = p.wide ? dy_sub + (p.T - 1) : dy_sub;
 
   float csum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (warp == 0) {
@@ -452,7 +467,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) pconv_wgrad_kernel(const __grid
         apos = (long)tile * 128;
         dpos = apos;
       }
-      dpos += (p.dy_off & ~7);
+      dpos += (dy_first & ~7);              // (dy_first may be -1 for layer 0: the grid has a zero prefix of 8 rows)
       mbar_wait(empty_bar(s), ph ^ 1, 31);
       if (elect_one()) {
         mbar_arrive_expect_tx(full_bar(s), a_bytes + (uint32_t)p.dy_rows * ROWB);
@@ -477,6 +492,24 @@ __global__ void __launch_bounds__(kPcThreads, 1) pconv_wgrad_kernel(const __grid
       mbar_wait(full_bar(s), ph, 32);
       tc_fence_after();
       if (elect_one()) {
+       if (p.wide) {
+        const uint32_t a_stage = smem_base + s * stage_bytes;
+        // B: nb_atoms MN-atoms of N columns each, one dY row (ROWB bytes) apart; K groups of 8 rows 8*ROWB apart
+        const uint32_t b_lo0 = ((a_stage + a_bytes + dy_sub * ROWB) >> 4) | (((uint32_t)ROWB >> 4) << 16);
+        const uint32_t idesc_w = make_idesc_bf16(128, NW, 1, 1);
+        for (int m = 0; m < mt; ++m) {
+          const uint32_t a_lo0 = ((a_stage + p.a_off[m]) >> 4) | (((uint32_t)p.a_lbo[m] >> 4) << 16);
+          const uint32_t d_tmem = tmem_u + m * NW;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint64_t ad = ((uint64_t)a_hi32 << 32) | (uint64_t)(a_lo0 + kk * 128);
+            const uint64_t bd = ((uint64_t)b_hi32 << 32) | (uint64_t)(b_lo0 + kk * (ROWB));
+            umma_bf16(d_tmem, ad, bd, idesc_w, (it > 0 || kk > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(empty_bar(s));
+        if (it == my_tiles - 1) umma_commit(done_bar);
+       } else {
         const uint32_t a_stage = smem_base + s * stage_bytes;
         const uint32_t b_lo0 = ((a_stage + a_bytes + dy_sub * ROWB) >> 4) | b_flags;
         for (int m = 0; m < mt; ++m) {
@@ -493,6 +526,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) pconv_wgrad_kernel(const __grid
         }
         umma_commit(empty_bar(s));
         if (it == my_tiles - 1) umma_commit(done_bar);
+       }
       }
       __syncwarp();
     }
@@ -510,7 +544,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) pconv_wgrad_kernel(const __grid
       const uint32_t b_stage = smem_base + s * stage_bytes + a_bytes;
 #pragma unroll
       for (int i = 0; i < RPT; ++i) {
-        const int r = dy_sub + r0 + i * (128 / CH);
+        const int r = dy_bias_sub + r0 + i * (128 / CH);
         const uint32_t addr = b_stage + swz_off<ROWB>(r, c);
         uint4 v;
         asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -541,6 +575,27 @@ __global__ void __launch_bounds__(kPcThreads, 1) pconv_wgrad_kernel(const __grid
       tc_fence_after();
     }
     const int r = q * 32 + lane;
+    if (p.wide) {
+      // D_i row r = (atom a, channel ch), columns = (tx atom j, co): 32-column chunks never straddle a tap
+      const int a = r >> 6, ch = r & 63;
+      const int P = p.planes;
+      for (int m = 0; m < mt; ++m) {
+        const int ty = p.ty0[m] + a * p.ty_step[m], pl = a * p.pl_step[m];
+        for (int c0 = h * (NW / 2); c0 < (h + 1) * (NW / 2); c0 += 32) {
+          const int j = c0 / N, co0 = c0 - j * N, tx = p.T - 1 - j;
+          const int blk = (ty * p.T + tx) * P + pl;
+          const bool ok = ty < p.T;
+          float* dst = p.partial + ((long)blockIdx.x * p.nblk * 64 + (long)(ok ? blk : 0) * 64 + ch) * N + co0;
+          uint32_t v[32];
+          if (my_tiles > 0) { tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + m * NW + c0, v); tmem_ld_wait(); }
+          else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0;
+          }
+          store_rows32_coalesced(smem_base + (uint32_t)(warp - 2) * kRowStoreScratch, v, dst, ok, lane);
+        }
+      }
+    } else
     for (int m = 0; m < mt; ++m) {
       const int blk = 2 * m + (r >> 6);
       float* dst = p.partial + ((long)blockIdx.x * p.nblk * 64 + (long)blk * 64 + (r & 63)) * N + h * HC;
