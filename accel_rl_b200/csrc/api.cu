@@ -2312,7 +2312,6 @@ int sync_fc_exchange(arl_ctx* c, cudaStream_t ws, cudaStream_t st) {
   ARL_CHECK(c, cudaStreamWaitEvent(c->cs, c->ev_cs_in[0], 0));
   ARL_CHECK(c, cudaStreamWaitEvent(c->cs, c->ev_cs_in[1], 0));
   const CommDev& d = c->comm.dev;
-  ARL_CHECK(c, launch_k(sync_signal_kernel, dim3(1), dim3(32), 0, c->cs, d, (int)FLAG_A));
   SyncFcArgs a{};
   a.param = c->params; a.m = c->m; a.v = c->v;
   a.fc_begin = c->off_Wfc; a.fc_len = (long)c->Kfc * c->H;
@@ -2323,7 +2322,7 @@ int sync_fc_exchange(arl_ctx* c, cudaStream_t ws, cudaStream_t st) {
   if (d.world <= 2) ARL_CHECK(c, launch_k(sync_fc_kernel<2>, dim3(kSyncFcBlocks), dim3(kSyncFcThreads), 0, c->cs, d, a));
   else if (d.world <= 4) ARL_CHECK(c, launch_k(sync_fc_kernel<4>, dim3(kSyncFcBlocks), dim3(kSyncFcThreads), 0, c->cs, d, a));
   else ARL_CHECK(c, launch_k(sync_fc_kernel<kMaxRanks>, dim3(kSyncFcBlocks), dim3(kSyncFcThreads), 0, c->cs, d, a));
-  c->launches += 2;
+  c->launches += 1;
   prof_mark(c, "sync_fc", c->cs);
   ARL_CHECK(c, cudaGetLastError());
   ARL_CHECK(c, cudaEventRecord(c->ev_cs_done, c->cs));
@@ -2334,7 +2333,6 @@ int sync_tail(arl_ctx* c, cudaStream_t st) {
   const CommDev& d = c->comm.dev;
   const long n_small = c->n_params - (long)c->Kfc * c->H;
   const int blocks = (int)((n_small + 255) / 256);
-  ARL_CHECK(c, launch_k(sync_signal_kernel, dim3(1), dim3(32), 0, st, d, (int)FLAG_2));
   SyncTailArgs a{};
   a.param = c->params; a.m = c->m; a.v = c->v; a.n = c->n_params;
   a.fc_begin = c->off_Wfc; a.fc_len = (long)c->Kfc * c->H;
@@ -2346,7 +2344,7 @@ int sync_tail(arl_ctx* c, cudaStream_t st) {
   if (d.world <= 2) ARL_CHECK(c, launch_k(sync_tail_kernel<2>, dim3(blocks), dim3(256), 0, st, d, a));
   else if (d.world <= 4) ARL_CHECK(c, launch_k(sync_tail_kernel<4>, dim3(blocks), dim3(256), 0, st, d, a));
   else ARL_CHECK(c, launch_k(sync_tail_kernel<kMaxRanks>, dim3(blocks), dim3(256), 0, st, d, a));
-  c->launches += 2;
+  c->launches += 1;
   prof_mark(c, "sync_tail", st);
   ARL_CHECK(c, cudaGetLastError());
   return 0;

@@ -364,16 +364,16 @@ __global__ void __launch_bounds__(kSyncThreads) sync_allreduce_update_kernel(Com
 // own stream beside that chain, and only the ~80 k other elements are exchanged on the critical path.  Plain launches
 // only (no cooperative grid, no intra-grid barrier): every block polls a LOCAL flag word that peers advance.
 //
-//   sync_signal_kernel(A)   after this rank's fc_wgrad + fc_dgrad: "my FC gradient is final and my FC weights have been
-//                           consumed" -> flag A of every peer
-//   sync_fc_kernel          blocks wait for flag A from all ranks; rank r reduces slice r of the FC range by P2P loads
+//   sync_fc_kernel          (stream-ordered behind this rank's fc_wgrad + fc_dgrad) block 0 tells every peer "my FC gradient
+//                           is final and my FC weights have been consumed" (flag A); all blocks wait for flag A from all
+//                           ranks; rank r reduces slice r of the FC range by P2P loads
 //                           (rank order: bit-identical everywhere), averages, Adam/RMSProp on the slice (its m, v live
 //                           here only), P2P-stores the new fp32 weights + bf16 operand tiles to every rank; the LAST
 //                           block publishes the slice's sum of squares to every rank, then flag B ("slice r published,
 //                           my reads of your gradients are done")
 //   finalize_grads_kernel   (main stream, as on one GPU) the other tensors' local gradients -> flat vector
-//   sync_signal_kernel(2)   "my small gradients are final" -> flag 2 of every peer
-//   sync_tail_kernel        blocks wait for flag 2 and flag B from all ranks; EVERY rank averages the small gradients of
+//   sync_tail_kernel        block 0 tells every peer "my small gradients are final" (flag 2); all blocks wait for flag 2
+//                           and flag B from all ranks; EVERY rank averages the small gradients of
 //                           all ranks (P2P loads, rank order) and applies the update to its own replica (identical
 //                           inputs, identical arithmetic -> bit-identical parameters, no broadcast), refreshes its conv
 //                           operand packs; the last block logs norm / loss and advances the device counters + epochs.
@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(kSyncThreads) sync_allreduce_update_kernel(Com
 // or a norm slot a peer may still be reading.
 // ===========================================================================
 // small CTAs (256 threads, <= 64 registers) so they co-reside with the persistent conv CTAs (352 threads x 118 registers)
-constexpr int kSyncFcBlocks = 96;
+constexpr int kSyncFcBlocks = 148;   // one per SM: 256 threads x 64 registers fit beside any conv CTA (<= 352 x 129)
 constexpr int kSyncFcThreads = 256;
 enum { FLAG_OLD = 0, FLAG_A = 16, FLAG_B = 32, FLAG_2 = 48 };           // u32 word offsets inside a rank's flag block
 enum { EP_A = 20, EP_B = 21, EP_2 = 22, TK_FC = 24, TK_TAIL = 26 };     // words of the local counter block (grid_counter)
@@ -428,6 +428,11 @@ __global__ void __launch_bounds__(kSyncFcThreads, 4) sync_fc_kernel(CommDev d, S
   unsigned long long tr0 = 0, tr1 = 0;
   if (threadIdx.x == 0) {
     tr0 = gtimer_ns();
+    if (blockIdx.x == 0) {
+      // "my FC gradient is final, my FC weights have been consumed" (this kernel is stream-ordered behind both kernels)
+      __threadfence_system();
+      for (int r = 0; r < d.world; ++r) st_relaxed_sys_add(d.peer_flag[r] + FLAG_A);
+    }
     sync_wait_flag(d, FLAG_A, EP_A, 330);
     tr1 = gtimer_ns();
     const int tstep = a.step[0] + 1;
@@ -446,18 +451,24 @@ __global__ void __launch_bounds__(kSyncFcThreads, 4) sync_fc_kernel(CommDev d, S
   const long end = min(a.fc_begin + a.fc_len, begin + a.per);
   const long len4 = end > begin ? (end - begin) >> 2 : 0;
   const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x, gsz = (long)gridDim.x * blockDim.x;
-  constexpr int U = 8 / W;                 // W x U = 8 independent 16-byte loads in flight per thread
+  // every load of an iteration is issued before the first use: W*U gradient groups (one local, the others over NVLink,
+  // ~2.5 us each) and the 3*U local state groups (p, m, v) — the loop is pure latency
+  constexpr int U = (W <= 2) ? 2 : 1;
   double acc = 0.0;
   for (long i0 = gtid; i0 < len4; i0 += U * gsz) {
-    float4 g[W][U];
+    float4 g[W][U], p4[U], v4[U], m4[U];
 #pragma unroll
-    for (int r = 0; r < W; ++r)
+    for (int u = 0; u < U; ++u) {
+      const long i = i0 + u * gsz;
+      const bool in = i < len4;
+      const long gi = begin + 4 * (in ? i : 0);
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const long i = i0 + u * gsz;
-        g[r][u] = (r < d.world && i < len4) ? *reinterpret_cast<const float4*>(d.peer_grad[r] + begin + 4 * i)
-                                            : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      for (int r = 0; r < W; ++r)
+        g[r][u] = (r < d.world && in) ? *reinterpret_cast<const float4*>(d.peer_grad[r] + gi) : make_float4(0.f, 0.f, 0.f, 0.f);
+      p4[u] = *reinterpret_cast<const float4*>(a.param + gi);
+      v4[u] = *reinterpret_cast<const float4*>(a.v + gi);
+      m4[u] = (a.kind == 0) ? *reinterpret_cast<const float4*>(a.m + gi) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long i = i0 + u * gsz;
@@ -469,22 +480,13 @@ __global__ void __launch_bounds__(kSyncFcThreads, 4) sync_fc_kernel(CommDev d, S
       t.x *= inv_world; t.y *= inv_world; t.z *= inv_world; t.w *= inv_world;
       acc += (double)(t.x * t.x + t.y * t.y) + (double)(t.z * t.z + t.w * t.w);
       const long gi = begin + 4 * i;
-      const float4 p4 = *reinterpret_cast<const float4*>(a.param + gi);
-      const float4 v4 = *reinterpret_cast<const float4*>(a.v + gi);
       float gg[4] = {t.x, t.y, t.z, t.w};
-      float pp[4] = {p4.x, p4.y, p4.z, p4.w};
-      float vv[4] = {v4.x, v4.y, v4.z, v4.w};
-      if (a.kind == 0) {
-        const float4 m4 = *reinterpret_cast<const float4*>(a.m + gi);
-        float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+      float pp[4] = {p4[u].x, p4[u].y, p4[u].z, p4[u].w};
+      float vv[4] = {v4[u].x, v4[u].y, v4[u].z, v4[u].w};
+      float mm[4] = {m4[u].x, m4[u].y, m4[u].z, m4[u].w};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) opt_step_raw(0, a.beta1, a.beta2, a.eps, a.rho, pp[k], mm[k], vv[k], gg[k], alpha);
-        *reinterpret_cast<float4*>(a.m + gi) = make_float4(mm[0], mm[1], mm[2], mm[3]);
-      } else {
-        float dummy = 0.f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) opt_step_raw(1, a.beta1, a.beta2, a.eps, a.rho, pp[k], dummy, vv[k], gg[k], alpha);
-      }
+      for (int k = 0; k < 4; ++k) opt_step_raw(a.kind, a.beta1, a.beta2, a.eps, a.rho, pp[k], mm[k], vv[k], gg[k], alpha);
+      if (a.kind == 0) *reinterpret_cast<float4*>(a.m + gi) = make_float4(mm[0], mm[1], mm[2], mm[3]);
       *reinterpret_cast<float4*>(a.v + gi) = make_float4(vv[0], vv[1], vv[2], vv[3]);
       const float4 pn = make_float4(pp[0], pp[1], pp[2], pp[3]);
       long off = gi - a.fc_begin;
@@ -548,6 +550,11 @@ __global__ void __launch_bounds__(256) sync_tail_kernel(CommDev d, SyncTailArgs 
   unsigned long long tr0 = 0, tr1 = 0;
   if (threadIdx.x == 0) {
     tr0 = gtimer_ns();
+    if (blockIdx.x == 0) {
+      // "my small gradients are final" (this kernel is stream-ordered behind finalize_grads and the side streams)
+      __threadfence_system();
+      for (int r = 0; r < d.world; ++r) st_relaxed_sys_add(d.peer_flag[r] + FLAG_2);
+    }
     sync_wait_flag(d, FLAG_2, EP_2, 331);
     sync_wait_flag(d, FLAG_B, EP_B, 332);
     tr1 = gtimer_ns();
@@ -605,16 +612,26 @@ __global__ void __launch_bounds__(256) sync_tail_kernel(CommDev d, SyncTailArgs 
   }
   __syncthreads();
   if (!s_last) return;
+  // last block: fixed-assignment strided sums over all its threads, then a fixed tree (bit-reproducible)
+  __threadfence();
+  double a2 = 0.0;
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) a2 += __ldcg(a.partial + b);
+  a2 = warp_sum_d(a2);
+  float l = 0.f;
+  for (int b = threadIdx.x; b < a.n_loss_blocks; b += blockDim.x) l += a.loss_partial[4 * b + 3];
+  l = warp_sum(l);
+  __shared__ float s_l[8];
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { s_red[threadIdx.x >> 5] = a2; s_l[threadIdx.x >> 5] = l; }
+  __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
     double t = 0.0;
-    for (int b = 0; b < (int)gridDim.x; ++b) t += __ldcg(a.partial + b);
+    float tl = 0.f;
+    for (int w = 0; w < 8; ++w) { t += s_red[w]; tl += s_l[w]; }
     const volatile double* np = d.peer_norm[d.rank];
     for (int r = 0; r < d.world; ++r) t += np[r];                           // FC slices, rank order
-    float l = 0.f;
-    for (int b = 0; b < a.n_loss_blocks; ++b) l += a.loss_partial[4 * b + 3];
     const int slot = a.log_slot[0];
-    if (slot < a.log_cap) { a.out_norm[slot] = (float)sqrt(t); a.out_loss[slot] = l; }
+    if (slot < a.log_cap) { a.out_norm[slot] = (float)sqrt(t); a.out_loss[slot] = tl; }
     a.step[0] += 1; a.log_slot[0] += 1; a.mb_counter[0] += 1;
     volatile unsigned int* gc = reinterpret_cast<volatile unsigned int*>(d.grid_counter);
     gc[EP_2] += 1u; gc[EP_B] += 1u;
