@@ -679,18 +679,20 @@ int launch_pconv_wgrad(arl_ctx* c, const PcWgradParams& p, int ctas, cudaStream_
   return 0;
 }
 
+bool pconv_bwd_fused_ok(arl_ctx* c, int l, int n, struct arl::PcBwdParams* out);
 int pc_wgrad_ctas(arl_ctx* c, int l, int n) {
   const PcLayer& q = c->pc[l];
   int ntiles = (l == 0) ? n * q.tiles_per_img : (int)(((long)n * q.S + 127) / 128);
+  if (pconv_bwd_fused_ok(c, l, n, nullptr)) return std::min(ntiles, 148);     // one partial per CTA of pconv_bwd_kernel
   int cap = (l > 0 && c->wgrad_ctas > 0) ? c->wgrad_ctas : 148;    // layer 0's wgrad runs alone at the end of the chain
   return std::min(ntiles, cap);
 }
 
 // weight (+ bias) gradient partials of conv layer l on the patch-resident path
-int pconv_wgrad_layer(arl_ctx* c, int l, const __nv_bfloat16* obs16, const int* idx, const int* idx_off, int n,
-                      cudaStream_t st) {
+int pconv_wgrad_params(arl_ctx* c, int l, const __nv_bfloat16* obs16, const int* idx, const int* idx_off, int n,
+                       PcWgradParams& p) {
   const PcLayer& q = c->pc[l];
-  PcWgradParams p{};
+  p = PcWgradParams{};
   if (l == 0) {
     p.a = obs16; p.a_plane_stride = 0; p.idx = idx; p.idx_off = idx_off; p.nb = n;
     p.tiles_per_img = q.tiles_per_img; p.ntiles = n * q.tiles_per_img; p.dy_off = 0;
@@ -730,6 +732,14 @@ int pconv_wgrad_layer(arl_ctx* c, int l, const __nv_bfloat16* obs16, const int* 
   for (p.stages = 4; p.stages >= 2; --p.stages)
     if (pc_wgrad_smem(q.N, q.P, p.a_rows, p.dy_rows, p.stages) <= 227 * 1024) break;
   if (p.stages < 2) ARL_FAIL(c, "pconv wgrad: stage does not fit shared memory");
+  return 0;
+}
+
+int pconv_wgrad_layer(arl_ctx* c, int l, const __nv_bfloat16* obs16, const int* idx, const int* idx_off, int n,
+                      cudaStream_t st) {
+  const PcLayer& q = c->pc[l];
+  PcWgradParams p;
+  if (pconv_wgrad_params(c, l, obs16, idx, idx_off, n, p)) return 2;
   int ctas = pc_wgrad_ctas(c, l, n);
   if (q.N == 32) return launch_pconv_wgrad<32>(c, p, ctas, st);
   if (q.N == 64) return launch_pconv_wgrad<64>(c, p, ctas, st);
@@ -737,11 +747,11 @@ int pconv_wgrad_layer(arl_ctx* c, int l, const __nv_bfloat16* obs16, const int* 
 }
 
 // data gradient of conv layer l (>= 1): dY_l -> gradient w.r.t. layer l-1's output, masked by that output's ReLU
-int pconv_dgrad_layer(arl_ctx* c, int l, int n, cudaStream_t st) {
+void pconv_dgrad_params(arl_ctx* c, int l, int n, PcParams& p) {
   const PcLayer& q = c->pc[l];
   const PcLayer& lo = c->pc[l - 1];
   const ConvLayer& L = c->conv[l];
-  PcParams p{};
+  p = PcParams{};
   const int Pout = q.N / 64;
   p.src = q.dY; p.src_plane_stride = q.dY_rows * 64; p.planes = Pout;
   p.S = q.S; p.Wp = q.Wp; p.n_img = n; p.tiles_per_img = 0;
@@ -768,7 +778,62 @@ int pconv_dgrad_layer(arl_ctx* c, int l, int n, cudaStream_t st) {
     o.us_shift = (L.s == 2) ? 1 : 2;
   }
   o.ds_shift = 0; if (o.us == 0) o.us = 1;
-  return launch_pconv_n(c, q.P * 64, p, st);
+}
+
+int pconv_dgrad_layer(arl_ctx* c, int l, int n, cudaStream_t st) {
+  PcParams p;
+  pconv_dgrad_params(c, l, n, p);
+  return launch_pconv_n(c, c->pc[l].P * 64, p, st);
+}
+
+// Data AND weight gradient of layer l (>= 1) in one kernel (pconv_bwd_kernel): both read the same dY tile.  Possible when
+// the weight gradient takes the wide form, the dY patch of the data gradient covers the rows the weight gradient needs,
+// and weights + >= 2 stages fit shared memory.
+// OFF by default (ARL_FUSED_BWD=1 enables; every parity test passes with it): measured 54.9 vs 51.0 ms per iteration.
+// The fused kernels are correct and remove the SM sharing between the two gradient kernels of a layer, but each of their
+// 148 CTAs handles only 3.5 tiles and pays both kernels' fixed costs (resident data-gradient weights, 512 TMEM columns,
+// two epilogues): 15.5 / 16.9 us against 9.2 + 17.3 / 11.6 + 14.5 us where the weight-gradient halves ran on 48 SMs BESIDE
+// the chain (10.8 tiles per CTA) — in SM-time, 148 x 15.5 = 2294 SM-us against 1362 + 830 = 2192, and the FC weight gradient
+// still shares the GPU with conv2_bwd (profiles/r2_timeline.md).
+bool pconv_bwd_fused_ok(arl_ctx* c, int l, int n, PcBwdParams* out) {
+  static const bool on = getenv("ARL_FUSED_BWD") && atoi(getenv("ARL_FUSED_BWD")) != 0;
+  if (!on || l < 1 || l >= (int)c->pc.size()) return false;
+  const PcLayer& q = c->pc[l];
+  if (q.N != 64) return false;
+  const int ND = q.P * 64;
+  if (ND != 64 && ND != 128) return false;
+  PcBwdParams b{};
+  pconv_dgrad_params(c, l, n, b.d);
+  if (pconv_wgrad_params(c, l, nullptr, nullptr, nullptr, n, b.g)) return false;
+  if (!b.g.wide || b.d.planes != 1) return false;
+  if (2 * ND + b.g.n_mma * b.g.nb_atoms * 64 > 512) return false;                 // TMEM columns
+  if (b.g.dy_off - (b.g.T - 1) < 0 || b.g.dy_off + 128 > b.d.load_rows) return false;   // dY rows inside the patch
+  for (b.d.stages = 4; b.d.stages >= 2; --b.d.stages)
+    if (pc_bwd_smem(ND, b.d.ntaps, b.d.planes, b.d.load_rows, b.g.planes, b.g.a_rows, b.d.stages) <= 227 * 1024) break;
+  if (b.d.stages < 2) return false;
+  if (out) *out = b;
+  return true;
+}
+
+template <int ND>
+int launch_pconv_bwd(arl_ctx* c, const PcBwdParams& b, cudaStream_t st) {
+  const int smem = pc_bwd_smem(ND, b.d.ntaps, b.d.planes, b.d.load_rows, b.g.planes, b.g.a_rows, b.d.stages);
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    ARL_CHECK(c, cudaFuncSetAttribute(pconv_bwd_kernel<ND, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
+  }
+  const int ctas = std::min(b.d.ntiles, 148);
+  ARL_CHECK(c, launch_k(pconv_bwd_kernel<ND, 64>, dim3(ctas), dim3(kPcBwdThreads), smem, st, b));
+  c->launches++;
+  ARL_CHECK(c, cudaGetLastError());
+  return 0;
+}
+
+int pconv_bwd_layer(arl_ctx* c, int l, int n, cudaStream_t st) {
+  PcBwdParams b;
+  if (!pconv_bwd_fused_ok(c, l, n, &b)) ARL_FAIL(c, "fused conv backward not available for this layer");
+  return (c->pc[l].P == 2) ? launch_pconv_bwd<128>(c, b, st) : launch_pconv_bwd<64>(c, b, st);
 }
 
 // gradient grids must be zero outside the rows the current batch writes
@@ -1326,11 +1391,27 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
     prof_mark(c, "fc_dgrad", st);
   }
   // ---- conv layers, last to first ----
+  bool used_side2 = false;
   for (int l = (int)c->conv.size() - 1; l >= 0 && pcb; --l) {
+    if (pconv_bwd_fused_ok(c, l, n, nullptr)) {
+      // data + weight gradient of layer l in one kernel on the main chain; its partials are finalised beside the chain
+      if (pconv_bwd_layer(c, l, n, st)) return 1;
+      prof_mark(c, l == 2 ? "conv2_bwd" : l == 1 ? "conv1_bwd" : "conv_bwd", st);
+      if (P->early_jobs) {
+        cudaStream_t fs = (ws != st) ? ws : st;
+        if (fs != st) {
+          ARL_CHECK(c, cudaEventRecord(c->ev_fin[l & 1], st));
+          ARL_CHECK(c, cudaStreamWaitEvent(fs, c->ev_fin[l & 1], 0));
+        }
+        if (launch_finalize(c, P, 2 * l, 2, "finalize_conv", fs)) return 1;
+      }
+      continue;
+    }
     // layer l's gradient grid was completed by the last kernel on `st` (FC dgrad or dgrad l+1); the first layer's
     // wgrad closes the main chain itself
     cudaStream_t wl = (l == 0 || ws == st) ? st : c->side2;
     if (wl != st) {
+      used_side2 = true;
       cudaEvent_t ev = c->ev_fork[1 + (l % 3)];
       ARL_CHECK(c, cudaEventRecord(ev, st));
       ARL_CHECK(c, cudaStreamWaitEvent(wl, ev, 0));
@@ -1355,7 +1436,7 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
   if (ws != st) {
     ARL_CHECK(c, cudaEventRecord(c->ev_join, ws));
     ARL_CHECK(c, cudaStreamWaitEvent(st, c->ev_join, 0));
-    if (c->conv.size() > 1) {
+    if (used_side2) {
       ARL_CHECK(c, cudaEventRecord(c->ev_join2, c->side2));
       ARL_CHECK(c, cudaStreamWaitEvent(st, c->ev_join2, 0));
     }

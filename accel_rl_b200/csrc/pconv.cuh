@@ -628,4 +628,275 @@ __global__ void __launch_bounds__(kPcThreads, 1) pconv_wgrad_kernel(const __grid
   }
 }
 
+// ---------------------------------------------------------------------------
+// pconv_bwd_kernel: data gradient AND weight gradient of one conv layer (l >= 1) in ONE persistent kernel.
+// Both read the same tile of the output-gradient grid dY: the data gradient as its K-major A operand (rows shifted per
+// tap, as in pconv_fwd_kernel), the weight gradient as its MN-major B operand (wide form: the taps of a row on the N
+// axis).  Run as two kernels they share the GPU — the weight gradient holds 48 SMs while the data-gradient chain, the
+// critical path, runs in two waves on the rest (profiles/r2_timeline.md).  Fused: one dY patch copy per tile serves both,
+// every SM works on the critical path, and one launch / prologue / drain is paid instead of two.
+//   TMEM (512 columns): [0, 2*ND) two data-gradient accumulators (epilogue overlaps the next tile),
+//                       [2*ND, 2*ND + n_mma*NW) the weight-gradient accumulators, accumulated over ALL tiles of the CTA.
+//   stage = dY patch (planes_out x load_rows x 128 B; wgrad B = the same bytes from row dy_first on) + forward-input patch
+//           (P x a_rows x 128 B, wgrad A).
+//   warps: 0 producer, 1 MMA issuer, 2..9 data-gradient epilogue per tile (+ weight-gradient epilogue at the end),
+//          10..13 column sums of dY (bias gradient).
+// ---------------------------------------------------------------------------
+constexpr int kPcBwdThreads = 448;
+
+struct PcBwdParams {
+  PcParams d;          // data gradient: src = dY grid, w = flipped/transposed weight pack, out = mask (+ unfold)
+  PcWgradParams g;     // weight gradient, wide form only (g.a = forward input grid, g.dy_off, g.a_off/a_lbo ...)
+};
+
+__host__ __device__ inline int pc_bwd_stage_bytes(int planes_out, int load_rows, int P, int a_rows) {
+  return (planes_out * load_rows + P * a_rows) * 128;
+}
+__host__ __device__ inline int pc_bwd_smem(int ND, int ntaps, int planes_out, int load_rows, int P, int a_rows, int stages) {
+  return ntaps * planes_out * ND * 128 + stages * pc_bwd_stage_bytes(planes_out, load_rows, P, a_rows) + 1024 + 256 + 128 * 8 * 4;
+}
+
+template <int ND, int NC>
+__global__ void __launch_bounds__(kPcBwdThreads, 1) pconv_bwd_kernel(const __grid_constant__ PcBwdParams pp) {
+  static_assert(ND == 64 || ND == 128, "data-gradient tile width");
+  static_assert(NC == 64, "weight-gradient filter count");
+  const PcParams& p = pp.d;
+  const PcWgradParams& g = pp.g;
+  if ((int)blockIdx.x >= p.ntiles) return;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int nblk = p.ntaps * p.planes;                                  // data-gradient weight tiles
+  const uint32_t w_base = smem_base;
+  const uint32_t dy_bytes = (uint32_t)p.planes * p.load_rows * 128;     // dY patch of a stage
+  const uint32_t a_bytes = (uint32_t)g.planes * g.a_rows * 128;         // forward-input patch of a stage
+  const uint32_t stage_bytes = dy_bytes + a_bytes;
+  const uint32_t st_base = w_base + nblk * (ND * 128);
+  const uint32_t bar_base = st_base + p.stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (16 + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (18 + b); };
+  const uint32_t wfull_bar = bar_base + 8u * 20;
+  const uint32_t done_bar = bar_base + 8u * 21;
+  const uint32_t tmem_ptr_addr = bar_base + 8u * 22;
+  float* red = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));   // [128][8] column-sum scratch
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NW = g.nb_atoms * NC;                                        // width of one weight-gradient accumulator
+  const int my_tiles = (p.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1;
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1 + 4);          // MMA commit + the four column-sum warps
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 8);
+    }
+    mbar_init(wfull_bar, 1);
+    mbar_init(done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_addr, 512);
+  pdl_wait();
+  pdl_trigger();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+  const uint32_t wg_col0 = 2 * ND;                                       // first weight-gradient column
+  const int dy_first = g.dy_off - (g.T - 1);                             // patch row of dY[q0 - (T-1)] (>= 0 here)
+
+  float csum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      mbar_arrive_expect_tx(wfull_bar, (uint32_t)nblk * ND * 128);
+      for (int b = 0; b < nblk; ++b) bulk_g2s(w_base + b * (ND * 128), p.w + (long)b * ND * 64, ND * 128, wfull_bar);
+    }
+    __syncwarp();
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int s = it % p.stages;
+      const uint32_t ph = (it / p.stages) & 1;
+      const long pos0 = (long)tile * 128;
+      mbar_wait(empty_bar(s), ph ^ 1, 41);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(full_bar(s), stage_bytes);
+        const uint32_t dst = st_base + s * stage_bytes;
+        for (int pl = 0; pl < p.planes; ++pl)
+          bulk_g2s(dst + pl * p.load_rows * 128, p.src + pl * p.src_plane_stride + pos0 * 64, p.load_rows * 128, full_bar(s));
+        for (int pl = 0; pl < g.planes; ++pl)
+          bulk_g2s(dst + dy_bytes + pl * g.a_rows * 128, g.a + pl * g.a_plane_stride + pos0 * 64, g.a_rows * 128, full_bar(s));
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t tmem_u = make_uniform(tmem_base);
+    constexpr uint32_t idesc_d = make_idesc_bf16(128, ND, 0, 0);
+    const uint32_t idesc_w = make_idesc_bf16(128, NW, 1, 1);
+    const uint64_t kd0 = make_smem_desc(0, 16, 1024, 2);                 // K-major SWIZZLE_128B (data gradient A, B)
+    const uint32_t k_hi32 = (uint32_t)(kd0 >> 32), k_flags = (uint32_t)kd0;
+    auto mk = [&](uint32_t lo) { return ((uint64_t)k_hi32 << 32) | (uint64_t)lo; };
+    const uint32_t mn_hi32 = (uint32_t)(make_smem_desc(0, 16, 1024, 2) >> 32);   // MN-major: SBO = 8 rows x 128 B
+    mbar_wait(wfull_bar, 0, 42);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int s = it % p.stages;
+      const uint32_t ph = (it / p.stages) & 1;
+      const int acc = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(tempty_bar(acc), aph ^ 1, 43);
+      mbar_wait(full_bar(s), ph, 44);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t stage = st_base + s * stage_bytes;
+        // ---- data gradient: every tap = the dY patch through a row-shifted descriptor ----
+        {
+          const uint32_t d_tmem = tmem_u + acc * ND;
+          uint32_t first = 0;
+          uint32_t b_lo = (w_base >> 4) | k_flags;
+          for (int t = 0; t < p.ntaps; ++t) {
+            uint32_t a_lo = ((stage + p.shift[t] * 128) >> 4) | k_flags;
+            for (int pl = 0; pl < p.planes; ++pl) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16(d_tmem, mk(a_lo + 2 * k), mk(b_lo + 2 * k), idesc_d, first);
+                first = 1;
+              }
+              a_lo += (uint32_t)p.load_rows * 8;
+              b_lo += ND * 8;
+            }
+          }
+          umma_commit(tfull_bar(acc));
+        }
+        // ---- weight gradient (wide form), accumulated over all tiles of this CTA ----
+        {
+          const uint32_t b_lo0 = ((stage + dy_first * 128) >> 4) | ((128u >> 4) << 16);    // atoms one dY row apart
+          for (int m = 0; m < g.n_mma; ++m) {
+            const uint32_t a_lo0 = ((stage + dy_bytes + g.a_off[m]) >> 4) | (((uint32_t)g.a_lbo[m] >> 4) << 16);
+            const uint32_t d_tmem = tmem_u + wg_col0 + m * NW;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+              const uint64_t ad = ((uint64_t)mn_hi32 << 32) | (uint64_t)(a_lo0 + kk * 128);
+              const uint64_t bd = ((uint64_t)mn_hi32 << 32) | (uint64_t)(b_lo0 + kk * 128);
+              umma_bf16(d_tmem, ad, bd, idesc_w, (it > 0 || kk > 0) ? 1u : 0u);
+            }
+          }
+        }
+        umma_commit(empty_bar(s));
+        if (it == my_tiles - 1) umma_commit(done_bar);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 2 && warp < 10) {
+    // ===================== data-gradient epilogue (as pconv_fwd_kernel, modes 1 / 2) =====================
+    const PcOut& o = p.out;
+    const int q = warp & 3;
+    const int h = (warp - 2) >> 2;
+    constexpr int HC = ND / 2;
+    constexpr int NB = HC / 32;
+    const uint32_t row = q * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const uint32_t qq = (uint32_t)tile * 128 + row;
+      const uint32_t b = pc_fdiv(qq, (uint32_t)p.S, p.magic_S);
+      const uint32_t pl_ = qq - b * p.S;
+      const uint32_t y = pc_fdiv(pl_, (uint32_t)p.Wp, p.magic_Wp), x = pl_ - y * p.Wp;
+      const bool valid = (int)b < p.n_img && (int)y < p.Ho && (int)x < p.Wo;
+      const int Y = y + o.dpad, X = x + o.dpad;
+      const long dpos = (long)b * o.dS + Y * o.dWp + X;
+      const bool store = valid && (o.mode == 2 || (Y < o.dHc && X < o.dWp));
+      uint4 mk[NB][4];
+      if (store) {
+        const long apos = (long)b * p.S + pl_ + o.act_off;
+#pragma unroll
+        for (int c = 0; c < NB; ++c) pc_load_mask32(o, h * HC + c * 32, apos, mk[c]);
+      }
+      mbar_wait(tfull_bar(acc), aph, 45);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ND + h * HC;
+      uint32_t r[NB][32];
+#pragma unroll
+      for (int c = 0; c < NB; ++c) tmem_ld32(taddr + c * 32, r[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (store) {
+#pragma unroll
+        for (int c = 0; c < NB; ++c) {
+          uint32_t packed[16];
+          pc_finish<32>(r[c], nullptr, 1.f, false, mk[c], packed);
+          if (o.mode == 2) pc_store_unfold(o, packed, (int)b, (int)y, (int)x, (h * HC + c * 32) >> 5);
+          else pc_store<32>(o, packed, dpos, h * HC + c * 32);
+        }
+      }
+    }
+  } else if (warp >= 10) {
+    // ===================== column sums of dY (bias gradient), warps 10..13 =====================
+    const int t4 = tid - 320;                      // 0..127
+    const int c = t4 & 7, r0 = t4 >> 3;            // 16-byte chunk, first row; rows r0 + 16*i
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int s = it % p.stages;
+      const uint32_t ph = (it / p.stages) & 1;
+      mbar_wait(full_bar(s), ph, 46);
+      const uint32_t b_stage = st_base + s * stage_bytes;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = g.dy_off + r0 + i * 16;      // patch row of dY[q0 + r0 + 16 i]
+        uint4 v;
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "r"(b_stage + swz_off<128>(r, c)));
+        csum[0] += bf16_lo(v.x); csum[1] += bf16_hi(v.x); csum[2] += bf16_lo(v.y); csum[3] += bf16_hi(v.y);
+        csum[4] += bf16_lo(v.z); csum[5] += bf16_hi(v.z); csum[6] += bf16_lo(v.w); csum[7] += bf16_hi(v.w);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar(s));
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[t4 * 8 + e] = csum[e];
+  }
+  __syncthreads();
+  // bias partial: fixed-order sum of the 16 row groups per column
+  if (tid < NC && g.bias_partial) {
+    const int c = tid >> 3, e = tid & 7;
+    float t = 0.f;
+    for (int gq = 0; gq < 16; ++gq) t += red[(gq * 8 + c) * 8 + e];
+    g.bias_partial[(long)blockIdx.x * NC + tid] = t;
+  }
+  // ===================== weight-gradient epilogue: TMEM -> this CTA's fp32 partial =====================
+  if (warp >= 2 && warp < 10) {
+    const int q = warp & 3, h = (warp - 2) >> 2;
+    mbar_wait(done_bar, 0, 47);
+    tc_fence_after();
+    const int r = q * 32 + lane;
+    const int a = r >> 6, ch = r & 63;
+    for (int m = 0; m < g.n_mma; ++m) {
+      const int ty = g.ty0[m] + a * g.ty_step[m], pl = a * g.pl_step[m];
+      for (int c0 = h * (NW / 2); c0 < (h + 1) * (NW / 2); c0 += 32) {
+        const int j = c0 / NC, co0 = c0 - j * NC, tx = g.T - 1 - j;
+        const int blk = (ty * g.T + tx) * g.planes + pl;
+        const bool ok = ty < g.T;
+        float* dst = g.partial + ((long)blockIdx.x * g.nblk * 64 + (long)(ok ? blk : 0) * 64 + ch) * NC + co0;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + wg_col0 + m * NW + c0, v);
+        tmem_ld_wait();
+        store_rows32_coalesced(st_base + (uint32_t)(warp - 2) * kRowStoreScratch, v, dst, ok, lane);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace arl

@@ -309,6 +309,8 @@ def kernel_flops(label, n, args):
     for k in ("conv0", "conv1", "conv2"):
         if base.startswith(k + "_") and base.split("_")[1] in ("fwd", "wgrad", "dgrad"):
             return 2.0 * macs[k] * n
+        if base == k + "_bwd":                       # data + weight gradient in one kernel (pconv_bwd_kernel)
+            return 4.0 * macs[k] * n
     if base in ("fc_fwd", "fc_wgrad", "fc_dgrad"):
         return 2.0 * macs["fc"] * n
     return None
