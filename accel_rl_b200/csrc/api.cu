@@ -598,6 +598,7 @@ int alloc_pconv(arl_ctx* c, std::vector<PackJob>& pj) {
 template <int N>
 int launch_pconv(arl_ctx* c, const PcParams& p, cudaStream_t st) {
   const int smem = pc_fwd_smem(N, p.ntaps, p.planes, p.load_rows, p.stages);
+  if (smem > 227 * 1024) ARL_FAIL(c, "pconv forward: stages do not fit shared memory");
   static int attr_smem = 0;
   if (smem > attr_smem) {
     ARL_CHECK(c, cudaFuncSetAttribute(pconv_fwd_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -641,9 +642,32 @@ void pc_out_forward(arl_ctx* c, int l, PcOut& o) {
   }
 }
 
+// The first conv layer can take its input straight from uint8 observations (pconv.cuh PcU8Src: converter warps build the
+// bf16 space-to-depth patch in shared memory): four input planes, rows of whole 16-byte groups, space-to-depth(4).
+// OFF by default (ARL_U8_CONV0=1 enables; all 93 GPU tests pass with it, the bf16 mirrors of the step buffer and of the
+// rollout — 2.18 GB — are then never allocated and the frame kernel writes 66 KB instead of 200 KB per env-step): measured
+// 56.8 vs 51.8 ms per iteration.  The rollout gets faster (8.1 -> 7.0 ms: the frame kernel) but conv0 forward / weight
+// gradient go from 12.4 / 11.9 to 24.5 / 21.6 us: these SS-mode tiles are bound by the shared-memory operand fetch of
+// tcgen05.mma (65 cycles per instruction for 16 of math), and 19.5 KB of generic-proxy patch stores per tile + the
+// proxy fences in front of the MMAs cost more there than the HBM bytes they save (profiles/r2_u8_conv0.md; staging the
+// uint8 rows with bulk copies first was no better: 27.0 / 24.9 us).
+bool u8_conv0_ok(arl_ctx* c) {
+  static const bool on = getenv("ARL_U8_CONV0") && atoi(getenv("ARL_U8_CONV0")) != 0;
+  return on && c->pc_mode >= 1 && !c->pc.empty() && c->pc[0].P == 1 && c->cfg.in_c == kU8Planes && c->conv[0].s == 4 &&
+         (c->cfg.in_w % 16 == 0) && (c->cfg.in_h % 4 == 0);
+}
+
+PcU8Src u8_source(arl_ctx* c, const uint8_t* obs8, int patch_rows) {
+  PcU8Src u{};
+  u.obs = obs8; u.H = c->cfg.in_h; u.W = c->cfg.in_w; u.Wc = u.W / 4; u.Hc = u.H / 4;
+  u.rows_max = 4 * ((u.Wc - 1 + patch_rows - 1) / u.Wc + 1);
+  u.img_bytes = (long)c->cfg.in_c * u.H * u.W;
+  return u;
+}
+
 // conv layer l forward on the patch-resident path
 int pconv_forward_layer(arl_ctx* c, int l, const __nv_bfloat16* obs16, const int* idx, const int* idx_off, int n,
-                        cudaStream_t st) {
+                        cudaStream_t st, const uint8_t* obs8 = nullptr) {
   const PcLayer& q = c->pc[l];
   const ConvLayer& L = c->conv[l];
   PcParams p{};
@@ -661,6 +685,7 @@ int pconv_forward_layer(arl_ctx* c, int l, const __nv_bfloat16* obs16, const int
   p.magic_S = pc_magic(p.S); p.magic_Wp = pc_magic(p.Wp); p.magic_tpi = pc_magic(p.tiles_per_img);
   pc_out_forward(c, l, p.out);
   p.out.ds_shift = (p.out.ds == 2) ? 1 : (p.out.ds == 4) ? 2 : 0; p.out.us = 1;
+  if (l == 0 && obs8) p.u8 = u8_source(c, obs8, p.load_rows);
   return launch_pconv_n(c, q.N, p, st);
 }
 
@@ -690,7 +715,7 @@ int pc_wgrad_ctas(arl_ctx* c, int l, int n) {
 
 // weight (+ bias) gradient partials of conv layer l on the patch-resident path
 int pconv_wgrad_params(arl_ctx* c, int l, const __nv_bfloat16* obs16, const int* idx, const int* idx_off, int n,
-                       PcWgradParams& p) {
+                       PcWgradParams& p, const uint8_t* obs8 = nullptr) {
   const PcLayer& q = c->pc[l];
   p = PcWgradParams{};
   if (l == 0) {
@@ -729,6 +754,7 @@ int pconv_wgrad_params(arl_ctx* c, int l, const __nv_bfloat16* obs16, const int*
     if (max_row >= p.a_rows) p.wide = 0;
   }
   p.partial = c->wgrad_partial[l]; p.bias_partial = c->bias_partial[l];
+  if (l == 0 && obs8) p.u8 = u8_source(c, obs8, p.a_rows);
   for (p.stages = 4; p.stages >= 2; --p.stages)
     if (pc_wgrad_smem(q.N, q.P, p.a_rows, p.dy_rows, p.stages) <= 227 * 1024) break;
   if (p.stages < 2) ARL_FAIL(c, "pconv wgrad: stage does not fit shared memory");
@@ -736,10 +762,10 @@ int pconv_wgrad_params(arl_ctx* c, int l, const __nv_bfloat16* obs16, const int*
 }
 
 int pconv_wgrad_layer(arl_ctx* c, int l, const __nv_bfloat16* obs16, const int* idx, const int* idx_off, int n,
-                      cudaStream_t st) {
+                      cudaStream_t st, const uint8_t* obs8 = nullptr) {
   const PcLayer& q = c->pc[l];
   PcWgradParams p;
-  if (pconv_wgrad_params(c, l, obs16, idx, idx_off, n, p)) return 2;
+  if (pconv_wgrad_params(c, l, obs16, idx, idx_off, n, p, obs8)) return 2;
   int ctas = pc_wgrad_ctas(c, l, n);
   if (q.N == 32) return launch_pconv_wgrad<32>(c, p, ctas, st);
   if (q.N == 64) return launch_pconv_wgrad<64>(c, p, ctas, st);
@@ -1107,13 +1133,13 @@ int convert_obs(arl_ctx* c, const uint8_t* obs, const int* idx, int n, bool swz,
 // conv stack + FC split-K partials for n observations given as bf16 space-to-depth images
 // (idx/idx_off: optional image gather applied by the first layer's loader)
 int forward_trunk(arl_ctx* c, const __nv_bfloat16* obs16, const int* idx, const int* idx_off, int n, int* fc_S,
-                  bool pc, cudaStream_t st) {
+                  bool pc, cudaStream_t st, const uint8_t* obs8 = nullptr) {
   if (n > c->cfg.max_rows) ARL_FAIL(c, "batch larger than max_rows");
   if (!c->params) ARL_FAIL(c, "parameters not bound");
   for (size_t l = 0; l < c->conv.size(); ++l) {
     if (pc) {
       // patch-resident tiles: obs16 and every intermediate activation are chunk-swizzled position grids
-      if (pconv_forward_layer(c, (int)l, obs16, idx, idx_off, n, st)) return 1;
+      if (pconv_forward_layer(c, (int)l, obs16, idx, idx_off, n, st, obs8)) return 1;
       prof_mark(c, kFwdName[l], st);
       continue;
     }
@@ -1172,9 +1198,10 @@ cudaError_t launch_head(const HeadParams& p, int n, cudaStream_t st) {
 }
 
 int policy_forward16(arl_ctx* c, const __nv_bfloat16* obs16, int n, const int* out_rows, float* prob, float* value,
-                     const double* uniforms, uint8_t* actions, bool pc, cudaStream_t st, const EnvStepArgs* es = nullptr) {
+                     const double* uniforms, uint8_t* actions, bool pc, cudaStream_t st, const EnvStepArgs* es = nullptr,
+                     const uint8_t* obs8 = nullptr, const int* idx = nullptr) {
   int S = 0;
-  if (forward_trunk(c, obs16, nullptr, nullptr, n, &S, pc, st)) return 1;
+  if (forward_trunk(c, obs16, idx, nullptr, n, &S, pc, st, obs8)) return 1;
   HeadParams p = head_base(c, n, S);
   if (es) { p.es = *es; p.es_on = 1; }
   p.out_rows = out_rows; p.prob = prob; p.value = value; p.uniforms = uniforms; p.actions = uniforms ? actions : nullptr;
@@ -1188,6 +1215,8 @@ int policy_forward16(arl_ctx* c, const __nv_bfloat16* obs16, int n, const int* o
 int policy_forward(arl_ctx* c, const uint8_t* obs, const int* idx, int n, const int* out_rows, float* prob,
                    float* value, const double* uniforms, uint8_t* actions, cudaStream_t st) {
   if (n > c->cfg.max_rows) ARL_FAIL(c, "batch larger than max_rows");
+  if (u8_conv0_ok(c))       // the first conv layer reads the uint8 rows itself (gathered through idx)
+    return policy_forward16(c, nullptr, n, out_rows, prob, value, uniforms, actions, true, st, nullptr, obs, idx);
   if (convert_obs(c, obs, idx, n, c->pc_mode >= 1, st)) return 1;
   return policy_forward16(c, c->obs16_stage, n, out_rows, prob, value, uniforms, actions, c->pc_mode >= 1, st);
 }
@@ -1282,8 +1311,12 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
   // first-layer input: the sampler's bf16 mirror of the rollout (gathered by the loader), or a conversion
   // of the caller's uint8 rows into the staging buffer
   const __nv_bfloat16* obs16;
+  const uint8_t* obs8 = nullptr;
   const int *gidx, *gidx_off;
-  if (c->sampler_set && c->t_obs == c->sc.observations && c->roll_obs16) {
+  if (c->pc_mode >= 2 && u8_conv0_ok(c)) {
+    // the first conv layer (forward and weight gradient) gathers the uint8 training rows itself
+    obs16 = nullptr; obs8 = c->t_obs; gidx = idx; gidx_off = idx_off;
+  } else if (c->sampler_set && c->t_obs == c->sc.observations && c->roll_obs16) {
     obs16 = c->roll_obs16; gidx = idx; gidx_off = idx_off;
   } else {
     if (idx_off) ARL_FAIL(c, "graph-replayed training needs the sampler's rollout buffers as training inputs");
@@ -1293,7 +1326,7 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
   const bool pcb = c->pc_mode >= 2;
   if (pcb && pconv_prepare_dy(c, n, st)) return 1;
   int S = 0;
-  if (forward_trunk(c, obs16, gidx, gidx_off, n, &S, pcb, st)) return 1;
+  if (forward_trunk(c, obs16, gidx, gidx_off, n, &S, pcb, st, obs8)) return 1;
   // ---- head: losses + dlogits + dh ----
   if (c->t_valids) {
     ARL_CHECK(c, launch_k(count_valids_idx_kernel, dim3(1), dim3(1024), 0, st, c->t_valids, idx, idx_off, n, c->valid_count));
@@ -1416,7 +1449,7 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
       ARL_CHECK(c, cudaEventRecord(ev, st));
       ARL_CHECK(c, cudaStreamWaitEvent(wl, ev, 0));
     }
-    if (pconv_wgrad_layer(c, l, obs16, gidx, gidx_off, n, wl)) return 1;
+    if (pconv_wgrad_layer(c, l, obs16, gidx, gidx_off, n, wl, obs8)) return 1;
     prof_mark(c, kWgradName[l], wl);
     if (l == 0) break;
     if (P->early_jobs) {
@@ -1691,12 +1724,15 @@ int rollout_begin(arl_ctx* c, cudaStream_t st) {
   if (s.observations) {
     copy_rows_kernel<<<(int)((chunks + 255) / 256), 256, 0, st>>>(s.step_obs, row_bytes, nullptr, s.observations, row_bytes,
                                                                  c->rows_tab, s.n_envs, row_bytes);
-    int row16 = (int)(c->obs16_elems * 2);
-    long chunks16 = (long)s.n_envs * (row16 / 16);
-    copy_rows_kernel<<<(int)((chunks16 + 255) / 256), 256, 0, st>>>(
-        reinterpret_cast<const uint8_t*>(c->step_obs16), row16, nullptr, reinterpret_cast<uint8_t*>(c->roll_obs16), row16,
-        c->rows_tab, s.n_envs, row16);
-    c->launches += 2;
+    c->launches += 1;
+    if (c->roll_obs16) {
+      int row16 = (int)(c->obs16_elems * 2);
+      long chunks16 = (long)s.n_envs * (row16 / 16);
+      copy_rows_kernel<<<(int)((chunks16 + 255) / 256), 256, 0, st>>>(
+          reinterpret_cast<const uint8_t*>(c->step_obs16), row16, nullptr, reinterpret_cast<uint8_t*>(c->roll_obs16), row16,
+          c->rows_tab, s.n_envs, row16);
+      c->launches += 1;
+    }
   }
   ARL_CHECK(c, cudaMemsetAsync(c->tout.count, 0, sizeof(int), st));
   ARL_CHECK(c, cudaGetLastError());
@@ -1709,8 +1745,9 @@ int rollout_step(arl_ctx* c, int s_idx, const uint8_t* staging, cudaStream_t st)
   // the env step of env e runs in the head kernel's block e right after its action is sampled
   EnvStepArgs es{synth_cfg(s), c->est, c->tout, c->cmd, s.rewards, s.dones, s.raw_reward, s.need_reset, B, T, s_idx,
                  s.max_path_length, s.discount, s.mid_batch_reset, s.clip_reward, s.episodic_lives, nullptr, 0};
+  const bool u8 = c->pc_mode >= 2 && u8_conv0_ok(c);
   if (policy_forward16(c, c->step_obs16, B, c->rows_tab + (long)s_idx * B, s.prob, s.value,
-                       s.uniforms + (long)s_idx * B, s.actions, c->pc_mode >= 2, st, &es))
+                       s.uniforms + (long)s_idx * B, s.actions, c->pc_mode >= 2, st, &es, u8 ? s.step_obs : nullptr))
     return 1;
   return launch_frame(c, staging, s_idx + 1, s_idx + 1 < T, st);
 }
@@ -1947,10 +1984,13 @@ int arl_sampler_configure(arl_ctx* c, const arl_sampler_cfg* cfg) {
     for (int e = 0; e < B; ++e) rt[(size_t)s * B + e] = e * T + s;
   ARL_CHECK(c, cudaMemcpy(c->rows_tab, rt.data(), rt.size() * sizeof(int), cudaMemcpyHostToDevice));
   // bf16 space-to-depth mirrors of the step buffer and of the rollout observations (what conv layer 0 reads)
-  if (dev_alloc(c, &c->step_obs16, (size_t)B * c->obs16_elems + 64 * 1024)) return 1;
+  // (none when the first conv layer reads the uint8 stacks itself: u8_conv0_ok)
+  const bool mirrors = !(c->pc_mode >= 2 && u8_conv0_ok(c) && cfg->frame_mode == 0);
+  c->step_obs16 = nullptr;
+  if (mirrors && dev_alloc(c, &c->step_obs16, (size_t)B * c->obs16_elems + 64 * 1024)) return 1;
   // a sampler without an observations buffer (evaluation: nothing is stored, sampler_with_eval.py:36-38) has no mirror
   c->roll_obs16 = nullptr;
-  if (cfg->observations && dev_alloc(c, &c->roll_obs16, (size_t)B * T * c->obs16_elems + 64 * 1024)) return 1;
+  if (mirrors && cfg->observations && dev_alloc(c, &c->roll_obs16, (size_t)B * T * c->obs16_elems + 64 * 1024)) return 1;
   c->sampler_set = true;
   if (c->rollout_graph) { cudaGraphExecDestroy(c->rollout_graph); c->rollout_graph = nullptr; }
   return 0;
@@ -2019,9 +2059,11 @@ int arl_rollout_serve(arl_ctx* c, int s, int e0, int n, void* stream) {
   if (s < 0 || s >= sc.horizon) ARL_FAIL(c, "serve step out of range");
   if (n < 0) n = sc.n_envs - e0;
   if (e0 < 0 || n < 1 || e0 + n > sc.n_envs) ARL_FAIL(c, "serve env range out of bounds");
-  return policy_forward16(c, c->step_obs16 + (long)e0 * c->obs16_elems, n, c->rows_tab + (long)s * sc.n_envs + e0, sc.prob,
-                          sc.value, sc.uniforms + (long)s * sc.n_envs + e0, sc.actions, c->pc_mode >= 2,
-                          (cudaStream_t)stream, nullptr);
+  const bool u8 = c->pc_mode >= 2 && u8_conv0_ok(c);
+  const long obs_bytes = (long)sc.planes * c->cfg.in_h * c->cfg.in_w;
+  return policy_forward16(c, u8 ? nullptr : c->step_obs16 + (long)e0 * c->obs16_elems, n, c->rows_tab + (long)s * sc.n_envs + e0,
+                          sc.prob, sc.value, sc.uniforms + (long)s * sc.n_envs + e0, sc.actions, c->pc_mode >= 2,
+                          (cudaStream_t)stream, nullptr, u8 ? sc.step_obs + (long)e0 * obs_bytes : nullptr);
 }
 
 int arl_rollout_ingest(arl_ctx* c, int s, int e0, int n, const uint8_t* staging, const arl_ext_step* ext, void* stream) {
@@ -2188,7 +2230,9 @@ int train_minibatches(arl_ctx* c, const int* idx, int mb_size, int count, int sy
       c->pending_ss_fin = c->pending_ss_fc = 0;
     }
   } active(c, sync == 0, overlap);
-  if (!(c->sampler_set && c->t_obs == c->sc.observations && c->roll_obs16) || (sync && c->sync_graph_failed)) {
+  const bool graphable = (c->pc_mode >= 2 && u8_conv0_ok(c) && c->t_obs) ||
+                         (c->sampler_set && c->t_obs == c->sc.observations && c->roll_obs16);
+  if (!graphable || (sync && c->sync_graph_failed)) {
     // training inputs that are not the sampler's rollout buffers: plain launches, one minibatch at a time
     const bool replay_idx = c->sampler_set && c->t_obs == c->sc.observations && c->roll_obs16;
     (void)replay_idx;

@@ -27,9 +27,158 @@
 
 namespace arl {
 
-constexpr int kPcThreads = 320;
-constexpr int kPcFwdThreads = 352;   // forward/dgrad kernel: + a second MMA-issuing warp (warp 10)
+constexpr int kPcThreads = 448;      // weight-gradient kernel: 10 warps + 4 converter warps (u8 first-layer input)
+constexpr int kPcFwdThreads = 480;   // forward/dgrad kernel: + a second MMA-issuing warp (warp 10) + 4 converter warps (11..14)
 constexpr int kPcMaxTaps = 16;
+
+// First-layer input taken straight from the uint8 observations (the reference's own buffer layout, [img][C=4][H][W]):
+// four converter warps load the image rows a tile touches with 16-byte global loads (two tiles ahead, in registers),
+// expand them to the bf16 space-to-depth(4) patch and store it in the SWIZZLE_128B layout the MMAs read (cell (Y, X),
+// channel = plane*16 + (y%4)*4 + x%4 — byte for byte what the frame kernel's bf16 mirror used to hold; u8 -> bf16 is
+// exact).  No bf16 copy of the rollout exists any more: 2.18 GB of HBM and half of this layer's training reads are gone,
+// and the frame kernel writes 66 KB per env-step instead of 200 KB.  (A first version staged the uint8 rows in shared
+// memory with bulk copies: correct, but these tiles are bound by the shared-memory operand fetch of SS-mode MMAs, and the
+// extra 23 KB of shared-memory traffic per tile doubled the kernel time — profiles/r2_u8_conv0.md.)
+struct PcU8Src {
+  const uint8_t* obs;     // nullptr: the patch comes from a bf16 grid (bulk copy), as for every other layer
+  int H, W, Wc, Hc;       // image rows / columns, cells per row (W/4), cell rows (H/4)
+  int rows_max;           // image rows per plane a tile can touch (multiple of 4)
+  long img_bytes;         // C*H*W
+};
+constexpr int kU8Planes = 4;
+
+// 4 packed u8 -> 4 bf16 (exact): byte b -> float(2^23 + b) - 2^23
+ARL_DEVINL uint2 pc_u8x4_to_bf16x4(uint32_t w) {
+  float f0 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650)) - 8388608.0f;
+  float f1 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7651)) - 8388608.0f;
+  float f2 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7652)) - 8388608.0f;
+  float f3 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7653)) - 8388608.0f;
+  return make_uint2(pack_bf16x2(f0, f1), pack_bf16x2(f2, f3));
+}
+
+// One item = (cell row Yr, plane, pair of image rows 2j / 2j+1, 16-byte column group g): two 16-byte loads -> four
+// 16-byte chunks of the patch (cells 4g .. 4g+3).  A converter thread (tid_c = 0..127) owns items tid_c + 128 k, k < 3
+// (at most 9 cell rows x 4 planes x 2 x G <= 384 items); their decomposition is tile-independent and computed once.
+struct PcU8Items {
+  int goff[3];       // byte offset of the item's first row relative to image row 4*Y0 of plane 0: (pl*H + 4*Yr + 2*j)*W + 16*g
+  int cell[3];       // Yr*Wc + 4*g: cell index relative to cell row Y0's first cell
+  int chunk[3];      // 2*pl + j
+  int yr[3];         // Yr (16: no such item)
+};
+struct PcU8Regs { uint4 r0[3], r1[3]; };
+
+ARL_DEVINL PcU8Items pc_u8_items(const PcU8Src& u, int tid_c) {
+  PcU8Items it;
+  const int G = u.W >> 4;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int item = tid_c + 128 * k;
+    const int g = item % G;
+    int t = item / G;
+    const int j = t & 1; t >>= 1;
+    const int pl = t & 3;
+    const int Yr = t >> 2;
+    it.goff[k] = (pl * u.H + 4 * Yr + 2 * j) * u.W + 16 * g;
+    it.cell[k] = Yr * u.Wc + 4 * g;
+    it.chunk[k] = 2 * pl + j;
+    it.yr[k] = (4 * Yr + 4 <= u.rows_max) ? Yr : 16;
+  }
+  return it;
+}
+
+// image rows of cells [c0, c0 + patch_rows) of image `img` -> registers (cells past the end of the image: zeros)
+ARL_DEVINL void pc_u8_load(const PcU8Src& u, const PcU8Items& it, long img, int c0, int patch_rows, PcU8Regs& R) {
+  const int Y0 = c0 / u.Wc;
+  const int n_yr = (c0 - Y0 * u.Wc + patch_rows - 1) / u.Wc + 1;
+  const uint8_t* base = u.obs + img * u.img_bytes + (long)(4 * Y0) * u.W;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    R.r0[k] = make_uint4(0u, 0u, 0u, 0u);
+    R.r1[k] = R.r0[k];
+    if (it.yr[k] < n_yr && Y0 + it.yr[k] < u.Hc) {
+      R.r0[k] = __ldg(reinterpret_cast<const uint4*>(base + it.goff[k]));
+      R.r1[k] = __ldg(reinterpret_cast<const uint4*>(base + it.goff[k] + u.W));
+    }
+  }
+}
+
+// registers -> bf16 patch rows [0, patch_rows) of `stage` (1024-aligned; c0 % 8 == 0, so the chunk swizzle by (row & 7)
+// equals the swizzle by (cell & 7))
+ARL_DEVINL void pc_u8_store(const PcU8Src& u, const PcU8Items& it, int c0, int patch_rows, const PcU8Regs& R, uint32_t stage) {
+  const int Y0 = c0 / u.Wc;
+  const int n_yr = (c0 - Y0 * u.Wc + patch_rows - 1) / u.Wc + 1;
+  const int base = Y0 * u.Wc - c0;                         // patch row of cell row Y0's first cell (<= 0)
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (it.yr[k] >= n_yr) continue;
+    const uint32_t w0[4] = {R.r0[k].x, R.r0[k].y, R.r0[k].z, R.r0[k].w}, w1[4] = {R.r1[k].x, R.r1[k].y, R.r1[k].z, R.r1[k].w};
+    const int rb = base + it.cell[k];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int r = rb + b;
+      if (r >= 0 && r < patch_rows) {
+        const uint2 lo = pc_u8x4_to_bf16x4(w0[b]), hi = pc_u8x4_to_bf16x4(w1[b]);
+        st_shared_v4(stage + swz_off<128>((uint32_t)r, (uint32_t)it.chunk[k]), make_uint4(lo.x, lo.y, hi.x, hi.y));
+      }
+    }
+  }
+}
+
+// The converter warps' tile loop, shared by the forward and the weight-gradient kernel: tile `it` of this CTA goes to
+// patch slot it % stages once `empty(s)` says the MMAs that read the slot have completed; the loads of tiles it+1 and it+2
+// are already in flight (two register sets, loop unrolled by two).  Image of a tile: idx[idx_base + tile / tiles_per_img]
+// (lane l looks up the image of the CTA's l-th tile, one round of latency per 32 tiles, as the TMA producer does).
+template <class FullBar, class EmptyBar>
+ARL_DEVINL void pc_u8_converter_loop(const PcU8Src& u, const int* idx, long idx_base, int tiles_per_img, int ntiles,
+                                     int patch_rows, int stages, uint32_t stage0, uint32_t stage_bytes, FullBar full_bar,
+                                     EmptyBar empty_bar, int tid_c, int lane, int code) {
+  const PcU8Items items = pc_u8_items(u, tid_c);
+  const int grid = (int)gridDim.x;
+  int img_l = 0;
+  auto image_of = [&](int it_, int tile_) -> long {
+    (void)tile_;
+    return __shfl_sync(0xffffffffu, img_l, it_ & 31);
+  };
+  auto refresh = [&](int it_, int tile_) {
+    if ((it_ & 31) == 0) {
+      const int tl = tile_ + lane * grid;
+      const int bl = min(tl, ntiles - 1) / tiles_per_img;
+      img_l = idx ? idx[idx_base + bl] : bl;
+    }
+  };
+  auto c0_of = [&](int tile_) { return (tile_ - (tile_ / tiles_per_img) * tiles_per_img) * 128; };
+  PcU8Regs A, B;
+  int tile = blockIdx.x;
+  // (tiles it and it+1 never straddle a refresh boundary in a way that matters: img_l holds 32 consecutive tiles)
+  refresh(0, tile);
+  if (tile < ntiles) pc_u8_load(u, items, image_of(0, tile), c0_of(tile), patch_rows, A);
+  if (tile + grid < ntiles) pc_u8_load(u, items, image_of(1, tile + grid), c0_of(tile + grid), patch_rows, B);
+  for (int it = 0; tile < ntiles; it += 2, tile += 2 * grid) {
+    {
+      const int s = it % stages;
+      mbar_wait(empty_bar(s), ((it / stages) & 1) ^ 1, code);
+      pc_u8_store(u, items, c0_of(tile), patch_rows, A, stage0 + s * stage_bytes);
+      fence_proxy_async();                             // generic-proxy stores -> visible to tcgen05.mma
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar(s));
+      const int t2 = tile + 2 * grid;
+      refresh(it + 2, t2);                             // (it + 2) % 32 == 0 only for even it: handled here
+      if (t2 < ntiles) pc_u8_load(u, items, image_of(it + 2, t2), c0_of(t2), patch_rows, A);
+    }
+    const int tile1 = tile + grid;
+    if (tile1 >= ntiles) break;
+    {
+      const int s = (it + 1) % stages;
+      mbar_wait(empty_bar(s), (((it + 1) / stages) & 1) ^ 1, code);
+      pc_u8_store(u, items, c0_of(tile1), patch_rows, B, stage0 + s * stage_bytes);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar(s));
+      const int t3 = tile1 + 2 * grid;
+      if (t3 < ntiles) pc_u8_load(u, items, image_of(it + 3, t3), c0_of(t3), patch_rows, B);
+    }
+  }
+}
 
 struct PcOut {
   int mode;                   // 0: acc*scale + bias, ReLU -> bf16   1: acc masked by act > 0 -> bf16   2: mask + unfold
@@ -67,11 +216,12 @@ struct PcParams {
   int load_rows;              // 128 + halo, multiple of 8
   const __nv_bfloat16* w;     // [ntaps*planes][N][64] bf16, rows chunk-swizzled (pack_weights_kernel PK_PCONV*)
   int stages;
+  PcU8Src u8;                 // first layer: uint8 observations instead of `src` (per-image tiling only)
   PcOut out;
 };
 
-__host__ __device__ inline int pc_fwd_smem(int N, int ntaps, int planes, int load_rows, int stages) {
-  return ntaps * planes * N * 128 + stages * planes * load_rows * 128 + 1024 /*align*/ + 256 /*barriers*/ + N * 4;
+__host__ __device__ inline int pc_fwd_smem(int N, int ntaps, int planes, int load_rows, int stages, int raw_stage_bytes = 0) {
+  return ntaps * planes * N * 128 + stages * (planes * load_rows * 128 + raw_stage_bytes) + 1024 /*align*/ + 256 /*barriers*/ + N * 4;
 }
 
 // n / d for d >= 1 with magic = floor(2^32/d) + 1 (exact for n < 2^32 / d; every use here is < 2^24)
@@ -151,6 +301,7 @@ __global__ void __launch_bounds__(kPcFwdThreads, 1) pconv_fwd_kernel(const __gri
   const uint32_t w_base = smem_base;                                  // nblk tiles of [N x 128 B]
   const uint32_t stage_bytes = (uint32_t)p.planes * p.load_rows * 128;
   const uint32_t a_base = w_base + nblk * (N * 128);
+  const bool u8 = p.u8.obs != nullptr;
   const uint32_t bar_base = a_base + p.stages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };
@@ -165,7 +316,7 @@ __global__ void __launch_bounds__(kPcFwdThreads, 1) pconv_fwd_kernel(const __gri
   const int lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), u8 ? 4 : 1);      // u8 mode: the four converter warps fill the patch
       mbar_init(empty_bar(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -216,6 +367,7 @@ __global__ void __launch_bounds__(kPcFwdThreads, 1) pconv_fwd_kernel(const __gri
       } else {
         pos0 = (long)tile * 128;
       }
+      if (u8) break;                           // the converter warps build the patches: nothing to copy
       mbar_wait(empty_bar(s), ph ^ 1, 21);
       if (lane == 0) ARL_TP(it * 6 + 0);
       if (elect_one()) {
@@ -272,6 +424,13 @@ __global__ void __launch_bounds__(kPcFwdThreads, 1) pconv_fwd_kernel(const __gri
       }
       __syncwarp();
       if (lane == 0) ARL_TP(it * 6 + 3);
+    }
+  } else if (warp >= 11) {
+    // ===================== converter warps (u8 first-layer input) =====================
+    if (u8) {
+      const long idx_base = (p.idx && p.idx_off) ? (long)p.idx_off[0] * p.nb : 0;
+      pc_u8_converter_loop(p.u8, p.idx, idx_base, p.tiles_per_img, p.ntiles, p.load_rows, p.stages, a_base, stage_bytes,
+                           full_bar, empty_bar, tid - 11 * 32, lane, 28);
     }
   } else if (warp >= 2 && warp < 10) {
     // ===================== epilogue warps =====================
@@ -390,13 +549,14 @@ struct PcWgradParams {
   int ty0[2], ty_step[2];      // tap row of A atom a of MMA i: ty0[i] + a*ty_step[i] (>= T: padding, dropped)
   int pl_step[2];              // plane of A atom a of MMA i: a*pl_step[i]
   int dy_bias_sub;             // stage row of dY[q0] (bias column sums); dy_sub = stage row of dY[q0 - (T-1)]
+  PcU8Src u8;                  // layer 0: A patches built from the uint8 observations (see pconv_fwd_kernel)
 };
 
 __host__ __device__ inline int pc_wgrad_stage_bytes(int N, int planes, int a_rows, int dy_rows) {
   return planes * a_rows * 128 + ((dy_rows * N * 2 + 1023) / 1024) * 1024;
 }
-__host__ __device__ inline int pc_wgrad_smem(int N, int planes, int a_rows, int dy_rows, int stages) {
-  return stages * pc_wgrad_stage_bytes(N, planes, a_rows, dy_rows) + 1024 + 256 + 128 * 8 * 4;
+__host__ __device__ inline int pc_wgrad_smem(int N, int planes, int a_rows, int dy_rows, int stages, int raw_stage_bytes = 0) {
+  return stages * (pc_wgrad_stage_bytes(N, planes, a_rows, dy_rows) + raw_stage_bytes) + 1024 + 256 + 128 * 8 * 4;
 }
 
 template <int N>
@@ -408,6 +568,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) pconv_wgrad_kernel(const __grid
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_bytes = (uint32_t)p.planes * p.a_rows * 128;
   const uint32_t stage_bytes = (uint32_t)pc_wgrad_stage_bytes(N, p.planes, p.a_rows, p.dy_rows);
+  const bool u8 = p.u8.obs != nullptr;
   const uint32_t bar_base = smem_base + p.stages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };
@@ -423,7 +584,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) pconv_wgrad_kernel(const __grid
   const int my_tiles = ((int)blockIdx.x < p.ntiles) ? (p.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), u8 ? 1 + 4 : 1);    // producer (dY bytes) + u8 mode: the four converter warps (A patch)
       mbar_init(empty_bar(s), 1 + 4);        // MMA commit + the four column-sum warps
     }
     mbar_init(done_bar, 1);
@@ -469,6 +630,15 @@ __global__ void __launch_bounds__(kPcThreads, 1) pconv_wgrad_kernel(const __grid
       }
       dpos += (dy_first & ~7);              // (dy_first may be -1 for layer 0: the grid has a zero prefix of 8 rows)
       mbar_wait(empty_bar(s), ph ^ 1, 31);
+      if (u8) {
+        // A patch: built by the converter warps; dY: bulk copy as before
+        if (elect_one()) {
+          mbar_arrive_expect_tx(full_bar(s), (uint32_t)p.dy_rows * ROWB);
+          bulk_g2s(smem_base + s * stage_bytes + a_bytes, p.dy + dpos * N, p.dy_rows * ROWB, full_bar(s));
+        }
+        __syncwarp();
+        continue;
+      }
       if (elect_one()) {
         mbar_arrive_expect_tx(full_bar(s), a_bytes + (uint32_t)p.dy_rows * ROWB);
         const uint32_t dst = smem_base + s * stage_bytes;
@@ -557,6 +727,12 @@ __global__ void __launch_bounds__(kPcThreads, 1) pconv_wgrad_kernel(const __grid
 #pragma unroll
     for (int e = 0; e < 8; ++e) red[t4 * 8 + e] = csum[e];
   }
+  if (warp >= 10 && u8) {
+    // ===================== converter warps (u8 first-layer input), warps 10..13 =====================
+    const long idx_base = (p.idx && p.idx_off) ? (long)p.idx_off[0] * p.nb : 0;
+    pc_u8_converter_loop(p.u8, p.idx, idx_base, p.tiles_per_img, p.ntiles, p.a_rows, p.stages, smem_base, stage_bytes,
+                         full_bar, empty_bar, tid - 10 * 32, lane, 38);
+  }
   __syncthreads();
   // bias partial: fixed-order sum of the 128/CH row groups per column
   if (tid < N && p.bias_partial) {
@@ -567,7 +743,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) pconv_wgrad_kernel(const __grid
     p.bias_partial[(long)blockIdx.x * N + tid] = t;
   }
   // ===================== epilogue: TMEM -> fp32 partial =====================
-  if (warp >= 2) {
+  if (warp >= 2 && warp < 10) {
     const int q = warp & 3, h = (warp - 2) >> 2;
     constexpr int HC = N / 2;
     if (my_tiles > 0) {
