@@ -79,6 +79,7 @@ class SamplerCfg(C.Structure):
         ("frame_stride", C.c_int),
         ("traj_cap", C.c_int),
         ("ext_emulator", C.c_int),
+        ("n_games", C.c_int),
         ("frame_mode", C.c_int),
     ]
 
@@ -146,6 +147,7 @@ SIGNATURES = {
     "arl_async_read_central": (C.c_int, [_P, C.c_int, _P, C.c_long, _P]),
     "arl_debug_activation": (C.c_int, [_P, C.c_int, _P, C.c_long, C.POINTER(C.c_long), _P]),
     "arl_kernel_launches": (C.c_long, [_P]),
+    "arl_source_hash": (C.c_char_p, []),
     "arl_profile_begin": (C.c_int, [_P, _P]),
     "arl_profile_timeline": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_char_p, C.c_int, _P, C.c_int, _P, _P]),
     "arl_profile_graph": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_char_p, C.c_int, _P, C.c_int,
@@ -167,6 +169,31 @@ def build(verbose=False):
     if r.returncode != 0:
         raise RuntimeError("building libaccelrl_b200.so failed")
     return LIB_PATH
+
+
+_HASH_FILES = ["api.cu", "common.cuh", "gemm_tc.cuh", "pconv.cuh", "fcgemm.cuh", "kernels.cuh", "comm.cuh",
+               os.path.join("..", "..", "include", "accelrl_b200.h")]          # = $(SRC) $(HDR) of csrc/Makefile
+
+
+def source_hash():
+    """sha256 of the CUDA sources in the tree, computed the way csrc/Makefile does"""
+    import hashlib
+    h = hashlib.sha256()
+    for f in _HASH_FILES:
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def check_source_hash():
+    """raise if the loaded library was not built from the sources next to it"""
+    lib = load()
+    built = lib.arl_source_hash().decode()
+    here = source_hash()
+    if built != here:
+        raise RuntimeError("libaccelrl_b200.so was built from other sources (library %s..., tree %s...): rebuild with "
+                           "`python -c 'import __graft_entry__ as g; g.build()'`" % (built[:12], here[:12]))
+    return built
 
 
 def load():

@@ -9,6 +9,8 @@
 #include <map>
 #include <algorithm>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/accelrl_b200.h"
 #include "common.cuh"
 #include "gemm_tc.cuh"
@@ -22,6 +24,13 @@ using namespace arl;
 namespace {
 
 std::string g_create_error;
+
+// NVTX ranges on the phase boundaries of the path (serve / frame / fwd / sample / gae / grad /
+// allreduce+adam): host-side markers around the launches (and around graph capture / replay), visible in any NVTX consumer
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 #define ARL_CHECK(ctx, call)                                                                    \
   do {                                                                                          \
@@ -1134,6 +1143,7 @@ int convert_obs(arl_ctx* c, const uint8_t* obs, const int* idx, int n, bool swz,
 // (idx/idx_off: optional image gather applied by the first layer's loader)
 int forward_trunk(arl_ctx* c, const __nv_bfloat16* obs16, const int* idx, const int* idx_off, int n, int* fc_S,
                   bool pc, cudaStream_t st, const uint8_t* obs8 = nullptr) {
+  NvtxRange nvtx_("fwd");
   if (n > c->cfg.max_rows) ARL_FAIL(c, "batch larger than max_rows");
   if (!c->params) ARL_FAIL(c, "parameters not bound");
   for (size_t l = 0; l < c->conv.size(); ++l) {
@@ -1303,6 +1313,7 @@ int sync_fc_exchange(arl_ctx* c, cudaStream_t ws, cudaStream_t st);
 
 // forward + loss + backward for one minibatch -> flat grad
 int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaStream_t st) {
+  NvtxRange nvtx_("grad: fwd + loss + bwd");
   if (!c->opt_set) ARL_FAIL(c, "optimizer not configured");
   if (!c->t_obs) ARL_FAIL(c, "training inputs not bound");
   if (!c->grad) ARL_FAIL(c, "gradient vector not bound");
@@ -1600,6 +1611,7 @@ UpdateParams update_params(arl_ctx* c, float gscale, bool* fused_cast_out) {
 }
 
 int clip_update(arl_ctx* c, float gscale, cudaStream_t st) {
+  NvtxRange nvtx_("clip + update");
   if (!c->opt_set) ARL_FAIL(c, "optimizer not configured");
   if (!c->m || !c->v) ARL_FAIL(c, "optimizer state not bound");
   bool fused_cast = false, scattered = false;
@@ -1678,13 +1690,14 @@ int clip_update(arl_ctx* c, float gscale, cudaStream_t st) {
 SynthCfg synth_cfg(const arl_sampler_cfg& s) {
   SynthCfg k{};
   k.pool_frames = s.pool_frames; k.lives0 = s.lives0; k.life_base = s.life_base; k.life_mul = s.life_mul;
-  k.life_mod = s.life_mod; k.reward_mod = s.reward_mod; k.frame_stride = s.frame_stride;
+  k.life_mod = s.life_mod; k.reward_mod = s.reward_mod; k.frame_stride = s.frame_stride; k.n_games = s.n_games;
   return k;
 }
 
 // frame pipeline for envs [e0, e0 + n) (n < 0: all).  The kernels index everything by env, so a sub-range is the same
 // launch over base pointers advanced by e0 envs (staging is the base of the whole [B][2][frame] block).
 int launch_frame(arl_ctx* c, const uint8_t* staging, int s_next, bool to_rollout, cudaStream_t st, int e0 = 0, int n = -1) {
+  NvtxRange nvtx_("frame");
   const arl_sampler_cfg& s = c->sc;
   if (n < 0) n = s.n_envs - e0;
   const long T = s.horizon;
@@ -1740,6 +1753,7 @@ int rollout_begin(arl_ctx* c, cudaStream_t st) {
 }
 
 int rollout_step(arl_ctx* c, int s_idx, const uint8_t* staging, cudaStream_t st) {
+  NvtxRange nvtx_("serve: fwd + sample + env step + frame");
   const arl_sampler_cfg& s = c->sc;
   const int B = s.n_envs, T = s.horizon;
   // the env step of env e runs in the head kernel's block e right after its action is sampled
@@ -1959,6 +1973,8 @@ int arl_sampler_configure(arl_ctx* c, const arl_sampler_cfg* cfg) {
   if (cfg->frame_mode == 1 && (c->cfg.in_h != kNsH || c->cfg.in_w != kNsW))
     ARL_FAIL(c, "frame_mode 1 (RGB frames) produces 84x84 observations");
   if (cfg->frame_mode != 0 && cfg->frame_mode != 1) ARL_FAIL(c, "frame_mode must be 0 or 1");
+  if (cfg->n_games > 1 && !cfg->ext_emulator && (cfg->pool_frames % cfg->n_games))
+    ARL_FAIL(c, "pool_frames must be a multiple of n_games");
   if ((cfg->planes * c->cfg.in_h * c->cfg.in_w) % 16) ARL_FAIL(c, "observation bytes must be a multiple of 16");
   if (B > c->cfg.max_rows) ARL_FAIL(c, "n_envs larger than max_rows");
   // env state block: 4 int arrays + ... allocate separately for clarity
@@ -2098,6 +2114,7 @@ int arl_copy_async(arl_ctx* c, void* dst, const void* src, size_t bytes, int to_
 }
 
 int arl_rollout_run(arl_ctx* c, void* stream) {
+  NvtxRange nvtx_("rollout");
   if (!c->sampler_set) ARL_FAIL(c, "sampler not configured");
   cudaStream_t st = (cudaStream_t)stream;
   if (!c->rollout_graph) {
@@ -2154,6 +2171,7 @@ int arl_peek_frame_cmds(arl_ctx* c, int* cmd_host, int n_envs, void* stream) {
 int arl_gae(arl_ctx* c, const float* rewards, float* values, const uint8_t* dones, const uint8_t* need_reset,
             const float* last_values, float discount, float gae_lambda, float* adv, float* ret, int8_t* valids,
             int n_envs, int horizon, int standardize, void* stream) {
+  NvtxRange nvtx_("gae");
   cudaStream_t st = (cudaStream_t)stream;
   int use_gae = (gae_lambda != 1.0f) ? 1 : 0;
   gae_kernel<<<(n_envs + 3) / 4, 128, 0, st>>>(rewards, values, dones, need_reset, last_values, discount, gae_lambda,
@@ -2215,6 +2233,7 @@ int arl_train_minibatches_async(arl_ctx* c, const int* idx, int mb_size, int cou
 }  // extern "C"
 namespace {
 int train_minibatches(arl_ctx* c, const int* idx, int mb_size, int count, int sync, cudaStream_t st) {
+  NvtxRange nvtx_("train minibatches");
   // sync: 0 = local clip + update, 1 = synchronous DP step, 2 = asynchronous push/pull
   const bool overlap = sync == 1 && sync_overlap_ok(c);
   if (overlap && sync_overlap_prepare(c)) return 1;
@@ -2391,6 +2410,7 @@ int arl_comm_trace(arl_ctx* c, double* out, int reset, void* stream) {
 }  // extern "C"
 namespace {
 int sync_update(arl_ctx* c, cudaStream_t st) {
+  NvtxRange nvtx_("allreduce+adam");
   if (!c->opt_set) ARL_FAIL(c, "optimizer not configured");
   SyncUpdateArgs a{};
   a.param = c->params; a.grad = c->grad; a.m = c->m; a.v = c->v; a.n = c->n_params;
@@ -2432,6 +2452,7 @@ int sync_overlap_prepare(arl_ctx* c) {
 }
 
 int sync_fc_exchange(arl_ctx* c, cudaStream_t ws, cudaStream_t st) {
+  NvtxRange nvtx_("allreduce+adam: FC slice exchange");
   (void)ws;                                              // ev_cs_in[0] was recorded on it right after the FC weight gradient
   ARL_CHECK(c, cudaEventRecord(c->ev_cs_in[1], st));
   ARL_CHECK(c, cudaStreamWaitEvent(c->cs, c->ev_cs_in[0], 0));
@@ -2455,6 +2476,7 @@ int sync_fc_exchange(arl_ctx* c, cudaStream_t ws, cudaStream_t st) {
 }
 
 int sync_tail(arl_ctx* c, cudaStream_t st) {
+  NvtxRange nvtx_("allreduce+adam: tail");
   const CommDev& d = c->comm.dev;
   const long n_small = c->n_params - (long)c->Kfc * c->H;
   const int blocks = (int)((n_small + 255) / 256);
@@ -2579,6 +2601,12 @@ int arl_debug_activation(arl_ctx* c, int layer, float* out, long cap, long* n, v
 }
 
 long arl_kernel_launches(arl_ctx* c) { return c->launches; }
+
+#ifndef ARL_SRC_HASH
+#define ARL_SRC_HASH "unknown"
+#endif
+/* sha256 of the CUDA sources this binary was built from (csrc/Makefile: api.cu + the headers, in Makefile order) */
+const char* arl_source_hash(void) { return ARL_SRC_HASH; }
 
 #ifdef ARL_TRACE
 extern "C" int arl_trace_read(long long* out, int n) {

@@ -19,7 +19,11 @@ struct SynthCfg {
   int life_mul, life_mod;
   int reward_mod;       // a frame pays when hash(env, f) % reward_mod == 0
   int frame_stride;     // pool index = (env + frame_stride * f) % pool_frames
+  // game mix (BASELINE configs[2] "4-game mix"): env e plays game g = e % n_games; every game has its own slice of the
+  // frame pool (pool_frames / n_games frames), its own reward table (reward_mod + 6 g) and life clock (life_base + 17 g)
+  int n_games;          // <= 1: one game
 };
+ARL_DEVINL int synth_game(const SynthCfg& c, int e) { return c.n_games > 1 ? e % c.n_games : 0; }
 
 ARL_DEVINL uint32_t synth_hash(uint32_t e, uint32_t f) {
   uint32_t h = e * 0x9E3779B1u + f * 0x85EBCA77u + 0x165667B1u;
@@ -28,16 +32,23 @@ ARL_DEVINL uint32_t synth_hash(uint32_t e, uint32_t f) {
 }
 ARL_DEVINL float synth_reward(const SynthCfg& c, int e, int f) {
   uint32_t h = synth_hash((uint32_t)e, (uint32_t)f);
-  if (h % (uint32_t)c.reward_mod != 0) return 0.f;
-  uint32_t k = (h / (uint32_t)c.reward_mod) & 3u;
+  const uint32_t rm = (uint32_t)(c.reward_mod + 6 * synth_game(c, e));
+  if (h % rm != 0) return 0.f;
+  uint32_t k = (h / rm) & 3u;
   return k == 2 ? 4.f : (k == 3 ? -1.f : 1.f);
 }
-ARL_DEVINL int synth_life_period(const SynthCfg& c, int e) { return c.life_base + (e * c.life_mul) % c.life_mod; }
+ARL_DEVINL int synth_life_period(const SynthCfg& c, int e) {
+  return c.life_base + 17 * synth_game(c, e) + (e * c.life_mul) % c.life_mod;
+}
 ARL_DEVINL int synth_lives(const SynthCfg& c, int e, int f) {
   int l = c.lives0 - f / synth_life_period(c, e);
   return l < 0 ? 0 : l;
 }
 ARL_DEVINL int synth_frame_index(const SynthCfg& c, int e, int f) {
+  if (c.n_games > 1) {
+    const int fpg = c.pool_frames / c.n_games;
+    return synth_game(c, e) * fpg + (int)(((long)e + (long)c.frame_stride * f) % fpg);
+  }
   return (int)(((long)e + (long)c.frame_stride * f) % c.pool_frames);
 }
 

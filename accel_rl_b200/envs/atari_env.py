@@ -17,6 +17,10 @@ W, H = (80, 104)  # atari_env.py:13
 # Minimal action sets (ALE getMinimalActionSet) for the games the BASELINE configs name
 MINIMAL_ACTIONS = {"breakout": 4, "pong": 6, "space_invaders": 6, "seaquest": 18, "qbert": 6, "beam_rider": 9}
 
+# Game mixes (BASELINE configs[2] "A2C 4-game Atari mix"): env e plays games[e % len(games)]; one policy serves them all,
+# its action count padded to the largest minimal action set of the mix (SURVEY.md §8(d) synthetic-inputs row)
+GAME_MIXES = {"mix4": ("breakout", "pong", "space_invaders", "beam_rider")}
+
 DEFAULT_SYNTH_RULES = dict(pool_frames=1024, lives0=5, life_base=400, life_mul=31, life_mod=257, reward_mod=389,
                            frame_stride=263, pool_seed=0)
 
@@ -54,7 +58,16 @@ class AtariEnv(object):
         self.synth_rules = dict(DEFAULT_SYNTH_RULES)
         if synth_rules:
             self.synth_rules.update(synth_rules)
-        n = n_actions if n_actions is not None else MINIMAL_ACTIONS.get(game, 4)
+        if game in GAME_MIXES:
+            games = GAME_MIXES[game]
+            self.synth_rules["n_games"] = len(games)
+            if self.synth_rules["pool_frames"] % len(games):
+                raise ValueError("pool_frames must be a multiple of the number of games in the mix")
+            default_n = max(MINIMAL_ACTIONS[g] for g in games)
+        else:
+            self.synth_rules.setdefault("n_games", 1)
+            default_n = MINIMAL_ACTIONS.get(game, 4)
+        n = n_actions if n_actions is not None else default_n
         self._action_space = Discrete(n)
         obs_hw = (H, W) if frame_mode == "gray" else (84, 84)
         self._observation_space = UintBox(shape=(num_img_obs,) + obs_hw, bits=8)

@@ -32,8 +32,12 @@ class SynthEmulator(object):
         self.e, self.f = int(env_id), 0
         self.pool = frame_pool(r["pool_frames"], pool_seed, channels)
         self.pool_frames, self.stride = r["pool_frames"], r["frame_stride"]
-        self.reward_mod, self.lives0 = r["reward_mod"], r["lives0"]
-        self.period = r["life_base"] + (self.e * r["life_mul"]) % r["life_mod"]
+        # game mix: env e plays game e % n_games (own pool slice, reward table, life clock), as csrc/kernels.cuh synth_game
+        n_games = int(r.get("n_games", 1))
+        self.game = self.e % n_games if n_games > 1 else 0
+        self.fpg = self.pool_frames // n_games if n_games > 1 else self.pool_frames
+        self.reward_mod, self.lives0 = r["reward_mod"] + 6 * self.game, r["lives0"]
+        self.period = r["life_base"] + 17 * self.game + (self.e * r["life_mul"]) % r["life_mod"]
 
     def getMinimalActionSet(self):
         return np.array([0, 1, 3, 4], dtype=np.int32)          # NOOP FIRE RIGHT LEFT (Breakout)
@@ -61,7 +65,7 @@ class SynthEmulator(object):
         return self.lives() == 0
 
     def getScreenGrayscale(self, buf):
-        buf[...] = self.pool[(self.e + self.stride * self.f) % self.pool_frames].reshape(buf.shape)
+        buf[...] = self.pool[self.game * self.fpg + (self.e + self.stride * self.f) % self.fpg].reshape(buf.shape)
         return buf
 
     getScreenRGB = getScreenGrayscale

@@ -75,6 +75,7 @@ class AAOEvalSampler(ActsrvAltOvrlpSampler):
         cfg.episodic_lives = int(bool(env.episodic_lives))
         for k in ("lives0", "life_base", "life_mul", "life_mod", "reward_mod", "frame_stride"):
             setattr(cfg, k, int(rules[k]))
+        cfg.n_games = int(rules.get("n_games", 1))
         cfg.frame_mode = 1 if self._frame_channels == 3 else 0
         cfg.traj_cap = max(4 * B, 1024, 2 * N // 16)
         self._eval_traj_cap = cfg.traj_cap

@@ -67,7 +67,8 @@ def parse():
                     help="multi-GPU learner: sync (configs[3], fused all-reduce) or async (configs[4], central store + chunk locks)")
     ap.add_argument("--game", default="breakout",
                     help="names the action count of the synthetic envs (ALE minimal action sets: breakout 4, pong / "
-                         "space_invaders 6, beam_rider 9, seaquest 18); BASELINE configs[4] is space_invaders")
+                         "space_invaders 6, beam_rider 9, seaquest 18); BASELINE configs[4] is space_invaders; mix4 = "
+                         "BASELINE configs[2]'s 4-game mix (env e plays game e % 4, actions padded to 9)")
     ap.add_argument("--poll-horizon", type=int, default=0,
                     help="async learners: ActsrvAltOvrlpPollSampler refreshing the policy from the central store every this "
                          "many rollout steps (0: plain sampler)")
@@ -320,11 +321,13 @@ def workload_config(args, world):
     """the `config` object both arms print (the reference arm times the SAME workload on the host cores)"""
     rgb = args.frames == "rgb"
     N = args.envs * args.horizon
-    return {"workload": ("PPO Breakout-shaped, %d envs/GPU x %d-step rollout, %s, "
-                         "%d epochs x mb %d, Adam; synthetic %s emulator frames"
-                         % (args.envs, args.horizon,
+    a2c = getattr(args, "algo", "ppo") == "a2c"
+    game = getattr(args, "game", "breakout")
+    return {"workload": ("%s %s-shaped (A=%d), %d envs/GPU x %d-step rollout, %s, %s; synthetic %s emulator frames"
+                         % ("A2C" if a2c else "PPO", game, action_count(game), args.envs, args.horizon,
                             "classic Nature-CNN @ (4,84,84)" if rgb else "cnn preset %d @ (4,104,80)" % args.spec,
-                            args.epochs, args.minibatch, "210x160x3 RGB" if rgb else "210x160 grayscale")),
+                            "one full-batch RMSProp step" if a2c else "%d epochs x mb %d, Adam" % (args.epochs, args.minibatch),
+                            "210x160x3 RGB" if rgb else "210x160 grayscale")),
             "frames": args.frames, "game": getattr(args, "game", "breakout"),
             "poll_horizon": getattr(args, "poll_horizon", 0),
             "algo": args.algo, "learner": ("single" if world == 1 and args.parallelism == "sync" else args.parallelism),
@@ -332,7 +335,15 @@ def workload_config(args, world):
             "l2_policy": "inputs larger than L2 (%.2f GB rollout buffer, %d MB frame pool)" %
                          (N * 4 * (84 * 84 if rgb else 104 * 80) / 1e9,
                           args.pool_frames * (100800 if rgb else 33600) // 2 ** 20),
-            "step": "one full PPO iteration"}
+            "step": "one full %s iteration" % ("A2C" if a2c else "PPO")}
+
+
+def action_count(game):
+    """policy action count of a --game (ALE minimal action sets; a mix pads to its largest set)"""
+    from accel_rl_b200.envs.atari_env import GAME_MIXES, MINIMAL_ACTIONS
+    if game in GAME_MIXES:
+        return max(MINIMAL_ACTIONS[g] for g in GAME_MIXES[game])
+    return MINIMAL_ACTIONS.get(game, 4)
 
 
 def sync_parity(runner, rank, world):
@@ -588,19 +599,24 @@ def cpu_port(args, steps=1, warmup=0):
     B, Ts = args.envs, args.cpu_sample_steps
     rgb = getattr(args, "frames", "gray") == "rgb"
     spec = dict(NATURE84_SPEC, conv_pads=[0, 0, 0]) if rgb else onet.CNN_SPECS[args.spec]
-    rules = dict(synth_ale.DEFAULT_RULES, pool_frames=256)
+    from accel_rl_b200.envs.atari_env import GAME_MIXES
+    game = getattr(args, "game", "breakout")
+    algo = getattr(args, "algo", "ppo")
+    A = action_count(game)
+    rules = dict(synth_ale.DEFAULT_RULES, pool_frames=256, n_games=len(GAME_MIXES.get(game, ("",))))
     pool = synth_ale.make_pool(256, seed=0, channels=3) if rgb else synth_ale.make_pool(256, seed=0)
-    flat = onet.init_params(spec, (4, 84, 84) if rgb else (4, 104, 80), 4, np.random.RandomState(0),
+    flat = onet.init_params(spec, (4, 84, 84) if rgb else (4, 104, 80), A, np.random.RandomState(0),
                             np.random.RandomState(1))
     n_par = ref_n_parallel(B, cores)
     master_threads = max(1, cores - 2 * n_par)
-    smp = mp_sampler.MpOracleSampler(n_par, B // (2 * n_par), Ts, pool, rules, 4, 0.99)
-    opt = onet.Adam(flat.size, 1e-3, epsilon=1e-5)
+    Ts = min(Ts, args.horizon)
+    smp = mp_sampler.MpOracleSampler(n_par, B // (2 * n_par), Ts, pool, rules, A, 0.99)
+    opt = onet.RMSProp(flat.size) if algo == "a2c" else onet.Adam(flat.size, 1e-3, epsilon=1e-5)
     rng = np.random.RandomState(0)
 
     def policy_fn(obs):
         with torch.no_grad():
-            p, v = onet.forward(torch.from_numpy(flat), torch.from_numpy(np.ascontiguousarray(obs)), spec, 4)
+            p, v = onet.forward(torch.from_numpy(flat), torch.from_numpy(np.ascontiguousarray(obs)), spec, A)
         return p.numpy(), v.numpy()
 
     mb = min(args.minibatch, B * Ts)
@@ -612,7 +628,7 @@ def cpu_port(args, steps=1, warmup=0):
             buf, _ = smp.obtain_samples(policy_fn, rng.rand(Ts, B))
             t1 = time.time()
             torch.set_num_threads(cores)
-            flat, _, _, _ = olearner.optimize_policy(flat, opt, buf, spec, 4, Ts, "ppo", rng, epochs=args.epochs,
+            flat, _, _, _ = olearner.optimize_policy(flat, opt, buf, spec, A, Ts, algo, rng, epochs=args.epochs,
                                                      minibatch_size=mb, emulate_bf16=False)
             t2 = time.time()
             if it >= warmup:
@@ -624,9 +640,11 @@ def cpu_port(args, steps=1, warmup=0):
     n = B * Ts
     return {"value": round(n / (samp + learn), 1), "unit": "env-steps/s", "cores": cores, "kind": "port",
             "sample": "per step: %d envs x %d rollout steps (%d env-steps) through %d simulator processes (two alternating "
-                      "groups of %d) + master, then GAE + %d epochs x mb %d on them; oracle/ port: Theano replaced by an fp32 "
+                      "groups of %d) + master, then GAE + %s on them; oracle/ port: Theano replaced by an fp32 "
                       "torch-CPU restatement (%d threads serving actions, %d for the learner), ALE by the synthetic emulator"
-                      % (B, Ts, n, 2 * n_par, n_par, args.epochs, mb, master_threads, cores),
+                      % (B, Ts, n, 2 * n_par, n_par,
+                         "one full-batch RMSProp step" if algo == "a2c" else "%d epochs x mb %d" % (args.epochs, mb),
+                         master_threads, cores),
             "sampler_env_steps_per_s": round(n / samp, 1), "learner_env_steps_per_s": round(n / learn, 1),
             "seconds_per_sample": round(samp + learn, 3), "sample_env_steps": n, "sim_processes": 2 * n_par}
 

@@ -69,6 +69,9 @@ typedef struct {
   int lives0, life_base, life_mul, life_mod, reward_mod, frame_stride;
   int traj_cap;                 /* capacity of the completed-trajectory record buffer */
   int ext_emulator;             /* != 0: emulators run in host worker processes; steps arrive through arl_rollout_ingest */
+  int n_games;                  /* > 1: game mix of the synthetic emulator (env e plays game e % n_games: own slice of the
+                                   frame pool, own reward table and life clock); the policy's action count is the largest
+                                   of the games' minimal action sets (BASELINE configs[2]) */
   int frame_mode;               /* 0: reference frames (210,160) gray -> (planes,104,80), atari_env.py:151-157;
                                  * 1: north-star frames (210,160,3) RGB -> gray -> (planes,84,84) (see arl_frame_update_rgb);
                                  *    frame_pool / staging then hold RGB frames */
@@ -231,6 +234,9 @@ int arl_async_read_central(arl_ctx* ctx, int which, float* host_out, long n, voi
 /* intermediate activations of the last forward (bf16 -> fp32 copies into host-visible device buffers) */
 int arl_debug_activation(arl_ctx* ctx, int layer, float* out, long cap, long* n, void* stream);
 long arl_kernel_launches(arl_ctx* ctx);
+/* sha256 (hex) of the CUDA sources the loaded binary was compiled from; __graft_entry__.smoke() and the GPU tests compare it
+ * with the sources next to the library, so a stale prebuilt .so is caught on the GPU box */
+const char* arl_source_hash(void);
 /* CUDA-event timing of every kernel launched (outside graphs) between begin and end, on `stream`:
  * names = ';'-separated launch labels, ms[i] = device time of launch i */
 int arl_profile_begin(arl_ctx* ctx, void* stream);

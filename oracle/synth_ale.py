@@ -30,16 +30,24 @@ def synth_hash(e, f):
     return h
 
 
+def game_of(rules, e):
+    """game mix (BASELINE configs[2] "4-game mix"): env e plays game e % n_games; every game has its own slice of the
+    frame pool, its own reward table (reward_mod + 6 g) and life clock (life_base + 17 g)"""
+    n = rules.get("n_games", 1)
+    return e % n if n > 1 else 0
+
+
 def synth_reward(rules, e, f):
     h = synth_hash(e, f)
-    if h % rules["reward_mod"] != 0:
+    rm = rules["reward_mod"] + 6 * game_of(rules, e)
+    if h % rm != 0:
         return 0.0
-    k = (h // rules["reward_mod"]) & 3
+    k = (h // rm) & 3
     return 4.0 if k == 2 else (-1.0 if k == 3 else 1.0)
 
 
 def life_period(rules, e):
-    return rules["life_base"] + (e * rules["life_mul"]) % rules["life_mod"]
+    return rules["life_base"] + 17 * game_of(rules, e) + (e * rules["life_mul"]) % rules["life_mod"]
 
 
 def synth_lives(rules, e, f):
@@ -47,6 +55,10 @@ def synth_lives(rules, e, f):
 
 
 def frame_index(rules, e, f):
+    n = rules.get("n_games", 1)
+    if n > 1:
+        fpg = rules["pool_frames"] // n
+        return game_of(rules, e) * fpg + (e + rules["frame_stride"] * f) % fpg
     return (e + rules["frame_stride"] * f) % rules["pool_frames"]
 
 

@@ -79,3 +79,10 @@ def test_engine_fails_loudly_without_gpu():
     from accel_rl_b200.engine import Engine
     with pytest.raises(RuntimeError):
         Engine([32, 64, 64], [8, 4, 3], [4, 2, 1], [0, 1, 1], [512], 4, (4, 104, 80))
+
+
+def test_loaded_library_matches_the_sources_in_the_tree():
+    """the prebuilt .so travels to the GPU box next to its sources: the sha256 compiled into it (csrc/Makefile) must be
+    the sha256 of those sources"""
+    from accel_rl_b200 import _lib as L
+    assert L.check_source_hash() == L.source_hash() and len(L.source_hash()) == 64

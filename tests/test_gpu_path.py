@@ -127,6 +127,49 @@ def test_device_sampler_vs_oracle_larger_batch():
 
 
 
+@pytest.mark.parametrize("mbr", [True, False])
+def test_game_mix_sampler_vs_oracle(mbr):
+    """BASELINE configs[2]: the 4-game mix (env e plays game e % 4: own frame-pool slice, reward table, life clock; action
+    count padded to the largest minimal set, 9).  Device buffers == the oracle's restatement, bit for bit."""
+    from accel_rl_b200.util.seeding import set_seed
+    rules = dict(synth_ale.DEFAULT_RULES, pool_frames=256, life_base=20, life_mod=17, reward_mod=11, pool_seed=0)
+    set_seed(1)
+    B, T, A = 32, 12, 9
+    sampler = _make_sampler(4, 4, T, rules=rules, mid_batch_reset=mbr, env_kw=dict(game="mix4"))
+    env_spec, _, _, _ = sampler.initialize(seed=2, affinities=dict(), discount=0.99, need_extra_obs=True)
+    assert env_spec.action_space.n == A
+    pol, flat, spec = make_policy(1, max_rows=B, n_actions=A)
+    sampler.policy_init(pol)
+    orules = dict({k: v for k, v in rules.items() if k != "pool_seed"}, n_games=4)
+    orc = osampler.OracleSampler(B, T, synth_ale.make_pool(256, seed=0), orules, A, 0.99, mid_batch_reset=mbr)
+    try:
+        n_traj, rew_by_game = 0, np.zeros(4)
+        for itr in range(6):
+            buf, infos = sampler.obtain_samples(itr)
+            b = _buf_np(buf)
+            u = sampler._uniforms_host.numpy().copy()
+            gp = b["prob"].reshape(B, T, A); gv = b["value"].reshape(B, T)
+            calls = {"k": 0}
+
+            def policy_fn(obs):
+                k = calls["k"]; calls["k"] += 1
+                s, j = divmod(k, 2)
+                lo, hi = j * B // 2, (j + 1) * B // 2
+                return gp[lo:hi, s], gv[lo:hi, s]
+            ob, oinf = orc.obtain_samples(policy_fn, u)
+            for k in ("observations", "extra_observations", "rewards", "dones", "raw_reward", "need_reset", "actions"):
+                assert np.array_equal(b[k], ob[k]), (k, itr)
+            assert sorted((t.Length, round(float(t.Return), 4)) for t in infos) == \
+                sorted((t["Length"], round(float(t["Return"]), 4)) for t in oinf)
+            n_traj += len(infos)
+            rew_by_game += np.abs(b["rewards"]).reshape(B // 4, 4, T).sum(axis=(0, 2))
+            assert b["actions"].max() < A
+        assert n_traj > 0
+        assert len(set(rew_by_game.tolist())) > 1            # the games' reward tables differ
+    finally:
+        pol.engine.close()
+
+
 @pytest.mark.parametrize("mbr,mpl", [(True, 27000), (False, 27000), (True, 11)])
 def test_decorrelated_start_vs_oracle(mbr, mpl):
     """start_envs with max_decorrelation_steps > 0 (sampler/util.py:33-55): every env takes its own number of warm-up

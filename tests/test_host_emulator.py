@@ -165,6 +165,39 @@ def test_product_synthetic_emulator_follows_the_oracle_rules():
         assert em.f == 0
 
 
+def test_game_mix_rules_product_emulator_vs_oracle():
+    """BASELINE configs[2] "4-game mix": env e plays game e % 4 — own slice of the frame pool, own reward table and life
+    clock.  The product's host emulator against the oracle's statement, and the properties that make it a mix."""
+    from accel_rl_b200.hostsim import synth_emulator as se
+    from accel_rl_b200.envs.atari_env import AtariEnv, GAME_MIXES, MINIMAL_ACTIONS
+    rules = dict(RULES, pool_frames=32, n_games=4)
+    pool = synth_ale.make_pool(32, seed=0)
+    seen = {g: set() for g in range(4)}
+    for e in range(12):
+        em = se.SynthEmulator(e, rules)
+        buf = np.zeros((210, 160), np.uint8)
+        for f in range(1, 120):
+            assert em.act(0) == synth_ale.synth_reward(rules, e, f)
+            assert em.lives() == synth_ale.synth_lives(rules, e, f)
+            em.getScreenGrayscale(buf)
+            i = synth_ale.frame_index(rules, e, f)
+            assert np.array_equal(buf, pool[i])
+            seen[e % 4].add(i)
+    for g in range(4):                                   # every game stays inside its own 8-frame slice, and uses all of it
+        assert seen[g] == set(range(8 * g, 8 * g + 8))
+    # life clocks differ by game: env 0 (game 0) vs env 4 (game 0) share the base; env 1 (game 1) is 17 frames longer
+    base = lambda e: synth_ale.life_period(rules, e) - (e * rules["life_mul"]) % rules["life_mod"]
+    assert base(4) == base(0) and base(1) == base(0) + 17 and base(3) == base(0) + 51
+    # one game: the mix rules reduce to the plain ones
+    assert all(synth_ale.frame_index(dict(rules, n_games=1), 3, f) == synth_ale.frame_index(RULES | dict(pool_frames=32), 3, f)
+               for f in range(40))
+    env = AtariEnv(game="mix4", max_start_noops=0, synth_rules=dict(pool_frames=32))
+    assert env.synth_rules["n_games"] == 4
+    assert env.action_space.n == max(MINIMAL_ACTIONS[g] for g in GAME_MIXES["mix4"]) == 9   # padded to the largest set
+    with pytest.raises(ValueError):
+        AtariEnv(game="mix4", max_start_noops=0, synth_rules=dict(pool_frames=30))
+
+
 def test_profiling_worker_dumps_a_profile(tmp_path):
     """profile_pathname (sampler/base.py:32-43, sampler/util.py:10-19): the worker runs under cProfile and leaves
     <path>_sim_<rank>.prof when it quits"""
