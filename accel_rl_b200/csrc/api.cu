@@ -1696,6 +1696,18 @@ SynthCfg synth_cfg(const arl_sampler_cfg& s) {
 
 // frame pipeline for envs [e0, e0 + n) (n < 0: all).  The kernels index everything by env, so a sub-range is the same
 // launch over base pointers advanced by e0 envs (staging is the base of the whole [B][2][frame] block).
+// Lean rollout (mid_batch_reset samplers that record observations and keep the bf16 mirror): inside a batch the current
+// stack of env e is rollout row e*T + s — the frame kernel reads the three kept planes from there and writes only row
+// e*T + s + 1 (u8 + mirror), the policy's first conv layer gathers rows e*T + s of the mirror; the step buffer and its
+// mirror are written by the batch's LAST step only (they are what extra_observations, the next batch's row 0 and the
+// caller see).  Saves one u8 stack and one bf16 stack of HBM writes per env-step (291 840 -> 192 000 B).  ARL_FRAME_LEAN=0:
+// every step also updates the step buffers (A/B).
+bool frame_lean(arl_ctx* c) {
+  static const bool on = !(getenv("ARL_FRAME_LEAN") && atoi(getenv("ARL_FRAME_LEAN")) == 0);
+  const arl_sampler_cfg& s = c->sc;
+  return on && s.mid_batch_reset && s.observations && c->roll_obs16 && c->step_obs16 && s.horizon > 1;
+}
+
 int launch_frame(arl_ctx* c, const uint8_t* staging, int s_next, bool to_rollout, cudaStream_t st, int e0 = 0, int n = -1) {
   NvtxRange nvtx_("frame");
   const arl_sampler_cfg& s = c->sc;
@@ -1709,11 +1721,20 @@ int launch_frame(arl_ctx* c, const uint8_t* staging, int s_next, bool to_rollout
   uint8_t* roll_obs = (to_rollout && s.observations) ? s.observations + (long)e0 * T * obs_bytes : nullptr;
   __nv_bfloat16* step16 = c->step_obs16 ? c->step_obs16 + (long)e0 * c->obs16_elems : nullptr;
   __nv_bfloat16* roll16 = (to_rollout && c->roll_obs16) ? c->roll_obs16 + (long)e0 * T * c->obs16_elems : nullptr;
+  const uint8_t* prev = step_obs;
+  long prev_stride = obs_bytes;
+  int lean = 0;
+  if (frame_lean(c) && s_next >= 1) {            // s_next in [1, T]: a step of the batch (0: start / reset / warm-up)
+    lean = 1;
+    prev = s.observations + ((long)e0 * T + (s_next - 1)) * obs_bytes;
+    prev_stride = T * obs_bytes;
+    if (to_rollout) { step_obs = nullptr; step16 = nullptr; }
+  }
   if (s.frame_mode == 1) {
     // north-star frames: RGB pool / staging -> gray -> 84x84 (frame_rgb_roll_kernel)
     ARL_CHECK(c, launch_k(frame_rgb_roll_kernel, dim3(n * (kNsH / kRgbRows)), dim3(kRgbThreads), 0, st, s.frame_pool, stg,
                           cmd, step_obs, roll_obs, step16, roll16, s.horizon, s_next, n, s.planes, c->pc_mode >= 2,
-                          c->pc_mode >= 2, c->obs16_elems));
+                          c->pc_mode >= 2, c->obs16_elems, prev, prev_stride, lean));
     c->launches++;
     prof_mark(c, "frame", st);
     ARL_CHECK(c, cudaGetLastError());
@@ -1722,7 +1743,7 @@ int launch_frame(arl_ctx* c, const uint8_t* staging, int s_next, bool to_rollout
   long items = (long)n * 520;
   int blocks = (int)((items + 255) / 256);
   ARL_CHECK(c, launch_k(frame_kernel, dim3(blocks), dim3(256), 0, st, s.frame_pool, stg, cmd, step_obs, roll_obs, step16, roll16,
-                        s.horizon, s_next, n, s.planes, c->pc_mode >= 2, c->pc_mode >= 2));
+                        s.horizon, s_next, n, s.planes, c->pc_mode >= 2, c->pc_mode >= 2, prev, prev_stride, lean));
   c->launches++;
   prof_mark(c, "frame", st);
   ARL_CHECK(c, cudaGetLastError());
@@ -1760,8 +1781,10 @@ int rollout_step(arl_ctx* c, int s_idx, const uint8_t* staging, cudaStream_t st)
   EnvStepArgs es{synth_cfg(s), c->est, c->tout, c->cmd, s.rewards, s.dones, s.raw_reward, s.need_reset, B, T, s_idx,
                  s.max_path_length, s.discount, s.mid_batch_reset, s.clip_reward, s.episodic_lives, nullptr, 0};
   const bool u8 = c->pc_mode >= 2 && u8_conv0_ok(c);
-  if (policy_forward16(c, c->step_obs16, B, c->rows_tab + (long)s_idx * B, s.prob, s.value,
-                       s.uniforms + (long)s_idx * B, s.actions, c->pc_mode >= 2, st, &es, u8 ? s.step_obs : nullptr))
+  const bool lean = frame_lean(c) && !u8;         // the current stacks are rollout rows e*T + s_idx (gathered through rows_tab)
+  if (policy_forward16(c, lean ? c->roll_obs16 : c->step_obs16, B, c->rows_tab + (long)s_idx * B, s.prob, s.value,
+                       s.uniforms + (long)s_idx * B, s.actions, c->pc_mode >= 2, st, &es, u8 ? s.step_obs : nullptr,
+                       lean ? c->rows_tab + (long)s_idx * B : nullptr))
     return 1;
   return launch_frame(c, staging, s_idx + 1, s_idx + 1 < T, st);
 }
@@ -2077,9 +2100,12 @@ int arl_rollout_serve(arl_ctx* c, int s, int e0, int n, void* stream) {
   if (e0 < 0 || n < 1 || e0 + n > sc.n_envs) ARL_FAIL(c, "serve env range out of bounds");
   const bool u8 = c->pc_mode >= 2 && u8_conv0_ok(c);
   const long obs_bytes = (long)sc.planes * c->cfg.in_h * c->cfg.in_w;
-  return policy_forward16(c, u8 ? nullptr : c->step_obs16 + (long)e0 * c->obs16_elems, n, c->rows_tab + (long)s * sc.n_envs + e0,
+  const int* rows = c->rows_tab + (long)s * sc.n_envs + e0;
+  const bool lean = frame_lean(c) && !u8;
+  return policy_forward16(c, u8 ? nullptr : lean ? c->roll_obs16 : c->step_obs16 + (long)e0 * c->obs16_elems, n, rows,
                           sc.prob, sc.value, sc.uniforms + (long)s * sc.n_envs + e0, sc.actions, c->pc_mode >= 2,
-                          (cudaStream_t)stream, nullptr, u8 ? sc.step_obs + (long)e0 * obs_bytes : nullptr);
+                          (cudaStream_t)stream, nullptr, u8 ? sc.step_obs + (long)e0 * obs_bytes : nullptr,
+                          lean ? rows : nullptr);
 }
 
 int arl_rollout_ingest(arl_ctx* c, int s, int e0, int n, const uint8_t* staging, const arl_ext_step* ext, void* stream) {

@@ -361,9 +361,13 @@ __global__ void __launch_bounds__(256) frame_kernel(const uint8_t* __restrict__ 
                                                     const FrameCmd* __restrict__ cmd, uint8_t* __restrict__ step_obs,
                                                     uint8_t* __restrict__ roll_obs, __nv_bfloat16* __restrict__ step_obs16,
                                                     __nv_bfloat16* __restrict__ roll_obs16, int T, int s_next, int n_envs,
-                                                    int planes, int swz_step, int swz_roll) {
+                                                    int planes, int swz_step, int swz_roll,
+                                                    const uint8_t* __restrict__ prev, long prev_stride, int lean) {
   pdl_wait();
   pdl_trigger();
+  // prev: where env e's CURRENT stack is read from (prev + e * prev_stride): the step buffer, or — lean rollout
+  // (launch_frame) — rollout row e*T + s_next - 1, in which case the step buffer and its mirror are only written by the
+  // last step of the batch (step_obs / step_obs16 == nullptr otherwise) and a skipped env's row is carried forward.
   // step_obs16 / roll_obs16: bf16 space-to-depth(4) mirrors of the same stacks, [26][20][planes*16] per
   // observation, channel = plane*16 + (y%4)*4 + (x%4) — the layout the first conv layer's tcgen05 tiles read
   // (u8 -> bf16 is exact).  They are written from the registers that already hold the u8 stack.
@@ -379,10 +383,12 @@ __global__ void __launch_bounds__(256) frame_kernel(const uint8_t* __restrict__ 
   int oy = rem / ITEMS_PER_ROW;
   int xc = rem - oy * ITEMS_PER_ROW;
   FrameCmd c = cmd[e];
-  if (c.flags & 2) return;   // env not stepped: nothing is written (rows keep their stale contents)
+  const bool skip = (c.flags & 2) != 0;
+  if (skip && !lean) return;   // env not stepped: nothing is written (rows keep their stale contents)
   const int plane_bytes = kObsH * kObsW;
   const long obs_bytes = (long)planes * plane_bytes;
-  uint8_t* cur = step_obs + (long)e * obs_bytes;
+  const uint8_t* prv = prev + (long)e * prev_stride;
+  uint8_t* cur = step_obs ? step_obs + (long)e * obs_bytes : nullptr;
   uint8_t* dst = roll_obs ? roll_obs + ((long)e * T + s_next) * obs_bytes : nullptr;
   const int pix = oy * kObsW + xc * 16;
   // ---- new plane ----
@@ -397,23 +403,30 @@ __global__ void __launch_bounds__(256) frame_kernel(const uint8_t* __restrict__ 
     if (c.src_b >= 0) fb = pool + (long)c.src_b * fbytes;
   }
   uint4 z = make_uint4(0, 0, 0, 0);
-  const uint4 newest = frame_box16(fa, fb, oy, xc);
+  uint4 newest;
   // ---- stack shift + store ----
   uint4 keep[3] = {z, z, z};
-  if (!(c.flags & 1)) {
+  if (skip) {                  // (lean) carry the unchanged stack forward
     for (int p = 0; p < planes - 1 && p < 3; ++p)
-      keep[p] = *reinterpret_cast<const uint4*>(cur + (p + 1) * plane_bytes + pix);
+      keep[p] = *reinterpret_cast<const uint4*>(prv + p * plane_bytes + pix);
+    newest = *reinterpret_cast<const uint4*>(prv + (planes - 1) * plane_bytes + pix);
+  } else {
+    newest = frame_box16(fa, fb, oy, xc);
+    if (!(c.flags & 1)) {
+      for (int p = 0; p < planes - 1 && p < 3; ++p)
+        keep[p] = *reinterpret_cast<const uint4*>(prv + (p + 1) * plane_bytes + pix);
+    }
   }
   for (int p = 0; p < planes - 1 && p < 3; ++p) {
-    *reinterpret_cast<uint4*>(cur + p * plane_bytes + pix) = keep[p];
+    if (cur) *reinterpret_cast<uint4*>(cur + p * plane_bytes + pix) = keep[p];
     if (dst) *reinterpret_cast<uint4*>(dst + p * plane_bytes + pix) = keep[p];
   }
-  *reinterpret_cast<uint4*>(cur + (planes - 1) * plane_bytes + pix) = newest;
+  if (cur) *reinterpret_cast<uint4*>(cur + (planes - 1) * plane_bytes + pix) = newest;
   if (dst) *reinterpret_cast<uint4*>(dst + (planes - 1) * plane_bytes + pix) = newest;
-  if (step_obs16) {
+  if (step_obs16 || roll_obs16) {
     const int Cs = planes * 16;
     const long obs16_elems = (long)(kObsH / 4) * (kObsW / 4) * Cs;
-    __nv_bfloat16* c16 = step_obs16 + (long)e * obs16_elems;
+    __nv_bfloat16* c16 = step_obs16 ? step_obs16 + (long)e * obs16_elems : nullptr;
     __nv_bfloat16* d16 = roll_obs16 ? roll_obs16 + ((long)e * T + s_next) * obs16_elems : nullptr;
     const int by = oy >> 2, dy = oy & 3;
     for (int p = 0; p < planes; ++p) {
@@ -425,7 +438,7 @@ __global__ void __launch_bounds__(256) frame_kernel(const uint8_t* __restrict__ 
         const long off = (long)pos * Cs + ch;
         const long offs = (long)pos * Cs + ((((ch >> 3) ^ (pos & 7)) << 3) | (ch & 7));   // chunk-swizzled (Cs == 64)
         const uint2 o = u8x4_to_bf16x4(w[b]);
-        *reinterpret_cast<uint2*>(c16 + (swz_step ? offs : off)) = o;
+        if (c16) *reinterpret_cast<uint2*>(c16 + (swz_step ? offs : off)) = o;
         if (d16) *reinterpret_cast<uint2*>(d16 + (swz_roll ? offs : off)) = o;
       }
     }
@@ -585,9 +598,10 @@ __global__ void __launch_bounds__(kRgbThreads) frame_rgb_roll_kernel(
     const uint8_t* __restrict__ pool, const uint8_t* __restrict__ staging, const FrameCmd* __restrict__ cmd,
     uint8_t* __restrict__ step_obs, uint8_t* __restrict__ roll_obs, __nv_bfloat16* __restrict__ step_obs16,
     __nv_bfloat16* __restrict__ roll_obs16, int T, int s_next, int n_envs, int planes, int swz_step, int swz_roll,
-    long img16) {
+    long img16, const uint8_t* __restrict__ prev, long prev_stride, int lean) {
   pdl_wait();
   pdl_trigger();
+  // prev / lean: as frame_kernel
   __shared__ __align__(16) uint32_t s_gray[kRgbGrayWords + 4];
   __shared__ __align__(4) uint8_t s_out[kRgbRows * kNsW];
   constexpr int GROUPS = kNsH / kRgbRows;
@@ -596,7 +610,8 @@ __global__ void __launch_bounds__(kRgbThreads) frame_rgb_roll_kernel(
   const int grp = blockIdx.x - e * GROUPS;
   const int tid = threadIdx.x;
   const FrameCmd c = cmd[e];
-  if (c.flags & 2) return;                       // env not stepped: rows keep their stale contents
+  const bool skip = (c.flags & 2) != 0;
+  if (skip && !lean) return;                     // env not stepped: rows keep their stale contents
   const bool rs = (c.flags & 1) != 0;
   const long fbytes = (long)kRgbH * kRgbW * 3;
   const long roff = (long)grp * kRgbInRows * kRgbW * 3;
@@ -615,33 +630,40 @@ __global__ void __launch_bounds__(kRgbThreads) frame_rgb_roll_kernel(
   const int pix = Y * kNsW + xw * 4;
   const int plane_px = kNsH * kNsW;
   const long obs_bytes = (long)planes * plane_px;
-  uint8_t* cur = step_obs + (long)e * obs_bytes + pix;
+  const uint8_t* prv = prev + (long)e * prev_stride + pix;
+  uint8_t* cur = step_obs ? step_obs + (long)e * obs_bytes + pix : nullptr;
   uint32_t older[3] = {0u, 0u, 0u};
-  if (outp && !rs) {
+  uint32_t newest = 0u;
+  if (outp && skip) {                            // (lean) carry the unchanged stack forward
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+      if (p < planes - 1) older[p] = *reinterpret_cast<const uint32_t*>(prv + p * plane_px);
+    newest = *reinterpret_cast<const uint32_t*>(prv + (planes - 1) * plane_px);
+  } else if (outp && !rs) {
 #pragma unroll
     for (int p = 1; p < 4; ++p)
-      if (p < planes) older[p - 1] = *reinterpret_cast<const uint32_t*>(cur + p * plane_px);
+      if (p < planes) older[p - 1] = *reinterpret_cast<const uint32_t*>(prv + p * plane_px);
   }
-  rgb_slab_to_rows(fa, fb, s_gray, s_out, tid);
+  if (!skip) rgb_slab_to_rows(fa, fb, s_gray, s_out, tid);     // (skip is uniform over the block)
   if (!outp) return;
   uint8_t* dst = roll_obs ? roll_obs + ((long)e * T + s_next) * obs_bytes + pix : nullptr;
   __nv_bfloat16* c16 = step_obs16 ? step_obs16 + (long)e * img16 : nullptr;
-  __nv_bfloat16* d16 = (step_obs16 && roll_obs16) ? roll_obs16 + ((long)e * T + s_next) * img16 : nullptr;
+  __nv_bfloat16* d16 = roll_obs16 ? roll_obs16 + ((long)e * T + s_next) * img16 : nullptr;
   const int Cs = planes * 16;
   const int pos = (Y >> 2) * (kNsW / 4) + xw;
-  const uint32_t newest = *reinterpret_cast<const uint32_t*>(s_out + oy * kNsW + xw * 4);
+  if (!skip) newest = *reinterpret_cast<const uint32_t*>(s_out + oy * kNsW + xw * 4);
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
     if (p >= planes) break;
     const uint32_t v = (p < planes - 1) ? older[p < 3 ? p : 2] : newest;
-    *reinterpret_cast<uint32_t*>(cur + p * plane_px) = v;
+    if (cur) *reinterpret_cast<uint32_t*>(cur + p * plane_px) = v;
     if (dst) *reinterpret_cast<uint32_t*>(dst + p * plane_px) = v;
-    if (c16) {
+    if (c16 || d16) {
       const int ch = p * 16 + (Y & 3) * 4;
       const long off = (long)pos * Cs + ch;
       const long offs = (long)pos * Cs + ((((ch >> 3) ^ (pos & 7)) << 3) | (ch & 7));
       const uint2 o2 = u8x4_to_bf16x4(v);
-      *reinterpret_cast<uint2*>(c16 + (swz_step ? offs : off)) = o2;
+      if (c16) *reinterpret_cast<uint2*>(c16 + (swz_step ? offs : off)) = o2;
       if (d16) *reinterpret_cast<uint2*>(d16 + (swz_roll ? offs : off)) = o2;
     }
   }

@@ -1,17 +1,35 @@
 """Multi-GPU runners (reference: accel_rl/runners/multigpu_rl.py:7-40, multigpu_rl_base.py:12-250).
 
 The reference forks one full runner per GPU from a master process and ships the NCCL clique id and
-the rank-0 parameters through an mp.Manager dict.  Here the launch is one process per GPU
-(torchrun / torch.distributed, backend nccl): every rank constructs the same AccelRLSync with its own
-`affinities` entry; rank r seeds with seed + 100*r (multigpu_rl_base.py:28), rank 0's initial
-parameters are broadcast (:119,:142-143), and n_itr is computed from sample_size * n_runners
-(:62-63).  Worker traj_infos are gathered to rank 0 for logging (:216-231)."""
+the rank-0 parameters through an mp.Manager dict.  Here every GPU has one process joined in a
+torch.distributed group (backend nccl); rank r seeds with seed + 100*r (multigpu_rl_base.py:28), rank 0's
+initial parameters are broadcast (:119,:142-143), and n_itr is computed from sample_size * n_runners
+(:62-63).  Worker traj_infos are gathered to rank 0 for logging (:216-231).
+
+Two ways to get the processes, same training either way (tests/test_gpu_multi.py compares them bit for bit):
+  * one script, like the reference: construct the runner with `affinities=[dict(gpu=0), dict(gpu=1), ...]` in a
+    plain `python script.py`; `train()` forks ranks 1.. itself (launch_workers, as multigpu_rl_base.py:20-45) and
+    forms the group over 127.0.0.1.  The runner must be built before the process touches CUDA (fork);
+  * torchrun / torch.distributed.run: every rank runs the script, the group already exists, nothing is forked."""
+import multiprocessing as mp
+import os
+import socket
+import sys
+import traceback
+
 import numpy as np
 import torch
 import torch.distributed as dist
 
 from accel_rl_b200.runners.accel_rl import AccelRL
 from accel_rl_b200.util import logger
+from accel_rl_b200.util.misc import make_seed
+
+
+def _free_port():
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
 
 
 class AccelRLSync(AccelRL):
@@ -21,10 +39,68 @@ class AccelRLSync(AccelRL):
         if isinstance(affinities, (list, tuple)):
             self.all_affinities = list(affinities)
             affinities = affinities[self.rank] if self.rank < len(affinities) else dict()
+        else:
+            self.all_affinities = [affinities]
         super().__init__(affinities=affinities, seed=seed, **kwargs)
         self._base_seed = seed
+        self.worker_procs = []
+        self._own_group = False
+
+    def launch_workers(self):
+        """one script, N GPUs (multigpu_rl_base.py:20-45): fork a full runner for every rank >= 1 and join them in a
+        process group.  Nothing to do under torchrun (the group exists) or with one affinity."""
+        n = len(self.all_affinities)
+        if dist.is_initialized() or n <= 1:
+            return
+        if torch.cuda.is_initialized():
+            raise RuntimeError("AccelRLSync/AccelRLAsync fork their per-GPU runners: build and train the runner before this "
+                               "process initialises CUDA, or launch one process per GPU with torch.distributed.run")
+        if self._base_seed is None:
+            self._base_seed = make_seed()                     # one base seed for all ranks (multigpu_rl_base.py:22-23)
+        port = _free_port()
+        ctx = mp.get_context("fork")
+        self.worker_procs = [ctx.Process(target=self._worker_main, args=(rank, n, port)) for rank in range(1, n)]
+        for w in self.worker_procs:
+            w.start()
+        self._join_group(0, n, port)
+
+    def _join_group(self, rank, n, port):
+        backend = os.environ.get("ACCELRL_DIST_BACKEND", "nccl")
+        dist.init_process_group(backend, init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=n)
+        self._own_group = True
+        self.rank, self.n_runners = rank, n
+        self.affinities = self.all_affinities[rank]
+
+    def _worker_main(self, rank, n, port):
+        """a forked runner of rank >= 1 (the reference's WorkerCls.train, multigpu_rl_base.py:77-108)"""
+        code = 0
+        try:
+            self.worker_procs = []
+            self._join_group(rank, n, port)
+            self.train()
+        except BaseException:
+            traceback.print_exc()
+            code = 1
+        finally:
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(code)                                    # no atexit handlers of the parent's state in a forked child
+
+    def shutdown(self):
+        super().shutdown()
+        if self._own_group:
+            dist.barrier()
+            dist.destroy_process_group()
+            self._own_group = False
+        for w in self.worker_procs:
+            w.join(60)
+        bad = [w.exitcode for w in self.worker_procs if w.exitcode != 0]
+        self.worker_procs = []
+        if bad:
+            raise RuntimeError("worker runners exited with %s" % bad)
 
     def startup(self, master=True):
+        self.launch_workers()
         if self._base_seed is not None:
             self.seed = self._base_seed + 100 * self.rank
         n_itr = super().startup(master=True)

@@ -659,7 +659,8 @@ def run_frame_sweep(args):
     torch.cuda.set_device(0)
     pk = peaks()
     out = {"metric": "frame-kernel achieved HBM GB/s", "unit": "GB/s", "peak": pk["hbm"], "peak_source": pk["src"],
-           "bytes_per_env_step": {"reference_mode": 75520, "north_star_rgb_mode": 208656}, "sweep": [], "rgb_sweep": []}
+           "bytes_per_env_step": {"reference_mode": 75520, "north_star_rgb_mode": 208656}, "game": args.game,
+           "sweep": [], "rgb_sweep": []}
     for B in (256, 512, 1024, 2048, 4096):
         a = argparse.Namespace(**vars(args))
         a.envs, a.horizon, a.minibatch, a.epochs = B, 2, 512, 1

@@ -189,3 +189,28 @@ def test_async_runner_host_logic_two_ranks():
     assert ("async_init", 0, 2, 3) in r0["calls"] and ("async_init", 1, 2, 3) in r1["calls"]
     assert ("pack",) in r1["calls"]
     assert (r0["regions"], r1["rank"], r1["n"]) == (148, 1, 2)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_one_script_launch_forks_and_joins_the_ranks(world):
+    """AccelRLSync.launch_workers (reference runners/multigpu_rl_base.py:20-45): one plain python process forks ranks 1..,
+    all join one group over 127.0.0.1; rank r gets affinities[r] and seed base + 100 r (one base seed for all, drawn by the
+    master when none is given); a failing forked runner takes the job down (tests/launch_stub.py, gloo)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "launch_stub.py"), str(world)], capture_output=True,
+                       text=True, timeout=300, cwd=root)
+    line = [l for l in r.stdout.splitlines() if l.startswith("LAUNCH ")]
+    assert r.returncode == 0 and len(line) == 1, r.stdout[-2000:] + r.stderr[-2000:]
+    out = json.loads(line[0][len("LAUNCH "):])
+    assert out["world"] == world and out["total"] == world * (world + 1) / 2 and out["exit"] == [0] * (world - 1)
+    base = out["seeds"][0][0]
+    assert [tuple(s) for s in out["seeds"]] == [(base + 100 * k, k) for k in range(world)]
+    if world == 2:
+        assert base == 7
+        r = subprocess.run([sys.executable, os.path.join(root, "tests", "launch_stub.py"), "2", "1"], capture_output=True,
+                           text=True, timeout=300, cwd=root)
+        # the forked runner reports its exception and dies; the master's next collective fails instead of hanging
+        assert r.returncode != 0 and "injected failure" in r.stderr and "LAUNCH " not in r.stdout

@@ -31,3 +31,33 @@ def test_sync_allreduce_adam_n_gpus(world):
     # small tensors) and the monolithic all-reduce + update kernel produce bit-identical parameters
     assert res["1"]["params"] == res["0"]["params"]
     np.testing.assert_allclose(res["1"]["norms"], res["0"]["norms"], rtol=2e-6)
+
+
+def _selflaunch(mode, world, torchrun):
+    import json
+    script = os.path.join(ROOT, "tests", "selflaunch_worker.py")
+    if torchrun:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world, "--master-addr",
+               "127.0.0.1", "--master-port", str(29590 + world), script, mode, str(world)]
+    else:
+        cmd = [sys.executable, script, mode, str(world)]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT")}
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("SELFLAUNCH_DIGEST ")]
+    assert r.returncode == 0 and len(lines) == 1, r.stdout[-3000:] + r.stderr[-3000:]
+    return json.loads(lines[0][len("SELFLAUNCH_DIGEST "):])
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_one_script_launch_trains_like_torchrun(world):
+    """AccelRLSync(affinities=[gpu 0, gpu 1, ...]).train() from ONE plain python process forks its per-GPU runners
+    (runners/multigpu_rl_base.py:20-45) and ends with the same parameters, bit for bit, as the same script launched one
+    process per GPU by torch.distributed.run; AccelRLAsync launches the same way (its result depends on learner timing,
+    so it is only required to finish with finite parameters)."""
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    own = _selflaunch("sync", world, torchrun=False)
+    tr = _selflaunch("sync", world, torchrun=True)
+    assert own["n_itr"] == tr["n_itr"] == 3 and not own["torchrun"] and tr["torchrun"]
+    assert own["params"] == tr["params"]
+    _selflaunch("async", world, torchrun=False)
