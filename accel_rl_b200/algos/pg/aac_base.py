@@ -104,6 +104,24 @@ class AdvActorCriticBase(RLAlgorithm):
             self.optimizer.set_lr_mult(self._lr_mult)
         return opt_input_values
 
+    def constraint_values(self, samples_data, opt_data=None):
+        """(pi_kl, v_kl) of aac_base.py:68-70 — mean KL(old policy || current policy) and mean squared change of the value
+        over the rollout rows (valids-weighted when the validity mask is in use).  The reference hands these two
+        expressions to its optimizers, none of which compiles them (optimizers/single/ppo_optimizer.py:30-58 ignores
+        `constraints`); here they are a diagnostic evaluated on demand: one forward pass of the current parameters over
+        the rollout's observations, the two means taken where the rows are (HBM)."""
+        agent_infos = samples_data["agent_infos"]
+        new = self.policy.dist_info_value(samples_data["observations"])
+        p, q = agent_infos["prob"], new["prob"]
+        tiny = 1e-8                                                   # distributions/categorical.py:6
+        kl = (p * (torch.log(p + tiny) - torch.log(q + tiny))).sum(dim=-1)
+        dv = (new["value"] - agent_infos["value"]) ** 2
+        if self._use_valids:
+            valids = (self._opt_buf if opt_data is None else opt_data)["valids"].to(kl.dtype)
+            n = valids.sum()
+            return float((kl * valids).sum() / n), float((dv * valids).sum() / n)
+        return float(kl.mean()), float(dv.mean())
+
     @property
     def opt_info_keys(self):
         return ["GradNorm"]

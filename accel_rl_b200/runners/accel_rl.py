@@ -38,12 +38,27 @@ class _EntropyEma(object):
 
     def __init__(self, ema_steps, sample_size):
         self.a = 1 - 0.01 ** (ema_steps / sample_size)
-        self.entropy = 1.
-        self.perplexity = 1.
+        self._state = [1., 1.]            # entropy, perplexity; becomes a 2-element device tensor on the first device update
 
     def update(self, entropies):
-        self.entropy += self.a * (np.mean(entropies) - self.entropy)
-        self.perplexity += self.a * (np.mean(np.exp(entropies)) - self.perplexity)
+        self._fold(np.mean(entropies), np.mean(np.exp(entropies)))
+
+    def update_from_probs(self, prob):
+        """every iteration, like the reference — from the rollout's probabilities where they already are (HBM): the two
+        means and the EMA stay on the device, nothing is copied to the host until a log line reads them"""
+        import torch
+        ent = -(prob * torch.log(prob + 1e-8)).sum(dim=1)           # distributions/categorical.py TINY
+        cur = torch.stack((ent.mean(), ent.exp().mean())).double()
+        if not torch.is_tensor(self._state):
+            self._state = torch.tensor(self._state, dtype=torch.float64, device=prob.device)
+        self._state = self._state + self.a * (cur - self._state)
+
+    def _fold(self, entropy, perplexity):
+        e, p = self.entropy, self.perplexity
+        self._state = [e + self.a * (entropy - e), p + self.a * (perplexity - p)]
+
+    entropy = property(lambda self: float(self._state[0]))
+    perplexity = property(lambda self: float(self._state[1]))
 
 
 class _TrainLoop(AccelRLBase):
@@ -101,10 +116,13 @@ class AccelRL(_TrainLoop):
         self._cum_completed_steps += sum(info["Length"] for info in traj_infos)
         self._traj_infos.extend(traj_infos)
         self._store_opt_infos(opt_infos)
-        # the reference folds every iteration's rollout entropy into the EMA (accel_rl.py:65-72); here only logging
-        # iterations do, which saves a device-to-host copy of the probabilities per iteration
-        if self._ema is not None and self._logging_itr(itr):
-            self._ema.update(self.policy.distribution.entropy(samples_data.agent_infos))
+        # every iteration's rollout entropy is folded into the EMA (accel_rl.py:65-72)
+        if self._ema is not None:
+            prob = samples_data.agent_infos["prob"]
+            if hasattr(prob, "is_cuda"):
+                self._ema.update_from_probs(prob)
+            else:
+                self._ema.update(self.policy.distribution.entropy(samples_data.agent_infos))
 
     def after_itr(self, itr):
         if self._logging_itr(itr):

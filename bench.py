@@ -38,7 +38,7 @@ FLOP_PER_ENV_STEP_CONV = 265.7e6    # conv tiles only: the nort
 
 def ncu_traffic(label):
     """DRAM bytes per launch of `label` from the committed ncu --set full capture (None when not captured)"""
-    for name in ("r1e_traffic.json", "r1c_traffic.json"):
+    for name in ("r2_traffic.json", "r1e_traffic.json"):
         try:
             return json.load(open(os.path.join(ROOT, "profiles", name)))["kernels"].get(label)
         except Exception:
@@ -288,10 +288,12 @@ def kernel_breakdown(runner, args):
     import torch
     eng = runner.policy.engine
     N = args.envs * args.horizon
-    n_mb = (N // args.minibatch) * args.epochs
-    idx = torch.randperm(N, device="cuda")[:8 * args.minibatch].to(torch.int32).contiguous()
+    a2c = getattr(args, "algo", "ppo") == "a2c"
+    mb = N if a2c else args.minibatch                   # A2C: one full-batch step per iteration
+    n_mb = 1 if a2c else (N // args.minibatch) * args.epochs
+    idx = torch.randperm(N, device="cuda")[:8 * mb].to(torch.int32).contiguous()
     out = {}
-    labels, ms = eng.profile_graph(0, idx, args.minibatch, reps=24)
+    labels, ms = eng.profile_graph(0, idx, mb, reps=24)
     for l, t in zip(labels, ms):
         prev = out.get(l, (0.0, n_mb))
         out[l] = (prev[0] + float(t), n_mb)
@@ -490,34 +492,53 @@ def run_ours(args):
     if args.parallelism == "async":
         parity = async_parity(runner, rank, world)
     if rank == 0:
-        bd = kernel_breakdown(runner, args) if (args.spec == 1 and world == 1 and args.algo == "ppo" and
-                                                args.parallelism == "sync") else {}
+        # (per-kernel timing replays single kernels of THIS rank's context after everything else was measured and
+        # checked; under the asynchronous learner the update is a cross-GPU kernel and is left out)
+        bd = kernel_breakdown(runner, args) if (args.spec == 1 and args.parallelism == "sync") else {}
         # dominant kernel by time per PPO iteration
         roof = None
         kernels = []
         total_ms = sum(t * c for t, c in bd.values())
         for label, (t, count) in sorted(bd.items(), key=lambda kv: -kv[1][0] * kv[1][1]):
-            n = args.envs if label.startswith("rollout/") else args.minibatch
+            n = args.envs if label.startswith("rollout/") else (N if args.algo == "a2c" else args.minibatch)
             fl = kernel_flops(label, n, args)
             kernels.append({"kernel": label, "ms": round(t, 5), "launches_per_step": count,
                             "share": round(t * count / total_ms, 4) if total_ms else None,
                             "tflops": round(fl / (t * 1e-3) / 1e12, 2) if fl else None})
+        # `roofline`: the kernel with the largest share of the step.  GEMM kernels are held against the tensor peak
+        # (flops = 2 * MACs of the launch); the update kernel against HBM with its algorithmic 28 B per parameter (read p,
+        # m, v, g; write p, m, v — DESIGN.md §3).  `roofline_tensor`: the largest GEMM kernel, when that is not the same.
+        roof_tensor = None
+        traffic_note = "DRAM bytes per launch (read + write), ncu --set full with cold caches (profiles/r2_full.md)"
+        if kernels and kernels[0]["kernel"] == "clip_update":
+            k = kernels[0]
+            nbytes = 28.0 * runner.policy.engine.n_params
+            gbs = nbytes / (k["ms"] * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": "clip_update", "achieved": round(gbs, 1), "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": round(gbs / pk["hbm"], 4), "traffic": ncu_traffic("clip_update"), "traffic_note": traffic_note,
+                    "algorithmic_bytes_per_launch": nbytes,
+                    "peak_source": pk["src"] + " (copy bandwidth; the kernel is timed alone, its 58 MB of optimiser state "
+                                               "and parameters partly stay in the 126 MB L2 between launches)",
+                    "share_of_step": k["share"]}
         for k in kernels:
             if k["tflops"] is not None:
-                roof = {"bound": "tensor", "kernel": k["kernel"], "achieved": k["tflops"], "peak": pk["tf_sustained"],
+                roof_tensor = {"bound": "tensor", "kernel": k["kernel"], "achieved": k["tflops"], "peak": pk["tf_sustained"],
                         "unit": "TFLOP/s", "frac": round(k["tflops"] / pk["tf_sustained"], 4),
                         "traffic": ncu_traffic(k["kernel"]),
-                        "traffic_note": "DRAM bytes per launch, ncu --set full with cold caches (profiles/r1e_full.md)",
+                        "traffic_note": traffic_note,
                         "peak_source": pk["src"] + " (sustained bf16, kernel timed inside a long step)",
                         "share_of_step": k["share"]}
+                roof_t = roof_tensor
                 if k["kernel"] in ("conv1_wgrad", "conv2_wgrad"):
                     # these two kernels are launched on a capped grid so the data-gradient chain runs beside them
                     # (csrc/api.cu: wgrad_ctas, ARL_WGRAD_CTAS); `achieved` is the whole-GPU figure of that launch
                     ctas = int(os.environ.get("ARL_WGRAD_CTAS", "48"))
-                    roof["note"] = ("launched on %d of 148 SMs by design, concurrent with the data-gradient kernels: %.0f TFLOP/s "
-                                    "per occupied-SM share; tensor pipe 34-37 %% active in profiles/r1e_full.md"
-                                    % (ctas, k["tflops"] * 148.0 / ctas))
+                    roof_t["note"] = ("launched on %d of 148 SMs by design, concurrent with the data-gradient kernels: %.0f TFLOP/s "
+                                      "per occupied-SM share; tensor pipe 41-51 %% active in profiles/r2_full.md"
+                                      % (ctas, k["tflops"] * 148.0 / ctas))
                 break
+        if roof is None:
+            roof, roof_tensor = roof_tensor, None
         # per-env-step model FLOPs: PPO = fwd + fwd/T + epochs*train; A2C = fwd + fwd/T + train
         fwd, train, cfwd, ctrain = FLOPS[args.frames]
         rgb = args.frames == "rgb"
@@ -537,6 +558,7 @@ def run_ours(args):
             if flop_step else None,
             "conv_tile_roofline_frac": round(value / world * flop_conv / (pk["tf_sustained"] * 1e12), 4) if flop_conv else None,
             "roofline": roof,
+            "roofline_tensor": roof_tensor,
             "kernels": kernels[:16],
             "host_wall_s": round(wall, 3),
             "phases": phases,

@@ -555,9 +555,20 @@ def test_operand_copies_refreshed_by_the_update_match_a_fresh_pack():
     algo.set_n_itr(10)
     try:
         buf, _ = sampler.obtain_samples(0)
+        kl0, dv0 = algo.constraint_values(buf)               # aac_base.py:68-70 before the update: old == new policy
+        assert abs(kl0) < 1e-6 and dv0 < 1e-10
         algo.optimize_policy(0, buf)
         trained = pol.get_param_values()
         assert not np.array_equal(trained, flat)
+        # ... and after it: against the oracle net with the trained parameters on the same rows
+        kl1, dv1 = algo.constraint_values(buf)
+        b = _buf_np(buf)
+        p_new, v_new = onet.forward(torch.tensor(trained), torch.tensor(b["observations"]), spec, 4, emulate_bf16=True)
+        p_old = b["prob"].astype(np.float64)
+        want_kl = float(np.mean(np.sum(p_old * (np.log(p_old + 1e-8) - np.log(p_new.numpy().astype(np.float64) + 1e-8)), axis=1)))
+        want_dv = float(np.mean((v_new.numpy().astype(np.float64) - b["value"]) ** 2))
+        assert kl1 > 0 and abs(kl1 - want_kl) <= 2e-2 * want_kl + 1e-7, (kl1, want_kl)
+        assert abs(dv1 - want_dv) <= 2e-2 * want_dv + 1e-9, (dv1, want_dv)
         obs = torch.tensor(res_obs).cuda()
         p1 = torch.zeros(64, 4, device="cuda"); v1 = torch.zeros(64, device="cuda")
         pol.engine.forward(obs, prob=p1, value=v1)

@@ -207,3 +207,28 @@ def test_bench_host_worker_count_divides_the_envs():
     for envs in (256, 64, 48):
         w = bench.host_workers(argparse.Namespace(envs=envs))
         assert w >= 2 and envs % w == 0 and w <= max(2, (os.cpu_count() or 2))
+
+
+def test_entropy_ema_every_iteration_device_and_host_forms_agree():
+    """runners/accel_rl.py:46-49,65-72: a = 1 - 0.01 ** (ema_steps / sample_size); every iteration
+    ema <- a * mean + (1 - a) * ema, for the entropy and for exp(entropy), both starting at 1.  The runner's on-device
+    form (from the rollout's probability tensor) equals the host form on the same probabilities."""
+    import torch
+    from accel_rl_b200.distributions.categorical import Categorical
+    from accel_rl_b200.runners.accel_rl import _EntropyEma
+    rng = np.random.RandomState(0)
+    host, dev = _EntropyEma(1000, 256), _EntropyEma(1000, 256)
+    a = 1 - 0.01 ** (1000 / 256)
+    assert host.a == a
+    want_e = want_p = 1.0
+    dist = Categorical(6)
+    for _ in range(5):
+        logits = rng.randn(256, 6).astype(np.float32)
+        prob = np.exp(logits) / np.exp(logits).sum(1, keepdims=True)
+        ent = dist.entropy(dict(prob=prob))
+        host.update(ent)
+        dev.update_from_probs(torch.from_numpy(prob))
+        want_e = a * float(np.mean(ent)) + (1 - a) * want_e
+        want_p = a * float(np.mean(np.exp(ent))) + (1 - a) * want_p
+    assert abs(host.entropy - want_e) < 1e-7 and abs(host.perplexity - want_p) < 1e-7   # (float32 means)
+    assert abs(dev.entropy - want_e) < 1e-5 and abs(dev.perplexity - want_p) < 1e-5
