@@ -165,6 +165,10 @@ struct arl_ctx {
   bool pending_stream = false;         // ... and the folding kernel is update_stream_kernel (no clipping: no barrier)
   cudaEvent_t ev_fcd = nullptr;        // "FC data gradient has read the FC weights"
   unsigned long long* ticket = nullptr; // grid-barrier ticket of update_fused_kernel
+  // split update (clip_update, ARL_SPLIT_UPDATE): the FC range's step runs on `side` beside the next minibatch's conv layers
+  cudaEvent_t ev_upd_fork = nullptr, ev_updB = nullptr;
+  bool split_capture = false;           // inside train_minibatches' graph capture with the local update
+  bool updB_pending = false;            // the next FC forward (or the end of the capture) joins ev_updB
   float* hyper = nullptr;          // [0] lr_mult
   int* step = nullptr;             // Adam t
   int* log_slot = nullptr;
@@ -1168,6 +1172,11 @@ int forward_trunk(arl_ctx* c, const __nv_bfloat16* obs16, const int* idx, const 
     if (launch_conv_persist_bn(c, L.Cout, mp, 1, L.K, mp.mtiles[0], st)) return 1;
     prof_mark(c, kFwdName[l], st);
   }
+  if (c->updB_pending) {
+    // the previous minibatch's FC-range update (side stream) must be complete before the FC weights are read
+    ARL_CHECK(c, cudaStreamWaitEvent(st, c->ev_updB, 0));
+    c->updB_pending = false;
+  }
   if (pc && fc_tiles_ok(c)) {
     if (fc_forward_tiles(c, n, fc_S, st)) return 1;
     prof_mark(c, "fc_fwd", st);
@@ -1653,7 +1662,24 @@ int clip_update(arl_ctx* c, float gscale, cudaStream_t st) {
     }
     if (nA + nA2 + nB > kStreamPartials) ARL_FAIL(c, "update_stream: partial buffer too small");
     u.adv_done = c->ticket + 2;                 // (its own arrival counter: the grid size differs from update_fused_kernel's)
-    ARL_CHECK(c, launch_k(update_stream_kernel, dim3(nA + nA2 + nB), dim3(256), 0, st, u, c->sumsq_partial, nA, nA2, P_total));
+    const int G = nA + nA2 + nB;
+    if (c->split_capture && c->side && c->ev_updB && nB > 0 && nA + nA2 > 0 && st != c->side) {
+      // two grids over the same block index space: the FC range (98 % of the bytes) on the side stream, joined by the
+      // next FC forward (forward_trunk) or the end of the capture; everything the next conv layers read on `st`
+      ARL_CHECK(c, cudaEventRecord(c->ev_upd_fork, st));
+      ARL_CHECK(c, cudaStreamWaitEvent(c->side, c->ev_upd_fork, 0));
+      ARL_CHECK(c, launch_k(update_stream_kernel, dim3(nB), dim3(256), 0, c->side, u, c->sumsq_partial, nA, nA2, P_total, nA + nA2, G,
+                            (unsigned long long*)nullptr, 0));
+      ARL_CHECK(c, cudaEventRecord(c->ev_updB, c->side));
+      ARL_CHECK(c, launch_k(update_stream_kernel, dim3(nA + nA2), dim3(256), 0, st, u, c->sumsq_partial, nA, nA2, P_total, 0, G,
+                            c->ticket + 3, 0));
+      c->updB_pending = true;
+      c->launches += 2;
+      ARL_CHECK(c, cudaGetLastError());
+      return 0;
+    }
+    ARL_CHECK(c, launch_k(update_stream_kernel, dim3(G), dim3(256), 0, st, u, c->sumsq_partial, nA, nA2, P_total, 0, G,
+                          (unsigned long long*)nullptr, 1));
     c->launches++;
     prof_mark(c, "clip_update", st);
     ARL_CHECK(c, cudaGetLastError());
@@ -1890,6 +1916,8 @@ void arl_destroy(arl_ctx* c) {
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->ev_join2) cudaEventDestroy(c->ev_join2);
   if (c->ev_fcd) cudaEventDestroy(c->ev_fcd);
+  if (c->ev_upd_fork) cudaEventDestroy(c->ev_upd_fork);
+  if (c->ev_updB) cudaEventDestroy(c->ev_updB);
   for (auto& e : c->ev_fin) if (e) cudaEventDestroy(e);
   for (auto& e : c->ev_cs_in) if (e) cudaEventDestroy(e);
   if (c->ev_cs_done) cudaEventDestroy(c->ev_cs_done);
@@ -2305,11 +2333,27 @@ int train_minibatches(arl_ctx* c, const int* idx, int mb_size, int count, int sy
     ARL_CHECK(c, create_main_stream(&cap));
     long l0 = c->launches;
     cudaGraph_t g = nullptr;
+    // ARL_SPLIT_UPDATE=1 (off by default): the FC range's update on the side stream, beside the next minibatch's conv
+    // layers.  Bit-identical results (tests/test_gpu_path.py), measured SLOWER on B200: 43.96 vs 43.20 ms per 256
+    // minibatches — the conv tiles lose more to the shared memory system than the hidden 20 us are worth
+    static const bool split_on = getenv("ARL_SPLIT_UPDATE") && atoi(getenv("ARL_SPLIT_UPDATE")) != 0;
+    if (split_on && sync == 0 && !c->ev_updB) {
+      ARL_CHECK(c, cudaEventCreateWithFlags(&c->ev_upd_fork, cudaEventDisableTiming));
+      ARL_CHECK(c, cudaEventCreateWithFlags(&c->ev_updB, cudaEventDisableTiming));
+    }
+    ARL_CHECK(c, cudaMemsetAsync(c->ticket + 2, 0, 2 * sizeof(unsigned long long), st));
+    ARL_CHECK(c, cudaStreamSynchronize(st));
     ARL_CHECK(c, cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
     int rc = 0;
+    c->split_capture = split_on && sync == 0;
     for (int k = 0; k < per && !rc; ++k) {
       rc = grad_minibatch(c, idx, c->mb_counter, mb_size, cap);
       if (!rc) rc = step(cap);
+    }
+    c->split_capture = false;
+    if (c->updB_pending) {
+      cudaStreamWaitEvent(cap, c->ev_updB, 0);
+      c->updB_pending = false;
     }
     cudaError_t ce = cudaStreamEndCapture(cap, &g);
     c->graph_train_nodes = c->launches - l0;

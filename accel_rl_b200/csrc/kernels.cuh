@@ -1527,8 +1527,14 @@ ARL_DEVINL void update_scalar(const UpdateParams& p, long i, float g, float alph
   }
 }
 
+// Split form (api.cu clip_update, ARL_SPLIT_UPDATE): the same block index space launched as TWO grids — parts A/A2 on the
+// main stream (blk0 = 0), part B on a forked stream (blk0 = nA + nA2) so that the FC range, 98 % of the bytes, streams
+// beside the NEXT minibatch's conv layers, which do not read it.  grid_total = blocks of both launches (the ticket of the
+// logs); mb_ticket != nullptr: the minibatch cursor — what the next forward pass reads — is advanced by the last block of
+// the launch that carries it (the main-stream one), not by the overall last block.
 __global__ void __launch_bounds__(256, 4) update_stream_kernel(UpdateParams p, double* __restrict__ partial, int nA,
-                                                              int nA2, long total_all) {
+                                                              int nA2, long total_all, int blk0, int grid_total,
+                                                              unsigned long long* mb_ticket, int advance_mb) {
   pdl_wait();
   pdl_trigger();
   __shared__ float s_alpha;
@@ -1538,14 +1544,15 @@ __global__ void __launch_bounds__(256, 4) update_stream_kernel(UpdateParams p, d
   __syncthreads();
   const float alpha = s_alpha;
   double acc = 0.0;
-  if ((int)blockIdx.x < nA) {
+  const int vb = (int)blockIdx.x + blk0;          // block index in the joint index space
+  if (vb < nA) {
     // part A (blocks [0, nA): scheduled first): 64 elements per block, a team of four lanes per element (finalize_sum4),
     // elements numbered through the concatenated job index space.  A separate set of blocks from part B: the partial sums are
     // 48..148 dependent-latency loads per element — ncu (profiles/r2_update_stream.md) showed warps that carried both
     // parts holding their whole block at the final barrier for 40 % of the kernel
     float* grad = const_cast<float*>(p.grad);
     const int lane = threadIdx.x & 31, q = lane >> 3;
-    long v = (long)blockIdx.x * kFinPerBlock + (threadIdx.x >> 5) * 8 + (lane & 7);
+    long v = (long)vb * kFinPerBlock + (threadIdx.x >> 5) * 8 + (lane & 7);
     int jn = 0;
     if (v < total_all) {
       for (; jn < p.n_fin_jobs; ++jn) {
@@ -1564,9 +1571,9 @@ __global__ void __launch_bounds__(256, 4) update_stream_kernel(UpdateParams p, d
       acc += (double)(g * g);
       update_scalar(p, dst, g, alpha);
     }
-  } else if ((int)blockIdx.x < nA + nA2) {
+  } else if (vb < nA + nA2) {
     // part A2: small tensors whose gradient is already in the flat vector
-    const long j = (long)((int)blockIdx.x - nA) * blockDim.x + threadIdx.x;
+    const long j = (long)(vb - nA) * blockDim.x + threadIdx.x;
     const long len0 = p.a2_mid - p.a2_begin;
     const long i = j < len0 ? p.a2_begin + j : p.a2_resume + (j - len0);
     if (i < p.n) {
@@ -1577,7 +1584,7 @@ __global__ void __launch_bounds__(256, 4) update_stream_kernel(UpdateParams p, d
   } else {
     // part B: the FC weights
     const int nAA = nA + nA2;
-    const long gtid = (long)((int)blockIdx.x - nAA) * blockDim.x + threadIdx.x, gsize = (long)((int)gridDim.x - nAA) * blockDim.x;
+    const long gtid = (long)(vb - nAA) * blockDim.x + threadIdx.x, gsize = (long)(grid_total - nAA) * blockDim.x;
     const float4* g4p = reinterpret_cast<const float4*>(p.grad) + p.fc4_begin;
     for (long j = gtid; j < p.fc4_len; j += gsize) {
       const float4 g4 = g4p[j];
@@ -1591,17 +1598,22 @@ __global__ void __launch_bounds__(256, 4) update_stream_kernel(UpdateParams p, d
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int w = 0; w < 8; ++w) t += s_red[w];
-    partial[blockIdx.x] = t;
+    partial[vb] = t;
     __threadfence();
+    if (mb_ticket) {
+      // (the cursor first: a block that is last in both senses must not log before it advanced it — harmless either way)
+      const unsigned long long tm = atomicAdd(mb_ticket, 1ULL);
+      if ((tm + 1ULL) % gridDim.x == 0ULL) p.adv_mb[0] += 1;
+    }
     const unsigned long long tk = atomicAdd(p.adv_done, 1ULL);
-    s_last = ((tk + 1ULL) % gridDim.x == 0ULL) ? 1 : 0;
+    s_last = ((tk + 1ULL) % (unsigned long long)grid_total == 0ULL) ? 1 : 0;
   }
   __syncthreads();
   if (!s_last) return;
   // last block: every other block has published its partial and read the update count / log slot
   __threadfence();
   double a2 = 0.0;
-  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) a2 += __ldcg(partial + i);
+  for (int i = threadIdx.x; i < grid_total; i += blockDim.x) a2 += __ldcg(partial + i);
   for (int i = threadIdx.x; i < p.n_partial2; i += blockDim.x) a2 += __ldcg(p.sumsq_partial2 + i);   // early FC update's share
   a2 = warp_sum_d(a2);
   float l = 0.f;
@@ -1617,7 +1629,8 @@ __global__ void __launch_bounds__(256, 4) update_stream_kernel(UpdateParams p, d
     for (int w = 0; w < 8; ++w) { t += s_red[w]; tl += s_l[w]; }
     const int slot = p.log_slot[0];
     if (slot < p.log_cap) { p.out_norm[slot] = (float)sqrt(t); p.out_loss[slot] = tl; }
-    p.step[0] += 1; p.adv_log_slot[0] += 1; p.adv_mb[0] += 1;
+    p.step[0] += 1; p.adv_log_slot[0] += 1;
+    if (advance_mb) p.adv_mb[0] += 1;
   }
 }
 

@@ -495,6 +495,10 @@ def run_ours(args):
         # (per-kernel timing replays single kernels of THIS rank's context after everything else was measured and
         # checked; under the asynchronous learner the update is a cross-GPU kernel and is left out)
         bd = kernel_breakdown(runner, args) if (args.spec == 1 and args.parallelism == "sync") else {}
+        if world > 1:
+            # the synchronous learner's update is the cross-GPU pair sync_fc_kernel / sync_tail_kernel (csrc/comm.cuh),
+            # timed on the device in `sync_timeline`; the local update kernel is not on this path
+            bd.pop("clip_update", None)
         # dominant kernel by time per PPO iteration
         roof = None
         kernels = []

@@ -638,11 +638,14 @@ def _ab_worker(env_over):
 def test_stream_update_and_iteration_graph_are_bit_identical():
     """Round-2 training path (update_stream_kernel: finalisation + Adam + operand refresh + logs in one launch without
     a grid barrier; ONE CUDA graph holding every minibatch of the optimize() call) against the round-1 path
-    (finalize_grads -> update_fused with barrier, one graph launch per minibatch): same per-element arithmetic, so the
+    (finalize_grads -> update_fused with barrier, one graph launch per minibatch), and with the update split over two
+    streams (ARL_SPLIT_UPDATE) or not: same per-element arithmetic, so the
     parameters and optimizer state after two PPO iterations are bit-identical; the logged norms agree to fp32 rounding
     (block partials are grouped differently)."""
     old = _ab_worker(dict(ARL_STREAM_UPDATE="0", ARL_GRAPH_MB="1"))
-    for over in (dict(), dict(ARL_STREAM_UPDATE="1", ARL_GRAPH_MB="1"), dict(ARL_STREAM_UPDATE="0", ARL_GRAPH_MB="512")):
+    # ARL_SPLIT_UPDATE=1: the stream update as two grids (the FC range on a side stream beside the next minibatch's conv layers)
+    for over in (dict(), dict(ARL_SPLIT_UPDATE="1"), dict(ARL_STREAM_UPDATE="1", ARL_GRAPH_MB="1"),
+                 dict(ARL_STREAM_UPDATE="0", ARL_GRAPH_MB="512")):
         new = _ab_worker(over)
         assert old["device_error"] == 0 and new["device_error"] == 0
         assert old["step"] == new["step"] == 2 * 2 * 4
