@@ -45,6 +45,7 @@ class OptCfg(C.Structure):
         ("epsilon", C.c_float),
         ("rho", C.c_float),
         ("grad_norm_clip", C.c_float),
+        ("ppo_tie_grad", C.c_int),
     ]
 
 

@@ -56,7 +56,7 @@ class AdvActorCriticBase(RLAlgorithm):
         self.optimizer.initialize(
             inputs=None,
             losses=dict(kind=self.loss_kind, v_loss_coeff=self.v_loss_coeff, ent_loss_coeff=self.ent_loss_coeff,
-                        clip_param=getattr(self, "clip_param", 0.)),
+                        clip_param=getattr(self, "clip_param", 0.), tie_grad=getattr(self, "tie_grad", 1)),
             constraints=None,
             target=policy,
             lr_mult=self._lr_mult,

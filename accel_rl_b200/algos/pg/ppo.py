@@ -20,11 +20,18 @@ class BasePPO(AdvActorCriticBase):
                               update_method=update_methods.adam, update_method_args=dict(epsilon=1e-5),
                               grad_norm_clip=None, shuffle=True)
 
-    def __init__(self, OptimizerCls=None, optimizer_args=None, discount=0.99, gae_lambda=0.95, clip_param=0.2, **kwargs):
+    def __init__(self, OptimizerCls=None, optimizer_args=None, discount=0.99, gae_lambda=0.95, clip_param=0.2, tie_grad=1,
+                 **kwargs):
+        # tie_grad (not a reference argument): inside the clip range the two surrogates of ppo.py:47-49 are exactly equal and
+        # T.minimum's gradient at a tie depends on the Theano version — 1: passed once (Theano >= 0.9, and standard PPO);
+        # 2: to both branches, i.e. twice the policy gradient there (older Theano)
         cls = OptimizerCls if OptimizerCls is not None else self.default_optimizer
         if cls is None:
             raise TypeError("BasePPO needs an OptimizerCls (use PPO, mPPO or mAPPO)")
+        if tie_grad not in (1, 2):
+            raise ValueError("tie_grad must be 1 or 2")
         self.clip_param = clip_param
+        self.tie_grad = tie_grad
         self.optimizer = cls(**with_defaults(optimizer_args, self.optimizer_defaults))
         super().__init__(discount=discount, gae_lambda=gae_lambda, **kwargs)
 

@@ -722,7 +722,9 @@ int pc_wgrad_ctas(arl_ctx* c, int l, int n) {
   const PcLayer& q = c->pc[l];
   int ntiles = (l == 0) ? n * q.tiles_per_img : (int)(((long)n * q.S + 127) / 128);
   if (pconv_bwd_fused_ok(c, l, n, nullptr)) return std::min(ntiles, 148);     // one partial per CTA of pconv_bwd_kernel
-  int cap = (l > 0 && c->wgrad_ctas > 0) ? c->wgrad_ctas : 148;    // layer 0's wgrad runs alone at the end of the chain
+  // layer 0's wgrad closes the main chain; ARL_WGRAD0_CTAS leaves the SMs still held by conv1's weight gradient alone
+  static const int cap0 = getenv("ARL_WGRAD0_CTAS") ? std::max(1, std::min(148, atoi(getenv("ARL_WGRAD0_CTAS")))) : 148;
+  int cap = (l > 0 && c->wgrad_ctas > 0) ? c->wgrad_ctas : (l == 0 ? cap0 : 148);
   return std::min(ntiles, cap);
 }
 
@@ -1357,6 +1359,7 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
   p.idx = idx; p.idx_off = idx_off; p.act_in = c->t_act; p.adv = c->t_adv; p.ret = c->t_ret; p.old_prob = c->t_oldp;
   p.valids = c->t_valids; p.valid_count = c->valid_count;
   p.algo = c->opt.algo; p.clip_param = c->opt.clip_param; p.v_coeff = c->opt.v_loss_coeff;
+  p.tie_grad = c->opt.ppo_tie_grad == 2 ? 2.f : 1.f;
   p.ent_coeff = c->opt.ent_loss_coeff; p.inv_count = 1.f / (float)n;
   p.h_out = c->h; p.dh_out = c->dh; p.dlogit_out = c->dlogit; p.loss_partial = c->loss_partial;
   const bool fct = pcb && fc_tiles_ok(c);
@@ -2010,6 +2013,8 @@ int arl_sampler_configure(arl_ctx* c, const arl_sampler_cfg* cfg) {
   if (c->sampler_set) {
     // re-configuring the selected slot: release what the previous configuration allocated
     if (c->rollout_graph) { cudaGraphExecDestroy(c->rollout_graph); c->rollout_graph = nullptr; }
+    // the training graph has the rollout mirror's address baked in (conv0 gathers from it)
+    if (c->train_graph) { cudaGraphExecDestroy(c->train_graph); c->train_graph = nullptr; }
     cudaFree(c->est.f); cudaFree(c->cmd); cudaFree(c->rows_tab); cudaFree(c->tout.count);
     cudaFree(c->step_obs16); cudaFree(c->roll_obs16);
     c->est = EnvState{}; c->tout = TrajOut{}; c->cmd = nullptr; c->rows_tab = nullptr;
@@ -2288,6 +2293,7 @@ int arl_train_minibatches_async(arl_ctx* c, const int* idx, int mb_size, int cou
 namespace {
 int train_minibatches(arl_ctx* c, const int* idx, int mb_size, int count, int sync, cudaStream_t st) {
   NvtxRange nvtx_("train minibatches");
+  if (count > c->log_cap) ARL_FAIL(c, "more minibatches in one call than loss / grad-norm log slots (4096): read the logs in between");
   // sync: 0 = local clip + update, 1 = synchronous DP step, 2 = asynchronous push/pull
   const bool overlap = sync == 1 && sync_overlap_ok(c);
   if (overlap && sync_overlap_prepare(c)) return 1;

@@ -393,13 +393,6 @@ ARL_DEVINL unsigned long long gtimer_ns() { unsigned long long t; asm volatile("
 //   exchange was over before the tail began, i.e. fully hidden behind the conv gradient chain)   [8] last FC end stamp
 enum { TR_FC_WAIT = 0, TR_FC_WORK = 1, TR_TAIL_WAIT = 2, TR_TAIL_WORK = 3, TR_COUNT = 4, TR_SLACK = 5, TR_FC_END = 8 };
 
-__global__ void sync_signal_kernel(CommDev d, int flag_word) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    __threadfence_system();
-    for (int r = 0; r < d.world; ++r) st_relaxed_sys_add(d.peer_flag[r] + flag_word);
-  }
-}
-
 // one thread: wait until every rank has signalled `flag_word` for the epoch after `epoch_word`
 ARL_DEVINL void sync_wait_flag(const CommDev& d, int flag_word, int epoch_word, int code) {
   const unsigned int ep = reinterpret_cast<volatile unsigned int*>(d.grid_counter)[epoch_word] + 1u;

@@ -765,6 +765,7 @@ struct HeadParams {
   const float* hyper;       // device scalars: [0]=lr_mult (PPO clip scales with it)
   int algo;                 // 0 = PPO, 1 = A2C
   float clip_param, v_coeff, ent_coeff;
+  float tie_grad;           // PPO: gradient multiplier inside the clip range (1, or 2 = both branches of the tied min())
   float inv_count;          // 1/M when valids == nullptr
   const float* valid_count; // device scalar sum(valids) (when valids != nullptr)
   // train outputs
@@ -928,7 +929,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadParams p) {
       float gr;
       if (ratio < lo) gr = (adv >= 0.f) ? adv : 0.f;
       else if (ratio > hi) gr = (adv <= 0.f) ? adv : 0.f;
-      else gr = adv;
+      else gr = adv * p.tie_grad;
       gact = -w * gr / (po + TINY);
     } else {
       l_pi = -logf(pa + TINY) * adv;

@@ -39,7 +39,8 @@ class BaseOptimizer(object):
             learning_rate=float(self._learning_rate),
             beta1=float(args.get("beta1", 0.9)), beta2=float(args.get("beta2", 0.999)),
             epsilon=float(args["epsilon"]), rho=float(args.get("rho", 0.9)),
-            grad_norm_clip=float(clip) if clip is not None else -1.0)
+            grad_norm_clip=float(clip) if clip is not None else -1.0,
+            ppo_tie_grad=int(losses.get("tie_grad", 1)))
         self._engine.reset_opt_state()
         self.set_lr_mult(lr_mult)
 

@@ -14,14 +14,18 @@ _csv_path = None
 _csv_header = None
 _snapshot_dir = None
 _snapshot_mode = "none"
+_snapshot_gap = 1
 _quiet = False
 last_row = {}
 
 
-def configure(log_dir=None, snapshot_mode="none", quiet=False):
-    global _csv_path, _csv_header, _snapshot_dir, _snapshot_mode, _quiet
+def configure(log_dir=None, snapshot_mode="none", quiet=False, snapshot_gap=1):
+    global _csv_path, _csv_header, _snapshot_dir, _snapshot_mode, _quiet, _snapshot_gap
+    if snapshot_mode not in ("all", "last", "gap", "none"):
+        raise NotImplementedError("snapshot_mode must be one of all / last / gap / none")
     _quiet = quiet
     _snapshot_mode = snapshot_mode
+    _snapshot_gap = max(1, int(snapshot_gap))
     _csv_header = None
     if log_dir is not None:
         os.makedirs(log_dir, exist_ok=True)
@@ -97,6 +101,10 @@ def save_itr_params(itr, params):
         path = os.path.join(_snapshot_dir, "itr_%d.pkl" % itr)
     elif _snapshot_mode == "last":
         path = os.path.join(_snapshot_dir, "params.pkl")
+    elif _snapshot_mode == "gap":                           # every snapshot_gap-th iteration, and the first
+        if not (itr == 0 or (itr + 1) % _snapshot_gap == 0):
+            return
+        path = os.path.join(_snapshot_dir, "itr_%d.pkl" % itr)
     else:
         return
     joblib.dump(params, path, compress=3)

@@ -7,9 +7,9 @@ from accel_rl_b200.util import logger
 
 
 @contextmanager
-def logger_context(log_dir, run_ID=0, name="run", log_params=None, snapshot_mode="none"):
+def logger_context(log_dir, run_ID=0, name="run", log_params=None, snapshot_mode="none", snapshot_gap=1):
     exp_dir = os.path.join(log_dir, "%s_%s" % (name, run_ID))
-    logger.configure(exp_dir, snapshot_mode=snapshot_mode)
+    logger.configure(exp_dir, snapshot_mode=snapshot_mode, snapshot_gap=snapshot_gap)
     if log_params is not None:
         os.makedirs(exp_dir, exist_ok=True)
         with open(os.path.join(exp_dir, "params.json"), "w") as f:

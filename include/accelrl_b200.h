@@ -43,6 +43,9 @@ typedef struct {
   int update;              /* 0 = adam, 1 = rmsprop (optimizers/update_methods_stats.py) */
   float learning_rate, beta1, beta2, epsilon, rho;
   float grad_norm_clip;    /* <= 0: None (norm is still reported) */
+  int ppo_tie_grad;        /* 0 or 1: inside the clip range, where surr_1 == surr_2 exactly, min() passes the gradient once
+                              (Theano >= 0.9 `Minimum.L_op`: "gx will be gz, gy will be 0", and standard PPO);
+                              2: to both branches, i.e. twice the policy-loss gradient there (older Theano's eq/eq form) */
 } arl_opt_cfg;
 
 /* Rollout buffers + synthetic-emulator description — sampler/act_server/buffers.py:7-38,

@@ -149,8 +149,10 @@ def forward(flat, obs_u8, spec, n_actions, emulate_bf16=False, dtype=torch.float
 
 
 def losses(prob, value, act, adv, ret, old_prob, algo, clip_param=0.2, lr_mult=1.0, v_coeff=1.0,
-           ent_coeff=0.01, valids=None):
-    """(pi_loss, v_loss, ent_loss) — aac_base.py:60-70; algo in {"ppo", "a2c"}."""
+           ent_coeff=0.01, valids=None, tie_grad=1):
+    """(pi_loss, v_loss, ent_loss) — aac_base.py:60-70; algo in {"ppo", "a2c"}.
+    tie_grad: inside the clip range surr_1 == surr_2 exactly; 1 = min() passes the gradient once (Theano >= 0.9
+    Minimum.L_op, standard PPO), 2 = to both branches (older Theano: eq(out, x) * gz and eq(out, y) * gz)."""
     def vmean(x):
         if valids is None:
             return x.mean()
@@ -162,7 +164,10 @@ def losses(prob, value, act, adv, ret, old_prob, algo, clip_param=0.2, lr_mult=1
     if algo == "ppo":
         ratio = (prob[idx, a] + TINY) / (old_prob[idx, a] + TINY)
         cp = clip_param * lr_mult
-        surr = torch.minimum(ratio * adv, torch.clamp(ratio, 1.0 - cp, 1.0 + cp) * adv)
+        s1, s2 = ratio * adv, torch.clamp(ratio, 1.0 - cp, 1.0 + cp) * adv
+        surr = torch.minimum(s1, s2)
+        if tie_grad == 2:
+            surr = surr + (s1 - s1.detach()) * (s1 == s2).to(s1.dtype)     # same value, one more gradient share at ties
         pi_loss = -vmean(surr)
     else:
         pi_loss = -vmean(torch.log(prob[idx, a] + TINY) * adv)

@@ -226,6 +226,47 @@ def test_loss_and_gradient_vs_oracle(spec_id, algo, n, valids):
         eng.close()
 
 
+@pytest.mark.parametrize("tie", [1, 2])
+def test_ppo_tie_gradient_option(tie):
+    """Inside the clip range the two PPO surrogates (ppo.py:47-49) are exactly equal; what T.minimum's gradient does at a
+    tie depends on the Theano version: once (>= 0.9; the default here, standard PPO) or to both branches, i.e. twice the
+    policy gradient there (older releases) — `ppo_tie_grad` / PPO(tie_grad=2).  Half of the rows sit inside the range (old
+    probabilities = the current policy's), the others outside; the loss value is the same either way."""
+    n = 96
+    pol, flat, spec = make_policy(1, max_rows=n)
+    eng = pol.engine
+    try:
+        rng = np.random.RandomState(77)
+        obs = rng.randint(0, 256, (n, 4, 104, 80), dtype=np.uint8)
+        act = rng.randint(0, 4, n).astype(np.uint8)
+        adv = rng.randn(n).astype(np.float32)
+        ret = rng.randn(n).astype(np.float32)
+        oldp = rng.dirichlet(np.ones(4), n).astype(np.float32)
+        p_now, _ = onet.forward(torch.tensor(flat), torch.tensor(obs), spec, 4, emulate_bf16=True)
+        oldp[: n // 2] = p_now.detach().numpy()[: n // 2]
+        oldv = rng.randn(n).astype(np.float32)
+        grads, losses = {}, {}
+        for t in (1, tie):
+            eng.opt_configure(algo=0, clip_param=0.2, v_loss_coeff=1.0, ent_loss_coeff=0.01, update=0, learning_rate=1e-3,
+                              beta1=0.9, beta2=0.999, epsilon=1e-5, rho=0.9, grad_norm_clip=-1.0, ppo_tie_grad=t)
+            eng.bind_train_inputs(*[torch.tensor(x).cuda() for x in (obs, act, adv, ret, oldv, oldp)], valids=None)
+            eng.grad_minibatch(torch.arange(n, dtype=torch.int32, device="cuda"), n)
+            torch.cuda.synchronize()
+            grads[t] = t2n(eng.grad).copy()
+            eng.clip_update(1.0)
+            losses[t] = eng.read_logs()[0][0]
+            eng.set_params(flat)
+            eng.reset_opt_state()
+        loss_ref, g_ref, _ = onet.loss_and_grad(flat, obs, act, adv, ret, oldp, spec, 4, "ppo", emulate_bf16=True, tie_grad=tie)
+        assert relerr(grads[tie], g_ref) < 0.10 / np.sqrt(n)
+        assert abs(losses[tie] - loss_ref) <= 1e-4 * abs(loss_ref) + 2e-4
+        if tie == 2:
+            assert losses[2] == losses[1]                      # same value ...
+            assert relerr(grads[2], grads[1]) > 0.05           # ... different gradient
+    finally:
+        eng.close()
+
+
 @pytest.mark.parametrize("kind,clip", [("adam", None), ("adam", 0.5), ("rmsprop", 0.5), ("rmsprop", None)])
 def test_clip_and_update_rules(kind, clip):
     pol, flat, spec = make_policy(0, max_rows=8)

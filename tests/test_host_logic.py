@@ -232,3 +232,22 @@ def test_entropy_ema_every_iteration_device_and_host_forms_agree():
         want_p = a * float(np.mean(np.exp(ent))) + (1 - a) * want_p
     assert abs(host.entropy - want_e) < 1e-7 and abs(host.perplexity - want_p) < 1e-7   # (float32 means)
     assert abs(dev.entropy - want_e) < 1e-5 and abs(dev.perplexity - want_p) < 1e-5
+
+
+def test_snapshot_modes_all_last_gap_none(tmp_path):
+    """rllab/misc/logger.py:319-340: all -> itr_<n>.pkl every time, last -> params.pkl, gap -> iteration 0 and every
+    snapshot_gap-th, none -> nothing; anything else is rejected"""
+    import os
+    from accel_rl_b200.util import logger
+    try:
+        for mode, want in (("all", {"itr_0.pkl", "itr_1.pkl", "itr_2.pkl", "itr_3.pkl", "itr_4.pkl", "itr_5.pkl"}),
+                           ("last", {"params.pkl"}), ("gap", {"itr_0.pkl", "itr_2.pkl", "itr_5.pkl"}), ("none", set())):
+            d = tmp_path / mode
+            logger.configure(str(d), snapshot_mode=mode, quiet=True, snapshot_gap=3)
+            for itr in range(6):
+                logger.save_itr_params(itr, dict(itr=itr))
+            assert {f for f in os.listdir(d) if f.endswith(".pkl")} == want, mode
+        with pytest.raises(NotImplementedError):
+            logger.configure(None, snapshot_mode="sometimes")
+    finally:
+        logger.configure(None, quiet=True)
