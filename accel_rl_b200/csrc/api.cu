@@ -608,30 +608,62 @@ int alloc_pconv(arl_ctx* c, std::vector<PackJob>& pj) {
   return 0;
 }
 
-template <int N>
+template <int N, int TW = 1>
 int launch_pconv(arl_ctx* c, const PcParams& p, cudaStream_t st) {
-  const int smem = pc_fwd_smem(N, p.ntaps, p.planes, p.load_rows, p.stages);
+  const int smem = pc_fwd_smem(N, p.ntaps, p.planes, p.load_rows, p.stages, 0, TW > 1);
   if (smem > 227 * 1024) ARL_FAIL(c, "pconv forward: stages do not fit shared memory");
   static int attr_smem = 0;
   if (smem > attr_smem) {
-    ARL_CHECK(c, cudaFuncSetAttribute(pconv_fwd_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ARL_CHECK(c, (cudaFuncSetAttribute(pconv_fwd_kernel<N, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)));
     attr_smem = smem;
   }
   int ctas = std::min(p.ntiles, 148);
   if (p.out.mode != 0 && c->dgrad_ctas > 0) ctas = std::min(ctas, c->dgrad_ctas);   // data gradient sharing the GPU with a wgrad
-  ARL_CHECK(c, launch_k(pconv_fwd_kernel<N>, dim3(ctas), dim3(kPcFwdThreads), smem, st, p));
+  ARL_CHECK(c, (launch_k(pconv_fwd_kernel<N, TW>, dim3(ctas), dim3(kPcFwdThreads), smem, st, p)));
   c->launches++;
   ARL_CHECK(c, cudaGetLastError());
   return 0;
 }
 
-int launch_pconv_n(arl_ctx* c, int N, const PcParams& p, cudaStream_t st) {
+int launch_pconv_n(arl_ctx* c, int N, const PcParams& p, cudaStream_t st, int TW = 1) {
+  if (TW == 2 && N == 32) return launch_pconv<32, 2>(c, p, st);
+  if (TW == 2 && N == 64) return launch_pconv<64, 2>(c, p, st);
+  if (TW == 3 && N == 64) return launch_pconv<64, 3>(c, p, st);
+  if (TW != 1) ARL_FAIL(c, "unsupported wide pconv tile");
   switch (N) {
     case 32: return launch_pconv<32>(c, p, st);
     case 64: return launch_pconv<64>(c, p, st);
     case 128: return launch_pconv<128>(c, p, st);
   }
   ARL_FAIL(c, "unsupported pconv tile width N=" + std::to_string(N));
+}
+
+// Wide forward / data-gradient tiles (pconv.cuh, PcParams): the taps of a filter row on the N axis.  ARL_FWD_WIDE=0 keeps the
+// one-tap-per-MMA tiles (A/B).  Returns TW (1: not applicable) and rewrites the tiling of p for 120-row tiles.
+int pconv_make_wide(arl_ctx* c, const PcLayer& q, int N, int mode, PcParams& p, int n, int which) {
+  // ARL_FWD_WIDE: bit mask of the launches that take the wide form — bits 0..2: forward of conv layer 0..2, bit 3: data
+  // gradients.  OFF by default (mask 0).  Parity-green (tests/test_gpu_kernels.py runs its oracle comparisons under mask 15)
+  // and the MMA burst of a tile does shrink as modelled (conv0: 1 180 -> 700 cycles, device trace), but the tile period is
+  // then set by the epilogue chain (accumulator wait -> tcgen05.ld -> exchange barrier -> shuffles -> stores -> next tile:
+  // ~1 650 cycles against ~1 100 for the classic tile, which is itself only just MMA-bound): conv0/1/2 forward 12.5 / 8.4 /
+  // 8.7 -> 18.8 / 9.6 / 11.5 us, 51.4 -> 54.6 ms per iteration.  Needs a second epilogue warp set before it can pay.
+  static const int mask = getenv("ARL_FWD_WIDE") ? atoi(getenv("ARL_FWD_WIDE")) : 0;
+  const bool on = (mask >> which) & 1;
+  const int TW = q.T;
+  if (!on || mode == 2 || p.u8.obs || TW < 2 || TW > 3 || TW * N > 256 || (N != 32 && N != 64)) return 1;
+  if (TW == 3 && N != 64) return 1;
+  for (int st = p.stages; st >= 2; --st)
+    if (pc_fwd_smem(N, p.ntaps, p.planes, p.load_rows, st, 0, 1) <= 227 * 1024) { p.stages = st; break; }
+  if (pc_fwd_smem(N, p.ntaps, p.planes, p.load_rows, p.stages, 0, 1) > 227 * 1024) return 1;
+  p.n_ty = q.T;
+  if (p.tiles_per_img > 0) {
+    p.tiles_per_img = ((p.Ho - 1) * p.Wp + p.Wo + kPcWideRows - 1) / kPcWideRows;
+    p.ntiles = n * p.tiles_per_img;
+    p.magic_tpi = pc_magic(p.tiles_per_img);
+  } else {
+    p.ntiles = (int)(((long)n * p.S + kPcWideRows - 1) / kPcWideRows);
+  }
+  return TW;
 }
 
 bool fc_tiles_ok(arl_ctx* c);
@@ -699,7 +731,8 @@ int pconv_forward_layer(arl_ctx* c, int l, const __nv_bfloat16* obs16, const int
   pc_out_forward(c, l, p.out);
   p.out.ds_shift = (p.out.ds == 2) ? 1 : (p.out.ds == 4) ? 2 : 0; p.out.us = 1;
   if (l == 0 && obs8) p.u8 = u8_source(c, obs8, p.load_rows);
-  return launch_pconv_n(c, q.N, p, st);
+  const int TW = pconv_make_wide(c, q, q.N, 0, p, n, std::min(l, 2));
+  return launch_pconv_n(c, q.N, p, st, TW);
 }
 
 
@@ -824,7 +857,9 @@ void pconv_dgrad_params(arl_ctx* c, int l, int n, PcParams& p) {
 int pconv_dgrad_layer(arl_ctx* c, int l, int n, cudaStream_t st) {
   PcParams p;
   pconv_dgrad_params(c, l, n, p);
-  return launch_pconv_n(c, c->pc[l].P * 64, p, st);
+  const int Nd = c->pc[l].P * 64;
+  const int TW = (p.planes == 1) ? pconv_make_wide(c, c->pc[l], Nd, p.out.mode, p, n, 3) : 1;
+  return launch_pconv_n(c, Nd, p, st, TW);
 }
 
 // Data AND weight gradient of layer l (>= 1) in one kernel (pconv_bwd_kernel): both read the same dY tile.  Possible when

@@ -218,10 +218,22 @@ struct PcParams {
   int stages;
   PcU8Src u8;                 // first layer: uint8 observations instead of `src` (per-image tiling only)
   PcOut out;
+  // ---- wide form (pconv_fwd_kernel<N, TW>, TW = taps per filter row > 1): the taps of a row ride on the N axis ----
+  //   D_tx[r][co] = sum_ty sum_k A[r + ty*Wp][k] * W[ty][tx][k][co]      one MMA per (ty, plane, k16): M = 128, N = TW*N,
+  //   out[q][co]  = sum_tx D_tx[q + tx][co]                              B = the TW weight tiles of the row, contiguous
+  // so one 4 KB A slice feeds TW x the math (issue cycles per the measured 25 + (4 KB + N*32 B)/128 model: 9 taps x N = 64:
+  // 36 x 73 -> 12 x 105), and the epilogue adds the column groups one row apart (warp shuffles; the first rows of the next
+  // lane quadrant through shared memory).  Rows 128-TW+1.. of a tile have no partner rows: tiles advance by kPcWideRows = 120
+  // (a multiple of the 8-row swizzle period) and only rows < 120 are stored.
+  int n_ty;                   // wide: filter rows; A row shift of row ty = shift[ty * TW]
 };
+constexpr int kPcWideRows = 120;
+constexpr int kPcExFloats = 2 /*parity*/ * 2 /*halves*/ * 4 /*quadrants*/ * 2 /*lanes*/ * 3 /*tx*/ * 16;
 
-__host__ __device__ inline int pc_fwd_smem(int N, int ntaps, int planes, int load_rows, int stages, int raw_stage_bytes = 0) {
-  return ntaps * planes * N * 128 + stages * (planes * load_rows * 128 + raw_stage_bytes) + 1024 /*align*/ + 256 /*barriers*/ + N * 4;
+__host__ __device__ inline int pc_fwd_smem(int N, int ntaps, int planes, int load_rows, int stages, int raw_stage_bytes = 0,
+                                           int wide = 0) {
+  return ntaps * planes * N * 128 + stages * (planes * load_rows * 128 + raw_stage_bytes) + 1024 /*align*/ + 256 /*barriers*/ + N * 4 +
+         (wide ? 6144 + 16 : 0) /* cross-quadrant exchange rows: kPcExFloats floats */;
 }
 
 // n / d for d >= 1 with magic = floor(2^32/d) + 1 (exact for n < 2^32 / d; every use here is < 2^24)
@@ -291,9 +303,13 @@ ARL_DEVINL void pc_store_unfold(const PcOut& o, const uint32_t* packed, int b, i
 }
 
 #define ARL_TP(slot) do { if (N == 32) ARL_T(slot); } while (0)
-template <int N>
+template <int N, int TW = 1>
 __global__ void __launch_bounds__(kPcFwdThreads, 1) pconv_fwd_kernel(const __grid_constant__ PcParams p) {
   static_assert(N == 32 || N == 64 || N == 128, "tile width");
+  static_assert(TW >= 1 && TW <= 3 && TW * N <= 256, "wide form: TW taps of a row on the N axis");
+  constexpr int NW = TW * N;                                          // accumulator columns per tile
+  constexpr int TCOLS = (2 * NW <= 64) ? 64 : (2 * NW <= 128) ? 128 : (2 * NW <= 256) ? 256 : 512;
+  constexpr int TROWS = (TW > 1) ? kPcWideRows : 128;                  // positions a tile advances by / stores
   if ((int)blockIdx.x >= p.ntiles) return;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -310,6 +326,7 @@ __global__ void __launch_bounds__(kPcFwdThreads, 1) pconv_fwd_kernel(const __gri
   const uint32_t wfull_bar = bar_base + 8u * 20;
   const uint32_t tmem_ptr_addr = bar_base + 8u * 21;
   float* bias_s = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
+  float* ex_s = bias_s + ((N + 3) & ~3);                              // wide form: exchange rows (kPcExFloats floats)
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -326,7 +343,7 @@ __global__ void __launch_bounds__(kPcFwdThreads, 1) pconv_fwd_kernel(const __gri
     mbar_init(wfull_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr_addr, 2 * N);
+  if (warp == 1) tmem_alloc(tmem_ptr_addr, TCOLS);
   pdl_wait();                                  // everything below may read what the previous kernel wrote
   pdl_trigger();
   if (p.out.mode == 0)
@@ -341,8 +358,16 @@ __global__ void __launch_bounds__(kPcFwdThreads, 1) pconv_fwd_kernel(const __gri
     // ===================== TMA producer (converged warp, one elected lane issues) =====================
     if (elect_one()) {
       mbar_arrive_expect_tx(wfull_bar, (uint32_t)nblk * N * 128);
-      // one bulk copy per (tap, plane) weight tile
-      for (int b = 0; b < nblk; ++b) bulk_g2s(w_base + b * (N * 128), p.w + (long)b * N * 64, N * 128, wfull_bar);
+      // one bulk copy per (tap, plane) weight tile; wide form: the TW tiles of a (filter row, plane) sit next to each other
+      // = the N = TW*N B operand of one MMA
+      for (int b = 0; b < nblk; ++b) {
+        int slot = b;
+        if constexpr (TW > 1) {
+          const int t = b / p.planes, pl = b - t * p.planes, ty = t / TW, tx = t - ty * TW;
+          slot = (ty * p.planes + pl) * TW + tx;
+        }
+        bulk_g2s(w_base + slot * (N * 128), p.w + (long)b * N * 64, N * 128, wfull_bar);
+      }
     }
     __syncwarp();
     // gathered images: the index lookups (two dependent global loads, ~1.5 us) are hoisted out of the tile loop —
@@ -363,9 +388,9 @@ __global__ void __launch_bounds__(kPcFwdThreads, 1) pconv_fwd_kernel(const __gri
         const int b = tile / p.tiles_per_img;
         const int j = tile - b * p.tiles_per_img;
         const long img = __shfl_sync(0xffffffffu, img_l, it & 31);
-        pos0 = img * p.S + (long)j * 128;
+        pos0 = img * p.S + (long)j * TROWS;
       } else {
-        pos0 = (long)tile * 128;
+        pos0 = (long)tile * TROWS;
       }
       if (u8) break;                           // the converter warps build the patches: nothing to copy
       mbar_wait(empty_bar(s), ph ^ 1, 21);
@@ -387,7 +412,7 @@ __global__ void __launch_bounds__(kPcFwdThreads, 1) pconv_fwd_kernel(const __gri
     // done when the tensor pipe frees up.
     const int which = (warp == 10) ? 1 : 0;
     const uint32_t tmem_u = make_uniform(tmem_base);
-    constexpr uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+    constexpr uint32_t idesc = make_idesc_bf16(128, NW, 0, 0);
     // descriptor high words are constant (SBO 1024, version 1, SWIZZLE_128B); only the 14-bit address field moves
     const uint64_t desc0 = make_smem_desc(0, 16, 1024, 2);
     const uint32_t desc_hi32 = (uint32_t)(desc0 >> 32), desc_lo_flags = (uint32_t)desc0;   // LBO field lives in the low word
@@ -404,11 +429,12 @@ __global__ void __launch_bounds__(kPcFwdThreads, 1) pconv_fwd_kernel(const __gri
       tc_fence_after();
       if (elect_one()) {
         const uint32_t a_stage = a_base + s * stage_bytes;
-        const uint32_t d_tmem = tmem_u + acc * N;
+        const uint32_t d_tmem = tmem_u + acc * NW;
         uint32_t first = 0;
         uint32_t b_lo = (w_base >> 4) | desc_lo_flags;        // shared memory addresses are < 2^18: no carry into the flags
-        for (int t = 0; t < p.ntaps; ++t) {
-          uint32_t a_lo = ((a_stage + p.shift[t] * 128) >> 4) | desc_lo_flags;
+        const int n_a = (TW > 1) ? p.n_ty : p.ntaps;          // wide: one (shifted) A view per filter row
+        for (int t = 0; t < n_a; ++t) {
+          uint32_t a_lo = ((a_stage + p.shift[t * TW] * 128) >> 4) | desc_lo_flags;
           for (int pl = 0; pl < p.planes; ++pl) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -416,7 +442,7 @@ __global__ void __launch_bounds__(kPcFwdThreads, 1) pconv_fwd_kernel(const __gri
               first = 1;
             }
             a_lo += (uint32_t)p.load_rows * 8;     // next plane: load_rows * 128 bytes
-            b_lo += N * 8;                         // next weight tile: N * 128 bytes
+            b_lo += NW * 8;                        // next weight tile (group): NW * 128 bytes
           }
         }
         umma_commit(empty_bar(s));
@@ -454,14 +480,14 @@ __global__ void __launch_bounds__(kPcFwdThreads, 1) pconv_fwd_kernel(const __gri
       uint32_t b, pl_;
       if (p.tiles_per_img > 0) {
         b = pc_fdiv((uint32_t)tile, (uint32_t)p.tiles_per_img, p.magic_tpi);
-        pl_ = ((uint32_t)tile - b * p.tiles_per_img) * 128 + row;
+        pl_ = ((uint32_t)tile - b * p.tiles_per_img) * TROWS + row;
       } else {
-        const uint32_t qq = (uint32_t)tile * 128 + row;
+        const uint32_t qq = (uint32_t)tile * TROWS + row;
         b = pc_fdiv(qq, (uint32_t)p.S, p.magic_S);
         pl_ = qq - b * p.S;
       }
       const uint32_t y = pc_fdiv(pl_, (uint32_t)p.Wp, p.magic_Wp), x = pl_ - y * p.Wp;
-      const bool valid = (int)b < p.n_img && (int)y < p.Ho && (int)x < p.Wo;
+      const bool valid = (int)b < p.n_img && (int)y < p.Ho && (int)x < p.Wo && (int)row < TROWS;
       const int Y = y + o.dpad, X = x + o.dpad;
       const int cy = Y >> o.ds_shift, cx = X >> o.ds_shift;
       const int sub = ((Y & (o.ds - 1)) << o.ds_shift) | (X & (o.ds - 1));
@@ -476,6 +502,70 @@ __global__ void __launch_bounds__(kPcFwdThreads, 1) pconv_fwd_kernel(const __gri
       mbar_wait(tfull_bar(acc), aph, 25);
       if (warp == 2 && lane == 0) ARL_TP(it * 6 + 4);
       tc_fence_after();
+      if constexpr (TW > 1) {
+        // ---- wide form: 16 output columns at a time; out[row] = D_0[row] + D_1[row + 1] (+ D_2[row + 2]) ----
+        static_assert(HC % 16 == 0, "wide epilogue works on 16-column chunks");
+        constexpr int NCH = HC / 16;
+        const uint32_t tw = tmem_base + ((uint32_t)(q * 32) << 16) + acc * NW + h * HC;
+#pragma unroll
+        for (int cc = 0; cc < NCH; ++cc) {
+          uint32_t d[TW][16];
+#pragma unroll
+          for (int tx = 0; tx < TW; ++tx) tmem_ld16(tw + tx * N + cc * 16, d[tx]);
+          tmem_ld_wait();
+          if (cc == NCH - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));  // accumulator is in registers: the next tile's MMAs may start
+          }
+          // Lane L needs D_tx[L + tx]: lanes L + tx < 32 get it from lane L + tx of this warp, the last tx lanes from rows
+          // 0 .. tx-1 of the NEXT lane quadrant.  Lanes 0 .. TW-2 export their rows, import the next quadrant's same rows, and
+          // one ROTATING shuffle serves everybody: its sources 0 .. tx-1 (never read by an in-warp partner) hand out the
+          // imported rows.  One barrier per chunk among the four warps of this column half; buffers alternate by parity.
+          const int par = (it * NCH + cc) & 1;
+          float* ex = ex_s + ((par * 2 + h) * 4) * (2 * 3 * 16);
+          if (lane < TW - 1) {
+            float4* e4 = reinterpret_cast<float4*>(ex + (q * 2 + lane) * (3 * 16));
+#pragma unroll
+            for (int tx = 1; tx < TW; ++tx)
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                e4[tx * 4 + i] = make_float4(__uint_as_float(d[tx][4 * i]), __uint_as_float(d[tx][4 * i + 1]),
+                                             __uint_as_float(d[tx][4 * i + 2]), __uint_as_float(d[tx][4 * i + 3]));
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + h) : "memory");
+          if (lane < TW - 1) {
+            // (lane j overwrites its d[tx] for tx > j only: those were exported above and have no in-warp reader, while
+            // d[tx], tx <= j, is what lane j - tx reads)
+            const float4* n4 = reinterpret_cast<const float4*>(ex + (((q + 1) & 3) * 2 + lane) * (3 * 16));
+#pragma unroll
+            for (int tx = 1; tx < TW; ++tx)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                if (tx <= lane) continue;
+                const float4 v = (q < 3) ? n4[tx * 4 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                d[tx][4 * i] = __float_as_uint(v.x); d[tx][4 * i + 1] = __float_as_uint(v.y);
+                d[tx][4 * i + 2] = __float_as_uint(v.z); d[tx][4 * i + 3] = __float_as_uint(v.w);
+              }
+          }
+          uint32_t outw[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float acc_f = __uint_as_float(d[0][i]);
+#pragma unroll
+            for (int tx = 1; tx < TW; ++tx)
+              acc_f += __uint_as_float(__shfl_sync(0xffffffffu, d[tx][i], (lane + tx) & 31));
+            outw[i] = __float_as_uint(acc_f);
+          }
+          if (store) {
+            uint32_t packed[8];
+            pc_finish<16>(outw, bias_r + (NC > 16 ? cc * 16 : 0), o.scale, fwd, &mk[cc >> 1][2 * (cc & 1)], packed);
+            pc_store<16>(o, packed, dpos, sub * N + h * HC + cc * 16);
+          }
+        }
+        if (warp == 2 && lane == 0) ARL_TP(it * 6 + 5);
+        continue;
+      }
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * N + h * HC;
       uint32_t r[NB][NC];
       if constexpr (NC == 16) {
@@ -503,7 +593,7 @@ __global__ void __launch_bounds__(kPcFwdThreads, 1) pconv_fwd_kernel(const __gri
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * N);
+    tmem_dealloc(tmem_base, TCOLS);
   }
 }
 

@@ -1,6 +1,8 @@
 """Per-kernel parity: CUDA (through the C ABI) vs the oracle.  Needs a B200."""
 import ctypes as C
 
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -224,6 +226,21 @@ def test_loss_and_gradient_vs_oracle(spec_id, algo, n, valids):
         assert e_loss <= 5e-4 and e_grad <= (6e-3 if n >= 512 else 0.12)
     finally:
         eng.close()
+
+
+def test_wide_forward_tiles_option_passes_the_oracle_comparisons():
+    """ARL_FWD_WIDE=15 (off by default: measured slower, csrc/api.cu pconv_make_wide): the taps of a filter row on the N
+    axis of the forward / data-gradient tiles, column groups added one row apart in the epilogue.  The forward and
+    loss / gradient comparisons with the oracle must pass unchanged with it."""
+    import subprocess
+    import sys
+    if os.environ.get("ARL_FWD_WIDE"):
+        pytest.skip("already running under the option")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_kernels.py"), "-q", "-x", "-k",
+                        "forward or loss_and_gradient"], env=dict(os.environ, ARL_FWD_WIDE="15"), capture_output=True, text=True,
+                       timeout=900, cwd=root)
+    assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
 
 
 @pytest.mark.parametrize("tie", [1, 2])
