@@ -271,6 +271,9 @@ ARL_DEVINL void pc_finish(const uint32_t* r, const float* bias_r, float scale, b
 // NC/8 packed 16-byte chunks -> destination position dpos, channel ch0 of the destination cell
 template <int NC>
 ARL_DEVINL void pc_store(const PcOut& o, const uint32_t* packed, long dpos, int ch0) {
+#ifdef ARL_DBG_NOSTORE
+  if (packed[0] != 0x12345678u) return;      // timing experiment only: (almost) never store
+#endif
   const int plane = ch0 >> 6, chunk0 = (ch0 & 63) >> 3;
   if (o.swz) {
     __nv_bfloat16* drow = o.dst + plane * o.dst_plane_stride + dpos * 64;
@@ -394,7 +397,9 @@ __global__ void __launch_bounds__(kPcFwdThreads, 1) pconv_fwd_kernel(const __gri
       }
       if (u8) break;                           // the converter warps build the patches: nothing to copy
       mbar_wait(empty_bar(s), ph ^ 1, 21);
+#ifndef ARL_DBG_EPI
       if (lane == 0) ARL_TP(it * 6 + 0);
+#endif
       if (elect_one()) {
         mbar_arrive_expect_tx(full_bar(s), stage_bytes);
         const uint32_t dst = a_base + s * stage_bytes;
@@ -402,7 +407,9 @@ __global__ void __launch_bounds__(kPcFwdThreads, 1) pconv_fwd_kernel(const __gri
           bulk_g2s(dst + pl * p.load_rows * 128, p.src + pl * p.src_plane_stride + pos0 * 64, p.load_rows * 128, full_bar(s));
       }
       __syncwarp();
+#ifndef ARL_DBG_EPI
       if (lane == 0) ARL_TP(it * 6 + 1);
+#endif
     }
   } else if (warp == 1 || warp == 10) {
     // ===================== MMA issuers (converged warps, one elected lane issues) =====================
@@ -476,6 +483,9 @@ __global__ void __launch_bounds__(kPcFwdThreads, 1) pconv_fwd_kernel(const __gri
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t aph = (it >> 1) & 1;
+#ifdef ARL_DBG_EPI
+      if (warp == 2 && lane == 0) ARL_TP(it * 6 + 0);
+#endif
       // decode this thread's output row (and prefetch its mask) while the MMAs run
       uint32_t b, pl_;
       if (p.tiles_per_img > 0) {
@@ -499,6 +509,9 @@ __global__ void __launch_bounds__(kPcFwdThreads, 1) pconv_fwd_kernel(const __gri
 #pragma unroll
         for (int c = 0; c < NB; ++c) pc_load_mask32(o, h * HC + c * 32, apos, mk[c]);
       }
+#ifdef ARL_DBG_EPI
+      if (warp == 2 && lane == 0) ARL_TP(it * 6 + 1);
+#endif
       mbar_wait(tfull_bar(acc), aph, 25);
       if (warp == 2 && lane == 0) ARL_TP(it * 6 + 4);
       tc_fence_after();
