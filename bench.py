@@ -291,7 +291,8 @@ def kernel_breakdown(runner, args):
     a2c = getattr(args, "algo", "ppo") == "a2c"
     mb = N if a2c else args.minibatch                   # A2C: one full-batch step per iteration
     n_mb = 1 if a2c else (N // args.minibatch) * args.epochs
-    idx = torch.randperm(N, device="cuda")[:8 * mb].to(torch.int32).contiguous()
+    # (the profiling pass replays the minibatch a few times with an advancing cursor: 8 index slices, any valid rows)
+    idx = torch.cat([torch.randperm(N, device="cuda")[:mb] for _ in range(8)]).to(torch.int32).contiguous()
     out = {}
     labels, ms = eng.profile_graph(0, idx, mb, reps=24)
     for l, t in zip(labels, ms):
@@ -563,6 +564,11 @@ def run_ours(args):
             "conv_tile_roofline_frac": round(value / world * flop_conv / (pk["tf_sustained"] * 1e12), 4) if flop_conv else None,
             "roofline": roof,
             "roofline_tensor": roof_tensor,
+            "kernels_note": "per-kernel ms (and the roofline `achieved` figures): measured live in this run, after the timed "
+                            "region, by re-launching each kernel node of the product's captured graphs alone (24 chained "
+                            "replays, CUDA events, warm caches); `share` = that time x launches per step / the sum over all "
+                            "kernels, i.e. a share of summed kernel time, not of the timed region (whose kernels overlap on three "
+                            "streams; profiles/r2_timeline.md has the in-graph timeline)",
             "kernels": kernels[:16],
             "host_wall_s": round(wall, 3),
             "phases": phases,
