@@ -165,6 +165,9 @@ struct arl_ctx {
   bool pending_stream = false;         // ... and the folding kernel is update_stream_kernel (no clipping: no barrier)
   cudaEvent_t ev_fcd = nullptr;        // "FC data gradient has read the FC weights"
   unsigned long long* ticket = nullptr; // grid-barrier ticket of update_fused_kernel
+  // L2 residency of the optimiser state (ARL_L2_PERSIST): access-policy window over [params .. v] for the update kernel
+  cudaAccessPolicyWindow l2win{};
+  bool l2_on = false;
   // split update (clip_update, ARL_SPLIT_UPDATE): the FC range's step runs on `side` beside the next minibatch's conv layers
   cudaEvent_t ev_upd_fork = nullptr, ev_updB = nullptr;
   bool split_capture = false;           // inside train_minibatches' graph capture with the local update
@@ -263,6 +266,20 @@ cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
+
+// launch_k with an L2 access-policy window (captured into the graph's kernel node like any launch attribute)
+template <class... KArgs, class... Args>
+cudaError_t launch_k_win(const cudaAccessPolicyWindow* win, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                         cudaStream_t st, Args&&... args) {
+  if (!win) return launch_k(kern, grid, block, smem, st, std::forward<Args>(args)...);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeAccessPolicyWindow;
+  at[0].val.accessPolicyWindow = *win;
+  cfg.attrs = at; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
 }
 
@@ -1716,8 +1733,8 @@ int clip_update(arl_ctx* c, float gscale, cudaStream_t st) {
       ARL_CHECK(c, cudaGetLastError());
       return 0;
     }
-    ARL_CHECK(c, launch_k(update_stream_kernel, dim3(G), dim3(256), 0, st, u, c->sumsq_partial, nA, nA2, P_total, 0, G,
-                          (unsigned long long*)nullptr, 1));
+    ARL_CHECK(c, launch_k_win(c->l2_on ? &c->l2win : nullptr, update_stream_kernel, dim3(G), dim3(256), 0, st, u, c->sumsq_partial,
+                              nA, nA2, P_total, 0, G, (unsigned long long*)nullptr, 1));
     c->launches++;
     prof_mark(c, "clip_update", st);
     ARL_CHECK(c, cudaGetLastError());
@@ -1990,8 +2007,37 @@ int arl_param_layout(arl_ctx* c, long* offsets, long* sizes, int cap) {
   return n;
 }
 
+// ARL_L2_PERSIST=1: ask the L2 to keep the optimiser state (fp32 params, m, v: 3 x 14.5 MB, read and rewritten by the update
+// kernel once per minibatch and by nothing else) resident between updates: a persisting carve-out of that size and an
+// access-policy window on the update kernel's launches.  Applies when the three vectors sit in one allocation (engine.py).
+void l2_persist_setup(arl_ctx* c) {
+  static const int mode = getenv("ARL_L2_PERSIST") ? atoi(getenv("ARL_L2_PERSIST")) : 0;
+  c->l2_on = false;
+  if (!mode || !c->params || !c->m || !c->v) return;
+  const char* lo = reinterpret_cast<const char*>(std::min(c->params, std::min(c->m, c->v)));
+  const char* hi = reinterpret_cast<const char*>(std::max(c->params, std::max(c->m, c->v))) + c->n_params * sizeof(float);
+  const size_t bytes = (size_t)(hi - lo);
+  if (bytes > (size_t)4 * c->n_params * sizeof(float)) return;             // not one allocation
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceProp prop{};
+  cudaGetDeviceProperties(&prop, dev);
+  const size_t carve = std::min(bytes, (size_t)prop.persistingL2CacheMaxSize);
+  if (carve == 0 || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) != cudaSuccess) { cudaGetLastError(); return; }
+  c->l2win.base_ptr = const_cast<char*>(lo);
+  c->l2win.num_bytes = std::min(bytes, (size_t)prop.accessPolicyMaxWindowSize);
+  c->l2win.hitRatio = (float)std::min(1.0, (double)carve / (double)c->l2win.num_bytes);
+  c->l2win.hitProp = cudaAccessPropertyPersisting;
+  c->l2win.missProp = cudaAccessPropertyStreaming;
+  c->l2_on = true;
+  if (mode > 1)
+    fprintf(stderr, "[accel_rl_b200] L2 persistence: window %.1f MB, carve-out %.1f MB (max %.1f MB, L2 %.1f MB), hit ratio %.2f\n",
+            c->l2win.num_bytes / 1e6, carve / 1e6, prop.persistingL2CacheMaxSize / 1e6, prop.l2CacheSize / 1e6, c->l2win.hitRatio);
+}
+
 int arl_bind_params(arl_ctx* c, float* params, float* grad, float* m, float* v) {
   c->params = params; c->grad = grad; c->m = m; c->v = v;
+  l2_persist_setup(c);
   if (c->train_graph) { cudaGraphExecDestroy(c->train_graph); c->train_graph = nullptr; }
   if (c->rollout_graph) { cudaGraphExecDestroy(c->rollout_graph); c->rollout_graph = nullptr; }
   for (auto& o : c->slots)

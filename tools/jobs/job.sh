@@ -1,6 +1,8 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/r2_gpu_tests.log; cat gpurun_out/r2_gpu_tests.log
-python bench.py > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err; tail -c 400 gpurun_out/r2_bench_n1.json
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2_bench_ref.json 2> gpurun_out/r2_bench_ref.err; tail -c 300 gpurun_out/r2_bench_ref.json
+for v in 2 0 2 0; do
+  echo "=== ARL_L2_PERSIST=$v"
+  ARL_L2_PERSIST=$v python bench.py --steps 20 --warmup 4 --no-e2e --no-cpu-baseline 2> gpurun_out/l2.err | python -c "
+import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['phases']); print({k['kernel']: round(k['ms']*1e3,2) for k in d['kernels'][:8]})"
+  grep "L2 persistence" gpurun_out/l2.err | head -1
+done
+python -m pytest tests/test_gpu_path.py -x -q -k "bit_identical or ppo_iteration" 2>&1 | tail -2
 python bench.py --algo a2c --envs 1024 --horizon 5 --game mix4 --steps 200 --warmup 10 --no-cpu-baseline > gpurun_out/r2_bench_c3_a2c_mix4.json 2> gpurun_out/r2_bench_c3.err; tail -c 300 gpurun_out/r2_bench_c3_a2c_mix4.json
-python bench.py --workload frame_sweep --game mix4 > gpurun_out/r2_frame_sweep_mix4.json 2> gpurun_out/r2_fs.err; cat gpurun_out/r2_frame_sweep_mix4.json
-python bench.py --frames rgb --no-cpu-baseline > gpurun_out/r2_bench_rgb.json 2> gpurun_out/r2_bench_rgb.err; tail -c 300 gpurun_out/r2_bench_rgb.json
