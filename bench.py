@@ -36,8 +36,12 @@ FLOP_PER_ENV_STEP_PPO = 357.9e6     # 1 act-fwd + 1/128 bootstrap fwd + 4 x trai
 FLOP_PER_ENV_STEP_CONV = 265.7e6    # conv tiles only: the north-star's "conv-tile roofline" numerator
 
 
-def ncu_traffic(label):
-    """DRAM bytes per launch of `label` from the committed ncu --set full capture (None when not captured)"""
+def ncu_traffic(label, args=None):
+    """DRAM bytes per launch of `label` from the committed ncu --set full capture (None when not captured, or when this run's
+    launch shapes are not the captured ones: minibatch 512, preset 1, reference frames)"""
+    if args is not None and (getattr(args, "algo", "ppo") != "ppo" or args.minibatch != 512 or args.spec != 1 or
+                             getattr(args, "frames", "gray") != "gray"):
+        return None
     for name in ("r2_traffic.json", "r1e_traffic.json"):
         try:
             return json.load(open(os.path.join(ROOT, "profiles", name)))["kernels"].get(label)
@@ -520,7 +524,7 @@ def run_ours(args):
             nbytes = 28.0 * runner.policy.engine.n_params
             gbs = nbytes / (k["ms"] * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": "clip_update", "achieved": round(gbs, 1), "peak": pk["hbm"], "unit": "GB/s",
-                    "frac": round(gbs / pk["hbm"], 4), "traffic": ncu_traffic("clip_update"), "traffic_note": traffic_note,
+                    "frac": round(gbs / pk["hbm"], 4), "traffic": ncu_traffic("clip_update", args), "traffic_note": traffic_note,
                     "algorithmic_bytes_per_launch": nbytes,
                     "peak_source": pk["src"] + " (copy bandwidth; the kernel is timed alone, its 58 MB of optimiser state "
                                                "and parameters partly stay in the 126 MB L2 between launches)",
@@ -529,7 +533,7 @@ def run_ours(args):
             if k["tflops"] is not None:
                 roof_tensor = {"bound": "tensor", "kernel": k["kernel"], "achieved": k["tflops"], "peak": pk["tf_sustained"],
                         "unit": "TFLOP/s", "frac": round(k["tflops"] / pk["tf_sustained"], 4),
-                        "traffic": ncu_traffic(k["kernel"]),
+                        "traffic": ncu_traffic(k["kernel"], args),
                         "traffic_note": traffic_note,
                         "peak_source": pk["src"] + " (sustained bf16, kernel timed inside a long step)",
                         "share_of_step": k["share"]}
