@@ -600,6 +600,38 @@ def test_operand_copies_refreshed_by_the_update_match_a_fresh_pack():
         pol.engine.close()
 
 
+def test_sampler_reconfigure_and_log_overflow():
+    """re-configuring the sampler frees the bf16 rollout mirror the captured training graph gathers from — the
+    graph must be dropped with it (a stale graph would read freed memory); and an optimize() call with more minibatches
+    than log slots must fail loudly instead of truncating the returned losses."""
+    from accel_rl_b200.algos import PPO
+    from accel_rl_b200._lib import ArlError
+    from accel_rl_b200.util.seeding import set_seed
+    rules = dict(synth_ale.DEFAULT_RULES, pool_frames=128, life_base=24, life_mod=11, reward_mod=7, pool_seed=0)
+    set_seed(7)
+    sampler = _make_sampler(4, 2, 16, rules=rules)
+    env_spec, sample_size, horizon, mbr = sampler.initialize(seed=8, affinities=dict(), discount=0.99, need_extra_obs=True)
+    pol, flat, spec = make_policy(1)
+    algo = PPO(optimizer_args=dict(minibatch_size=64, epochs=2))
+    algo.initialize(pol, env_spec, sample_size, horizon, mbr)
+    sampler.policy_init(pol)
+    algo.set_n_itr(10)
+    try:
+        buf, _ = sampler.obtain_samples(0)
+        _, info0 = algo.optimize_policy(0, buf)
+        sampler._configure_engine()                          # same torch buffers, new mirrors / tables inside the library
+        buf, _ = sampler.obtain_samples(1)
+        _, info1 = algo.optimize_policy(1, buf)
+        torch.cuda.synchronize()
+        assert np.isfinite(info0["GradNorm"]).all() and np.isfinite(info1["GradNorm"]).all()
+        assert pol.engine.device_error() == 0
+        idx = torch.zeros(5000 * 8, dtype=torch.int32, device="cuda")
+        with pytest.raises(ArlError, match="log slots"):
+            pol.engine.train_minibatches(idx, 8, 5000)
+    finally:
+        pol.engine.close()
+
+
 def test_early_fc_update_is_bit_identical():
     """Without global-norm clipping (PPO's default) the FC weights are updated as soon as their gradient is final, while
     the conv gradient chain still runs (update_range_kernel).  Same arithmetic per element: parameters and optimizer
