@@ -600,6 +600,21 @@ def test_operand_copies_refreshed_by_the_update_match_a_fresh_pack():
         pol.engine.close()
 
 
+def test_example_script_trains_and_logs(tmp_path):
+    """scripts/example/example_train_ppo.py (the reference's example_train_ppo.py / example_train_a2c.py with the imports
+    swapped): builds sampler / algo / policy / runner the reference's way — incl. its defaults
+    (max_decorrelation_steps 2000, start no-ops 30) — trains and writes <log_dir>/<game>_<run_ID>/progress.csv"""
+    import csv
+    from accel_rl_b200.scripts.example.example_train_ppo import build_and_run
+    for algo, n_steps, interval in (("ppo", 3 * 16 * 128, 16 * 128), ("a2c", 40 * 16 * 5, 10 * 16 * 5)):
+        build_and_run(str(tmp_path), "breakout", algo, algo=algo, n_envs=16, n_steps=n_steps, n_sim_cores=2,
+                      log_interval_steps=interval)
+        rows = list(csv.DictReader(open(tmp_path / ("breakout_%s" % algo) / "progress.csv")))
+        assert len(rows) >= 3
+        assert all(np.isfinite(float(r["GradNormAverage"])) for r in rows) and float(rows[-1]["SamplesPerSecond"]) > 0
+        assert float(rows[-1]["CumTotalSteps"]) >= n_steps
+
+
 def test_sampler_reconfigure_and_log_overflow():
     """re-configuring the sampler frees the bf16 rollout mirror the captured training graph gathers from — the
     graph must be dropped with it (a stale graph would read freed memory); and an optimize() call with more minibatches

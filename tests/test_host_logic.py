@@ -251,3 +251,18 @@ def test_snapshot_modes_all_last_gap_none(tmp_path):
             logger.configure(None, snapshot_mode="sometimes")
     finally:
         logger.configure(None, quiet=True)
+
+
+def test_logger_context_takes_the_reference_argument_order(tmp_path):
+    """util/logging.py:20-43: logger_context(log_dir, name, run_ID, log_params, snapshot_mode) -> <log_dir>/<name>_<run_ID>/
+    with params.json holding the caller's parameters plus name and run_ID (the example scripts call it positionally)"""
+    import json
+    import os
+    from accel_rl_b200.util import logger
+    from accel_rl_b200.util.logging import logger_context
+    with logger_context(str(tmp_path), "breakout", 3, dict(exp="basic_ppo", learning_rate=1e-3)):
+        logger.record_tabular("Iteration", 0)
+        logger.dump_tabular(with_prefix=False)
+    d = tmp_path / "breakout_3"
+    assert (d / "progress.csv").exists()
+    assert json.load(open(d / "params.json")) == dict(exp="basic_ppo", learning_rate=1e-3, name="breakout", run_ID=3)
