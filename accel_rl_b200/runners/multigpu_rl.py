@@ -21,7 +21,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from accel_rl_b200.runners.accel_rl import AccelRL
+from accel_rl_b200.runners.accel_rl import AccelRL, AccelRLEval
 from accel_rl_b200.util import logger
 from accel_rl_b200.util.misc import make_seed
 
@@ -32,7 +32,10 @@ def _free_port():
         return s.getsockname()[1]
 
 
-class AccelRLSync(AccelRL):
+class _MultiGpuBase(object):
+    """launch + process group + seeds + n_itr of the multi-GPU runners (multigpu_rl_base.py:12-108); mixed in front of
+    AccelRL / AccelRLEval together with a communication flavour (_SyncComm / _AsyncComm) and a log flavour"""
+
     def __init__(self, affinities=None, seed=None, **kwargs):
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.n_runners = dist.get_world_size() if dist.is_initialized() else 1
@@ -114,6 +117,18 @@ class AccelRLSync(AccelRL):
         self._sample_size = sample_size * self.n_runners
         return n_itr
 
+    def _exchange(self, handle):
+        """all-gather of one picklable object (the 64-byte IPC handles)"""
+        if self.n_runners == 1:
+            return [handle]
+        out = [None] * self.n_runners
+        dist.all_gather_object(out, handle)
+        return out
+
+
+class _SyncComm(object):
+    """multigpu_rl_base.py:109-153"""
+
     def init_comm(self):
         eng = self.policy.engine
         # rank 0's initial parameters to everyone (reference ships them through a Manager dict)
@@ -121,17 +136,18 @@ class AccelRLSync(AccelRL):
             dist.broadcast(eng.params, src=0)
             eng.pack()
 
-        def exchange(handle):
-            if self.n_runners == 1:
-                return [handle]
-            out = [None] * self.n_runners
-            dist.all_gather_object(out, handle)
-            return out
-
-        self.algo.optimizer.init_comm(exchange, self.rank, self.n_runners)
+        self.algo.optimizer.init_comm(self._exchange, self.rank, self.n_runners)
         self._initial_param_vector = self.policy.get_param_values()
         if self.n_runners > 1:
             dist.barrier()
+
+    @property
+    def parallelism_tag(self):
+        return "synchronous"
+
+
+class _OnlineLog(object):
+    """multigpu_rl_base.py:216-231: the master logs the trajectories of every runner"""
 
     def store_diagnostics(self, itr, samples_data, opt_data, traj_infos, opt_infos):
         if self.n_runners > 1 and (itr + 1) % self._log_interval_itrs == 0:
@@ -148,14 +164,30 @@ class AccelRLSync(AccelRL):
         self._pending_trajs = []
         super().init_logging()
 
-    @property
-    def parallelism_tag(self):
-        return "synchronous"
+
+class _EvalLog(object):
+    """multigpu_rl_base.py:233-250: offline evaluation on a multi-GPU run — only the master evaluates and logs; the other
+    runners skip the evaluation, keep no diagnostics and wait for the master at the log point"""
+
+    def eval_policy(self, itr):
+        if self.rank != 0:
+            return None, None
+        return super().eval_policy(itr)
+
+    def store_diagnostics(self, itr, samples_data, opt_data, traj_infos, opt_infos):
+        if self.rank == 0:
+            super().store_diagnostics(itr, samples_data, opt_data, traj_infos, opt_infos)
+
+    def log_diagnostics(self, itr, eval_traj_infos, eval_time):
+        if self.rank == 0:
+            super().log_diagnostics(itr, eval_traj_infos, eval_time)
+        if self.n_runners > 1:
+            dist.barrier()
 
 
-class AccelRLAsync(AccelRLSync):
-    """reference: multigpu_rl.py:18-26 / multigpu_rl_base.py:161-208.  Same launch as AccelRLSync (one process per
-    GPU, rank r seeds with seed + 100*r, rank 0's initial parameters broadcast) but no collective on the data path:
+class _AsyncComm(object):
+    """reference: multigpu_rl.py:18-26 / multigpu_rl_base.py:161-208.  Same launch as the synchronous runners (one process
+    per GPU, rank r seeds with seed + 100*r, rank 0's initial parameters broadcast) but no collective on the data path:
     every learner pushes its locally clipped gradient into the central (params, m, v) store in rank 0's HBM under
     the chunk locks and pulls the new parameters (optimizers/async_/base.py)."""
 
@@ -166,14 +198,7 @@ class AccelRLAsync(AccelRLSync):
             eng.pack()
             torch.cuda.synchronize()
 
-        def exchange(handle):
-            if self.n_runners == 1:
-                return [handle]
-            out = [None] * self.n_runners
-            dist.all_gather_object(out, handle)
-            return out
-
-        self.algo.optimizer.init_comm(self.rank, self.n_runners, dict(exchange=exchange))
+        self.algo.optimizer.init_comm(self.rank, self.n_runners, dict(exchange=self._exchange))
         if hasattr(self.sampler, "poll_init"):
             # the reference leaves this call to the experiment script (nothing in its tree makes it)
             self.sampler.poll_init(self.algo.optimizer.central_params_handle, None)
@@ -184,3 +209,19 @@ class AccelRLAsync(AccelRLSync):
     @property
     def parallelism_tag(self):
         return "asynchronous"
+
+
+class AccelRLSync(_MultiGpuBase, _SyncComm, _OnlineLog, AccelRL):
+    """multigpu_rl.py:7-15"""
+
+
+class AccelRLAsync(_MultiGpuBase, _AsyncComm, _OnlineLog, AccelRL):
+    """multigpu_rl.py:18-26"""
+
+
+class AccelRLEvalSync(_MultiGpuBase, _SyncComm, _EvalLog, AccelRLEval):
+    """multigpu_rl.py:29-37 (needs a sampler with evaluate_policy, e.g. AAOEvalSampler)"""
+
+
+class AccelRLEvalAsync(_MultiGpuBase, _AsyncComm, _EvalLog, AccelRLEval):
+    """multigpu_rl.py:40-48"""

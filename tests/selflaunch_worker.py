@@ -25,19 +25,25 @@ def main():
     from accel_rl_b200.algos import mPPO, mAPPO
     from accel_rl_b200.envs import AtariEnv
     from accel_rl_b200.policies import AtariCnnPolicy, cnn_specs
-    from accel_rl_b200.runners import AccelRLSync, AccelRLAsync
-    from accel_rl_b200.sampler import ActsrvAltOvrlpSampler
+    from accel_rl_b200.runners import AccelRLSync, AccelRLAsync, AccelRLEvalSync
+    from accel_rl_b200.sampler import ActsrvAltOvrlpSampler, AAOEvalSampler
     from accel_rl_b200.util import logger
-    logger.configure(None, quiet=True)
+    log_dir = sys.argv[3] if len(sys.argv) > 3 else None
+    logger.configure(log_dir, quiet=True)
     rules = dict(pool_frames=128, life_base=24, life_mod=11, reward_mod=7)
-    sampler = ActsrvAltOvrlpSampler(EnvCls=AtariEnv, env_args=dict(game="breakout", max_start_noops=0, synth_rules=rules),
-                                    horizon=16, n_parallel=4, envs_per=4, max_decorrelation_steps=0)
-    Algo, Runner = (mPPO, AccelRLSync) if mode == "sync" else (mAPPO, AccelRLAsync)
+    sampler_args = dict(EnvCls=AtariEnv, env_args=dict(game="breakout", max_start_noops=0, synth_rules=rules),
+                        horizon=16, n_parallel=4, envs_per=4, max_decorrelation_steps=0)
+    if mode == "evalsync":                                    # offline evaluation: only the master evaluates and logs
+        sampler = AAOEvalSampler(eval_steps=4096, eval_envs_per=2, **sampler_args)
+    else:
+        sampler = ActsrvAltOvrlpSampler(**sampler_args)
+    Algo, Runner = dict(sync=(mPPO, AccelRLSync), evalsync=(mPPO, AccelRLEvalSync), **{"async": (mAPPO, AccelRLAsync)})[mode]
     algo = Algo(optimizer_args=dict(minibatch_size=128, epochs=2))
     policy = AtariCnnPolicy(**cnn_specs[1])
     assert under_torchrun or not torch.cuda.is_initialized()
+    interval = dict(eval_interval_steps=512 * world) if mode == "evalsync" else dict(log_interval_steps=512 * 2 * world)
     runner = Runner(algo=algo, policy=policy, sampler=sampler, n_steps=512 * 2 * world, seed=3,
-                    affinities=[dict(gpu=i) for i in range(world)], log_interval_steps=512 * 2 * world)
+                    affinities=[dict(gpu=i) for i in range(world)], **interval)
     runner.train()                                            # 3 iterations (accel_rl_base.py:84-97 rounding)
     # only rank 0 returns here in the one-script launch (the forked runners exit inside train())
     if runner.rank == 0:

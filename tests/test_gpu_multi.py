@@ -33,14 +33,15 @@ def test_sync_allreduce_adam_n_gpus(world):
     np.testing.assert_allclose(res["1"]["norms"], res["0"]["norms"], rtol=2e-6)
 
 
-def _selflaunch(mode, world, torchrun):
+def _selflaunch(mode, world, torchrun, log_dir=None):
     import json
     script = os.path.join(ROOT, "tests", "selflaunch_worker.py")
+    extra = [str(log_dir)] if log_dir is not None else []
     if torchrun:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world, "--master-addr",
-               "127.0.0.1", "--master-port", str(29590 + world), script, mode, str(world)]
+               "127.0.0.1", "--master-port", str(29590 + world), script, mode, str(world)] + extra
     else:
-        cmd = [sys.executable, script, mode, str(world)]
+        cmd = [sys.executable, script, mode, str(world)] + extra
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT")}
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
     lines = [l for l in r.stdout.splitlines() if l.startswith("SELFLAUNCH_DIGEST ")]
@@ -61,3 +62,18 @@ def test_one_script_launch_trains_like_torchrun(world):
     assert own["n_itr"] == tr["n_itr"] == 3 and not own["torchrun"] and tr["torchrun"]
     assert own["params"] == tr["params"]
     _selflaunch("async", world, torchrun=False)
+
+
+def test_multi_gpu_runner_with_offline_evaluation(tmp_path):
+    """AccelRLEvalSync (runners/multigpu_rl.py:29-37, log mixins multigpu_rl_base.py:233-250): synchronous learners where only
+    the master runs the evaluation episodes and writes the log while the others wait; same parameters from the one-script
+    launch and from torchrun; progress.csv holds one evaluation row per log point with the evaluation columns."""
+    import csv
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    own = _selflaunch("evalsync", 2, torchrun=False, log_dir=tmp_path / "own")
+    tr = _selflaunch("evalsync", 2, torchrun=True, log_dir=tmp_path / "tr")
+    assert own["n_itr"] == tr["n_itr"] == 3 and own["params"] == tr["params"]
+    rows = list(csv.DictReader(open(tmp_path / "own" / "progress.csv")))
+    assert len(rows) == 3 and all(int(r["TrajsInEval"]) > 0 and int(r["StepsInEval"]) > 0 for r in rows)
+    assert [int(r["Iteration"]) for r in rows] == [0, 1, 2]
