@@ -74,6 +74,19 @@ ARL_DEVINL void mbar_wait(uint32_t bar, uint32_t parity, int where) {
   }
 }
 
+// thread-block clusters: rank of this CTA, cluster-wide barrier (all threads of all CTAs), distributed shared memory load
+ARL_DEVINL uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+ARL_DEVINL void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+ARL_DEVINL float4 ld_dsmem_f4(uint32_t local_smem_addr, uint32_t cta_rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(cta_rank));
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote) : "memory");
+  return v;
+}
+
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma reads)
 ARL_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

@@ -47,6 +47,10 @@ struct FcParams {
   long act_plane;
   int sc_Wo, sc_S, sc_Wp, sc_pad;
   // KIND 2 / 3
+  // KIND 0, cluster > 1: the `cluster` CTAs of consecutive blockIdx.z (one thread-block cluster) add their split-K partials
+  // through distributed shared memory — CTA rank r sums rows [r*128/cluster, ...) of all of them in rank order — and only
+  // the sums go to out_f32[blockIdx.z / cluster]: 1/cluster of the partial traffic on the FC-forward -> head edge
+  int cluster;
   int fc_HW;                   // D row (hw, c) -> gradient row c*HW + hw
   double* ss_out;              // optional: per-epilogue-warp sums of squares of the gradient rows written,
                                // [(blockIdx.y * gridDim.x + blockIdx.x) * 8 + warp - 2] (global-norm partials)
@@ -153,7 +157,17 @@ __global__ void __launch_bounds__(kFcThreads, 1) fc_gemm_kernel(const __grid_con
         for (int i = 0; i < 32; ++i) v[i] = 0;
       }
       const int col = h * HC + c0;            // first of 32 tile columns
-      if (KIND == 0) {
+      if (KIND == 0 && p.cluster > 1) {
+        // own partial -> shared memory [128 rows][32 float4], float4 slot j of row r at (j ^ (r & 31)): conflict-free for the
+        // row-per-lane writes here and for the row-major reads of the reduction below
+        const uint32_t red = smem_base + (uint32_t)r * 512u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t slot = (uint32_t)((col >> 2) + j) ^ (uint32_t)(r & 31);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(red + slot * 16u), "r"(v[4 * j]), "r"(v[4 * j + 1]),
+                       "r"(v[4 * j + 2]), "r"(v[4 * j + 3]) : "memory");
+        }
+      } else if (KIND == 0) {
         const int row = blockIdx.x * 128 + r;
         float* dst = p.out_f32 + ((long)blockIdx.z * p.M + row) * p.ldo + blockIdx.y * BN + col;
         store_rows32_coalesced(scratch, v, dst, row < p.M, lane);
@@ -203,6 +217,29 @@ __global__ void __launch_bounds__(kFcThreads, 1) fc_gemm_kernel(const __grid_con
       if (lane == 0) p.ss_out[((long)blockIdx.y * gridDim.x + blockIdx.x) * 8 + (warp - 2)] = ssq;
     }
     tc_fence_before();
+  }
+  if (KIND == 0 && p.cluster > 1) {
+    // every thread of every CTA of the cluster: partials are in shared memory -> reduce my row slice -> peers may exit
+    cluster_sync_all();
+    if (warp >= 2) {
+      const int S = p.cluster;
+      const uint32_t crank = cluster_ctarank();
+      const int rows_per = 128 / S;                       // (cluster in {2, 4, 8})
+      const int t = tid - 64;                             // 0 .. 255
+      for (int e = t; e < rows_per * 32; e += 256) {
+        const int rr = (int)crank * rows_per + (e >> 5), f = e & 31;
+        const uint32_t local = smem_base + (uint32_t)rr * 512u + (uint32_t)((f ^ (rr & 31)) * 16);
+        float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int z = 0; z < S; ++z) {                     // fixed rank order: bit-reproducible
+          const float4 x = ld_dsmem_f4(local, (uint32_t)z);
+          acc4.x += x.x; acc4.y += x.y; acc4.z += x.z; acc4.w += x.w;
+        }
+        const int row = blockIdx.x * 128 + rr;
+        if (row < p.M)
+          *reinterpret_cast<float4*>(p.out_f32 + ((long)(blockIdx.z / S) * p.M + row) * p.ldo + blockIdx.y * BN + f * 4) = acc4;
+      }
+    }
+    cluster_sync_all();
   }
   __syncthreads();
   if (warp == 1) {
