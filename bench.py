@@ -573,7 +573,7 @@ def run_ours(args):
                             "replays, CUDA events, warm caches); `share` = that time x launches per step / the sum over all "
                             "kernels, i.e. a share of summed kernel time, not of the timed region (whose kernels overlap on three "
                             "streams; profiles/r2_timeline.md has the in-graph timeline)",
-            "kernels": kernels[:16],
+            "kernels": kernels,
             "host_wall_s": round(wall, 3),
             "phases": phases,
         }
