@@ -1,3 +1,4 @@
+# 8-GPU tests + synchronous N = 8 / 4 and asynchronous 8-GPU bench lines (gpurun --gpus 8 --timeout 1500 -- 'mkdir -p gpurun_out; bash tools/jobs/job8.sh')
 timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q -x -k "4 or 8" 2>&1 | tail -6 > gpurun_out/r2_tests8.log
 cat gpurun_out/r2_tests8.log
 for n in 8 4; do
