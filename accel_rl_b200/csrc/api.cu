@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <set>
 #include <vector>
 #include <map>
 #include <algorithm>
@@ -258,8 +259,18 @@ int roundup(int x, int m) { return (x + m - 1) / m * m; }
 // Kernel launch with the programmatic-dependent-launch attribute (see common.cuh: pdl_wait / pdl_trigger): inside the
 // captured graphs the next kernel's prologue may overlap this kernel's tail.  Off by default; ARL_PDL=1 enables.
 bool g_pdl = false;   // measured on B200: no gain inside CUDA graphs (72.2 vs 73.1 ms/iter), early trigger slower (76.0)
+// ARL_CARVEOUT=<percent>: one preferred shared-memory carve-out for every kernel launched through launch_k (an SM whose
+// consecutive kernels ask for different L1 / shared splits has to drain and reconfigure between them)
+int g_carveout = -1;
+inline void apply_carveout(const void* kern) {
+  if (g_carveout < 0) return;
+  static std::set<const void*> done;
+  if (done.insert(kern).second) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, g_carveout);
+}
+
 template <class... KArgs, class... Args>
 cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  apply_carveout(reinterpret_cast<const void*>(kern));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
@@ -1962,6 +1973,7 @@ int arl_create(const arl_net_cfg* cfg, arl_ctx** out) {
   // everything / for training only (A/B measurements)
   c->pc_mode = c->pc.empty() ? 0 : 2;
   if (const char* ev = getenv("ARL_PDL")) g_pdl = atoi(ev) != 0;
+  if (const char* ev = getenv("ARL_CARVEOUT")) g_carveout = atoi(ev);
   if (const char* ev = getenv("ARL_DGRAD_CTAS")) c->dgrad_ctas = atoi(ev);
   if (const char* ev = getenv("ARL_WGRAD_CTAS")) c->wgrad_ctas = atoi(ev);
   if (const char* ev = getenv("ARL_PCONV")) c->pc_mode = c->pc.empty() ? 0 : std::max(0, std::min(2, atoi(ev)));
