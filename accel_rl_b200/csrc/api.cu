@@ -169,6 +169,8 @@ struct arl_ctx {
   // L2 residency of the optimiser state (ARL_L2_PERSIST): access-policy window over [params .. v] for the update kernel
   cudaAccessPolicyWindow l2win{};
   bool l2_on = false;
+  size_t l2_carve = 0;                  // ARL_L2_PERSIST=3: the carve-out exists only while minibatches train
+  bool l2_toggle = false, l2_carved = false, l2_grad_in_window = false;
   // split update (clip_update, ARL_SPLIT_UPDATE): the FC range's step runs on `side` beside the next minibatch's conv layers
   cudaEvent_t ev_upd_fork = nullptr, ev_updB = nullptr;
   bool split_capture = false;           // inside train_minibatches' graph capture with the local update
@@ -965,7 +967,10 @@ int launch_fc_gemm(arl_ctx* c, const FcParams& p, dim3 grid, cudaStream_t st) {
     ARL_CHECK(c, cudaFuncSetAttribute(fc_gemm_kernel<KIND, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_smem = smem;
   }
-  ARL_CHECK(c, launch_k(fc_gemm_kernel<KIND, BN>, grid, dim3(kFcThreads), (size_t)smem, st, p));
+  // (the FC weight gradient's fp32 rows are inside the optimiser-state window when the caller put grad next to params:
+  // the update reads them from L2, ARL_L2_PERSIST)
+  const cudaAccessPolicyWindow* win = (KIND >= 2 && c->l2_on && c->l2_grad_in_window) ? &c->l2win : nullptr;
+  ARL_CHECK(c, launch_k_win(win, fc_gemm_kernel<KIND, BN>, grid, dim3(kFcThreads), (size_t)smem, st, p));
   c->launches++;
   ARL_CHECK(c, cudaGetLastError());
   return 0;
@@ -1994,6 +1999,7 @@ int arl_create(const arl_net_cfg* cfg, arl_ctx** out) {
 void arl_destroy(arl_ctx* c) {
   if (!c) return;
   cudaDeviceSynchronize();
+  if (c->l2_on && c->l2_carved) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
   comm_destroy(c->comm);
   async_destroy(c->async_);
   // device workspaces are released with the context's process lifetime; free the large ones explicitly
@@ -2056,17 +2062,36 @@ int arl_param_layout(arl_ctx* c, long* offsets, long* sizes, int cap) {
   return n;
 }
 
-// ARL_L2_PERSIST=1: ask the L2 to keep the optimiser state (fp32 params, m, v: 3 x 14.5 MB, read and rewritten by the update
-// kernel once per minibatch and by nothing else) resident between updates: a persisting carve-out of that size and an
-// access-policy window on the update kernel's launches.  Applies when the three vectors sit in one allocation (engine.py).
+// L2 residency of the optimiser state (fp32 params, m, v: 3 x 14.5 MB, read and rewritten by the update kernel once per
+// minibatch and by nothing else): a persisting carve-out of that size + an access-policy window on the update kernel's
+// launches, so the three vectors stay in the 126 MB L2 between updates instead of being streamed from HBM 256 times per
+// iteration.  Applies when the three vectors sit in one allocation (engine.py; not the synchronous learner, whose
+// parameters live in the symmetric peer allocation).  ARL_L2_PERSIST: 0 off; 1 (2: + a line on stderr) carve-out always on (rollouts lose 43 MB of
+// L2: 7.5 -> 7.9..9.2 ms); 3 (default) carve-out only while minibatches train (the runner has read the previous phase back
+// before the other starts): 51.3 -> 50.3 ms per iteration; 4 also the gradient vector (no further gain).
+void l2_carve(arl_ctx* c, bool on) {
+  if (!c->l2_toggle || c->l2_carved == on) return;
+  cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, on ? c->l2_carve : 0);
+  c->l2_carved = on;
+}
+
 void l2_persist_setup(arl_ctx* c) {
-  static const int mode = getenv("ARL_L2_PERSIST") ? atoi(getenv("ARL_L2_PERSIST")) : 0;
-  c->l2_on = false;
+  static const int mode = getenv("ARL_L2_PERSIST") ? atoi(getenv("ARL_L2_PERSIST")) : 3;
+  if (c->l2_on && c->l2_carved) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);     // re-binding: start over
+  c->l2_on = false; c->l2_toggle = false; c->l2_carved = false;
   if (!mode || !c->params || !c->m || !c->v) return;
   const char* lo = reinterpret_cast<const char*>(std::min(c->params, std::min(c->m, c->v)));
   const char* hi = reinterpret_cast<const char*>(std::max(c->params, std::max(c->m, c->v))) + c->n_params * sizeof(float);
-  const size_t bytes = (size_t)(hi - lo);
+  size_t bytes = (size_t)(hi - lo);
   if (bytes > (size_t)4 * c->n_params * sizeof(float)) return;             // not one allocation
+  // the gradient right behind them (engine.py): the window covers it too (mode 4)
+  c->l2_grad_in_window = false;
+  if (mode == 4 && c->grad && reinterpret_cast<const char*>(c->grad) >= hi &&
+      reinterpret_cast<const char*>(c->grad) < hi + 4096) {
+    hi = reinterpret_cast<const char*>(c->grad) + c->n_params * sizeof(float);
+    bytes = (size_t)(hi - lo);
+    c->l2_grad_in_window = true;
+  }
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceProp prop{};
@@ -2079,7 +2104,8 @@ void l2_persist_setup(arl_ctx* c) {
   c->l2win.hitProp = cudaAccessPropertyPersisting;
   c->l2win.missProp = cudaAccessPropertyStreaming;
   c->l2_on = true;
-  if (mode > 1)
+  c->l2_carve = carve; c->l2_toggle = (mode >= 3); c->l2_carved = true;
+  if (mode == 2)
     fprintf(stderr, "[accel_rl_b200] L2 persistence: window %.1f MB, carve-out %.1f MB (max %.1f MB, L2 %.1f MB), hit ratio %.2f\n",
             c->l2win.num_bytes / 1e6, carve / 1e6, prop.persistingL2CacheMaxSize / 1e6, prop.l2CacheSize / 1e6, c->l2win.hitRatio);
 }
@@ -2244,6 +2270,7 @@ int arl_sampler_warmup(arl_ctx* c, const int* n_steps, int max_steps, void* stre
 
 int arl_rollout_begin(arl_ctx* c, void* stream) {
   if (!c->sampler_set) ARL_FAIL(c, "sampler not configured");
+  l2_carve(c, false);
   return rollout_begin(c, (cudaStream_t)stream);
 }
 int arl_rollout_step(arl_ctx* c, int s, const uint8_t* staging, void* stream) {
@@ -2306,6 +2333,7 @@ int arl_rollout_run(arl_ctx* c, void* stream) {
   NvtxRange nvtx_("rollout");
   if (!c->sampler_set) ARL_FAIL(c, "sampler not configured");
   cudaStream_t st = (cudaStream_t)stream;
+  l2_carve(c, false);                          // (the previous optimize() call has been read back: nothing is training)
   if (!c->rollout_graph) {
     // warm every kernel's lazy attribute setup outside capture
     cudaStream_t cap;
@@ -2424,6 +2452,7 @@ namespace {
 int train_minibatches(arl_ctx* c, const int* idx, int mb_size, int count, int sync, cudaStream_t st) {
   NvtxRange nvtx_("train minibatches");
   if (count > c->log_cap) ARL_FAIL(c, "more minibatches in one call than loss / grad-norm log slots (4096): read the logs in between");
+  if (count >= 8) l2_carve(c, true);      // (a single full-batch step per rollout, A2C, has nothing to keep resident)
   // sync: 0 = local clip + update, 1 = synchronous DP step, 2 = asynchronous push/pull
   const bool overlap = sync == 1 && sync_overlap_ok(c);
   if (overlap && sync_overlap_prepare(c)) return 1;

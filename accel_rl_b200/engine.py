@@ -54,11 +54,11 @@ class Engine(object):
         # params, m, v in ONE allocation (what the update kernel reads and rewrites every minibatch: the library can ask the
         # L2 to keep that range resident between updates, csrc/api.cu l2_persist_setup); the gradient is a stream
         npad = (self.n_params + 63) // 64 * 64
-        self._state = torch.zeros(3 * npad, dtype=torch.float32, device=self.device)
+        self._state = torch.zeros(4 * npad, dtype=torch.float32, device=self.device)
         self.params = self._state[:self.n_params]
         self.m = self._state[npad:npad + self.n_params]
         self.v = self._state[2 * npad:2 * npad + self.n_params]
-        self.grad = torch.zeros(self.n_params, dtype=torch.float32, device=self.device)
+        self.grad = self._state[3 * npad:3 * npad + self.n_params]
         self._keep = {}
         self._sym = None
         self._dp_mode = None            # "synchronous" / "asynchronous" once comm_init / async_init ran
