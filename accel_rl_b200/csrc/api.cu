@@ -161,6 +161,7 @@ struct arl_ctx {
   double* ss_fc = nullptr;             // [kSsFcCap]  FC weight-gradient tiles' per-warp sums of squares
   int pending_ss_fin = 0, pending_ss_fc = 0;   // > 0: this minibatch's global-norm partials came from the producers
   bool train_step_active = false;      // grad_minibatch is followed by the local clip_update (train_minibatches, sync == 0)
+  bool in_grad_fwd = false;            // forward_trunk called by grad_minibatch: conv0's gathered rows are read again (wgrad)
   bool early_fc_done = false;          // this minibatch's FC weights were updated by update_range_kernel
   const void* pending_fin = nullptr;   // TrainPlan whose gradient finalisation clip_update must fold into its update kernel
   bool pending_stream = false;         // ... and the folding kernel is update_stream_kernel (no clipping: no barrier)
@@ -761,6 +762,10 @@ int pconv_forward_layer(arl_ctx* c, int l, const __nv_bfloat16* obs16, const int
   pc_out_forward(c, l, p.out);
   p.out.ds_shift = (p.out.ds == 2) ? 1 : (p.out.ds == 4) ? 2 : 0; p.out.us = 1;
   if (l == 0 && obs8) p.u8 = u8_source(c, obs8, p.load_rows);
+  // ARL_OBS_L2_HINT=1: the gathered observation rows of a training minibatch (34 MB) are read twice, by this kernel and ~100 us
+  // later by layer 0's weight gradient: first read evict_last, second read evict_first
+  static const bool obs_hint = getenv("ARL_OBS_L2_HINT") && atoi(getenv("ARL_OBS_L2_HINT")) != 0;
+  p.src_evict_last = (l == 0 && obs_hint && c->in_grad_fwd) ? 1 : 0;
   const int TW = pconv_make_wide(c, q, q.N, 0, p, n, std::min(l, 2));
   return launch_pconv_n(c, q.N, p, st, TW);
 }
@@ -799,6 +804,8 @@ int pconv_wgrad_params(arl_ctx* c, int l, const __nv_bfloat16* obs16, const int*
   if (l == 0) {
     p.a = obs16; p.a_plane_stride = 0; p.idx = idx; p.idx_off = idx_off; p.nb = n;
     p.tiles_per_img = q.tiles_per_img; p.ntiles = n * q.tiles_per_img; p.dy_off = 0;
+    static const bool obs_hint = getenv("ARL_OBS_L2_HINT") && atoi(getenv("ARL_OBS_L2_HINT")) != 0;
+    p.a_evict_first = obs_hint ? 1 : 0;
   } else {
     p.a = q.in; p.a_plane_stride = q.in_rows * 64;
     p.tiles_per_img = 0; p.ntiles = (int)(((long)n * q.S + 127) / 128);
@@ -1453,7 +1460,10 @@ int grad_minibatch(arl_ctx* c, const int* idx, const int* idx_off, int n, cudaSt
   const bool pcb = c->pc_mode >= 2;
   if (pcb && pconv_prepare_dy(c, n, st)) return 1;
   int S = 0;
-  if (forward_trunk(c, obs16, gidx, gidx_off, n, &S, pcb, st, obs8)) return 1;
+  c->in_grad_fwd = true;
+  const int rc_fwd = forward_trunk(c, obs16, gidx, gidx_off, n, &S, pcb, st, obs8);
+  c->in_grad_fwd = false;
+  if (rc_fwd) return 1;
   // ---- head: losses + dlogits + dh ----
   if (c->t_valids) {
     ARL_CHECK(c, launch_k(count_valids_idx_kernel, dim3(1), dim3(1024), 0, st, c->t_valids, idx, idx_off, n, c->valid_count));

@@ -108,6 +108,25 @@ ARL_DEVINL void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uin
       : "memory");
 }
 
+// the same copy with an L2 eviction-priority hint (policy from l2_policy_evict_last / _first; 0 = no hint)
+ARL_DEVINL void bulk_g2s_hint(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  if (policy == 0) { bulk_g2s(dst_smem, src, bytes, bar); return; }
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+      "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
+ARL_DEVINL uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+ARL_DEVINL uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+
 // ---------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ---------------------------------------------------------------------------

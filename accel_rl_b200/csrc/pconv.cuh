@@ -226,6 +226,9 @@ struct PcParams {
   // lane quadrant through shared memory).  Rows 128-TW+1.. of a tile have no partner rows: tiles advance by kPcWideRows = 120
   // (a multiple of the 8-row swizzle period) and only rows < 120 are stored.
   int n_ty;                   // wide: filter rows; A row shift of row ty = shift[ty * TW]
+  int src_evict_last;         // 1: the input patches are read again soon (layer 0 in training: the weight gradient re-reads
+                              // the same gathered rows ~100 us later) -> ask the L2 to keep them in front of the streamed
+                              // activations in between
 };
 constexpr int kPcWideRows = 120;
 constexpr int kPcExFloats = 2 /*parity*/ * 2 /*halves*/ * 4 /*quadrants*/ * 2 /*lanes*/ * 3 /*tx*/ * 16;
@@ -403,8 +406,10 @@ __global__ void __launch_bounds__(kPcFwdThreads, 1) pconv_fwd_kernel(const __gri
       if (elect_one()) {
         mbar_arrive_expect_tx(full_bar(s), stage_bytes);
         const uint32_t dst = a_base + s * stage_bytes;
+        const uint64_t pol = p.src_evict_last ? l2_policy_evict_last() : 0ull;
         for (int pl = 0; pl < p.planes; ++pl)
-          bulk_g2s(dst + pl * p.load_rows * 128, p.src + pl * p.src_plane_stride + pos0 * 64, p.load_rows * 128, full_bar(s));
+          bulk_g2s_hint(dst + pl * p.load_rows * 128, p.src + pl * p.src_plane_stride + pos0 * 64, p.load_rows * 128, full_bar(s),
+                        pol);
       }
       __syncwarp();
 #ifndef ARL_DBG_EPI
@@ -641,6 +646,7 @@ struct PcWgradParams {
   float* partial;              // [gridDim.x][nblk*64][N]
   float* bias_partial;         // [gridDim.x][N]
   int stages;
+  int a_evict_first;           // 1: last reader of the gathered input rows (layer 0): let the L2 drop them first
   // ---- wide form (wide = 1): the taps of one row, tx = T-1 .. 0, ride on the N axis -----------------------------------
   //   D_i[(a, ch)][(j, co)] = sum_q'' A[q'' + ty*Wp][plane, ch] * dY[q'' - tx][co]   (= dW[ty][tx][plane, ch][co], q = q'' - tx)
   // B = the SAME dY patch seen through `nb_atoms` MN-atoms one row apart (descriptor LBO = one dY row), so one MMA is
@@ -746,7 +752,8 @@ __global__ void __launch_bounds__(kPcThreads, 1) pconv_wgrad_kernel(const __grid
         mbar_arrive_expect_tx(full_bar(s), a_bytes + (uint32_t)p.dy_rows * ROWB);
         const uint32_t dst = smem_base + s * stage_bytes;
         for (int pl = 0; pl < p.planes; ++pl)
-          bulk_g2s(dst + pl * p.a_rows * 128, p.a + pl * p.a_plane_stride + apos * 64, p.a_rows * 128, full_bar(s));
+          bulk_g2s_hint(dst + pl * p.a_rows * 128, p.a + pl * p.a_plane_stride + apos * 64, p.a_rows * 128, full_bar(s),
+                        p.a_evict_first ? l2_policy_evict_first() : 0ull);
         bulk_g2s(dst + a_bytes, p.dy + dpos * N, p.dy_rows * ROWB, full_bar(s));
       }
       __syncwarp();
