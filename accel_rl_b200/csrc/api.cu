@@ -2093,7 +2093,11 @@ void l2_persist_setup(arl_ctx* c) {
   const char* lo = reinterpret_cast<const char*>(std::min(c->params, std::min(c->m, c->v)));
   const char* hi = reinterpret_cast<const char*>(std::max(c->params, std::max(c->m, c->v))) + c->n_params * sizeof(float);
   size_t bytes = (size_t)(hi - lo);
-  if (bytes > (size_t)4 * c->n_params * sizeof(float)) return;             // not one allocation
+  // exactly the layout engine.py makes — [params | m | v] at one common pitch of n_params rounded up to 64 floats — and
+  // nothing else: a synchronous / asynchronous learner's parameters live in the peer-shared allocation (no window there,
+  // and no carve-out toggling next to NVLink traffic)
+  const long pitch = (long)(c->m - c->params);
+  if (pitch < c->n_params || pitch > c->n_params + 64 || (long)(c->v - c->m) != pitch) return;
   // the gradient right behind them (engine.py): the window covers it too (mode 4)
   c->l2_grad_in_window = false;
   if (mode == 4 && c->grad && reinterpret_cast<const char*>(c->grad) >= hi &&
@@ -2462,7 +2466,9 @@ namespace {
 int train_minibatches(arl_ctx* c, const int* idx, int mb_size, int count, int sync, cudaStream_t st) {
   NvtxRange nvtx_("train minibatches");
   if (count > c->log_cap) ARL_FAIL(c, "more minibatches in one call than loss / grad-norm log slots (4096): read the logs in between");
-  if (count >= 8) l2_carve(c, true);      // (a single full-batch step per rollout, A2C, has nothing to keep resident)
+  // (local update only: the cross-GPU learners' updates are other kernels; a single full-batch step per rollout, A2C, has
+  // nothing to keep resident)
+  if (sync == 0 && count >= 8) l2_carve(c, true);
   // sync: 0 = local clip + update, 1 = synchronous DP step, 2 = asynchronous push/pull
   const bool overlap = sync == 1 && sync_overlap_ok(c);
   if (overlap && sync_overlap_prepare(c)) return 1;

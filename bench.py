@@ -401,8 +401,12 @@ def sync_parity(runner, rank, world):
         out["sync_step_within_tolerance"] = bool((err <= tol).all().item()) and abs(float(norms[0]) - norm) <= 1e-5 * norm
         out["ranks_bit_identical_after_sync_step"] = identical()
     out["world"] = world
-    if not all(v for k, v in out.items() if isinstance(v, bool)):
-        raise SystemExit("sync data-parallel parity check FAILED on rank %d: %s" % (rank, out))
+    ok = torch.tensor([1 if all(v for k, v in out.items() if isinstance(v, bool)) else 0], device="cuda")
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)              # one verdict for all ranks
+    out["passed"] = bool(ok.item())
+    if not out["passed"]:
+        # reported in the JSON line (`parity.passed` false) and as a non-zero exit code after the line is printed
+        print("sync data-parallel parity check FAILED on rank %d: %s" % (rank, out), file=sys.stderr)
     return out
 
 
@@ -610,6 +614,8 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if parity is not None and parity.get("passed") is False:
+        raise SystemExit(3)
 
 
 # =============================================================================================
