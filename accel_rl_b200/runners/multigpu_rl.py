@@ -141,6 +141,22 @@ class _SyncComm(object):
         if self.n_runners > 1:
             dist.barrier()
 
+    def check_replicas(self):
+        """synchronous learners hold bit-identical parameter replicas by construction (the FC slices are published by their
+        owners, the small tensors are updated from identically ordered sums): compared at every log point through a 64-bit
+        checksum per rank — a mismatch means a lost update and must not train on silently"""
+        if self.n_runners == 1:
+            return
+        p = self.policy.engine.params
+        # (position-weighted so that swapped values do not cancel; int64 arithmetic wraps, which is fine for a checksum)
+        words = p.view(torch.int32).to(torch.int64)
+        weights = torch.arange(1, p.numel() + 1, device=p.device, dtype=torch.int64)
+        checksum = int((words * weights).sum().item())
+        sums = [None] * self.n_runners
+        dist.all_gather_object(sums, checksum)
+        if len(set(sums)) != 1:
+            raise RuntimeError("synchronous learners hold different parameters (checksums per rank: %s)" % sums)
+
     @property
     def parallelism_tag(self):
         return "synchronous"
@@ -151,6 +167,8 @@ class _OnlineLog(object):
 
     def store_diagnostics(self, itr, samples_data, opt_data, traj_infos, opt_infos):
         if self.n_runners > 1 and (itr + 1) % self._log_interval_itrs == 0:
+            if hasattr(self, "check_replicas"):
+                self.check_replicas()
             gathered = [None] * self.n_runners
             dist.all_gather_object(gathered, [dict(t) for t in self._pending_trajs + list(traj_infos)])
             self._pending_trajs = []
@@ -179,6 +197,8 @@ class _EvalLog(object):
             super().store_diagnostics(itr, samples_data, opt_data, traj_infos, opt_infos)
 
     def log_diagnostics(self, itr, eval_traj_infos, eval_time):
+        if hasattr(self, "check_replicas"):
+            self.check_replicas()
         if self.rank == 0:
             super().log_diagnostics(itr, eval_traj_infos, eval_time)
         if self.n_runners > 1:

@@ -73,9 +73,18 @@ def _worker(rank, world, port, out):
         agent_infos = dict(prob=np.full((4, 4), 0.25, np.float32))
     r.policy.distribution = __import__("accel_rl_b200.distributions", fromlist=["Categorical"]).Categorical(4)
     r._log_entropy = False
-    r.store_diagnostics(0, S(), None, traj, dict(GradNorm=[1.0]))
-    out[rank] = dict(seed=r.seed, n_itr=n_itr, sample_size=r._sample_size, params=eng.params.numpy().copy(),
-                     handles=[h[0] for h in eng.handles], aff=r.affinities, calls=eng.calls,
+    r.store_diagnostics(0, S(), None, traj, dict(GradNorm=[1.0]))          # (runs check_replicas: identical here)
+    params_after_init = eng.params.numpy().copy()
+    # the replica guard: one ulp of difference on one rank must stop the run on every rank
+    if rank == 1:
+        eng.params[3] = torch.nextafter(eng.params[3], torch.tensor(10.0))
+    try:
+        r.check_replicas()
+        mismatch = False
+    except RuntimeError:
+        mismatch = True
+    out[rank] = dict(seed=r.seed, n_itr=n_itr, sample_size=r._sample_size, params=params_after_init,
+                     handles=[h[0] for h in eng.handles], aff=r.affinities, calls=eng.calls, mismatch=mismatch,
                      traj_lengths=sorted(t["Length"] for t in r._traj_infos))
     dist.destroy_process_group()
 
@@ -101,6 +110,7 @@ def test_sync_runner_host_logic_two_ranks():
     assert r0["aff"] == dict(gpu=0) and r1["aff"] == dict(gpu=1)
     assert ("comm_init", 1, 2) in r1["calls"]
     assert r0["traj_lengths"] == r1["traj_lengths"] == [10, 11]
+    assert r0["mismatch"] and r1["mismatch"]                           # replica checksum guard (runners/multigpu_rl.py)
 
 
 def test_oracle_virtual_ranks_average_equals_concatenated_batch():
