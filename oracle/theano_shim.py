@@ -109,6 +109,43 @@ def install(session):
     return saved
 
 
+def install_eager_tensor(extra_stubs=()):
+    """For reference code that only BUILDS elementwise expressions (the loss terms of algos/pg/{ppo,a2c,aac_base}.py,
+    distributions/categorical.py:*_sym, algos/pg/util.py:valids_mean): `theano.tensor` as eager float32 numpy.  Symbolic
+    inputs are numpy arrays, so every `*_sym` function returns the VALUE of its expression.  `extra_stubs`: module names
+    that the loaded files import but never use on these paths (registered as empty modules with a permissive base class).
+    Returns the previous sys.modules entries for restore()."""
+    names = ["theano", "theano.tensor"] + list(extra_stubs)
+    saved = {n: sys.modules.get(n) for n in names}
+    th = types.ModuleType("theano")
+    tt = types.ModuleType("theano.tensor")
+    f32 = lambda x: np.asarray(x, dtype=np.float32) if np.asarray(x).dtype.kind == "f" else np.asarray(x)
+    tt.clip = lambda x, lo, hi: np.clip(f32(x), np.float32(lo), np.float32(hi))
+    tt.minimum = lambda a, b: np.minimum(f32(a), f32(b))
+    tt.maximum = lambda a, b: np.maximum(f32(a), f32(b))
+    tt.mean = lambda x, axis=None: np.mean(f32(x), axis=axis, dtype=np.float32)
+    tt.sum = lambda x, axis=None: np.sum(f32(x), axis=axis, dtype=np.float32 if np.asarray(x).dtype.kind == "f" else None)
+    tt.log = lambda x: np.log(f32(x))
+    tt.exp = lambda x: np.exp(f32(x))
+    tt.sqr = lambda x: f32(x) * f32(x)
+    tt.arange = np.arange
+    tt.shape = lambda x: np.asarray(x).shape
+    tt.cast = lambda x, dt: np.asarray(x).astype(dt)
+    th.tensor = tt
+    th.config = types.SimpleNamespace(floatX="float32")
+    sys.modules["theano"], sys.modules["theano.tensor"] = th, tt
+    for n in extra_stubs:
+        m = types.ModuleType(n)
+        m.__getattr__ = lambda item, _n=n: type(item, (object,), {"__init__": lambda self, *a, **k: None})
+        sys.modules[n] = m
+    for n in extra_stubs:                       # wire parents -> children where both are stubs
+        if "." in n:
+            parent, child = n.rsplit(".", 1)
+            if parent in sys.modules:
+                setattr(sys.modules[parent], child, sys.modules[n])
+    return saved
+
+
 def restore(saved):
     for n, m in saved.items():
         if m is None:
@@ -117,4 +154,4 @@ def restore(saved):
             sys.modules[n] = m
 
 
-__all__ = ["Shared", "Session", "install", "restore", "OrderedDict"]
+__all__ = ["Shared", "Session", "install", "install_eager_tensor", "restore", "OrderedDict"]

@@ -166,3 +166,35 @@ def test_theano_shim_update_semantics():
         sess.step(fn, np.array([0.5, 1.0], np.float32), p)
     assert len(sess.vars) == 1 and np.array_equal(sess.vars[0].value, [1.5, 3.0])
     assert np.array_equal(p.value, np.array([1.0 - 0.5 - 1.0 - 1.5, 2.0 - 1.0 - 2.0 - 3.0], np.float32))
+
+
+def test_loss_terms_vs_the_reference_expressions(golden_dir):
+    """tests/golden/loss_terms.npz holds the VALUES of the reference's own loss expressions — `pi_loss` of algos/pg/ppo.py
+    and a2c.py, the value / entropy terms and pi_kl / v_kl of aac_base.py:60-70, categorical.py's *_sym functions and
+    valids_mean — executed on arrays under the eager theano.tensor stand-in (tests/golden/make_golden_losses.py).  The oracle's
+    loss terms (oracle/net.py:losses), which the CUDA loss kernel is tested against, must reproduce them: PPO with the clip
+    range scaled by lr_mult, exact ties of the two surrogates, A2C, with and without the validity mask."""
+    import torch
+    from oracle import net as onet
+    from accel_rl_b200.distributions.categorical import Categorical
+    g = np.load(os.path.join(golden_dir, "loss_terms.npz"))
+    t = lambda k: torch.tensor(g[k])
+    for tag in g["cases"]:
+        algo, v, lr = str(tag).split("_")
+        use_valids, lr_mult = v == "v1", float(lr[2:])
+        valids = t("valids") if use_valids else None
+        pl, vl, el = onet.losses(t("new_prob"), t("new_value"), t("act"), t("adv"), t("ret"), t("old_prob"), algo,
+                                 clip_param=0.2, lr_mult=lr_mult, v_coeff=1.0 if algo == "ppo" else 0.25, ent_coeff=0.01,
+                                 valids=valids)
+        want = g[str(tag)]
+        np.testing.assert_allclose([float(pl), float(vl), float(el)], want[:3], rtol=2e-6, atol=1e-8, err_msg=str(tag))
+        # pi_kl / v_kl (aac_base.py:68-70): the host diagnostic's formula (algos/pg/aac_base.py:constraint_values)
+        kl = Categorical(6).kl(dict(prob=g["old_prob"]), dict(prob=g["new_prob"]))
+        dv = (g["new_value"] - g["old_value"]) ** 2
+        if use_valids:
+            w = g["valids"].astype(np.float32)
+            got = [float((kl * w).sum() / w.sum()), float((dv * w).sum() / w.sum())]
+        else:
+            got = [float(kl.mean()), float(dv.mean())]
+        np.testing.assert_allclose(got, want[3:], rtol=2e-6, err_msg=str(tag))
+    assert {str(c).split("_")[0] for c in g["cases"]} == {"ppo", "a2c"}
