@@ -198,3 +198,26 @@ def test_loss_terms_vs_the_reference_expressions(golden_dir):
             got = [float(kl.mean()), float(dv.mean())]
         np.testing.assert_allclose(got, want[3:], rtol=2e-6, err_msg=str(tag))
     assert {str(c).split("_")[0] for c in g["cases"]} == {"ppo", "a2c"}
+
+
+def test_dense_initialiser_vs_the_reference_normc_init(golden_dir):
+    """tests/golden/norm_c_init.npz: outputs of the reference's NormCInit.sample (policies/layers.py:9-19) drawn from the
+    global numpy stream in the network builder's order (hidden layer, pi head with std 0.01, v head).  The product's
+    initial parameter vector (AtariCnnPolicy._init_param_values) and the oracle's (oracle/net.py:init_params) draw the same
+    numbers."""
+    from accel_rl_b200.policies.pg.atari_cnn_policy import AtariCnnPolicy
+    from oracle import net as onet
+    g = np.load(os.path.join(golden_dir, "norm_c_init.npz"))
+    want = np.concatenate([g["hidden"].ravel(), np.zeros(32, np.float32), g["pi"].ravel(), np.zeros(6, np.float32),
+                           g["v"].ravel(), np.zeros(1, np.float32)])
+    pol = object.__new__(AtariCnnPolicy)
+    pol._conv_filters, pol._hidden_sizes = [], [32]
+    pol._shapes = [(96, 32), (32,), (32, 6), (6,), (32, 1), (1,)]
+    np.random.seed(31)
+    got = pol._init_param_values()
+    assert got.dtype == np.float32 and np.array_equal(got, want)
+    # the oracle's initialiser on a geometry with the same dense shapes: one 1x1 conv (6 channels) over a 4x4 image
+    spec = dict(conv_filters=[6], conv_filter_sizes=[1], conv_strides=[1], conv_pads=[0], hidden_sizes=[32])
+    flat = onet.init_params(spec, (3, 4, 4), 6, np.random.RandomState(0), np.random.RandomState(31))
+    n_conv = 6 * 3 + 6
+    assert np.array_equal(flat[n_conv:], want)
